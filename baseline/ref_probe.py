@@ -34,12 +34,8 @@ else:
 import numba  # noqa: E402
 import numba.cuda  # noqa: E402
 
-if os.environ.get("NUMBA_ENABLE_CUDASIM") == "1":
-    # The reference calls numba.cuda.local.array(...) through the `numba`
-    # global (gvom.py:734,1125,1174-1176,1464); the simulator only swaps globals
-    # that ARE the cuda module, so that spelling has no `local` under CUDASIM.
-    from numba.cuda.simulator.kernelapi import FakeCUDALocal
-    numba.cuda.local = FakeCUDALocal()
+sys.path.insert(0, HERE)
+import ref_shims  # noqa: E402,F401  (external shims, see baseline/ref_shims.py)
 
 import gvom  # noqa: E402
 
