@@ -1,0 +1,691 @@
+// gvom_api.cu -- C-ABI (include/gvom_b200.h) and host orchestration of the
+// G-VOM voxel-mapping path on B200.  Replaces the host side of the reference
+// class (scripts/gvom.py:21-442, 1069-1119): ring buffer of per-scan maps,
+// launch sequencing, state carried between combine_maps() calls.
+//
+// Differences from the reference's host code that matter for speed, not results:
+//   * no allocation after gvom_create(): every slot / grid lives in one caller
+//     provided workspace (the reference cudaMallocs >= 7 arrays per scan)
+//   * no host round trip inside Process_pointcloud (gvom.py:172 blocks on the
+//     cell count); counts stay on the device
+//   * 4 launches per scan and 4 per combine instead of ~15 and ~3B+30
+//   * one stream per handle orders slot overwrites against combine reads, which
+//     the reference gets from allocating fresh arrays under Python semaphores.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gvom_b200.h"
+#include "gvom_kernels.cuh"
+
+using namespace gvom;
+
+static thread_local std::string g_err;
+const char* gvom_last_error(void) { return g_err.c_str(); }
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(GVOM_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+namespace {
+
+struct Slot {
+    int* index_map = nullptr;     // [V]
+    int* hit = nullptr;           // [cap]
+    int* total = nullptr;         // [cap]
+    double* metrics = nullptr;    // [cap,10]
+    float* minh = nullptr;        // [cap]
+    int* cell_voxel = nullptr;    // [cap]
+    int* counter = nullptr;       // device cell count
+    double origin[3] = {0, 0, 0};
+    bool valid = false;
+};
+
+struct Combined {
+    int* index_map = nullptr;     // [V]
+    int* hit = nullptr;           // [ccap]
+    int* total = nullptr;
+    float* minh = nullptr;
+    float* metrics = nullptr;     // [ccap,10]
+    float* eig = nullptr;         // [ccap,3]
+    int* cell_voxel = nullptr;
+    int* counter = nullptr;
+    double origin[3] = {0, 0, 0};
+    bool valid = false;
+    int64_t cells = 0;
+};
+
+struct Carver {                    // sub-allocates a workspace block, 256-byte aligned
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+enum { EV_START = 0, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER, EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS, EV_D2H, EV_COUNT };
+
+}  // namespace
+
+struct GvomHandle {
+    GvomParams p;
+    DevParams dp;
+    int device = 0;
+    int64_t max_points = 0, cap = 0, ccap = 0, V = 0;
+    int S2 = 0;
+    // device
+    int *hit_grid = nullptr, *total_grid = nullptr;
+    double* acc = nullptr;
+    char* stage_dev = nullptr;           // input cloud staging [max_points * 32 B]
+    std::vector<Slot> slots;
+    Combined comb[2];
+    int cur = 0;                          // comb[cur] = last combined map (if valid)
+    double* maps = nullptr;               // height, inferred, rough, xs, ys, guessed  [6][S*S]
+    int* imaps = nullptr;                 // pos, neg, vis [3][S*S]
+    float* debug_dev = nullptr;           // [max(ccap*8, S*S*10)]
+    int* flags = nullptr;
+    // multi-GPU scratch
+    double* cacc = nullptr;               // [ccap,10] raw-moment scratch of the multi-GPU combine
+    // pinned host
+    char* stage_host = nullptr;           // [max_points * 32 B]
+    double* out_rough_host = nullptr;     // [S*S]
+    int* out_i_host = nullptr;            // [3*S*S]
+    int* counters_host = nullptr;         // [8]
+    // state
+    int buffer_index = 0, last_buffer_index = 0;
+    double ego[3] = {0, 0, 0};
+    bool have_maps = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_stage = nullptr;       // completion of the last H2D that read stage_host
+    bool stage_busy = false;
+    cudaEvent_t ev[EV_COUNT];
+    bool profiling = false;
+    bool prof_process = false, prof_combine = false;
+    int sm_count = 148;
+    GvomStats stats{};
+    std::mutex mu;
+};
+
+namespace {
+
+size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
+    const GvomParams& p = h->p;
+    const size_t V = (size_t)h->V, cap = (size_t)h->cap, ccap = (size_t)h->ccap, S2 = (size_t)h->S2;
+    Carver d(dev);
+    h->hit_grid = d.take<int>(V);
+    h->total_grid = d.take<int>(V);
+    h->acc = d.take<double>(cap * ACC);
+    h->stage_dev = d.take<char>((size_t)h->max_points * 32);
+    h->slots.resize(p.buffer_size);
+    for (auto& s : h->slots) {
+        s.index_map = d.take<int>(V);
+        s.hit = d.take<int>(cap);
+        s.total = d.take<int>(cap);
+        s.metrics = d.take<double>(cap * 10);
+        s.minh = d.take<float>(cap);
+        s.cell_voxel = d.take<int>(cap);
+        s.counter = d.take<int>(4);
+    }
+    for (auto& c : h->comb) {
+        c.index_map = d.take<int>(V);
+        c.hit = d.take<int>(ccap);
+        c.total = d.take<int>(ccap);
+        c.minh = d.take<float>(ccap);
+        c.metrics = d.take<float>(ccap * 10);
+        c.eig = d.take<float>(ccap * 3);
+        c.cell_voxel = d.take<int>(ccap);
+        c.counter = d.take<int>(4);
+    }
+    h->maps = d.take<double>(6 * S2);
+    h->imaps = d.take<int>(3 * S2);
+    h->debug_dev = d.take<float>(std::max(ccap * 8, S2 * 10));
+    h->flags = d.take<int>(8);
+    h->cacc = d.take<double>(ccap * 10);
+    Carver c(host);
+    h->stage_host = c.take<char>((size_t)h->max_points * 32);
+    h->out_rough_host = c.take<double>(S2);
+    h->out_i_host = c.take<int>(3 * S2);
+    h->counters_host = c.take<int>(8);
+    *host_bytes = c.off + 256;
+    return d.off + 256;
+}
+
+int check_params(const GvomParams* p, int64_t max_points) {
+    if (!p) return fail(GVOM_EINVAL, "params is NULL");
+    if (!(p->xy_resolution > 0) || !(p->z_resolution > 0)) return fail(GVOM_EINVAL, "resolutions must be > 0");
+    if (p->xy_size < 1 || p->z_size < 1) return fail(GVOM_EINVAL, "grid sizes must be >= 1");
+    if (p->buffer_size < 1 || p->buffer_size > MAX_SLOTS) return fail(GVOM_EINVAL, "buffer_size must be in [1,64]");
+    if (p->xy_eigen_dist < 0 || p->z_eigen_dist < 0) return fail(GVOM_EINVAL, "eigen distances must be >= 0");
+    const double V = (double)p->xy_size * p->xy_size * p->z_size;
+    if (V >= 2147483647.0) return fail(GVOM_EINVAL, "grid has >= 2^31 voxels");
+    if (max_points < 1 || max_points > (1 << 30)) return fail(GVOM_EINVAL, "max_points out of range");
+    return GVOM_OK;
+}
+
+void fill_sizes(GvomHandle* h, const GvomParams* p, int64_t max_points, int64_t max_cells) {
+    h->p = *p;
+    h->V = (int64_t)p->xy_size * p->xy_size * p->z_size;
+    h->S2 = p->xy_size * p->xy_size;
+    h->max_points = max_points;
+    h->cap = std::min<int64_t>(max_points, h->V);
+    int64_t dflt = std::min<int64_t>(h->V, 4 * max_points * ((int64_t)p->buffer_size + 1));
+    h->ccap = max_cells > 0 ? std::min<int64_t>(max_cells, h->V) : dflt;
+    DevParams& d = h->dp;
+    d.xy_res = p->xy_resolution; d.z_res = p->z_resolution;
+    d.min_d2 = p->min_distance * p->min_distance;
+    d.pos_thr = p->positive_obstacle_threshold; d.neg_thr = p->negative_obstacle_threshold;
+    d.slope_thr = p->slope_obsacle_threshold; d.robot_height = p->robot_height;
+    d.r2 = p->robot_radius * p->robot_radius; d.ground_to_lidar = p->ground_to_lidar_height;
+    d.S = p->xy_size; d.Z = p->z_size; d.rx = p->xy_eigen_dist; d.rz = p->z_eigen_dist;
+    d.V = h->V;
+}
+
+inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+bool is_pinned_or_device(const void* p, bool* is_device) {
+    cudaPointerAttributes a;
+    *is_device = false;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) { *is_device = true; return true; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+void rec(GvomHandle* h, int e, cudaStream_t st) {
+    if (h->profiling) cudaEventRecord(h->ev[e], st);
+}
+
+// Build the ordered source list of a combine: valid ring slots 0..B-1, then the
+// previous combined map (gvom.py:242-257).  `org` = combined origin (voxels).
+void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs* A) {
+    A->n = 0;
+    for (auto& s : h->slots) {
+        if (!s.valid) continue;
+        SlotRef& r = A->s[A->n++];
+        r.map = s.index_map; r.metrics = s.metrics; r.hit = s.hit; r.total = s.total; r.minh = s.minh;
+        r.dx = (int)(org[0] - s.origin[0]); r.dy = (int)(org[1] - s.origin[1]); r.dz = (int)(org[2] - s.origin[2]);
+        r.is_prev = 0;
+    }
+    Combined& pc = h->comb[h->cur];
+    if (with_prev && pc.valid) {
+        SlotRef& r = A->s[A->n++];
+        r.map = pc.index_map; r.metrics = pc.metrics; r.hit = pc.hit; r.total = pc.total; r.minh = pc.minh;
+        r.dx = (int)(org[0] - pc.origin[0]); r.dy = (int)(org[1] - pc.origin[1]); r.dz = (int)(org[2] - pc.origin[2]);
+        r.is_prev = 1;
+    }
+}
+
+// 2-D stage + outputs, shared by the single- and multi-GPU combine.
+int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* positive, int32_t* negative,
+                        double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st) {
+    const int S2 = h->S2;
+    double* height = h->maps; double* inferred = h->maps + S2; double* rough = h->maps + 2 * (size_t)S2;
+    double* xs = h->maps + 3 * (size_t)S2; double* ys = h->maps + 4 * (size_t)S2; double* guessed = h->maps + 5 * (size_t)S2;
+    int* pos = h->imaps; int* neg = h->imaps + S2; int* vis = h->imaps + 2 * (size_t)S2;
+    k_column_maps<<<blocks_for(S2, 256), 256, 0, st>>>(c.index_map, c.minh, c.origin[0], c.origin[1], c.origin[2],
+                                                       h->ego[0], h->ego[1], h->ego[2], h->dp, height, inferred);
+    k_surface_maps<<<blocks_for(S2, 128), 128, 0, st>>>(c.index_map, c.hit, c.total, height, inferred, c.origin[2],
+                                                        h->dp, rough, xs, ys, guessed, pos, neg, vis);
+    h->stats.kernel_launches += 2;
+    rec(h, EV_MAPS, st);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h->counters_host, c.counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+    const size_t bi = (size_t)S2 * sizeof(int), bd = (size_t)S2 * sizeof(double);
+    if (out_mem == GVOM_DEVICE) {
+        if (positive) CUDA_TRY(cudaMemcpyAsync(positive, pos, bi, cudaMemcpyDeviceToDevice, st));
+        if (negative) CUDA_TRY(cudaMemcpyAsync(negative, neg, bi, cudaMemcpyDeviceToDevice, st));
+        if (visibility) CUDA_TRY(cudaMemcpyAsync(visibility, vis, bi, cudaMemcpyDeviceToDevice, st));
+        if (roughness) CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToDevice, st));
+        rec(h, EV_D2H, st);
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        bool dev = false;
+        const bool direct = positive && negative && visibility && roughness && is_pinned_or_device(positive, &dev) &&
+                            is_pinned_or_device(negative, &dev) && is_pinned_or_device(visibility, &dev) &&
+                            is_pinned_or_device(roughness, &dev);
+        if (direct) {                      // caller's buffers are pinned: DMA straight into them
+            CUDA_TRY(cudaMemcpyAsync(positive, pos, bi, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(negative, neg, bi, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(visibility, vis, bi, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToHost, st));
+            rec(h, EV_D2H, st);
+            CUDA_TRY(cudaStreamSynchronize(st));
+        } else {                           // pageable: one DMA per dtype into pinned staging, then memcpy
+            CUDA_TRY(cudaMemcpyAsync(h->out_i_host, h->imaps, 3 * bi, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h->out_rough_host, rough, bd, cudaMemcpyDeviceToHost, st));
+            rec(h, EV_D2H, st);
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (positive) memcpy(positive, h->out_i_host, bi);
+            if (negative) memcpy(negative, h->out_i_host + S2, bi);
+            if (visibility) memcpy(visibility, h->out_i_host + 2 * (size_t)S2, bi);
+            if (roughness) memcpy(roughness, h->out_rough_host, bd);
+        }
+    }
+    c.cells = std::min<int64_t>(h->counters_host[0], h->ccap);
+    if (h->counters_host[0] > h->ccap)
+        return fail(GVOM_ECAPACITY, "combined map has more occupied cells than max_combined_cells");
+    h->stats.combined_cells = c.cells;
+    h->have_maps = true;
+    if (origin) {                          // gvom.py:385-388
+        origin[0] = c.origin[0] * h->p.xy_resolution;
+        origin[1] = c.origin[1] * h->p.xy_resolution;
+        origin[2] = c.origin[2] * h->p.z_resolution;
+    }
+    return GVOM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gvom_workspace_size(const GvomParams* p, int64_t max_points, int64_t max_combined_cells,
+                        size_t* device_bytes, size_t* host_bytes) {
+    if (int e = check_params(p, max_points)) return e;
+    GvomHandle tmp;
+    fill_sizes(&tmp, p, max_points, max_combined_cells);
+    size_t hb = 0;
+    const size_t db = carve(&tmp, nullptr, nullptr, &hb);
+    if (device_bytes) *device_bytes = db;
+    if (host_bytes) *host_bytes = hb;
+    return GVOM_OK;
+}
+
+int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_cells, int device,
+                void* device_ws, size_t device_bytes, void* host_ws, size_t host_bytes, GvomHandle** out) {
+    if (int e = check_params(p, max_points)) return e;
+    if (!out || !device_ws || !host_ws) return fail(GVOM_EINVAL, "NULL workspace or handle pointer");
+    CUDA_TRY(cudaSetDevice(device));
+    GvomHandle* h = new GvomHandle();
+    h->device = device;
+    fill_sizes(h, p, max_points, max_combined_cells);
+    size_t hb = 0;
+    const size_t db = carve(h, device_ws, host_ws, &hb);
+    if (db > device_bytes || hb > host_bytes) {
+        delete h;
+        return fail(GVOM_EINVAL, "workspace smaller than gvom_workspace_size() asked for");
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming);
+    for (int i = 0; i < EV_COUNT && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    int sms = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (sms > 0) h->sm_count = sms;
+    // dense grids are kept zero between scans (k_build_index re-zeroes what it reads)
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->hit_grid, 0, sizeof(int) * (size_t)h->V, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->total_grid, 0, sizeof(int) * (size_t)h->V, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->flags, 0, sizeof(int) * 8, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(GVOM_ECUDA, std::string("gvom_create: ") + cudaGetErrorString(e));
+    }
+    *out = h;
+    return GVOM_OK;
+}
+
+int gvom_destroy(GvomHandle* h) {
+    if (!h) return GVOM_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(h->ev[i]);
+    cudaEventDestroy(h->ev_stage);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return GVOM_OK;
+}
+
+int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_t stride, int32_t dtype,
+                            int32_t mem, const double ego[3], const double* T, void* stream) {
+    if (!h || !ego) return fail(GVOM_EINVAL, "NULL handle or ego");
+    if (n < 0 || n > h->max_points) return fail(GVOM_ECAPACITY, "point count exceeds max_points");
+    if (stride < 3 || stride > 4) return fail(GVOM_EINVAL, "stride must be 3 or 4 elements");
+    if (dtype != GVOM_F32 && dtype != GVOM_F64) return fail(GVOM_EINVAL, "dtype must be GVOM_F32 or GVOM_F64");
+    if (n > 0 && !points) return fail(GVOM_EINVAL, "NULL points");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const GvomParams& p = h->p;
+
+    // gvom.py:110-112, 138-141
+    Frame fr;
+    for (int k = 0; k < 3; ++k) { h->ego[k] = ego[k]; fr.ego[k] = ego[k]; }
+    fr.origin[0] = std::floor(ego[0] / p.xy_resolution - p.xy_size / 2.0);
+    fr.origin[1] = std::floor(ego[1] / p.xy_resolution - p.xy_size / 2.0);
+    fr.origin[2] = std::floor(ego[2] / p.z_resolution - p.z_size / 2.0);
+    for (int k = 0; k < 3; ++k)
+        if (!(std::fabs(fr.origin[k]) < 1.0e9)) return fail(GVOM_EINVAL, "ego position out of range (|ego/res| >= 1e9)");
+    fr.start[0] = (float)(ego[0] / p.xy_resolution);
+    fr.start[1] = (float)(ego[1] / p.xy_resolution);
+    fr.start[2] = (float)(ego[2] / p.z_resolution);
+    Xform tf;
+    tf.enabled = T ? 1 : 0;
+    for (int k = 0; k < 12; ++k) tf.m[k] = T ? T[k] : 0.0;
+
+    rec(h, EV_START, st);
+    // ---- input staging
+    const size_t esz = dtype == GVOM_F32 ? 4 : 8;
+    const size_t bytes = (size_t)n * stride * esz;
+    const void* src = points;
+    if (n > 0) {
+        if (mem == GVOM_DEVICE) {
+            if (stride == 4 && ((uintptr_t)points & 15)) {   // vector loads need 16-byte alignment
+                CUDA_TRY(cudaMemcpyAsync(h->stage_dev, points, bytes, cudaMemcpyDeviceToDevice, st));
+                src = h->stage_dev;
+            }
+        } else {
+            bool dev = false;
+            if (is_pinned_or_device(points, &dev)) {
+                CUDA_TRY(cudaMemcpyAsync(h->stage_dev, points, bytes, cudaMemcpyDefault, st));
+                CUDA_TRY(cudaEventRecord(h->ev_stage, st));
+                // the caller may reuse its buffer as soon as we return
+                CUDA_TRY(cudaEventSynchronize(h->ev_stage));
+            } else {
+                if (h->stage_busy) CUDA_TRY(cudaEventSynchronize(h->ev_stage));
+                memcpy(h->stage_host, points, bytes);
+                CUDA_TRY(cudaMemcpyAsync(h->stage_dev, h->stage_host, bytes, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaEventRecord(h->ev_stage, st));
+                h->stage_busy = true;
+            }
+            src = h->stage_dev;
+        }
+    }
+    rec(h, EV_H2D, st);
+
+    Slot& s = h->slots[h->buffer_index];
+    const int cap = (int)h->cap;
+    const int nb = blocks_for(n, 256);
+    CUDA_TRY(cudaMemsetAsync(s.counter, 0, sizeof(int), st));
+    if (n > 0) {
+        if (dtype == GVOM_F32)
+            k_voxelize_raycast<float><<<nb, 256, 0, st>>>((const float*)src, stride, (int)n, tf, fr, h->dp, h->hit_grid, h->total_grid);
+        else
+            k_voxelize_raycast<double><<<nb, 256, 0, st>>>((const double*)src, stride, (int)n, tf, fr, h->dp, h->hit_grid, h->total_grid);
+        h->stats.kernel_launches++;
+    }
+    rec(h, EV_RAYCAST, st);
+    k_build_index<<<h->sm_count * 8, 256, 0, st>>>(h->hit_grid, h->total_grid, s.index_map, s.counter, s.hit, s.total,
+                                                  s.cell_voxel, h->acc, s.minh, h->V, cap);
+    h->stats.kernel_launches++;
+    rec(h, EV_INDEX, st);
+    if (n > 0) {
+        if (dtype == GVOM_F32)
+            k_moments<float><<<nb, 256, 0, st>>>((const float*)src, stride, (int)n, tf, fr, h->dp, s.index_map, h->acc, s.minh);
+        else
+            k_moments<double><<<nb, 256, 0, st>>>((const double*)src, stride, (int)n, tf, fr, h->dp, s.index_map, h->acc, s.minh);
+        h->stats.kernel_launches++;
+    }
+    rec(h, EV_MOMENTS, st);
+    k_gather_metrics<<<h->sm_count * 4, 128, 0, st>>>(s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap);
+    h->stats.kernel_launches++;
+    rec(h, EV_GATHER, st);
+    CUDA_TRY(cudaGetLastError());
+    h->prof_process = h->profiling;
+
+    // gvom.py:198-216
+    for (int k = 0; k < 3; ++k) s.origin[k] = fr.origin[k];
+    s.valid = true;
+    h->last_buffer_index = h->buffer_index;
+    h->buffer_index = (h->buffer_index + 1) % p.buffer_size;
+    h->stats.process_calls++;
+    return GVOM_OK;
+}
+
+int gvom_combine_maps(GvomHandle* h, double origin[3], int32_t* positive, int32_t* negative, double* roughness,
+                      int32_t* visibility, int32_t out_mem, void* stream) {
+    if (!h) return fail(GVOM_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    Slot& newest = h->slots[h->last_buffer_index];
+    if (!newest.valid) return GVOM_NO_DATA;                 // gvom.py:225-227
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    rec(h, EV_CSTART, st);
+    MergeArgs A;
+    build_sources(h, newest.origin, true, &A);
+    Combined& c = h->comb[1 - h->cur];
+    for (int k = 0; k < 3; ++k) c.origin[k] = newest.origin[k];   // gvom.py:229
+    CUDA_TRY(cudaMemsetAsync(c.counter, 0, sizeof(int), st));
+    k_merge_codes<<<h->sm_count * 8, 256, 0, st>>>(A, c.index_map, c.counter, c.cell_voxel, h->dp, (int)h->ccap);
+    rec(h, EV_CODES, st);
+    k_merge_cells<<<h->sm_count * 4, 128, 0, st>>>(A, c.counter, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
+                                                  h->dp, (int)h->ccap);
+    rec(h, EV_CELLS, st);
+    h->stats.kernel_launches += 2;
+    h->prof_combine = h->profiling;
+    const int r = run_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st);
+    if (r != GVOM_OK) return r;
+    c.valid = true;                                          // gvom.py:302-308
+    h->cur = 1 - h->cur;
+    h->stats.combine_calls++;
+    return GVOM_OK;
+}
+
+int gvom_combined_cell_count(GvomHandle* h, int64_t* cells) {
+    if (!h || !cells) return fail(GVOM_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!h->comb[h->cur].valid) return GVOM_NO_DATA;
+    *cells = h->comb[h->cur].cells;
+    return GVOM_OK;
+}
+
+int gvom_debug_voxel_map(GvomHandle* h, float* out, int64_t capacity_rows, int64_t* rows) {
+    if (!h || !out) return fail(GVOM_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    Combined& c = h->comb[h->cur];
+    if (!c.valid) return GVOM_NO_DATA;
+    if (capacity_rows < c.cells) return fail(GVOM_ECAPACITY, "output has fewer rows than combined cells");
+    if (c.cells > 0) {
+        k_debug_voxels<<<h->sm_count * 4, 256, 0, h->stream>>>(c.counter, c.cell_voxel, c.hit, c.total, c.eig, c.origin[0],
+                                                              c.origin[1], c.origin[2], h->dp, (int)h->ccap, h->debug_dev);
+        h->stats.kernel_launches++;
+        CUDA_TRY(cudaMemcpyAsync(out, h->debug_dev, sizeof(float) * 8 * (size_t)c.cells, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (rows) *rows = c.cells;
+    return GVOM_OK;
+}
+
+static int debug_height_common(GvomHandle* h, float* out7, float* out3) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    Combined& c = h->comb[h->cur];
+    if (!c.valid || !h->have_maps) return GVOM_NO_DATA;
+    const size_t S2 = (size_t)h->S2;
+    float* d7 = h->debug_dev; float* d3 = h->debug_dev + 7 * S2;
+    k_debug_height<<<blocks_for(h->S2, 256), 256, 0, h->stream>>>(h->maps, h->maps + 2 * S2, h->maps + 3 * S2, h->maps + 4 * S2,
+                                                                h->maps + 5 * S2, c.origin[0], c.origin[1], h->dp,
+                                                                out7 ? d7 : nullptr, out3 ? d3 : nullptr);
+    h->stats.kernel_launches++;
+    if (out7) CUDA_TRY(cudaMemcpyAsync(out7, d7, sizeof(float) * 7 * S2, cudaMemcpyDeviceToHost, h->stream));
+    if (out3) CUDA_TRY(cudaMemcpyAsync(out3, d3, sizeof(float) * 3 * S2, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GVOM_OK;
+}
+
+int gvom_debug_height_map(GvomHandle* h, float* out) {
+    if (!h || !out) return fail(GVOM_EINVAL, "NULL argument");
+    return debug_height_common(h, out, nullptr);
+}
+int gvom_debug_inferred_height_map(GvomHandle* h, float* out) {
+    if (!h || !out) return fail(GVOM_EINVAL, "NULL argument");
+    return debug_height_common(h, nullptr, out);
+}
+
+// ---------------------------------------------------------------- test hooks
+int gvom_last_slot(GvomHandle* h, int32_t* slot) {
+    if (!h || !slot) return fail(GVOM_EINVAL, "NULL argument");
+    *slot = h->last_buffer_index;
+    return GVOM_OK;
+}
+
+int gvom_slot_info(GvomHandle* h, int32_t slot, int32_t* valid, int64_t* cells, double origin[3]) {
+    if (!h || slot < 0 || slot >= h->p.buffer_size) return fail(GVOM_EINVAL, "bad slot");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    Slot& s = h->slots[slot];
+    if (valid) *valid = s.valid ? 1 : 0;
+    if (s.valid) {
+        int cnt = 0;
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaMemcpy(&cnt, s.counter, sizeof(int), cudaMemcpyDeviceToHost));
+        if (cells) *cells = std::min<int64_t>(cnt, h->cap);
+        h->stats.scan_cells = cnt;
+        if (origin) for (int k = 0; k < 3; ++k) origin[k] = s.origin[k];
+        if (cnt > h->cap) return fail(GVOM_ECAPACITY, "scan has more occupied voxels than max_points");
+    } else if (cells) *cells = 0;
+    return GVOM_OK;
+}
+
+int gvom_export_slot(GvomHandle* h, int32_t slot, int32_t* index_map, int32_t* hit, int32_t* total, double* metrics,
+                     float* min_height) {
+    if (!h || slot < 0 || slot >= h->p.buffer_size) return fail(GVOM_EINVAL, "bad slot");
+    int64_t cells = 0; int32_t valid = 0;
+    if (int e = gvom_slot_info(h, slot, &valid, &cells, nullptr)) return e;
+    if (!valid) return GVOM_NO_DATA;
+    std::lock_guard<std::mutex> lock(h->mu);
+    Slot& s = h->slots[slot];
+    if (index_map) CUDA_TRY(cudaMemcpy(index_map, s.index_map, sizeof(int) * (size_t)h->V, cudaMemcpyDeviceToHost));
+    if (hit) CUDA_TRY(cudaMemcpy(hit, s.hit, sizeof(int) * (size_t)cells, cudaMemcpyDeviceToHost));
+    if (total) CUDA_TRY(cudaMemcpy(total, s.total, sizeof(int) * (size_t)cells, cudaMemcpyDeviceToHost));
+    if (metrics) CUDA_TRY(cudaMemcpy(metrics, s.metrics, sizeof(double) * 10 * (size_t)cells, cudaMemcpyDeviceToHost));
+    if (min_height) CUDA_TRY(cudaMemcpy(min_height, s.minh, sizeof(float) * (size_t)cells, cudaMemcpyDeviceToHost));
+    return GVOM_OK;
+}
+
+int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_t* total, float* min_height,
+                         float* metrics, float* eig, double* maps6) {
+    if (!h) return fail(GVOM_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    Combined& c = h->comb[h->cur];
+    if (!c.valid) return GVOM_NO_DATA;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const size_t n = (size_t)c.cells;
+    if (index_map) CUDA_TRY(cudaMemcpy(index_map, c.index_map, sizeof(int) * (size_t)h->V, cudaMemcpyDeviceToHost));
+    if (hit) CUDA_TRY(cudaMemcpy(hit, c.hit, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (total) CUDA_TRY(cudaMemcpy(total, c.total, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (min_height) CUDA_TRY(cudaMemcpy(min_height, c.minh, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (metrics) CUDA_TRY(cudaMemcpy(metrics, c.metrics, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost));
+    if (eig) CUDA_TRY(cudaMemcpy(eig, c.eig, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    if (maps6) CUDA_TRY(cudaMemcpy(maps6, h->maps, sizeof(double) * 6 * (size_t)h->S2, cudaMemcpyDeviceToHost));
+    return GVOM_OK;
+}
+
+int gvom_get_stats(GvomHandle* h, GvomStats* out) {
+    if (!h || !out) return fail(GVOM_EINVAL, "NULL argument");
+    *out = h->stats;
+    return GVOM_OK;
+}
+
+int gvom_set_profiling(GvomHandle* h, int32_t on) {
+    if (!h) return fail(GVOM_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->profiling = on != 0;
+    if (!on) h->prof_process = h->prof_combine = false;
+    return GVOM_OK;
+}
+
+int gvom_stage_times(GvomHandle* h, float ms[16]) {
+    if (!h || !ms) return fail(GVOM_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int i = 0; i < 16; ++i) ms[i] = 0.f;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->prof_process) {
+        const int a[5] = {EV_START, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS};
+        const int b[5] = {EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER};
+        for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], h->ev[a[i]], h->ev[b[i]]));
+    }
+    if (h->prof_combine) {
+        const int a[4] = {EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS};
+        const int b[4] = {EV_CODES, EV_CELLS, EV_MAPS, EV_D2H};
+        for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[5 + i], h->ev[a[i]], h->ev[b[i]]));
+    }
+    return GVOM_OK;
+}
+
+// ------------------------------------------------------------- multi-GPU
+int gvom_newest_origin(GvomHandle* h, double origin[3]) {
+    if (!h || !origin) return fail(GVOM_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    Slot& newest = h->slots[h->last_buffer_index];
+    if (!newest.valid) return GVOM_NO_DATA;
+    for (int k = 0; k < 3; ++k) origin[k] = newest.origin[k];
+    return GVOM_OK;
+}
+
+int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, float* records_dev,
+                         int64_t record_capacity, int32_t* record_count_dev, void* stream) {
+    if (!h || !origin || !code_grid_dev || !records_dev || !record_count_dev) return fail(GVOM_EINVAL, "NULL argument");
+    if (record_capacity < 1 || record_capacity > 2147483647LL) return fail(GVOM_EINVAL, "bad record capacity");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    rec(h, EV_CSTART, st);
+    MergeArgs A;
+    build_sources(h, origin, false, &A);       // a rank without data contributes an empty grid
+    CUDA_TRY(cudaMemsetAsync(record_count_dev, 0, sizeof(int), st));
+    k_partial_codes<<<h->sm_count * 8, 256, 0, st>>>(A, code_grid_dev, record_count_dev, records_dev, h->dp, (int)record_capacity);
+    k_partial_cells<<<h->sm_count * 4, 128, 0, st>>>(A, record_count_dev, records_dev, h->dp, (int)record_capacity);
+    rec(h, EV_CODES, st);
+    h->stats.kernel_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return GVOM_OK;
+}
+
+int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* code_grid_dev, const float* records_dev,
+                        const int32_t* record_counts_dev, int32_t nranks, int64_t record_capacity, double origin_out[3],
+                        int32_t* positive, int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem,
+                        void* stream) {
+    if (!h || !origin || !code_grid_dev || !records_dev || !record_counts_dev) return fail(GVOM_EINVAL, "NULL argument");
+    if (nranks < 1) return fail(GVOM_EINVAL, "nranks must be >= 1");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    Combined& pc = h->comb[h->cur];
+    Combined& c = h->comb[1 - h->cur];
+    for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];
+    SlotRef prev{};
+    const int has_prev = pc.valid ? 1 : 0;
+    if (has_prev) {
+        prev.map = pc.index_map; prev.metrics = pc.metrics; prev.hit = pc.hit; prev.total = pc.total; prev.minh = pc.minh;
+        prev.dx = (int)(origin[0] - pc.origin[0]); prev.dy = (int)(origin[1] - pc.origin[1]); prev.dz = (int)(origin[2] - pc.origin[2]);
+        prev.is_prev = 1;
+    }
+    // the per-scan accumulator block doubles as the per-cell raw-moment scratch when it is big enough
+    double* cacc = h->cacc;
+    CUDA_TRY(cudaMemsetAsync(c.counter, 0, sizeof(int), st));
+    k_finish_codes<<<h->sm_count * 8, 256, 0, st>>>(code_grid_dev, prev, has_prev, c.index_map, c.counter, c.cell_voxel, cacc,
+                                                   c.hit, c.total, c.minh, h->dp, (int)h->ccap);
+    k_scatter_records<<<h->sm_count * 4, 256, 0, st>>>(records_dev, record_counts_dev, nranks, record_capacity, c.index_map,
+                                                      cacc, c.hit, c.total, c.minh);
+    k_finish_cells<<<h->sm_count * 4, 128, 0, st>>>(prev, has_prev, c.counter, c.cell_voxel, cacc, c.hit, c.total, c.minh,
+                                                   c.metrics, c.eig, h->dp, (int)h->ccap);
+    rec(h, EV_CELLS, st);
+    h->stats.kernel_launches += 3;
+    h->prof_combine = h->profiling;
+    const int r = run_maps_and_output(h, c, origin_out, positive, negative, roughness, visibility, out_mem, st);
+    if (r != GVOM_OK) return r;
+    c.valid = true;
+    h->cur = 1 - h->cur;
+    h->stats.combine_calls++;
+    return GVOM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+"""Drop-in `Gvom` class over the B200 C-ABI (include/gvom_b200.h).
+
+Mirrors the public surface of the reference class (scripts/gvom.py:8-442) that
+scripts/gvom_ros.py uses: the 14 positional constructor arguments
+(gvom.py:21-22), Process_pointcloud (gvom.py:105), combine_maps (gvom.py:222)
+and the three make_debug_* exports (gvom.py:395-442), with the reference's
+return types and its "print and return None" error convention.
+
+Python here is only the host shim: argument checking, buffer ownership (torch
+tensors own the device and pinned workspaces) and one ctypes call per method.
+All computation is in hand-written sm_100a CUDA behind the C-ABI; there is no
+Numba, Triton or CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import GVOM_DEVICE, GVOM_F32, GVOM_F64, GVOM_HOST, GVOM_NO_DATA, GvomParams, GvomStats, check
+
+DEFAULT_MAX_POINTS = 1 << 19          # 524,288: two OS1-128 scans
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("gvom_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+class Gvom:
+    """
+    A class to take lidar scans and create a costmap (B200-native build)\n
+    xy_resolution:  x,y resolution in metres of each voxel\n
+    z_resolution:   z resolution in metres of each voxel\n
+    xy_size:        Number of voxels in x,y\n
+    z_size:         Number of voxels in z\n
+    buffer_size:    Number of lidar scans to keep in memory\n
+    min_distance:   Minimum point distance, any points closer than this will be discarded\n
+    Keyword-only extras (not in the reference): max_points (capacity of one scan),
+    device (CUDA ordinal), max_combined_cells, pinned_outputs.
+    """
+
+    def __init__(self, xy_resolution, z_resolution, xy_size, z_size, buffer_size, min_distance,
+                 positive_obstacle_threshold, negative_obstacle_threshold, slope_obsacle_threshold,
+                 robot_height, robot_radius, ground_to_lidar_height, xy_eigen_dist, z_eigen_dist, *,
+                 max_points=DEFAULT_MAX_POINTS, device=None, max_combined_cells=0, pinned_outputs=True):
+        self.xy_resolution, self.z_resolution = xy_resolution, z_resolution
+        self.xy_size, self.z_size, self.buffer_size = int(xy_size), int(z_size), int(buffer_size)
+        self.min_distance = min_distance
+        self.positive_obstacle_threshold = positive_obstacle_threshold
+        self.negative_obstacle_threshold = negative_obstacle_threshold
+        self.slope_obsacle_threshold = slope_obsacle_threshold
+        self.robot_height, self.robot_radius = robot_height, robot_radius
+        self.ground_to_lidar_height = ground_to_lidar_height
+        self.xy_eigen_dist, self.z_eigen_dist = int(xy_eigen_dist), int(z_eigen_dist)
+        self.metrics_count = 10
+        self.voxel_count = self.xy_size * self.xy_size * self.z_size
+        self.max_points = int(max_points)
+        self.pinned_outputs = bool(pinned_outputs)
+        self.ego_position = [0, 0, 0]
+        self._h = None
+
+        self._L = _lib.lib()                     # raises if the CUDA library is missing
+        torch = self._torch = _torch()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._P = GvomParams(float(xy_resolution), float(z_resolution), self.xy_size, self.z_size,
+                             self.buffer_size, 0, float(min_distance), float(positive_obstacle_threshold),
+                             float(negative_obstacle_threshold), float(slope_obsacle_threshold),
+                             float(robot_height), float(robot_radius), float(ground_to_lidar_height),
+                             self.xy_eigen_dist, self.z_eigen_dist)
+        db, hb = C.c_size_t(0), C.c_size_t(0)
+        check(self._L.gvom_workspace_size(C.byref(self._P), self.max_points, int(max_combined_cells),
+                                          C.byref(db), C.byref(hb)), "gvom_workspace_size")
+        # torch owns the memory; raw pointers cross the ABI
+        self._dev_ws = torch.empty(db.value, dtype=torch.uint8, device=f"cuda:{self.device}")
+        self._host_ws = torch.empty(hb.value, dtype=torch.uint8, pin_memory=True)
+        h = C.c_void_p()
+        check(self._L.gvom_create(C.byref(self._P), self.max_points, int(max_combined_cells), self.device,
+                                  self._dev_ws.data_ptr(), db.value, self._host_ws.data_ptr(), hb.value,
+                                  C.byref(h)), "gvom_create")
+        self._h = h
+        self._ego_c = (C.c_double * 3)()
+        self._org_c = (C.c_double * 3)()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gvom_destroy(self._h)
+            self._h = None
+
+    # ------------------------------------------------------------------ scans
+    def _describe(self, pointcloud):
+        """-> (keepalive, pointer, n, stride, dtype code, mem)"""
+        torch = self._torch
+        if isinstance(pointcloud, torch.Tensor):
+            t = pointcloud
+            if t.dim() != 2 or t.shape[1] < 3:
+                raise ValueError("pointcloud must have shape (N, >=3)")
+            if t.dtype not in (torch.float32, torch.float64):
+                t = t.to(torch.float64)
+            if t.shape[1] > 4:
+                t = t[:, :3]
+            t = t.contiguous()
+            mem = GVOM_DEVICE if t.is_cuda else GVOM_HOST
+            if t.is_cuda and t.device.index != self.device:
+                t = t.to(f"cuda:{self.device}")
+            return t, t.data_ptr(), t.shape[0], t.shape[1], GVOM_F32 if t.dtype == torch.float32 else GVOM_F64, mem
+        a = pointcloud if isinstance(pointcloud, np.ndarray) else np.asarray(pointcloud)
+        if a.ndim != 2 or a.shape[1] < 3:
+            raise ValueError("pointcloud must have shape (N, >=3)")
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        if a.shape[1] > 4:
+            a = a[:, :3]
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        return a, a.ctypes.data, a.shape[0], a.shape[1], GVOM_F32 if a.dtype == np.float32 else GVOM_F64, GVOM_HOST
+
+    def Process_pointcloud(self, pointcloud, ego_position, transform=None):
+        """ Imports a pointcloud and processes it into a voxel map then adds the map to the buffer"""
+        keep, ptr, n, stride, dt, mem = self._describe(pointcloud)
+        self.ego_position = ego_position
+        e = self._ego_c
+        e[0], e[1], e[2] = float(ego_position[0]), float(ego_position[1]), float(ego_position[2])
+        if transform is None:
+            tp = None
+        else:
+            T = np.ascontiguousarray(transform, dtype=np.float64)
+            if T.shape != (4, 4):
+                raise ValueError("transform must be 4x4")
+            tp = T.ctypes.data
+        check(self._L.gvom_process_pointcloud(self._h, ptr, n, stride, dt, mem, e, tp, None),
+              "gvom_process_pointcloud")
+        del keep
+
+    process_pointcloud = Process_pointcloud      # spelling used by BASELINE.json
+
+    # ---------------------------------------------------------------- combine
+    def _out_arrays(self):
+        S = self.xy_size
+        if self.pinned_outputs:
+            torch = self._torch
+            ti = torch.empty((3, S, S), dtype=torch.int32, pin_memory=True)
+            tr = torch.empty((S, S), dtype=torch.float64, pin_memory=True)
+            ai, rough = ti.numpy(), tr.numpy()
+            return ai[0], ai[1], rough, ai[2]
+        return (np.empty((S, S), np.int32), np.empty((S, S), np.int32), np.empty((S, S), np.float64),
+                np.empty((S, S), np.int32))
+
+    def combine_maps(self):
+        """ Combines all maps in the buffer and processes into 2D maps """
+        pos, neg, rough, vis = self._out_arrays()
+        rc = check(self._L.gvom_combine_maps(self._h, self._org_c, pos.ctypes.data, neg.ctypes.data,
+                                             rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None),
+                   "gvom_combine_maps")
+        if rc == GVOM_NO_DATA:
+            print("ERROR: No data in buffer")
+            return None
+        origin = np.array([self._org_c[0], self._org_c[1], self._org_c[2]])
+        return (origin, pos, neg, rough, vis)
+
+    # ------------------------------------------------------------------ debug
+    def make_debug_voxel_map(self):
+        n = C.c_int64(0)
+        if self._L.gvom_combined_cell_count(self._h, C.byref(n)) == GVOM_NO_DATA:
+            print("No data")
+            return None
+        out = np.zeros((n.value, 8), np.float32)
+        rows = C.c_int64(0)
+        check(self._L.gvom_debug_voxel_map(self._h, out.ctypes.data, n.value, C.byref(rows)), "gvom_debug_voxel_map")
+        return out
+
+    def make_debug_height_map(self):
+        out = np.zeros((self.xy_size * self.xy_size, 7), np.float32)
+        if check(self._L.gvom_debug_height_map(self._h, out.ctypes.data), "gvom_debug_height_map") == GVOM_NO_DATA:
+            print("No data")
+            return None
+        return out
+
+    def make_debug_inferred_height_map(self):
+        out = np.zeros((self.xy_size * self.xy_size, 3), np.float32)
+        if check(self._L.gvom_debug_inferred_height_map(self._h, out.ctypes.data),
+                 "gvom_debug_inferred_height_map") == GVOM_NO_DATA:
+            print("No data")
+            return None
+        return out
+
+    # ---------------------------------------------------------------- tooling
+    def stats(self):
+        s = GvomStats()
+        check(self._L.gvom_get_stats(self._h, C.byref(s)), "gvom_get_stats")
+        return {k: getattr(s, k) for k, _ in GvomStats._fields_}
+
+    def set_profiling(self, on):
+        check(self._L.gvom_set_profiling(self._h, int(bool(on))), "gvom_set_profiling")
+
+    def stage_times(self):
+        ms = (C.c_float * 16)()
+        check(self._L.gvom_stage_times(self._h, ms), "gvom_stage_times")
+        names = ("h2d", "raycast", "index", "moments", "gather", "merge_codes", "merge_cells", "maps", "d2h")
+        return {k: float(ms[i]) for i, k in enumerate(names)}
+
+    def refview(self):
+        """Host copy of the state under the reference's attribute names (test hook)."""
+        return _RefView(self)
+
+
+class _RefView:
+    """Snapshot of a Gvom's device state named like the reference's attributes
+    (gvom.py:50-70), for the canonical parity dumps in tests/canon.py."""
+
+    def __init__(self, g):
+        L, h = g._L, g._h
+        self._g = g
+        B, V, S = g.buffer_size, g.voxel_count, g.xy_size
+        slot = C.c_int32(0)
+        check(L.gvom_last_slot(h, C.byref(slot)), "gvom_last_slot")
+        self.last_buffer_index = slot.value
+        self.index_buffer, self.hit_count_buffer, self.total_count_buffer = [None] * B, [None] * B, [None] * B
+        self.metrics_buffer, self.min_height_buffer, self.origin_buffer = [None] * B, [None] * B, [None] * B
+        for i in range(B):
+            valid, cells, org = C.c_int32(0), C.c_int64(0), (C.c_double * 3)()
+            check(L.gvom_slot_info(h, i, C.byref(valid), C.byref(cells), org), "gvom_slot_info")
+            if not valid.value:
+                continue
+            n = cells.value
+            idx, hit, tot = np.empty(V, np.int32), np.empty(n, np.int32), np.empty(n, np.int32)
+            met, mnh = np.empty((n, 10), np.float64), np.empty(n, np.float32)
+            check(L.gvom_export_slot(h, i, idx.ctypes.data, hit.ctypes.data, tot.ctypes.data, met.ctypes.data,
+                                     mnh.ctypes.data), "gvom_export_slot")
+            self.index_buffer[i], self.hit_count_buffer[i], self.total_count_buffer[i] = idx, hit, tot
+            self.metrics_buffer[i], self.min_height_buffer[i] = met, mnh
+            self.origin_buffer[i] = np.array(list(org))
+        n = C.c_int64(0)
+        self.combined_index_map = None
+        if L.gvom_combined_cell_count(h, C.byref(n)) != GVOM_NO_DATA:
+            n = n.value
+            self.combined_cell_count_cpu = n
+            self.combined_index_map = np.empty(V, np.int32)
+            self.combined_hit_count, self.combined_total_count = np.empty(n, np.int32), np.empty(n, np.int32)
+            self.combined_min_height = np.empty(n, np.float32)
+            self.combined_metrics, self.voxels_eigenvalues = np.empty((n, 10), np.float32), np.empty((n, 3), np.float32)
+            maps = np.empty((6, S, S), np.float64)
+            check(L.gvom_export_combined(h, self.combined_index_map.ctypes.data, self.combined_hit_count.ctypes.data,
+                                         self.combined_total_count.ctypes.data, self.combined_min_height.ctypes.data,
+                                         self.combined_metrics.ctypes.data, self.voxels_eigenvalues.ctypes.data,
+                                         maps.ctypes.data), "gvom_export_combined")
+            (self.height_map, self.inferred_height_map, self.roughness_map, self.x_slope_map, self.y_slope_map,
+             self.guessed_height_delta) = maps
+
+    def make_debug_voxel_map(self):
+        return self._g.make_debug_voxel_map()
+
+    def make_debug_height_map(self):
+        return self._g.make_debug_height_map()
+
+    def make_debug_inferred_height_map(self):
+        return self._g.make_debug_inferred_height_map()

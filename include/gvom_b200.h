@@ -1,0 +1,157 @@
+/*
+ * gvom_b200.h -- C-ABI of the B200-native G-VOM voxel-mapping path.
+ *
+ * The reference has no FFI seam: its boundary is the Python class `Gvom`
+ * (reference scripts/gvom.py:8-442, used by scripts/gvom_ros.py:44-59,109,115,
+ * 171-185).  This header is the C boundary a replacement binds instead; each
+ * entry point names the reference interface it replaces.  Plain pointers and
+ * sizes only -- no torch / numpy / CUDA types in the signatures (`stream` is a
+ * cudaStream_t passed as void*; NULL = the handle's own stream).
+ *
+ * Conventions: every function returns 0 on success, a positive GVOM_E* code on
+ * error (gvom_last_error() holds the text); gvom_combine_maps* return
+ * GVOM_NO_DATA (-1) when the newest ring-buffer slot is empty (the reference
+ * prints "ERROR: No data in buffer" and returns None, gvom.py:225-227).
+ *
+ * Memory: the library never allocates device or pinned memory itself.  The
+ * caller asks gvom_workspace_size() how much is needed, allocates both blocks
+ * (the Python host side uses torch tensors for ownership) and hands them to
+ * gvom_create(); they must outlive the handle.
+ */
+#ifndef GVOM_B200_H
+#define GVOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVOM_OK 0
+#define GVOM_NO_DATA (-1)
+#define GVOM_EINVAL 1   /* bad argument */
+#define GVOM_ECUDA 2    /* CUDA runtime error */
+#define GVOM_ECAPACITY 3 /* more points / cells than the workspace was sized for */
+
+/* point cloud element types (the reference keeps the caller's dtype on the device,
+ * gvom.py:115, and its arithmetic depends on it) */
+#define GVOM_F32 0
+#define GVOM_F64 1
+/* where a caller buffer lives */
+#define GVOM_HOST 0
+#define GVOM_DEVICE 1
+
+/* Constructor parameters: replaces Gvom.__init__'s 14 positional arguments
+ * (gvom.py:21-22), same order and meaning. */
+typedef struct GvomParams {
+    double xy_resolution;
+    double z_resolution;
+    int32_t xy_size;
+    int32_t z_size;
+    int32_t buffer_size;
+    int32_t _pad0;
+    double min_distance;
+    double positive_obstacle_threshold;
+    double negative_obstacle_threshold;
+    double slope_obsacle_threshold;      /* sic: the reference's spelling */
+    double robot_height;
+    double robot_radius;
+    double ground_to_lidar_height;
+    int32_t xy_eigen_dist;
+    int32_t z_eigen_dist;
+} GvomParams;
+
+/* Work counters of the last calls (device-side counts are read back lazily). */
+typedef struct GvomStats {
+    int64_t scan_cells;          /* occupied voxels of the last processed scan */
+    int64_t combined_cells;      /* cells of the last combined map */
+    int64_t kernel_launches;     /* kernels launched by this handle since creation */
+    int64_t process_calls;
+    int64_t combine_calls;
+} GvomStats;
+
+typedef struct GvomHandle GvomHandle;
+
+const char* gvom_last_error(void);
+
+/* Bytes of device and pinned-host workspace a handle needs. */
+int gvom_workspace_size(const GvomParams* p, int64_t max_points, int64_t max_combined_cells,
+                        size_t* device_bytes, size_t* host_bytes);
+
+/* Replaces Gvom.__init__ (gvom.py:21-101).  max_combined_cells <= 0 selects the
+ * default min(V, 4*max_points*(buffer_size+1)). */
+int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_cells, int device,
+                void* device_ws, size_t device_bytes, void* host_ws, size_t host_bytes,
+                GvomHandle** out);
+int gvom_destroy(GvomHandle* h);
+
+/* Replaces Gvom.Process_pointcloud (gvom.py:105-220): transform (optional 4x4
+ * row-major float64, NULL = none), voxelise, ray-cast, per-voxel moments, and
+ * store the per-scan map in the next ring-buffer slot.
+ * points: n rows of `stride` elements (>= 3; x,y,z first) of `dtype`, in host
+ * (pageable or pinned) or device memory.  Asynchronous on `stream` except for
+ * the staging copy of pageable host input. */
+int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_t stride,
+                            int32_t dtype, int32_t mem, const double ego[3],
+                            const double* transform16, void* stream);
+
+/* Replaces Gvom.combine_maps (gvom.py:222-393).  Outputs are [x,y]-indexed
+ * (row-major, x major) xy_size*xy_size arrays: positive / negative obstacle and
+ * visibility int32, roughness float64; origin is the combined map's world origin.
+ * Output pointers may be host (pageable or pinned) or device memory (out_mem).
+ * Returns after the outputs are complete (synchronises `stream`). */
+int gvom_combine_maps(GvomHandle* h, double origin[3], int32_t* positive, int32_t* negative,
+                      double* roughness, int32_t* visibility, int32_t out_mem, void* stream);
+
+/* Replaces make_debug_voxel_map / make_debug_height_map /
+ * make_debug_inferred_height_map (gvom.py:395-442).  GVOM_NO_DATA before the
+ * first combine.  voxel rows: [x,y,z, hit/total, hit, l0-l1, l1-l2, l2] float32. */
+int gvom_combined_cell_count(GvomHandle* h, int64_t* cells);
+int gvom_debug_voxel_map(GvomHandle* h, float* out_rows8, int64_t capacity_rows, int64_t* rows);
+int gvom_debug_height_map(GvomHandle* h, float* out_rows7);
+int gvom_debug_inferred_height_map(GvomHandle* h, float* out_rows3);
+
+/* ---- multi-GPU: independent sensor streams per GPU, merged at combine time ----
+ * Each rank pre-merges its own ring buffer into the common frame `origin`
+ * (integral voxel units): a dense int32 code grid (V entries: occupied flag
+ * 1<<26, else the pass count) and compact cell records (GVOM_RECORD_FLOATS
+ * float32 each).  The caller sums the grids and gathers the records and their
+ * counts across ranks (NCCL via torch.distributed); records_dev then holds
+ * nranks blocks of record_capacity records and record_counts_dev nranks counts.
+ * gvom_combine_finish() completes the combine on every rank.  See DESIGN.md. */
+#define GVOM_RECORD_FLOATS 16   /* voxel id, hit, total, min_h, 10 metrics, 2 pad */
+int gvom_newest_origin(GvomHandle* h, double origin[3]);
+int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_grid_dev,
+                         float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
+                         void* stream);
+int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* code_grid_dev,
+                        const float* records_dev, const int32_t* record_counts_dev, int32_t nranks,
+                        int64_t record_capacity, double origin_out[3], int32_t* positive,
+                        int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem,
+                        void* stream);
+
+/* ---- test / tooling hooks (canonical parity dumps; not on the hot path) ---- */
+int gvom_slot_info(GvomHandle* h, int32_t slot, int32_t* valid, int64_t* cells, double origin[3]);
+int gvom_last_slot(GvomHandle* h, int32_t* slot);
+/* host outputs: index_map[V] int32, hit/total[cells] int32, metrics[cells*10] float64,
+ * min_height[cells] float32 (any may be NULL) */
+int gvom_export_slot(GvomHandle* h, int32_t slot, int32_t* index_map, int32_t* hit, int32_t* total,
+                     double* metrics, float* min_height);
+/* host outputs of the last combined map (any may be NULL): index_map[V], hit/total[cells],
+ * min_height[cells], metrics[cells*10] float32, eig[cells*3] float32, and the six float64
+ * xy*xy maps height, inferred, roughness, x_slope, y_slope, guessed. */
+int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_t* total,
+                         float* min_height, float* metrics, float* eig, double* maps6);
+int gvom_get_stats(GvomHandle* h, GvomStats* out);
+/* CUDA-event time (ms) of the stages of the last process / combine call:
+ * [0] H2D+staging, [1] voxelise+ray-cast, [2] index build, [3] moments, [4] gather,
+ * [5] merge codes, [6] merge cells, [7] 2-D maps, [8] D2H.  Only recorded when
+ * gvom_set_profiling(h, 1) is on (adds event records to the stream). */
+int gvom_set_profiling(GvomHandle* h, int32_t on);
+int gvom_stage_times(GvomHandle* h, float ms[16]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVOM_B200_H */

@@ -96,12 +96,14 @@ class Golden:
         pre = f"s{step}_"
         return {k[len(pre):]: self.z[k] for k in self.z.files if k.startswith(pre)}
 
-    def compare(self, step, got, what=""):
+    def compare(self, step, got, what="", skip=()):
         """Return a list of mismatch descriptions for one step (empty = parity)."""
         bad = []
         gold = self.fields(step)
         kind = self.meta["steps"][step]
         for k, gv in gold.items():
+            if k in skip:
+                continue
             if k not in got:
                 bad.append(f"{what} step {step} ({kind}): field {k} missing from result")
                 continue

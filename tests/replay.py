@@ -14,7 +14,7 @@ def golden(name, suffix=""):
     return canon.Golden(os.path.join(GOLDEN_DIR, f"{name}{suffix}.npz"))
 
 
-def replay(make, name, gold=None, view=lambda g: g, what="", full=True, on_step=None):
+def replay(make, name, gold=None, view=lambda g: g, what="", full=True, on_step=None, skip=()):
     """make(params) -> object with the Gvom API; view(obj) -> ref-style state.
     Returns (list of mismatches, list of canonical dumps)."""
     P, steps = synth.scenario(name)
@@ -36,7 +36,7 @@ def replay(make, name, gold=None, view=lambda g: g, what="", full=True, on_step=
             d = canon.canon_debug(view(g))
         dumps.append(d)
         if gold is not None:
-            bad += gold.compare(i, d, what)
+            bad += gold.compare(i, d, what, skip)
         if on_step:
             on_step(i, st, d)
     return bad, dumps

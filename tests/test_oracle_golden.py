@@ -23,7 +23,16 @@ def test_oracle_matches_reference_full_size(name):
 
 
 def test_oracle_matches_cudasim_tiny():
-    """CUDASIM types the DDA differently from compiled PTX; the tiny
-    scenario is chosen so both agree, which pins the host-side call order."""
-    bad, _ = replay.replay(lambda P: OracleGvom(*P), "tiny", replay.golden("tiny", "_sim"), what="oracle-vs-sim")
+    """Secondary pin: the same tiny scenario through NUMBA_ENABLE_CUDASIM in the CPU container.
+    The simulator has no FMA contraction, so the least-squares plane fit of
+    __calculate_slope (gvom.py:717-805) differs from compiled code wherever the 3x3 fit is
+    degenerate (det == 0 exactly in the simulator, ~1e-17 on the GPU); slope, roughness and
+    the slope-gated positive map are therefore left to the compiled-reference goldens.
+    Everything else -- voxel codes, counts, moments, heights, guessed heights, negative
+    obstacles, visibility -- must agree, which pins the host-side call order."""
+    skip = ("out_pos", "out_rough", "x_slope", "y_slope")
+    P, steps = replay.synth.scenario("tiny")
+    gold = replay.golden("tiny", "_sim")
+    bad, dumps = replay.replay(lambda P: OracleGvom(*P), "tiny", gold, what="oracle-vs-sim", skip=skip)
+    bad = [b for b in bad if "(debug): height" not in b]      # debug rows carry the slopes too
     assert not bad, "\n".join(bad[:20])
