@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""bench.py -- scans/s and per-scan latency of Process_pointcloud + combine_maps.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (N>1: under torchrun)
+  python bench.py --impl reference ...                           (reference arm)
+
+One step = one synthetic OS1-128 scan (262,144 points) processed into
+a 256x256x64 grid (buffer 4) followed by one combine_maps() -- BASELINE.json
+configs[1]; at N>1 every rank owns one sensor stream (configs[2]) and the combine
+is reduced across ranks.  Prints ONE JSON line (rank 0).
+
+  value  : scans/s with the cloud already in HBM and the maps left in HBM
+           (CUDA events around every step on the launching stream; L2 flushed
+           between steps, outside the timed region)
+  e2e    : the same through the public drop-in API with HOST buffers: pinned float64
+           cloud in, numpy maps out, H2D and D2H inside the timed region
+  roofline / rooflines : per-kernel CUDA-event times (library profiling events on the
+           same stream) against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+           and, for the ray-cast kernel, the L2 atomic throughput measured here by the
+           library's microbenchmark
+  cpu_baseline : the CPU oracle port (oracle/) timed on this box's host cores on a
+           bounded sample of the same workload (reported, not a target)
+
+--impl reference: the UNMODIFIED reference class (baseline/_ref/gvom.py or
+/root/reference/scripts/gvom.py) through Numba-CUDA on the same GPU with the two
+external shims of baseline/ref_shims.py -- the reference has no CPU implementation
+other than Numba's simulator (about a day per scan at this size).  If
+Numba cannot drive the GPU the arm falls back to the CPU oracle port on all host
+threads (cpu_baseline.kind = "port").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gvom_b200 import synth  # noqa: E402
+
+METRIC = "scans/sec (Process_pointcloud+combine_maps, OS1-128 262,144 pts, 256x256x64 grid, buffer 4)"
+BEAMS, COLS = 128, 2048
+NFRAMES = 8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def frames(rank=0):
+    """NFRAMES consecutive frames of the SURVEY 8(d) stream (sensor `rank` on a 2 m ring)."""
+    out = []
+    for i in range(NFRAMES):
+        pc, ego, T = synth.frame(i, BEAMS, COLS, seed_base=1000 * rank)
+        if rank:
+            a = np.pi / 4 * rank
+            T = T.copy()
+            T[0, 3] += 2.0 * np.cos(a)
+            T[1, 3] += 2.0 * np.sin(a)
+        out.append((pc, ego, T))
+    return out
+
+
+def cpu_baseline(sample_steps=4, threads=None):
+    """CPU oracle port on the host cores: bounded sample of the same workload."""
+    from oracle import gvom_oracle
+    L = gvom_oracle.lib()
+    cores = threads or os.cpu_count()
+    L.gvo_set_threads(cores)
+    g = gvom_oracle.OracleGvom(*synth.params_tuple())
+    fr = frames()
+    g.Process_pointcloud(*fr[0]); g.combine_maps()                       # warm-up (page faults)
+    t0 = time.perf_counter()
+    for i in range(sample_steps):
+        g.Process_pointcloud(*fr[(i + 1) % NFRAMES])
+        g.combine_maps()
+    dt = time.perf_counter() - t0
+    return {"value": sample_steps / dt, "unit": "scans/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_steps} scans+combines of the bench workload, oracle/gvom_oracle.c "
+                      f"(OpenMP on the ray-cast and merge loops, {cores} threads; moment passes serial)",
+            "ms_per_step": 1e3 * dt / sample_steps, "work": g.work}
+
+
+def run_reference(args):
+    """Reference arm: unmodified reference Gvom via Numba-CUDA on this GPU."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = {"impl": "reference", "metric": METRIC, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic OS1-128 scan (128x2048=262,144 pts), 256x256x64 grid "
+                                   "@0.4/0.2 m, buffer 4, one sensor", "frames": NFRAMES}}
+    fr = frames()
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        for cand in ("/root/reference/scripts", os.path.join(ROOT, "baseline", "_ref")):
+            if os.path.exists(os.path.join(cand, "gvom.py")):
+                sys.path.insert(0, cand)
+                break
+        else:
+            raise RuntimeError("reference gvom.py not present (baseline/_ref)")
+        if args.ref_mode == "oracle":
+            raise RuntimeError("--ref-mode oracle")
+        import ref_shims  # noqa: F401
+        import numba.cuda
+        import gvom as refgvom
+        if refgvom.__file__.startswith(os.path.join(ROOT, "gvom_b200")):
+            raise RuntimeError("import gvom resolved to the B200 shim, not the reference")
+        g = refgvom.Gvom(*synth.params_tuple())
+        ts = []
+        for i in range(args.warmup + args.steps):
+            pc, ego, T = fr[i % NFRAMES]
+            t0 = time.perf_counter()
+            g.Process_pointcloud(pc, ego, T)
+            g.combine_maps()
+            numba.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        ts = ts[args.warmup:]
+        v = len(ts) / sum(ts)
+        base.update({"value": v, "ms_per_step": 1e3 * sum(ts) / len(ts), "p50_latency_ms": 1e3 * statistics.median(ts),
+                     "cpu_baseline": {"value": v, "unit": "scans/s", "cores": 1, "kind": "reference",
+                                      "sample": f"{len(ts)} steps; unmodified reference class through Numba-CUDA "
+                                                "(PTX JIT compute_90->sm_100) on the same B200, 1 host thread; "
+                                                "shims: baseline/ref_shims.py"},
+                     "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": None})
+    except Exception as ex:  # Numba cannot drive this GPU: CPU oracle port on all host threads
+        steps = max(1, min(args.steps, 6))
+        cb = cpu_baseline(sample_steps=steps)
+        base.update({"value": cb["value"], "ms_per_step": cb["ms_per_step"], "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "note": f"reference via Numba unavailable ({type(ex).__name__}: {ex}); timed the CPU oracle port"})
+    print(json.dumps(base), flush=True)
+
+
+def atomic_peak(L, torch, dev):
+    """L2 atomic throughput (G atomics/s): random words of a 16 MiB table, and one word."""
+    import ctypes as C
+    words = 1 << 22
+    table = torch.empty(words, dtype=torch.int32, device=f"cuda:{dev}")
+    res = {}
+    for name, mode in (("spread", 0), ("same_address", 1)):
+        ms, n = C.c_float(0), C.c_int64(0)
+        rc = L.gvom_bench_atomics(dev, table.data_ptr(), words, 64, mode, 5, C.byref(ms), C.byref(n))
+        if rc == 0 and ms.value > 0:
+            res[name] = n.value / (ms.value * 1e-3) / 1e9
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-mode", default="numba", choices=["numba", "oracle"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from gvom_b200 import _lib
+    from gvom_b200.gvom import Gvom
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    dev = local
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
+
+    stream = torch.cuda.Stream(device=dev)
+    P = synth.params_tuple()
+    if multi:
+        from gvom_b200.multi import MultiGpuGvom
+        g = MultiGpuGvom(*P, device=dev, stream=stream.cuda_stream, torch_stream=stream)
+    else:
+        g = Gvom(*P, device=dev, stream=stream.cuda_stream)
+    fr = frames(rank)
+    pinned = [torch.from_numpy(f[0]).pin_memory() for f in fr]
+    on_dev = [p.cuda(dev) for p in pinned]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")
+    torch.cuda.synchronize()
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(device_io, steps, warmup, profile=False):
+        """-> (per-step ms list [device events], per-step wall ms, stage-time sums)"""
+        ev, wall, stages = [], [], {}
+        for i in range(warmup + steps):
+            k = i % NFRAMES
+            with torch.cuda.stream(stream):
+                flush.zero_()                                   # L2 flush, outside the timed region
+            stream.synchronize()
+            if multi:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record(stream)
+            if device_io:
+                g.Process_pointcloud(on_dev[k], fr[k][1], fr[k][2])
+                out = g.combine_maps(device_outputs=True)
+            else:
+                g.Process_pointcloud(pinned[k], fr[k][1], fr[k][2])
+                out = g.combine_maps()
+            b.record(stream)
+            b.synchronize()
+            t1 = time.perf_counter()
+            assert out is not None
+            if i >= warmup:
+                ev.append(a.elapsed_time(b))
+                wall.append(1e3 * (t1 - t0))
+                if profile:
+                    for kk, vv in g.stage_times().items():
+                        stages[kk] = stages.get(kk, 0.0) + vv
+        return ev, wall, stages
+
+    # ---- timed regions
+    barrier()
+    sampler = ClockSampler(dev) if rank == 0 else None
+    ev_dev, wall_dev, _ = timed(True, args.steps, args.warmup)
+    barrier()
+    ev_e2e, wall_e2e, _ = timed(False, args.steps, args.warmup)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches0 = g.stats()["kernel_launches"]
+    calls0 = g.stats()["process_calls"]
+    # ---- per-kernel CUDA-event times (separate pass: the extra event records stay out of the numbers above)
+    g.set_profiling(True)
+    psteps = min(args.steps, 50)
+    _, _, stages = timed(True, psteps, 3, profile=True)
+    g.set_profiling(False)
+    st = g.stats()
+    launches_per_step = (st["kernel_launches"] - launches0) / max(1, st["process_calls"] - calls0)
+
+    def agg(ms_list):
+        t = torch.tensor([sum(ms_list)], dtype=torch.float64, device=f"cuda:{dev}")
+        if multi:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    tot_dev, tot_e2e = agg(ev_dev), agg(wall_e2e)
+    if rank != 0:
+        if multi:
+            dist.destroy_process_group()
+        return
+
+    value = world * args.steps / (tot_dev * 1e-3)
+    e2e = world * args.steps / (tot_e2e * 1e-3)
+    hbm, hbm_src = peaks()
+    V = P[2] * P[2] * P[3]
+    B = P[4]
+    N = BEAMS * COLS
+    sources = min(B, args.warmup + args.steps) + 1
+    stage_ms = {k: v / psteps for k, v in stages.items()}
+    # algorithmic bytes per launch (DESIGN.md "kernels")
+    work = None
+    atom = atomic_peak(_lib.lib(), torch, dev)
+    try:
+        from oracle.gvom_oracle import OracleGvom
+        o = OracleGvom(*P)
+        o.Process_pointcloud(*fr[0])
+        work = o.work
+    except Exception:
+        pass
+    abytes = {"raycast": 24 * N, "index": 12 * V, "merge_codes": 4 * V * sources + 4 * V, "maps": 4 * V + 20 * P[2] * P[2]}
+    rooflines = {}
+    for k, bts in abytes.items():
+        if stage_ms.get(k, 0) > 0:
+            ach = bts / (stage_ms[k] * 1e-3) / 1e9
+            rooflines[k] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                            "ms": stage_ms[k], "algorithmic_bytes": bts}
+    if work and stage_ms.get("raycast", 0) > 0 and atom.get("spread"):
+        n_at = 2 * work["n_in"] + work["dda_steps"]
+        ach = n_at / (stage_ms["raycast"] * 1e-3) / 1e9
+        rooflines["raycast_atomics"] = {"bound": "l2_atomic", "achieved": ach, "peak": atom["spread"],
+                                        "unit": "G atomic increments/s", "frac": ach / atom["spread"],
+                                        "ms": stage_ms["raycast"], "algorithmic_atomics": n_at,
+                                        "peak_same_address": atom.get("same_address"),
+                                        "note": "increments delivered (warp-aggregated) vs RED.ADD.U32 issue rate to "
+                                                "random words of a 16 MiB table measured by gvom_bench_atomics"}
+    kernels = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h")}
+    dom = max((k for k in kernels if k in rooflines), key=lambda k: kernels[k], default=None)
+    roof = dict(rooflines[dom], kernel=dom, traffic=None, peak_source=hbm_src) if dom else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tot_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": ("configs[1]: synthetic OS1-128 scan (128x2048=262,144 pts), 256x256x64 grid @0.4/0.2 m, "
+                                "buffer 4, one sensor per GPU" + ("; configs[2]: per-GPU streams, NCCL-reduced combine" if multi else "")),
+                   "frames": NFRAMES, "l2": "flushed between steps (256 MiB memset, outside the timed region)",
+                   "value_io": "cloud resident in HBM (float64 Nx3), maps left in HBM",
+                   "e2e_io": "pinned host float64 Nx3 cloud in, numpy maps out (pinned), per-step wall clock around both calls"},
+        "p50_latency_ms": statistics.median(ev_dev),
+        "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": int(fr[0][0].nbytes),
+                "d2h_bytes_per_step": 20 * P[2] * P[2], "p50_latency_ms": statistics.median(wall_e2e),
+                "p50_device_ms": statistics.median(ev_e2e)},
+        "gpu_launches": int(round(launches_per_step * args.steps)),
+        "gpu_launches_per_step": launches_per_step,
+        "clocks": clocks,
+        "roofline": roof,
+        "rooflines": rooflines,
+        "stage_ms": stage_ms,
+        "l2_atomic_peak_gops": atom,
+        "work_per_scan": work,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as ex:
+            line["cpu_baseline"] = {"error": repr(ex)}
+    print(json.dumps(line), flush=True)
+    if multi:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

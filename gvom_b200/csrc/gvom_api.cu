@@ -97,22 +97,23 @@ struct GvomHandle {
     std::vector<Slot> slots;
     Combined comb[2];
     int cur = 0;                          // comb[cur] = last combined map (if valid)
-    double* maps = nullptr;               // height, inferred, rough, xs, ys, guessed  [6][S*S]
-    int* imaps = nullptr;                 // pos, neg, vis [3][S*S]
+    double* maps = nullptr;               // height, inferred, rough_work, xs, ys, guessed  [6][S*S]
+    int* imaps = nullptr;                 // result block: pos, neg, vis int32 [3][S*S] then roughness f64 [S*S]
+    double* rough_out = nullptr;          // = (double*)(imaps + 3*S*S)
     float* debug_dev = nullptr;           // [max(ccap*8, S*S*10)]
     int* flags = nullptr;
     // multi-GPU scratch
     double* cacc = nullptr;               // [ccap,10] raw-moment scratch of the multi-GPU combine
     // pinned host
     char* stage_host = nullptr;           // [max_points * 32 B]
-    double* out_rough_host = nullptr;     // [S*S]
     int* out_i_host = nullptr;            // [3*S*S]
     int* counters_host = nullptr;         // [8]
     // state
     int buffer_index = 0, last_buffer_index = 0;
     double ego[3] = {0, 0, 0};
     bool have_maps = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // the handle's own stream
+    cudaStream_t active = nullptr;        // stream of the last process / combine call (tooling syncs it)
     cudaEvent_t ev_stage = nullptr;       // completion of the last H2D that read stage_host
     bool stage_busy = false;
     cudaEvent_t ev[EV_COUNT];
@@ -154,14 +155,14 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
         c.counter = d.take<int>(4);
     }
     h->maps = d.take<double>(6 * S2);
-    h->imaps = d.take<int>(3 * S2);
+    h->imaps = d.take<int>(3 * S2 + 2 * S2);
+    h->rough_out = reinterpret_cast<double*>(h->imaps ? h->imaps + 3 * S2 : nullptr);
     h->debug_dev = d.take<float>(std::max(ccap * 8, S2 * 10));
     h->flags = d.take<int>(8);
     h->cacc = d.take<double>(ccap * 10);
     Carver c(host);
     h->stage_host = c.take<char>((size_t)h->max_points * 32);
-    h->out_rough_host = c.take<double>(S2);
-    h->out_i_host = c.take<int>(3 * S2);
+    h->out_i_host = c.take<int>(3 * S2 + 2 * S2);   // mirrors the device result block
     h->counters_host = c.take<int>(8);
     *host_bytes = c.off + 256;
     return d.off + 256;
@@ -235,7 +236,7 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
 int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* positive, int32_t* negative,
                         double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st) {
     const int S2 = h->S2;
-    double* height = h->maps; double* inferred = h->maps + S2; double* rough = h->maps + 2 * (size_t)S2;
+    double* height = h->maps; double* inferred = h->maps + S2; double* rough = h->rough_out;
     double* xs = h->maps + 3 * (size_t)S2; double* ys = h->maps + 4 * (size_t)S2; double* guessed = h->maps + 5 * (size_t)S2;
     int* pos = h->imaps; int* neg = h->imaps + S2; int* vis = h->imaps + 2 * (size_t)S2;
     k_column_maps<<<blocks_for(S2, 256), 256, 0, st>>>(c.index_map, c.minh, c.origin[0], c.origin[1], c.origin[2],
@@ -260,21 +261,26 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
                             is_pinned_or_device(negative, &dev) && is_pinned_or_device(visibility, &dev) &&
                             is_pinned_or_device(roughness, &dev);
         if (direct) {                      // caller's buffers are pinned: DMA straight into them
-            CUDA_TRY(cudaMemcpyAsync(positive, pos, bi, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(negative, neg, bi, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(visibility, vis, bi, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToHost, st));
+            if (negative == positive + S2 && visibility == negative + S2 &&
+                reinterpret_cast<char*>(roughness) == reinterpret_cast<char*>(visibility + S2)) {
+                // laid out like the device result block: one transfer for all four maps
+                CUDA_TRY(cudaMemcpyAsync(positive, pos, 3 * bi + bd, cudaMemcpyDeviceToHost, st));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(positive, pos, bi, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(negative, neg, bi, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(visibility, vis, bi, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToHost, st));
+            }
             rec(h, EV_D2H, st);
             CUDA_TRY(cudaStreamSynchronize(st));
         } else {                           // pageable: one DMA per dtype into pinned staging, then memcpy
-            CUDA_TRY(cudaMemcpyAsync(h->out_i_host, h->imaps, 3 * bi, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(h->out_rough_host, rough, bd, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h->out_i_host, h->imaps, 3 * bi + bd, cudaMemcpyDeviceToHost, st));
             rec(h, EV_D2H, st);
             CUDA_TRY(cudaStreamSynchronize(st));
             if (positive) memcpy(positive, h->out_i_host, bi);
             if (negative) memcpy(negative, h->out_i_host + S2, bi);
             if (visibility) memcpy(visibility, h->out_i_host + 2 * (size_t)S2, bi);
-            if (roughness) memcpy(roughness, h->out_rough_host, bd);
+            if (roughness) memcpy(roughness, h->out_i_host + 3 * (size_t)S2, bd);
         }
     }
     c.cells = std::min<int64_t>(h->counters_host[0], h->ccap);
@@ -335,6 +341,7 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
         delete h;
         return fail(GVOM_ECUDA, std::string("gvom_create: ") + cudaGetErrorString(e));
     }
+    h->active = h->stream;
     *out = h;
     return GVOM_OK;
 }
@@ -360,6 +367,7 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->active = st;
     const GvomParams& p = h->p;
 
     // gvom.py:110-112, 138-141
@@ -454,6 +462,7 @@ int gvom_combine_maps(GvomHandle* h, double origin[3], int32_t* positive, int32_
     Slot& newest = h->slots[h->last_buffer_index];
     if (!newest.valid) return GVOM_NO_DATA;                 // gvom.py:225-227
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->active = st;
     rec(h, EV_CSTART, st);
     MergeArgs A;
     build_sources(h, newest.origin, true, &A);
@@ -491,11 +500,11 @@ int gvom_debug_voxel_map(GvomHandle* h, float* out, int64_t capacity_rows, int64
     if (!c.valid) return GVOM_NO_DATA;
     if (capacity_rows < c.cells) return fail(GVOM_ECAPACITY, "output has fewer rows than combined cells");
     if (c.cells > 0) {
-        k_debug_voxels<<<h->sm_count * 4, 256, 0, h->stream>>>(c.counter, c.cell_voxel, c.hit, c.total, c.eig, c.origin[0],
+        k_debug_voxels<<<h->sm_count * 4, 256, 0, h->active>>>(c.counter, c.cell_voxel, c.hit, c.total, c.eig, c.origin[0],
                                                               c.origin[1], c.origin[2], h->dp, (int)h->ccap, h->debug_dev);
         h->stats.kernel_launches++;
-        CUDA_TRY(cudaMemcpyAsync(out, h->debug_dev, sizeof(float) * 8 * (size_t)c.cells, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaMemcpyAsync(out, h->debug_dev, sizeof(float) * 8 * (size_t)c.cells, cudaMemcpyDeviceToHost, h->active));
+        CUDA_TRY(cudaStreamSynchronize(h->active));
     }
     if (rows) *rows = c.cells;
     return GVOM_OK;
@@ -508,13 +517,13 @@ static int debug_height_common(GvomHandle* h, float* out7, float* out3) {
     if (!c.valid || !h->have_maps) return GVOM_NO_DATA;
     const size_t S2 = (size_t)h->S2;
     float* d7 = h->debug_dev; float* d3 = h->debug_dev + 7 * S2;
-    k_debug_height<<<blocks_for(h->S2, 256), 256, 0, h->stream>>>(h->maps, h->maps + 2 * S2, h->maps + 3 * S2, h->maps + 4 * S2,
+    k_debug_height<<<blocks_for(h->S2, 256), 256, 0, h->active>>>(h->maps, h->rough_out, h->maps + 3 * S2, h->maps + 4 * S2,
                                                                 h->maps + 5 * S2, c.origin[0], c.origin[1], h->dp,
                                                                 out7 ? d7 : nullptr, out3 ? d3 : nullptr);
     h->stats.kernel_launches++;
-    if (out7) CUDA_TRY(cudaMemcpyAsync(out7, d7, sizeof(float) * 7 * S2, cudaMemcpyDeviceToHost, h->stream));
-    if (out3) CUDA_TRY(cudaMemcpyAsync(out3, d3, sizeof(float) * 3 * S2, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (out7) CUDA_TRY(cudaMemcpyAsync(out7, d7, sizeof(float) * 7 * S2, cudaMemcpyDeviceToHost, h->active));
+    if (out3) CUDA_TRY(cudaMemcpyAsync(out3, d3, sizeof(float) * 3 * S2, cudaMemcpyDeviceToHost, h->active));
+    CUDA_TRY(cudaStreamSynchronize(h->active));
     return GVOM_OK;
 }
 
@@ -542,7 +551,7 @@ int gvom_slot_info(GvomHandle* h, int32_t slot, int32_t* valid, int64_t* cells, 
     if (valid) *valid = s.valid ? 1 : 0;
     if (s.valid) {
         int cnt = 0;
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->active));
         CUDA_TRY(cudaMemcpy(&cnt, s.counter, sizeof(int), cudaMemcpyDeviceToHost));
         if (cells) *cells = std::min<int64_t>(cnt, h->cap);
         h->stats.scan_cells = cnt;
@@ -575,7 +584,7 @@ int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_
     CUDA_TRY(cudaSetDevice(h->device));
     Combined& c = h->comb[h->cur];
     if (!c.valid) return GVOM_NO_DATA;
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->active));
     const size_t n = (size_t)c.cells;
     if (index_map) CUDA_TRY(cudaMemcpy(index_map, c.index_map, sizeof(int) * (size_t)h->V, cudaMemcpyDeviceToHost));
     if (hit) CUDA_TRY(cudaMemcpy(hit, c.hit, sizeof(int) * n, cudaMemcpyDeviceToHost));
@@ -583,7 +592,11 @@ int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_
     if (min_height) CUDA_TRY(cudaMemcpy(min_height, c.minh, sizeof(float) * n, cudaMemcpyDeviceToHost));
     if (metrics) CUDA_TRY(cudaMemcpy(metrics, c.metrics, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost));
     if (eig) CUDA_TRY(cudaMemcpy(eig, c.eig, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
-    if (maps6) CUDA_TRY(cudaMemcpy(maps6, h->maps, sizeof(double) * 6 * (size_t)h->S2, cudaMemcpyDeviceToHost));
+    if (maps6) {
+        const size_t mb = sizeof(double) * (size_t)h->S2;
+        CUDA_TRY(cudaMemcpy(maps6, h->maps, 6 * mb, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(maps6 + 2 * (size_t)h->S2, h->rough_out, mb, cudaMemcpyDeviceToHost));
+    }
     return GVOM_OK;
 }
 
@@ -606,7 +619,7 @@ int gvom_stage_times(GvomHandle* h, float ms[16]) {
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
     for (int i = 0; i < 16; ++i) ms[i] = 0.f;
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->active));
     if (h->prof_process) {
         const int a[5] = {EV_START, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS};
         const int b[5] = {EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER};
@@ -617,6 +630,36 @@ int gvom_stage_times(GvomHandle* h, float ms[16]) {
         const int b[4] = {EV_CODES, EV_CELLS, EV_MAPS, EV_D2H};
         for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[5 + i], h->ev[a[i]], h->ev[b[i]]));
     }
+    return GVOM_OK;
+}
+
+// ------------------------------------------------------------- tooling: atomic roofline
+int gvom_bench_atomics(int device, void* table_dev, int64_t table_words, int32_t per_thread, int32_t mode,
+                       int32_t repeats, float* best_ms, int64_t* atomics_per_launch) {
+    if (!table_dev || !best_ms || table_words < 1 || (table_words & (table_words - 1)))
+        return fail(GVOM_EINVAL, "table_words must be a power of two");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8;
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    CUDA_TRY(cudaMemset(table_dev, 0, sizeof(int) * (size_t)table_words));
+    float best = 1e30f;
+    for (int r = 0; r < repeats + 2; ++r) {
+        CUDA_TRY(cudaEventRecord(a, 0));
+        k_atomic_bench<<<blocks, 256>>>((int*)table_dev, (unsigned)(table_words - 1), per_thread, mode);
+        CUDA_TRY(cudaEventRecord(b, 0));
+        CUDA_TRY(cudaEventSynchronize(b));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+        if (r >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *best_ms = best;
+    if (atomics_per_launch) *atomics_per_launch = (int64_t)blocks * 256 * per_thread;
     return GVOM_OK;
 }
 
@@ -637,6 +680,7 @@ int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_gr
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->active = st;
     rec(h, EV_CSTART, st);
     MergeArgs A;
     build_sources(h, origin, false, &A);       // a rank without data contributes an empty grid
@@ -658,6 +702,7 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->active = st;
     Combined& pc = h->comb[h->cur];
     Combined& c = h->comb[1 - h->cur];
     for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];

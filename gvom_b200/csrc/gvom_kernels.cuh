@@ -996,4 +996,20 @@ k_finish_cells(SlotRef prev, int has_prev, const int* __restrict__ counter, cons
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// tooling: L2 atomic-throughput microbenchmark (roofline denominator of the
+// ray-cast kernel).  Every thread issues `per_thread` RED.ADD.U32 to
+// pseudo-random words of an L2-resident table (mode 0) or to ONE word (mode 1).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_atomic_bench(int* __restrict__ table, unsigned mask, int per_thread, int mode) {
+    unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int k = 0; k < per_thread; ++k) {
+        s = s * 1664525u + 1013904223u;
+        const unsigned a = mode ? 0u : ((s >> 8) & mask);
+        atomicAdd(table + a, 1);
+    }
+}
+
 }  // namespace gvom

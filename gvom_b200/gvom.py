@@ -44,7 +44,8 @@ class Gvom:
     def __init__(self, xy_resolution, z_resolution, xy_size, z_size, buffer_size, min_distance,
                  positive_obstacle_threshold, negative_obstacle_threshold, slope_obsacle_threshold,
                  robot_height, robot_radius, ground_to_lidar_height, xy_eigen_dist, z_eigen_dist, *,
-                 max_points=DEFAULT_MAX_POINTS, device=None, max_combined_cells=0, pinned_outputs=True):
+                 max_points=DEFAULT_MAX_POINTS, device=None, max_combined_cells=0, pinned_outputs=True,
+                 stream=None):
         self.xy_resolution, self.z_resolution = xy_resolution, z_resolution
         self.xy_size, self.z_size, self.buffer_size = int(xy_size), int(z_size), int(buffer_size)
         self.min_distance = min_distance
@@ -60,6 +61,8 @@ class Gvom:
         self.pinned_outputs = bool(pinned_outputs)
         self.ego_position = [0, 0, 0]
         self._h = None
+        # cudaStream_t (int) all work is enqueued on; None = the handle's own non-blocking stream
+        self._stream = None if stream is None else C.c_void_p(int(stream))
 
         self._L = _lib.lib()                     # raises if the CUDA library is missing
         torch = self._torch = _torch()
@@ -135,7 +138,7 @@ class Gvom:
             if T.shape != (4, 4):
                 raise ValueError("transform must be 4x4")
             tp = T.ctypes.data
-        check(self._L.gvom_process_pointcloud(self._h, ptr, n, stride, dt, mem, e, tp, None),
+        check(self._L.gvom_process_pointcloud(self._h, ptr, n, stride, dt, mem, e, tp, self._stream),
               "gvom_process_pointcloud")
         del keep
 
@@ -143,22 +146,35 @@ class Gvom:
 
     # ---------------------------------------------------------------- combine
     def _out_arrays(self):
+        """Fresh output arrays (positive, negative, roughness, visibility).  With pinned_outputs
+        they are views of ONE pinned block laid out like the device-side result block, so the
+        library moves all four maps with a single DMA straight into the returned arrays."""
         S = self.xy_size
         if self.pinned_outputs:
-            torch = self._torch
-            ti = torch.empty((3, S, S), dtype=torch.int32, pin_memory=True)
-            tr = torch.empty((S, S), dtype=torch.float64, pin_memory=True)
-            ai, rough = ti.numpy(), tr.numpy()
-            return ai[0], ai[1], rough, ai[2]
+            blk = self._torch.empty(20 * S * S, dtype=self._torch.uint8, pin_memory=True).numpy()
+            i32 = blk[:12 * S * S].view(np.int32).reshape(3, S, S)
+            rough = blk[12 * S * S:].view(np.float64).reshape(S, S)
+            return i32[0], i32[1], rough, i32[2]
         return (np.empty((S, S), np.int32), np.empty((S, S), np.int32), np.empty((S, S), np.float64),
                 np.empty((S, S), np.int32))
 
-    def combine_maps(self):
-        """ Combines all maps in the buffer and processes into 2D maps """
-        pos, neg, rough, vis = self._out_arrays()
-        rc = check(self._L.gvom_combine_maps(self._h, self._org_c, pos.ctypes.data, neg.ctypes.data,
-                                             rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None),
-                   "gvom_combine_maps")
+    def combine_maps(self, device_outputs=False):
+        """ Combines all maps in the buffer and processes into 2D maps.
+        device_outputs=True (extension) returns torch CUDA tensors instead of numpy arrays."""
+        if device_outputs:
+            torch, S = self._torch, self.xy_size
+            dev = f"cuda:{self.device}"
+            ti = torch.empty((3, S, S), dtype=torch.int32, device=dev)
+            rough = torch.empty((S, S), dtype=torch.float64, device=dev)
+            rc = check(self._L.gvom_combine_maps(self._h, self._org_c, ti[0].data_ptr(), ti[1].data_ptr(),
+                                                 rough.data_ptr(), ti[2].data_ptr(), GVOM_DEVICE, self._stream),
+                       "gvom_combine_maps")
+            pos, neg, vis = ti[0], ti[1], ti[2]
+        else:
+            pos, neg, rough, vis = self._out_arrays()
+            rc = check(self._L.gvom_combine_maps(self._h, self._org_c, pos.ctypes.data, neg.ctypes.data,
+                                                 rough.ctypes.data, vis.ctypes.data, GVOM_HOST, self._stream),
+                       "gvom_combine_maps")
         if rc == GVOM_NO_DATA:
             print("ERROR: No data in buffer")
             return None

@@ -151,6 +151,14 @@ int gvom_get_stats(GvomHandle* h, GvomStats* out);
 int gvom_set_profiling(GvomHandle* h, int32_t on);
 int gvom_stage_times(GvomHandle* h, float ms[16]);
 
+/* Tooling: L2 atomic-throughput microbenchmark (denominator of the ray-cast roofline).
+ * Launches sm_count*8 blocks of 256 threads, each thread issuing per_thread
+ * red.global.add.u32 to pseudo-random words of table_dev (mode 0; table_words a power
+ * of two, caller-owned device memory) or to one single word (mode 1).  Best-of-repeats
+ * CUDA-event time in ms. */
+int gvom_bench_atomics(int device, void* table_dev, int64_t table_words, int32_t per_thread,
+                       int32_t mode, int32_t repeats, float* best_ms, int64_t* atomics_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

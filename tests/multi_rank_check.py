@@ -1,0 +1,49 @@
+"""Run under torchrun (any world size): MultiGpuGvom over NCCL must equal one Gvom
+holding all ranks' slots.  argv[1] = backend ("nccl")."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import canon  # noqa: E402
+from gvom_b200 import synth  # noqa: E402
+from gvom_b200.gvom import Gvom  # noqa: E402
+from gvom_b200.multi import MultiGpuGvom  # noqa: E402
+from test_multi_gpu import compare_state, sensor_frames  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    B = 2
+    P1 = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B, robot_radius=2.0)
+    PN = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B * world, robot_radius=2.0)
+    fr = sensor_frames(world, 4)
+    g = MultiGpuGvom(*P1, device=local)
+    for step in range(4):
+        g.Process_pointcloud(*fr[step][rank])
+        out = g.combine_maps()
+        ref = Gvom(*PN, device=local)
+        for s2 in range(step + 1):
+            for q in range(max(0, s2 - B + 1), s2 + 1):
+                for r in range(world):
+                    ref.Process_pointcloud(*fr[q][r])
+            last = ref.combine_maps()
+        compare_state(canon.canon_combine(g.refview(), out), canon.canon_combine(ref.refview(), last),
+                      f"step {step} rank {rank}")
+    dist.barrier()
+    if rank == 0:
+        print("MULTI_RANK_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+"""Multi-GPU combine: per-rank partial merge + exchange + finish must
+equal one Gvom that holds every rank's ring slots.
+
+ * test_partial_finish_equals_single (1 GPU): two handles on the same device play
+   two ranks; the exchange (sum of code grids, concatenation of records) is done in
+   process, so the kernels of gvom_combine_partial / gvom_combine_finish are
+   covered on the single-GPU box.
+ * test_nccl_two_ranks (>= 2 GPUs): the same through MultiGpuGvom over NCCL.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import canon
+from gvom_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sensor_frames(nranks, nsteps, beams=16, cols=256, wall=9.0):
+    """frames[step][rank] = (cloud, ego, T): common ego per step, sensors on a ring."""
+    out = []
+    for i in range(nsteps):
+        row = []
+        for r in range(nranks):
+            pc, ego, T = synth.frame(i, beams, cols, wall_radius=wall, seed_base=1000 * r, ego0=(10.0, 5.0, 1.0),
+                                     dego=(0.9, 0.5, 0.25))
+            T = T.copy()
+            T[0, 3] += 0.5 * np.cos(2.0 * r)
+            T[1, 3] += 0.5 * np.sin(2.0 * r)
+            row.append((pc, ego, T))
+        out.append(row)
+    return out
+
+
+def local_exchange(ranks, outs_host=True):
+    """Emulate the collectives for handles living in one process. Returns per-rank 5-tuples."""
+    import torch
+    from gvom_b200._lib import GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, check
+    g0 = ranks[0]
+    L, V, S = g0._L, g0.voxel_count, g0.xy_size
+    dev = f"cuda:{g0.device}"
+    org = (C.c_double * 3)()
+    grids, recs, counts = [], [], []
+    origin = None
+    for g in ranks:
+        if L.gvom_newest_origin(g._h, org) != GVOM_NO_DATA and origin is None:
+            origin = [org[0], org[1], org[2]]
+    assert origin is not None
+    o = (C.c_double * 3)(*origin)
+    cap = int(min(V, g0.buffer_size * g0.max_points))
+    for g in ranks:
+        grid = torch.empty(V, dtype=torch.int32, device=dev)
+        rec = torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(L.gvom_combine_partial(g._h, o, grid.data_ptr(), rec.data_ptr(), cap, cnt.data_ptr(), None), "partial")
+        torch.cuda.synchronize()
+        grids.append(grid); recs.append(rec); counts.append(int(cnt.item()))
+    total = torch.stack(grids).sum(0).to(torch.int32)
+    maxc = max(1, max(counts))
+    gathered = torch.stack([r[:maxc] for r in recs]).contiguous()
+    cdev = torch.tensor(counts, dtype=torch.int32, device=dev)
+    outs = []
+    for g in ranks:
+        pos, neg, rough, vis = g._out_arrays()
+        oo = (C.c_double * 3)()
+        check(L.gvom_combine_finish(g._h, o, total.data_ptr(), gathered.data_ptr(), cdev.data_ptr(), len(ranks), maxc,
+                                    oo, pos.ctypes.data, neg.ctypes.data, rough.ctypes.data, vis.ctypes.data,
+                                    GVOM_HOST, None), "finish")
+        outs.append((np.array(list(oo)), pos, neg, rough, vis))
+    return outs
+
+
+def compare_state(a, b, what):
+    """a, b: canon_combine dumps. ints exact, floats to tolerance."""
+    for k in ("out_origin", "out_pos", "out_neg", "out_vis", "codes", "ids", "hit", "total", "minh"):
+        assert np.array_equal(a[k], b[k]), f"{what}: {k}"
+    for k in ("out_rough", "height", "inferred", "x_slope", "y_slope", "guessed"):
+        assert np.allclose(a[k], b[k], rtol=1e-4, atol=1e-9), f"{what}: {k}"
+    assert np.allclose(a["metrics"], b["metrics"], rtol=1e-4, atol=2e-6), f"{what}: metrics"
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+def test_partial_finish_equals_single(nranks):
+    from gvom_b200 import Gvom
+    B = 2
+    P1 = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B, robot_radius=2.0)
+    PN = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B * nranks, robot_radius=2.0)
+    fr = sensor_frames(nranks, 5)
+    ranks = [Gvom(*P1) for _ in range(nranks)]
+    for step in range(5):
+        for r in range(nranks):
+            ranks[r].Process_pointcloud(*fr[step][r])
+        outs = local_exchange(ranks)
+        # One Gvom with B*nranks slots holding the same scans: replay the whole history from
+        # scratch (it needs the same chain of "previous combined map" states), feeding before
+        # every combine the scans the rank rings hold at that step, newest step last.
+        ref = Gvom(*PN)
+        for s2 in range(step + 1):
+            for q in range(max(0, s2 - B + 1), s2 + 1):
+                for r in range(nranks):
+                    ref.Process_pointcloud(*fr[q][r])
+            last = ref.combine_maps()
+        want = canon.canon_combine(ref.refview(), last)
+        for r in range(nranks):
+            got = canon.canon_combine(ranks[r].refview(), outs[r])
+            compare_state(got, want, f"step {step} rank {r}")
+
+
+def test_nccl_two_ranks(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    script = os.path.join(ROOT, "tests", "multi_rank_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script, "nccl"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTI_RANK_OK" in r.stdout
