@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -49,6 +50,8 @@ struct Slot {
     float* minh = nullptr;        // [cap]
     int* cell_voxel = nullptr;    // [cap]
     int* counter = nullptr;       // device cell count
+    unsigned* gmask = nullptr;    // [V/256] one bit per 8-voxel group: something known (valid when has_gmask)
+    bool has_gmask = false;
     double origin[3] = {0, 0, 0};
     bool valid = false;
 };
@@ -62,6 +65,8 @@ struct Combined {
     float* eig = nullptr;         // [ccap,3]
     int* cell_voxel = nullptr;
     int* counter = nullptr;
+    unsigned* gmask = nullptr;
+    bool has_gmask = false;
     double origin[3] = {0, 0, 0};
     bool valid = false;
     int64_t cells = 0;
@@ -100,8 +105,10 @@ struct GvomHandle {
     double* maps = nullptr;               // height, inferred, rough_work, xs, ys, guessed  [6][S*S]
     int* imaps = nullptr;                 // result block: pos, neg, vis int32 [3][S*S] then roughness f64 [S*S]
     double* rough_out = nullptr;          // = (double*)(imaps + 3*S*S)
+    int* col_minz = nullptr;              // [2][S*S] lowest occupied / lowest free z per column (C1 -> C3)
+    unsigned* known = nullptr;            // [2][S*ceil(S/32)] "height known" bit maps (rows over y, rows over x)
     float* debug_dev = nullptr;           // [max(ccap*8, S*S*10)]
-    int* flags = nullptr;
+    int* flags = nullptr;                 // [0] running cell counter of K2, [1] of C1 (reset by their consumers)
     // multi-GPU scratch
     double* cacc = nullptr;               // [ccap,10] raw-moment scratch of the multi-GPU combine
     // pinned host
@@ -116,10 +123,15 @@ struct GvomHandle {
     cudaStream_t active = nullptr;        // stream of the last process / combine call (tooling syncs it)
     cudaEvent_t ev_stage = nullptr;       // completion of the last H2D that read stage_host
     bool stage_busy = false;
+    cudaStream_t copy_stream = nullptr;   // H2D of the cloud, chunked so that ray casting overlaps the transfer
+    cudaEvent_t ev_chunk[8];              // chunk c has landed in stage_dev
+    cudaEvent_t ev_proc_done = nullptr;   // last reader of stage_dev (K3 of the previous scan) is done
     cudaEvent_t ev[EV_COUNT];
     bool profiling = false;
+    bool zero_copy = true;                // host clouds: K1 reads pinned memory directly (else chunked DMA)
     bool prof_process = false, prof_combine = false;
     int sm_count = 148;
+    int grid_index = 0, grid_codes = 0, grid_cells = 0, grid_gather = 0;   // resident grids (set at create)
     GvomStats stats{};
     std::mutex mu;
 };
@@ -143,6 +155,7 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
         s.minh = d.take<float>(cap);
         s.cell_voxel = d.take<int>(cap);
         s.counter = d.take<int>(4);
+        s.gmask = d.take<unsigned>(V / 256 + 2);
     }
     for (auto& c : h->comb) {
         c.index_map = d.take<int>(V);
@@ -153,10 +166,13 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
         c.eig = d.take<float>(ccap * 3);
         c.cell_voxel = d.take<int>(ccap);
         c.counter = d.take<int>(4);
+        c.gmask = d.take<unsigned>(V / 256 + 2);
     }
     h->maps = d.take<double>(6 * S2);
     h->imaps = d.take<int>(3 * S2 + 2 * S2);
     h->rough_out = reinterpret_cast<double*>(h->imaps ? h->imaps + 3 * S2 : nullptr);
+    h->col_minz = d.take<int>(2 * S2);
+    h->known = d.take<unsigned>(2 * (size_t)p.xy_size * ((p.xy_size + 31) / 32));
     h->debug_dev = d.take<float>(std::max(ccap * 8, S2 * 10));
     h->flags = d.take<int>(8);
     h->cacc = d.take<double>(ccap * 10);
@@ -196,9 +212,22 @@ void fill_sizes(GvomHandle* h, const GvomParams* p, int64_t max_points, int64_t 
     d.r2 = p->robot_radius * p->robot_radius; d.ground_to_lidar = p->ground_to_lidar_height;
     d.S = p->xy_size; d.Z = p->z_size; d.rx = p->xy_eigen_dist; d.rz = p->z_eigen_dist;
     d.V = h->V;
+    d.lgS = -1;
+    for (int b = 0; b < 31; ++b) if ((1 << b) == p->xy_size) d.lgS = b;
 }
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// grid of a grid-stride kernel: exactly the blocks that are resident at once (one wave, no tail)
+template <typename K>
+int resident_grid(K kernel, int threads, int sm_count, size_t smem = 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 2;
+    }
+    return per_sm * sm_count;
+}
 
 bool is_pinned_or_device(const void* p, bool* is_device) {
     cudaPointerAttributes a;
@@ -216,12 +245,15 @@ void rec(GvomHandle* h, int e, cudaStream_t st) {
 // previous combined map (gvom.py:242-257).  `org` = combined origin (voxels).
 void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs* A) {
     A->n = 0;
+    A->use_masks = 1;
     for (auto& s : h->slots) {
         if (!s.valid) continue;
         SlotRef& r = A->s[A->n++];
         r.map = s.index_map; r.metrics = s.metrics; r.hit = s.hit; r.total = s.total; r.minh = s.minh;
         r.dx = (int)(org[0] - s.origin[0]); r.dy = (int)(org[1] - s.origin[1]); r.dz = (int)(org[2] - s.origin[2]);
         r.is_prev = 0;
+        r.gmask = s.has_gmask ? s.gmask : nullptr;
+        if (!r.gmask) A->use_masks = 0;
     }
     Combined& pc = h->comb[h->cur];
     if (with_prev && pc.valid) {
@@ -229,6 +261,8 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
         r.map = pc.index_map; r.metrics = pc.metrics; r.hit = pc.hit; r.total = pc.total; r.minh = pc.minh;
         r.dx = (int)(org[0] - pc.origin[0]); r.dy = (int)(org[1] - pc.origin[1]); r.dz = (int)(org[2] - pc.origin[2]);
         r.is_prev = 1;
+        r.gmask = pc.has_gmask ? pc.gmask : nullptr;
+        if (!r.gmask) A->use_masks = 0;
     }
 }
 
@@ -239,10 +273,16 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
     double* height = h->maps; double* inferred = h->maps + S2; double* rough = h->rough_out;
     double* xs = h->maps + 3 * (size_t)S2; double* ys = h->maps + 4 * (size_t)S2; double* guessed = h->maps + 5 * (size_t)S2;
     int* pos = h->imaps; int* neg = h->imaps + S2; int* vis = h->imaps + 2 * (size_t)S2;
-    k_column_maps<<<blocks_for(S2, 256), 256, 0, st>>>(c.index_map, c.minh, c.origin[0], c.origin[1], c.origin[2],
-                                                       h->ego[0], h->ego[1], h->ego[2], h->dp, height, inferred);
-    k_surface_maps<<<blocks_for(S2, 128), 128, 0, st>>>(c.index_map, c.hit, c.total, height, inferred, c.origin[2],
-                                                        h->dp, rough, xs, ys, guessed, pos, neg, vis);
+    const int W = (h->p.xy_size + 31) / 32;
+    unsigned* known = h->known; unsigned* knownT = h->known + (size_t)h->p.xy_size * W;
+    k_column_maps<<<dim3(W, W), 1024, 0, st>>>(c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
+                                               c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, height, inferred, known, knownT,
+                                               h->flags + 1, c.counter);
+    const size_t mask_bytes = 2 * (size_t)h->p.xy_size * W * sizeof(unsigned);
+    const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
+    k_surface_maps<<<blocks_for(S2, 256), 256, in_smem ? mask_bytes : 0, st>>>(c.index_map, c.hit, c.total, height, inferred, known, knownT,
+                                                                            c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
+                                                                            in_smem, h->col_minz, h->flags + 1);
     h->stats.kernel_launches += 2;
     rec(h, EV_MAPS, st);
     CUDA_TRY(cudaGetLastError());
@@ -328,19 +368,34 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
     }
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_proc_done, cudaEventDisableTiming);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming);
     for (int i = 0; i < EV_COUNT && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
     int sms = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (sms > 0) h->sm_count = sms;
+    {
+        const bool v8 = p->xy_size % 8 == 0, v4 = h->V % 4 == 0, s4 = p->xy_size % 4 == 0;
+        h->grid_index = v8 ? resident_grid(k_build_index<8>, 256, h->sm_count)
+                           : v4 ? resident_grid(k_build_index<4>, 256, h->sm_count) : resident_grid(k_build_index<1>, 256, h->sm_count);
+        h->grid_codes = v8 ? resident_grid(k_merge_codes<8>, 256, h->sm_count)
+                           : s4 ? resident_grid(k_merge_codes<4>, 256, h->sm_count) : resident_grid(k_merge_codes<1>, 256, h->sm_count);
+        h->grid_cells = resident_grid(k_merge_cells, 128, h->sm_count);
+        h->grid_gather = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics<1, 1>, 256, h->sm_count)
+                                                                         : resident_grid(k_gather_metrics<-1, -1>, 256, h->sm_count);
+    }
     // dense grids are kept zero between scans (k_build_index re-zeroes what it reads)
     if (e == cudaSuccess) e = cudaMemsetAsync(h->hit_grid, 0, sizeof(int) * (size_t)h->V, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->total_grid, 0, sizeof(int) * (size_t)h->V, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->flags, 0, sizeof(int) * 8, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->col_minz, 0x7f, sizeof(int) * 2 * (size_t)h->S2, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
         delete h;
         return fail(GVOM_ECUDA, std::string("gvom_create: ") + cudaGetErrorString(e));
     }
+    if (const char* m = getenv("GVOM_H2D")) h->zero_copy = std::string(m) != "dma";
     h->active = h->stream;
     *out = h;
     return GVOM_OK;
@@ -352,6 +407,9 @@ int gvom_destroy(GvomHandle* h) {
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(h->ev[i]);
     cudaEventDestroy(h->ev_stage);
+    cudaEventDestroy(h->ev_proc_done);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]);
+    cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
     delete h;
     return GVOM_OK;
@@ -386,64 +444,116 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
     for (int k = 0; k < 12; ++k) tf.m[k] = T ? T[k] : 0.0;
 
     rec(h, EV_START, st);
-    // ---- input staging
+    // ---- input staging + K1.  Host clouds are moved in chunks on a copy stream and every chunk
+    // is ray-cast as soon as it has landed, so K1 hides behind the PCIe transfer.
     const size_t esz = dtype == GVOM_F32 ? 4 : 8;
-    const size_t bytes = (size_t)n * stride * esz;
+    const size_t row = (size_t)stride * esz;
     const void* src = points;
-    if (n > 0) {
-        if (mem == GVOM_DEVICE) {
-            if (stride == 4 && ((uintptr_t)points & 15)) {   // vector loads need 16-byte alignment
-                CUDA_TRY(cudaMemcpyAsync(h->stage_dev, points, bytes, cudaMemcpyDeviceToDevice, st));
-                src = h->stage_dev;
-            }
-        } else {
-            bool dev = false;
-            if (is_pinned_or_device(points, &dev)) {
-                CUDA_TRY(cudaMemcpyAsync(h->stage_dev, points, bytes, cudaMemcpyDefault, st));
-                CUDA_TRY(cudaEventRecord(h->ev_stage, st));
-                // the caller may reuse its buffer as soon as we return
-                CUDA_TRY(cudaEventSynchronize(h->ev_stage));
-            } else {
-                if (h->stage_busy) CUDA_TRY(cudaEventSynchronize(h->ev_stage));
-                memcpy(h->stage_host, points, bytes);
-                CUDA_TRY(cudaMemcpyAsync(h->stage_dev, h->stage_host, bytes, cudaMemcpyHostToDevice, st));
-                CUDA_TRY(cudaEventRecord(h->ev_stage, st));
-                h->stage_busy = true;
-            }
+    const int nb = blocks_for(n, 256);
+    Xform tf_moments = tf;                               // transform K3 applies (none after a zero-copy K1)
+    auto launch_k1 = [&](const void* base, int64_t first, int64_t count, void* world_out) {
+        if (count <= 0) return;
+        const char* p0 = static_cast<const char*>(base) + (size_t)first * row;
+        const int blocks = blocks_for(count, 256);
+        if (dtype == GVOM_F32)
+            k_voxelize_raycast<float><<<blocks, 256, 0, st>>>((const float*)p0, stride, (int)count, tf, fr, h->dp, h->hit_grid,
+                                                              h->total_grid, (float*)world_out);
+        else
+            k_voxelize_raycast<double><<<blocks, 256, 0, st>>>((const double*)p0, stride, (int)count, tf, fr, h->dp, h->hit_grid,
+                                                               h->total_grid, (double*)world_out);
+        h->stats.kernel_launches++;
+    };
+    bool wait_for_input = false;
+    if (n > 0 && mem == GVOM_DEVICE) {
+        if (stride == 4 && ((uintptr_t)points & 15)) {   // vector loads need 16-byte alignment
+            CUDA_TRY(cudaMemcpyAsync(h->stage_dev, points, (size_t)n * row, cudaMemcpyDeviceToDevice, st));
             src = h->stage_dev;
         }
+        rec(h, EV_H2D, st);
+        launch_k1(src, 0, n, nullptr);
+    } else if (n > 0) {
+        bool dev = false;
+        const bool pinned = is_pinned_or_device(points, &dev);
+        if (!pinned && h->stage_busy) CUDA_TRY(cudaEventSynchronize(h->ev_stage));   // stage_host still being read
+        void* mapped = nullptr;
+        if (h->zero_copy) {
+            const void* hostp = points;
+            if (!pinned) { memcpy(h->stage_host, points, (size_t)n * row); hostp = h->stage_host; }
+            if (cudaHostGetDevicePointer(&mapped, const_cast<void*>(hostp), 0) != cudaSuccess) { cudaGetLastError(); mapped = nullptr; }
+            if (mapped && ((uintptr_t)mapped & 15)) mapped = nullptr;   // the staged loads are 128-bit
+        }
+        if (mapped) {
+            // zero-copy: one kernel streams the cloud over PCIe while it ray-casts; no DMA op, no staging pass
+            rec(h, EV_H2D, st);
+            launch_k1(mapped, 0, n, h->stage_dev);
+            CUDA_TRY(cudaEventRecord(h->ev_stage, st));
+            tf_moments.enabled = 0;
+        } else {
+            // chunked DMA on a copy stream; every chunk is ray-cast as soon as it has landed
+            const int nchunks = n >= 65536 ? 4 : 1;
+            const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~int64_t(255);
+            CUDA_TRY(cudaEventRecord(h->ev_proc_done, st));   // stage_dev: previous scan's readers first
+            CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_proc_done, 0));
+            for (int c = 0; c < nchunks; ++c) {
+                const int64_t first = c * per, count = std::min<int64_t>(per, n - first);
+                if (count <= 0) break;
+                const size_t off = (size_t)first * row, bytes = (size_t)count * row;
+                const char* from = static_cast<const char*>(points) + off;
+                if (!pinned) { memcpy(h->stage_host + off, from, bytes); from = h->stage_host + off; }
+                CUDA_TRY(cudaMemcpyAsync(h->stage_dev + off, from, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+                CUDA_TRY(cudaEventRecord(h->ev_chunk[c], h->copy_stream));
+                CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
+                launch_k1(h->stage_dev, first, count, nullptr);
+            }
+            CUDA_TRY(cudaEventRecord(h->ev_stage, h->copy_stream));
+            rec(h, EV_H2D, st);
+        }
+        h->stage_busy = !pinned;
+        wait_for_input = pinned;                         // the caller may reuse its buffer when we return
+        src = h->stage_dev;
+    } else {
+        rec(h, EV_H2D, st);
     }
-    rec(h, EV_H2D, st);
 
     Slot& s = h->slots[h->buffer_index];
     const int cap = (int)h->cap;
-    const int nb = blocks_for(n, 256);
-    CUDA_TRY(cudaMemsetAsync(s.counter, 0, sizeof(int), st));
-    if (n > 0) {
-        if (dtype == GVOM_F32)
-            k_voxelize_raycast<float><<<nb, 256, 0, st>>>((const float*)src, stride, (int)n, tf, fr, h->dp, h->hit_grid, h->total_grid);
-        else
-            k_voxelize_raycast<double><<<nb, 256, 0, st>>>((const double*)src, stride, (int)n, tf, fr, h->dp, h->hit_grid, h->total_grid);
-        h->stats.kernel_launches++;
-    }
     rec(h, EV_RAYCAST, st);
-    k_build_index<<<h->sm_count * 8, 256, 0, st>>>(h->hit_grid, h->total_grid, s.index_map, s.counter, s.hit, s.total,
-                                                  s.cell_voxel, h->acc, s.minh, h->V, cap);
+    if (h->p.xy_size % 8 == 0) {
+        k_build_index<8><<<h->grid_index, 256, 0, st>>>(h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
+                                                         s.cell_voxel, h->acc, s.minh, h->V, cap, s.gmask);
+        s.has_gmask = true;
+    } else {
+        if (h->V % 4 == 0)
+            k_build_index<4><<<h->grid_index, 256, 0, st>>>(h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
+                                                             s.cell_voxel, h->acc, s.minh, h->V, cap, nullptr);
+        else
+            k_build_index<1><<<h->grid_index, 256, 0, st>>>(h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
+                                                             s.cell_voxel, h->acc, s.minh, h->V, cap, nullptr);
+        s.has_gmask = false;
+    }
     h->stats.kernel_launches++;
     rec(h, EV_INDEX, st);
-    if (n > 0) {
+    {   // always launched (>= 1 block): thread 0 also publishes the slot's cell count
+        const int mb = nb > 0 ? nb : 1;
         if (dtype == GVOM_F32)
-            k_moments<float><<<nb, 256, 0, st>>>((const float*)src, stride, (int)n, tf, fr, h->dp, s.index_map, h->acc, s.minh);
+            k_moments<float><<<mb, 256, 0, st>>>((const float*)src, stride, (int)n, tf_moments, fr, h->dp, s.index_map, h->acc, s.minh,
+                                                 h->flags, s.counter);
         else
-            k_moments<double><<<nb, 256, 0, st>>>((const double*)src, stride, (int)n, tf, fr, h->dp, s.index_map, h->acc, s.minh);
+            k_moments<double><<<mb, 256, 0, st>>>((const double*)src, stride, (int)n, tf_moments, fr, h->dp, s.index_map, h->acc, s.minh,
+                                                  h->flags, s.counter);
         h->stats.kernel_launches++;
     }
     rec(h, EV_MOMENTS, st);
-    k_gather_metrics<<<h->sm_count * 4, 128, 0, st>>>(s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap);
+    if (h->p.xy_eigen_dist == 1 && h->p.z_eigen_dist == 1)
+        k_gather_metrics<1, 1><<<h->grid_gather, 256, 0, st>>>(s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+    else
+        k_gather_metrics<-1, -1><<<h->grid_gather, 256, 0, st>>>(s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
     h->stats.kernel_launches++;
     rec(h, EV_GATHER, st);
     CUDA_TRY(cudaGetLastError());
     h->prof_process = h->profiling;
+    // a caller-owned host buffer may be reused as soon as we return: wait for the transfer (not the kernels)
+    if (wait_for_input) CUDA_TRY(cudaEventSynchronize(h->ev_stage));
 
     // gvom.py:198-216
     for (int k = 0; k < 3; ++k) s.origin[k] = fr.origin[k];
@@ -468,14 +578,23 @@ int gvom_combine_maps(GvomHandle* h, double origin[3], int32_t* positive, int32_
     build_sources(h, newest.origin, true, &A);
     Combined& c = h->comb[1 - h->cur];
     for (int k = 0; k < 3; ++k) c.origin[k] = newest.origin[k];   // gvom.py:229
-    CUDA_TRY(cudaMemsetAsync(c.counter, 0, sizeof(int), st));
-    k_merge_codes<<<h->sm_count * 8, 256, 0, st>>>(A, c.index_map, c.counter, c.cell_voxel, h->dp, (int)h->ccap);
+    // flags[1] (running cell counter) and the column minima are left clean by the previous combine's C4
+    {
+        int* col = h->col_minz;
+        if (h->p.xy_size % 8 == 0)
+            k_merge_codes<8><<<h->grid_codes, 256, 0, st>>>(A, c.index_map, h->flags + 1, c.cell_voxel, col, col + h->S2, h->dp, (int)h->ccap, c.gmask);
+        else if (h->p.xy_size % 4 == 0)
+            k_merge_codes<4><<<h->grid_codes, 256, 0, st>>>(A, c.index_map, h->flags + 1, c.cell_voxel, col, col + h->S2, h->dp, (int)h->ccap, nullptr);
+        else
+            k_merge_codes<1><<<h->grid_codes, 256, 0, st>>>(A, c.index_map, h->flags + 1, c.cell_voxel, col, col + h->S2, h->dp, (int)h->ccap, nullptr);
+    }
     rec(h, EV_CODES, st);
-    k_merge_cells<<<h->sm_count * 4, 128, 0, st>>>(A, c.counter, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
+    k_merge_cells<<<h->grid_cells, 128, 0, st>>>(A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
                                                   h->dp, (int)h->ccap);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 2;
     h->prof_combine = h->profiling;
+    c.has_gmask = h->p.xy_size % 8 == 0;
     const int r = run_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st);
     if (r != GVOM_OK) return r;
     c.valid = true;                                          // gvom.py:302-308
@@ -715,16 +834,16 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     }
     // the per-scan accumulator block doubles as the per-cell raw-moment scratch when it is big enough
     double* cacc = h->cacc;
-    CUDA_TRY(cudaMemsetAsync(c.counter, 0, sizeof(int), st));
-    k_finish_codes<<<h->sm_count * 8, 256, 0, st>>>(code_grid_dev, prev, has_prev, c.index_map, c.counter, c.cell_voxel, cacc,
-                                                   c.hit, c.total, c.minh, h->dp, (int)h->ccap);
+    k_finish_codes<<<h->sm_count * 8, 256, 0, st>>>(code_grid_dev, prev, has_prev, c.index_map, h->flags + 1, c.cell_voxel, cacc,
+                                                   c.hit, c.total, c.minh, h->col_minz, h->col_minz + h->S2, h->dp, (int)h->ccap);
     k_scatter_records<<<h->sm_count * 4, 256, 0, st>>>(records_dev, record_counts_dev, nranks, record_capacity, c.index_map,
                                                       cacc, c.hit, c.total, c.minh);
-    k_finish_cells<<<h->sm_count * 4, 128, 0, st>>>(prev, has_prev, c.counter, c.cell_voxel, cacc, c.hit, c.total, c.minh,
+    k_finish_cells<<<h->sm_count * 4, 128, 0, st>>>(prev, has_prev, h->flags + 1, c.cell_voxel, cacc, c.hit, c.total, c.minh,
                                                    c.metrics, c.eig, h->dp, (int)h->ccap);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 3;
     h->prof_combine = h->profiling;
+    c.has_gmask = false;                                     // k_finish_codes writes no group mask
     const int r = run_maps_and_output(h, c, origin_out, positive, negative, roughness, visibility, out_mem, st);
     if (r != GVOM_OK) return r;
     c.valid = true;

@@ -29,6 +29,7 @@ struct DevParams {
     double pos_thr, neg_thr, slope_thr, robot_height, r2, ground_to_lidar;
     int S, Z;                 // xy_size, z_size
     int rx, rz;               // xy_eigen_dist, z_eigen_dist
+    int lgS;                  // log2(S) if S is a power of two, else -1
     long long V;              // S*S*Z
 };
 
@@ -76,10 +77,20 @@ __device__ __forceinline__ void load3<double>(const double* __restrict__ pts, in
 }
 
 template <typename T>
+__device__ __forceinline__ bool world_from_raw(T p0, T p1, T p2, const Xform& tf, double min_d2,
+                                               double& wx, double& wy, double& wz);
+
+template <typename T>
 __device__ __forceinline__ bool load_world(const T* __restrict__ pts, int stride, long long i, const Xform& tf,
                                            double min_d2, double& wx, double& wy, double& wz) {
     T p0, p1, p2;
     load3<T>(pts, stride, i, p0, p1, p2);
+    return world_from_raw<T>(p0, p1, p2, tf, min_d2, wx, wy, wz);
+}
+
+template <typename T>
+__device__ __forceinline__ bool world_from_raw(T p0, T p1, T p2, const Xform& tf, double min_d2,
+                                               double& wx, double& wy, double& wz) {
     if (tf.enabled) {
         const double a0 = (double)p0, a1 = (double)p1, a2 = (double)p2;
         double o[3];
@@ -121,9 +132,9 @@ __device__ __forceinline__ bool load_world(const T* __restrict__ pts, int stride
 //   * aggregation changes who issues the atomic, never the per-ray arithmetic.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 k_voxelize_raycast(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevParams P,
-                   int* __restrict__ hit, int* __restrict__ total) {
+                   int* __restrict__ hit, int* __restrict__ total, T* __restrict__ world_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const double ox = fr.origin[0], oy = fr.origin[1], oz = fr.origin[2];
@@ -131,7 +142,32 @@ k_voxelize_raycast(const T* __restrict__ pts, int stride, int n, Xform tf, Frame
 
     double wx = 0, wy = 0, wz = 0;
     bool ok = false;
-    if (i < n) ok = load_world<T>(pts, stride, i, tf, P.min_d2, wx, wy, wz);
+    if (world_out) {
+        // zero-copy mode: pts is pinned HOST memory, read over PCIe exactly once.  The block's
+        // contiguous chunk (256 points) is fetched with 128-bit coalesced loads into shared memory
+        // (every byte requested once, full-width PCIe reads), then each thread picks its point.
+        // The transformed point (in the cloud's dtype, as the reference stores it back,
+        // gvom.py:1136-1138) is kept in HBM for the moment pass.
+        __shared__ uint4 chunk[256 * 4 * sizeof(double) / 16];
+        const long long first = (long long)blockIdx.x * blockDim.x;
+        const int cnt = (int)min((long long)blockDim.x, (long long)n - first);
+        const size_t bytes = (size_t)cnt * stride * sizeof(T);
+        const char* g = reinterpret_cast<const char*>(pts + first * stride);
+        const int n16 = (int)(bytes >> 4);
+        for (int k = threadIdx.x; k < n16; k += blockDim.x)
+            chunk[k] = __ldg(reinterpret_cast<const uint4*>(g) + k);
+        if (threadIdx.x < (int)(bytes & 15))                  // tail bytes (none when the chunk is full)
+            reinterpret_cast<char*>(chunk)[(n16 << 4) + threadIdx.x] = g[(n16 << 4) + threadIdx.x];
+        __syncthreads();
+        if (i < n) {
+            const T* q = reinterpret_cast<const T*>(chunk) + (long long)threadIdx.x * stride;
+            ok = world_from_raw<T>(q[0], q[1], q[2], tf, P.min_d2, wx, wy, wz);
+            T* w = world_out + (long long)i * stride;
+            w[0] = (T)wx; w[1] = (T)wy; w[2] = (T)wz;
+        }
+    } else if (i < n) {
+        ok = load_world<T>(pts, stride, i, tf, P.min_d2, wx, wy, wz);
+    }
 
     // ---- hit (gvom.py:1153-1171)
     double ex = 0, ey = 0, ez = 0;
@@ -179,32 +215,29 @@ k_voxelize_raycast(const T* __restrict__ pts, int stride, int n, Xform tf, Frame
         }
     }
 
-    // ---- DDA (gvom.py:1208-1231), warp-synchronous.
+    // ---- DDA (gvom.py:1208-1231), warp-synchronous and branch-free.
     // The reference evaluates floor(float64(pt) - origin) per axis.  origin is integral and
     // float64(pt) - origin is exact (24-bit pt, |origin| < 2^31), so floor(pt - origin) ==
     // floorf(pt) - origin exactly: the loop runs on float32/int32 only, plus the float64
-    // length accumulation whose sequential rounding decides the trip count.
+    // length accumulation whose sequential rounding decides the trip count.  The ego voxel is
+    // the grid centre and a ray ends as soon as it leaves the grid, so pt stays within one
+    // voxel of the grid and the float->int conversions cannot overflow.
+    // Finished lanes keep stepping with zero increments and take a unique negative key in the
+    // match, so the only branch in the loop is the loop itself.
     const int iox = (int)ox, ioy = (int)oy, ioz = (int)oz;
-    while (__any_sync(FULL, active)) {
-        bool inside = false;
-        int vv = 0;
-        if (active) {
-            px = __fadd_rn(px, ix); py = __fadd_rn(py, iy); pz = __fadd_rn(pz, iz);
-            const float bound = 1.0e9f;
-            if (fabsf(px) < bound && fabsf(py) < bound && fabsf(pz) < bound) {
-                const int x = (int)floorf(px) - iox, y = (int)floorf(py) - ioy, z = (int)floorf(pz) - ioz;
-                inside = ((unsigned)x < (unsigned)P.S) && ((unsigned)y < (unsigned)P.S) && ((unsigned)z < (unsigned)P.Z);
-                vv = x + (y + z * P.S) * P.S;
-            }
-            if (!inside) active = false;                  // left the grid: ray ends
-        }
-        const unsigned ms = __ballot_sync(FULL, inside);
-        if (inside) {
-            const unsigned peers = __match_any_sync(ms, vv);
-            if (lane == __ffs(peers) - 1) atomicAdd(total + vv, __popc(peers));
-            length = __dadd_rn(length, dlen);
-            active = length < lim;
-        }
+    if (!active) { ix = 0.f; iy = 0.f; iz = 0.f; dlen = 0.0; }
+    unsigned any = __ballot_sync(FULL, active);
+    while (any) {
+        px = __fadd_rn(px, ix); py = __fadd_rn(py, iy); pz = __fadd_rn(pz, iz);
+        const int x = __float2int_rd(px) - iox, y = __float2int_rd(py) - ioy, z = __float2int_rd(pz) - ioz;
+        const bool inside = active && ((unsigned)x < (unsigned)P.S) && ((unsigned)y < (unsigned)P.S) &&
+                            ((unsigned)z < (unsigned)P.Z);
+        const int vv = x + (y + z * P.S) * P.S;
+        const unsigned peers = __match_any_sync(FULL, inside ? vv : ~lane);
+        if (inside && lane == __ffs(peers) - 1) atomicAdd(total + vv, __popc(peers));
+        length = __dadd_rn(length, dlen);
+        active = inside && (length < lim);
+        any = __ballot_sync(FULL, active);
     }
 }
 
@@ -214,41 +247,94 @@ k_voxelize_raycast(const T* __restrict__ pts, int stride, int n, Xform tf, Frame
 // stays on the device and compact arrays are sized for the worst case.  Also
 // re-zeroes the dense grids for the next scan (replaces the three fill launches
 // of gvom.py:125-131) and initialises the per-cell accumulators
-// (gvom.py:1079-1085).  Compact ids are allotted per warp (ballot + one atomic).
+// (gvom.py:1079-1085).  Compact ids are allotted per warp (ballots + one atomic).
+// VEC = 4: 128-bit loads/stores, four voxels per thread (needs V % 4 == 0).
 // ---------------------------------------------------------------------------
+template <int VEC>
 __global__ void __launch_bounds__(256)
 k_build_index(int* __restrict__ hit, int* __restrict__ total, int* __restrict__ index_map,
               int* __restrict__ counter, int* __restrict__ hit_c, int* __restrict__ total_c,
               int* __restrict__ cell_voxel, double* __restrict__ acc, float* __restrict__ minh,
-              long long V, int cap) {
+              long long V, int cap, unsigned* __restrict__ gmask) {
+    constexpr int U = 2;                                // items in flight per thread
     const int lane = threadIdx.x & 31;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    const long long Vp = (V + 31) & ~31LL;
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < Vp; v += step) {
-        int h = 0, t = 0;
-        if (v < V) { h = hit[v]; t = total[v]; }
-        const bool occ = h > 0;
-        const unsigned m = __ballot_sync(FULL, occ);
-        int base = 0;
-        if (m) {
-            if (lane == 0) base = atomicAdd(counter, __popc(m));
-            base = __shfl_sync(FULL, base, 0);
-        }
-        if (v < V) {
-            int code = -t - 1;
-            if (occ) {
-                const int id = base + __popc(m & ((1u << lane) - 1u));
-                if (id < cap) {
-                    code = id;
-                    hit_c[id] = h; total_c[id] = t; cell_voxel[id] = (int)v; minh[id] = 1.0f;
-                    double* a = acc + (long long)id * ACC;
+    const unsigned lt = (1u << lane) - 1u;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long NQ = V / VEC;                       // items of VEC voxels
+    const long long NQp = (NQ + 31) & ~31LL;
+    for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < NQp; q0 += nthreads * U) {
+        int h[U][VEC], t[U][VEC];
 #pragma unroll
-                    for (int k = 0; k < ACC; ++k) a[k] = 0.0;
+        for (int u = 0; u < U; ++u) {
+            const long long q = q0 + u * nthreads;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { h[u][j] = 0; t[u][j] = 0; }
+            if (q < NQ) {
+                if (VEC >= 4) {
+#pragma unroll
+                    for (int g = 0; g < VEC / 4; ++g) {
+                        const int4 hv = reinterpret_cast<const int4*>(hit)[q * (VEC / 4) + g];
+                        const int4 tv = reinterpret_cast<const int4*>(total)[q * (VEC / 4) + g];
+                        h[u][4 * g] = hv.x; h[u][4 * g + (VEC > 1 ? 1 : 0)] = hv.y; h[u][4 * g + (VEC > 2 ? 2 : 0)] = hv.z; h[u][4 * g + (VEC > 3 ? 3 : 0)] = hv.w;
+                        t[u][4 * g] = tv.x; t[u][4 * g + (VEC > 1 ? 1 : 0)] = tv.y; t[u][4 * g + (VEC > 2 ? 2 : 0)] = tv.z; t[u][4 * g + (VEC > 3 ? 3 : 0)] = tv.w;
+                    }
+                } else {
+                    h[u][0] = hit[q]; t[u][0] = total[q];
                 }
             }
-            index_map[v] = code;
-            if (t != 0) total[v] = 0;
-            if (h != 0) hit[v] = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long q = q0 + u * nthreads;
+            if (q >= NQp) break;                        // warp-uniform: NQp and q0 are multiples of 32 apart
+            unsigned m[VEC];
+            int nocc = 0;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { m[j] = __ballot_sync(FULL, h[u][j] > 0); nocc += __popc(m[j]); }
+            int base = 0;
+            if (nocc) {
+                if (lane == 0) base = atomicAdd(counter, nocc);
+                base = __shfl_sync(FULL, base, 0);
+            }
+            bool known_any = false;
+            if (q < NQ) {
+                int code[VEC];
+                bool anyh = false, anyt = false;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    code[j] = -t[u][j] - 1;
+                    if (h[u][j] > 0) {
+                        const int id = base + __popc(m[j] & lt);
+                        if (id < cap) {
+                            code[j] = id;
+                            hit_c[id] = h[u][j]; total_c[id] = t[u][j]; cell_voxel[id] = (int)(q * VEC + j); minh[id] = 1.0f;
+                            double2* a = reinterpret_cast<double2*>(acc + (long long)id * ACC);
+#pragma unroll
+                            for (int k = 0; k < ACC / 2; ++k) a[k] = make_double2(0.0, 0.0);
+                        }
+                    }
+                    base += __popc(m[j]);
+                    anyh |= h[u][j] != 0; anyt |= t[u][j] != 0;
+                }
+                if (VEC >= 4) {
+#pragma unroll
+                    for (int g = 0; g < VEC / 4; ++g) {
+                        reinterpret_cast<int4*>(index_map)[q * (VEC / 4) + g] =
+                            make_int4(code[4 * g], code[4 * g + (VEC > 1 ? 1 : 0)], code[4 * g + (VEC > 2 ? 2 : 0)], code[4 * g + (VEC > 3 ? 3 : 0)]);
+                        if (anyt) reinterpret_cast<int4*>(total)[q * (VEC / 4) + g] = make_int4(0, 0, 0, 0);
+                        if (anyh) reinterpret_cast<int4*>(hit)[q * (VEC / 4) + g] = make_int4(0, 0, 0, 0);
+                    }
+                } else {
+                    index_map[q] = code[0];
+                    if (anyt) total[q] = 0;
+                    if (anyh) hit[q] = 0;
+                }
+                known_any = anyt;                       // a voxel is known iff a ray touched it (total > 0)
+            }
+            if (VEC == 8) {                             // one bit per 8-voxel group: "anything known in here"
+                const unsigned w = __ballot_sync(FULL, known_any);
+                if (lane == 0 && q < NQ) gmask[q >> 5] = w;
+            }
         }
     }
 }
@@ -260,40 +346,82 @@ k_build_index(int* __restrict__ hit, int* __restrict__ total, int* __restrict__ 
 // The reference scatters every point into every occupied voxel of its
 // (2rx+1)^2(2rz+1) neighbourhood, twice (16.6 M float64 atomics per OS1-128 scan).
 // Here a point only adds its raw first/second moments (about its own voxel's
-// centre) to its OWN cell -- 10 atomics -- and K4 gathers the neighbourhood.
+// centre) to its OWN cell, and K4 gathers the neighbourhood.  Consecutive points
+// of a spinning lidar mostly fall into the same voxel, so each warp first reduces
+// runs of equal voxel id with a segmented shuffle scan and only the head lane of a
+// run issues the 10 float64 REDs (+1 min): ~5x fewer atomics again.
 // Points whose own voxel lies outside the grid still reach in-grid neighbours in
 // the reference (gvom.py:1262-1279); they are rare and are scattered directly into
 // the neighbour's "apron" accumulators.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ double seg_add(double v, int offset, bool take) {
+    const double t = __shfl_down_sync(FULL, v, offset);
+    return take ? v + t : v;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_moments(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevParams P,
-          const int* __restrict__ index_map, double* __restrict__ acc, float* __restrict__ minh) {
+          const int* __restrict__ index_map, double* __restrict__ acc, float* __restrict__ minh,
+          const int* __restrict__ scratch_count, int* __restrict__ slot_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double wx, wy, wz;
-    if (!load_world<T>(pts, stride, i, tf, P.min_d2, wx, wy, wz)) return;
-    const double fx = __dsub_rn(__ddiv_rn(wx, P.xy_res), fr.origin[0]);
-    const double fy = __dsub_rn(__ddiv_rn(wy, P.xy_res), fr.origin[1]);
-    const double fz = __dsub_rn(__ddiv_rn(wz, P.z_res), fr.origin[2]);
-    const double bx = floor(fx), by = floor(fy), bz = floor(fz);
-    const double dS = (double)P.S, dZ = (double)P.Z;
-    const bool inb = (bx >= 0.0) && (bx < dS) && (by >= 0.0) && (by < dS) && (bz >= 0.0) && (bz < dZ);
+    const int lane = threadIdx.x & 31;
+    if (i == 0) *slot_count = *scratch_count;             // K2's running counter -> the slot's cell count
+    double wx = 0, wy = 0, wz = 0;
+    bool ok = false;
+    if (i < n) ok = load_world<T>(pts, stride, i, tf, P.min_d2, wx, wy, wz);
+    double fx = 0, fy = 0, fz = 0, bx = 0, by = 0, bz = 0;
+    bool inb = false;
+    if (ok) {
+        fx = __dsub_rn(__ddiv_rn(wx, P.xy_res), fr.origin[0]);
+        fy = __dsub_rn(__ddiv_rn(wy, P.xy_res), fr.origin[1]);
+        fz = __dsub_rn(__ddiv_rn(wz, P.z_res), fr.origin[2]);
+        bx = floor(fx); by = floor(fy); bz = floor(fz);
+        const double dS = (double)P.S, dZ = (double)P.Z;
+        inb = (bx >= 0.0) && (bx < dS) && (by >= 0.0) && (by < dS) && (bz >= 0.0) && (bz < dZ);
+    }
+    // ---- own-voxel accumulation, run-reduced within the warp
+    int id = -1 - lane;                                   // distinct negative keys: never equal to a neighbour
+    double q[10];
+    float lzf = 1.0f;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) q[k] = 0.0;
     if (inb) {
         const int v = (int)bx + ((int)by + (int)bz * P.S) * P.S;
-        const int id = index_map[v];
-        if (id < 0) return;                               // only on compact-capacity overflow
-        const double lz = __dsub_rn(fz, bz);
-        const double qx = (fx - bx) - 0.5, qy = (fy - by) - 0.5, qz = lz - 0.5;
+        const int c = index_map[v];
+        if (c >= 0) {                                     // < 0 only on compact-capacity overflow
+            id = c;
+            const double lz = __dsub_rn(fz, bz);
+            const double qx = (fx - bx) - 0.5, qy = (fy - by) - 0.5, qz = lz - 0.5;
+            q[0] = qx; q[1] = qy; q[2] = qz;
+            q[3] = qx * qx; q[4] = qx * qy; q[5] = qx * qz; q[6] = qy * qy; q[7] = qy * qz; q[8] = qz * qz;
+            q[9] = 1.0;
+            lzf = (float)lz;                              // min height: float32 of the in-voxel z fraction
+        }
+    }
+    const int id_up = __shfl_up_sync(FULL, id, 1);
+    const bool head = (lane == 0) || (id_up != id);
+    // distance (in lanes) to the end of my run = number of following lanes with the same id
+    const unsigned heads = __ballot_sync(FULL, head);
+    const unsigned after = heads & ~((2u << lane) - 1u);  // heads strictly above my lane
+    const int run_end = after ? (__ffs(after) - 2) : 31;  // last lane of my run
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const bool take = (lane + off) <= run_end;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) q[k] = seg_add(q[k], off, take);
+        const float t = __shfl_down_sync(FULL, lzf, off);
+        if (take) lzf = fminf(lzf, t);
+    }
+    if (head && id >= 0) {
         double* a = acc + (long long)id * ACC;
-        atomicAdd(a + 0, qx); atomicAdd(a + 1, qy); atomicAdd(a + 2, qz);
-        atomicAdd(a + 3, qx * qx); atomicAdd(a + 4, qx * qy); atomicAdd(a + 5, qx * qz);
-        atomicAdd(a + 6, qy * qy); atomicAdd(a + 7, qy * qz); atomicAdd(a + 8, qz * qz);
-        atomicAdd(a + 9, 1.0);
-        // min height: float32 of the in-voxel z fraction, in [0,1] -> ordered as int bits
-        atomicMin(reinterpret_cast<int*>(minh) + id, __float_as_int((float)lz));
-    } else {
-        // apron: walk the neighbourhood like the reference does
+#pragma unroll
+        for (int k = 0; k < 10; ++k) atomicAdd(a + k, q[k]);
+        atomicMin(reinterpret_cast<int*>(minh) + id, __float_as_int(lzf));   // values in [0,1]: ordered as int bits
+    }
+    // ---- apron: own voxel outside the grid; walk the neighbourhood like the reference does
+    if (ok && !inb) {
+        const double dS = (double)P.S, dZ = (double)P.Z;
         const double rx = (double)P.rx, rz = (double)P.rz;
         if (bx < -rx - 1.0 || bx > dS + rx || by < -rx - 1.0 || by > dS + rx || bz < -rz - 1.0 || bz > dZ + rz) return;
         const int x0 = (int)bx - P.rx, y0 = (int)by - P.rx, z0 = (int)bz - P.rz;
@@ -303,10 +431,10 @@ k_moments(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevP
                 if (y < 0 || y >= P.S) continue;
                 for (int x = x0; x <= x0 + 2 * P.rx; ++x) {
                     if (x < 0 || x >= P.S) continue;
-                    const int id = index_map[x + (y + z * P.S) * P.S];
-                    if (id < 0) continue;
+                    const int nid = index_map[x + (y + z * P.S) * P.S];
+                    if (nid < 0) continue;
                     const double qx = (fx - (double)x) - 0.5, qy = (fy - (double)y) - 0.5, qz = (fz - (double)z) - 0.5;
-                    double* a = acc + (long long)id * ACC + 10;
+                    double* a = acc + (long long)nid * ACC + 10;
                     atomicAdd(a + 0, qx); atomicAdd(a + 1, qy); atomicAdd(a + 2, qz);
                     atomicAdd(a + 3, qx * qx); atomicAdd(a + 4, qx * qy); atomicAdd(a + 5, qx * qz);
                     atomicAdd(a + 6, qy * qy); atomicAdd(a + 7, qy * qz); atomicAdd(a + 8, qz * qz);
@@ -324,51 +452,73 @@ k_moments(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevP
 // A neighbour's raw moments are about ITS centre; shifting by the integer voxel
 // offset d gives moments about this cell's centre:
 //   S' = S + n d,  Q'_ab = Q_ab + d_a S_b + S_a d_b + n d_a d_b.
+// LPC (4) lanes per cell: each lane takes every 4th neighbour (independent loads in
+// flight), two shuffle steps reduce the group; 30 k cells x 4 lanes fill the GPU, which
+// one thread per cell would not, and a whole warp per cell spends its time in shuffles.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int LPC = 4;
+
+template <int RX, int RZ>      // compile-time neighbourhood radius (RX < 0: runtime P.rx / P.rz)
+__global__ void __launch_bounds__(256)
 k_gather_metrics(const int* __restrict__ index_map, const int* __restrict__ cell_voxel,
                  const int* __restrict__ counter, const double* __restrict__ acc,
-                 double* __restrict__ metrics, DevParams P, int cap) {
+                 double* __restrict__ metrics, DevParams P, int cap, int* __restrict__ scratch_count) {
     const int count = min(*counter, cap);
-    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
-        const int v = cell_voxel[id];
-        const int x = v % P.S, y = (v / P.S) % P.S, z = v / (P.S * P.S);
-        double s0 = 0, s1 = 0, s2 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0, q5 = 0, n = 0;
-        for (int dz = -P.rz; dz <= P.rz; ++dz) {
-            const int zz = z + dz;
-            if (zz < 0 || zz >= P.Z) continue;
-            for (int dy = -P.rx; dy <= P.rx; ++dy) {
-                const int yy = y + dy;
-                if (yy < 0 || yy >= P.S) continue;
-                for (int dx = -P.rx; dx <= P.rx; ++dx) {
-                    const int xx = x + dx;
-                    if (xx < 0 || xx >= P.S) continue;
-                    const int nid = index_map[xx + (yy + zz * P.S) * P.S];
-                    if (nid < 0) continue;
-                    const double* a = acc + (long long)nid * ACC;
-                    const double an = a[9], a0 = a[0], a1 = a[1], a2 = a[2];
-                    const double ddx = (double)dx, ddy = (double)dy, ddz = (double)dz;
-                    s0 += a0 + an * ddx; s1 += a1 + an * ddy; s2 += a2 + an * ddz;
-                    q0 += a[3] + 2.0 * ddx * a0 + an * ddx * ddx;
-                    q1 += a[4] + ddx * a1 + ddy * a0 + an * ddx * ddy;
-                    q2 += a[5] + ddx * a2 + ddz * a0 + an * ddx * ddz;
-                    q3 += a[6] + 2.0 * ddy * a1 + an * ddy * ddy;
-                    q4 += a[7] + ddy * a2 + ddz * a1 + an * ddy * ddz;
-                    q5 += a[8] + 2.0 * ddz * a2 + an * ddz * ddz;
-                    n += an;
-                }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *scratch_count = 0;   // ready for the next scan's K2
+    const int sub = threadIdx.x & (LPC - 1);
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / LPC;
+    const int ngroups = (gridDim.x * blockDim.x) / LPC;
+    const int rx = RX >= 0 ? RX : P.rx, rz = RX >= 0 ? RZ : P.rz;
+    const int wx = 2 * rx + 1, wz = 2 * rz + 1;
+    const int nn = wx * wx * wz;
+    const int per_lane = (nn + LPC - 1) / LPC;
+    const int count_pad = (count + (32 / LPC) - 1) / (32 / LPC) * (32 / LPC);   // whole warps iterate together
+    for (int id = gid; id < count_pad; id += ngroups) {
+        double r[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) r[k] = 0.0;
+        if (id < count) {
+            const int v = cell_voxel[id];
+            const int x = v % P.S, y = (v / P.S) % P.S, z = v / (P.S * P.S);
+#pragma unroll 7
+            for (int u = 0; u < per_lane; ++u) {
+                const int j = sub + u * LPC;
+                if (j >= nn) continue;
+                const int dx = j % wx - rx, dy = (j / wx) % wx - rx, dz = j / (wx * wx) - rz;
+                const int xx = x + dx, yy = y + dy, zz = z + dz;
+                if (xx < 0 || xx >= P.S || yy < 0 || yy >= P.S || zz < 0 || zz >= P.Z) continue;
+                const int nid = __ldg(index_map + (xx + (yy + zz * P.S) * P.S));
+                if (nid < 0) continue;
+                const double2* a2 = reinterpret_cast<const double2*>(acc + (long long)nid * ACC);
+                const double2 a01 = a2[0], a23 = a2[1], a45 = a2[2], a67 = a2[3], a89 = a2[4];
+                const double a0 = a01.x, a1 = a01.y, a2v = a23.x, an = a89.y;
+                const double ddx = (double)dx, ddy = (double)dy, ddz = (double)dz;
+                r[0] += a0 + an * ddx; r[1] += a1 + an * ddy; r[2] += a2v + an * ddz;
+                r[3] += a23.y + 2.0 * ddx * a0 + an * ddx * ddx;
+                r[4] += a45.x + ddx * a1 + ddy * a0 + an * ddx * ddy;
+                r[5] += a45.y + ddx * a2v + ddz * a0 + an * ddx * ddz;
+                r[6] += a67.x + 2.0 * ddy * a1 + an * ddy * ddy;
+                r[7] += a67.y + ddy * a2v + ddz * a1 + an * ddy * ddz;
+                r[8] += a89.x + 2.0 * ddz * a2v + an * ddz * ddz;
+                r[9] += an;
             }
         }
-        const double* e = acc + (long long)id * ACC + 10;
-        s0 += e[0]; s1 += e[1]; s2 += e[2];
-        q0 += e[3]; q1 += e[4]; q2 += e[5]; q3 += e[6]; q4 += e[7]; q5 += e[8];
-        n += e[9];
-        double* mo = metrics + (long long)id * 10;
-        const double m0 = s0 / n, m1 = s1 / n, m2 = s2 / n;
-        mo[0] = m0 + 0.5; mo[1] = m1 + 0.5; mo[2] = m2 + 0.5;
-        mo[3] = q0 / n - m0 * m0; mo[4] = q1 / n - m0 * m1; mo[5] = q2 / n - m0 * m2;
-        mo[6] = q3 / n - m1 * m1; mo[7] = q4 / n - m1 * m2; mo[8] = q5 / n - m2 * m2;
-        mo[9] = n;
+#pragma unroll
+        for (int off = LPC / 2; off > 0; off >>= 1)
+#pragma unroll
+            for (int k = 0; k < 10; ++k) r[k] += __shfl_xor_sync(FULL, r[k], off);
+        if (sub == 0 && id < count) {
+            const double* e = acc + (long long)id * ACC + 10;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) r[k] += e[k];
+            const double n = r[9];
+            double* mo = metrics + (long long)id * 10;
+            const double m0 = r[0] / n, m1 = r[1] / n, m2 = r[2] / n;
+            mo[0] = m0 + 0.5; mo[1] = m1 + 0.5; mo[2] = m2 + 0.5;
+            mo[3] = r[3] / n - m0 * m0; mo[4] = r[4] / n - m0 * m1; mo[5] = r[5] / n - m0 * m2;
+            mo[6] = r[6] / n - m1 * m1; mo[7] = r[7] / n - m1 * m2; mo[8] = r[8] / n - m2 * m2;
+            mo[9] = n;
+        }
     }
 }
 
@@ -383,55 +533,213 @@ struct SlotRef {
     const float* minh;
     int dx, dy, dz;          // combined_origin - source_origin, voxels
     int is_prev;             // 1: previous combined map (float32 metrics, [-11,-1] rule)
+    const unsigned* gmask;   // one bit per 8-voxel group: something known in the group (NULL: no mask)
 };
 struct MergeArgs {
     SlotRef s[MAX_SLOTS + 1];
     int n;
+    int use_masks;           // every source carries a group mask
 };
 
 // ---------------------------------------------------------------------------
 // C1  merged code per voxel.  Result of __combine_indices run once per slot in
 // slot order followed by __combine_old_indices (gvom.py:1009-1063, 242-257), in
-// ONE pass: each thread folds all sources of its voxel in the reference's order.
-// Once a voxel is occupied nothing later changes it, so the fold stops there.
+// ONE pass over the combined grid: each thread folds all sources of its voxels in
+// the reference's order (once a voxel is occupied nothing later changes it).
+//   * VEC = 4: four x-consecutive voxels per thread (S % 4 == 0), sources read with
+//     128-bit loads when the slot's x-shift keeps them aligned, SLOT_BATCH sources
+//     in flight before the fold -- the kernel is a pure streaming pass.
+//   * the column reduction of __make_height_map / __make_inferred_height_map
+//     (gvom.py:560-590: lowest occupied / lowest free voxel of every column) is fused
+//     in: an atomicMin per candidate on two S*S int maps, pre-filtered by a plain load.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_merge_codes(MergeArgs A, int* __restrict__ cmap, int* __restrict__ counter,
-              int* __restrict__ cell_voxel, DevParams P, int cap) {
+constexpr int SLOT_BATCH = 4;
+
+__device__ __forceinline__ void column_min(int* __restrict__ col, int z) {
+    if (z < *col) atomicMin(col, z);
+}
+
+// VEC x-consecutive codes of one source row, starting at xs (may be out of range / unaligned);
+// anything outside the source grid reads as -1 (unknown), which folds to nothing.
+// does the source hold anything but "unknown" in the <= 2 eight-voxel groups that the run
+// [lin, lin+VEC) overlaps?  (one bit per group; the run is clipped to the source row first)
+__device__ __forceinline__ bool group_known(const unsigned* __restrict__ gmask, long long row0, int xs, int S, int VEC_) {
+    const int a = max(xs, 0), b = min(xs + VEC_ - 1, S - 1);
+    if (a > b) return false;
+    const long long g0 = (row0 + a) >> 3, g1 = (row0 + b) >> 3;
+    unsigned hitb = (__ldg(gmask + (g0 >> 5)) >> (g0 & 31)) & 1u;
+    if (g1 != g0) hitb |= (__ldg(gmask + (g1 >> 5)) >> (g1 & 31)) & 1u;
+    return hitb != 0;
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_codes(const int* __restrict__ row, int xs, int S, int (&o)[VEC]) {
+    if (VEC >= 4 && xs >= 0 && xs + VEC <= S && (xs & 3) == 0) {
+#pragma unroll
+        for (int g = 0; g < VEC / 4; ++g) {
+            const int4 t = __ldg(reinterpret_cast<const int4*>(row + xs) + g);
+            o[4 * g] = t.x; o[4 * g + (VEC > 1 ? 1 : 0)] = t.y; o[4 * g + (VEC > 2 ? 2 : 0)] = t.z; o[4 * g + (VEC > 3 ? 3 : 0)] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = (xs + j >= 0 && xs + j < S) ? __ldg(row + xs + j) : -1;
+    }
+}
+
+// The fold over the ring slots is order independent: a voxel is occupied iff any slot is
+// (code >= 0 <=> sign bit clear, so AND the codes), otherwise its code is -1 - sum(passes) with
+// passes = -code-1 = ~code for free voxels and 0 for unknown (-1): sum += max(~code, 0).  Only
+// the previous combined map has an order dependent rule (the [-11,-1] window) and it comes last.
+template <int VEC>
+__global__ void __launch_bounds__(256, 3)
+k_merge_codes(MergeArgs A, int* __restrict__ cmap, int* __restrict__ counter, int* __restrict__ cell_voxel,
+              int* __restrict__ col_occ, int* __restrict__ col_free, DevParams P, int cap,
+              unsigned* __restrict__ gmask_out) {
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const long long step = (long long)gridDim.x * blockDim.x;
-    const long long Vp = (P.V + 31) & ~31LL;
     const int S = P.S, Z = P.Z;
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < Vp; v += step) {
-        bool occ = false;
-        int c = -1;
-        if (v < P.V) {
-            const int x = (int)(v % S), y = (int)((v / S) % S), z = (int)(v / ((long long)S * S));
-            for (int k = 0; k < A.n; ++k) {
-                const SlotRef& s = A.s[k];
-                const int xs = x + s.dx, ys = y + s.dy, zs = z + s.dz;
-                if (xs < 0 || xs >= S || ys < 0 || ys >= S || zs < 0 || zs >= Z) continue;
-                const int o = __ldg(s.map + (xs + (ys + (long long)zs * S) * S));
-                if (o >= 0) {
-                    if (!s.is_prev || c >= -11) { occ = true; break; }
-                } else if (o < -1) {
-                    c += o + 1;
+    const long long NQ = P.V / VEC;
+    const long long NQp = (NQ + 31) & ~31LL;
+    const int has_prev = (A.n > 0 && A.s[A.n - 1].is_prev) ? 1 : 0;
+    const int nreg = A.n - has_prev;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < NQp; q += step) {
+        int acc_and[VEC], sum[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { acc_and[j] = -1; sum[j] = 0; }
+        int x = 0, y = 0, z = 0;
+        int op[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) op[j] = -1;
+        if (q < NQ) {
+            const unsigned v0 = (unsigned)(q * VEC);          // V < 2^31
+            if (P.lgS >= 0) {
+                x = (int)(v0 & (unsigned)(S - 1));
+                const unsigned yz = v0 >> P.lgS;
+                y = (int)(yz & (unsigned)(S - 1)); z = (int)(yz >> P.lgS);
+            } else {
+                x = (int)(v0 % (unsigned)S);
+                const unsigned yz = v0 / (unsigned)S;
+                y = (int)(yz % (unsigned)S); z = (int)(yz / (unsigned)S);
+            }
+            // Sources in batches of SLOT_BATCH, the previous combined map riding in the last batch.
+            // Phase A: which sources hold anything but "unknown" here (group-mask words, independent
+            // loads).  Phase B: the code loads of those sources, all in flight together.  Phase C: fold.
+            for (int k0 = 0; k0 < A.n; k0 += SLOT_BATCH) {
+                long long row0[SLOT_BATCH];
+                int xs[SLOT_BATCH];
+                unsigned need = 0;
+                unsigned w0[SLOT_BATCH], w1[SLOT_BATCH];
+                int b0[SLOT_BATCH], b1[SLOT_BATCH];
+#pragma unroll
+                for (int u = 0; u < SLOT_BATCH; ++u) {            // branch-free: clamp, load, mask afterwards
+                    const int k = min(k0 + u, A.n - 1);
+                    const SlotRef& s = A.s[k];
+                    const int ys = y + s.dy, zs = z + s.dz;
+                    xs[u] = x + s.dx;
+                    const int a = max(xs[u], 0), b = min(xs[u] + VEC - 1, S - 1);
+                    const bool in = (k0 + u < A.n) && ys >= 0 && ys < S && zs >= 0 && zs < Z && a <= b;
+                    row0[u] = in ? ((long long)zs * S + ys) * S : 0;
+                    if (in) need |= 1u << u;
+                    const long long g0 = in ? (row0[u] + a) >> 3 : 0, g1 = in ? (row0[u] + b) >> 3 : 0;
+                    b0[u] = (int)(g0 & 31); b1[u] = (int)(g1 & 31);
+                    w0[u] = 0xffffffffu; w1[u] = 0xffffffffu;
+                    if (A.use_masks) { w0[u] = __ldg(s.gmask + (g0 >> 5)); w1[u] = __ldg(s.gmask + (g1 >> 5)); }
+                }
+#pragma unroll
+                for (int u = 0; u < SLOT_BATCH; ++u)
+                    if ((((w0[u] >> b0[u]) | (w1[u] >> b1[u])) & 1u) == 0) need &= ~(1u << u);
+                int o[SLOT_BATCH][VEC];
+#pragma unroll
+                for (int u = 0; u < SLOT_BATCH; ++u) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) o[u][j] = -1;          // -1 = unknown: folds to nothing
+                    if (need & (1u << u)) load_codes<VEC>(A.s[k0 + u].map + row0[u], xs[u], S, o[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < SLOT_BATCH; ++u) {
+                    if (has_prev && k0 + u == A.n - 1) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) op[j] = o[u][j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) { acc_and[j] &= o[u][j]; sum[j] += max(~o[u][j], 0); }
+                    }
                 }
             }
         }
-        const unsigned m = __ballot_sync(FULL, occ);
+        (void)nreg;
+        bool occ[VEC];
+        int c[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            occ[j] = acc_and[j] >= 0;
+            c[j] = -1 - sum[j];
+            if (!occ[j]) {                                    // previous combined map (gvom.py:1058-1063)
+                if (op[j] >= 0) { if (c[j] >= -11) occ[j] = true; }
+                else if (op[j] < -1) c[j] += op[j] + 1;
+            }
+        }
+        unsigned m[VEC];
+        int nocc = 0;
+        bool any_free = false;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { m[j] = __ballot_sync(FULL, occ[j]); nocc += __popc(m[j]); any_free |= (!occ[j] && c[j] < -1); }
         int base = 0;
-        if (m) {
-            if (lane == 0) base = atomicAdd(counter, __popc(m));
+        if (nocc) {
+            if (lane == 0) base = atomicAdd(counter, nocc);
             base = __shfl_sync(FULL, base, 0);
         }
-        if (v < P.V) {
-            if (occ) {
-                const int id = base + __popc(m & ((1u << lane) - 1u));
-                if (id < cap) { c = id; cell_voxel[id] = (int)v; }
-                else c = -1;
+        bool known_any = false;
+        if (q < NQ) {
+            int* colo = col_occ + (long long)y * S + x;
+            int* colf = col_free + (long long)y * S + x;
+            // current column minima, pre-filter of the atomicMin (vector loads, issued together)
+            int cur_occ[VEC], cur_free[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { cur_occ[j] = 0x7fffffff; cur_free[j] = 0x7fffffff; }
+            bool my_occ = false;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) my_occ |= occ[j];
+            if (VEC >= 4) {
+#pragma unroll
+                for (int g = 0; g < VEC / 4; ++g) {
+                    if (my_occ) {
+                        const int4 a = *(reinterpret_cast<const int4*>(colo) + g);
+                        cur_occ[4 * g] = a.x; cur_occ[4 * g + (VEC > 1 ? 1 : 0)] = a.y; cur_occ[4 * g + (VEC > 2 ? 2 : 0)] = a.z; cur_occ[4 * g + (VEC > 3 ? 3 : 0)] = a.w;
+                    }
+                    if (any_free) {
+                        const int4 b = *(reinterpret_cast<const int4*>(colf) + g);
+                        cur_free[4 * g] = b.x; cur_free[4 * g + (VEC > 1 ? 1 : 0)] = b.y; cur_free[4 * g + (VEC > 2 ? 2 : 0)] = b.z; cur_free[4 * g + (VEC > 3 ? 3 : 0)] = b.w;
+                    }
+                }
+            } else {
+                cur_occ[0] = colo[0]; cur_free[0] = colf[0];
             }
-            cmap[v] = c;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                if (occ[j]) {
+                    const int id = base + __popc(m[j] & lt);
+                    if (id < cap) { c[j] = id; cell_voxel[id] = (int)(q * VEC + j); if (z < cur_occ[j]) atomicMin(colo + j, z); }
+                    else c[j] = -1;
+                } else if (c[j] < -1) {
+                    if (z < cur_free[j]) atomicMin(colf + j, z);
+                }
+                base += __popc(m[j]);
+                known_any |= c[j] != -1;
+            }
+            if (VEC >= 4) {
+#pragma unroll
+                for (int g = 0; g < VEC / 4; ++g)
+                    reinterpret_cast<int4*>(cmap)[q * (VEC / 4) + g] =
+                        make_int4(c[4 * g], c[4 * g + (VEC > 1 ? 1 : 0)], c[4 * g + (VEC > 2 ? 2 : 0)], c[4 * g + (VEC > 3 ? 3 : 0)]);
+            } else {
+                cmap[q] = c[0];
+            }
+        }
+        if (VEC == 8) {                                       // group mask of the new combined map
+            const unsigned w = __ballot_sync(FULL, known_any);
+            if (lane == 0 && q < NQ) gmask_out[q >> 5] = w;
         }
     }
 }
@@ -471,17 +779,19 @@ __device__ __forceinline__ void eigen3(const float* m, float* e) {
 // one pairwise (Chan) merge step of __combine_metrics (gvom.py:926-980): float64
 // math on float32-stored running values, stores round to float32.
 __device__ __forceinline__ void merge_step(float* c, const double* o) {
-    const double n1 = c[9], n2 = o[9], nt = n1 + n2;
+    // results are stored as float32: one float64 reciprocal instead of nine divisions changes them
+    // by < 1e-15 relative (the parity bar for moments is 1e-4)
+    const double n1 = c[9], n2 = o[9], nt = n1 + n2, inv = 1.0 / nt;
     const double c0 = c[0], c1 = c[1], c2 = c[2];
-    const double mx = (c0 * n1 + o[0] * n2) / nt;
-    const double my = (c1 * n1 + o[1] * n2) / nt;
-    const double mz = (c2 * n1 + o[2] * n2) / nt;
+    const double mx = (c0 * n1 + o[0] * n2) * inv;
+    const double my = (c1 * n1 + o[1] * n2) * inv;
+    const double mz = (c2 * n1 + o[2] * n2) * inv;
     const double cd[3] = {c0 - mx, c1 - my, c2 - mz};
     const double od[3] = {o[0] - mx, o[1] - my, o[2] - mz};
     const int A[6] = {0, 0, 0, 1, 1, 2}, B[6] = {0, 1, 2, 1, 2, 2};
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
-        const double v = (n1 * (double)c[3 + e] + n2 * o[3 + e] + n1 * cd[A[e]] * cd[B[e]] + n2 * od[A[e]] * od[B[e]]) / nt;
+        const double v = (n1 * (double)c[3 + e] + n2 * o[3 + e] + n1 * cd[A[e]] * cd[B[e]] + n2 * od[A[e]] * od[B[e]]) * inv;
         c[3 + e] = (float)v;
     }
     c[0] = (float)mx; c[1] = (float)my; c[2] = (float)mz;
@@ -508,26 +818,37 @@ k_merge_cells(MergeArgs A, const int* __restrict__ counter, const int* __restric
         for (int k = 0; k < 10; ++k) c[k] = 0.f;
         int hit = 0, tot = 0;
         float mh = 1.0f;
-        for (int k = 0; k < A.n; ++k) {
-            const SlotRef& s = A.s[k];
-            const int xs = x + s.dx, ys = y + s.dy, zs = z + s.dz;
-            if (xs < 0 || xs >= S || ys < 0 || ys >= S || zs < 0 || zs >= Z) continue;
-            const int io = __ldg(s.map + (xs + (ys + (long long)zs * S) * S));
-            if (io < 0) continue;
-            double o[10];
-            if (s.is_prev) {
-                const float* om = reinterpret_cast<const float*>(s.metrics) + (long long)io * 10;
+        for (int k0 = 0; k0 < A.n; k0 += SLOT_BATCH) {
+            int io[SLOT_BATCH];
 #pragma unroll
-                for (int a = 0; a < 10; ++a) o[a] = (double)om[a];
-            } else {
-                const double* om = reinterpret_cast<const double*>(s.metrics) + (long long)io * 10;
-#pragma unroll
-                for (int a = 0; a < 10; ++a) o[a] = om[a];
+            for (int u = 0; u < SLOT_BATCH; ++u) {                  // independent index loads first
+                io[u] = -1;
+                if (k0 + u < A.n) {
+                    const SlotRef& s = A.s[k0 + u];
+                    const int xs = x + s.dx, ys = y + s.dy, zs = z + s.dz;
+                    if (!(xs < 0 || xs >= S || ys < 0 || ys >= S || zs < 0 || zs >= Z))
+                        io[u] = __ldg(s.map + (xs + (ys + (long long)zs * S) * S));
+                }
             }
-            merge_step(c, o);
-            hit += s.hit[io];
-            tot += s.total[io];
-            mh = fminf(mh, s.minh[io]);
+#pragma unroll
+            for (int u = 0; u < SLOT_BATCH; ++u) {
+                if (io[u] < 0) continue;
+                const SlotRef& s = A.s[k0 + u];
+                double o[10];
+                if (s.is_prev) {
+                    const float2* om = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(s.metrics) + (long long)io[u] * 10);
+#pragma unroll
+                    for (int a = 0; a < 5; ++a) { const float2 t = om[a]; o[2 * a] = (double)t.x; o[2 * a + 1] = (double)t.y; }
+                } else {
+                    const double2* om = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(s.metrics) + (long long)io[u] * 10);
+#pragma unroll
+                    for (int a = 0; a < 5; ++a) { const double2 t = om[a]; o[2 * a] = t.x; o[2 * a + 1] = t.y; }
+                }
+                merge_step(c, o);
+                hit += s.hit[io[u]];
+                tot += s.total[io[u]];
+                mh = fminf(mh, s.minh[io[u]]);
+            }
         }
         float* mo = cmet + (long long)id * 10;
 #pragma unroll
@@ -543,102 +864,169 @@ k_merge_cells(MergeArgs A, const int* __restrict__ counter, const int* __restric
 #define GVOM_HM(a, x, y) (a)[(long long)(x) * S + (y)]
 
 // ---------------------------------------------------------------------------
-// C3  column reduction 3-D -> height maps.  Result of __make_height_map and
-// __make_inferred_height_map (gvom.py:560-590) incl. their -1000 fills.
-// Thread <-> x fastest so that a warp reads 32 consecutive voxels of each z layer.
+// C3  height maps from the column minima of C1.  Result of __make_height_map and
+// __make_inferred_height_map (gvom.py:560-590) incl. their -1000 fills.  Also
+// builds two bit maps of "height known" cells for the ring search of C4:
+//   known [x][y/32] (bits over y) and knownT[y][x/32] (bits over x).
+// Block = 32x32 cell tile, 1024 threads (x fastest), one column per thread.
+// Also publishes the combined cell count (thread 0): C1's running counter -> the map's counter.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_column_maps(const int* __restrict__ cmap, const float* __restrict__ cminh, double o0, double o1, double o2,
-              double e0, double e1, double e2, DevParams P, double* __restrict__ height,
-              double* __restrict__ inferred) {
+__global__ void __launch_bounds__(1024)
+k_column_maps(const int* __restrict__ cmap, const float* __restrict__ cminh, const int* __restrict__ col_occ,
+              const int* __restrict__ col_free, double o0, double o1, double o2, double e0, double e1, double e2,
+              DevParams P, double* __restrict__ height, double* __restrict__ inferred,
+              unsigned* __restrict__ known, unsigned* __restrict__ knownT,
+              const int* __restrict__ scratch_count, int* __restrict__ map_count) {
+    __shared__ unsigned char flag[32][33];
     const int S = P.S;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= S * S) return;
-    const int x = t % S, y = t / S;
-    double h = -1000.0, inf = -1000.0;
-    // ego disc: xp = (o+x)*res - ego with the product and difference fused (ptxas contracts
-    // the reference's mul+sub), then fma(xp,xp, yp*yp) <= r*r
-    const double xp = __fma_rn(__dadd_rn(o0, (double)x), P.xy_res, -e0);
-    const double yp = __fma_rn(__dadd_rn(o1, (double)y), P.xy_res, -e1);
-    if (__fma_rn(xp, xp, __dmul_rn(yp, yp)) <= P.r2) h = __dsub_rn(e2, P.ground_to_lidar);
-    bool got_h = false, got_i = false;
-    const int* col = cmap + x + (long long)y * S;
+    const int W = (S + 31) >> 5;                          // words per bit row
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 32 + ty;
     const long long zs = (long long)S * S;
-    for (int z = 0; z < P.Z && !(got_h && got_i); ++z) {
-        const int idx = __ldg(col + z * zs);
-        if (idx >= 0 && !got_h) {
-            h = __dmul_rn(__dadd_rn(__dadd_rn((double)z, (double)cminh[idx]), o2), P.z_res);
-            got_h = true;
-        } else if (idx < -1 && !got_i) {
-            inf = __dmul_rn(__dadd_rn(o2, (double)z), P.z_res);
-            got_i = true;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *map_count = *scratch_count;
+    bool kn = false;
+    if (x < S && y < S) {
+        double h = -1000.0, inf = -1000.0;
+        // ego disc: xp = (o+x)*res - ego with product and difference fused (ptxas contracts the
+        // reference's mul+sub), then fma(xp,xp, yp*yp) <= r*r
+        const double xp = __fma_rn(__dadd_rn(o0, (double)x), P.xy_res, -e0);
+        const double yp = __fma_rn(__dadd_rn(o1, (double)y), P.xy_res, -e1);
+        if (__fma_rn(xp, xp, __dmul_rn(yp, yp)) <= P.r2) h = __dsub_rn(e2, P.ground_to_lidar);
+        const int zo = col_occ[(long long)y * S + x], zf = col_free[(long long)y * S + x];
+        if (zo < P.Z) {
+            const int idx = cmap[x + (long long)y * S + zo * zs];
+            h = __dmul_rn(__dadd_rn(__dadd_rn((double)zo, (double)cminh[idx]), o2), P.z_res);
         }
+        if (zf < P.Z) inf = __dmul_rn(__dadd_rn(o2, (double)zf), P.z_res);
+        GVOM_HM(height, x, y) = h;
+        GVOM_HM(inferred, x, y) = inf;
+        kn = h > -1000.0;
     }
-    GVOM_HM(height, x, y) = h;
-    GVOM_HM(inferred, x, y) = inf;
+    flag[ty][tx] = kn ? 1 : 0;
+    const unsigned wT = __ballot_sync(FULL, kn);          // bits over x for row y
+    if (tx == 0 && y < S) knownT[(long long)y * W + blockIdx.x] = wT;
+    __syncthreads();
+    if (threadIdx.x < 32) {                               // bits over y for column x = tile x0 + threadIdx.x
+        unsigned w = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) w |= (unsigned)flag[b][threadIdx.x] << b;
+        const int xx = blockIdx.x * 32 + threadIdx.x;
+        if (xx < S) known[(long long)xx * W + blockIdx.y] = w;
+    }
+}
+
+// first set bit with index in [lo, hi] of a bit row, or -1
+__device__ __forceinline__ int first_known(const unsigned* row, int lo, int hi) {
+    for (int w = lo >> 5; w <= (hi >> 5); ++w) {
+        unsigned m = row[w];
+        if (w == (lo >> 5)) m &= 0xffffffffu << (lo & 31);
+        if (w == (hi >> 5)) m &= 0xffffffffu >> (31 - (hi & 31));
+        if (m) return (w << 5) + __ffs(m) - 1;
+    }
+    return -1;
 }
 
 // ---------------------------------------------------------------------------
 // C4  surface maps.  Result of __calculate_slope, __guess_height,
 // __make_positive_obstacle_map, __make_negative_obstacle_map and
 // __make_visability_map (gvom.py:444-452, 505-555, 592-805) and their fills, one
-// thread per map cell (slope of the own cell is all the positive-obstacle test needs).
-// Thread <-> y fastest: height-map reads of a warp are contiguous.
+// thread per map cell (the slope of the own cell is all the positive-obstacle test
+// needs).  Thread <-> y fastest: height-map reads of a warp are contiguous.
+// The ring search of __guess_height walks up to 4x15 row/column segments per cell;
+// here each segment is one or two words of the "height known" bit maps and a
+// find-first-set, and only the found cell's height is loaded.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_surface_maps(const int* __restrict__ cmap, const int* __restrict__ chit, const int* __restrict__ ctot,
-               const double* __restrict__ height, const double* __restrict__ inferred, double o2,
+               const double* __restrict__ height, const double* __restrict__ inferred,
+               const unsigned* __restrict__ known_g, const unsigned* __restrict__ knownT_g, double o2,
                DevParams P, double* __restrict__ rough, double* __restrict__ xs, double* __restrict__ ys,
-               double* __restrict__ guessed, int* __restrict__ pos, int* __restrict__ neg, int* __restrict__ vis) {
+               double* __restrict__ guessed, int* __restrict__ pos, int* __restrict__ neg, int* __restrict__ vis,
+               int masks_in_smem, int* __restrict__ col_minz, int* __restrict__ scratch_count) {
+    extern __shared__ unsigned smask[];
     const int S = P.S, Z = P.Z;
+    const int W = (S + 31) >> 5;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // both bit maps (2*S*W words, 16 KB at S = 256) go to shared memory when they fit: the ring
+    // search then never waits on L2
+    const unsigned* known = known_g;
+    const unsigned* knownT = knownT_g;
+    if (masks_in_smem) {
+        const int nw4 = (2 * S * W) >> 2;                  // known and knownT are contiguous; S*W % 2 == 0 here
+        const uint4* g4 = reinterpret_cast<const uint4*>(known_g);
+        uint4* s4 = reinterpret_cast<uint4*>(smask);
+#pragma unroll 4
+        for (int k = threadIdx.x; k < nw4; k += blockDim.x) s4[k] = __ldg(g4 + k);
+        __syncthreads();
+        known = smask;
+        knownT = smask + S * W;
+    }
     if (t >= S * S) return;
+    // housekeeping for the next combine: C1's column minima and running counter start clean
+    col_minz[t] = 0x7f7f7f7f;
+    col_minz[S * S + t] = 0x7f7f7f7f;
+    if (t == 0) *scratch_count = 0;
     const int y0 = t % S, x0 = t / S;
-    const double h0 = GVOM_HM(height, x0, y0);
 
-    // ---- slope + roughness (gvom.py:717-805); contraction pattern = SASS of the reference
+    // ---- slope + roughness (gvom.py:717-805); contraction pattern = SASS of the reference.
+    // 3x3 neighbourhood in registers, visited in the reference's order (x outer, y inner).
+    double hz[9];
+    unsigned okm = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const int x = x0 - 1 + a, y = y0 - 1 + b;
+            double h = -1000.0;
+            if (x >= 0 && x < S && y >= 0 && y < S) h = GVOM_HM(height, x, y);
+            hz[a * 3 + b] = h;
+            if (h > -1000.0) okm |= 1u << (a * 3 + b);
+        }
+    const double h0 = hz[4];
     double sxv = 0.0, syv = 0.0, rg = -1.0;
-    {
-        double px[9], py[9], pz[9];
-        int n = 0;
+    const int n = __popc(okm);
+    if (n >= 3) {
         double sx = 0, sy = 0, sz = 0;
-        const int xa = max(0, x0 - 1), xb = min(S, x0 + 2), ya = max(0, y0 - 1), yb = min(S, y0 + 2);
-        for (int x = xa; x < xb; ++x)
-            for (int y = ya; y < yb; ++y) {
-                const double h = GVOM_HM(height, x, y);
-                if (h > -1000.0) {
-                    px[n] = __dmul_rn((double)x, P.xy_res); py[n] = __dmul_rn((double)y, P.xy_res); pz[n] = h;
-                    sx = __dadd_rn(sx, px[n]); sy = __dadd_rn(sy, py[n]); sz = __dadd_rn(sz, pz[n]);
-                    ++n;
-                }
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+            if (okm & (1u << j)) {
+                sx = __dadd_rn(sx, __dmul_rn((double)(x0 - 1 + j / 3), P.xy_res));
+                sy = __dadd_rn(sy, __dmul_rn((double)(y0 - 1 + j % 3), P.xy_res));
+                sz = __dadd_rn(sz, hz[j]);
             }
-        if (n >= 3) {
-            const double mx = __ddiv_rn(sx, (double)n), my = __ddiv_rn(sy, (double)n), mz = __ddiv_rn(sz, (double)n);
-            double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0;
-            for (int i = 0; i < n; ++i) {
-                const double dx = __dsub_rn(px[i], mx), dy = __dsub_rn(py[i], my), dz = __dsub_rn(pz[i], mz);
+        const double dn = (double)n;
+        const double mx = __ddiv_rn(sx, dn), my = __ddiv_rn(sy, dn), mz = __ddiv_rn(sz, dn);
+        double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+            if (okm & (1u << j)) {
+                const double dx = __dsub_rn(__dmul_rn((double)(x0 - 1 + j / 3), P.xy_res), mx);
+                const double dy = __dsub_rn(__dmul_rn((double)(y0 - 1 + j % 3), P.xy_res), my);
+                const double dz = __dsub_rn(hz[j], mz);
                 xx = __fma_rn(dx, dx, xx); xy = __fma_rn(dx, dy, xy); xz = __fma_rn(dx, dz, xz);
                 yy = __fma_rn(dy, dy, yy); yz = __fma_rn(dy, dz, yz);
             }
-            const double det = __fma_rn(xx, yy, -__dmul_rn(xy, xy));
-            if (det != 0.0) {
-                double a0 = __ddiv_rn(__fma_rn(xz, yy, -__dmul_rn(xy, yz)), det);
-                double a1 = __ddiv_rn(__fma_rn(xx, yz, -__dmul_rn(xy, xz)), det);
-                const double m = __dsqrt_rn(__dadd_rn(__fma_rn(a0, a0, __dmul_rn(a1, a1)), 1.0));
-                a0 = __ddiv_rn(a0, m); a1 = __ddiv_rn(a1, m);
-                double err = 0.0;
-                for (int i = 0; i < n; ++i) {
-                    const double e = __dsub_rn(__dsub_rn(pz[i], mz),
-                                               __fma_rn(a0, __dsub_rn(px[i], mx), __dmul_rn(a1, __dsub_rn(py[i], my))));
+        const double det = __fma_rn(xx, yy, -__dmul_rn(xy, xy));
+        if (det != 0.0) {
+            double a0 = __ddiv_rn(__fma_rn(xz, yy, -__dmul_rn(xy, yz)), det);
+            double a1 = __ddiv_rn(__fma_rn(xx, yz, -__dmul_rn(xy, xz)), det);
+            const double m = __dsqrt_rn(__dadd_rn(__fma_rn(a0, a0, __dmul_rn(a1, a1)), 1.0));
+            a0 = __ddiv_rn(a0, m); a1 = __ddiv_rn(a1, m);
+            double err = 0.0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if (okm & (1u << j)) {
+                    const double dx = __dsub_rn(__dmul_rn((double)(x0 - 1 + j / 3), P.xy_res), mx);
+                    const double dy = __dsub_rn(__dmul_rn((double)(y0 - 1 + j % 3), P.xy_res), my);
+                    const double e = __dsub_rn(__dsub_rn(hz[j], mz), __fma_rn(a0, dx, __dmul_rn(a1, dy)));
                     err = __fma_rn(e, e, err);
                 }
-                err = __ddiv_rn(err, (double)n);
-                if (err > 0.0) err = log(err);
-                rg = err;
-                const double im = __drcp_rn(m);
-                sxv = atan2(a0, im);
-                syv = atan2(a1, im);
-            }
+            err = __ddiv_rn(err, dn);
+            if (err > 0.0) err = log(err);
+            rg = err;
+            const double im = __drcp_rn(m);
+            sxv = atan2(a0, im);
+            syv = atan2(a1, im);
         }
     }
     GVOM_HM(rough, x0, y0) = rg;
@@ -647,55 +1035,40 @@ k_surface_maps(const int* __restrict__ cmap, const int* __restrict__ chit, const
 
     // ---- guessed height delta (gvom.py:592-713), quirks kept (see oracle/gvom_oracle.c)
     double dh_out = 0.0;
-    if (!(h0 > -1000.0) && GVOM_HM(inferred, x0, y0) != -1000.0) {
+    const double inf0 = GVOM_HM(inferred, x0, y0);
+    if (!(h0 > -1000.0) && inf0 != -1000.0) {
         bool xpd = false, xnd = false, ypd = false, ynd = false;
-        int x_p = x0, x_n = x0, y_p = y0, y_n = y0;
         double x_ph = -1000.0, x_nh = -1000.0, y_ph = -1000.0, y_nh = -1000.0;
         int i = 0;
         while (i < 15 && !(xnd && ypd && ynd)) {          // x_p_done is NOT part of the condition (gvom.py:619)
-            x_p += 1; x_n -= 1; y_p += 1; y_n -= 1; i += 1;
+            i += 1;
+            const int x_p = x0 + i, x_n = x0 - i, y_p = y0 + i, y_n = y0 - i;
             if (!xpd) {
-                if (x_p < S) {
-                    for (int d = -i; d < i; ++d) {
-                        const int yy = y0 + d;
-                        if (yy >= S || yy < 0) continue;
-                        const double h = GVOM_HM(height, x_p, yy);
-                        if (h > -1000.0) { x_ph = h; xpd = true; break; }
-                    }
+                if (x_p < S) {                            // y in [y0-i, y0+i-1], ascending
+                    const int f = first_known(known + (long long)x_p * W, max(0, y0 - i), min(S - 1, y0 + i - 1));
+                    if (f >= 0) { x_ph = GVOM_HM(height, x_p, f); xpd = true; }
                 } else xpd = true;
             }
             if (!xnd) {
-                if (x_n >= 0) {
-                    for (int d = -i + 1; d < i + 1; ++d) {
-                        const int yy = y0 + d;
-                        if (yy >= S || yy < 0) continue;
-                        const double h = GVOM_HM(height, x_n, yy);
-                        if (h > -1000.0) { x_nh = h; xnd = true; break; }
-                    }
+                if (x_n >= 0) {                           // y in [y0-i+1, y0+i]
+                    const int f = first_known(known + (long long)x_n * W, max(0, y0 - i + 1), min(S - 1, y0 + i));
+                    if (f >= 0) { x_nh = GVOM_HM(height, x_n, f); xnd = true; }
                 } else xnd = true;
             }
             if (!ypd) {
-                if (y_p < S) {
-                    for (int d = -i + 1; d < i + 1; ++d) {
-                        const int xx = x0 + d;
-                        if (xx >= S || xx < 0) continue;
-                        const double h = GVOM_HM(height, xx, y_p);
-                        if (h > -1000.0) { y_ph = h; ypd = true; break; }
-                    }
+                if (y_p < S) {                            // x in [x0-i+1, x0+i]
+                    const int f = first_known(knownT + (long long)y_p * W, max(0, x0 - i + 1), min(S - 1, x0 + i));
+                    if (f >= 0) { y_ph = GVOM_HM(height, f, y_p); ypd = true; }
                 } else ypd = true;
             }
             if (!ynd) {
-                if (y_n >= 0) {
-                    for (int d = -i; d < i; ++d) {
-                        const int xx = x0 + d;
-                        if (xx >= S || xx < 0) continue;
-                        const double h = GVOM_HM(height, xx, y_n);
-                        if (h > -1000.0) { y_nh = h; ynd = true; break; }
-                    }
+                if (y_n >= 0) {                           // x in [x0-i, x0+i-1]
+                    const int f = first_known(knownT + (long long)y_n * W, max(0, x0 - i), min(S - 1, x0 + i - 1));
+                    if (f >= 0) { y_nh = GVOM_HM(height, f, y_n); ynd = true; }
                 } else ynd = true;
             }
         }
-        double mn = 1000.0, mx = GVOM_HM(inferred, x0, y0);
+        double mn = 1000.0, mx = inf0;
         if (x_ph > -1000.0) { mn = fmin(x_ph, mn); mx = fmax(x_ph, mx); }
         if (x_nh > -1000.0) { mn = fmin(x_nh, mn); mx = fmax(x_nh, mx); }
         if (y_ph > -1000.0) { mn = fmin(y_ph, mn); mx = fmax(y_ph, mx); }
@@ -715,19 +1088,24 @@ k_surface_maps(const int* __restrict__ cmap, const int* __restrict__ chit, const
     } else {
         const double lo = floor(__dsub_rn(__ddiv_rn(__dadd_rn(h0, P.pos_thr), P.z_res), o2));
         const double hi = floor(__dsub_rn(__ddiv_rn(__dadd_rn(h0, P.robot_height), P.z_res), o2));
-        // |h0| <= ~1e3 here, so the conversions cannot overflow
-        const long long zlo = (long long)lo + 1, zhi = (long long)hi;
-        if (zlo >= 0 && zlo < Z && zhi >= 0 && zhi < Z) {
-            double density = 0.0, n = 0.0;
-            for (long long z = zlo; z <= zhi; ++z) {
-                const int idx = __ldg(cmap + (x0 + (y0 + z * S) * S));
-                if (idx >= 0) {
-                    const int hc = chit[idx];
-                    if (hc > 10) { n = __dadd_rn(n, (double)ctot[idx]); density = __dadd_rn(density, (double)hc); }
+        if (lo > -2.0e9 && lo < 2.0e9 && hi > -2.0e9 && hi < 2.0e9) {
+            const long long zlo = (long long)lo + 1, zhi = (long long)hi;
+            if (zlo >= 0 && zlo < Z && zhi >= 0 && zhi < Z) {
+                double density = 0.0, nn = 0.0;
+                for (long long zb = zlo; zb <= zhi; zb += 8) {        // 8 levels per batch: loads first
+                    int idx[8], hc[8], tc[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        idx[u] = (zb + u <= zhi) ? __ldg(cmap + (x0 + (y0 + (zb + u) * S) * S)) : -1;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { hc[u] = idx[u] >= 0 ? __ldg(chit + idx[u]) : 0; tc[u] = idx[u] >= 0 ? __ldg(ctot + idx[u]) : 0; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (hc[u] > 10) { nn = __dadd_rn(nn, (double)tc[u]); density = __dadd_rn(density, (double)hc[u]); }
                 }
+                if (nn > 0.0) density = __ddiv_rn(density, nn);
+                pv = (int)__dmul_rn(density, 100.0);
             }
-            if (n > 0.0) density = __ddiv_rn(density, n);
-            pv = (int)__dmul_rn(density, 100.0);
         }
     }
     GVOM_HM(pos, x0, y0) = pv;
@@ -876,7 +1254,8 @@ k_partial_cells(MergeArgs A, const int* __restrict__ counter, float* __restrict_
 __global__ void __launch_bounds__(256)
 k_finish_codes(const int* __restrict__ grid, SlotRef prev, int has_prev, int* __restrict__ cmap,
                int* __restrict__ counter, int* __restrict__ cell_voxel, double* __restrict__ cacc,
-               int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh, DevParams P, int cap) {
+               int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
+               int* __restrict__ col_occ, int* __restrict__ col_free, DevParams P, int cap) {
     const int lane = threadIdx.x & 31;
     const long long step = (long long)gridDim.x * blockDim.x;
     const long long Vp = (P.V + 31) & ~31LL;
@@ -917,6 +1296,9 @@ k_finish_codes(const int* __restrict__ grid, SlotRef prev, int has_prev, int* __
                 } else c = -1;
             }
             cmap[v] = c;
+            const int x = (int)(v % S), y = (int)((v / S) % S), z = (int)(v / ((long long)S * S));
+            if (c >= 0) column_min(col_occ + (long long)y * S + x, z);
+            else if (c < -1) column_min(col_free + (long long)y * S + x, z);
         }
     }
 }
