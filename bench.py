@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-mode", default="numba", choices=["numba", "oracle"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU combine exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -224,7 +225,7 @@ def main():
     P = synth.params_tuple()
     if multi:
         from gvom_b200.multi import MultiGpuGvom
-        g = MultiGpuGvom(*P, device=dev, stream=stream.cuda_stream, torch_stream=stream)
+        g = MultiGpuGvom(*P, device=dev, stream=stream.cuda_stream, torch_stream=stream, exchange=args.exchange)
     else:
         g = Gvom(*P, device=dev, stream=stream.cuda_stream)
     fr = frames(rank)
@@ -343,7 +344,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": ("configs[1]: synthetic OS1-128 scan (128x2048=262,144 pts), 256x256x64 grid @0.4/0.2 m, "
                                 "buffer 4, one sensor per GPU" + ("; configs[2]: per-GPU streams, NCCL-reduced combine" if multi else "")),
-                   "frames": NFRAMES, "l2": "flushed between steps (256 MiB memset, outside the timed region)",
+                   "exchange": getattr(g, "exchange", None), "frames": NFRAMES, "l2": "flushed between steps (256 MiB memset, outside the timed region)",
                    "value_io": "cloud resident in HBM (float64 Nx3), maps left in HBM",
                    "e2e_io": "pinned host float64 Nx3 cloud in, numpy maps out (pinned), per-step wall clock around both calls"},
         "p50_latency_ms": statistics.median(ev_dev),

@@ -266,6 +266,17 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
     }
 }
 
+template <int MODE>
+void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStream_t st) {
+    if (h->p.xy_size % 8 == 0)
+        k_merge_codes<8, MODE><<<h->grid_codes, 256, 0, st>>>(A, O, h->dp);
+    else if (h->p.xy_size % 4 == 0)
+        k_merge_codes<4, MODE><<<h->grid_codes, 256, 0, st>>>(A, O, h->dp);
+    else
+        k_merge_codes<1, MODE><<<h->grid_codes, 256, 0, st>>>(A, O, h->dp);
+    h->stats.kernel_launches++;
+}
+
 // 2-D stage + outputs, shared by the single- and multi-GPU combine.
 int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* positive, int32_t* negative,
                         double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st) {
@@ -273,6 +284,9 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
     double* height = h->maps; double* inferred = h->maps + S2; double* rough = h->rough_out;
     double* xs = h->maps + 3 * (size_t)S2; double* ys = h->maps + 4 * (size_t)S2; double* guessed = h->maps + 5 * (size_t)S2;
     int* pos = h->imaps; int* neg = h->imaps + S2; int* vis = h->imaps + 2 * (size_t)S2;
+    // device-resident outputs: the surface kernel writes straight into the caller's buffers
+    const bool direct_dev = out_mem == GVOM_DEVICE && positive && negative && roughness && visibility;
+    if (direct_dev) { pos = positive; neg = negative; vis = visibility; rough = roughness; }
     const int W = (h->p.xy_size + 31) / 32;
     unsigned* known = h->known; unsigned* knownT = h->known + (size_t)h->p.xy_size * W;
     k_column_maps<<<dim3(W, W), 1024, 0, st>>>(c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
@@ -288,7 +302,12 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h->counters_host, c.counter, sizeof(int), cudaMemcpyDeviceToHost, st));
     const size_t bi = (size_t)S2 * sizeof(int), bd = (size_t)S2 * sizeof(double);
-    if (out_mem == GVOM_DEVICE) {
+    if (direct_dev) {
+        // keep the library's own copy of the roughness map current for the debug exports
+        CUDA_TRY(cudaMemcpyAsync(h->rough_out, roughness, (size_t)S2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        rec(h, EV_D2H, st);
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else if (out_mem == GVOM_DEVICE) {
         if (positive) CUDA_TRY(cudaMemcpyAsync(positive, pos, bi, cudaMemcpyDeviceToDevice, st));
         if (negative) CUDA_TRY(cudaMemcpyAsync(negative, neg, bi, cudaMemcpyDeviceToDevice, st));
         if (visibility) CUDA_TRY(cudaMemcpyAsync(visibility, vis, bi, cudaMemcpyDeviceToDevice, st));
@@ -379,8 +398,9 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
         const bool v8 = p->xy_size % 8 == 0, v4 = h->V % 4 == 0, s4 = p->xy_size % 4 == 0;
         h->grid_index = v8 ? resident_grid(k_build_index<8>, 256, h->sm_count)
                            : v4 ? resident_grid(k_build_index<4>, 256, h->sm_count) : resident_grid(k_build_index<1>, 256, h->sm_count);
-        h->grid_codes = v8 ? resident_grid(k_merge_codes<8>, 256, h->sm_count)
-                           : s4 ? resident_grid(k_merge_codes<4>, 256, h->sm_count) : resident_grid(k_merge_codes<1>, 256, h->sm_count);
+        h->grid_codes = v8 ? resident_grid(k_merge_codes<8, MERGE_FINISH>, 256, h->sm_count)
+                           : s4 ? resident_grid(k_merge_codes<4, MERGE_FINISH>, 256, h->sm_count)
+                                : resident_grid(k_merge_codes<1, MERGE_FINISH>, 256, h->sm_count);
         h->grid_cells = resident_grid(k_merge_cells, 128, h->sm_count);
         h->grid_gather = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics<1, 1>, 256, h->sm_count)
                                                                          : resident_grid(k_gather_metrics<-1, -1>, 256, h->sm_count);
@@ -580,19 +600,17 @@ int gvom_combine_maps(GvomHandle* h, double origin[3], int32_t* positive, int32_
     for (int k = 0; k < 3; ++k) c.origin[k] = newest.origin[k];   // gvom.py:229
     // flags[1] (running cell counter) and the column minima are left clean by the previous combine's C4
     {
-        int* col = h->col_minz;
-        if (h->p.xy_size % 8 == 0)
-            k_merge_codes<8><<<h->grid_codes, 256, 0, st>>>(A, c.index_map, h->flags + 1, c.cell_voxel, col, col + h->S2, h->dp, (int)h->ccap, c.gmask);
-        else if (h->p.xy_size % 4 == 0)
-            k_merge_codes<4><<<h->grid_codes, 256, 0, st>>>(A, c.index_map, h->flags + 1, c.cell_voxel, col, col + h->S2, h->dp, (int)h->ccap, nullptr);
-        else
-            k_merge_codes<1><<<h->grid_codes, 256, 0, st>>>(A, c.index_map, h->flags + 1, c.cell_voxel, col, col + h->S2, h->dp, (int)h->ccap, nullptr);
+        MergeOut O{};
+        O.cmap = c.index_map; O.counter = h->flags + 1; O.cell_voxel = c.cell_voxel;
+        O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
+        O.gmask = (h->p.xy_size % 8 == 0) ? c.gmask : nullptr; O.cap = (int)h->ccap;
+        launch_merge<MERGE_FULL>(h, A, O, st);
     }
     rec(h, EV_CODES, st);
     k_merge_cells<<<h->grid_cells, 128, 0, st>>>(A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
                                                   h->dp, (int)h->ccap);
     rec(h, EV_CELLS, st);
-    h->stats.kernel_launches += 2;
+    h->stats.kernel_launches += 1;
     h->prof_combine = h->profiling;
     c.has_gmask = h->p.xy_size % 8 == 0;
     const int r = run_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st);
@@ -792,8 +810,8 @@ int gvom_newest_origin(GvomHandle* h, double origin[3]) {
     return GVOM_OK;
 }
 
-int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, float* records_dev,
-                         int64_t record_capacity, int32_t* record_count_dev, void* stream) {
+int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, uint32_t* group_mask_dev,
+                         float* records_dev, int64_t record_capacity, int32_t* record_count_dev, void* stream) {
     if (!h || !origin || !code_grid_dev || !records_dev || !record_count_dev) return fail(GVOM_EINVAL, "NULL argument");
     if (record_capacity < 1 || record_capacity > 2147483647LL) return fail(GVOM_EINVAL, "bad record capacity");
     std::lock_guard<std::mutex> lock(h->mu);
@@ -804,20 +822,31 @@ int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_gr
     MergeArgs A;
     build_sources(h, origin, false, &A);       // a rank without data contributes an empty grid
     CUDA_TRY(cudaMemsetAsync(record_count_dev, 0, sizeof(int), st));
-    k_partial_codes<<<h->sm_count * 8, 256, 0, st>>>(A, code_grid_dev, record_count_dev, records_dev, h->dp, (int)record_capacity);
-    k_partial_cells<<<h->sm_count * 4, 128, 0, st>>>(A, record_count_dev, records_dev, h->dp, (int)record_capacity);
+    MergeOut O{};
+    O.cmap = code_grid_dev; O.counter = record_count_dev; O.records = records_dev;
+    O.gmask = (h->p.xy_size % 8 == 0) ? group_mask_dev : nullptr; O.cap = (int)record_capacity;
+    launch_merge<MERGE_PARTIAL>(h, A, O, st);
+    k_partial_cells<<<h->grid_cells, 128, 0, st>>>(A, record_count_dev, records_dev, h->dp, (int)record_capacity);
     rec(h, EV_CODES, st);
-    h->stats.kernel_launches += 2;
+    h->stats.kernel_launches += 1;
     CUDA_TRY(cudaGetLastError());
     return GVOM_OK;
 }
 
-int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* code_grid_dev, const float* records_dev,
-                        const int32_t* record_counts_dev, int32_t nranks, int64_t record_capacity, double origin_out[3],
-                        int32_t* positive, int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem,
-                        void* stream) {
-    if (!h || !origin || !code_grid_dev || !records_dev || !record_counts_dev) return fail(GVOM_EINVAL, "NULL argument");
-    if (nranks < 1) return fail(GVOM_EINVAL, "nranks must be >= 1");
+int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* const* code_grids,
+                        const uint32_t* const* group_masks, int32_t n_grids,
+                        const float* const* records, const int32_t* const* record_counts, int32_t nranks,
+                        int64_t record_capacity, double origin_out[3], int32_t* positive, int32_t* negative,
+                        double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
+    if (!h || !origin || !code_grids || !records || !record_counts) return fail(GVOM_EINVAL, "NULL argument");
+    if (nranks < 1 || nranks > MAX_RANKS || n_grids < 1 || n_grids > MAX_RANKS) return fail(GVOM_EINVAL, "1..16 ranks / grids");
+    RecordSet R;
+    R.n = nranks;
+    for (int k = 0; k < n_grids; ++k) if (!code_grids[k]) return fail(GVOM_EINVAL, "NULL grid");
+    for (int k = 0; k < nranks; ++k) {
+        R.r[k] = records[k]; R.count[k] = record_counts[k];
+        if (!R.r[k] || !R.count[k]) return fail(GVOM_EINVAL, "NULL record buffer");
+    }
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
@@ -825,25 +854,45 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     Combined& pc = h->comb[h->cur];
     Combined& c = h->comb[1 - h->cur];
     for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];
+    // sources of the merge pass: every rank's encoded grid (unshifted: all are in the common frame), then
+    // this rank's copy of the previous combined map
+    MergeArgs A;
+    A.n = 0; A.use_masks = (h->p.xy_size % 8 == 0) ? 1 : 0;
+    for (int k = 0; k < n_grids; ++k) {
+        SlotRef& r = A.s[A.n++];
+        r = SlotRef{};
+        r.map = code_grids[k];
+        r.gmask = group_masks ? group_masks[k] : nullptr;
+        if (!r.gmask) A.use_masks = 0;
+    }
     SlotRef prev{};
     const int has_prev = pc.valid ? 1 : 0;
     if (has_prev) {
         prev.map = pc.index_map; prev.metrics = pc.metrics; prev.hit = pc.hit; prev.total = pc.total; prev.minh = pc.minh;
         prev.dx = (int)(origin[0] - pc.origin[0]); prev.dy = (int)(origin[1] - pc.origin[1]); prev.dz = (int)(origin[2] - pc.origin[2]);
         prev.is_prev = 1;
+        prev.gmask = pc.has_gmask ? pc.gmask : nullptr;
+        if (!prev.gmask) A.use_masks = 0;
+        A.s[A.n++] = prev;
     }
-    // the per-scan accumulator block doubles as the per-cell raw-moment scratch when it is big enough
     double* cacc = h->cacc;
-    k_finish_codes<<<h->sm_count * 8, 256, 0, st>>>(code_grid_dev, prev, has_prev, c.index_map, h->flags + 1, c.cell_voxel, cacc,
-                                                   c.hit, c.total, c.minh, h->col_minz, h->col_minz + h->S2, h->dp, (int)h->ccap);
-    k_scatter_records<<<h->sm_count * 4, 256, 0, st>>>(records_dev, record_counts_dev, nranks, record_capacity, c.index_map,
+    {
+        MergeOut O{};
+        O.cmap = c.index_map; O.counter = h->flags + 1; O.cell_voxel = c.cell_voxel;
+        O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
+        O.gmask = (h->p.xy_size % 8 == 0) ? c.gmask : nullptr; O.cap = (int)h->ccap;
+        O.cacc = cacc; O.chit = c.hit; O.ctot = c.total; O.cminh = c.minh;
+        launch_merge<MERGE_FINISH>(h, A, O, st);
+    }
+    rec(h, EV_CODES, st);
+    k_scatter_records<<<h->sm_count * 8, 256, 0, st>>>(R, record_capacity, c.index_map,
                                                       cacc, c.hit, c.total, c.minh);
-    k_finish_cells<<<h->sm_count * 4, 128, 0, st>>>(prev, has_prev, h->flags + 1, c.cell_voxel, cacc, c.hit, c.total, c.minh,
+    k_finish_cells<<<h->grid_cells, 128, 0, st>>>(prev, has_prev, h->flags + 1, c.cell_voxel, cacc, c.hit, c.total, c.minh,
                                                    c.metrics, c.eig, h->dp, (int)h->ccap);
     rec(h, EV_CELLS, st);
-    h->stats.kernel_launches += 3;
+    h->stats.kernel_launches += 2;
     h->prof_combine = h->profiling;
-    c.has_gmask = false;                                     // k_finish_codes writes no group mask
+    c.has_gmask = h->p.xy_size % 8 == 0;
     const int r = run_maps_and_output(h, c, origin_out, positive, negative, roughness, visibility, out_mem, st);
     if (r != GVOM_OK) return r;
     c.valid = true;

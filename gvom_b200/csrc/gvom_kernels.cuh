@@ -554,6 +554,28 @@ struct MergeArgs {
 //     in: an atomicMin per candidate on two S*S int maps, pre-filtered by a plain load.
 // ---------------------------------------------------------------------------
 constexpr int SLOT_BATCH = 4;
+constexpr int OCC_FLAG = 1 << 26;     // multi-GPU partial grids: "occupied" flag; below it: summed pass count
+constexpr int REC = 16;               // floats per multi-GPU cell record
+
+// What the merge pass does with the folded codes:
+//   MERGE_FULL    single-GPU combine: ring slots + previous map -> combined index map
+//   MERGE_PARTIAL multi-GPU, step 1: this rank's ring slots -> encoded grid (OCC_FLAG | passes) + record ids
+//   MERGE_FINISH  multi-GPU, step 2: every rank's encoded grid (own HBM or a peer's over NVLink, or one
+//                 all-reduced grid) + previous map -> combined index map, cell accumulators cleared
+enum { MERGE_FULL = 0, MERGE_PARTIAL = 1, MERGE_FINISH = 2 };
+
+struct MergeOut {
+    int* cmap;               // combined index map (FULL / FINISH) or encoded grid (PARTIAL)
+    int* counter;            // running cell / record counter
+    int* cell_voxel;         // FULL / FINISH: compact id -> voxel
+    float* records;          // PARTIAL: record rows, voxel id in column 0
+    int* col_occ;            // FULL / FINISH: per-column lowest occupied / free z
+    int* col_free;
+    unsigned* gmask;         // group mask of the output (VEC == 8) or NULL
+    double* cacc;            // FINISH: per-cell raw-moment accumulators (cleared here)
+    int* chit; int* ctot; float* cminh;
+    int cap;
+};
 
 __device__ __forceinline__ void column_min(int* __restrict__ col, int z) {
     if (z < *col) atomicMin(col, z);
@@ -590,11 +612,9 @@ __device__ __forceinline__ void load_codes(const int* __restrict__ row, int xs, 
 // (code >= 0 <=> sign bit clear, so AND the codes), otherwise its code is -1 - sum(passes) with
 // passes = -code-1 = ~code for free voxels and 0 for unknown (-1): sum += max(~code, 0).  Only
 // the previous combined map has an order dependent rule (the [-11,-1] window) and it comes last.
-template <int VEC>
+template <int VEC, int MODE>
 __global__ void __launch_bounds__(256, 3)
-k_merge_codes(MergeArgs A, int* __restrict__ cmap, int* __restrict__ counter, int* __restrict__ cell_voxel,
-              int* __restrict__ col_occ, int* __restrict__ col_free, DevParams P, int cap,
-              unsigned* __restrict__ gmask_out) {
+k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -602,11 +622,10 @@ k_merge_codes(MergeArgs A, int* __restrict__ cmap, int* __restrict__ counter, in
     const long long NQ = P.V / VEC;
     const long long NQp = (NQ + 31) & ~31LL;
     const int has_prev = (A.n > 0 && A.s[A.n - 1].is_prev) ? 1 : 0;
-    const int nreg = A.n - has_prev;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < NQp; q += step) {
-        int acc_and[VEC], sum[VEC];
+        int acc_and[VEC], sum[VEC], enc_or[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) { acc_and[j] = -1; sum[j] = 0; }
+        for (int j = 0; j < VEC; ++j) { acc_and[j] = -1; sum[j] = 0; enc_or[j] = 0; }
         int x = 0, y = 0, z = 0;
         int op[VEC];
 #pragma unroll
@@ -652,15 +671,28 @@ k_merge_codes(MergeArgs A, int* __restrict__ cmap, int* __restrict__ counter, in
                 int o[SLOT_BATCH][VEC];
 #pragma unroll
                 for (int u = 0; u < SLOT_BATCH; ++u) {
+                    const bool enc = MODE == MERGE_FINISH && !(has_prev && k0 + u == A.n - 1);
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) o[u][j] = -1;          // -1 = unknown: folds to nothing
-                    if (need & (1u << u)) load_codes<VEC>(A.s[k0 + u].map + row0[u], xs[u], S, o[u]);
+                    for (int j = 0; j < VEC; ++j) o[u][j] = enc ? 0 : -1;   // "unknown": folds to nothing
+                    if (need & (1u << u)) {
+                        if (enc) {                                          // encoded grids: unknown reads as 0
+                            int t[VEC];
+                            load_codes<VEC>(A.s[k0 + u].map + row0[u], xs[u], S, t);
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) o[u][j] = (xs[u] + j >= 0 && xs[u] + j < S) ? t[j] : 0;
+                        } else {
+                            load_codes<VEC>(A.s[k0 + u].map + row0[u], xs[u], S, o[u]);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < SLOT_BATCH; ++u) {
                     if (has_prev && k0 + u == A.n - 1) {
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) op[j] = o[u][j];
+                    } else if (MODE == MERGE_FINISH) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) { enc_or[j] |= o[u][j]; sum[j] += o[u][j] & (OCC_FLAG - 1); }
                     } else {
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) { acc_and[j] &= o[u][j]; sum[j] += max(~o[u][j], 0); }
@@ -668,12 +700,11 @@ k_merge_codes(MergeArgs A, int* __restrict__ cmap, int* __restrict__ counter, in
                 }
             }
         }
-        (void)nreg;
         bool occ[VEC];
         int c[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            occ[j] = acc_and[j] >= 0;
+            occ[j] = (acc_and[j] >= 0) || (enc_or[j] >= OCC_FLAG);
             c[j] = -1 - sum[j];
             if (!occ[j]) {                                    // previous combined map (gvom.py:1058-1063)
                 if (op[j] >= 0) { if (c[j] >= -11) occ[j] = true; }
@@ -682,64 +713,85 @@ k_merge_codes(MergeArgs A, int* __restrict__ cmap, int* __restrict__ counter, in
         }
         unsigned m[VEC];
         int nocc = 0;
-        bool any_free = false;
+        bool any_free = false, my_occ = false;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) { m[j] = __ballot_sync(FULL, occ[j]); nocc += __popc(m[j]); any_free |= (!occ[j] && c[j] < -1); }
+        for (int j = 0; j < VEC; ++j) {
+            m[j] = __ballot_sync(FULL, occ[j]); nocc += __popc(m[j]);
+            any_free |= (!occ[j] && c[j] < -1); my_occ |= occ[j];
+        }
         int base = 0;
         if (nocc) {
-            if (lane == 0) base = atomicAdd(counter, nocc);
+            if (lane == 0) base = atomicAdd(O.counter, nocc);
             base = __shfl_sync(FULL, base, 0);
         }
         bool known_any = false;
         if (q < NQ) {
-            int* colo = col_occ + (long long)y * S + x;
-            int* colf = col_free + (long long)y * S + x;
-            // current column minima, pre-filter of the atomicMin (vector loads, issued together)
-            int cur_occ[VEC], cur_free[VEC];
+            if (MODE == MERGE_PARTIAL) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) { cur_occ[j] = 0x7fffffff; cur_free[j] = 0x7fffffff; }
-            bool my_occ = false;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) my_occ |= occ[j];
-            if (VEC >= 4) {
-#pragma unroll
-                for (int g = 0; g < VEC / 4; ++g) {
-                    if (my_occ) {
-                        const int4 a = *(reinterpret_cast<const int4*>(colo) + g);
-                        cur_occ[4 * g] = a.x; cur_occ[4 * g + (VEC > 1 ? 1 : 0)] = a.y; cur_occ[4 * g + (VEC > 2 ? 2 : 0)] = a.z; cur_occ[4 * g + (VEC > 3 ? 3 : 0)] = a.w;
+                for (int j = 0; j < VEC; ++j) {
+                    if (occ[j]) {
+                        const int id = base + __popc(m[j] & lt);
+                        if (id < O.cap) O.records[(long long)id * REC] = __int_as_float((int)(q * VEC + j));
                     }
-                    if (any_free) {
-                        const int4 b = *(reinterpret_cast<const int4*>(colf) + g);
-                        cur_free[4 * g] = b.x; cur_free[4 * g + (VEC > 1 ? 1 : 0)] = b.y; cur_free[4 * g + (VEC > 2 ? 2 : 0)] = b.z; cur_free[4 * g + (VEC > 3 ? 3 : 0)] = b.w;
-                    }
+                    base += __popc(m[j]);
+                    c[j] = occ[j] ? OCC_FLAG : min(sum[j], OCC_FLAG - 1);
+                    known_any |= c[j] != 0;
                 }
             } else {
-                cur_occ[0] = colo[0]; cur_free[0] = colf[0];
-            }
+                int* colo = O.col_occ + (long long)y * S + x;
+                int* colf = O.col_free + (long long)y * S + x;
+                // current column minima, pre-filter of the atomicMin (vector loads, issued together)
+                int cur_occ[VEC], cur_free[VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                if (occ[j]) {
-                    const int id = base + __popc(m[j] & lt);
-                    if (id < cap) { c[j] = id; cell_voxel[id] = (int)(q * VEC + j); if (z < cur_occ[j]) atomicMin(colo + j, z); }
-                    else c[j] = -1;
-                } else if (c[j] < -1) {
-                    if (z < cur_free[j]) atomicMin(colf + j, z);
+                for (int j = 0; j < VEC; ++j) { cur_occ[j] = 0x7fffffff; cur_free[j] = 0x7fffffff; }
+                if (VEC >= 4) {
+#pragma unroll
+                    for (int g = 0; g < VEC / 4; ++g) {
+                        if (my_occ) {
+                            const int4 a = *(reinterpret_cast<const int4*>(colo) + g);
+                            cur_occ[4 * g] = a.x; cur_occ[4 * g + (VEC > 1 ? 1 : 0)] = a.y; cur_occ[4 * g + (VEC > 2 ? 2 : 0)] = a.z; cur_occ[4 * g + (VEC > 3 ? 3 : 0)] = a.w;
+                        }
+                        if (any_free) {
+                            const int4 b = *(reinterpret_cast<const int4*>(colf) + g);
+                            cur_free[4 * g] = b.x; cur_free[4 * g + (VEC > 1 ? 1 : 0)] = b.y; cur_free[4 * g + (VEC > 2 ? 2 : 0)] = b.z; cur_free[4 * g + (VEC > 3 ? 3 : 0)] = b.w;
+                        }
+                    }
+                } else {
+                    cur_occ[0] = colo[0]; cur_free[0] = colf[0];
                 }
-                base += __popc(m[j]);
-                known_any |= c[j] != -1;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if (occ[j]) {
+                        const int id = base + __popc(m[j] & lt);
+                        if (id < O.cap) {
+                            c[j] = id; O.cell_voxel[id] = (int)(q * VEC + j);
+                            if (z < cur_occ[j]) atomicMin(colo + j, z);
+                            if (MODE == MERGE_FINISH) {
+                                O.chit[id] = 0; O.ctot[id] = 0; O.cminh[id] = 1.0f;
+                                double2* a = reinterpret_cast<double2*>(O.cacc + (long long)id * 10);
+#pragma unroll
+                                for (int k = 0; k < 5; ++k) a[k] = make_double2(0.0, 0.0);
+                            }
+                        } else c[j] = -1;
+                    } else if (c[j] < -1) {
+                        if (z < cur_free[j]) atomicMin(colf + j, z);
+                    }
+                    base += __popc(m[j]);
+                    known_any |= c[j] != -1;
+                }
             }
             if (VEC >= 4) {
 #pragma unroll
                 for (int g = 0; g < VEC / 4; ++g)
-                    reinterpret_cast<int4*>(cmap)[q * (VEC / 4) + g] =
+                    reinterpret_cast<int4*>(O.cmap)[q * (VEC / 4) + g] =
                         make_int4(c[4 * g], c[4 * g + (VEC > 1 ? 1 : 0)], c[4 * g + (VEC > 2 ? 2 : 0)], c[4 * g + (VEC > 3 ? 3 : 0)]);
             } else {
-                cmap[q] = c[0];
+                O.cmap[q] = c[0];
             }
         }
-        if (VEC == 8) {                                       // group mask of the new combined map
+        if (VEC == 8 && O.gmask) {                            // group mask of the output grid
             const unsigned w = __ballot_sync(FULL, known_any);
-            if (lane == 0 && q < NQ) gmask_out[q >> 5] = w;
+            if (lane == 0 && q < NQ) O.gmask[q >> 5] = w;
         }
     }
 }
@@ -1175,45 +1227,12 @@ __global__ void k_debug_height(const double* __restrict__ height, const double* 
 // single Gvom holding all ranks' slots; moments are reduced commutatively (raw
 // sums in float64 atomics) and agree to float32 rounding.
 // ===========================================================================
-constexpr int OCC_FLAG = 1 << 26;
-constexpr int REC = 16;
+constexpr int MAX_RANKS = 16;
 
-__global__ void __launch_bounds__(256)
-k_partial_codes(MergeArgs A, int* __restrict__ grid, int* __restrict__ counter, float* __restrict__ records,
-                DevParams P, int cap) {
-    const int lane = threadIdx.x & 31;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    const long long Vp = (P.V + 31) & ~31LL;
-    const int S = P.S, Z = P.Z;
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < Vp; v += step) {
-        bool occ = false;
-        int passes = 0;
-        if (v < P.V) {
-            const int x = (int)(v % S), y = (int)((v / S) % S), z = (int)(v / ((long long)S * S));
-            for (int k = 0; k < A.n; ++k) {
-                const SlotRef& s = A.s[k];
-                const int xs = x + s.dx, ys = y + s.dy, zs = z + s.dz;
-                if (xs < 0 || xs >= S || ys < 0 || ys >= S || zs < 0 || zs >= Z) continue;
-                const int o = __ldg(s.map + (xs + (ys + (long long)zs * S) * S));
-                if (o >= 0) { occ = true; break; }
-                if (o < -1) passes += -o - 1;
-            }
-        }
-        const unsigned m = __ballot_sync(FULL, occ);
-        int base = 0;
-        if (m) {
-            if (lane == 0) base = atomicAdd(counter, __popc(m));
-            base = __shfl_sync(FULL, base, 0);
-        }
-        if (v < P.V) {
-            if (occ) {
-                const int id = base + __popc(m & ((1u << lane) - 1u));
-                if (id < cap) records[(long long)id * REC] = __int_as_float((int)v);
-            }
-            grid[v] = occ ? OCC_FLAG : min(passes, OCC_FLAG - 1);
-        }
-    }
-}
+// Per-rank exchange buffers as the finishing rank sees them.  With the NCCL exchange these
+// point into local (all-reduced / all-gathered) memory; with the peer-to-peer exchange they are
+// the OTHER GPUs' buffers mapped over NVLink, read directly by the kernels below.
+struct RecordSet { const float* r[MAX_RANKS]; const int* count[MAX_RANKS]; int n; };
 
 // per record: fold this rank's slots (reference order, float32 rounding as in C2)
 __global__ void __launch_bounds__(128)
@@ -1249,68 +1268,14 @@ k_partial_cells(MergeArgs A, const int* __restrict__ counter, float* __restrict_
     }
 }
 
-// final code per voxel from the all-reduced grid + this rank's copy of the previous
-// combined map (gvom.py:1037-1063); allots compact ids and clears the cell accumulators.
-__global__ void __launch_bounds__(256)
-k_finish_codes(const int* __restrict__ grid, SlotRef prev, int has_prev, int* __restrict__ cmap,
-               int* __restrict__ counter, int* __restrict__ cell_voxel, double* __restrict__ cacc,
-               int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
-               int* __restrict__ col_occ, int* __restrict__ col_free, DevParams P, int cap) {
-    const int lane = threadIdx.x & 31;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    const long long Vp = (P.V + 31) & ~31LL;
-    const int S = P.S, Z = P.Z;
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < Vp; v += step) {
-        bool occ = false;
-        int c = -1;
-        if (v < P.V) {
-            const int g = grid[v];
-            if (g >= OCC_FLAG) occ = true;
-            else {
-                c = -1 - g;
-                if (has_prev) {
-                    const int x = (int)(v % S), y = (int)((v / S) % S), z = (int)(v / ((long long)S * S));
-                    const int xs = x + prev.dx, ys = y + prev.dy, zs = z + prev.dz;
-                    if (!(xs < 0 || xs >= S || ys < 0 || ys >= S || zs < 0 || zs >= Z)) {
-                        const int o = __ldg(prev.map + (xs + (ys + (long long)zs * S) * S));
-                        if (o >= 0) { if (c >= -11) occ = true; }
-                        else if (o < -1) c += o + 1;
-                    }
-                }
-            }
-        }
-        const unsigned m = __ballot_sync(FULL, occ);
-        int base = 0;
-        if (m) {
-            if (lane == 0) base = atomicAdd(counter, __popc(m));
-            base = __shfl_sync(FULL, base, 0);
-        }
-        if (v < P.V) {
-            if (occ) {
-                const int id = base + __popc(m & ((1u << lane) - 1u));
-                if (id < cap) {
-                    c = id; cell_voxel[id] = (int)v; chit[id] = 0; ctot[id] = 0; cminh[id] = 1.0f;
-                    double* a = cacc + (long long)id * 10;
-#pragma unroll
-                    for (int k = 0; k < 10; ++k) a[k] = 0.0;
-                } else c = -1;
-            }
-            cmap[v] = c;
-            const int x = (int)(v % S), y = (int)((v / S) % S), z = (int)(v / ((long long)S * S));
-            if (c >= 0) column_min(col_occ + (long long)y * S + x, z);
-            else if (c < -1) column_min(col_free + (long long)y * S + x, z);
-        }
-    }
-}
-
 // scatter every rank's records into the cells: raw moments n, n*mu, n*(C + mu mu^T) in float64
 __global__ void __launch_bounds__(256)
-k_scatter_records(const float* __restrict__ records, const int* __restrict__ counts, int nranks, long long capacity,
+k_scatter_records(RecordSet R, long long capacity,
                   const int* __restrict__ cmap, double* __restrict__ cacc, int* __restrict__ chit,
                   int* __restrict__ ctot, float* __restrict__ cminh) {
-    for (int rk = 0; rk < nranks; ++rk) {
-        const int count = (int)min((long long)counts[rk], capacity);
-        const float* base = records + (long long)rk * capacity * REC;
+    for (int rk = 0; rk < R.n; ++rk) {
+        const int count = (int)min((long long)*R.count[rk], capacity);
+        const float* base = R.r[rk];
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
             const float* r = base + (long long)i * REC;
             const int id = cmap[__float_as_int(r[0])];

@@ -8,11 +8,18 @@ B200, and the exchange happens only at combine time:
 
   1. every rank folds its OWN slots into the common frame (gvom_combine_partial):
      a dense int32 code grid (occupied flag | summed pass count) + compact records
-  2. NCCL over NVLink (torch.distributed): all-reduce(sum) of the grids,
-     all-gather of the records and of a small header (count, origin)
-  3. every rank finishes the combine redundantly (gvom_combine_finish) -- cheaper
-     than broadcasting the result and it keeps the "previous combined map" state
-     replicated, so any rank can serve the maps.
+  2. exchange, one of
+       "p2p"  (default): the grids / records live in torch symmetric memory, i.e.
+              every rank's buffers are mapped into every other rank over NVLink.
+              One device-side barrier, then the finishing kernels read the peers'
+              buffers directly -- compute and "collective" are the same kernels,
+              no NCCL launch, no host synchronisation, no staging copy.
+       "nccl": all-reduce(sum) of the grids + all-gather of records and a header
+              through torch.distributed (the baseline; also the fallback when
+              symmetric memory cannot be set up).
+  3. every rank finishes the combine (gvom_combine_finish) -- redundantly, which is
+     cheaper than broadcasting the result and keeps the "previous combined map"
+     state replicated, so any rank can serve the maps.
 
 The result equals a single Gvom holding all ranks' slots: occupancy (OR), pass
 sums, hit/total sums and min heights are order independent in the reference's
@@ -27,11 +34,14 @@ import numpy as np
 from ._lib import GVOM_DEVICE, GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, check
 from .gvom import Gvom
 
+HEADER_DOUBLES = 8          # [valid, count, ox, oy, oz, pad...]
+
 
 def merge_headers(headers):
-    """headers: (world, 5) float64 rows [valid, count, ox, oy, oz] -> (origin or None, counts int32).
+    """headers: (world, >=5) float64 rows [valid, count, ox, oy, oz] -> (origin or None, counts int32).
     Pure host logic (covered by the CPU gloo test)."""
-    headers = np.asarray(headers, dtype=np.float64).reshape(-1, 5)
+    headers = np.asarray(headers, dtype=np.float64)
+    headers = headers.reshape(-1, headers.shape[-1])[:, :5]
     valid = headers[:, 0] > 0
     counts = np.where(valid, headers[:, 1], 0).astype(np.int32)
     if not valid.any():
@@ -42,11 +52,15 @@ def merge_headers(headers):
     return org.copy(), counts
 
 
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+
+
 class MultiGpuGvom(Gvom):
     """One rank of a multi-GPU Gvom.  Same API as Gvom; combine_maps() is collective
     (every rank must call it) and returns the same maps on every rank."""
 
-    def __init__(self, *args, group=None, torch_stream=None, **kw):
+    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", **kw):
         import torch
         import torch.distributed as dist
         self._dist, self._group = dist, group
@@ -58,31 +72,134 @@ class MultiGpuGvom(Gvom):
         super().__init__(*args, **kw)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        dev = f"cuda:{self.device}"
+        self._dev = torch.device(f"cuda:{self.device}")
         # a rank's records: at most one per occupied voxel of its slots
         self._rec_cap = int(min(self.voxel_count, self.buffer_size * self.max_points))
-        self._grid = torch.empty(self.voxel_count, dtype=torch.int32, device=dev)
-        self._records = torch.empty((self._rec_cap, RECORD_FLOATS), dtype=torch.float32, device=dev)
-        self._count = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._header = torch.zeros(5, dtype=torch.float64, device=dev)
-        self._headers = torch.zeros((self.world, 5), dtype=torch.float64, device=dev)
-        self._counts_dev = torch.zeros(self.world, dtype=torch.int32, device=dev)
         self._org_in = (C.c_double * 3)()
+        self._calls = 0
+        self.exchange = None
+        if exchange in ("auto", "p2p"):
+            try:
+                self._init_p2p()
+                self.exchange = "p2p"
+            except Exception as ex:          # symmetric memory unavailable: fall back (all ranks agree below)
+                self._p2p_error = repr(ex)
+                if exchange == "p2p":
+                    raise
+        # every rank must use the same exchange
+        ok = torch.tensor([1 if self.exchange == "p2p" else 0], device=self._dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.exchange = "nccl"
+            self._init_nccl()
+
+    # ------------------------------------------------------------------ buffers
+    def _layout(self):
+        """byte offsets inside one exchange set: grid | group mask | records | count(+pad) | header"""
+        V, cap = self.voxel_count, self._rec_cap
+        o_grid = 0
+        o_msk = (o_grid + 4 * V + 255) & ~255
+        o_rec = (o_msk + 4 * (V // 256 + 2) + 255) & ~255
+        o_cnt = (o_rec + 4 * RECORD_FLOATS * cap + 255) & ~255
+        o_hdr = o_cnt + 256
+        total = o_hdr + 8 * HEADER_DOUBLES + 256
+        return o_grid, o_msk, o_rec, o_cnt, o_hdr, total
+
+    def _init_p2p(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        torch, dist = self._torch, self._dist
+        group = self._group if self._group is not None else dist.group.WORLD
+        self._off = self._layout()
+        total = self._off[5]
+        self._sets = []
+        for _ in range(2):                   # double buffered: one device barrier per combine is enough
+            t = symm_mem.empty(total, dtype=torch.uint8, device=self._dev)
+            hdl = symm_mem.rendezvous(t, group)
+            t.zero_()
+            self._sets.append((t, hdl, [int(p) for p in hdl.buffer_ptrs]))
+        torch.cuda.synchronize(self._dev)
+        dist.barrier(group=self._group)
+        self._hdr_host = torch.zeros(HEADER_DOUBLES, dtype=torch.float64).pin_memory()
+
+    def _init_nccl(self):
+        torch = self._torch
+        self._grid = torch.empty(self.voxel_count, dtype=torch.int32, device=self._dev)
+        self._records = torch.empty((self._rec_cap, RECORD_FLOATS), dtype=torch.float32, device=self._dev)
+        self._count = torch.zeros(1, dtype=torch.int32, device=self._dev)
+        self._header = torch.zeros(HEADER_DOUBLES, dtype=torch.float64, device=self._dev)
+        self._headers = torch.zeros((self.world, HEADER_DOUBLES), dtype=torch.float64, device=self._dev)
+        self._counts_dev = torch.zeros(self.world, dtype=torch.int32, device=self._dev)
+
+    # ------------------------------------------------------------------ outputs
+    def _outputs(self, device_outputs):
+        torch, S = self._torch, self.xy_size
+        if device_outputs:
+            ti = torch.empty((3, S, S), dtype=torch.int32, device=self._dev)
+            rough = torch.empty((S, S), dtype=torch.float64, device=self._dev)
+            return (ti[0], ti[1], rough, ti[2]), (ti[0].data_ptr(), ti[1].data_ptr(), rough.data_ptr(), ti[2].data_ptr()), GVOM_DEVICE
+        pos, neg, rough, vis = self._out_arrays()
+        return (pos, neg, rough, vis), (pos.ctypes.data, neg.ctypes.data, rough.ctypes.data, vis.ctypes.data), GVOM_HOST
 
     def combine_maps(self, device_outputs=False):
+        self._calls += 1
+        if self.exchange == "p2p":
+            return self._combine_p2p(device_outputs)
+        return self._combine_nccl(device_outputs)
+
+    # ------------------------------------------------------------------ peer-to-peer exchange
+    def _combine_p2p(self, device_outputs):
+        torch, L = self._torch, self._L
+        t, hdl, ptrs = self._sets[self._calls & 1]
+        o_grid, o_msk, o_rec, o_cnt, o_hdr, _ = self._off
+        me = ptrs[self.rank]
+        have = L.gvom_newest_origin(self._h, self._org_in) != GVOM_NO_DATA
+        with torch.cuda.stream(self._tstream):
+            if have:
+                check(L.gvom_combine_partial(self._h, self._org_in, me + o_grid, me + o_msk, me + o_rec, self._rec_cap,
+                                             me + o_cnt, self._stream), "gvom_combine_partial")
+            else:
+                t[o_grid:o_rec].zero_()              # empty grid, empty group mask
+                t[o_cnt:o_cnt + 4].zero_()
+            hh = self._hdr_host
+            hh[0] = 1.0 if have else 0.0
+            hh[2], hh[3], hh[4] = (self._org_in[0], self._org_in[1], self._org_in[2]) if have else (0.0, 0.0, 0.0)
+            t[o_hdr:o_hdr + 8 * HEADER_DOUBLES].view(torch.float64).copy_(hh, non_blocking=True)
+            hdl.barrier(channel=0)           # device-side: every rank's partial results are visible to its peers
+            if not have:                     # start-up only: adopt the origin of a rank that has data
+                heads = np.stack([hdl.get_buffer(r, (HEADER_DOUBLES,), torch.float64, o_hdr // 8).cpu().numpy()
+                                  for r in range(self.world)])
+                origin, _ = merge_headers(heads)
+                if origin is None:
+                    print("ERROR: No data in buffer")
+                    return None
+                for k in range(3):
+                    self._org_in[k] = float(origin[k])
+            outs, optr, mem = self._outputs(device_outputs)
+            grids = _ptr_array([p + o_grid for p in ptrs])
+            masks = _ptr_array([p + o_msk for p in ptrs])
+            recs = _ptr_array([p + o_rec for p in ptrs])
+            cnts = _ptr_array([p + o_cnt for p in ptrs])
+            check(L.gvom_combine_finish(self._h, self._org_in, grids, masks, self.world, recs, cnts, self.world, self._rec_cap,
+                                        self._org_c, optr[0], optr[1], optr[2], optr[3], mem, self._stream),
+                  "gvom_combine_finish")
+        pos, neg, rough, vis = outs
+        return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
+
+    # ------------------------------------------------------------------ NCCL exchange
+    def _combine_nccl(self, device_outputs):
         torch, dist, L = self._torch, self._dist, self._L
         have = L.gvom_newest_origin(self._h, self._org_in) != GVOM_NO_DATA
         org = [self._org_in[0], self._org_in[1], self._org_in[2]] if have else [0.0, 0.0, 0.0]
         with torch.cuda.stream(self._tstream):
             if have:
-                check(L.gvom_combine_partial(self._h, self._org_in, self._grid.data_ptr(), self._records.data_ptr(),
+                check(L.gvom_combine_partial(self._h, self._org_in, self._grid.data_ptr(), None, self._records.data_ptr(),
                                              self._rec_cap, self._count.data_ptr(), self._stream),
                       "gvom_combine_partial")
             else:
                 self._grid.zero_()
                 self._count.zero_()
-            # header: [valid, count, origin]
-            self._header.copy_(torch.tensor([1.0 if have else 0.0, 0.0] + org, dtype=torch.float64), non_blocking=False)
+            hdr = [1.0 if have else 0.0, 0.0] + org + [0.0] * (HEADER_DOUBLES - 5)
+            self._header.copy_(torch.tensor(hdr, dtype=torch.float64), non_blocking=False)
             self._header[1:2] = self._count.to(torch.float64)
             dist.all_gather_into_tensor(self._headers, self._header, group=self._group)
             dist.all_reduce(self._grid, op=dist.ReduceOp.SUM, group=self._group)
@@ -94,22 +211,17 @@ class MultiGpuGvom(Gvom):
             if (counts > self._rec_cap).any():
                 raise RuntimeError("multi-GPU combine: a rank has more occupied voxels than its record capacity")
             maxc = max(1, int(counts.max()))
-            gathered = torch.empty((self.world, maxc, RECORD_FLOATS), dtype=torch.float32, device=self._records.device)
+            gathered = torch.empty((self.world, maxc, RECORD_FLOATS), dtype=torch.float32, device=self._dev)
             dist.all_gather_into_tensor(gathered, self._records[:maxc], group=self._group)
             self._counts_dev.copy_(torch.from_numpy(counts))
             for k in range(3):
                 self._org_in[k] = float(origin[k])
-            S = self.xy_size
-            if device_outputs:
-                ti = torch.empty((3, S, S), dtype=torch.int32, device=self._records.device)
-                rough = torch.empty((S, S), dtype=torch.float64, device=self._records.device)
-                ptrs, mem = (ti[0].data_ptr(), ti[1].data_ptr(), rough.data_ptr(), ti[2].data_ptr()), GVOM_DEVICE
-                pos, neg, vis = ti[0], ti[1], ti[2]
-            else:
-                pos, neg, rough, vis = self._out_arrays()
-                ptrs, mem = (pos.ctypes.data, neg.ctypes.data, rough.ctypes.data, vis.ctypes.data), GVOM_HOST
-            check(L.gvom_combine_finish(self._h, self._org_in, self._grid.data_ptr(), gathered.data_ptr(),
-                                        self._counts_dev.data_ptr(), self.world, maxc, self._org_c,
-                                        ptrs[0], ptrs[1], ptrs[2], ptrs[3], mem, self._stream),
+            outs, optr, mem = self._outputs(device_outputs)
+            grids = _ptr_array([self._grid.data_ptr()])
+            recs = _ptr_array([gathered.data_ptr() + 4 * RECORD_FLOATS * maxc * r for r in range(self.world)])
+            cnts = _ptr_array([self._counts_dev.data_ptr() + 4 * r for r in range(self.world)])
+            check(L.gvom_combine_finish(self._h, self._org_in, grids, None, 1, recs, cnts, self.world, maxc, self._org_c,
+                                        optr[0], optr[1], optr[2], optr[3], mem, self._stream),
                   "gvom_combine_finish")
+        pos, neg, rough, vis = outs
         return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)

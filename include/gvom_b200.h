@@ -116,20 +116,27 @@ int gvom_debug_inferred_height_map(GvomHandle* h, float* out_rows3);
  * Each rank pre-merges its own ring buffer into the common frame `origin`
  * (integral voxel units): a dense int32 code grid (V entries: occupied flag
  * 1<<26, else the pass count) and compact cell records (GVOM_RECORD_FLOATS
- * float32 each).  The caller sums the grids and gathers the records and their
- * counts across ranks (NCCL via torch.distributed); records_dev then holds
- * nranks blocks of record_capacity records and record_counts_dev nranks counts.
- * gvom_combine_finish() completes the combine on every rank.  See DESIGN.md. */
+ * float32 each).  The caller either sums the grids and gathers the records across ranks
+ * (NCCL via torch.distributed) or simply maps every rank's buffers into every other rank
+ * (peer-to-peer over NVLink); gvom_combine_finish() then completes the combine on every
+ * rank.  See DESIGN.md. */
 #define GVOM_RECORD_FLOATS 16   /* voxel id, hit, total, min_h, 10 metrics, 2 pad */
 int gvom_newest_origin(GvomHandle* h, double origin[3]);
+/* group_mask_dev (V/256 + 2 words, may be NULL): one bit per 8-voxel group of the code grid,
+ * set where the group holds anything; lets the finishing pass skip the (mostly empty) rest. */
 int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_grid_dev,
-                         float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
-                         void* stream);
-int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* code_grid_dev,
-                        const float* records_dev, const int32_t* record_counts_dev, int32_t nranks,
-                        int64_t record_capacity, double origin_out[3], int32_t* positive,
-                        int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem,
-                        void* stream);
+                         uint32_t* group_mask_dev, float* records_dev, int64_t record_capacity,
+                         int32_t* record_count_dev, void* stream);
+/* code_grids: n_grids device pointers -- ONE all-reduced grid (NCCL exchange) or one grid
+ * per rank (peer-to-peer exchange: the other GPUs' buffers mapped over NVLink are read directly by
+ * the finishing kernels).  records / record_counts: nranks device pointers each (a rank's records
+ * and its record count). */
+int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* const* code_grids,
+                        const uint32_t* const* group_masks /* n_grids entries, or NULL */,
+                        int32_t n_grids, const float* const* records,
+                        const int32_t* const* record_counts, int32_t nranks, int64_t record_capacity,
+                        double origin_out[3], int32_t* positive, int32_t* negative, double* roughness,
+                        int32_t* visibility, int32_t out_mem, void* stream);
 
 /* ---- test / tooling hooks (canonical parity dumps; not on the hot path) ---- */
 int gvom_slot_info(GvomHandle* h, int32_t slot, int32_t* valid, int64_t* cells, double origin[3]);

@@ -1,5 +1,5 @@
 """Run under torchrun (any world size): MultiGpuGvom over NCCL must equal one Gvom
-holding all ranks' slots.  argv[1] = backend ("nccl")."""
+holding all ranks' slots.  argv[1] = exchange ("nccl", "p2p" or "auto")."""
 import os
 import sys
 
@@ -27,7 +27,7 @@ def main():
     P1 = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B, robot_radius=2.0)
     PN = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B * world, robot_radius=2.0)
     fr = sensor_frames(world, 4)
-    g = MultiGpuGvom(*P1, device=local)
+    g = MultiGpuGvom(*P1, device=local, exchange=sys.argv[1] if len(sys.argv) > 1 else "auto")
     for step in range(4):
         g.Process_pointcloud(*fr[step][rank])
         out = g.combine_maps()
@@ -41,7 +41,7 @@ def main():
                       f"step {step} rank {rank}")
     dist.barrier()
     if rank == 0:
-        print("MULTI_RANK_OK")
+        print("MULTI_RANK_OK exchange=" + g.exchange + (" p2p_error=" + getattr(g, "_p2p_error", "") if g.exchange != "p2p" else ""))
     dist.destroy_process_group()
 
 

@@ -38,15 +38,17 @@ def sensor_frames(nranks, nsteps, beams=16, cols=256, wall=9.0):
     return out
 
 
-def local_exchange(ranks, outs_host=True):
-    """Emulate the collectives for handles living in one process. Returns per-rank 5-tuples."""
+def local_exchange(ranks, reduced=False):
+    """Emulate the exchange for handles living in one process.  reduced=False: every "rank" reads
+    every other rank's grid / records directly (what the peer-to-peer exchange does over NVLink);
+    reduced=True: one summed grid + gathered records (what the NCCL exchange delivers)."""
     import torch
     from gvom_b200._lib import GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, check
     g0 = ranks[0]
-    L, V, S = g0._L, g0.voxel_count, g0.xy_size
+    L, V = g0._L, g0.voxel_count
     dev = f"cuda:{g0.device}"
     org = (C.c_double * 3)()
-    grids, recs, counts = [], [], []
+    grids, masks, recs, counts = [], [], [], []
     origin = None
     for g in ranks:
         if L.gvom_newest_origin(g._h, org) != GVOM_NO_DATA and origin is None:
@@ -56,22 +58,27 @@ def local_exchange(ranks, outs_host=True):
     cap = int(min(V, g0.buffer_size * g0.max_points))
     for g in ranks:
         grid = torch.empty(V, dtype=torch.int32, device=dev)
+        msk = torch.empty(V // 256 + 2, dtype=torch.int32, device=dev)
         rec = torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-        check(L.gvom_combine_partial(g._h, o, grid.data_ptr(), rec.data_ptr(), cap, cnt.data_ptr(), None), "partial")
+        check(L.gvom_combine_partial(g._h, o, grid.data_ptr(), msk.data_ptr(), rec.data_ptr(), cap, cnt.data_ptr(), None),
+              "partial")
         torch.cuda.synchronize()
-        grids.append(grid); recs.append(rec); counts.append(int(cnt.item()))
-    total = torch.stack(grids).sum(0).to(torch.int32)
-    maxc = max(1, max(counts))
-    gathered = torch.stack([r[:maxc] for r in recs]).contiguous()
-    cdev = torch.tensor(counts, dtype=torch.int32, device=dev)
+        grids.append(grid); masks.append(msk); recs.append(rec); counts.append(cnt)
+    n = len(ranks)
+    parr = lambda ps: (C.c_void_p * len(ps))(*[C.c_void_p(int(p)) for p in ps])
+    if reduced:
+        total = torch.stack(grids).sum(0).to(torch.int32)
+        gptrs, mptrs, ng = parr([total.data_ptr()]), None, 1
+    else:
+        gptrs, mptrs, ng = parr([t.data_ptr() for t in grids]), parr([t.data_ptr() for t in masks]), n
+    rptrs, cptrs = parr([t.data_ptr() for t in recs]), parr([t.data_ptr() for t in counts])
     outs = []
     for g in ranks:
         pos, neg, rough, vis = g._out_arrays()
         oo = (C.c_double * 3)()
-        check(L.gvom_combine_finish(g._h, o, total.data_ptr(), gathered.data_ptr(), cdev.data_ptr(), len(ranks), maxc,
-                                    oo, pos.ctypes.data, neg.ctypes.data, rough.ctypes.data, vis.ctypes.data,
-                                    GVOM_HOST, None), "finish")
+        check(L.gvom_combine_finish(g._h, o, gptrs, mptrs, ng, rptrs, cptrs, n, cap, oo, pos.ctypes.data, neg.ctypes.data,
+                                    rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None), "finish")
         outs.append((np.array(list(oo)), pos, neg, rough, vis))
     return outs
 
@@ -85,8 +92,8 @@ def compare_state(a, b, what):
     assert np.allclose(a["metrics"], b["metrics"], rtol=1e-4, atol=2e-6), f"{what}: metrics"
 
 
-@pytest.mark.parametrize("nranks", [1, 2, 3])
-def test_partial_finish_equals_single(nranks):
+@pytest.mark.parametrize("nranks,reduced", [(1, False), (2, False), (3, False), (2, True)])
+def test_partial_finish_equals_single(nranks, reduced):
     from gvom_b200 import Gvom
     B = 2
     P1 = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B, robot_radius=2.0)
@@ -96,7 +103,7 @@ def test_partial_finish_equals_single(nranks):
     for step in range(5):
         for r in range(nranks):
             ranks[r].Process_pointcloud(*fr[step][r])
-        outs = local_exchange(ranks)
+        outs = local_exchange(ranks, reduced)
         # One Gvom with B*nranks slots holding the same scans: replay the whole history from
         # scratch (it needs the same chain of "previous combined map" states), feeding before
         # every combine the scans the rank rings hold at that step, newest step last.
@@ -117,8 +124,10 @@ def test_nccl_two_ranks(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     script = os.path.join(ROOT, "tests", "multi_rank_check.py")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", script, "nccl"],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "MULTI_RANK_OK" in r.stdout
+    for port, exchange in ((29533, "nccl"), (29534, "auto")):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port), script, exchange],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        assert "MULTI_RANK_OK" in r.stdout, r.stdout[-2000:]
+        print(r.stdout[-300:])
