@@ -1,0 +1,132 @@
+"""World-size-2 `gloo` test of the multi-GPU combine PROTOCOL on CPU (no CUDA).
+
+The device kernels cannot run here, so each rank models its partial result with the CPU oracle
+and numpy: ring slots folded into the common frame as an encoded grid (1<<26 = occupied, else
+summed passes), exactly what gvom_combine_partial produces.  The ranks exchange with the same
+collectives the NCCL path uses (all_gather of the header, all_reduce(sum) of the grid), decode
+like gvom_combine_finish does, and rank 0 checks the result against ONE oracle Gvom that holds
+both ranks' scans.  This pins: the encoding, the order independence of the fold, the header
+logic (merge_headers) and the previous-map rule applied after the cross-rank sum."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OCC = 1 << 26
+
+
+def shifted(src, d, S, Z, fill):
+    """src indexed [z,y,x] in its own frame -> array in the combined frame (combined voxel (x,y,z) looks at
+    source voxel (x+dx, y+dy, z+dz), gvom.py:1017-1027); outside the source: `fill`."""
+    out = np.full((Z, S, S), fill, src.dtype)
+    dx, dy, dz = (int(v) for v in d)
+
+    def rng(n, dd):
+        lo, hi = max(0, -dd), min(n, n - dd)
+        return (slice(lo, hi), slice(lo + dd, hi + dd)) if hi > lo else (slice(0, 0), slice(0, 0))
+    (zc, zs), (yc, ys), (xc, xs) = rng(Z, dz), rng(S, dy), rng(S, dx)
+    out[zc, yc, xc] = src[zs, ys, xs]
+    return out
+
+
+def partial_grid(o, origin, S, Z):
+    """numpy model of gvom_combine_partial's code grid for the oracle `o` (its own valid slots)."""
+    occ = np.zeros((Z, S, S), bool)
+    passes = np.zeros((Z, S, S), np.int64)
+    for i in range(o.buffer_size):
+        if o.origin_buffer[i] is None:
+            continue
+        idx = shifted(o.index_buffer[i].reshape(Z, S, S), origin - o.origin_buffer[i], S, Z, -1)
+        occ |= idx >= 0
+        passes += np.where(idx < -1, -idx - 1, 0)
+    return np.where(occ, OCC, np.minimum(passes, OCC - 1)).astype(np.int32)
+
+
+def finish_codes(total, prev_codes, prev_origin, origin, S, Z):
+    """numpy model of the code part of gvom_combine_finish: canonical codes (occupied -> 0)."""
+    occ = total >= OCC
+    c = -1 - (total.astype(np.int64) & (OCC - 1))
+    if prev_codes is not None:
+        p = shifted(prev_codes, origin - prev_origin, S, Z, -1)
+        take = ~occ & (p >= 0) & (c >= -11)                    # gvom.py:1058
+        add = ~occ & (p < -1)
+        c = np.where(add, c + p + 1, c)
+        occ = occ | take
+    return np.where(occ, 0, c).astype(np.int32)
+
+
+def worker(rank, world, port, result):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gvom_b200 import synth
+    from gvom_b200.multi import HEADER_DOUBLES, merge_headers
+    from oracle.gvom_oracle import OracleGvom
+    from test_multi_gpu import sensor_frames
+    S, Z, B = 32, 8, 2
+    P1 = synth.params_tuple(xy_size=S, z_size=Z, buffer_size=B, robot_radius=2.0)
+    PN = synth.params_tuple(xy_size=S, z_size=Z, buffer_size=B * world, robot_radius=2.0)
+    fr = sensor_frames(world, 4, beams=8, cols=64, wall=5.0)
+    mine = OracleGvom(*P1)
+    ref = OracleGvom(*PN) if rank == 0 else None           # one Gvom holding all ranks' scans
+    prev_codes, prev_origin = None, None
+    ok = True
+    for step in range(4):
+        if not (rank == 1 and step == 0):                      # rank 1 has no data at the first combine
+            mine.Process_pointcloud(*fr[step][rank])
+        have = mine.origin_buffer[mine.last_buffer_index] is not None
+        org = mine.origin_buffer[mine.last_buffer_index] if have else np.zeros(3)
+        hdr = torch.zeros(HEADER_DOUBLES, dtype=torch.float64)
+        hdr[0], hdr[2:5] = float(have), torch.from_numpy(np.asarray(org, np.float64))
+        heads = [torch.zeros_like(hdr) for _ in range(world)]
+        dist.all_gather(heads, hdr)
+        origin, _ = merge_headers(torch.stack(heads).numpy())
+        assert origin is not None
+        grid = partial_grid(mine, origin, S, Z) if have else np.zeros((Z, S, S), np.int32)
+        t = torch.from_numpy(grid.copy())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        codes = finish_codes(t.numpy(), prev_codes, prev_origin, origin, S, Z)
+        # every rank must hold the same result (replicated state)
+        both = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(both, torch.from_numpy(codes.copy()))
+        ok &= bool(torch.equal(both[0], both[1]))
+        prev_codes, prev_origin = codes, origin
+        if rank == 0:
+            # the big ring (B*world slots) receives this step's scans; with rank 1 silent at step 0 the
+            # slots it overwrites are exactly the ones the per-rank rings (B slots each) drop
+            for r in range(world):
+                if not (r == 1 and step == 0):
+                    ref.Process_pointcloud(*fr[step][r])
+            ref.combine_maps()
+            want = np.where(ref.combined_index_map >= 0, 0, ref.combined_index_map).reshape(Z, S, S)
+            ok &= bool(np.array_equal(codes, want))
+    result[rank] = ok
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_protocol_gloo():
+    world = 2
+    with mp.Manager() as m:
+        result = m.dict()
+        mp.spawn(worker, args=(world, 29631, result), nprocs=world, join=True)
+        assert dict(result) == {0: True, 1: True}
+
+
+def test_merge_headers():
+    from gvom_b200.multi import merge_headers
+    h = np.zeros((3, 8))
+    assert merge_headers(h)[0] is None
+    h[1, :5] = [1, 7, 10, 20, -3]
+    h[2, :5] = [1, 9, 10, 20, -3]
+    org, counts = merge_headers(h)
+    assert list(org) == [10, 20, -3] and list(counts) == [0, 7, 9]
+    h[2, 2] = 11
+    with pytest.raises(RuntimeError):
+        merge_headers(h)
