@@ -189,6 +189,16 @@ def scenario(name):
             pc, ego, T = frame(i, 128, 2048, wall_radius=200.0)
             steps += [("scan", pc, ego, T), ("combine",)]
         return P, steps
+    if name == "dense":
+        # BASELINE.json configs[3]: 2M-point aggregated cloud (16 x 128x1024 scans), 1024x1024x128 grid @0.1 m
+        P = params_tuple(xy_resolution=0.1, z_resolution=0.1, xy_size=1024, z_size=128, buffer_size=4)
+        steps = []
+        for i in range(2):
+            ego = (100.0 + 0.4 * i, 50.0 + 0.1 * i, 1.0)
+            T = pose_matrix(ego, 0.01 * i)
+            pc = np.concatenate([synthetic_scan(128, 1024, seed=5000 + 16 * i + k, ego=ego) for k in range(16)], axis=0)
+            steps += [("scan", np.ascontiguousarray(pc), ego, T), ("combine",)]
+        return P, steps
     raise KeyError(name)
 
 
