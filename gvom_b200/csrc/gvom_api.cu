@@ -17,7 +17,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -71,6 +74,12 @@ struct Combined {
     bool valid = false;
     int64_t cells = 0;
 };
+
+// Pageable host clouds have to pass through pinned memory; a single-threaded memcpy of a 6.3 MB scan costs
+// more than everything the GPU does with it, so the staging copy is split over a few persistent threads.
+}  // namespace
+#include "gvom_host.h"
+namespace {
 
 struct Carver {                    // sub-allocates a workspace block, 256-byte aligned
     char* base;
@@ -133,6 +142,8 @@ struct GvomHandle {
     int sm_count = 148;
     int grid_index = 0, grid_codes = 0, grid_cells = 0, grid_gather = 0;   // resident grids (set at create)
     GvomStats stats{};
+    float last_stage_copy_ms = 0.f;       // host time of the last pageable->pinned staging copy
+    CopyPool* pool = nullptr;             // staging threads for pageable input (created on first use)
     std::mutex mu;
 };
 
@@ -218,6 +229,19 @@ void fill_sizes(GvomHandle* h, const GvomParams* p, int64_t max_points, int64_t 
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor in
+// the stream drains; it calls pdl_wait() before touching the predecessor's results.
+template <typename... KArgs, typename... Args>
+void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 // grid of a grid-stride kernel: exactly the blocks that are resident at once (one wave, no tail)
 template <typename K>
 int resident_grid(K kernel, int threads, int sm_count, size_t smem = 0) {
@@ -269,11 +293,11 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
 template <int MODE>
 void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStream_t st) {
     if (h->p.xy_size % 8 == 0)
-        k_merge_codes<8, MODE><<<h->grid_codes, 256, 0, st>>>(A, O, h->dp);
+        launch(k_merge_codes<8, MODE>, dim3(h->grid_codes), dim3(256), 0, st, A, O, h->dp);
     else if (h->p.xy_size % 4 == 0)
-        k_merge_codes<4, MODE><<<h->grid_codes, 256, 0, st>>>(A, O, h->dp);
+        launch(k_merge_codes<4, MODE>, dim3(h->grid_codes), dim3(256), 0, st, A, O, h->dp);
     else
-        k_merge_codes<1, MODE><<<h->grid_codes, 256, 0, st>>>(A, O, h->dp);
+        launch(k_merge_codes<1, MODE>, dim3(h->grid_codes), dim3(256), 0, st, A, O, h->dp);
     h->stats.kernel_launches++;
 }
 
@@ -289,12 +313,12 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
     if (direct_dev) { pos = positive; neg = negative; vis = visibility; rough = roughness; }
     const int W = (h->p.xy_size + 31) / 32;
     unsigned* known = h->known; unsigned* knownT = h->known + (size_t)h->p.xy_size * W;
-    k_column_maps<<<dim3(W, W), 1024, 0, st>>>(c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
+    launch(k_column_maps, dim3(W, W), dim3(1024), 0, st, c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
                                                c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, height, inferred, known, knownT,
                                                h->flags + 1, c.counter);
     const size_t mask_bytes = 2 * (size_t)h->p.xy_size * W * sizeof(unsigned);
     const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
-    k_surface_maps<<<blocks_for(S2, 256), 256, in_smem ? mask_bytes : 0, st>>>(c.index_map, c.hit, c.total, height, inferred, known, knownT,
+    launch(k_surface_maps, dim3(blocks_for(S2, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit, c.total, height, inferred, known, knownT,
                                                                             c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
                                                                             in_smem, h->col_minz, h->flags + 1);
     h->stats.kernel_launches += 2;
@@ -431,6 +455,7 @@ int gvom_destroy(GvomHandle* h) {
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]);
     cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
+    delete h->pool;
     delete h;
     return GVOM_OK;
 }
@@ -474,12 +499,13 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
     auto launch_k1 = [&](const void* base, int64_t first, int64_t count, void* world_out) {
         if (count <= 0) return;
         const char* p0 = static_cast<const char*>(base) + (size_t)first * row;
+        if (world_out) world_out = static_cast<char*>(world_out) + (size_t)first * row;
         const int blocks = blocks_for(count, 256);
         if (dtype == GVOM_F32)
-            k_voxelize_raycast<float><<<blocks, 256, 0, st>>>((const float*)p0, stride, (int)count, tf, fr, h->dp, h->hit_grid,
+            launch(k_voxelize_raycast<float>, dim3(blocks), dim3(256), 0, st, (const float*)p0, stride, (int)count, tf, fr, h->dp, h->hit_grid,
                                                               h->total_grid, (float*)world_out);
         else
-            k_voxelize_raycast<double><<<blocks, 256, 0, st>>>((const double*)p0, stride, (int)count, tf, fr, h->dp, h->hit_grid,
+            launch(k_voxelize_raycast<double>, dim3(blocks), dim3(256), 0, st, (const double*)p0, stride, (int)count, tf, fr, h->dp, h->hit_grid,
                                                                h->total_grid, (double*)world_out);
         h->stats.kernel_launches++;
     };
@@ -497,15 +523,34 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
         if (!pinned && h->stage_busy) CUDA_TRY(cudaEventSynchronize(h->ev_stage));   // stage_host still being read
         void* mapped = nullptr;
         if (h->zero_copy) {
-            const void* hostp = points;
-            if (!pinned) { memcpy(h->stage_host, points, (size_t)n * row); hostp = h->stage_host; }
+            const void* hostp = pinned ? points : h->stage_host;
             if (cudaHostGetDevicePointer(&mapped, const_cast<void*>(hostp), 0) != cudaSuccess) { cudaGetLastError(); mapped = nullptr; }
             if (mapped && ((uintptr_t)mapped & 15)) mapped = nullptr;   // the staged loads are 128-bit
         }
         if (mapped) {
-            // zero-copy: one kernel streams the cloud over PCIe while it ray-casts; no DMA op, no staging pass
+            // zero-copy: K1 streams the cloud over PCIe while it ray-casts; no DMA op, no staging pass on the GPU
             rec(h, EV_H2D, st);
-            launch_k1(mapped, 0, n, h->stage_dev);
+            if (pinned) {
+                launch_k1(mapped, 0, n, h->stage_dev);
+            } else {
+                // pageable: the staging copy (threaded, non-temporal) is pipelined with the kernel chunk by chunk
+                if (!h->pool) {
+                    int helpers = 3;
+                    if (const char* e = getenv("GVOM_COPY_THREADS")) helpers = std::max(0, atoi(e) - 1);
+                    h->pool = new CopyPool(helpers);
+                }
+                const auto t0 = std::chrono::steady_clock::now();
+                const int nchunks = n >= 131072 ? 4 : 1;
+                const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~int64_t(255);
+                for (int c = 0; c < nchunks; ++c) {
+                    const int64_t first = c * per, count = std::min<int64_t>(per, n - first);
+                    if (count <= 0) break;
+                    h->pool->copy(h->stage_host + (size_t)first * row, static_cast<const char*>(points) + (size_t)first * row,
+                                  (size_t)count * row);
+                    launch_k1(mapped, first, count, h->stage_dev);
+                }
+                h->last_stage_copy_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            }
             CUDA_TRY(cudaEventRecord(h->ev_stage, st));
             tf_moments.enabled = 0;
         } else {
@@ -539,15 +584,15 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
     const int cap = (int)h->cap;
     rec(h, EV_RAYCAST, st);
     if (h->p.xy_size % 8 == 0) {
-        k_build_index<8><<<h->grid_index, 256, 0, st>>>(h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
+        launch(k_build_index<8>, dim3(h->grid_index), dim3(256), 0, st, h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
                                                          s.cell_voxel, h->acc, s.minh, h->V, cap, s.gmask);
         s.has_gmask = true;
     } else {
         if (h->V % 4 == 0)
-            k_build_index<4><<<h->grid_index, 256, 0, st>>>(h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
+            launch(k_build_index<4>, dim3(h->grid_index), dim3(256), 0, st, h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
                                                              s.cell_voxel, h->acc, s.minh, h->V, cap, nullptr);
         else
-            k_build_index<1><<<h->grid_index, 256, 0, st>>>(h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
+            launch(k_build_index<1>, dim3(h->grid_index), dim3(256), 0, st, h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
                                                              s.cell_voxel, h->acc, s.minh, h->V, cap, nullptr);
         s.has_gmask = false;
     }
@@ -556,18 +601,18 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
     {   // always launched (>= 1 block): thread 0 also publishes the slot's cell count
         const int mb = nb > 0 ? nb : 1;
         if (dtype == GVOM_F32)
-            k_moments<float><<<mb, 256, 0, st>>>((const float*)src, stride, (int)n, tf_moments, fr, h->dp, s.index_map, h->acc, s.minh,
+            launch(k_moments<float>, dim3(mb), dim3(256), 0, st, (const float*)src, stride, (int)n, tf_moments, fr, h->dp, s.index_map, h->acc, s.minh,
                                                  h->flags, s.counter);
         else
-            k_moments<double><<<mb, 256, 0, st>>>((const double*)src, stride, (int)n, tf_moments, fr, h->dp, s.index_map, h->acc, s.minh,
+            launch(k_moments<double>, dim3(mb), dim3(256), 0, st, (const double*)src, stride, (int)n, tf_moments, fr, h->dp, s.index_map, h->acc, s.minh,
                                                   h->flags, s.counter);
         h->stats.kernel_launches++;
     }
     rec(h, EV_MOMENTS, st);
     if (h->p.xy_eigen_dist == 1 && h->p.z_eigen_dist == 1)
-        k_gather_metrics<1, 1><<<h->grid_gather, 256, 0, st>>>(s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+        launch(k_gather_metrics<1, 1>, dim3(h->grid_gather), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
     else
-        k_gather_metrics<-1, -1><<<h->grid_gather, 256, 0, st>>>(s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+        launch(k_gather_metrics<-1, -1>, dim3(h->grid_gather), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
     h->stats.kernel_launches++;
     rec(h, EV_GATHER, st);
     CUDA_TRY(cudaGetLastError());
@@ -607,7 +652,7 @@ int gvom_combine_maps(GvomHandle* h, double origin[3], int32_t* positive, int32_
         launch_merge<MERGE_FULL>(h, A, O, st);
     }
     rec(h, EV_CODES, st);
-    k_merge_cells<<<h->grid_cells, 128, 0, st>>>(A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
+    launch(k_merge_cells, dim3(h->grid_cells), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
                                                   h->dp, (int)h->ccap);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 1;
@@ -762,6 +807,7 @@ int gvom_stage_times(GvomHandle* h, float ms[16]) {
         const int b[5] = {EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER};
         for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], h->ev[a[i]], h->ev[b[i]]));
     }
+    ms[9] = h->last_stage_copy_ms;
     if (h->prof_combine) {
         const int a[4] = {EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS};
         const int b[4] = {EV_CODES, EV_CELLS, EV_MAPS, EV_D2H};
@@ -826,7 +872,7 @@ int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_gr
     O.cmap = code_grid_dev; O.counter = record_count_dev; O.records = records_dev;
     O.gmask = (h->p.xy_size % 8 == 0) ? group_mask_dev : nullptr; O.cap = (int)record_capacity;
     launch_merge<MERGE_PARTIAL>(h, A, O, st);
-    k_partial_cells<<<h->grid_cells, 128, 0, st>>>(A, record_count_dev, records_dev, h->dp, (int)record_capacity);
+    launch(k_partial_cells, dim3(h->grid_cells), dim3(128), 0, st, A, record_count_dev, records_dev, h->dp, (int)record_capacity);
     rec(h, EV_CODES, st);
     h->stats.kernel_launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -885,9 +931,9 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
         launch_merge<MERGE_FINISH>(h, A, O, st);
     }
     rec(h, EV_CODES, st);
-    k_scatter_records<<<h->sm_count * 8, 256, 0, st>>>(R, record_capacity, c.index_map,
+    launch(k_scatter_records, dim3(h->sm_count * 8), dim3(256), 0, st, R, record_capacity, c.index_map,
                                                       cacc, c.hit, c.total, c.minh);
-    k_finish_cells<<<h->grid_cells, 128, 0, st>>>(prev, has_prev, h->flags + 1, c.cell_voxel, cacc, c.hit, c.total, c.minh,
+    launch(k_finish_cells, dim3(h->grid_cells), dim3(128), 0, st, prev, has_prev, h->flags + 1, c.cell_voxel, cacc, c.hit, c.total, c.minh,
                                                    c.metrics, c.eig, h->dp, (int)h->ccap);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 2;

@@ -20,6 +20,15 @@
 namespace gvom {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// Programmatic dependent launch: every pipeline kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its blocks are scheduled while the previous
+// kernel of the stream drains; nothing may touch that kernel's output before this call returns.
+__device__ __forceinline__ void pdl_wait() {
+#if __CUDA_ARCH__ >= 900
+    cudaGridDependencySynchronize();
+#endif
+}
 constexpr int MAX_SLOTS = 64;   // ring-buffer slots a single merge pass can take
 constexpr int ACC = 20;         // per-cell accumulators: [0..9] own voxel, [10..19] apron
 
@@ -135,6 +144,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 8)
 k_voxelize_raycast(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevParams P,
                    int* __restrict__ hit, int* __restrict__ total, T* __restrict__ world_out) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const double ox = fr.origin[0], oy = fr.origin[1], oz = fr.origin[2];
@@ -256,6 +266,7 @@ k_build_index(int* __restrict__ hit, int* __restrict__ total, int* __restrict__ 
               int* __restrict__ counter, int* __restrict__ hit_c, int* __restrict__ total_c,
               int* __restrict__ cell_voxel, double* __restrict__ acc, float* __restrict__ minh,
               long long V, int cap, unsigned* __restrict__ gmask) {
+    pdl_wait();
     constexpr int U = 2;                                // items in flight per thread
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -364,6 +375,7 @@ __global__ void __launch_bounds__(256)
 k_moments(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevParams P,
           const int* __restrict__ index_map, double* __restrict__ acc, float* __restrict__ minh,
           const int* __restrict__ scratch_count, int* __restrict__ slot_count) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     if (i == 0) *slot_count = *scratch_count;             // K2's running counter -> the slot's cell count
@@ -463,6 +475,7 @@ __global__ void __launch_bounds__(256)
 k_gather_metrics(const int* __restrict__ index_map, const int* __restrict__ cell_voxel,
                  const int* __restrict__ counter, const double* __restrict__ acc,
                  double* __restrict__ metrics, DevParams P, int cap, int* __restrict__ scratch_count) {
+    pdl_wait();
     const int count = min(*counter, cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) *scratch_count = 0;   // ready for the next scan's K2
     const int sub = threadIdx.x & (LPC - 1);
@@ -553,7 +566,7 @@ struct MergeArgs {
 //     (gvom.py:560-590: lowest occupied / lowest free voxel of every column) is fused
 //     in: an atomicMin per candidate on two S*S int maps, pre-filtered by a plain load.
 // ---------------------------------------------------------------------------
-constexpr int SLOT_BATCH = 4;
+constexpr int SLOT_BATCH = 3;          // sources in flight per thread (B = 4: 4 slots + new map + previous = 2 batches)
 constexpr int OCC_FLAG = 1 << 26;     // multi-GPU partial grids: "occupied" flag; below it: summed pass count
 constexpr int REC = 16;               // floats per multi-GPU cell record
 
@@ -615,6 +628,7 @@ __device__ __forceinline__ void load_codes(const int* __restrict__ row, int xs, 
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(256, 3)
 k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -645,7 +659,7 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
             // Phase A: which sources hold anything but "unknown" here (group-mask words, independent
             // loads).  Phase B: the code loads of those sources, all in flight together.  Phase C: fold.
             for (int k0 = 0; k0 < A.n; k0 += SLOT_BATCH) {
-                long long row0[SLOT_BATCH];
+                int row0[SLOT_BATCH];                              // V < 2^31: 32-bit linear indices
                 int xs[SLOT_BATCH];
                 unsigned need = 0;
                 unsigned w0[SLOT_BATCH], w1[SLOT_BATCH];
@@ -657,13 +671,16 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
                     const int ys = y + s.dy, zs = z + s.dz;
                     xs[u] = x + s.dx;
                     const int a = max(xs[u], 0), b = min(xs[u] + VEC - 1, S - 1);
-                    const bool in = (k0 + u < A.n) && ys >= 0 && ys < S && zs >= 0 && zs < Z && a <= b;
-                    row0[u] = in ? ((long long)zs * S + ys) * S : 0;
+                    const bool in = (k0 + u < A.n) && ((unsigned)ys < (unsigned)S) && ((unsigned)zs < (unsigned)Z) && a <= b;
+                    row0[u] = in ? (zs * S + ys) * S : 0;
                     if (in) need |= 1u << u;
-                    const long long g0 = in ? (row0[u] + a) >> 3 : 0, g1 = in ? (row0[u] + b) >> 3 : 0;
-                    b0[u] = (int)(g0 & 31); b1[u] = (int)(g1 & 31);
+                    const int g0 = in ? (row0[u] + a) >> 3 : 0, g1 = in ? (row0[u] + b) >> 3 : 0;
+                    b0[u] = g0 & 31; b1[u] = g1 & 31;
                     w0[u] = 0xffffffffu; w1[u] = 0xffffffffu;
-                    if (A.use_masks) { w0[u] = __ldg(s.gmask + (g0 >> 5)); w1[u] = __ldg(s.gmask + (g1 >> 5)); }
+                    if (A.use_masks) {
+                        w0[u] = __ldg(s.gmask + (g0 >> 5));
+                        w1[u] = ((g1 >> 5) == (g0 >> 5)) ? w0[u] : __ldg(s.gmask + (g1 >> 5));
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < SLOT_BATCH; ++u)
@@ -737,9 +754,12 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
                     c[j] = occ[j] ? OCC_FLAG : min(sum[j], OCC_FLAG - 1);
                     known_any |= c[j] != 0;
                 }
+            } else if (!my_occ && !any_free) {                    // nothing known here (the common case)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) c[j] = -1;
             } else {
-                int* colo = O.col_occ + (long long)y * S + x;
-                int* colf = O.col_free + (long long)y * S + x;
+                int* colo = O.col_occ + y * S + x;
+                int* colf = O.col_free + y * S + x;
                 // current column minima, pre-filter of the atomicMin (vector loads, issued together)
                 int cur_occ[VEC], cur_free[VEC];
 #pragma unroll
@@ -860,6 +880,7 @@ __global__ void __launch_bounds__(128)
 k_merge_cells(MergeArgs A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
               int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
               float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap) {
+    pdl_wait();
     const int count = min(*counter, cap);
     const int S = P.S, Z = P.Z;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
@@ -929,6 +950,7 @@ k_column_maps(const int* __restrict__ cmap, const float* __restrict__ cminh, con
               DevParams P, double* __restrict__ height, double* __restrict__ inferred,
               unsigned* __restrict__ known, unsigned* __restrict__ knownT,
               const int* __restrict__ scratch_count, int* __restrict__ map_count) {
+    pdl_wait();
     __shared__ unsigned char flag[32][33];
     const int S = P.S;
     const int W = (S + 31) >> 5;                          // words per bit row
@@ -995,10 +1017,16 @@ k_surface_maps(const int* __restrict__ cmap, const int* __restrict__ chit, const
                DevParams P, double* __restrict__ rough, double* __restrict__ xs, double* __restrict__ ys,
                double* __restrict__ guessed, int* __restrict__ pos, int* __restrict__ neg, int* __restrict__ vis,
                int masks_in_smem, int* __restrict__ col_minz, int* __restrict__ scratch_count) {
+    pdl_wait();
     extern __shared__ unsigned smask[];
     const int S = P.S, Z = P.Z;
     const int W = (S + 31) >> 5;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // 128 cells per block, two warp-groups: warps 0-3 fit the plane (slope, roughness, positive
+    // obstacles), warps 4-7 run the ring search (guessed height, negative obstacles, visibility).  The
+    // two chains are independent and both latency bound, so running them side by side doubles the
+    // warps an SM can switch between.
+    const int role = threadIdx.x >> 7;
+    const int t = blockIdx.x * 128 + (threadIdx.x & 127);
     // both bit maps (2*S*W words, 16 KB at S = 256) go to shared memory when they fit: the ring
     // search then never waits on L2
     const unsigned* known = known_g;
@@ -1014,11 +1042,62 @@ k_surface_maps(const int* __restrict__ cmap, const int* __restrict__ chit, const
         knownT = smask + S * W;
     }
     if (t >= S * S) return;
+    const int y0 = t % S, x0 = t / S;
+    if (role == 1) {
     // housekeeping for the next combine: C1's column minima and running counter start clean
     col_minz[t] = 0x7f7f7f7f;
     col_minz[S * S + t] = 0x7f7f7f7f;
     if (t == 0) *scratch_count = 0;
-    const int y0 = t % S, x0 = t / S;
+    const double h0 = GVOM_HM(height, x0, y0);
+
+    // ---- guessed height delta (gvom.py:592-713), quirks kept (see oracle/gvom_oracle.c)
+    double dh_out = 0.0;
+    const double inf0 = GVOM_HM(inferred, x0, y0);
+    if (!(h0 > -1000.0) && inf0 != -1000.0) {
+        bool xpd = false, xnd = false, ypd = false, ynd = false;
+        double x_ph = -1000.0, x_nh = -1000.0, y_ph = -1000.0, y_nh = -1000.0;
+        int i = 0;
+        while (i < 15 && !(xnd && ypd && ynd)) {          // x_p_done is NOT part of the condition (gvom.py:619)
+            i += 1;
+            const int x_p = x0 + i, x_n = x0 - i, y_p = y0 + i, y_n = y0 - i;
+            if (!xpd) {
+                if (x_p < S) {                            // y in [y0-i, y0+i-1], ascending
+                    const int f = first_known(known + (long long)x_p * W, max(0, y0 - i), min(S - 1, y0 + i - 1));
+                    if (f >= 0) { x_ph = GVOM_HM(height, x_p, f); xpd = true; }
+                } else xpd = true;
+            }
+            if (!xnd) {
+                if (x_n >= 0) {                           // y in [y0-i+1, y0+i]
+                    const int f = first_known(known + (long long)x_n * W, max(0, y0 - i + 1), min(S - 1, y0 + i));
+                    if (f >= 0) { x_nh = GVOM_HM(height, x_n, f); xnd = true; }
+                } else xnd = true;
+            }
+            if (!ypd) {
+                if (y_p < S) {                            // x in [x0-i+1, x0+i]
+                    const int f = first_known(knownT + (long long)y_p * W, max(0, x0 - i + 1), min(S - 1, x0 + i));
+                    if (f >= 0) { y_ph = GVOM_HM(height, f, y_p); ypd = true; }
+                } else ypd = true;
+            }
+            if (!ynd) {
+                if (y_n >= 0) {                           // x in [x0-i, x0+i-1]
+                    const int f = first_known(knownT + (long long)y_n * W, max(0, x0 - i), min(S - 1, x0 + i - 1));
+                    if (f >= 0) { y_nh = GVOM_HM(height, f, y_n); ynd = true; }
+                } else ynd = true;
+            }
+        }
+        double mn = 1000.0, mx = inf0;
+        if (x_ph > -1000.0) { mn = fmin(x_ph, mn); mx = fmax(x_ph, mx); }
+        if (x_nh > -1000.0) { mn = fmin(x_nh, mn); mx = fmax(x_nh, mx); }
+        if (y_ph > -1000.0) { mn = fmin(y_ph, mn); mx = fmax(y_ph, mx); }
+        if (x_nh > -1000.0) { mn = fmin(y_nh, mn); mx = fmax(y_nh, mx); }   // sic (gvom.py:704-706)
+        const double dh = __dsub_rn(mx, mn);
+        if (dh > 0.0) dh_out = dh;
+    }
+    GVOM_HM(guessed, x0, y0) = dh_out;
+    GVOM_HM(neg, x0, y0) = dh_out > P.neg_thr ? 100 : 0;
+    GVOM_HM(vis, x0, y0) = h0 > -1000.0 ? 1 : 0;
+    return;
+    }
 
     // ---- slope + roughness (gvom.py:717-805); contraction pattern = SASS of the reference.
     // 3x3 neighbourhood in registers, visited in the reference's order (x outer, y inner).
@@ -1084,53 +1163,6 @@ k_surface_maps(const int* __restrict__ cmap, const int* __restrict__ chit, const
     GVOM_HM(rough, x0, y0) = rg;
     GVOM_HM(xs, x0, y0) = sxv;
     GVOM_HM(ys, x0, y0) = syv;
-
-    // ---- guessed height delta (gvom.py:592-713), quirks kept (see oracle/gvom_oracle.c)
-    double dh_out = 0.0;
-    const double inf0 = GVOM_HM(inferred, x0, y0);
-    if (!(h0 > -1000.0) && inf0 != -1000.0) {
-        bool xpd = false, xnd = false, ypd = false, ynd = false;
-        double x_ph = -1000.0, x_nh = -1000.0, y_ph = -1000.0, y_nh = -1000.0;
-        int i = 0;
-        while (i < 15 && !(xnd && ypd && ynd)) {          // x_p_done is NOT part of the condition (gvom.py:619)
-            i += 1;
-            const int x_p = x0 + i, x_n = x0 - i, y_p = y0 + i, y_n = y0 - i;
-            if (!xpd) {
-                if (x_p < S) {                            // y in [y0-i, y0+i-1], ascending
-                    const int f = first_known(known + (long long)x_p * W, max(0, y0 - i), min(S - 1, y0 + i - 1));
-                    if (f >= 0) { x_ph = GVOM_HM(height, x_p, f); xpd = true; }
-                } else xpd = true;
-            }
-            if (!xnd) {
-                if (x_n >= 0) {                           // y in [y0-i+1, y0+i]
-                    const int f = first_known(known + (long long)x_n * W, max(0, y0 - i + 1), min(S - 1, y0 + i));
-                    if (f >= 0) { x_nh = GVOM_HM(height, x_n, f); xnd = true; }
-                } else xnd = true;
-            }
-            if (!ypd) {
-                if (y_p < S) {                            // x in [x0-i+1, x0+i]
-                    const int f = first_known(knownT + (long long)y_p * W, max(0, x0 - i + 1), min(S - 1, x0 + i));
-                    if (f >= 0) { y_ph = GVOM_HM(height, f, y_p); ypd = true; }
-                } else ypd = true;
-            }
-            if (!ynd) {
-                if (y_n >= 0) {                           // x in [x0-i, x0+i-1]
-                    const int f = first_known(knownT + (long long)y_n * W, max(0, x0 - i), min(S - 1, x0 + i - 1));
-                    if (f >= 0) { y_nh = GVOM_HM(height, f, y_n); ynd = true; }
-                } else ynd = true;
-            }
-        }
-        double mn = 1000.0, mx = inf0;
-        if (x_ph > -1000.0) { mn = fmin(x_ph, mn); mx = fmax(x_ph, mx); }
-        if (x_nh > -1000.0) { mn = fmin(x_nh, mn); mx = fmax(x_nh, mx); }
-        if (y_ph > -1000.0) { mn = fmin(y_ph, mn); mx = fmax(y_ph, mx); }
-        if (x_nh > -1000.0) { mn = fmin(y_nh, mn); mx = fmax(y_nh, mx); }   // sic (gvom.py:704-706)
-        const double dh = __dsub_rn(mx, mn);
-        if (dh > 0.0) dh_out = dh;
-    }
-    GVOM_HM(guessed, x0, y0) = dh_out;
-    GVOM_HM(neg, x0, y0) = dh_out > P.neg_thr ? 100 : 0;
-    GVOM_HM(vis, x0, y0) = h0 > -1000.0 ? 1 : 0;
 
     // ---- positive obstacles (gvom.py:515-555)
     int pv = 0;
@@ -1237,6 +1269,7 @@ struct RecordSet { const float* r[MAX_RANKS]; const int* count[MAX_RANKS]; int n
 // per record: fold this rank's slots (reference order, float32 rounding as in C2)
 __global__ void __launch_bounds__(128)
 k_partial_cells(MergeArgs A, const int* __restrict__ counter, float* __restrict__ records, DevParams P, int cap) {
+    pdl_wait();
     const int count = min(*counter, cap);
     const int S = P.S, Z = P.Z;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
@@ -1273,6 +1306,7 @@ __global__ void __launch_bounds__(256)
 k_scatter_records(RecordSet R, long long capacity,
                   const int* __restrict__ cmap, double* __restrict__ cacc, int* __restrict__ chit,
                   int* __restrict__ ctot, float* __restrict__ cminh) {
+    pdl_wait();
     for (int rk = 0; rk < R.n; ++rk) {
         const int count = (int)min((long long)*R.count[rk], capacity);
         const float* base = R.r[rk];
@@ -1299,6 +1333,7 @@ __global__ void __launch_bounds__(128)
 k_finish_cells(SlotRef prev, int has_prev, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
                const double* __restrict__ cacc, int* __restrict__ chit, int* __restrict__ ctot,
                float* __restrict__ cminh, float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap) {
+    pdl_wait();
     const int count = min(*counter, cap);
     const int S = P.S, Z = P.Z;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {

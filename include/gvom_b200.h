@@ -153,7 +153,8 @@ int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_
 int gvom_get_stats(GvomHandle* h, GvomStats* out);
 /* CUDA-event time (ms) of the stages of the last process / combine call:
  * [0] H2D+staging, [1] voxelise+ray-cast, [2] index build, [3] moments, [4] gather,
- * [5] merge codes, [6] merge cells, [7] 2-D maps, [8] D2H.  Only recorded when
+ * [5] merge codes, [6] merge cells, [7] 2-D maps, [8] D2H, [9] host time of the last
+ * pageable->pinned staging copy.  [0..8] are only recorded when
  * gvom_set_profiling(h, 1) is on (adds event records to the stream). */
 int gvom_set_profiling(GvomHandle* h, int32_t on);
 int gvom_stage_times(GvomHandle* h, float ms[16]);

@@ -17,7 +17,7 @@ for mode in ("pageable", "pinned", "device"):
         out = g.combine_maps()
         t1 = time.perf_counter()
         ts.append(t1 - t0)
-    print(mode, "p50 ms", np.median(ts[10:]) * 1e3, "min", min(ts) * 1e3)
+    print(mode, "p50 ms", np.median(ts[10:]) * 1e3, "min", min(ts) * 1e3, "stage_copy_ms", g.stage_times()["stage_copy_host"])
 g.set_profiling(True)
 for it in range(3):
     pc, ego, T = frames[it]
