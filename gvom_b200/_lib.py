@@ -48,8 +48,8 @@ SYMBOLS = {
     "gvom_debug_height_map": (C.c_int, [_vp, _vp]),
     "gvom_debug_inferred_height_map": (C.c_int, [_vp, _vp]),
     "gvom_newest_origin": (C.c_int, [_vp, _pd]),
-    "gvom_combine_partial": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "gvom_combine_finish": (C.c_int, [_vp, _pd, C.POINTER(_vp), C.POINTER(_vp), _i32, C.POINTER(_vp), C.POINTER(_vp), _i32, _i64, _pd,
+    "gvom_combine_partial": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _i64, _vp, C.POINTER(_vp), _i32, _i32, _vp]),
+    "gvom_combine_finish": (C.c_int, [_vp, _pd, C.POINTER(_vp), C.POINTER(_vp), _i32, C.POINTER(_vp), C.POINTER(_vp), _i32, _i64, _vp, _i32, _pd,
                                       _vp, _vp, _vp, _vp, _i32, _vp]),
     "gvom_slot_info": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i64), _pd]),
     "gvom_last_slot": (C.c_int, [_vp, C.POINTER(_i32)]),

@@ -857,7 +857,8 @@ int gvom_newest_origin(GvomHandle* h, double origin[3]) {
 }
 
 int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, uint32_t* group_mask_dev,
-                         float* records_dev, int64_t record_capacity, int32_t* record_count_dev, void* stream) {
+                         float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
+                         int32_t* const* signal_slots, int32_t n_signal, int32_t epoch, void* stream) {
     if (!h || !origin || !code_grid_dev || !records_dev || !record_count_dev) return fail(GVOM_EINVAL, "NULL argument");
     if (record_capacity < 1 || record_capacity > 2147483647LL) return fail(GVOM_EINVAL, "bad record capacity");
     std::lock_guard<std::mutex> lock(h->mu);
@@ -873,8 +874,15 @@ int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_gr
     O.gmask = (h->p.xy_size % 8 == 0) ? group_mask_dev : nullptr; O.cap = (int)record_capacity;
     launch_merge<MERGE_PARTIAL>(h, A, O, st);
     launch(k_partial_cells, dim3(h->grid_cells), dim3(128), 0, st, A, record_count_dev, records_dev, h->dp, (int)record_capacity);
-    rec(h, EV_CODES, st);
     h->stats.kernel_launches += 1;
+    if (signal_slots && n_signal > 0) {            // peer-to-peer exchange: tell every rank this one is done
+        if (n_signal > MAX_RANKS) return fail(GVOM_EINVAL, "too many ranks");
+        SignalSet S; S.n = n_signal;
+        for (int k = 0; k < n_signal; ++k) S.slot[k] = signal_slots[k];
+        launch(k_signal, dim3(1), dim3(32), 0, st, S, (int)epoch);
+        h->stats.kernel_launches += 1;
+    }
+    rec(h, EV_CODES, st);
     CUDA_TRY(cudaGetLastError());
     return GVOM_OK;
 }
@@ -882,8 +890,9 @@ int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_gr
 int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* const* code_grids,
                         const uint32_t* const* group_masks, int32_t n_grids,
                         const float* const* records, const int32_t* const* record_counts, int32_t nranks,
-                        int64_t record_capacity, double origin_out[3], int32_t* positive, int32_t* negative,
-                        double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
+                        int64_t record_capacity, const int32_t* wait_flags, int32_t wait_epoch, double origin_out[3],
+                        int32_t* positive, int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem,
+                        void* stream) {
     if (!h || !origin || !code_grids || !records || !record_counts) return fail(GVOM_EINVAL, "NULL argument");
     if (nranks < 1 || nranks > MAX_RANKS || n_grids < 1 || n_grids > MAX_RANKS) return fail(GVOM_EINVAL, "1..16 ranks / grids");
     RecordSet R;
@@ -928,6 +937,7 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
         O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
         O.gmask = (h->p.xy_size % 8 == 0) ? c.gmask : nullptr; O.cap = (int)h->ccap;
         O.cacc = cacc; O.chit = c.hit; O.ctot = c.total; O.cminh = c.minh;
+        O.wait_flags = wait_flags; O.wait_n = nranks; O.wait_epoch = wait_epoch;
         launch_merge<MERGE_FINISH>(h, A, O, st);
     }
     rec(h, EV_CODES, st);

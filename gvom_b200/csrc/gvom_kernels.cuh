@@ -588,6 +588,8 @@ struct MergeOut {
     double* cacc;            // FINISH: per-cell raw-moment accumulators (cleared here)
     int* chit; int* ctot; float* cminh;
     int cap;
+    const int* wait_flags;   // FINISH, peer-to-peer: flags[k] >= wait_epoch once rank k's partial results are visible
+    int wait_n, wait_epoch;
 };
 
 __device__ __forceinline__ void column_min(int* __restrict__ col, int z) {
@@ -629,6 +631,19 @@ template <int VEC, int MODE>
 __global__ void __launch_bounds__(256, 3)
 k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
     pdl_wait();
+    if (MODE == MERGE_FINISH && O.wait_flags) {
+        // device-side barrier of the peer-to-peer exchange, folded into the consumer: every block waits
+        // until all ranks have published this combine's partial results (their signal kernel wrote the epoch
+        // into OUR flag slots after a system-scope fence), then reads the peers' grids over NVLink.
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < O.wait_n; ++k) {
+                const volatile int* f = O.wait_flags + k;
+                while (*f < O.wait_epoch) __nanosleep(100);
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -1265,6 +1280,19 @@ constexpr int MAX_RANKS = 16;
 // point into local (all-reduced / all-gathered) memory; with the peer-to-peer exchange they are
 // the OTHER GPUs' buffers mapped over NVLink, read directly by the kernels below.
 struct RecordSet { const float* r[MAX_RANKS]; const int* count[MAX_RANKS]; int n; };
+
+// publish "my partial results of combine `epoch` are complete" into every rank's flag slot for this rank
+struct SignalSet { int* slot[MAX_RANKS]; int n; };
+
+__global__ void k_signal(SignalSet S, int epoch) {
+    pdl_wait();                                   // after this rank's partial kernels
+    __threadfence_system();
+    if (threadIdx.x < S.n) {
+        volatile int* f = S.slot[threadIdx.x];
+        *f = epoch;
+    }
+    __threadfence_system();
+}
 
 // per record: fold this rank's slots (reference order, float32 rounding as in C2)
 __global__ void __launch_bounds__(128)

@@ -28,6 +28,7 @@ All sensors must share the vehicle ego position (as in gvom_ros.py, where the
 origin comes from odometry, not from the sensor pose).
 """
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -102,8 +103,9 @@ class MultiGpuGvom(Gvom):
         o_rec = (o_msk + 4 * (V // 256 + 2) + 255) & ~255
         o_cnt = (o_rec + 4 * RECORD_FLOATS * cap + 255) & ~255
         o_hdr = o_cnt + 256
-        total = o_hdr + 8 * HEADER_DOUBLES + 256
-        return o_grid, o_msk, o_rec, o_cnt, o_hdr, total
+        o_flg = o_hdr + 8 * HEADER_DOUBLES + 256          # flags[rank] int32: rank's epoch, written by that rank
+        total = o_flg + 4 * 64 + 256
+        return o_grid, o_msk, o_rec, o_cnt, o_hdr, total, o_flg
 
     def _init_p2p(self):
         import torch.distributed._symmetric_memory as symm_mem
@@ -116,7 +118,17 @@ class MultiGpuGvom(Gvom):
             t = symm_mem.empty(total, dtype=torch.uint8, device=self._dev)
             hdl = symm_mem.rendezvous(t, group)
             t.zero_()
-            self._sets.append((t, hdl, [int(p) for p in hdl.buffer_ptrs]))
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            o_grid, o_msk, o_rec, o_cnt, o_hdr, _, o_flg = self._off
+            self._sets.append({
+                "t": t, "hdl": hdl, "me": ptrs[self.rank],
+                # per-rank pointer tables handed to gvom_combine_finish (constant: built once)
+                "grids": _ptr_array([p + o_grid for p in ptrs]), "masks": _ptr_array([p + o_msk for p in ptrs]),
+                "recs": _ptr_array([p + o_rec for p in ptrs]), "cnts": _ptr_array([p + o_cnt for p in ptrs]),
+                "hdr_view": t[o_hdr:o_hdr + 8 * HEADER_DOUBLES].view(torch.float64),
+                # my flag slot in every rank's block (signal) / all ranks' slots in my block (wait)
+                "signal": _ptr_array([p + o_flg + 4 * self.rank for p in ptrs]), "wait": ptrs[self.rank] + o_flg,
+            })
         torch.cuda.synchronize(self._dev)
         dist.barrier(group=self._group)
         self._hdr_host = torch.zeros(HEADER_DOUBLES, dtype=torch.float64).pin_memory()
@@ -149,23 +161,31 @@ class MultiGpuGvom(Gvom):
     # ------------------------------------------------------------------ peer-to-peer exchange
     def _combine_p2p(self, device_outputs):
         torch, L = self._torch, self._L
-        t, hdl, ptrs = self._sets[self._calls & 1]
-        o_grid, o_msk, o_rec, o_cnt, o_hdr, _ = self._off
-        me = ptrs[self.rank]
+        X = self._sets[self._calls & 1]
+        t, hdl, me = X["t"], X["hdl"], X["me"]
+        o_grid, o_msk, o_rec, o_cnt, o_hdr, _, o_flg = self._off
+        epoch = self._calls
         have = L.gvom_newest_origin(self._h, self._org_in) != GVOM_NO_DATA
         with torch.cuda.stream(self._tstream):
-            if have:
-                check(L.gvom_combine_partial(self._h, self._org_in, me + o_grid, me + o_msk, me + o_rec, self._rec_cap,
-                                             me + o_cnt, self._stream), "gvom_combine_partial")
-            else:
-                t[o_grid:o_rec].zero_()              # empty grid, empty group mask
-                t[o_cnt:o_cnt + 4].zero_()
-            hh = self._hdr_host
+            hh = self._hdr_host                      # header: only read by ranks that have no scan yet (start-up)
             hh[0] = 1.0 if have else 0.0
             hh[2], hh[3], hh[4] = (self._org_in[0], self._org_in[1], self._org_in[2]) if have else (0.0, 0.0, 0.0)
-            t[o_hdr:o_hdr + 8 * HEADER_DOUBLES].view(torch.float64).copy_(hh, non_blocking=True)
-            hdl.barrier(channel=0)           # device-side: every rank's partial results are visible to its peers
-            if not have:                     # start-up only: adopt the origin of a rank that has data
+            X["hdr_view"].copy_(hh, non_blocking=True)
+            if have:
+                # partial kernels, then the signal kernel: "rank `me`, combine `epoch`: done" into every rank's block
+                check(L.gvom_combine_partial(self._h, self._org_in, me + o_grid, me + o_msk, me + o_rec, self._rec_cap,
+                                             me + o_cnt, X["signal"], self.world, epoch, self._stream), "gvom_combine_partial")
+            else:
+                # start-up only: this rank has no scan yet.  Publish an empty grid, signal, then wait (on the host)
+                # for the others and adopt the origin of a rank that has data.
+                t[o_grid:o_rec].zero_()              # empty grid, empty group mask
+                t[o_cnt:o_cnt + 4].zero_()
+                for r in range(self.world):
+                    hdl.get_buffer(r, (64,), torch.int32, o_flg // 4)[self.rank:self.rank + 1].fill_(epoch)
+                self._tstream.synchronize()
+                flags = t[o_flg:o_flg + 4 * 64].view(torch.int32)[:self.world]
+                while int(flags.min().item()) < epoch:
+                    time.sleep(1e-4)
                 heads = np.stack([hdl.get_buffer(r, (HEADER_DOUBLES,), torch.float64, o_hdr // 8).cpu().numpy()
                                   for r in range(self.world)])
                 origin, _ = merge_headers(heads)
@@ -175,13 +195,10 @@ class MultiGpuGvom(Gvom):
                 for k in range(3):
                     self._org_in[k] = float(origin[k])
             outs, optr, mem = self._outputs(device_outputs)
-            grids = _ptr_array([p + o_grid for p in ptrs])
-            masks = _ptr_array([p + o_msk for p in ptrs])
-            recs = _ptr_array([p + o_rec for p in ptrs])
-            cnts = _ptr_array([p + o_cnt for p in ptrs])
-            check(L.gvom_combine_finish(self._h, self._org_in, grids, masks, self.world, recs, cnts, self.world, self._rec_cap,
-                                        self._org_c, optr[0], optr[1], optr[2], optr[3], mem, self._stream),
-                  "gvom_combine_finish")
+            # the finishing merge kernel waits on the flag slots itself, then reads the peers' buffers over NVLink
+            check(L.gvom_combine_finish(self._h, self._org_in, X["grids"], X["masks"], self.world, X["recs"], X["cnts"],
+                                        self.world, self._rec_cap, X["wait"], epoch, self._org_c, optr[0], optr[1],
+                                        optr[2], optr[3], mem, self._stream), "gvom_combine_finish")
         pos, neg, rough, vis = outs
         return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
 
@@ -193,7 +210,7 @@ class MultiGpuGvom(Gvom):
         with torch.cuda.stream(self._tstream):
             if have:
                 check(L.gvom_combine_partial(self._h, self._org_in, self._grid.data_ptr(), None, self._records.data_ptr(),
-                                             self._rec_cap, self._count.data_ptr(), self._stream),
+                                             self._rec_cap, self._count.data_ptr(), None, 0, 0, self._stream),
                       "gvom_combine_partial")
             else:
                 self._grid.zero_()
@@ -220,7 +237,7 @@ class MultiGpuGvom(Gvom):
             grids = _ptr_array([self._grid.data_ptr()])
             recs = _ptr_array([gathered.data_ptr() + 4 * RECORD_FLOATS * maxc * r for r in range(self.world)])
             cnts = _ptr_array([self._counts_dev.data_ptr() + 4 * r for r in range(self.world)])
-            check(L.gvom_combine_finish(self._h, self._org_in, grids, None, 1, recs, cnts, self.world, maxc, self._org_c,
+            check(L.gvom_combine_finish(self._h, self._org_in, grids, None, 1, recs, cnts, self.world, maxc, None, 0, self._org_c,
                                         optr[0], optr[1], optr[2], optr[3], mem, self._stream),
                   "gvom_combine_finish")
         pos, neg, rough, vis = outs

@@ -124,17 +124,25 @@ int gvom_debug_inferred_height_map(GvomHandle* h, float* out_rows3);
 int gvom_newest_origin(GvomHandle* h, double origin[3]);
 /* group_mask_dev (V/256 + 2 words, may be NULL): one bit per 8-voxel group of the code grid,
  * set where the group holds anything; lets the finishing pass skip the (mostly empty) rest. */
+/* signal_slots (n_signal device pointers, may be NULL): peer-to-peer exchange only -- one int32 slot in
+ * every rank's (mapped) memory into which this rank writes `epoch` once its partial results are
+ * visible system-wide. */
 int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_grid_dev,
                          uint32_t* group_mask_dev, float* records_dev, int64_t record_capacity,
-                         int32_t* record_count_dev, void* stream);
+                         int32_t* record_count_dev, int32_t* const* signal_slots, int32_t n_signal,
+                         int32_t epoch, void* stream);
 /* code_grids: n_grids device pointers -- ONE all-reduced grid (NCCL exchange) or one grid
  * per rank (peer-to-peer exchange: the other GPUs' buffers mapped over NVLink are read directly by
  * the finishing kernels).  records / record_counts: nranks device pointers each (a rank's records
- * and its record count). */
+ * and its record count).
+ * wait_flags (nranks local int32 slots, may be NULL): peer-to-peer exchange -- the finishing kernel
+ * itself waits until every slot is >= wait_epoch before it reads the peers' buffers (the barrier is
+ * part of the consumer kernel; no collective launch, no host synchronisation). */
 int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* const* code_grids,
                         const uint32_t* const* group_masks /* n_grids entries, or NULL */,
                         int32_t n_grids, const float* const* records,
                         const int32_t* const* record_counts, int32_t nranks, int64_t record_capacity,
+                        const int32_t* wait_flags, int32_t wait_epoch,
                         double origin_out[3], int32_t* positive, int32_t* negative, double* roughness,
                         int32_t* visibility, int32_t out_mem, void* stream);
 

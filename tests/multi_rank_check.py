@@ -28,6 +28,14 @@ def main():
     PN = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B * world, robot_radius=2.0)
     fr = sensor_frames(world, 4)
     g = MultiGpuGvom(*P1, device=local, exchange=sys.argv[1] if len(sys.argv) > 1 else "auto")
+    if len(sys.argv) > 2 and sys.argv[2] == "late":        # start-up path: rank 1 joins one combine late
+        first = MultiGpuGvom(*P1, device=local, exchange=sys.argv[1])
+        if rank == 0:
+            first.Process_pointcloud(*fr[0][0])
+        o = first.combine_maps()
+        assert o is not None and o[1].shape == (64, 64)
+        torch.cuda.synchronize()
+        dist.barrier()
     for step in range(4):
         g.Process_pointcloud(*fr[step][rank])
         out = g.combine_maps()

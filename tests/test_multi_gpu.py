@@ -61,7 +61,7 @@ def local_exchange(ranks, reduced=False):
         msk = torch.empty(V // 256 + 2, dtype=torch.int32, device=dev)
         rec = torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-        check(L.gvom_combine_partial(g._h, o, grid.data_ptr(), msk.data_ptr(), rec.data_ptr(), cap, cnt.data_ptr(), None),
+        check(L.gvom_combine_partial(g._h, o, grid.data_ptr(), msk.data_ptr(), rec.data_ptr(), cap, cnt.data_ptr(), None, 0, 0, None),
               "partial")
         torch.cuda.synchronize()
         grids.append(grid); masks.append(msk); recs.append(rec); counts.append(cnt)
@@ -77,7 +77,7 @@ def local_exchange(ranks, reduced=False):
     for g in ranks:
         pos, neg, rough, vis = g._out_arrays()
         oo = (C.c_double * 3)()
-        check(L.gvom_combine_finish(g._h, o, gptrs, mptrs, ng, rptrs, cptrs, n, cap, oo, pos.ctypes.data, neg.ctypes.data,
+        check(L.gvom_combine_finish(g._h, o, gptrs, mptrs, ng, rptrs, cptrs, n, cap, None, 0, oo, pos.ctypes.data, neg.ctypes.data,
                                     rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None), "finish")
         outs.append((np.array(list(oo)), pos, neg, rough, vis))
     return outs
@@ -124,9 +124,9 @@ def test_nccl_two_ranks(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     script = os.path.join(ROOT, "tests", "multi_rank_check.py")
-    for port, exchange in ((29533, "nccl"), (29534, "auto")):
+    for port, exchange, extra in ((29533, "nccl", []), (29534, "auto", []), (29535, "auto", ["late"])):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                            "--master-addr", "127.0.0.1", "--master-port", str(port), script, exchange],
+                            "--master-addr", "127.0.0.1", "--master-port", str(port), script, exchange] + extra,
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         assert "MULTI_RANK_OK" in r.stdout, r.stdout[-2000:]
