@@ -957,4 +957,95 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     return GVOM_OK;
 }
 
+
+// Sharded finish of the peer-to-peer exchange.  Rank `rank` of `nranks`:
+//   1. merges the z-planes it owns (z % nranks == rank) from every rank's encoded grid + its (replicated) copy of
+//      the previous combined map                        -> res_map (own planes), local cell ids
+//   2. folds the ranks' records of those cells (found through the record ids in the grids) + previous map, eigenvalues
+//                                                       -> res_cells, res_count;  signals "slab done"
+//   3. waits for every rank's slab, assembles the full combined map / cell arrays (ids rebased), column minima, group
+//      mask; then the 2-D stage and the outputs as in the single-GPU combine.
+int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t rank, int32_t nranks,
+                                const int32_t* const* code_grids, const uint32_t* const* group_masks,
+                                const float* const* records, int64_t record_capacity,
+                                const int32_t* wait_partial, int32_t* const* res_maps, void* const* res_cells,
+                                int32_t* const* res_counts, int64_t res_capacity,
+                                int32_t* const* signal_slab, const int32_t* wait_slab, int32_t epoch, int32_t phases,
+                                double origin_out[3], int32_t* positive, int32_t* negative, double* roughness,
+                                int32_t* visibility, int32_t out_mem, void* stream) {
+    if (!h || !origin || !code_grids || !records || !res_maps || !res_cells || !res_counts || !signal_slab)
+        return fail(GVOM_EINVAL, "NULL argument");
+    if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return fail(GVOM_EINVAL, "bad rank / nranks");
+    if (h->p.xy_size % 8 != 0 || (((int64_t)h->p.xy_size * h->p.xy_size / 8) % 32) != 0)
+        return fail(GVOM_EINVAL, "sharded finish needs xy_size % 16 == 0");
+    if (res_capacity < 1 || res_capacity > 2147483647LL) return fail(GVOM_EINVAL, "bad result capacity");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->active = st;
+    Combined& pc = h->comb[h->cur];
+    Combined& c = h->comb[1 - h->cur];
+    for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];
+
+    MergeArgs A;
+    A.n = 0; A.use_masks = 1;
+    RankBufs B; B.n = nranks;
+    SlabSet R; R.n = nranks;
+    for (int k = 0; k < nranks; ++k) {
+        if (!code_grids[k] || !records[k] || !res_maps[k] || !res_cells[k] || !res_counts[k]) return fail(GVOM_EINVAL, "NULL rank buffer");
+        SlotRef& r = A.s[A.n++];
+        r = SlotRef{};
+        r.map = code_grids[k];
+        r.gmask = group_masks ? group_masks[k] : nullptr;
+        if (!r.gmask) A.use_masks = 0;
+        B.grid[k] = code_grids[k]; B.rec[k] = records[k];
+        R.map[k] = res_maps[k]; R.count[k] = res_counts[k]; R.cells[k] = res_cells[k];
+    }
+    SlotRef prev{};
+    const int has_prev = pc.valid ? 1 : 0;
+    if (has_prev) {
+        prev.map = pc.index_map; prev.metrics = pc.metrics; prev.hit = pc.hit; prev.total = pc.total; prev.minh = pc.minh;
+        prev.dx = (int)(origin[0] - pc.origin[0]); prev.dy = (int)(origin[1] - pc.origin[1]); prev.dz = (int)(origin[2] - pc.origin[2]);
+        prev.is_prev = 1;
+        prev.gmask = pc.has_gmask ? pc.gmask : nullptr;
+        if (!prev.gmask) A.use_masks = 0;
+        A.s[A.n++] = prev;
+    }
+    const SlabCells mine = slab_cells_at(res_cells[rank], res_capacity);
+    if (phases & 1) {   // 1. my planes
+        MergeOut O{};
+        O.cmap = res_maps[rank]; O.counter = h->flags + 1; O.cell_voxel = mine.voxel;
+        O.cap = (int)res_capacity;
+        O.wait_flags = wait_partial; O.wait_n = nranks; O.wait_epoch = epoch;
+        O.slab_r = rank; O.slab_n = nranks;
+        launch(k_merge_codes<8, MERGE_FINISH>, dim3(std::max(1, h->grid_codes / std::max(1, nranks / 2))), dim3(256), 0, st, A, O, h->dp);
+    rec(h, EV_CODES, st);
+    // 2. my cells
+    launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 1, mine, res_counts[rank], h->dp,
+           (int)res_capacity, (int)record_capacity);
+    {
+        SignalSet S; S.n = nranks;
+        for (int k = 0; k < nranks; ++k) S.slot[k] = signal_slab[k];
+        launch(k_signal, dim3(1), dim3(32), 0, st, S, (int)epoch);
+    }
+    h->stats.kernel_launches += 3;
+    }
+    if (!(phases & 2)) { CUDA_TRY(cudaGetLastError()); return GVOM_OK; }
+    // 3. everybody's planes and cells
+    launch(k_gather_maps, dim3(h->sm_count * 4), dim3(256), 0, st, R, wait_slab, (int)epoch, c.index_map, c.gmask, h->col_minz,
+           h->col_minz + h->S2, h->flags + 1, h->dp);
+    launch(k_gather_cells, dim3(h->sm_count * 2), dim3(256), 0, st, R, (long long)res_capacity, c.hit, c.total, c.minh, c.metrics,
+           c.eig, c.cell_voxel, (int)h->ccap);
+    rec(h, EV_CELLS, st);
+    h->stats.kernel_launches += 2;
+    h->prof_combine = h->profiling;
+    c.has_gmask = true;
+    const int r = run_maps_and_output(h, c, origin_out, positive, negative, roughness, visibility, out_mem, st);
+    if (r != GVOM_OK) return r;
+    c.valid = true;
+    h->cur = 1 - h->cur;
+    h->stats.combine_calls++;
+    return GVOM_OK;
+}
+
 }  // extern "C"

@@ -590,6 +590,7 @@ struct MergeOut {
     int cap;
     const int* wait_flags;   // FINISH, peer-to-peer: flags[k] >= wait_epoch once rank k's partial results are visible
     int wait_n, wait_epoch;
+    int slab_r, slab_n;      // FINISH, sharded: this rank finishes the z-planes with z % slab_n == slab_r (slab_n <= 1: all)
 };
 
 __device__ __forceinline__ void column_min(int* __restrict__ col, int z) {
@@ -648,10 +649,18 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
     const unsigned lt = (1u << lane) - 1u;
     const long long step = (long long)gridDim.x * blockDim.x;
     const int S = P.S, Z = P.Z;
-    const long long NQ = P.V / VEC;
+    // sharded finish: only the z-planes this rank owns (interleaved: z % slab_n == slab_r, so the few ground
+    // planes that hold most cells spread over all ranks); QP = items per plane
+    const bool slab = MODE == MERGE_FINISH && O.slab_n > 1;
+    const long long QP = ((long long)S * S) / VEC;
+    const int my_planes = slab ? (Z - O.slab_r + O.slab_n - 1) / O.slab_n : Z;
+    const long long NQ = slab ? my_planes * QP : P.V / VEC;
     const long long NQp = (NQ + 31) & ~31LL;
     const int has_prev = (A.n > 0 && A.s[A.n - 1].is_prev) ? 1 : 0;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < NQp; q += step) {
+    for (long long ql = (long long)blockIdx.x * blockDim.x + threadIdx.x; ql < NQp; ql += step) {
+        // local item -> global item (warp-uniform plane: QP is a multiple of 32 in slab mode)
+        const long long q = slab ? ((long long)O.slab_r + (long long)O.slab_n * (ql / QP)) * QP + ql % QP : ql;
+        const bool live = ql < NQ;
         int acc_and[VEC], sum[VEC], enc_or[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { acc_and[j] = -1; sum[j] = 0; enc_or[j] = 0; }
@@ -659,7 +668,7 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
         int op[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) op[j] = -1;
-        if (q < NQ) {
+        if (live) {
             const unsigned v0 = (unsigned)(q * VEC);          // V < 2^31
             if (P.lgS >= 0) {
                 x = (int)(v0 & (unsigned)(S - 1));
@@ -724,7 +733,7 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
                         for (int j = 0; j < VEC; ++j) op[j] = o[u][j];
                     } else if (MODE == MERGE_FINISH) {
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j) { enc_or[j] |= o[u][j]; sum[j] += o[u][j] & (OCC_FLAG - 1); }
+                        for (int j = 0; j < VEC; ++j) { enc_or[j] |= o[u][j]; sum[j] += o[u][j] < OCC_FLAG ? o[u][j] : 0; }
                     } else {
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) { acc_and[j] &= o[u][j]; sum[j] += max(~o[u][j], 0); }
@@ -757,29 +766,33 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
             base = __shfl_sync(FULL, base, 0);
         }
         bool known_any = false;
-        if (q < NQ) {
+        if (live) {
             if (MODE == MERGE_PARTIAL) {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
+                    int rid = OCC_FLAG - 1;                    // "occupied, record dropped" (capacity overflow)
                     if (occ[j]) {
                         const int id = base + __popc(m[j] & lt);
-                        if (id < O.cap) O.records[(long long)id * REC] = __int_as_float((int)(q * VEC + j));
+                        if (id < O.cap) { O.records[(long long)id * REC] = __int_as_float((int)(q * VEC + j)); rid = id; }
                     }
                     base += __popc(m[j]);
-                    c[j] = occ[j] ? OCC_FLAG : min(sum[j], OCC_FLAG - 1);
+                    // occupied: flag | record id (lets a finishing rank fetch the record without a search)
+                    c[j] = occ[j] ? (OCC_FLAG | rid) : min(sum[j], OCC_FLAG - 1);
                     known_any |= c[j] != 0;
                 }
             } else if (!my_occ && !any_free) {                    // nothing known here (the common case)
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) c[j] = -1;
             } else {
+                const bool cols = O.col_occ != nullptr;            // (the sharded finish leaves them to the gather pass)
                 int* colo = O.col_occ + y * S + x;
                 int* colf = O.col_free + y * S + x;
                 // current column minima, pre-filter of the atomicMin (vector loads, issued together)
                 int cur_occ[VEC], cur_free[VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) { cur_occ[j] = 0x7fffffff; cur_free[j] = 0x7fffffff; }
-                if (VEC >= 4) {
+                for (int j = 0; j < VEC; ++j) { cur_occ[j] = cols ? 0x7fffffff : -1; cur_free[j] = cols ? 0x7fffffff : -1; }
+                if (!cols) {
+                } else if (VEC >= 4) {
 #pragma unroll
                     for (int g = 0; g < VEC / 4; ++g) {
                         if (my_occ) {
@@ -801,7 +814,7 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
                         if (id < O.cap) {
                             c[j] = id; O.cell_voxel[id] = (int)(q * VEC + j);
                             if (z < cur_occ[j]) atomicMin(colo + j, z);
-                            if (MODE == MERGE_FINISH) {
+                            if (MODE == MERGE_FINISH && O.cacc) {
                                 O.chit[id] = 0; O.ctot[id] = 0; O.cminh[id] = 1.0f;
                                 double2* a = reinterpret_cast<double2*>(O.cacc + (long long)id * 10);
 #pragma unroll
@@ -826,7 +839,7 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
         }
         if (VEC == 8 && O.gmask) {                            // group mask of the output grid
             const unsigned w = __ballot_sync(FULL, known_any);
-            if (lane == 0 && q < NQ) O.gmask[q >> 5] = w;
+            if (lane == 0 && live) O.gmask[q >> 5] = w;
         }
     }
 }
@@ -1406,6 +1419,180 @@ k_finish_cells(SlotRef prev, int has_prev, const int* __restrict__ counter, cons
     }
 }
 
+
+// ===========================================================================
+// sharded finish (peer-to-peer exchange): rank r finishes only its z-planes, then every rank
+// assembles the full combined map from all ranks' results.  Per-rank finishing work is V/N.
+// ===========================================================================
+struct RankBufs {                 // every rank's partial results as seen from here (own HBM or NVLink-mapped)
+    const int* grid[MAX_RANKS];   // encoded grid: OCC_FLAG | record id, or summed passes
+    const float* rec[MAX_RANKS];  // records [*, REC]
+    int n;
+};
+
+// result of a rank's slab, struct of arrays with `cap` rows, living in symmetric memory
+struct SlabCells {
+    int* hit; int* tot; float* minh; int* voxel; float* met; float* eig;
+};
+__host__ __device__ inline SlabCells slab_cells_at(void* base, long long cap) {
+    SlabCells c;
+    char* b = static_cast<char*>(base);
+    c.hit = reinterpret_cast<int*>(b);
+    c.tot = reinterpret_cast<int*>(b + 4 * cap);
+    c.minh = reinterpret_cast<float*>(b + 8 * cap);
+    c.voxel = reinterpret_cast<int*>(b + 12 * cap);
+    c.met = reinterpret_cast<float*>(b + 16 * cap);
+    c.eig = reinterpret_cast<float*>(b + 56 * cap);
+    return c;
+}
+constexpr int SLAB_CELL_BYTES = 68;
+
+// per cell of this rank's slab: fold every rank's record of that voxel (rank order), then the previous
+// combined map, then the eigenvalues -- the multi-GPU counterpart of C2 without atomics: the record is
+// found through the id stored in the rank's encoded grid.
+__global__ void __launch_bounds__(128)
+k_slab_cells(RankBufs B, SlotRef prev, int has_prev, const int* __restrict__ counter, SlabCells out,
+             int* __restrict__ out_count, DevParams P, int cap, int rec_cap) {
+    pdl_wait();
+    const int count = min(*counter, cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = count;
+    const int S = P.S, Z = P.Z;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
+        const int v = out.voxel[id];
+        float c[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) c[k] = 0.f;
+        int hit = 0, tot = 0;
+        float mh = 1.0f;
+        int g[MAX_RANKS];
+        for (int k = 0; k < B.n; ++k) g[k] = __ldg(B.grid[k] + v);          // independent (remote) loads first
+        for (int k = 0; k < B.n; ++k) {
+            if (g[k] < OCC_FLAG) continue;
+            const int rid = g[k] & (OCC_FLAG - 1);
+            if (rid >= rec_cap) continue;
+            const float4* r4 = reinterpret_cast<const float4*>(B.rec[k] + (long long)rid * REC);
+            const float4 a = __ldg(r4), b = __ldg(r4 + 1), d = __ldg(r4 + 2), e = __ldg(r4 + 3);
+            const double o[10] = {b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w, e.x, e.y};
+            merge_step(c, o);
+            hit += __float_as_int(a.y); tot += __float_as_int(a.z); mh = fminf(mh, a.w);
+        }
+        if (has_prev) {
+            const int x = v % S, y = (v / S) % S, z = v / (S * S);
+            const int xs = x + prev.dx, ys = y + prev.dy, zs = z + prev.dz;
+            if (!(xs < 0 || xs >= S || ys < 0 || ys >= S || zs < 0 || zs >= Z)) {
+                const int io = __ldg(prev.map + (xs + (ys + (long long)zs * S) * S));
+                if (io >= 0) {
+                    double o[10];
+                    const float* om = reinterpret_cast<const float*>(prev.metrics) + (long long)io * 10;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) o[k] = (double)om[k];
+                    merge_step(c, o);
+                    hit += prev.hit[io]; tot += prev.total[io]; mh = fminf(mh, prev.minh[io]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) out.met[(long long)id * 10 + k] = c[k];
+        out.hit[id] = hit; out.tot[id] = tot; out.minh[id] = mh;
+        float e[3];
+        eigen3(c, e);
+        out.eig[id * 3 + 0] = e[0]; out.eig[id * 3 + 1] = e[1]; out.eig[id * 3 + 2] = e[2];
+    }
+}
+
+struct SlabSet {                  // every rank's slab result as seen from here
+    const int* map[MAX_RANKS];    // full-size index map, valid on the rank's own planes, ids local to the rank
+    const int* count[MAX_RANKS];
+    const void* cells[MAX_RANKS]; // SlabCells base
+    int n;
+};
+
+__device__ __forceinline__ void slab_wait_and_offsets(const SlabSet& R, const int* wait_flags, int epoch, int* off) {
+    // off[k] = first global cell id of rank k, off[n] = total; computed once per block in shared memory
+    if (threadIdx.x == 0) {
+        if (wait_flags)
+            for (int k = 0; k < R.n; ++k) {
+                const volatile int* f = wait_flags + k;
+                while (*f < epoch) __nanosleep(100);
+            }
+        __threadfence_system();
+        int acc = 0;
+        for (int k = 0; k < R.n; ++k) { off[k] = acc; acc += *reinterpret_cast<const volatile int*>(R.count[k]); }
+        off[R.n] = acc;
+    }
+    __syncthreads();
+}
+
+// assemble the full combined index map from the ranks' planes (compact ids rebased to the global
+// numbering), with the column minima and the group mask the single-GPU merge would have produced
+__global__ void __launch_bounds__(256)
+k_gather_maps(SlabSet R, const int* __restrict__ wait_flags, int epoch, int* __restrict__ cmap,
+              unsigned* __restrict__ gmask, int* __restrict__ col_occ, int* __restrict__ col_free,
+              int* __restrict__ total_count, DevParams P) {
+    pdl_wait();
+    __shared__ int off[MAX_RANKS + 1];
+    slab_wait_and_offsets(R, wait_flags, epoch, off);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total_count = off[R.n];
+    const int lane = threadIdx.x & 31;
+    const int S = P.S;
+    const long long QP = ((long long)S * S) / 8;
+    const long long NQ = P.V / 8, NQp = (NQ + 31) & ~31LL;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < NQp; q += (long long)gridDim.x * blockDim.x) {
+        bool known_any = false;
+        if (q < NQ) {
+            const int z = (int)(q / QP);
+            const int k = z % R.n;
+            const int4* src = reinterpret_cast<const int4*>(R.map[k]) + q * 2;
+            int4 a = __ldg(src), b = __ldg(src + 1);
+            int c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            const long long rem = q % QP;
+            const int y = (int)((rem * 8) / S), x = (int)((rem * 8) % S);
+            bool any_occ = false, any_free = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (c[j] >= 0) { c[j] += off[k]; any_occ = true; }
+                else if (c[j] < -1) any_free = true;
+                known_any |= c[j] != -1;
+            }
+            if (any_occ || any_free) {
+                int* colo = col_occ + y * S + x;
+                int* colf = col_free + y * S + x;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (c[j] >= 0) { if (z < colo[j]) atomicMin(colo + j, z); }
+                    else if (c[j] < -1) { if (z < colf[j]) atomicMin(colf + j, z); }
+                }
+            }
+            int4* dst = reinterpret_cast<int4*>(cmap) + q * 2;
+            dst[0] = make_int4(c[0], c[1], c[2], c[3]);
+            dst[1] = make_int4(c[4], c[5], c[6], c[7]);
+        }
+        const unsigned w = __ballot_sync(FULL, known_any);
+        if (lane == 0 && q < NQ) gmask[q >> 5] = w;
+    }
+}
+
+// copy every rank's cells into the global compact arrays (global id = rank offset + local id)
+__global__ void __launch_bounds__(256)
+k_gather_cells(SlabSet R, long long res_cap, int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
+               float* __restrict__ cmet, float* __restrict__ ceig, int* __restrict__ cell_voxel, int cap) {
+    pdl_wait();
+    __shared__ int off[MAX_RANKS + 1];
+    slab_wait_and_offsets(R, nullptr, 0, off);           // k_gather_maps (same stream) already waited
+    const int total = min(off[R.n], cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int k = 0;
+        while (k + 1 < R.n && i >= off[k + 1]) ++k;
+        const int l = i - off[k];
+        const SlabCells s = slab_cells_at(const_cast<void*>(R.cells[k]), res_cap);
+        chit[i] = s.hit[l]; ctot[i] = s.tot[l]; cminh[i] = s.minh[l]; cell_voxel[i] = s.voxel[l];
+        const float2* m2 = reinterpret_cast<const float2*>(s.met + (long long)l * 10);
+        float2* d2 = reinterpret_cast<float2*>(cmet + (long long)i * 10);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) d2[a] = m2[a];
+        ceig[i * 3 + 0] = s.eig[l * 3 + 0]; ceig[i * 3 + 1] = s.eig[l * 3 + 1]; ceig[i * 3 + 2] = s.eig[l * 3 + 2];
+    }
+}
 
 // ---------------------------------------------------------------------------
 // tooling: L2 atomic-throughput microbenchmark (roofline denominator of the

@@ -61,7 +61,7 @@ class MultiGpuGvom(Gvom):
     """One rank of a multi-GPU Gvom.  Same API as Gvom; combine_maps() is collective
     (every rank must call it) and returns the same maps on every rank."""
 
-    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", **kw):
+    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", sharded=True, **kw):
         import torch
         import torch.distributed as dist
         self._dist, self._group = dist, group
@@ -79,6 +79,10 @@ class MultiGpuGvom(Gvom):
         self._org_in = (C.c_double * 3)()
         self._calls = 0
         self.exchange = None
+        # sharded finish (each rank merges 1/world of the z-planes) needs whole warps per plane
+        self._sharded = sharded and self.xy_size % 16 == 0
+        ccap = min(self.voxel_count, 4 * self.max_points * (self.buffer_size + 1))
+        self._res_cap = int(min(self.voxel_count, max(1 << 18, 4 * ccap // self.world)))
         if exchange in ("auto", "p2p"):
             try:
                 self._init_p2p()
@@ -105,6 +109,13 @@ class MultiGpuGvom(Gvom):
         o_hdr = o_cnt + 256
         o_flg = o_hdr + 8 * HEADER_DOUBLES + 256          # flags[rank] int32: rank's epoch, written by that rank
         total = o_flg + 4 * 64 + 256
+        # sharded finish: slab-done flags, result count, result index map, result cells (68 B per row)
+        self._o_flg2 = total
+        self._o_rcnt = self._o_flg2 + 4 * 64 + 256
+        self._o_rmap = self._o_rcnt + 256
+        self._o_rcel = (self._o_rmap + 4 * V + 255) & ~255
+        if self._sharded:
+            total = self._o_rcel + 68 * self._res_cap + 256
         return o_grid, o_msk, o_rec, o_cnt, o_hdr, total, o_flg
 
     def _init_p2p(self):
@@ -128,6 +139,9 @@ class MultiGpuGvom(Gvom):
                 "hdr_view": t[o_hdr:o_hdr + 8 * HEADER_DOUBLES].view(torch.float64),
                 # my flag slot in every rank's block (signal) / all ranks' slots in my block (wait)
                 "signal": _ptr_array([p + o_flg + 4 * self.rank for p in ptrs]), "wait": ptrs[self.rank] + o_flg,
+                "signal2": _ptr_array([p + self._o_flg2 + 4 * self.rank for p in ptrs]), "wait2": ptrs[self.rank] + self._o_flg2,
+                "rmaps": _ptr_array([p + self._o_rmap for p in ptrs]), "rcells": _ptr_array([p + self._o_rcel for p in ptrs]),
+                "rcnts": _ptr_array([p + self._o_rcnt for p in ptrs]),
             })
         torch.cuda.synchronize(self._dev)
         dist.barrier(group=self._group)
@@ -195,6 +209,15 @@ class MultiGpuGvom(Gvom):
                 for k in range(3):
                     self._org_in[k] = float(origin[k])
             outs, optr, mem = self._outputs(device_outputs)
+            if self._sharded:
+                # every rank finishes 1/world of the planes, publishes them, and assembles the full map from all ranks
+                check(L.gvom_combine_finish_sharded(self._h, self._org_in, self.rank, self.world, X["grids"], X["masks"],
+                                                    X["recs"], self._rec_cap, X["wait"], X["rmaps"], X["rcells"], X["rcnts"],
+                                                    self._res_cap, X["signal2"], X["wait2"], epoch, 3, self._org_c,
+                                                    optr[0], optr[1], optr[2], optr[3], mem, self._stream),
+                      "gvom_combine_finish_sharded")
+                pos, neg, rough, vis = outs
+                return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
             # the finishing merge kernel waits on the flag slots itself, then reads the peers' buffers over NVLink
             check(L.gvom_combine_finish(self._h, self._org_in, X["grids"], X["masks"], self.world, X["recs"], X["cnts"],
                                         self.world, self._rec_cap, X["wait"], epoch, self._org_c, optr[0], optr[1],

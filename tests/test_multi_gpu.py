@@ -83,6 +83,53 @@ def local_exchange(ranks, reduced=False):
     return outs
 
 
+def local_exchange_sharded(ranks, epoch):
+    """In-process emulation of the SHARDED peer-to-peer finish: every "rank" merges the z-planes it owns
+    (phase 1, all ranks), then assembles the full map from all ranks' planes (phase 2)."""
+    import torch
+    from gvom_b200._lib import GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, check
+    g0 = ranks[0]
+    L, V = g0._L, g0.voxel_count
+    dev = f"cuda:{g0.device}"
+    n = len(ranks)
+    org = (C.c_double * 3)()
+    origin = None
+    for g in ranks:
+        if L.gvom_newest_origin(g._h, org) != GVOM_NO_DATA and origin is None:
+            origin = [org[0], org[1], org[2]]
+    o = (C.c_double * 3)(*origin)
+    cap = int(min(V, g0.buffer_size * g0.max_points))
+    rcap = V
+    parr = lambda ps: (C.c_void_p * len(ps))(*[C.c_void_p(int(p)) for p in ps])
+    B = [dict(grid=torch.empty(V, dtype=torch.int32, device=dev), msk=torch.empty(V // 256 + 2, dtype=torch.int32, device=dev),
+              rec=torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev), cnt=torch.zeros(1, dtype=torch.int32, device=dev),
+              f1=torch.zeros(64, dtype=torch.int32, device=dev), f2=torch.zeros(64, dtype=torch.int32, device=dev),
+              rcnt=torch.zeros(1, dtype=torch.int32, device=dev), rmap=torch.full((V,), -7, dtype=torch.int32, device=dev),
+              rcel=torch.empty(68 * rcap, dtype=torch.uint8, device=dev)) for _ in ranks]
+    for r, g in enumerate(ranks):
+        sig = parr([b["f1"].data_ptr() + 4 * r for b in B])
+        check(L.gvom_combine_partial(g._h, o, B[r]["grid"].data_ptr(), B[r]["msk"].data_ptr(), B[r]["rec"].data_ptr(), cap,
+                                     B[r]["cnt"].data_ptr(), sig, n, epoch, None), "partial")
+    torch.cuda.synchronize()
+    grids, masks = parr([b["grid"].data_ptr() for b in B]), parr([b["msk"].data_ptr() for b in B])
+    recs = parr([b["rec"].data_ptr() for b in B])
+    rmaps, rcels = parr([b["rmap"].data_ptr() for b in B]), parr([b["rcel"].data_ptr() for b in B])
+    rcnts = parr([b["rcnt"].data_ptr() for b in B])
+    outs = []
+    for phase in (1, 2):
+        for r, g in enumerate(ranks):
+            sig2 = parr([b["f2"].data_ptr() + 4 * r for b in B])
+            pos, neg, rough, vis = g._out_arrays()
+            oo = (C.c_double * 3)()
+            check(L.gvom_combine_finish_sharded(g._h, o, r, n, grids, masks, recs, cap, B[r]["f1"].data_ptr(), rmaps, rcels, rcnts,
+                                                rcap, sig2, B[r]["f2"].data_ptr(), epoch, phase, oo, pos.ctypes.data,
+                                                neg.ctypes.data, rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None), "sharded")
+            torch.cuda.synchronize()
+            if phase == 2:
+                outs.append((np.array(list(oo)), pos, neg, rough, vis))
+    return outs
+
+
 def compare_state(a, b, what):
     """a, b: canon_combine dumps. ints exact, floats to tolerance."""
     for k in ("out_origin", "out_pos", "out_neg", "out_vis", "codes", "ids", "hit", "total", "minh"):
@@ -92,7 +139,8 @@ def compare_state(a, b, what):
     assert np.allclose(a["metrics"], b["metrics"], rtol=1e-4, atol=2e-6), f"{what}: metrics"
 
 
-@pytest.mark.parametrize("nranks,reduced", [(1, False), (2, False), (3, False), (2, True)])
+@pytest.mark.parametrize("nranks,reduced", [(1, False), (2, False), (3, False), (2, True), (1, "sharded"), (2, "sharded"),
+                                            (3, "sharded")])
 def test_partial_finish_equals_single(nranks, reduced):
     from gvom_b200 import Gvom
     B = 2
@@ -103,7 +151,7 @@ def test_partial_finish_equals_single(nranks, reduced):
     for step in range(5):
         for r in range(nranks):
             ranks[r].Process_pointcloud(*fr[step][r])
-        outs = local_exchange(ranks, reduced)
+        outs = local_exchange_sharded(ranks, step + 1) if reduced == "sharded" else local_exchange(ranks, reduced)
         # One Gvom with B*nranks slots holding the same scans: replay the whole history from
         # scratch (it needs the same chain of "previous combined map" states), feeding before
         # every combine the scans the rank rings hold at that step, newest step last.
