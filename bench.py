@@ -344,7 +344,8 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": ("configs[1]: synthetic OS1-128 scan (128x2048=262,144 pts), 256x256x64 grid @0.4/0.2 m, "
                                 "buffer 4, one sensor per GPU" + ("; configs[2]: per-GPU streams, NCCL-reduced combine" if multi else "")),
-                   "exchange": getattr(g, "exchange", None), "frames": NFRAMES, "l2": "flushed between steps (256 MiB memset, outside the timed region)",
+                   "exchange": (getattr(g, "exchange", None) or "") + (" sharded-finish" if getattr(g, "_sharded", False) and getattr(g, "exchange", "") == "p2p" else ""),
+                   "frames": NFRAMES, "l2": "flushed between steps (256 MiB memset, outside the timed region)",
                    "value_io": "cloud resident in HBM (float64 Nx3), maps left in HBM",
                    "e2e_io": "pinned host float64 Nx3 cloud in, numpy maps out (pinned), per-step wall clock around both calls"},
         "p50_latency_ms": statistics.median(ev_dev),

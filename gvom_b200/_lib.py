@@ -52,7 +52,7 @@ SYMBOLS = {
     "gvom_combine_finish": (C.c_int, [_vp, _pd, C.POINTER(_vp), C.POINTER(_vp), _i32, C.POINTER(_vp), C.POINTER(_vp), _i32, _i64, _vp, _i32, _pd,
                                       _vp, _vp, _vp, _vp, _i32, _vp]),
     "gvom_combine_finish_sharded": (C.c_int, [_vp, _pd, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i64, _vp,
-                                              C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i64, C.POINTER(_vp), _vp, _i32, _i32,
+                                              C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, C.POINTER(_vp), _vp, _i32, _i32,
                                               _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gvom_slot_info": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i64), _pd]),
     "gvom_last_slot": (C.c_int, [_vp, C.POINTER(_i32)]),

@@ -94,7 +94,8 @@ struct Carver {                    // sub-allocates a workspace block, 256-byte 
     }
 };
 
-enum { EV_START = 0, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER, EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS, EV_D2H, EV_COUNT };
+enum { EV_START = 0, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER, EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS, EV_D2H,
+       EV_X0, EV_X1, EV_X2, EV_COUNT };   // EV_X*: extra marks inside the multi-GPU combine
 
 }  // namespace
 
@@ -138,7 +139,7 @@ struct GvomHandle {
     cudaEvent_t ev[EV_COUNT];
     bool profiling = false;
     bool zero_copy = true;                // host clouds: K1 reads pinned memory directly (else chunked DMA)
-    bool prof_process = false, prof_combine = false;
+    bool prof_process = false, prof_combine = false, prof_x = false;
     int sm_count = 148;
     int grid_index = 0, grid_codes = 0, grid_cells = 0, grid_gather = 0;   // resident grids (set at create)
     GvomStats stats{};
@@ -808,6 +809,11 @@ int gvom_stage_times(GvomHandle* h, float ms[16]) {
         for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], h->ev[a[i]], h->ev[b[i]]));
     }
     ms[9] = h->last_stage_copy_ms;
+    if (h->prof_x) {   // sharded multi-GPU combine: [10] slab cells, [11] signal + wait + gather maps, [12] gather cells
+        CUDA_TRY(cudaEventElapsedTime(&ms[10], h->ev[EV_CODES], h->ev[EV_X0]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[11], h->ev[EV_X0], h->ev[EV_X1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[12], h->ev[EV_X1], h->ev[EV_CELLS]));
+    }
     if (h->prof_combine) {
         const int a[4] = {EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS};
         const int b[4] = {EV_CODES, EV_CELLS, EV_MAPS, EV_D2H};
@@ -969,11 +975,11 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
                                 const int32_t* const* code_grids, const uint32_t* const* group_masks,
                                 const float* const* records, int64_t record_capacity,
                                 const int32_t* wait_partial, int32_t* const* res_maps, void* const* res_cells,
-                                int32_t* const* res_counts, int64_t res_capacity,
+                                int32_t* const* count_slots, const int32_t* count_table, int64_t res_capacity,
                                 int32_t* const* signal_slab, const int32_t* wait_slab, int32_t epoch, int32_t phases,
                                 double origin_out[3], int32_t* positive, int32_t* negative, double* roughness,
                                 int32_t* visibility, int32_t out_mem, void* stream) {
-    if (!h || !origin || !code_grids || !records || !res_maps || !res_cells || !res_counts || !signal_slab)
+    if (!h || !origin || !code_grids || !records || !res_maps || !res_cells || !count_slots || !count_table || !signal_slab)
         return fail(GVOM_EINVAL, "NULL argument");
     if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return fail(GVOM_EINVAL, "bad rank / nranks");
     if (h->p.xy_size % 8 != 0 || (((int64_t)h->p.xy_size * h->p.xy_size / 8) % 32) != 0)
@@ -990,16 +996,16 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     MergeArgs A;
     A.n = 0; A.use_masks = 1;
     RankBufs B; B.n = nranks;
-    SlabSet R; R.n = nranks;
+    SlabSet R; R.n = nranks; R.counts = count_table;
     for (int k = 0; k < nranks; ++k) {
-        if (!code_grids[k] || !records[k] || !res_maps[k] || !res_cells[k] || !res_counts[k]) return fail(GVOM_EINVAL, "NULL rank buffer");
+        if (!code_grids[k] || !records[k] || !res_maps[k] || !res_cells[k] || !count_slots[k]) return fail(GVOM_EINVAL, "NULL rank buffer");
         SlotRef& r = A.s[A.n++];
         r = SlotRef{};
         r.map = code_grids[k];
         r.gmask = group_masks ? group_masks[k] : nullptr;
         if (!r.gmask) A.use_masks = 0;
         B.grid[k] = code_grids[k]; B.rec[k] = records[k];
-        R.map[k] = res_maps[k]; R.count[k] = res_counts[k]; R.cells[k] = res_cells[k];
+        R.map[k] = res_maps[k]; R.cells[k] = res_cells[k];
     }
     SlotRef prev{};
     const int has_prev = pc.valid ? 1 : 0;
@@ -1021,8 +1027,13 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
         launch(k_merge_codes<8, MERGE_FINISH>, dim3(std::max(1, h->grid_codes / std::max(1, nranks / 2))), dim3(256), 0, st, A, O, h->dp);
     rec(h, EV_CODES, st);
     // 2. my cells
-    launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 1, mine, res_counts[rank], h->dp,
-           (int)res_capacity, (int)record_capacity);
+    {
+        SignalSet CS; CS.n = nranks;
+        for (int k = 0; k < nranks; ++k) CS.slot[k] = count_slots[k];
+        launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 1, mine, CS, h->dp,
+               (int)res_capacity, (int)record_capacity);
+    }
+    rec(h, EV_X0, st);
     {
         SignalSet S; S.n = nranks;
         for (int k = 0; k < nranks; ++k) S.slot[k] = signal_slab[k];
@@ -1034,11 +1045,13 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     // 3. everybody's planes and cells
     launch(k_gather_maps, dim3(h->sm_count * 4), dim3(256), 0, st, R, wait_slab, (int)epoch, c.index_map, c.gmask, h->col_minz,
            h->col_minz + h->S2, h->flags + 1, h->dp);
+    rec(h, EV_X1, st);
     launch(k_gather_cells, dim3(h->sm_count * 2), dim3(256), 0, st, R, (long long)res_capacity, c.hit, c.total, c.minh, c.metrics,
            c.eig, c.cell_voxel, (int)h->ccap);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 2;
     h->prof_combine = h->profiling;
+    h->prof_x = h->profiling && (phases == 3);
     c.has_gmask = true;
     const int r = run_maps_and_output(h, c, origin_out, positive, negative, roughness, visibility, out_mem, st);
     if (r != GVOM_OK) return r;

@@ -1293,10 +1293,9 @@ constexpr int MAX_RANKS = 16;
 // point into local (all-reduced / all-gathered) memory; with the peer-to-peer exchange they are
 // the OTHER GPUs' buffers mapped over NVLink, read directly by the kernels below.
 struct RecordSet { const float* r[MAX_RANKS]; const int* count[MAX_RANKS]; int n; };
-
-// publish "my partial results of combine `epoch` are complete" into every rank's flag slot for this rank
 struct SignalSet { int* slot[MAX_RANKS]; int n; };
 
+// publish "my partial results of combine `epoch` are complete" into every rank's flag slot for this rank
 __global__ void k_signal(SignalSet S, int epoch) {
     pdl_wait();                                   // after this rank's partial kernels
     __threadfence_system();
@@ -1452,10 +1451,11 @@ constexpr int SLAB_CELL_BYTES = 68;
 // found through the id stored in the rank's encoded grid.
 __global__ void __launch_bounds__(128)
 k_slab_cells(RankBufs B, SlotRef prev, int has_prev, const int* __restrict__ counter, SlabCells out,
-             int* __restrict__ out_count, DevParams P, int cap, int rec_cap) {
+             SignalSet count_slots, DevParams P, int cap, int rec_cap) {
     pdl_wait();
     const int count = min(*counter, cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = count;
+    // publish my cell count into every rank's count table (remote WRITES are posted; a remote read costs ~2 us)
+    if (blockIdx.x == 0 && threadIdx.x < count_slots.n) *count_slots.slot[threadIdx.x] = count;
     const int S = P.S, Z = P.Z;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
         const int v = out.voxel[id];
@@ -1502,7 +1502,7 @@ k_slab_cells(RankBufs B, SlotRef prev, int has_prev, const int* __restrict__ cou
 
 struct SlabSet {                  // every rank's slab result as seen from here
     const int* map[MAX_RANKS];    // full-size index map, valid on the rank's own planes, ids local to the rank
-    const int* count[MAX_RANKS];
+    const int* counts;            // LOCAL table: counts[k] = cells of rank k (pushed by rank k)
     const void* cells[MAX_RANKS]; // SlabCells base
     int n;
 };
@@ -1517,7 +1517,7 @@ __device__ __forceinline__ void slab_wait_and_offsets(const SlabSet& R, const in
             }
         __threadfence_system();
         int acc = 0;
-        for (int k = 0; k < R.n; ++k) { off[k] = acc; acc += *reinterpret_cast<const volatile int*>(R.count[k]); }
+        for (int k = 0; k < R.n; ++k) { off[k] = acc; acc += *reinterpret_cast<const volatile int*>(R.counts + k); }
         off[R.n] = acc;
     }
     __syncthreads();

@@ -61,7 +61,7 @@ class MultiGpuGvom(Gvom):
     """One rank of a multi-GPU Gvom.  Same API as Gvom; combine_maps() is collective
     (every rank must call it) and returns the same maps on every rank."""
 
-    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", sharded=True, **kw):
+    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", sharded="auto", **kw):
         import torch
         import torch.distributed as dist
         self._dist, self._group = dist, group
@@ -80,7 +80,11 @@ class MultiGpuGvom(Gvom):
         self._calls = 0
         self.exchange = None
         # sharded finish (each rank merges 1/world of the z-planes) needs whole warps per plane
-        self._sharded = sharded and self.xy_size % 16 == 0
+        # measured on 8x B200 (profiles/): the sharded finish wins from ~6 ranks up; below that the extra assembly
+        # pass costs more than the finishing work it saves, so the replicated finish is used
+        if sharded == "auto":
+            sharded = self.world >= 6
+        self._sharded = bool(sharded) and self.xy_size % 16 == 0
         ccap = min(self.voxel_count, 4 * self.max_points * (self.buffer_size + 1))
         self._res_cap = int(min(self.voxel_count, max(1 << 18, 4 * ccap // self.world)))
         if exchange in ("auto", "p2p"):
@@ -112,7 +116,7 @@ class MultiGpuGvom(Gvom):
         # sharded finish: slab-done flags, result count, result index map, result cells (68 B per row)
         self._o_flg2 = total
         self._o_rcnt = self._o_flg2 + 4 * 64 + 256
-        self._o_rmap = self._o_rcnt + 256
+        self._o_rmap = self._o_rcnt + 4 * 64 + 256
         self._o_rcel = (self._o_rmap + 4 * V + 255) & ~255
         if self._sharded:
             total = self._o_rcel + 68 * self._res_cap + 256
@@ -141,7 +145,8 @@ class MultiGpuGvom(Gvom):
                 "signal": _ptr_array([p + o_flg + 4 * self.rank for p in ptrs]), "wait": ptrs[self.rank] + o_flg,
                 "signal2": _ptr_array([p + self._o_flg2 + 4 * self.rank for p in ptrs]), "wait2": ptrs[self.rank] + self._o_flg2,
                 "rmaps": _ptr_array([p + self._o_rmap for p in ptrs]), "rcells": _ptr_array([p + self._o_rcel for p in ptrs]),
-                "rcnts": _ptr_array([p + self._o_rcnt for p in ptrs]),
+                # count table (64 ints) in every rank's block: entry r is pushed by rank r
+                "cslots": _ptr_array([p + self._o_rcnt + 4 * self.rank for p in ptrs]), "ctable": ptrs[self.rank] + self._o_rcnt,
             })
         torch.cuda.synchronize(self._dev)
         dist.barrier(group=self._group)
@@ -212,8 +217,8 @@ class MultiGpuGvom(Gvom):
             if self._sharded:
                 # every rank finishes 1/world of the planes, publishes them, and assembles the full map from all ranks
                 check(L.gvom_combine_finish_sharded(self._h, self._org_in, self.rank, self.world, X["grids"], X["masks"],
-                                                    X["recs"], self._rec_cap, X["wait"], X["rmaps"], X["rcells"], X["rcnts"],
-                                                    self._res_cap, X["signal2"], X["wait2"], epoch, 3, self._org_c,
+                                                    X["recs"], self._rec_cap, X["wait"], X["rmaps"], X["rcells"], X["cslots"],
+                                                    X["ctable"], self._res_cap, X["signal2"], X["wait2"], epoch, 3, self._org_c,
                                                     optr[0], optr[1], optr[2], optr[3], mem, self._stream),
                       "gvom_combine_finish_sharded")
                 pos, neg, rough, vis = outs

@@ -148,8 +148,8 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
 
 /* Sharded finish (peer-to-peer exchange, xy_size % 16 == 0): rank `rank` merges only the z-planes with
  * z % nranks == rank (from every rank's encoded grid, read over NVLink) and the cells on them, publishes
- * the result (res_maps[rank], res_cells[rank], res_counts[rank]; all arrays are nranks pointers into
- * the ranks' mapped memory), then assembles the full combined map from all ranks' planes.  Per-rank
+ * the result (res_maps[rank], res_cells[rank]; arrays of nranks pointers into the ranks' mapped
+ * memory; its cell count is pushed into count_slots[k] = entry `rank` of rank k's count_table), then assembles the full combined map from all ranks' planes.  Per-rank
  * finishing work is V / nranks; the combined state stays replicated.  wait_partial / wait_slab:
  * nranks local int32 flag slots (partial results / slab results published, value >= epoch);
  * signal_slab: this rank's slab flag slot in every rank's memory.  res_cells block: 68 bytes per row.
@@ -159,7 +159,8 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
                                 const int32_t* const* code_grids, const uint32_t* const* group_masks,
                                 const float* const* records, int64_t record_capacity,
                                 const int32_t* wait_partial, int32_t* const* res_maps,
-                                void* const* res_cells, int32_t* const* res_counts, int64_t res_capacity,
+                                void* const* res_cells, int32_t* const* count_slots,
+                                const int32_t* count_table, int64_t res_capacity,
                                 int32_t* const* signal_slab, const int32_t* wait_slab, int32_t epoch,
                                 int32_t phases, double origin_out[3], int32_t* positive, int32_t* negative,
                                 double* roughness, int32_t* visibility, int32_t out_mem, void* stream);

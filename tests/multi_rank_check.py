@@ -27,7 +27,8 @@ def main():
     P1 = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B, robot_radius=2.0)
     PN = synth.params_tuple(xy_size=64, z_size=16, buffer_size=B * world, robot_radius=2.0)
     fr = sensor_frames(world, 4)
-    g = MultiGpuGvom(*P1, device=local, exchange=sys.argv[1] if len(sys.argv) > 1 else "auto")
+    g = MultiGpuGvom(*P1, device=local, exchange=sys.argv[1] if len(sys.argv) > 1 else "auto",
+                     sharded=True if "sharded" in sys.argv else "auto")
     if len(sys.argv) > 2 and sys.argv[2] == "late":        # start-up path: rank 1 joins one combine late
         first = MultiGpuGvom(*P1, device=local, exchange=sys.argv[1])
         if rank == 0:
@@ -49,7 +50,7 @@ def main():
                       f"step {step} rank {rank}")
     dist.barrier()
     if rank == 0:
-        print("MULTI_RANK_OK exchange=" + g.exchange + (" p2p_error=" + getattr(g, "_p2p_error", "") if g.exchange != "p2p" else ""))
+        print("MULTI_RANK_OK exchange=" + g.exchange + (" sharded" if getattr(g, "_sharded", False) and g.exchange == "p2p" else "") + (" p2p_error=" + getattr(g, "_p2p_error", "") if g.exchange != "p2p" else ""))
     dist.destroy_process_group()
 
 

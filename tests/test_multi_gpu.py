@@ -104,7 +104,7 @@ def local_exchange_sharded(ranks, epoch):
     B = [dict(grid=torch.empty(V, dtype=torch.int32, device=dev), msk=torch.empty(V // 256 + 2, dtype=torch.int32, device=dev),
               rec=torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev), cnt=torch.zeros(1, dtype=torch.int32, device=dev),
               f1=torch.zeros(64, dtype=torch.int32, device=dev), f2=torch.zeros(64, dtype=torch.int32, device=dev),
-              rcnt=torch.zeros(1, dtype=torch.int32, device=dev), rmap=torch.full((V,), -7, dtype=torch.int32, device=dev),
+              rcnt=torch.zeros(64, dtype=torch.int32, device=dev), rmap=torch.full((V,), -7, dtype=torch.int32, device=dev),
               rcel=torch.empty(68 * rcap, dtype=torch.uint8, device=dev)) for _ in ranks]
     for r, g in enumerate(ranks):
         sig = parr([b["f1"].data_ptr() + 4 * r for b in B])
@@ -114,15 +114,15 @@ def local_exchange_sharded(ranks, epoch):
     grids, masks = parr([b["grid"].data_ptr() for b in B]), parr([b["msk"].data_ptr() for b in B])
     recs = parr([b["rec"].data_ptr() for b in B])
     rmaps, rcels = parr([b["rmap"].data_ptr() for b in B]), parr([b["rcel"].data_ptr() for b in B])
-    rcnts = parr([b["rcnt"].data_ptr() for b in B])
     outs = []
     for phase in (1, 2):
         for r, g in enumerate(ranks):
             sig2 = parr([b["f2"].data_ptr() + 4 * r for b in B])
+            cslots = parr([b["rcnt"].data_ptr() + 4 * r for b in B])
             pos, neg, rough, vis = g._out_arrays()
             oo = (C.c_double * 3)()
-            check(L.gvom_combine_finish_sharded(g._h, o, r, n, grids, masks, recs, cap, B[r]["f1"].data_ptr(), rmaps, rcels, rcnts,
-                                                rcap, sig2, B[r]["f2"].data_ptr(), epoch, phase, oo, pos.ctypes.data,
+            check(L.gvom_combine_finish_sharded(g._h, o, r, n, grids, masks, recs, cap, B[r]["f1"].data_ptr(), rmaps, rcels, cslots,
+                                                B[r]["rcnt"].data_ptr(), rcap, sig2, B[r]["f2"].data_ptr(), epoch, phase, oo, pos.ctypes.data,
                                                 neg.ctypes.data, rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None), "sharded")
             torch.cuda.synchronize()
             if phase == 2:
@@ -172,7 +172,8 @@ def test_nccl_two_ranks(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     script = os.path.join(ROOT, "tests", "multi_rank_check.py")
-    for port, exchange, extra in ((29533, "nccl", []), (29534, "auto", []), (29535, "auto", ["late"])):
+    for port, exchange, extra in ((29533, "nccl", []), (29534, "auto", []), (29535, "auto", ["late"]),
+                                  (29536, "p2p", ["sharded"])):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                             "--master-addr", "127.0.0.1", "--master-port", str(port), script, exchange] + extra,
                            capture_output=True, text=True, timeout=600)
