@@ -181,8 +181,9 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
         c.gmask = d.take<unsigned>(V / 256 + 2);
     }
     h->maps = d.take<double>(6 * S2);
-    h->imaps = d.take<int>(3 * S2 + 2 * S2);
-    h->rough_out = reinterpret_cast<double*>(h->imaps ? h->imaps + 3 * S2 : nullptr);
+    // result block: three int32 maps, padding to 8 bytes (odd xy_size), then the float64 roughness map
+    h->imaps = d.take<int>(3 * S2 + 2 * S2 + 2);
+    h->rough_out = reinterpret_cast<double*>(h->imaps ? h->imaps + ((3 * S2 + 1) & ~size_t(1)) : nullptr);
     h->col_minz = d.take<int>(2 * S2);
     h->known = d.take<unsigned>(2 * (size_t)p.xy_size * ((p.xy_size + 31) / 32));
     h->debug_dev = d.take<float>(std::max(ccap * 8, S2 * 10));
@@ -190,7 +191,7 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
     h->cacc = d.take<double>(ccap * 10);
     Carver c(host);
     h->stage_host = c.take<char>((size_t)h->max_points * 32);
-    h->out_i_host = c.take<int>(3 * S2 + 2 * S2);   // mirrors the device result block
+    h->out_i_host = c.take<int>(3 * S2 + 2 * S2 + 2);   // mirrors the device result block
     h->counters_host = c.take<int>(8);
     *host_bytes = c.off + 256;
     return d.off + 256;
@@ -345,10 +346,11 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
                             is_pinned_or_device(negative, &dev) && is_pinned_or_device(visibility, &dev) &&
                             is_pinned_or_device(roughness, &dev);
         if (direct) {                      // caller's buffers are pinned: DMA straight into them
+            const size_t rough_off = ((3 * (size_t)S2 + 1) & ~size_t(1)) * sizeof(int);
             if (negative == positive + S2 && visibility == negative + S2 &&
-                reinterpret_cast<char*>(roughness) == reinterpret_cast<char*>(visibility + S2)) {
+                reinterpret_cast<char*>(roughness) == reinterpret_cast<char*>(positive) + rough_off) {
                 // laid out like the device result block: one transfer for all four maps
-                CUDA_TRY(cudaMemcpyAsync(positive, pos, 3 * bi + bd, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(positive, pos, rough_off + bd, cudaMemcpyDeviceToHost, st));
             } else {
                 CUDA_TRY(cudaMemcpyAsync(positive, pos, bi, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaMemcpyAsync(negative, neg, bi, cudaMemcpyDeviceToHost, st));
@@ -358,13 +360,14 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
             rec(h, EV_D2H, st);
             CUDA_TRY(cudaStreamSynchronize(st));
         } else {                           // pageable: one DMA per dtype into pinned staging, then memcpy
-            CUDA_TRY(cudaMemcpyAsync(h->out_i_host, h->imaps, 3 * bi + bd, cudaMemcpyDeviceToHost, st));
+            const size_t rough_off = ((3 * (size_t)S2 + 1) & ~size_t(1)) * sizeof(int);
+            CUDA_TRY(cudaMemcpyAsync(h->out_i_host, h->imaps, rough_off + bd, cudaMemcpyDeviceToHost, st));
             rec(h, EV_D2H, st);
             CUDA_TRY(cudaStreamSynchronize(st));
             if (positive) memcpy(positive, h->out_i_host, bi);
             if (negative) memcpy(negative, h->out_i_host + S2, bi);
             if (visibility) memcpy(visibility, h->out_i_host + 2 * (size_t)S2, bi);
-            if (roughness) memcpy(roughness, h->out_i_host + 3 * (size_t)S2, bd);
+            if (roughness) memcpy(roughness, reinterpret_cast<char*>(h->out_i_host) + rough_off, bd);
         }
     }
     c.cells = std::min<int64_t>(h->counters_host[0], h->ccap);

@@ -728,6 +728,7 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
                 }
 #pragma unroll
                 for (int u = 0; u < SLOT_BATCH; ++u) {
+                    if (!(need & (1u << u))) continue;                      // nothing but "unknown" there: no fold either
                     if (has_prev && k0 + u == A.n - 1) {
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) op[j] = o[u][j];

@@ -151,9 +151,10 @@ class Gvom:
         library moves all four maps with a single DMA straight into the returned arrays."""
         S = self.xy_size
         if self.pinned_outputs:
-            blk = self._torch.empty(20 * S * S, dtype=self._torch.uint8, pin_memory=True).numpy()
+            ro = (12 * S * S + 7) & ~7               # roughness starts 8-byte aligned (odd xy_size)
+            blk = self._torch.empty(ro + 8 * S * S, dtype=self._torch.uint8, pin_memory=True).numpy()
             i32 = blk[:12 * S * S].view(np.int32).reshape(3, S, S)
-            rough = blk[12 * S * S:].view(np.float64).reshape(S, S)
+            rough = blk[ro:].view(np.float64).reshape(S, S)
             return i32[0], i32[1], rough, i32[2]
         return (np.empty((S, S), np.int32), np.empty((S, S), np.int32), np.empty((S, S), np.float64),
                 np.empty((S, S), np.int32))

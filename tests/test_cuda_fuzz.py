@@ -1,0 +1,119 @@
+"""Randomised replay of small configurations: CUDA path vs the pinned oracle, every step.
+
+Covers what the fixed scenarios do not: grid sizes that take the non-vectorised kernel variants
+(xy_size % 8 != 0 -> 4 voxels/thread, xy_size % 4 != 0 -> 1 voxel/thread, no group masks), neighbourhood
+radii 0..2, buffer sizes 1..3, clouds with many out-of-grid / too-close points, float32 and float64,
+N x 3 and N x 4, arbitrary ego jumps (large origin shifts, also negative), repeated combines."""
+import threading
+
+import numpy as np
+import pytest
+
+import canon
+from gvom_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def random_case(seed):
+    rng = np.random.default_rng(seed)
+    S = int(rng.choice([16, 18, 20, 24, 33, 40]))
+    Z = int(rng.choice([6, 8, 12]))
+    res_xy, res_z = float(rng.choice([0.4, 0.25, 0.5])), float(rng.choice([0.2, 0.25, 0.4]))
+    P = synth.params_tuple(xy_resolution=res_xy, z_resolution=res_z, xy_size=S, z_size=Z,
+                           buffer_size=int(rng.integers(1, 4)), min_distance=float(rng.choice([0.0, 0.7, 1.0])),
+                           robot_radius=float(rng.choice([0.9, 1.7])), robot_height=float(rng.choice([1.0, 2.0])),
+                           xy_eigen_dist=int(rng.integers(0, 3)), z_eigen_dist=int(rng.integers(0, 3)))
+    ego = np.array([rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(0.5, 1.5)])
+    steps = []
+    for i in range(int(rng.integers(3, 7))):
+        ego = ego + np.array([rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(-0.4, 0.4)])
+        e = tuple(float(np.round(v * 1024) / 1024) for v in ego)
+        n = int(rng.integers(1, 700))
+        half = 0.5 * S * res_xy
+        pts = np.stack([rng.uniform(-1.3 * half, 1.3 * half, n) + e[0], rng.uniform(-1.3 * half, 1.3 * half, n) + e[1],
+                        rng.uniform(-0.8 * Z * res_z, 0.8 * Z * res_z, n) + e[2]], axis=1)
+        # clusters so that some voxels collect > 10 hits (positive-obstacle threshold) and dense columns exist
+        k = n // 3
+        pts[:k] = np.array([e[0] + 1.5, e[1] - 1.0, e[2] - 0.3]) + rng.normal(0, 0.15, (k, 3))
+        pts = np.round(pts * 1024) / 1024
+        T = None
+        if rng.random() < 0.5:                       # give the cloud in a sensor frame + transform
+            T = synth.pose_matrix(e, float(rng.uniform(-3, 3)))
+            R, t = T[:3, :3], T[:3, 3]
+            pts = np.round(((pts - t) @ R) * 1024) / 1024
+        if rng.random() < 0.4:
+            pts = pts.astype(np.float32)
+        if rng.random() < 0.3:
+            pts = np.concatenate([pts, np.ones((n, 1), pts.dtype)], axis=1)
+        steps.append(("scan", np.ascontiguousarray(pts), e, T))
+        for _ in range(int(rng.integers(0, 3))):
+            steps.append(("combine",))
+    steps += [("combine",), ("debug",)]
+    return P, steps
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_replay_matches_oracle(seed):
+    from gvom_b200 import Gvom
+    from oracle.gvom_oracle import OracleGvom
+    P, steps = random_case(seed)
+    g, o = Gvom(*P, max_points=1024), OracleGvom(*P)
+    for i, st in enumerate(steps):
+        if st[0] == "scan":
+            g.Process_pointcloud(st[1], st[2], st[3])
+            o.Process_pointcloud(st[1], st[2], st[3])
+            a, b = canon.canon_scan(g.refview()), canon.canon_scan(o)
+        elif st[0] == "combine":
+            og, oo = g.combine_maps(), o.combine_maps()
+            a, b = canon.canon_combine(g.refview(), og), canon.canon_combine(o, oo)
+        else:
+            a, b = canon.canon_debug(g.refview()), canon.canon_debug(o)
+        for k, bv in b.items():
+            av = a[k]
+            if isinstance(bv, str):
+                assert av == bv, (seed, i, st[0], k)
+            elif k in canon.EXACT:
+                assert np.array_equal(np.asarray(av), np.asarray(bv)), (seed, i, st[0], k, P)
+            else:
+                rtol, atol = canon.FLOAT.get(k, (1e-4, 1e-9))
+                x, y = np.asarray(av, np.float64), np.asarray(bv, np.float64)
+                ok = np.isclose(x, y, rtol=rtol, atol=atol)
+                if k in ("eig", "voxel") and x.ndim == 2 and x.size:
+                    cols = slice(0, 3) if k == "eig" else slice(5, 8)
+                    scale = np.abs(y[:, cols]).sum(axis=1, keepdims=True)
+                    ok[:, cols] |= np.abs(x[:, cols] - y[:, cols]) <= 1e-3 * scale + 1e-6
+                assert ok.all(), (seed, i, st[0], k, float(np.abs(x - y).max()))
+
+
+def test_concurrent_callers():
+    """ROS use: a subscriber thread feeds scans while a timer thread combines (README.md:49)."""
+    from gvom_b200 import Gvom
+    P = synth.params_tuple(xy_size=64, z_size=16, buffer_size=3, robot_radius=2.0)
+    g = Gvom(*P)
+    frames = [synth.frame(i, 16, 256, wall_radius=9.0, ego0=(10.0, 5.0, 1.0), dego=(0.3, 0.2, 0.05)) for i in range(40)]
+    errors, outs = [], []
+
+    def feeder():
+        try:
+            for pc, ego, T in frames:
+                g.Process_pointcloud(pc, ego, T)
+        except Exception as ex:                      # pragma: no cover
+            errors.append(ex)
+
+    def timer():
+        try:
+            for _ in range(60):
+                out = g.combine_maps()
+                if out is not None:
+                    outs.append(out)
+                    g.make_debug_voxel_map(); g.make_debug_height_map()
+        except Exception as ex:                      # pragma: no cover
+            errors.append(ex)
+
+    th = [threading.Thread(target=feeder), threading.Thread(target=timer)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    assert outs and all(o[1].shape == (64, 64) and np.isfinite(o[3]).all() for o in outs)
+    assert set(np.unique(outs[-1][4])) <= {0, 1} and set(np.unique(outs[-1][2])) <= {0, 100}
