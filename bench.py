@@ -334,9 +334,16 @@ def main():
                                         "peak_same_address": atom.get("same_address"),
                                         "note": "increments delivered (warp-aggregated) vs RED.ADD.U32 issue rate to "
                                                 "random words of a 16 MiB table measured by gvom_bench_atomics"}
-    kernels = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h")}
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tp):                        # DRAM bytes per launch from the committed ncu --set full capture
+        for k, v in json.load(open(tp)).items():
+            if isinstance(v, dict) and v.get("dram_read") is not None and v.get("dram_write") is not None:
+                traffic[k] = v["dram_read"] + v["dram_write"]
+    kernels = {k: v for k, v in stage_ms.items() if k in ("raycast", "index", "moments", "gather", "merge_codes", "merge_cells", "maps")}
     dom = max((k for k in kernels if k in rooflines), key=lambda k: kernels[k], default=None)
-    roof = dict(rooflines[dom], kernel=dom, traffic=None, peak_source=hbm_src) if dom else None
+    roof = dict(rooflines[dom], kernel=dom, traffic=traffic.get(dom), peak_source=hbm_src,
+                traffic_source="profiles/traffic_r01.json (ncu --set full, bytes per launch)") if dom else None
 
     line = {
         "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
