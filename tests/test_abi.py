@@ -23,6 +23,31 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 and a C program must link against the library."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "gvom_b200.h")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "abi.c"
+    src.write_text('''#include "gvom_b200.h"
+#include <stdio.h>
+int main(void) {
+    GvomParams p = {0.4, 0.2, 256, 64, 4, 0, 1.0, 0.5, 0.5, 0.3, 2.0, 4.0, 1.0, 1, 1};
+    size_t db = 0, hb = 0;
+    int rc = gvom_workspace_size(&p, 262144, 0, &db, &hb);
+    printf("%d %zu %zu %zu\\n", rc, db, hb, sizeof(GvomParams));
+    p.buffer_size = 0;
+    return rc != 0 || gvom_workspace_size(&p, 262144, 0, &db, &hb) != GVOM_EINVAL || gvom_last_error()[0] == 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "gvom_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lgvom_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert out[0] == "0" and int(out[1]) > 1 << 28 and out[3] == "96"
+
+
 def test_struct_layout_matches_header():
     from gvom_b200 import _lib
     assert C.sizeof(_lib.GvomParams) == 96
