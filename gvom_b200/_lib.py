@@ -12,7 +12,8 @@ SO_PATH = os.path.join(HERE, "libgvom_b200.so")
 
 GVOM_OK, GVOM_NO_DATA = 0, -1
 GVOM_F32, GVOM_F64 = 0, 1
-GVOM_HOST, GVOM_DEVICE = 0, 1
+GVOM_HOST, GVOM_DEVICE, GVOM_NONE = 0, 1, 2
+GRID_NAMES = ("hard", "soft", "certainty", "negative", "roughness")     # GVOM_GRID_* order
 RECORD_FLOATS = 16
 
 
@@ -43,6 +44,15 @@ SYMBOLS = {
     "gvom_destroy": (C.c_int, [_vp]),
     "gvom_process_pointcloud": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _pd, _vp, _vp]),
     "gvom_combine_maps": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "gvom_process_pointcloud2": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _pd, _vp, _vp]),
+    "gvom_combine_maps_async": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "gvom_combine_wait": (C.c_int, [_vp]),
+    "gvom_occupancy_grids": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, _vp, _i32, _vp]),
+    "gvom_combine_maps_grids": (C.c_int, [_vp, _pd, C.c_double, C.c_double, C.c_double, _vp, _i32, _vp]),
+    "gvom_state_size": (C.c_int, [_vp, C.POINTER(_sz)]),
+    "gvom_save_state": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "gvom_load_state": (C.c_int, [_vp, _vp, _sz]),
+    "gvom_set_variant": (C.c_int, [_vp, C.c_uint32]),
     "gvom_combined_cell_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "gvom_debug_voxel_map": (C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "gvom_debug_height_map": (C.c_int, [_vp, _vp]),

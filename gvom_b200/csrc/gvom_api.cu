@@ -97,6 +97,10 @@ struct Carver {                    // sub-allocates a workspace block, 256-byte 
 enum { EV_START = 0, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER, EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS, EV_D2H,
        EV_X0, EV_X1, EV_X2, EV_COUNT };   // EV_X*: extra marks inside the multi-GPU combine
 
+// GVOM_VARIANT bits (environment, read at create): earlier builds of kernels kept selectable so that one GPU
+// run can time both and the parity tests can be run on either
+enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_OLD_CELLS = 8, VAR_MERGE_NB6 = 16 };
+
 }  // namespace
 
 struct GvomHandle {
@@ -142,9 +146,22 @@ struct GvomHandle {
     bool prof_process = false, prof_combine = false, prof_x = false;
     int sm_count = 148;
     int grid_index = 0, grid_codes = 0, grid_cells = 0, grid_gather = 0;   // resident grids (set at create)
+    int grid_cells2 = 0, grid_gather2 = 0, grid_rows3 = 0, grid_rows6 = 0;
     GvomStats stats{};
     float last_stage_copy_ms = 0.f;       // host time of the last pageable->pinned staging copy
     CopyPool* pool = nullptr;             // staging threads for pageable input (created on first use)
+    signed char* grids_dev = nullptr;     // [GVOM_GRID_COUNT][S*S] int8 OccupancyGrid payloads
+    signed char* grids_host = nullptr;    // pinned mirror
+    unsigned variant = 0;                 // GVOM_VARIANT bit mask: kernel builds kept for A/B measurements (see create)
+    // outputs of the last combine that still have to be completed on the host (gvom_combine_maps_async)
+    struct Pending {
+        bool active = false;
+        Combined* c = nullptr;
+        cudaStream_t st = nullptr;
+        bool from_mirror = false;         // pageable outputs: copy out of the pinned mirror after the stream drained
+        int32_t *positive = nullptr, *negative = nullptr, *visibility = nullptr;
+        double* roughness = nullptr;
+    } pend;
     std::mutex mu;
 };
 
@@ -189,10 +206,12 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
     h->debug_dev = d.take<float>(std::max(ccap * 8, S2 * 10));
     h->flags = d.take<int>(8);
     h->cacc = d.take<double>(ccap * 10);
+    h->grids_dev = d.take<signed char>(GVOM_GRID_COUNT * S2);
     Carver c(host);
     h->stage_host = c.take<char>((size_t)h->max_points * 32);
     h->out_i_host = c.take<int>(3 * S2 + 2 * S2 + 2);   // mirrors the device result block
     h->counters_host = c.take<int>(8);
+    h->grids_host = c.take<signed char>(GVOM_GRID_COUNT * S2);
     *host_bytes = c.off + 256;
     return d.off + 256;
 }
@@ -294,6 +313,14 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
 
 template <int MODE>
 void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStream_t st) {
+    if (MODE == MERGE_FULL && h->p.xy_size % 256 == 0 && A.use_masks && O.gmask && !(h->variant & VAR_OLD_MERGE)) {
+        if (h->variant & VAR_MERGE_NB6)
+            launch(k_merge_rows<6>, dim3(h->grid_rows6), dim3(256), 0, st, A, O, h->dp);
+        else
+            launch(k_merge_rows<3>, dim3(h->grid_rows3), dim3(256), 0, st, A, O, h->dp);
+        h->stats.kernel_launches++;
+        return;
+    }
     if (h->p.xy_size % 8 == 0)
         launch(k_merge_codes<8, MODE>, dim3(h->grid_codes), dim3(256), 0, st, A, O, h->dp);
     else if (h->p.xy_size % 4 == 0)
@@ -303,16 +330,68 @@ void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStre
     h->stats.kernel_launches++;
 }
 
-// 2-D stage + outputs, shared by the single- and multi-GPU combine.
-int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* positive, int32_t* negative,
-                        double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st) {
+// K4: neighbourhood gather of the per-cell moments
+void launch_gather(GvomHandle* h, Slot& s, cudaStream_t st) {
+    const int cap = (int)h->cap;
+    const bool r11 = h->p.xy_eigen_dist == 1 && h->p.z_eigen_dist == 1;
+    if (h->variant & VAR_OLD_GATHER) {
+        if (r11)
+            launch(k_gather_metrics<1, 1>, dim3(h->grid_gather), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+        else
+            launch(k_gather_metrics<-1, -1>, dim3(h->grid_gather), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+    } else {
+        if (r11)
+            launch(k_gather_metrics2<1, 1>, dim3(h->grid_gather2), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+        else
+            launch(k_gather_metrics2<-1, -1>, dim3(h->grid_gather2), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+    }
+}
+
+// C2: per-cell record merge + eigenvalues
+void launch_cells(GvomHandle* h, const MergeArgs& A, Combined& c, cudaStream_t st) {
+    if (h->variant & VAR_OLD_CELLS)
+        launch(k_merge_cells, dim3(h->grid_cells), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
+                                                      h->dp, (int)h->ccap);
+    else
+        launch(k_merge_cells2, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
+                                                       h->dp, (int)h->ccap);
+}
+
+// Completes the outputs of the last combine on the host: waits for the stream, copies pageable outputs out of
+// the pinned mirror, publishes the cell count.  No-op when nothing is pending.
+int finish_outputs(GvomHandle* h) {
+    GvomHandle::Pending& pd = h->pend;
+    if (!pd.active) return GVOM_OK;
+    pd.active = false;
+    CUDA_TRY(cudaStreamSynchronize(pd.st));
+    const size_t S2 = (size_t)h->S2;
+    if (pd.from_mirror) {
+        const size_t bi = S2 * sizeof(int), bd = S2 * sizeof(double);
+        const size_t rough_off = ((3 * S2 + 1) & ~size_t(1)) * sizeof(int);
+        if (pd.positive) memcpy(pd.positive, h->out_i_host, bi);
+        if (pd.negative) memcpy(pd.negative, h->out_i_host + S2, bi);
+        if (pd.visibility) memcpy(pd.visibility, h->out_i_host + 2 * S2, bi);
+        if (pd.roughness) memcpy(pd.roughness, reinterpret_cast<char*>(h->out_i_host) + rough_off, bd);
+    }
+    Combined& c = *pd.c;
+    c.cells = std::min<int64_t>(h->counters_host[0], h->ccap);
+    h->stats.combined_cells = c.cells;
+    if (h->counters_host[0] > h->ccap)
+        return fail(GVOM_ECAPACITY, "combined map has more occupied cells than max_combined_cells");
+    return GVOM_OK;
+}
+
+// 2-D stage + outputs, shared by the single- and multi-GPU combine.  Everything is enqueued on `st`;
+// finish_outputs() completes it (the synchronous entry points call it right away).
+int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* positive, int32_t* negative,
+                            double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st) {
     const int S2 = h->S2;
     double* height = h->maps; double* inferred = h->maps + S2; double* rough = h->rough_out;
     double* xs = h->maps + 3 * (size_t)S2; double* ys = h->maps + 4 * (size_t)S2; double* guessed = h->maps + 5 * (size_t)S2;
     int* pos = h->imaps; int* neg = h->imaps + S2; int* vis = h->imaps + 2 * (size_t)S2;
-    // device-resident outputs: the surface kernel writes straight into the caller's buffers
+    // device-resident outputs: the surface kernel writes them itself, next to the library's own result block
+    // (which the debug exports and the OccupancyGrid post-processing read)
     const bool direct_dev = out_mem == GVOM_DEVICE && positive && negative && roughness && visibility;
-    if (direct_dev) { pos = positive; neg = negative; vis = visibility; rough = roughness; }
     const int W = (h->p.xy_size + 31) / 32;
     unsigned* known = h->known; unsigned* knownT = h->known + (size_t)h->p.xy_size * W;
     launch(k_column_maps, dim3(W, W), dim3(1024), 0, st, c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
@@ -320,33 +399,46 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
                                                h->flags + 1, c.counter);
     const size_t mask_bytes = 2 * (size_t)h->p.xy_size * W * sizeof(unsigned);
     const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
-    launch(k_surface_maps, dim3(blocks_for(S2, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit, c.total, height, inferred, known, knownT,
-                                                                            c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
-                                                                            in_smem, h->col_minz, h->flags + 1);
+    if (h->variant & VAR_OLD_SURFACE) {
+        launch(k_surface_maps, dim3(blocks_for(S2, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit, c.total, height, inferred, known, knownT,
+                                                                                c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
+                                                                                in_smem, h->col_minz, h->flags + 1);
+        if (direct_dev) {
+            const size_t bi = (size_t)S2 * sizeof(int);
+            CUDA_TRY(cudaMemcpyAsync(positive, pos, bi, cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(negative, neg, bi, cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(visibility, vis, bi, cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(roughness, rough, (size_t)S2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+    } else {
+        launch(k_surface_maps2, dim3(blocks_for(S2, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit, c.total, height, inferred, known, knownT,
+                                                                                 c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
+                                                                                 in_smem, h->col_minz, h->flags + 1,
+                                                                                 direct_dev ? positive : nullptr, direct_dev ? negative : nullptr,
+                                                                                 direct_dev ? visibility : nullptr, direct_dev ? roughness : nullptr);
+    }
     h->stats.kernel_launches += 2;
     rec(h, EV_MAPS, st);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h->counters_host, c.counter, sizeof(int), cudaMemcpyDeviceToHost, st));
     const size_t bi = (size_t)S2 * sizeof(int), bd = (size_t)S2 * sizeof(double);
-    if (direct_dev) {
-        // keep the library's own copy of the roughness map current for the debug exports
-        CUDA_TRY(cudaMemcpyAsync(h->rough_out, roughness, (size_t)S2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        rec(h, EV_D2H, st);
-        CUDA_TRY(cudaStreamSynchronize(st));
+    GvomHandle::Pending& pd = h->pend;
+    pd = GvomHandle::Pending{};
+    pd.active = true; pd.c = &c; pd.st = st;
+    if (direct_dev || out_mem == GVOM_NONE) {
+        // nothing to move
     } else if (out_mem == GVOM_DEVICE) {
         if (positive) CUDA_TRY(cudaMemcpyAsync(positive, pos, bi, cudaMemcpyDeviceToDevice, st));
         if (negative) CUDA_TRY(cudaMemcpyAsync(negative, neg, bi, cudaMemcpyDeviceToDevice, st));
         if (visibility) CUDA_TRY(cudaMemcpyAsync(visibility, vis, bi, cudaMemcpyDeviceToDevice, st));
         if (roughness) CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToDevice, st));
-        rec(h, EV_D2H, st);
-        CUDA_TRY(cudaStreamSynchronize(st));
     } else {
         bool dev = false;
         const bool direct = positive && negative && visibility && roughness && is_pinned_or_device(positive, &dev) &&
                             is_pinned_or_device(negative, &dev) && is_pinned_or_device(visibility, &dev) &&
                             is_pinned_or_device(roughness, &dev);
+        const size_t rough_off = ((3 * (size_t)S2 + 1) & ~size_t(1)) * sizeof(int);
         if (direct) {                      // caller's buffers are pinned: DMA straight into them
-            const size_t rough_off = ((3 * (size_t)S2 + 1) & ~size_t(1)) * sizeof(int);
             if (negative == positive + S2 && visibility == negative + S2 &&
                 reinterpret_cast<char*>(roughness) == reinterpret_cast<char*>(positive) + rough_off) {
                 // laid out like the device result block: one transfer for all four maps
@@ -357,23 +449,13 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
                 CUDA_TRY(cudaMemcpyAsync(visibility, vis, bi, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToHost, st));
             }
-            rec(h, EV_D2H, st);
-            CUDA_TRY(cudaStreamSynchronize(st));
-        } else {                           // pageable: one DMA per dtype into pinned staging, then memcpy
-            const size_t rough_off = ((3 * (size_t)S2 + 1) & ~size_t(1)) * sizeof(int);
+        } else {                           // pageable: one DMA into the pinned mirror, memcpy when it has landed
             CUDA_TRY(cudaMemcpyAsync(h->out_i_host, h->imaps, rough_off + bd, cudaMemcpyDeviceToHost, st));
-            rec(h, EV_D2H, st);
-            CUDA_TRY(cudaStreamSynchronize(st));
-            if (positive) memcpy(positive, h->out_i_host, bi);
-            if (negative) memcpy(negative, h->out_i_host + S2, bi);
-            if (visibility) memcpy(visibility, h->out_i_host + 2 * (size_t)S2, bi);
-            if (roughness) memcpy(roughness, reinterpret_cast<char*>(h->out_i_host) + rough_off, bd);
+            pd.from_mirror = true;
+            pd.positive = positive; pd.negative = negative; pd.visibility = visibility; pd.roughness = roughness;
         }
     }
-    c.cells = std::min<int64_t>(h->counters_host[0], h->ccap);
-    if (h->counters_host[0] > h->ccap)
-        return fail(GVOM_ECAPACITY, "combined map has more occupied cells than max_combined_cells");
-    h->stats.combined_cells = c.cells;
+    rec(h, EV_D2H, st);
     h->have_maps = true;
     if (origin) {                          // gvom.py:385-388
         origin[0] = c.origin[0] * h->p.xy_resolution;
@@ -381,6 +463,12 @@ int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* p
         origin[2] = c.origin[2] * h->p.z_resolution;
     }
     return GVOM_OK;
+}
+
+int run_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* positive, int32_t* negative,
+                        double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st) {
+    if (int e = enqueue_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st)) return e;
+    return finish_outputs(h);
 }
 
 }  // namespace
@@ -430,6 +518,12 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
                            : s4 ? resident_grid(k_merge_codes<4, MERGE_FINISH>, 256, h->sm_count)
                                 : resident_grid(k_merge_codes<1, MERGE_FINISH>, 256, h->sm_count);
         h->grid_cells = resident_grid(k_merge_cells, 128, h->sm_count);
+        h->grid_cells2 = resident_grid(k_merge_cells2, 128, h->sm_count);
+        h->grid_gather2 = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics2<1, 1>, 256, h->sm_count)
+                                                                          : resident_grid(k_gather_metrics2<-1, -1>, 256, h->sm_count);
+        if (const char* m = getenv("GVOM_VARIANT")) h->variant = (unsigned)strtoul(m, nullptr, 0);
+        h->grid_rows3 = resident_grid(k_merge_rows<3>, 256, h->sm_count);
+        h->grid_rows6 = resident_grid(k_merge_rows<6>, 256, h->sm_count);
         h->grid_gather = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics<1, 1>, 256, h->sm_count)
                                                                          : resident_grid(k_gather_metrics<-1, -1>, 256, h->sm_count);
     }
@@ -438,6 +532,12 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
     if (e == cudaSuccess) e = cudaMemsetAsync(h->total_grid, 0, sizeof(int) * (size_t)h->V, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->flags, 0, sizeof(int) * 8, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->col_minz, 0x7f, sizeof(int) * 2 * (size_t)h->S2, h->stream);
+    // both combined-map buffers start as "all unknown" with an empty group mask (k_merge_rows relies on map and
+    // mask of its destination being consistent)
+    for (auto& c : h->comb) {
+        if (e == cudaSuccess) e = cudaMemsetAsync(c.index_map, 0xff, sizeof(int) * (size_t)h->V, h->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c.gmask, 0, sizeof(unsigned) * ((size_t)h->V / 256 + 2), h->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
         delete h;
@@ -464,16 +564,17 @@ int gvom_destroy(GvomHandle* h) {
     return GVOM_OK;
 }
 
-int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_t stride, int32_t dtype,
-                            int32_t mem, const double ego[3], const double* T, void* stream) {
-    if (!h || !ego) return fail(GVOM_EINVAL, "NULL handle or ego");
-    if (n < 0 || n > h->max_points) return fail(GVOM_ECAPACITY, "point count exceeds max_points");
-    if (stride < 3 || stride > 4) return fail(GVOM_EINVAL, "stride must be 3 or 4 elements");
-    if (dtype != GVOM_F32 && dtype != GVOM_F64) return fail(GVOM_EINVAL, "dtype must be GVOM_F32 or GVOM_F64");
-    if (n > 0 && !points) return fail(GVOM_EINVAL, "NULL points");
-    std::lock_guard<std::mutex> lock(h->mu);
-    CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+// One scan, handle locked.  pc2 = PointCloud2 wire records (point_step / offsets) instead of an array of
+// `stride` elements of `dtype`.
+struct CloudDesc {
+    const void* points; int64_t n; int32_t stride, dtype, mem;
+    bool pc2; int32_t point_step, ox, oy, oz;
+};
+
+static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3], const double* T, cudaStream_t st) {
+    const int64_t n = cd.n;
+    const int32_t stride = cd.pc2 ? 3 : cd.stride, dtype = cd.pc2 ? GVOM_F64 : cd.dtype, mem = cd.mem;
+    const void* points = cd.points;
     h->active = st;
     const GvomParams& p = h->p;
 
@@ -513,8 +614,65 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
                                                                h->total_grid, (double*)world_out);
         h->stats.kernel_launches++;
     };
+    // PointCloud2 records: the kernel widens the float32 fields and keeps the world points (float64 x 3) in stage_dev
+    auto launch_k1_pc2 = [&](const void* base, int step, int ox, int oy, int oz, int64_t first, int64_t count) {
+        if (count <= 0) return;
+        const char* p0 = static_cast<const char*>(base) + (size_t)first * step;
+        double* wo = reinterpret_cast<double*>(h->stage_dev) + (size_t)first * 3;
+        launch(k_voxelize_raycast_pc2, dim3(blocks_for(count, 256)), dim3(256), 0, st, p0, step, ox, oy, oz, (int)count, tf, fr, h->dp,
+                                                               h->hit_grid, h->total_grid, wo);
+        h->stats.kernel_launches++;
+    };
+    auto ensure_pool = [&]() {
+        if (!h->pool) {
+            int helpers = 3;
+            if (const char* e = getenv("GVOM_COPY_THREADS")) helpers = std::max(0, atoi(e) - 1);
+            h->pool = new CopyPool(helpers);
+        }
+    };
     bool wait_for_input = false;
-    if (n > 0 && mem == GVOM_DEVICE) {
+    bool pc2_done = false;
+    if (cd.pc2 && n > 0) {
+        if (mem == GVOM_DEVICE) {
+            rec(h, EV_H2D, st);
+            launch_k1_pc2(points, cd.point_step, cd.ox, cd.oy, cd.oz, 0, n);
+            pc2_done = true;
+        } else {
+            if (h->stage_busy) CUDA_TRY(cudaEventSynchronize(h->ev_stage));   // stage_host still being read
+            void* mapped = nullptr;
+            if (h->zero_copy && cudaHostGetDevicePointer(&mapped, h->stage_host, 0) != cudaSuccess) { cudaGetLastError(); mapped = nullptr; }
+            if (mapped && ((uintptr_t)mapped & 15)) mapped = nullptr;
+            ensure_pool();
+            const auto t0 = std::chrono::steady_clock::now();
+            if (mapped) {
+                // field extraction (threaded, non-temporal) into packed 16-byte records, pipelined chunk by chunk
+                // with the zero-copy ray-cast that streams them over PCIe
+                rec(h, EV_H2D, st);
+                const int nchunks = n >= 131072 ? 4 : 1;
+                const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~int64_t(255);
+                for (int c = 0; c < nchunks; ++c) {
+                    const int64_t first = c * per, count = std::min<int64_t>(per, n - first);
+                    if (count <= 0) break;
+                    h->pool->extract_xyz(h->stage_host + (size_t)first * 16, static_cast<const char*>(points) + (size_t)first * cd.point_step,
+                                         count, cd.point_step, cd.ox, cd.oy, cd.oz, false);
+                    launch_k1_pc2(mapped, 16, 0, 4, 8, first, count);
+                }
+                CUDA_TRY(cudaEventRecord(h->ev_stage, st));
+                h->stage_busy = true;
+                pc2_done = true;
+            } else {
+                // no mapped access: widen to float64 x 3 in the staging block and take the array path below
+                h->pool->extract_xyz(h->stage_host, static_cast<const char*>(points), n, cd.point_step, cd.ox, cd.oy, cd.oz, true);
+                points = h->stage_host;
+                src = points;
+            }
+            h->last_stage_copy_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (pc2_done) { tf_moments.enabled = 0; src = h->stage_dev; }
+    }
+    if (pc2_done) {
+        // K1 launched above
+    } else if (n > 0 && mem == GVOM_DEVICE) {
         if (stride == 4 && ((uintptr_t)points & 15)) {   // vector loads need 16-byte alignment
             CUDA_TRY(cudaMemcpyAsync(h->stage_dev, points, (size_t)n * row, cudaMemcpyDeviceToDevice, st));
             src = h->stage_dev;
@@ -523,7 +681,8 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
         launch_k1(src, 0, n, nullptr);
     } else if (n > 0) {
         bool dev = false;
-        const bool pinned = is_pinned_or_device(points, &dev);
+        const bool staged = points == h->stage_host;     // PointCloud2 fallback: already in the pinned staging block
+        const bool pinned = staged || is_pinned_or_device(points, &dev);
         if (!pinned && h->stage_busy) CUDA_TRY(cudaEventSynchronize(h->ev_stage));   // stage_host still being read
         void* mapped = nullptr;
         if (h->zero_copy) {
@@ -538,11 +697,7 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
                 launch_k1(mapped, 0, n, h->stage_dev);
             } else {
                 // pageable: the staging copy (threaded, non-temporal) is pipelined with the kernel chunk by chunk
-                if (!h->pool) {
-                    int helpers = 3;
-                    if (const char* e = getenv("GVOM_COPY_THREADS")) helpers = std::max(0, atoi(e) - 1);
-                    h->pool = new CopyPool(helpers);
-                }
+                ensure_pool();
                 const auto t0 = std::chrono::steady_clock::now();
                 const int nchunks = n >= 131072 ? 4 : 1;
                 const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~int64_t(255);
@@ -577,8 +732,8 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
             CUDA_TRY(cudaEventRecord(h->ev_stage, h->copy_stream));
             rec(h, EV_H2D, st);
         }
-        h->stage_busy = !pinned;
-        wait_for_input = pinned;                         // the caller may reuse its buffer when we return
+        h->stage_busy = !pinned || staged;
+        wait_for_input = pinned && !staged;              // the caller may reuse its buffer when we return
         src = h->stage_dev;
     } else {
         rec(h, EV_H2D, st);
@@ -613,10 +768,7 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
         h->stats.kernel_launches++;
     }
     rec(h, EV_MOMENTS, st);
-    if (h->p.xy_eigen_dist == 1 && h->p.z_eigen_dist == 1)
-        launch(k_gather_metrics<1, 1>, dim3(h->grid_gather), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
-    else
-        launch(k_gather_metrics<-1, -1>, dim3(h->grid_gather), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+    launch_gather(h, s, st);
     h->stats.kernel_launches++;
     rec(h, EV_GATHER, st);
     CUDA_TRY(cudaGetLastError());
@@ -633,14 +785,44 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
     return GVOM_OK;
 }
 
-int gvom_combine_maps(GvomHandle* h, double origin[3], int32_t* positive, int32_t* negative, double* roughness,
-                      int32_t* visibility, int32_t out_mem, void* stream) {
-    if (!h) return fail(GVOM_EINVAL, "NULL handle");
+int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_t stride, int32_t dtype,
+                            int32_t mem, const double ego[3], const double* T, void* stream) {
+    if (!h || !ego) return fail(GVOM_EINVAL, "NULL handle or ego");
+    if (n < 0 || n > h->max_points) return fail(GVOM_ECAPACITY, "point count exceeds max_points");
+    if (stride < 3 || stride > 4) return fail(GVOM_EINVAL, "stride must be 3 or 4 elements");
+    if (dtype != GVOM_F32 && dtype != GVOM_F64) return fail(GVOM_EINVAL, "dtype must be GVOM_F32 or GVOM_F64");
+    if (mem != GVOM_HOST && mem != GVOM_DEVICE) return fail(GVOM_EINVAL, "bad mem");
+    if (n > 0 && !points) return fail(GVOM_EINVAL, "NULL points");
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
+    const CloudDesc cd{points, n, stride, dtype, mem, false, 0, 0, 0, 0};
+    return process_locked(h, cd, ego, T, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int gvom_process_pointcloud2(GvomHandle* h, const void* data, int64_t n, int32_t point_step, int32_t off_x,
+                             int32_t off_y, int32_t off_z, int32_t mem, const double ego[3], const double* T,
+                             void* stream) {
+    if (!h || !ego) return fail(GVOM_EINVAL, "NULL handle or ego");
+    if (n < 0 || n > h->max_points) return fail(GVOM_ECAPACITY, "point count exceeds max_points");
+    if (point_step < 12 || point_step > 65536 || (point_step & 3)) return fail(GVOM_EINVAL, "point_step must be a multiple of 4, >= 12");
+    const int32_t offs[3] = {off_x, off_y, off_z};
+    for (int k = 0; k < 3; ++k)
+        if (offs[k] < 0 || offs[k] + 4 > point_step || (offs[k] & 3)) return fail(GVOM_EINVAL, "field offsets must be multiples of 4 inside the record");
+    if (mem != GVOM_HOST && mem != GVOM_DEVICE) return fail(GVOM_EINVAL, "bad mem");
+    if (n > 0 && !data) return fail(GVOM_EINVAL, "NULL data");
+    if (mem == GVOM_DEVICE && ((uintptr_t)data & 3)) return fail(GVOM_EINVAL, "device payload must be 4-byte aligned");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const CloudDesc cd{data, n, 3, GVOM_F64, mem, true, point_step, off_x, off_y, off_z};
+    return process_locked(h, cd, ego, T, stream ? (cudaStream_t)stream : h->stream);
+}
+
+// combine_maps with the handle locked: merge, 2-D stage, outputs enqueued; completed unless `async`
+static int combine_locked(GvomHandle* h, double origin[3], int32_t* positive, int32_t* negative, double* roughness,
+                          int32_t* visibility, int32_t out_mem, cudaStream_t st, bool async) {
+    if (int e = finish_outputs(h)) return e;                // a pending asynchronous combine owns the pinned mirrors
     Slot& newest = h->slots[h->last_buffer_index];
     if (!newest.valid) return GVOM_NO_DATA;                 // gvom.py:225-227
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->active = st;
     rec(h, EV_CSTART, st);
     MergeArgs A;
@@ -656,23 +838,105 @@ int gvom_combine_maps(GvomHandle* h, double origin[3], int32_t* positive, int32_
         launch_merge<MERGE_FULL>(h, A, O, st);
     }
     rec(h, EV_CODES, st);
-    launch(k_merge_cells, dim3(h->grid_cells), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
-                                                  h->dp, (int)h->ccap);
+    launch_cells(h, A, c, st);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 1;
     h->prof_combine = h->profiling;
     c.has_gmask = h->p.xy_size % 8 == 0;
-    const int r = run_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st);
-    if (r != GVOM_OK) return r;
+    if (int e = enqueue_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st)) return e;
+    if (!async)
+        if (int e = finish_outputs(h)) return e;
     c.valid = true;                                          // gvom.py:302-308
     h->cur = 1 - h->cur;
     h->stats.combine_calls++;
     return GVOM_OK;
 }
 
+int gvom_combine_maps(GvomHandle* h, double origin[3], int32_t* positive, int32_t* negative, double* roughness,
+                      int32_t* visibility, int32_t out_mem, void* stream) {
+    if (!h) return fail(GVOM_EINVAL, "NULL handle");
+    if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE && out_mem != GVOM_NONE) return fail(GVOM_EINVAL, "bad out_mem");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    return combine_locked(h, origin, positive, negative, roughness, visibility, out_mem,
+                          stream ? (cudaStream_t)stream : h->stream, false);
+}
+
+int gvom_combine_maps_async(GvomHandle* h, double origin[3], int32_t* positive, int32_t* negative, double* roughness,
+                            int32_t* visibility, int32_t out_mem, void* stream) {
+    if (!h) return fail(GVOM_EINVAL, "NULL handle");
+    if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE && out_mem != GVOM_NONE) return fail(GVOM_EINVAL, "bad out_mem");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    return combine_locked(h, origin, positive, negative, roughness, visibility, out_mem,
+                          stream ? (cudaStream_t)stream : h->stream, true);
+}
+
+int gvom_combine_wait(GvomHandle* h) {
+    if (!h) return fail(GVOM_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    return finish_outputs(h);
+}
+
+// OccupancyGrid payloads from the library's result block (handle locked)
+static int grids_locked(GvomHandle* h, double thr, double minr, double maxr, int8_t* out, int32_t out_mem, cudaStream_t st) {
+    if (!h->have_maps || !h->comb[h->cur].valid) return GVOM_NO_DATA;
+    const int S = h->p.xy_size;
+    const size_t S2 = (size_t)h->S2, bytes = GVOM_GRID_COUNT * S2;
+    const int* pos = h->imaps;
+    signed char* dst = (out_mem == GVOM_DEVICE) ? reinterpret_cast<signed char*>(out) : h->grids_dev;
+    const int T = (S + 31) / 32;
+    launch(k_occupancy_grids, dim3(T, T), dim3(256), 0, st, pos, pos + S2, pos + 2 * S2, (const double*)h->rough_out, S, thr, minr, maxr, dst);
+    h->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (out_mem == GVOM_DEVICE) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return GVOM_OK;
+    }
+    bool dev = false;
+    if (is_pinned_or_device(out, &dev) && !dev) {           // pinned: straight into the caller's block
+        CUDA_TRY(cudaMemcpyAsync(out, h->grids_dev, bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(h->grids_host, h->grids_dev, bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        memcpy(out, h->grids_host, bytes);
+    }
+    return GVOM_OK;
+}
+
+int gvom_occupancy_grids(GvomHandle* h, double density_threshold, double min_roughness, double max_roughness,
+                         int8_t* out, int32_t out_mem, void* stream) {
+    if (!h || !out) return fail(GVOM_EINVAL, "NULL argument");
+    if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE) return fail(GVOM_EINVAL, "bad out_mem");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (int e = finish_outputs(h)) return e;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->active;
+    return grids_locked(h, density_threshold, min_roughness, max_roughness, out, out_mem, st);
+}
+
+int gvom_combine_maps_grids(GvomHandle* h, double origin[3], double density_threshold, double min_roughness,
+                            double max_roughness, int8_t* out, int32_t out_mem, void* stream) {
+    if (!h || !out) return fail(GVOM_EINVAL, "NULL argument");
+    if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE) return fail(GVOM_EINVAL, "bad out_mem");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    // the maps stay on the device (GVOM_NONE); the int8 grids are the only D2H traffic of the tick
+    const int r = combine_locked(h, origin, nullptr, nullptr, nullptr, nullptr, GVOM_NONE, st, true);
+    if (r != GVOM_OK) return r;
+    const int g = grids_locked(h, density_threshold, min_roughness, max_roughness, out, out_mem, st);
+    const int f = finish_outputs(h);                        // stream already drained: publishes the cell count
+    return g != GVOM_OK ? g : f;
+}
+
 int gvom_combined_cell_count(GvomHandle* h, int64_t* cells) {
     if (!h || !cells) return fail(GVOM_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lock(h->mu);
+    cudaSetDevice(h->device);
+    if (int e = finish_outputs(h)) return e;
     if (!h->comb[h->cur].valid) return GVOM_NO_DATA;
     *cells = h->comb[h->cur].cells;
     return GVOM_OK;
@@ -682,6 +946,7 @@ int gvom_debug_voxel_map(GvomHandle* h, float* out, int64_t capacity_rows, int64
     if (!h || !out) return fail(GVOM_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
+    if (int e = finish_outputs(h)) return e;
     Combined& c = h->comb[h->cur];
     if (!c.valid) return GVOM_NO_DATA;
     if (capacity_rows < c.cells) return fail(GVOM_ECAPACITY, "output has fewer rows than combined cells");
@@ -699,6 +964,7 @@ int gvom_debug_voxel_map(GvomHandle* h, float* out, int64_t capacity_rows, int64
 static int debug_height_common(GvomHandle* h, float* out7, float* out3) {
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
+    if (int e = finish_outputs(h)) return e;
     Combined& c = h->comb[h->cur];
     if (!c.valid || !h->have_maps) return GVOM_NO_DATA;
     const size_t S2 = (size_t)h->S2;
@@ -768,6 +1034,7 @@ int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_
     if (!h) return fail(GVOM_EINVAL, "NULL handle");
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
+    if (int e = finish_outputs(h)) return e;
     Combined& c = h->comb[h->cur];
     if (!c.valid) return GVOM_NO_DATA;
     CUDA_TRY(cudaStreamSynchronize(h->active));
@@ -788,6 +1055,7 @@ int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_
 
 int gvom_get_stats(GvomHandle* h, GvomStats* out) {
     if (!h || !out) return fail(GVOM_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(h->mu);
     *out = h->stats;
     return GVOM_OK;
 }
@@ -822,6 +1090,179 @@ int gvom_stage_times(GvomHandle* h, float ms[16]) {
         const int b[4] = {EV_CODES, EV_CELLS, EV_MAPS, EV_D2H};
         for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[5 + i], h->ev[a[i]], h->ev[b[i]]));
     }
+    return GVOM_OK;
+}
+
+int gvom_set_variant(GvomHandle* h, uint32_t mask) {
+    if (!h) return fail(GVOM_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->variant = mask;
+    return GVOM_OK;
+}
+
+// ------------------------------------------------------------- state save / restore
+}  // extern "C"
+namespace {
+
+struct StateHeader {
+    char magic[8];                 // "GVOMST01"
+    GvomParams p;
+    int64_t max_points, cap, ccap, V;
+    int32_t buffer_index, last_buffer_index, have_maps, comb_valid;
+    double ego[3];
+    double comb_origin[3];
+    int64_t comb_cells;
+    int64_t slot_cells[MAX_SLOTS];
+    int32_t slot_valid[MAX_SLOTS];
+    double slot_origin[MAX_SLOTS][3];
+};
+
+// sections of the blob after the header, in order; `visit(device_ptr, bytes)` is called for each
+template <typename F>
+void state_sections(GvomHandle* h, const StateHeader& H, F&& visit) {
+    const size_t V = (size_t)h->V, S2 = (size_t)h->S2, gm = V / 256 + 2;
+    for (int i = 0; i < h->p.buffer_size; ++i) {
+        if (!H.slot_valid[i]) continue;
+        Slot& s = h->slots[i];
+        const size_t n = (size_t)H.slot_cells[i];
+        visit(s.index_map, V * sizeof(int)); visit(s.gmask, gm * sizeof(unsigned));
+        visit(s.hit, n * sizeof(int)); visit(s.total, n * sizeof(int)); visit(s.metrics, n * 10 * sizeof(double));
+        visit(s.minh, n * sizeof(float)); visit(s.cell_voxel, n * sizeof(int)); visit(s.counter, sizeof(int));
+    }
+    if (H.comb_valid) {
+        Combined& c = h->comb[h->cur];
+        const size_t n = (size_t)H.comb_cells;
+        visit(c.index_map, V * sizeof(int)); visit(c.gmask, gm * sizeof(unsigned));
+        visit(c.hit, n * sizeof(int)); visit(c.total, n * sizeof(int)); visit(c.minh, n * sizeof(float));
+        visit(c.metrics, n * 10 * sizeof(float)); visit(c.eig, n * 3 * sizeof(float)); visit(c.cell_voxel, n * sizeof(int));
+        visit(c.counter, sizeof(int));
+    }
+    if (H.have_maps) {
+        visit(h->maps, 6 * S2 * sizeof(double));
+        visit(h->imaps, (3 * S2 + 2 * S2 + 2) * sizeof(int));
+    }
+}
+
+int fill_state_header(GvomHandle* h, StateHeader* H) {
+    if (int e = finish_outputs(h)) return e;
+    CUDA_TRY(cudaStreamSynchronize(h->active));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    memset(H, 0, sizeof(*H));
+    memcpy(H->magic, "GVOMST01", 8);
+    H->p = h->p; H->max_points = h->max_points; H->cap = h->cap; H->ccap = h->ccap; H->V = h->V;
+    H->buffer_index = h->buffer_index; H->last_buffer_index = h->last_buffer_index;
+    H->have_maps = h->have_maps ? 1 : 0;
+    for (int k = 0; k < 3; ++k) H->ego[k] = h->ego[k];
+    for (int i = 0; i < h->p.buffer_size; ++i) {
+        Slot& s = h->slots[i];
+        H->slot_valid[i] = s.valid ? 1 : 0;
+        if (!s.valid) continue;
+        int cnt = 0;
+        CUDA_TRY(cudaMemcpy(&cnt, s.counter, sizeof(int), cudaMemcpyDeviceToHost));
+        H->slot_cells[i] = std::min<int64_t>(cnt, h->cap);
+        for (int k = 0; k < 3; ++k) H->slot_origin[i][k] = s.origin[k];
+    }
+    Combined& c = h->comb[h->cur];
+    H->comb_valid = c.valid ? 1 : 0;
+    if (c.valid) {
+        H->comb_cells = c.cells;
+        for (int k = 0; k < 3; ++k) H->comb_origin[k] = c.origin[k];
+    }
+    return GVOM_OK;
+}
+
+}  // namespace
+extern "C" {
+
+int gvom_state_size(GvomHandle* h, size_t* bytes) {
+    if (!h || !bytes) return fail(GVOM_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    StateHeader H;
+    if (int e = fill_state_header(h, &H)) return e;
+    size_t total = sizeof(StateHeader);
+    state_sections(h, H, [&](void*, size_t b) { total += (b + 15) & ~size_t(15); });
+    *bytes = total;
+    return GVOM_OK;
+}
+
+int gvom_save_state(GvomHandle* h, void* blob, size_t capacity, size_t* written) {
+    if (!h || !blob) return fail(GVOM_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    StateHeader H;
+    if (int e = fill_state_header(h, &H)) return e;
+    size_t total = sizeof(StateHeader);
+    state_sections(h, H, [&](void*, size_t b) { total += (b + 15) & ~size_t(15); });
+    if (total > capacity) return fail(GVOM_ECAPACITY, "state blob larger than the buffer (ask gvom_state_size)");
+    char* out = static_cast<char*>(blob);
+    memcpy(out, &H, sizeof(H));
+    size_t off = sizeof(StateHeader);
+    cudaError_t err = cudaSuccess;
+    state_sections(h, H, [&](void* d, size_t b) {
+        if (b && err == cudaSuccess) err = cudaMemcpy(out + off, d, b, cudaMemcpyDeviceToHost);
+        off += (b + 15) & ~size_t(15);
+    });
+    if (err != cudaSuccess) return fail(GVOM_ECUDA, std::string("gvom_save_state: ") + cudaGetErrorString(err));
+    if (written) *written = total;
+    return GVOM_OK;
+}
+
+int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes) {
+    if (!h || !blob) return fail(GVOM_EINVAL, "NULL argument");
+    if (bytes < sizeof(StateHeader)) return fail(GVOM_EINVAL, "state blob too small");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    StateHeader H;
+    memcpy(&H, blob, sizeof(H));
+    if (memcmp(H.magic, "GVOMST01", 8) != 0) return fail(GVOM_EINVAL, "not a gvom_b200 state blob");
+    if (memcmp(&H.p, &h->p, sizeof(GvomParams)) != 0 || H.max_points != h->max_points || H.ccap != h->ccap || H.V != h->V)
+        return fail(GVOM_EINVAL, "state blob was saved with different parameters / capacities");
+    if (int e = finish_outputs(h)) return e;
+    CUDA_TRY(cudaStreamSynchronize(h->active));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < h->p.buffer_size; ++i) {
+        if (H.slot_valid[i] && (H.slot_cells[i] < 0 || H.slot_cells[i] > h->cap)) return fail(GVOM_EINVAL, "corrupt state blob (slot cells)");
+    }
+    if (H.comb_valid && (H.comb_cells < 0 || H.comb_cells > h->ccap)) return fail(GVOM_EINVAL, "corrupt state blob (combined cells)");
+    // host state first: state_sections() walks the buffers the header describes
+    h->buffer_index = H.buffer_index; h->last_buffer_index = H.last_buffer_index;
+    h->have_maps = H.have_maps != 0;
+    for (int k = 0; k < 3; ++k) h->ego[k] = H.ego[k];
+    for (int i = 0; i < h->p.buffer_size; ++i) {
+        Slot& s = h->slots[i];
+        s.valid = H.slot_valid[i] != 0;
+        s.has_gmask = s.valid && (h->p.xy_size % 8 == 0);
+        for (int k = 0; k < 3; ++k) s.origin[k] = H.slot_origin[i][k];
+    }
+    h->cur = 0;
+    Combined& c = h->comb[0];
+    c.valid = H.comb_valid != 0; c.cells = H.comb_cells; c.has_gmask = c.valid && (h->p.xy_size % 8 == 0);
+    for (int k = 0; k < 3; ++k) c.origin[k] = H.comb_origin[k];
+    h->comb[1].valid = false; h->comb[1].cells = 0;
+    h->stats.combined_cells = c.cells;
+    size_t total = sizeof(StateHeader);
+    state_sections(h, H, [&](void*, size_t b) { total += (b + 15) & ~size_t(15); });
+    if (total > bytes) return fail(GVOM_EINVAL, "state blob truncated");
+    const char* in = static_cast<const char*>(blob);
+    size_t off = sizeof(StateHeader);
+    cudaError_t err = cudaSuccess;
+    state_sections(h, H, [&](void* d, size_t b) {
+        if (b && err == cudaSuccess) err = cudaMemcpy(d, in + off, b, cudaMemcpyHostToDevice);
+        off += (b + 15) & ~size_t(15);
+    });
+    // buffers the blob does not describe go back to their start-up state
+    for (int q = 0; q < 2 && err == cudaSuccess; ++q) {
+        if (q == 0 && c.valid) continue;
+        err = cudaMemset(h->comb[q].index_map, 0xff, sizeof(int) * (size_t)h->V);
+        if (err == cudaSuccess) err = cudaMemset(h->comb[q].gmask, 0, sizeof(unsigned) * ((size_t)h->V / 256 + 2));
+    }
+    if (err == cudaSuccess) err = cudaMemset(h->hit_grid, 0, sizeof(int) * (size_t)h->V);
+    if (err == cudaSuccess) err = cudaMemset(h->total_grid, 0, sizeof(int) * (size_t)h->V);
+    if (err == cudaSuccess) err = cudaMemset(h->flags, 0, sizeof(int) * 8);
+    if (err == cudaSuccess) err = cudaMemset(h->col_minz, 0x7f, sizeof(int) * 2 * (size_t)h->S2);
+    if (err != cudaSuccess) return fail(GVOM_ECUDA, std::string("gvom_load_state: ") + cudaGetErrorString(err));
+    h->stage_busy = false;
     return GVOM_OK;
 }
 
@@ -872,6 +1313,7 @@ int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_gr
     if (record_capacity < 1 || record_capacity > 2147483647LL) return fail(GVOM_EINVAL, "bad record capacity");
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
+    if (int e = finish_outputs(h)) return e;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->active = st;
     rec(h, EV_CSTART, st);
@@ -913,6 +1355,7 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     }
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
+    if (int e = finish_outputs(h)) return e;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->active = st;
     Combined& pc = h->comb[h->cur];
@@ -990,6 +1433,7 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     if (res_capacity < 1 || res_capacity > 2147483647LL) return fail(GVOM_EINVAL, "bad result capacity");
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
+    if (int e = finish_outputs(h)) return e;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->active = st;
     Combined& pc = h->comb[h->cur];

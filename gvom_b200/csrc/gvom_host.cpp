@@ -2,6 +2,7 @@
 #include "gvom_host.h"
 
 #include <emmintrin.h>
+#include <xmmintrin.h>
 
 #include <algorithm>
 #include <condition_variable>
@@ -31,15 +32,48 @@ static void stream_copy(char* dst, const char* src, size_t n) {
     _mm_sfence();
 }
 
+// PointCloud2 records -> packed xyz (see gvom_host.h); dst is 16-byte aligned (pinned staging block)
+static void extract_range(char* dst, const char* src, int64_t first, int64_t last, int step, int ox, int oy, int oz,
+                          bool as_double) {
+    if (!as_double) {
+        for (int64_t i = first; i < last; ++i) {
+            const char* q = src + (size_t)i * step;
+            float x, y, z;
+            memcpy(&x, q + ox, 4); memcpy(&y, q + oy, 4); memcpy(&z, q + oz, 4);
+            _mm_stream_ps(reinterpret_cast<float*>(dst + (size_t)i * 16), _mm_set_ps(0.f, z, y, x));
+        }
+    } else {
+        for (int64_t i = first; i < last; ++i) {
+            const char* q = src + (size_t)i * step;
+            float x, y, z;
+            memcpy(&x, q + ox, 4); memcpy(&y, q + oy, 4); memcpy(&z, q + oz, 4);
+            double* d = reinterpret_cast<double*>(dst + (size_t)i * 24);
+            _mm_stream_si64(reinterpret_cast<long long*>(d), _mm_cvtsi128_si64(_mm_castpd_si128(_mm_set_sd((double)x))));
+            _mm_stream_si64(reinterpret_cast<long long*>(d + 1), _mm_cvtsi128_si64(_mm_castpd_si128(_mm_set_sd((double)y))));
+            _mm_stream_si64(reinterpret_cast<long long*>(d + 2), _mm_cvtsi128_si64(_mm_castpd_si128(_mm_set_sd((double)z))));
+        }
+    }
+    _mm_sfence();
+}
+
 struct CopyPool::Impl {
     std::vector<std::thread> th;
     std::mutex m;
     std::condition_variable cv, done;
     char* dst = nullptr; const char* src = nullptr; size_t bytes = 0;
+    // extraction job (mode 1) instead of a plain copy (mode 0)
+    int mode = 0;
+    int64_t n = 0; int step = 0, ox = 0, oy = 0, oz = 0; bool as_double = false;
     int gen = 0, pending = 0;
     bool stop = false;
 
     void slice(int i, int parts) {
+        if (mode == 1) {
+            const int64_t per = ((n / parts) + 255) & ~int64_t(255);
+            const int64_t a = std::min<int64_t>(n, per * i), b = std::min<int64_t>(n, per * (i + 1));
+            if (b > a) extract_range(dst, src, a, b, step, ox, oy, oz, as_double);
+            return;
+        }
         const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);
         const size_t a = std::min(bytes, per * i), b = std::min(bytes, per * (i + 1));
         if (b > a) stream_copy(dst + a, src + a, b - a);
@@ -51,6 +85,13 @@ struct CopyPool::Impl {
             slice(i, (int)th.size() + 1);
             { std::lock_guard<std::mutex> l(m); if (--pending == 0) done.notify_one(); }
         }
+    }
+    void run(int parts) {       // caller thread takes slice 0
+        { std::lock_guard<std::mutex> l(m); pending = parts - 1; ++gen; }
+        cv.notify_all();
+        slice(0, parts);
+        std::unique_lock<std::mutex> l(m);
+        done.wait(l, [this] { return pending == 0; });
     }
 };
 
@@ -68,9 +109,14 @@ CopyPool::~CopyPool() {
 void CopyPool::copy(char* dst, const char* src, size_t bytes) {
     const int parts = (int)p_->th.size() + 1;
     if (bytes < (1u << 18) || parts == 1) { stream_copy(dst, src, bytes); return; }
-    { std::lock_guard<std::mutex> l(p_->m); p_->dst = dst; p_->src = src; p_->bytes = bytes; p_->pending = parts - 1; ++p_->gen; }
-    p_->cv.notify_all();
-    p_->slice(0, parts);
-    std::unique_lock<std::mutex> l(p_->m);
-    p_->done.wait(l, [this] { return p_->pending == 0; });
+    p_->mode = 0; p_->dst = dst; p_->src = src; p_->bytes = bytes;
+    p_->run(parts);
+}
+
+void CopyPool::extract_xyz(char* dst, const char* src, int64_t n, int point_step, int ox, int oy, int oz, bool as_double) {
+    const int parts = (int)p_->th.size() + 1;
+    if (n < 16384 || parts == 1) { extract_range(dst, src, 0, n, point_step, ox, oy, oz, as_double); return; }
+    p_->mode = 1; p_->dst = dst; p_->src = src; p_->n = n; p_->step = point_step; p_->ox = ox; p_->oy = oy; p_->oz = oz;
+    p_->as_double = as_double;
+    p_->run(parts);
 }

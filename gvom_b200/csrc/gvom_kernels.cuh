@@ -141,45 +141,12 @@ __device__ __forceinline__ bool world_from_raw(T p0, T p1, T p2, const Xform& tf
 //     atomic units.
 //   * aggregation changes who issues the atomic, never the per-ray arithmetic.
 // ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256, 8)
-k_voxelize_raycast(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevParams P,
-                   int* __restrict__ hit, int* __restrict__ total, T* __restrict__ world_out) {
-    pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// per-point part of K1 shared by every input layout: hit + DDA of one world-frame point per lane
+__device__ __forceinline__ void raycast_point(bool ok, double wx, double wy, double wz, const Frame& fr,
+                                              const DevParams& P, int* __restrict__ hit, int* __restrict__ total) {
     const int lane = threadIdx.x & 31;
     const double ox = fr.origin[0], oy = fr.origin[1], oz = fr.origin[2];
     const double dS = (double)P.S, dZ = (double)P.Z;
-
-    double wx = 0, wy = 0, wz = 0;
-    bool ok = false;
-    if (world_out) {
-        // zero-copy mode: pts is pinned HOST memory, read over PCIe exactly once.  The block's
-        // contiguous chunk (256 points) is fetched with 128-bit coalesced loads into shared memory
-        // (every byte requested once, full-width PCIe reads), then each thread picks its point.
-        // The transformed point (in the cloud's dtype, as the reference stores it back,
-        // gvom.py:1136-1138) is kept in HBM for the moment pass.
-        __shared__ uint4 chunk[256 * 4 * sizeof(double) / 16];
-        const long long first = (long long)blockIdx.x * blockDim.x;
-        const int cnt = (int)min((long long)blockDim.x, (long long)n - first);
-        const size_t bytes = (size_t)cnt * stride * sizeof(T);
-        const char* g = reinterpret_cast<const char*>(pts + first * stride);
-        const int n16 = (int)(bytes >> 4);
-        for (int k = threadIdx.x; k < n16; k += blockDim.x)
-            chunk[k] = __ldg(reinterpret_cast<const uint4*>(g) + k);
-        if (threadIdx.x < (int)(bytes & 15))                  // tail bytes (none when the chunk is full)
-            reinterpret_cast<char*>(chunk)[(n16 << 4) + threadIdx.x] = g[(n16 << 4) + threadIdx.x];
-        __syncthreads();
-        if (i < n) {
-            const T* q = reinterpret_cast<const T*>(chunk) + (long long)threadIdx.x * stride;
-            ok = world_from_raw<T>(q[0], q[1], q[2], tf, P.min_d2, wx, wy, wz);
-            T* w = world_out + (long long)i * stride;
-            w[0] = (T)wx; w[1] = (T)wy; w[2] = (T)wz;
-        }
-    } else if (i < n) {
-        ok = load_world<T>(pts, stride, i, tf, P.min_d2, wx, wy, wz);
-    }
-
     // ---- hit (gvom.py:1153-1171)
     double ex = 0, ey = 0, ez = 0;
     bool inb = false;
@@ -264,6 +231,78 @@ k_voxelize_raycast(const T* __restrict__ pts, int stride, int n, Xform tf, Frame
         active = inside && (length < lim);
         any = __ballot_sync(FULL, active);
     }
+}
+
+
+template <typename T>
+__global__ void __launch_bounds__(256, 8)
+k_voxelize_raycast(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevParams P,
+                   int* __restrict__ hit, int* __restrict__ total, T* __restrict__ world_out) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+
+    double wx = 0, wy = 0, wz = 0;
+    bool ok = false;
+    if (world_out) {
+        // zero-copy mode: pts is pinned HOST memory, read over PCIe exactly once.  The block's
+        // contiguous chunk (256 points) is fetched with 128-bit coalesced loads into shared memory
+        // (every byte requested once, full-width PCIe reads), then each thread picks its point.
+        // The transformed point (in the cloud's dtype, as the reference stores it back,
+        // gvom.py:1136-1138) is kept in HBM for the moment pass.
+        __shared__ uint4 chunk[256 * 4 * sizeof(double) / 16];
+        const long long first = (long long)blockIdx.x * blockDim.x;
+        const int cnt = (int)min((long long)blockDim.x, (long long)n - first);
+        const size_t bytes = (size_t)cnt * stride * sizeof(T);
+        const char* g = reinterpret_cast<const char*>(pts + first * stride);
+        const int n16 = (int)(bytes >> 4);
+        for (int k = threadIdx.x; k < n16; k += blockDim.x)
+            chunk[k] = __ldg(reinterpret_cast<const uint4*>(g) + k);
+        if (threadIdx.x < (int)(bytes & 15))                  // tail bytes (none when the chunk is full)
+            reinterpret_cast<char*>(chunk)[(n16 << 4) + threadIdx.x] = g[(n16 << 4) + threadIdx.x];
+        __syncthreads();
+        if (i < n) {
+            const T* q = reinterpret_cast<const T*>(chunk) + (long long)threadIdx.x * stride;
+            ok = world_from_raw<T>(q[0], q[1], q[2], tf, P.min_d2, wx, wy, wz);
+            T* w = world_out + (long long)i * stride;
+            w[0] = (T)wx; w[1] = (T)wy; w[2] = (T)wz;
+        }
+    } else if (i < n) {
+        ok = load_world<T>(pts, stride, i, tf, P.min_d2, wx, wy, wz);
+    }
+
+    raycast_point(ok, wx, wy, wz, fr, P, hit, total);
+}
+
+// K1 for PointCloud2 wire records (sensor_msgs/PointCloud2: n records of point_step bytes, float32 x / y / z
+// at byte offsets ox / oy / oz).  Replaces ros_numpy.point_cloud2.pointcloud2_to_xyz_array + Process_pointcloud
+// (gvom_ros.py:108-109): the float32 fields are widened to float64 (what ros_numpy hands the reference), NaN / Inf
+// points are dropped (ros_numpy's remove_nans), and everything downstream is the float64 path.  The transformed
+// points are kept in HBM (float64 x 3) for the moment pass.  Packed 16-byte records (x, y, z, pad) -- the layout
+// the host-side field extraction produces -- are read with one 128-bit load per point.
+__global__ void __launch_bounds__(256, 8)
+k_voxelize_raycast_pc2(const char* __restrict__ data, int point_step, int offx, int offy, int offz, int n, Xform tf,
+                       Frame fr, DevParams P, int* __restrict__ hit, int* __restrict__ total,
+                       double* __restrict__ world_out) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double wx = 0, wy = 0, wz = 0;
+    bool ok = false;
+    if (i < n) {
+        const char* q = data + (size_t)i * point_step;
+        float x, y, z;
+        if (point_step == 16 && offx == 0 && offy == 4 && offz == 8) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(q));
+            x = v.x; y = v.y; z = v.z;
+        } else {
+            x = __ldg(reinterpret_cast<const float*>(q + offx));
+            y = __ldg(reinterpret_cast<const float*>(q + offy));
+            z = __ldg(reinterpret_cast<const float*>(q + offz));
+        }
+        ok = world_from_raw<double>((double)x, (double)y, (double)z, tf, P.min_d2, wx, wy, wz);
+        double* w = world_out + (long long)i * 3;
+        w[0] = wx; w[1] = wy; w[2] = wz;
+    }
+    raycast_point(ok, wx, wy, wz, fr, P, hit, total);
 }
 
 // ---------------------------------------------------------------------------
@@ -533,6 +572,85 @@ k_gather_metrics(const int* __restrict__ index_map, const int* __restrict__ cell
         }
 #pragma unroll
         for (int off = LPC / 2; off > 0; off >>= 1)
+#pragma unroll
+            for (int k = 0; k < 10; ++k) r[k] += __shfl_xor_sync(FULL, r[k], off);
+        if (sub == 0 && id < count) {
+            const double* e = acc + (long long)id * ACC + 10;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) r[k] += e[k];
+            const double n = r[9];
+            double* mo = metrics + (long long)id * 10;
+            const double m0 = r[0] / n, m1 = r[1] / n, m2 = r[2] / n;
+            mo[0] = m0 + 0.5; mo[1] = m1 + 0.5; mo[2] = m2 + 0.5;
+            mo[3] = r[3] / n - m0 * m0; mo[4] = r[4] / n - m0 * m1; mo[5] = r[5] / n - m0 * m2;
+            mo[6] = r[6] / n - m1 * m1; mo[7] = r[7] / n - m1 * m2; mo[8] = r[8] / n - m2 * m2;
+            mo[9] = n;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4 (second build)  same results as k_gather_metrics, restructured for memory-level parallelism: 8 lanes per
+// cell, each lane first issues ALL its neighbour look-ups (independent loads, no branches between them) and only
+// then fetches the moments of the occupied ones, so a cell costs ~3 dependent memory round trips instead of up
+// to 2 x 7.  Three shuffle steps reduce the group.
+// ---------------------------------------------------------------------------
+constexpr int LPC2 = 8;
+
+template <int RX, int RZ>      // compile-time neighbourhood radius (RX < 0: runtime P.rx / P.rz)
+__global__ void __launch_bounds__(256, 3)
+k_gather_metrics2(const int* __restrict__ index_map, const int* __restrict__ cell_voxel,
+                  const int* __restrict__ counter, const double* __restrict__ acc,
+                  double* __restrict__ metrics, DevParams P, int cap, int* __restrict__ scratch_count) {
+    pdl_wait();
+    const int count = min(*counter, cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *scratch_count = 0;   // ready for the next scan's K2
+    const int sub = threadIdx.x & (LPC2 - 1);
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / LPC2;
+    const int ngroups = (gridDim.x * blockDim.x) / LPC2;
+    const int rx = RX >= 0 ? RX : P.rx, rz = RX >= 0 ? RZ : P.rz;
+    const int wx = 2 * rx + 1, wz = 2 * rz + 1;
+    const int nn = wx * wx * wz;
+    constexpr int CH = 4;                                  // look-ups in flight per lane
+    const int count_pad = (count + (32 / LPC2) - 1) / (32 / LPC2) * (32 / LPC2);   // whole warps iterate together
+    for (int id = gid; id < count_pad; id += ngroups) {
+        double r[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) r[k] = 0.0;
+        if (id < count) {
+            const int v = cell_voxel[id];
+            const int x = v % P.S, y = (v / P.S) % P.S, z = v / (P.S * P.S);
+            for (int j0 = sub; j0 < nn; j0 += LPC2 * CH) {
+                int nid[CH], dxs[CH], dys[CH], dzs[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const int j = j0 + u * LPC2;
+                    const int dx = j % wx - rx, dy = (j / wx) % wx - rx, dz = j / (wx * wx) - rz;
+                    const int xx = x + dx, yy = y + dy, zz = z + dz;
+                    const bool in = j < nn && (unsigned)xx < (unsigned)P.S && (unsigned)yy < (unsigned)P.S && (unsigned)zz < (unsigned)P.Z;
+                    nid[u] = in ? __ldg(index_map + (xx + (yy + zz * P.S) * P.S)) : -1;
+                    dxs[u] = dx; dys[u] = dy; dzs[u] = dz;
+                }
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    if (nid[u] < 0) continue;
+                    const double2* a2 = reinterpret_cast<const double2*>(acc + (long long)nid[u] * ACC);
+                    const double2 a01 = a2[0], a23 = a2[1], a45 = a2[2], a67 = a2[3], a89 = a2[4];
+                    const double a0 = a01.x, a1 = a01.y, a2v = a23.x, an = a89.y;
+                    const double ddx = (double)dxs[u], ddy = (double)dys[u], ddz = (double)dzs[u];
+                    r[0] += a0 + an * ddx; r[1] += a1 + an * ddy; r[2] += a2v + an * ddz;
+                    r[3] += a23.y + 2.0 * ddx * a0 + an * ddx * ddx;
+                    r[4] += a45.x + ddx * a1 + ddy * a0 + an * ddx * ddy;
+                    r[5] += a45.y + ddx * a2v + ddz * a0 + an * ddx * ddz;
+                    r[6] += a67.x + 2.0 * ddy * a1 + an * ddy * ddy;
+                    r[7] += a67.y + ddy * a2v + ddz * a1 + an * ddy * ddz;
+                    r[8] += a89.x + 2.0 * ddz * a2v + an * ddz * ddz;
+                    r[9] += an;
+                }
+            }
+        }
+#pragma unroll
+        for (int off = LPC2 / 2; off > 0; off >>= 1)
 #pragma unroll
             for (int k = 0; k < 10; ++k) r[k] += __shfl_xor_sync(FULL, r[k], off);
         if (sub == 0 && id < count) {
@@ -860,6 +978,174 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// C1 (second build, single-GPU combine, xy_size % 256 == 0)  same results as k_merge_codes<8, MERGE_FULL>,
+// organised by ROW SEGMENTS instead of independent 8-voxel items: a warp owns 256 x-consecutive voxels of one
+// (y, z) row, lane l the eight voxels [8l, 8l+8).
+//   * everything that depends on (y, z) -- source row, range checks -- is warp-uniform
+//   * the group-mask bits of a source for the whole segment are two words: lanes 0-15 / 16-31 fetch word 0 / 1
+//     of sources 0-15 with ONE load instruction and the warp shares them by shuffle, so the mask phase costs one
+//     memory round trip per segment instead of one per source batch, and sources that hold nothing in the segment
+//     are skipped by a uniform branch
+//   * NB sources' code loads are in flight before the fold
+//   * segments in which no source knows anything (most of the grid) are not even written when the destination
+//     buffer's own group mask says it already holds "unknown" there (both combined-map buffers start as all
+//     unknown with an empty mask, and every writer keeps map and mask consistent).
+// ---------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(256, (NB > 3) ? 2 : 3)
+k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int S = P.S, Z = P.Z;
+    const int spr = S >> 8;                               // segments per row
+    const int nseg = (int)(P.V >> 8);
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int has_prev = (A.n > 0 && A.s[A.n - 1].is_prev) ? 1 : 0;
+    for (int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += warps) {
+        const int row = seg / spr;                        // y + z*S
+        const int x0s = (seg - row * spr) << 8;
+        const int z = row / S, y = row - z * S;
+        const unsigned old_word = O.gmask[seg];           // what the destination buffer holds here now
+        int acc_and[8], sum[8], op[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc_and[j] = -1; sum[j] = 0; op[j] = -1; }
+        unsigned seen = 0;                                // any source knows anything in this segment (uniform)
+        for (int kb = 0; kb < A.n; kb += 16) {
+            unsigned word = 0;
+            {
+                const int k = kb + (lane & 15), which = lane >> 4;
+                if (k < A.n) {
+                    const SlotRef& s = A.s[k];
+                    const int ys = y + s.dy, zs = z + s.dz;
+                    const int wi = ((x0s + s.dx) >> 8) + which;          // floor: source word of the segment start, +1
+                    if ((unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z && wi >= 0 && wi < spr)
+                        word = __ldg(s.gmask + (zs * S + ys) * spr + wi);
+                }
+            }
+            seen |= __ballot_sync(FULL, word != 0);
+            const int kend = min(kb + 16, A.n);
+            for (int k0 = kb; k0 < kend; k0 += NB) {
+                unsigned need = 0;
+                int xs[NB];
+                const int* rowp[NB];
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    xs[u] = 0; rowp[u] = nullptr;
+                    const int k = k0 + u;
+                    if (k < kend) {                                       // uniform
+                        const unsigned w0 = __shfl_sync(FULL, word, k - kb), w1 = __shfl_sync(FULL, word, 16 + k - kb);
+                        if ((w0 | w1) != 0) {                             // uniform: the source holds something in this segment
+                            const SlotRef& s = A.s[k];
+                            const int sx0 = x0s + s.dx;
+                            const unsigned long long Wd = ((unsigned long long)w1 << 32) | w0;
+                            const int b = ((sx0 >> 3) & 31) + lane;       // my first voxel's group, relative to word 0
+                            const unsigned m = (sx0 & 7) ? 3u : 1u;       // an unaligned shift straddles two groups
+                            if ((unsigned)(Wd >> b) & m) need |= 1u << u;
+                            xs[u] = sx0 + 8 * lane;
+                            rowp[u] = s.map + ((z + s.dz) * S + (y + s.dy)) * S;
+                        }
+                    }
+                }
+                int o[NB][8];
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[u][j] = -1;
+                    if (need & (1u << u)) load_codes<8>(rowp[u], xs[u], S, o[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    if (!(need & (1u << u))) continue;
+                    if (has_prev && k0 + u == A.n - 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) op[j] = o[u][j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { acc_and[j] &= o[u][j]; sum[j] += max(~o[u][j], 0); }
+                    }
+                }
+            }
+        }
+        if (seen == 0) {                                  // uniform: nothing known anywhere in the segment
+            if (old_word != 0) {
+                int4* dst = reinterpret_cast<int4*>(O.cmap) + (long long)seg * 64 + lane * 2;
+                dst[0] = make_int4(-1, -1, -1, -1); dst[1] = make_int4(-1, -1, -1, -1);
+                if (lane == 0) O.gmask[seg] = 0u;
+            }
+            continue;
+        }
+        bool occ[8];
+        int c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            occ[j] = acc_and[j] >= 0;
+            c[j] = -1 - sum[j];
+            if (!occ[j]) {                                // previous combined map (gvom.py:1058-1063)
+                if (op[j] >= 0) { if (c[j] >= -11) occ[j] = true; }
+                else if (op[j] < -1) c[j] += op[j] + 1;
+            }
+        }
+        unsigned m[8];
+        int nocc = 0;
+        bool any_free = false, my_occ = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            m[j] = __ballot_sync(FULL, occ[j]); nocc += __popc(m[j]);
+            any_free |= (!occ[j] && c[j] < -1); my_occ |= occ[j];
+        }
+        int base = 0;
+        if (nocc) {
+            if (lane == 0) base = atomicAdd(O.counter, nocc);
+            base = __shfl_sync(FULL, base, 0);
+        }
+        bool known_any = false;
+        const int x = x0s + 8 * lane;
+        if (!my_occ && !any_free) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = -1;
+        } else {
+            int* colo = O.col_occ + y * S + x;
+            int* colf = O.col_free + y * S + x;
+            int cur_occ[8], cur_free[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cur_occ[j] = 0x7fffffff; cur_free[j] = 0x7fffffff; }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (my_occ) {
+                    const int4 a = *(reinterpret_cast<const int4*>(colo) + g);
+                    cur_occ[4 * g] = a.x; cur_occ[4 * g + 1] = a.y; cur_occ[4 * g + 2] = a.z; cur_occ[4 * g + 3] = a.w;
+                }
+                if (any_free) {
+                    const int4 b = *(reinterpret_cast<const int4*>(colf) + g);
+                    cur_free[4 * g] = b.x; cur_free[4 * g + 1] = b.y; cur_free[4 * g + 2] = b.z; cur_free[4 * g + 3] = b.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (occ[j]) {
+                    const int id = base + __popc(m[j] & lt);
+                    if (id < O.cap) {
+                        c[j] = id; O.cell_voxel[id] = seg * 256 + lane * 8 + j;
+                        if (z < cur_occ[j]) atomicMin(colo + j, z);
+                    } else c[j] = -1;
+                } else if (c[j] < -1) {
+                    if (z < cur_free[j]) atomicMin(colf + j, z);
+                }
+                base += __popc(m[j]);
+                known_any |= c[j] != -1;
+            }
+        }
+        const unsigned w = __ballot_sync(FULL, known_any);
+        if (w != 0 || old_word != 0) {                    // uniform
+            int4* dst = reinterpret_cast<int4*>(O.cmap) + (long long)seg * 64 + lane * 2;
+            dst[0] = make_int4(c[0], c[1], c[2], c[3]); dst[1] = make_int4(c[4], c[5], c[6], c[7]);
+            if (lane == 0) O.gmask[seg] = w;
+        }
+    }
+}
+
 // closed-form eigenvalues of the float32 covariance (gvom.py:1423-1487)
 __device__ __forceinline__ void eigen3(const float* m, float* e) {
     const float xx = m[3], xy = m[4], xz = m[5], yy = m[6], yz = m[7], zz = m[8];
@@ -965,6 +1251,76 @@ k_merge_cells(MergeArgs A, const int* __restrict__ counter, const int* __restric
                 hit += s.hit[io[u]];
                 tot += s.total[io[u]];
                 mh = fminf(mh, s.minh[io[u]]);
+            }
+        }
+        float* mo = cmet + (long long)id * 10;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) mo[k] = c[k];
+        chit[id] = hit; ctot[id] = tot; cminh[id] = mh;
+        float e[3];
+        eigen3(c, e);
+        ceig[id * 3 + 0] = e[0]; ceig[id * 3 + 1] = e[1]; ceig[id * 3 + 2] = e[2];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// C2 (second build)  same results and the same fold order as k_merge_cells; the look-ups of ALL sources of a
+// cell are issued together (up to 8 per round), and the record of the next present source is fetched while the
+// current one is merged (the Chan merge is a long float64 dependency chain).
+// ---------------------------------------------------------------------------
+struct CellRec { double o[10]; int hit, tot; float mh; };
+
+__device__ __forceinline__ void load_cell_rec(const SlotRef& s, int io, CellRec& r) {
+    if (s.is_prev) {
+        const float2* om = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(s.metrics) + (long long)io * 10);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) { const float2 t = om[a]; r.o[2 * a] = (double)t.x; r.o[2 * a + 1] = (double)t.y; }
+    } else {
+        const double2* om = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(s.metrics) + (long long)io * 10);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) { const double2 t = om[a]; r.o[2 * a] = t.x; r.o[2 * a + 1] = t.y; }
+    }
+    r.hit = s.hit[io]; r.tot = s.total[io]; r.mh = s.minh[io];
+}
+
+__global__ void __launch_bounds__(128, 5)
+k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
+               int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
+               float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap) {
+    pdl_wait();
+    const int count = min(*counter, cap);
+    const int S = P.S, Z = P.Z;
+    constexpr int RB = 8;                                   // sources looked up per round
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
+        const int v = cell_voxel[id];
+        const int x = v % S, y = (v / S) % S, z = v / (S * S);
+        float c[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) c[k] = 0.f;
+        int hit = 0, tot = 0;
+        float mh = 1.0f;
+        for (int k0 = 0; k0 < A.n; k0 += RB) {
+            int io[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {                  // independent index loads first
+                io[u] = -1;
+                if (k0 + u < A.n) {
+                    const SlotRef& s = A.s[k0 + u];
+                    const int xs = x + s.dx, ys = y + s.dy, zs = z + s.dz;
+                    if ((unsigned)xs < (unsigned)S && (unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z)
+                        io[u] = __ldg(s.map + (xs + (ys + zs * S) * S));
+                }
+            }
+            // software pipeline over the present sources: buffer (u & 1) holds source u's record
+            CellRec rb[2];
+            if (io[0] >= 0) load_cell_rec(A.s[k0], io[0], rb[0]);
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                if (u + 1 < RB && io[u + 1 < RB ? u + 1 : u] >= 0) load_cell_rec(A.s[k0 + u + 1], io[u + 1 < RB ? u + 1 : u], rb[(u + 1) & 1]);
+                if (io[u] >= 0) {
+                    merge_step(c, rb[u & 1].o);
+                    hit += rb[u & 1].hit; tot += rb[u & 1].tot; mh = fminf(mh, rb[u & 1].mh);
+                }
             }
         }
         float* mo = cmet + (long long)id * 10;
@@ -1237,6 +1593,271 @@ k_surface_maps(const int* __restrict__ cmap, const int* __restrict__ chit, const
         }
     }
     GVOM_HM(pos, x0, y0) = pv;
+}
+
+// 32 bits of a bit row starting at bit position `pos` (may be negative / run past the row: those bits read 0)
+__device__ __forceinline__ unsigned row_window(const unsigned* __restrict__ row, int W, int pos) {
+    const int wi = pos >> 5;                                  // floor
+    const unsigned lo = (wi >= 0 && wi < W) ? row[wi] : 0u;
+    const unsigned hi = (wi + 1 >= 0 && wi + 1 < W) ? row[wi + 1] : 0u;
+    return __funnelshift_r(lo, hi, pos & 31);
+}
+
+// ---------------------------------------------------------------------------
+// C4 (second build)  same results as k_surface_maps, restructured for latency:
+//   * the ring search of __guess_height is branch-free per ring: every row / column segment it inspects lies
+//     within +-16 cells of the cell, so it is ONE 32-bit window of the "height known" bit rows (two shared-memory
+//     words + a funnel shift) ANDed with the wedge mask of the ring, and find-first-set gives the reference's
+//     first hit (it scans ascending).  Heights of the (at most four) cells found are loaded after the search,
+//     together.
+//   * only the ring-search warps stage the bit maps and wait for them (named barrier); the plane-fit warps
+//     start on their height loads at once.
+//   * optional second output set (pos2 ...): device-resident caller buffers are written by the kernel itself.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4)
+k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, const int* __restrict__ ctot,
+                const double* __restrict__ height, const double* __restrict__ inferred,
+                const unsigned* __restrict__ known_g, const unsigned* __restrict__ knownT_g, double o2,
+                DevParams P, double* __restrict__ rough, double* __restrict__ xs, double* __restrict__ ys,
+                double* __restrict__ guessed, int* __restrict__ pos, int* __restrict__ neg, int* __restrict__ vis,
+                int masks_in_smem, int* __restrict__ col_minz, int* __restrict__ scratch_count,
+                int* __restrict__ pos2, int* __restrict__ neg2, int* __restrict__ vis2, double* __restrict__ rough2) {
+    pdl_wait();
+    extern __shared__ unsigned smask[];
+    const int S = P.S, Z = P.Z;
+    const int W = (S + 31) >> 5;
+    const int role = threadIdx.x >> 7;
+    const int t = blockIdx.x * 128 + (threadIdx.x & 127);
+    if (role == 1) {
+        const unsigned* known = known_g;
+        const unsigned* knownT = knownT_g;
+        if (masks_in_smem) {
+            const int nw4 = (2 * S * W) >> 2;              // known and knownT are contiguous
+            const uint4* g4 = reinterpret_cast<const uint4*>(known_g);
+            uint4* s4 = reinterpret_cast<uint4*>(smask);
+#pragma unroll 4
+            for (int k = threadIdx.x & 127; k < nw4; k += 128) s4[k] = __ldg(g4 + k);
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the four ring-search warps only
+            known = smask;
+            knownT = smask + S * W;
+        }
+        if (t >= S * S) return;
+        const int y0 = t % S, x0 = t / S;
+        // housekeeping for the next combine: C1's column minima and running counter start clean
+        col_minz[t] = 0x7f7f7f7f;
+        col_minz[S * S + t] = 0x7f7f7f7f;
+        if (t == 0) *scratch_count = 0;
+        const double h0 = GVOM_HM(height, x0, y0);
+        const double inf0 = GVOM_HM(inferred, x0, y0);
+        double dh_out = 0.0;
+        if (!(h0 > -1000.0) && inf0 != -1000.0) {
+            // ---- guessed height delta (gvom.py:592-713), quirks kept (see oracle/gvom_oracle.c)
+            bool xpd = false, xnd = false, ypd = false, ynd = false;
+            int fxp = -1, fxn = -1, fyp = -1, fyn = -1;      // found coordinate along the scanned row, -1: none
+            int ixp = 0, ixn = 0, iyp = 0, iyn = 0;          // ring index at which it was found
+            const int yb = y0 - 16, xb = x0 - 16;
+            int i = 0;
+            while (i < 15 && !(xnd && ypd && ynd)) {          // x_p_done is NOT part of the condition (gvom.py:619)
+                i += 1;
+                const unsigned span = (1u << (2 * i)) - 1u;
+                const unsigned mP = span << (16 - i);         // offsets [-i, i-1]
+                const unsigned mN = span << (17 - i);         // offsets [-i+1, i]
+                const int x_p = x0 + i, x_n = x0 - i, y_p = y0 + i, y_n = y0 - i;
+                if (!xpd) {
+                    if (x_p < S) {
+                        const unsigned m = row_window(known + x_p * W, W, yb) & mP;
+                        if (m) { fxp = yb + __ffs(m) - 1; ixp = i; xpd = true; }
+                    } else xpd = true;
+                }
+                if (!xnd) {
+                    if (x_n >= 0) {
+                        const unsigned m = row_window(known + x_n * W, W, yb) & mN;
+                        if (m) { fxn = yb + __ffs(m) - 1; ixn = i; xnd = true; }
+                    } else xnd = true;
+                }
+                if (!ypd) {
+                    if (y_p < S) {
+                        const unsigned m = row_window(knownT + y_p * W, W, xb) & mN;
+                        if (m) { fyp = xb + __ffs(m) - 1; iyp = i; ypd = true; }
+                    } else ypd = true;
+                }
+                if (!ynd) {
+                    if (y_n >= 0) {
+                        const unsigned m = row_window(knownT + y_n * W, W, xb) & mP;
+                        if (m) { fyn = xb + __ffs(m) - 1; iyn = i; ynd = true; }
+                    } else ynd = true;
+                }
+            }
+            double x_ph = -1000.0, x_nh = -1000.0, y_ph = -1000.0, y_nh = -1000.0;
+            if (fxp >= 0) x_ph = GVOM_HM(height, x0 + ixp, fxp);
+            if (fxn >= 0) x_nh = GVOM_HM(height, x0 - ixn, fxn);
+            if (fyp >= 0) y_ph = GVOM_HM(height, fyp, y0 + iyp);
+            if (fyn >= 0) y_nh = GVOM_HM(height, fyn, y0 - iyn);
+            double mn = 1000.0, mx = inf0;
+            if (x_ph > -1000.0) { mn = fmin(x_ph, mn); mx = fmax(x_ph, mx); }
+            if (x_nh > -1000.0) { mn = fmin(x_nh, mn); mx = fmax(x_nh, mx); }
+            if (y_ph > -1000.0) { mn = fmin(y_ph, mn); mx = fmax(y_ph, mx); }
+            if (x_nh > -1000.0) { mn = fmin(y_nh, mn); mx = fmax(y_nh, mx); }   // sic (gvom.py:704-706)
+            const double dh = __dsub_rn(mx, mn);
+            if (dh > 0.0) dh_out = dh;
+        }
+        const int nv = dh_out > P.neg_thr ? 100 : 0, vv = h0 > -1000.0 ? 1 : 0;
+        GVOM_HM(guessed, x0, y0) = dh_out;
+        GVOM_HM(neg, x0, y0) = nv;
+        GVOM_HM(vis, x0, y0) = vv;
+        if (neg2) { GVOM_HM(neg2, x0, y0) = nv; GVOM_HM(vis2, x0, y0) = vv; }
+        return;
+    }
+    if (t >= S * S) return;
+    const int y0 = t % S, x0 = t / S;
+
+    // ---- slope + roughness (gvom.py:717-805); contraction pattern = SASS of the reference.
+    double hz[9];
+    unsigned okm = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const int x = x0 - 1 + a, y = y0 - 1 + b;
+            double h = -1000.0;
+            if (x >= 0 && x < S && y >= 0 && y < S) h = GVOM_HM(height, x, y);
+            hz[a * 3 + b] = h;
+            if (h > -1000.0) okm |= 1u << (a * 3 + b);
+        }
+    const double h0 = hz[4];
+    double sxv = 0.0, syv = 0.0, rg = -1.0;
+    const int n = __popc(okm);
+    if (n >= 3) {
+        double sx = 0, sy = 0, sz = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+            if (okm & (1u << j)) {
+                sx = __dadd_rn(sx, __dmul_rn((double)(x0 - 1 + j / 3), P.xy_res));
+                sy = __dadd_rn(sy, __dmul_rn((double)(y0 - 1 + j % 3), P.xy_res));
+                sz = __dadd_rn(sz, hz[j]);
+            }
+        const double dn = (double)n;
+        const double mx = __ddiv_rn(sx, dn), my = __ddiv_rn(sy, dn), mz = __ddiv_rn(sz, dn);
+        double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+            if (okm & (1u << j)) {
+                const double dx = __dsub_rn(__dmul_rn((double)(x0 - 1 + j / 3), P.xy_res), mx);
+                const double dy = __dsub_rn(__dmul_rn((double)(y0 - 1 + j % 3), P.xy_res), my);
+                const double dz = __dsub_rn(hz[j], mz);
+                xx = __fma_rn(dx, dx, xx); xy = __fma_rn(dx, dy, xy); xz = __fma_rn(dx, dz, xz);
+                yy = __fma_rn(dy, dy, yy); yz = __fma_rn(dy, dz, yz);
+            }
+        const double det = __fma_rn(xx, yy, -__dmul_rn(xy, xy));
+        if (det != 0.0) {
+            double a0 = __ddiv_rn(__fma_rn(xz, yy, -__dmul_rn(xy, yz)), det);
+            double a1 = __ddiv_rn(__fma_rn(xx, yz, -__dmul_rn(xy, xz)), det);
+            const double m = __dsqrt_rn(__dadd_rn(__fma_rn(a0, a0, __dmul_rn(a1, a1)), 1.0));
+            a0 = __ddiv_rn(a0, m); a1 = __ddiv_rn(a1, m);
+            double err = 0.0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if (okm & (1u << j)) {
+                    const double dx = __dsub_rn(__dmul_rn((double)(x0 - 1 + j / 3), P.xy_res), mx);
+                    const double dy = __dsub_rn(__dmul_rn((double)(y0 - 1 + j % 3), P.xy_res), my);
+                    const double e = __dsub_rn(__dsub_rn(hz[j], mz), __fma_rn(a0, dx, __dmul_rn(a1, dy)));
+                    err = __fma_rn(e, e, err);
+                }
+            err = __ddiv_rn(err, dn);
+            if (err > 0.0) err = log(err);
+            rg = err;
+            const double im = __drcp_rn(m);
+            sxv = atan2(a0, im);
+            syv = atan2(a1, im);
+        }
+    }
+    GVOM_HM(rough, x0, y0) = rg;
+    if (rough2) GVOM_HM(rough2, x0, y0) = rg;
+    GVOM_HM(xs, x0, y0) = sxv;
+    GVOM_HM(ys, x0, y0) = syv;
+
+    // ---- positive obstacles (gvom.py:515-555)
+    int pv = 0;
+    const double sl = __dsqrt_rn(__fma_rn(sxv, sxv, __dmul_rn(syv, syv)));
+    if (!(sl < P.slope_thr)) {
+        pv = 100;
+    } else {
+        const double lo = floor(__dsub_rn(__ddiv_rn(__dadd_rn(h0, P.pos_thr), P.z_res), o2));
+        const double hi = floor(__dsub_rn(__ddiv_rn(__dadd_rn(h0, P.robot_height), P.z_res), o2));
+        if (lo > -2.0e9 && lo < 2.0e9 && hi > -2.0e9 && hi < 2.0e9) {
+            const long long zlo = (long long)lo + 1, zhi = (long long)hi;
+            if (zlo >= 0 && zlo < Z && zhi >= 0 && zhi < Z) {
+                double density = 0.0, nn = 0.0;
+                for (long long zb = zlo; zb <= zhi; zb += 8) {        // 8 levels per batch: loads first
+                    int idx[8], hc[8], tc[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        idx[u] = (zb + u <= zhi) ? __ldg(cmap + (x0 + (y0 + (zb + u) * S) * S)) : -1;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { hc[u] = idx[u] >= 0 ? __ldg(chit + idx[u]) : 0; tc[u] = idx[u] >= 0 ? __ldg(ctot + idx[u]) : 0; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (hc[u] > 10) { nn = __dadd_rn(nn, (double)tc[u]); density = __dadd_rn(density, (double)hc[u]); }
+                }
+                if (nn > 0.0) density = __ddiv_rn(density, nn);
+                pv = (int)__dmul_rn(density, 100.0);
+            }
+        }
+    }
+    GVOM_HM(pos, x0, y0) = pv;
+    if (pos2) GVOM_HM(pos2, x0, y0) = pv;
+}
+
+// ---------------------------------------------------------------------------
+// OccupancyGrid post-processing of the reference's ROS node (gvom_ros.py:142-164), on the device: five int8
+// grids in Fortran order (cell [x,y] -> y*S + x) from the result block of the last combine.  numpy semantics
+// are kept: int32 comparisons against a Python float threshold are float64 comparisons, np.minimum / np.maximum
+// propagate NaN, and astype(int8) truncates toward zero and keeps the low byte (x86 cvttsd2si: out of range -> 0).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ signed char as_int8(double v) {
+    const int t = (v >= -2147483648.0 && v < 2147483648.0) ? __double2int_rz(v) : (int)0x80000000;
+    return (signed char)(t & 0xff);
+}
+
+__global__ void __launch_bounds__(256)
+k_occupancy_grids(const int* __restrict__ pos, const int* __restrict__ neg, const int* __restrict__ vis,
+                  const double* __restrict__ rough, int S, double thr, double minr, double maxr,
+                  signed char* __restrict__ out) {
+    pdl_wait();
+    // 32x32 tile transpose through shared memory: reads run along y (the maps' fast axis), writes along x
+    __shared__ int tp[32][33], tn[32][33], tv[32][33];
+    __shared__ double tr[32][33];
+    const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;      // 8 rows per pass
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int xl = ty0 + 8 * r, x = bx + xl, y = by + tx;
+        if (x < S && y < S) {
+            const long long a = (long long)x * S + y;
+            tp[xl][tx] = pos[a]; tn[xl][tx] = neg[a]; tv[xl][tx] = vis[a]; tr[xl][tx] = rough[a];
+        }
+    }
+    __syncthreads();
+    const long long S2 = (long long)S * S;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int yl = ty0 + 8 * r, y = by + yl, x = bx + tx;
+        if (x < S && y < S) {
+            const int p = tp[tx][yl], n = tn[tx][yl], v = tv[tx][yl];
+            const double rg = tr[tx][yl];
+            const long long o = (long long)y * S + x;
+            const int hard = max(((double)p > thr) ? 100 : 0, n);
+            const int soft = (((double)p <= thr) && p > 0) ? 100 : 0;
+            double c = (rg != rg) ? rg : (rg < maxr ? rg : maxr);          // np.minimum(rough, max)
+            c = (c != c) ? c : (c > minr ? c : minr);                      // np.maximum(., min)
+            const double q = __dmul_rn(__ddiv_rn(__dadd_rn(c, minr), __dsub_rn(maxr, minr)), 100.0);
+            out[0 * S2 + o] = (signed char)(hard & 0xff);
+            out[1 * S2 + o] = (signed char)(soft & 0xff);
+            out[2 * S2 + o] = (signed char)((v * 100) & 0xff);
+            out[3 * S2 + o] = (signed char)(n & 0xff);
+            out[4 * S2 + o] = as_int8(q);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -16,7 +16,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import GVOM_DEVICE, GVOM_F32, GVOM_F64, GVOM_HOST, GVOM_NO_DATA, GvomParams, GvomStats, check
+from ._lib import (GRID_NAMES, GVOM_DEVICE, GVOM_F32, GVOM_F64, GVOM_HOST, GVOM_NO_DATA, GvomParams, GvomStats,
+                   check)
 
 DEFAULT_MAX_POINTS = 1 << 19          # 524,288: two OS1-128 scans
 
@@ -144,6 +145,59 @@ class Gvom:
 
     process_pointcloud = Process_pointcloud      # spelling used by BASELINE.json
 
+    def _ego_and_transform(self, ego_position, transform):
+        self.ego_position = ego_position
+        e = self._ego_c
+        e[0], e[1], e[2] = float(ego_position[0]), float(ego_position[1]), float(ego_position[2])
+        if transform is None:
+            return e, None, None
+        T = np.ascontiguousarray(transform, dtype=np.float64)
+        if T.shape != (4, 4):
+            raise ValueError("transform must be 4x4")
+        return e, T, T.ctypes.data
+
+    def Process_pointcloud2(self, data, n_points, point_step, ego_position, transform=None, offsets=(0, 4, 8)):
+        """Extension: ingest the byte payload of a sensor_msgs/PointCloud2 directly --
+        `n_points` records of `point_step` bytes with little-endian float32 x, y, z at byte `offsets`.
+        Replaces ros_numpy.point_cloud2.pointcloud2_to_xyz_array(msg) + Process_pointcloud
+        (gvom_ros.py:108-109) with the same result: float32 fields widened to float64, NaN / Inf
+        records dropped.  `data`: bytes-like, numpy uint8 array, or torch uint8 tensor (CPU or CUDA)."""
+        torch = self._torch
+        n_points, point_step = int(n_points), int(point_step)
+        if isinstance(data, torch.Tensor):
+            t = data.contiguous().view(torch.uint8).reshape(-1)
+            if t.is_cuda and t.device.index != self.device:
+                t = t.to(f"cuda:{self.device}")
+            keep, ptr, nbytes, mem = t, t.data_ptr(), t.numel(), GVOM_DEVICE if t.is_cuda else GVOM_HOST
+        else:
+            a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+            keep, ptr, nbytes, mem = a, a.ctypes.data, a.size, GVOM_HOST
+        if nbytes < n_points * point_step:
+            raise ValueError("PointCloud2 payload shorter than n_points * point_step")
+        e, T, tp = self._ego_and_transform(ego_position, transform)
+        check(self._L.gvom_process_pointcloud2(self._h, ptr, n_points, point_step, int(offsets[0]), int(offsets[1]),
+                                               int(offsets[2]), mem, e, tp, self._stream), "gvom_process_pointcloud2")
+        del keep, T
+
+    def process_pointcloud2_msg(self, msg, ego_position, transform=None):
+        """Process_pointcloud2 for an object with the sensor_msgs/PointCloud2 attributes
+        (fields[name, offset, datatype], point_step, width, height, data, is_bigendian)."""
+        if getattr(msg, "is_bigendian", False):
+            raise ValueError("big-endian PointCloud2 payloads are not supported")
+        off = {}
+        for f in msg.fields:
+            if f.name in ("x", "y", "z"):
+                if int(f.datatype) != 7:                 # sensor_msgs/PointField.FLOAT32
+                    raise ValueError("x / y / z must be FLOAT32 fields")
+                off[f.name] = int(f.offset)
+        if len(off) != 3:
+            raise ValueError("PointCloud2 has no x / y / z fields")
+        n = int(msg.width) * int(msg.height)
+        if int(msg.height) > 1 and int(msg.row_step) != int(msg.width) * int(msg.point_step):
+            raise ValueError("PointCloud2 rows are padded (row_step != width * point_step)")
+        return self.Process_pointcloud2(msg.data, n, int(msg.point_step), ego_position, transform,
+                                        (off["x"], off["y"], off["z"]))
+
     # ---------------------------------------------------------------- combine
     def _out_arrays(self):
         """Fresh output arrays (positive, negative, roughness, visibility).  With pinned_outputs
@@ -182,6 +236,77 @@ class Gvom:
         origin = np.array([self._org_c[0], self._org_c[1], self._org_c[2]])
         return (origin, pos, neg, rough, vis)
 
+    def combine_maps_async(self):
+        """Extension: combine_maps that returns at once with a PendingMaps handle; the scan
+        pipeline can be fed while the maps are still being produced / copied.  `.result()` gives the
+        5-tuple of combine_maps (numpy views of a fresh pinned block), or None if the buffer was empty."""
+        pos, neg, rough, vis = self._out_arrays()
+        rc = check(self._L.gvom_combine_maps_async(self._h, self._org_c, pos.ctypes.data, neg.ctypes.data,
+                                                   rough.ctypes.data, vis.ctypes.data, GVOM_HOST, self._stream),
+                   "gvom_combine_maps_async")
+        if rc == GVOM_NO_DATA:
+            print("ERROR: No data in buffer")
+            return PendingMaps(self, None)
+        origin = np.array([self._org_c[0], self._org_c[1], self._org_c[2]])
+        return PendingMaps(self, (origin, pos, neg, rough, vis))
+
+    def _grid_block(self, device_outputs):
+        S = self.xy_size
+        if device_outputs:
+            t = self._torch.empty((len(GRID_NAMES), S * S), dtype=self._torch.int8, device=f"cuda:{self.device}")
+            return t, t.data_ptr(), GVOM_DEVICE
+        if self.pinned_outputs:
+            a = self._torch.empty((len(GRID_NAMES), S * S), dtype=self._torch.int8, pin_memory=True).numpy()
+        else:
+            a = np.empty((len(GRID_NAMES), S * S), np.int8)
+        return a, a.ctypes.data, GVOM_HOST
+
+    def occupancy_grids(self, density_threshold=50, min_roughness=-10, max_roughness=0, device_outputs=False):
+        """Extension: the OccupancyGrid payloads the reference node builds on the host from
+        the combine_maps outputs (gvom_ros.py:142-164), computed on the device from the last combine:
+        dict of int8 arrays of xy_size*xy_size cells flattened in Fortran order ('hard', 'soft',
+        'certainty', 'negative', 'roughness').  None before the first combine."""
+        blk, ptr, mem = self._grid_block(device_outputs)
+        rc = check(self._L.gvom_occupancy_grids(self._h, float(density_threshold), float(min_roughness),
+                                                float(max_roughness), ptr, mem, self._stream), "gvom_occupancy_grids")
+        if rc == GVOM_NO_DATA:
+            print("No data")
+            return None
+        return {k: blk[i] for i, k in enumerate(GRID_NAMES)}
+
+    def combine_maps_grids(self, density_threshold=50, min_roughness=-10, max_roughness=0, device_outputs=False):
+        """combine_maps() + occupancy_grids() in one call; only the int8 grids leave the device.
+        Returns (origin, grids dict) or None when the buffer is empty."""
+        blk, ptr, mem = self._grid_block(device_outputs)
+        rc = check(self._L.gvom_combine_maps_grids(self._h, self._org_c, float(density_threshold), float(min_roughness),
+                                                   float(max_roughness), ptr, mem, self._stream), "gvom_combine_maps_grids")
+        if rc == GVOM_NO_DATA:
+            print("ERROR: No data in buffer")
+            return None
+        origin = np.array([self._org_c[0], self._org_c[1], self._org_c[2]])
+        return origin, {k: blk[i] for i, k in enumerate(GRID_NAMES)}
+
+    # ------------------------------------------------------------------ state
+    def save_state(self, path=None):
+        """Extension: ring slots + last combined map + ego as one opaque uint8 array
+        (written to `path` with numpy.save if given)."""
+        n = C.c_size_t(0)
+        check(self._L.gvom_state_size(self._h, C.byref(n)), "gvom_state_size")
+        blob = np.empty(n.value, np.uint8)
+        w = C.c_size_t(0)
+        check(self._L.gvom_save_state(self._h, blob.ctypes.data, blob.size, C.byref(w)), "gvom_save_state")
+        blob = blob[:w.value]
+        if path is not None:
+            np.save(path, blob, allow_pickle=False)
+        return blob
+
+    def load_state(self, blob):
+        """Restore a state saved by save_state (array or path) into this Gvom (same parameters)."""
+        if isinstance(blob, str):
+            blob = np.load(blob, allow_pickle=False)
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        check(self._L.gvom_load_state(self._h, blob.ctypes.data, blob.size), "gvom_load_state")
+
     # ------------------------------------------------------------------ debug
     def make_debug_voxel_map(self):
         n = C.c_int64(0)
@@ -214,6 +339,10 @@ class Gvom:
         check(self._L.gvom_get_stats(self._h, C.byref(s)), "gvom_get_stats")
         return {k: getattr(s, k) for k, _ in GvomStats._fields_}
 
+    def set_variant(self, mask):
+        """Tooling: select earlier kernel builds (bit mask, gvom_api.cu VAR_*); 0 = current."""
+        check(self._L.gvom_set_variant(self._h, int(mask)), "gvom_set_variant")
+
     def set_profiling(self, on):
         check(self._L.gvom_set_profiling(self._h, int(bool(on))), "gvom_set_profiling")
 
@@ -226,6 +355,22 @@ class Gvom:
     def refview(self):
         """Host copy of the state under the reference's attribute names (test hook)."""
         return _RefView(self)
+
+
+class PendingMaps:
+    """Outputs of combine_maps_async: `.result()` waits and returns the combine_maps 5-tuple (or None)."""
+
+    def __init__(self, g, out):
+        self._g, self._out, self._done = g, out, out is None
+
+    def done(self):
+        return self._done
+
+    def result(self):
+        if not self._done:
+            check(self._g._L.gvom_combine_wait(self._g._h), "gvom_combine_wait")
+            self._done = True
+        return self._out
 
 
 class _RefView:

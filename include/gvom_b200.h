@@ -112,6 +112,61 @@ int gvom_debug_voxel_map(GvomHandle* h, float* out_rows8, int64_t capacity_rows,
 int gvom_debug_height_map(GvomHandle* h, float* out_rows7);
 int gvom_debug_inferred_height_map(GvomHandle* h, float* out_rows3);
 
+/* ---- the callers and data formats either side of the path ---- */
+
+/* where a caller buffer lives, continued: GVOM_NONE = "do not deliver this output" (combine only) */
+#define GVOM_NONE 2
+
+/* Replaces ros_numpy.point_cloud2.pointcloud2_to_xyz_array(data) followed by Process_pointcloud
+ * (gvom_ros.py:108-109): `data` is the byte payload of a sensor_msgs/PointCloud2 -- n_points records of
+ * point_step bytes holding little-endian float32 x / y / z at byte offsets off_x / off_y / off_z (all
+ * multiples of 4).  The fields are widened to float64 exactly as ros_numpy does, records with a NaN / Inf
+ * coordinate are dropped (remove_nans=True), and the result equals Process_pointcloud on that float64
+ * array.  Host payloads (pageable or pinned) are reduced to packed 16-byte records by the library's staging
+ * threads, so 16 instead of 24 (or point_step) bytes per point cross PCIe; device payloads are read in place. */
+int gvom_process_pointcloud2(GvomHandle* h, const void* data, int64_t n_points, int32_t point_step,
+                             int32_t off_x, int32_t off_y, int32_t off_z, int32_t mem,
+                             const double ego[3], const double* transform16, void* stream);
+
+/* Asynchronous combine (double-buffer the outputs on the caller's side): same arguments and results as
+ * gvom_combine_maps, but returns as soon as everything is enqueued.  The outputs (pinned host or device
+ * memory; pageable host memory is completed by a memcpy inside gvom_combine_wait) are valid after
+ * gvom_combine_wait(), which also reports GVOM_ECAPACITY.  `origin` is written before the call returns.
+ * Scans may be processed between the two calls; any other call on the handle waits implicitly. */
+int gvom_combine_maps_async(GvomHandle* h, double origin[3], int32_t* positive, int32_t* negative,
+                            double* roughness, int32_t* visibility, int32_t out_mem, void* stream);
+int gvom_combine_wait(GvomHandle* h);
+
+/* Replaces the OccupancyGrid post-processing of gvom_ros.py:142-164 (five numpy passes per map on the
+ * host): from the maps of the last combine, GVOM_GRID_COUNT int8 grids of xy_size*xy_size cells, each
+ * flattened in Fortran order (cell [x,y] at y*xy_size + x, the `order='F'` reshape of the node):
+ *   HARD      max(100*(positive > density_threshold), negative)        (:143)
+ *   SOFT      100*(positive <= density_threshold)*(positive > 0)       (:148)
+ *   CERTAINTY visibility*100                                           (:153, published twice)
+ *   NEGATIVE  negative                                                 (:159)
+ *   ROUGHNESS ((clip(roughness, min, max) + min) / (max - min)) * 100  (:164, the reference's formula, sic)
+ * converted like numpy's astype(int8) (truncate toward zero, keep the low byte).
+ * out: GVOM_GRID_COUNT * xy_size * xy_size bytes in host (out_mem GVOM_HOST) or device memory. */
+#define GVOM_GRID_HARD 0
+#define GVOM_GRID_SOFT 1
+#define GVOM_GRID_CERTAINTY 2
+#define GVOM_GRID_NEGATIVE 3
+#define GVOM_GRID_ROUGHNESS 4
+#define GVOM_GRID_COUNT 5
+int gvom_occupancy_grids(GvomHandle* h, double density_threshold, double min_roughness, double max_roughness,
+                         int8_t* out, int32_t out_mem, void* stream);
+/* combine_maps + the post-processing above in one call: only the int8 grids (5 bytes per cell instead
+ * of 20) leave the device.  Returns GVOM_NO_DATA like gvom_combine_maps. */
+int gvom_combine_maps_grids(GvomHandle* h, double origin[3], double density_threshold, double min_roughness,
+                            double max_roughness, int8_t* out, int32_t out_mem, void* stream);
+
+/* State save / restore (deterministic replay, regression corpora): ring slots, the last combined map
+ * (gvom.py:302-308 `last_combined_*`), ego position and ring position, as one opaque host blob that can
+ * be loaded into any handle created with the same parameters and capacities. */
+int gvom_state_size(GvomHandle* h, size_t* bytes);
+int gvom_save_state(GvomHandle* h, void* blob, size_t capacity, size_t* written);
+int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes);
+
 /* ---- multi-GPU: independent sensor streams per GPU, merged at combine time ----
  * Each rank pre-merges its own ring buffer into the common frame `origin`
  * (integral voxel units): a dense int32 code grid (V entries: occupied flag
@@ -185,6 +240,11 @@ int gvom_get_stats(GvomHandle* h, GvomStats* out);
  * gvom_set_profiling(h, 1) is on (adds event records to the stream). */
 int gvom_set_profiling(GvomHandle* h, int32_t on);
 int gvom_stage_times(GvomHandle* h, float ms[16]);
+
+/* Tooling: select earlier builds of individual kernels (bit mask, see gvom_api.cu VAR_*; 0 = current builds)
+ * so that one process can time both and the parity tests can exercise either.  Also read from the
+ * environment variable GVOM_VARIANT at gvom_create(). */
+int gvom_set_variant(GvomHandle* h, uint32_t mask);
 
 /* Tooling: L2 atomic-throughput microbenchmark (denominator of the ray-cast roofline).
  * Launches sm_count*8 blocks of 256 threads, each thread issuing per_thread
