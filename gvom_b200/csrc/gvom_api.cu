@@ -99,7 +99,7 @@ enum { EV_START = 0, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER, EV_CST
 
 // GVOM_VARIANT bits (environment, read at create): earlier builds of kernels kept selectable so that one GPU
 // run can time both and the parity tests can be run on either
-enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_OLD_CELLS = 8, VAR_MERGE_NB6 = 16 };
+enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_CELLS2 = 8, VAR_MERGE_NB6 = 16, VAR_GATHER_LB2 = 32 };
 
 }  // namespace
 
@@ -146,7 +146,7 @@ struct GvomHandle {
     bool prof_process = false, prof_combine = false, prof_x = false;
     int sm_count = 148;
     int grid_index = 0, grid_codes = 0, grid_cells = 0, grid_gather = 0;   // resident grids (set at create)
-    int grid_cells2 = 0, grid_gather2 = 0, grid_rows3 = 0, grid_rows6 = 0;
+    int grid_cells2 = 0, grid_gather2 = 0, grid_gather2b = 0, grid_rows3 = 0, grid_rows6 = 0;
     GvomStats stats{};
     float last_stage_copy_ms = 0.f;       // host time of the last pageable->pinned staging copy
     CopyPool* pool = nullptr;             // staging threads for pageable input (created on first use)
@@ -340,16 +340,18 @@ void launch_gather(GvomHandle* h, Slot& s, cudaStream_t st) {
         else
             launch(k_gather_metrics<-1, -1>, dim3(h->grid_gather), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
     } else {
-        if (r11)
-            launch(k_gather_metrics2<1, 1>, dim3(h->grid_gather2), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+        if (r11 && (h->variant & VAR_GATHER_LB2))
+            launch(k_gather_metrics2<1, 1, 2>, dim3(h->grid_gather2b), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+        else if (r11)
+            launch(k_gather_metrics2<1, 1, 3>, dim3(h->grid_gather2), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
         else
-            launch(k_gather_metrics2<-1, -1>, dim3(h->grid_gather2), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
+            launch(k_gather_metrics2<-1, -1, 3>, dim3(h->grid_gather2), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
     }
 }
 
 // C2: per-cell record merge + eigenvalues
 void launch_cells(GvomHandle* h, const MergeArgs& A, Combined& c, cudaStream_t st) {
-    if (h->variant & VAR_OLD_CELLS)
+    if (!(h->variant & VAR_CELLS2))
         launch(k_merge_cells, dim3(h->grid_cells), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
                                                       h->dp, (int)h->ccap);
     else
@@ -519,8 +521,9 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
                                 : resident_grid(k_merge_codes<1, MERGE_FINISH>, 256, h->sm_count);
         h->grid_cells = resident_grid(k_merge_cells, 128, h->sm_count);
         h->grid_cells2 = resident_grid(k_merge_cells2, 128, h->sm_count);
-        h->grid_gather2 = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics2<1, 1>, 256, h->sm_count)
-                                                                          : resident_grid(k_gather_metrics2<-1, -1>, 256, h->sm_count);
+        h->grid_gather2 = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics2<1, 1, 3>, 256, h->sm_count)
+                                                                          : resident_grid(k_gather_metrics2<-1, -1, 3>, 256, h->sm_count);
+        h->grid_gather2b = resident_grid(k_gather_metrics2<1, 1, 2>, 256, h->sm_count);
         if (const char* m = getenv("GVOM_VARIANT")) h->variant = (unsigned)strtoul(m, nullptr, 0);
         h->grid_rows3 = resident_grid(k_merge_rows<3>, 256, h->sm_count);
         h->grid_rows6 = resident_grid(k_merge_rows<6>, 256, h->sm_count);
@@ -625,7 +628,7 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
     };
     auto ensure_pool = [&]() {
         if (!h->pool) {
-            int helpers = 3;
+            int helpers = std::max(3, std::min(7, (int)std::thread::hardware_concurrency() / 2 - 1));
             if (const char* e = getenv("GVOM_COPY_THREADS")) helpers = std::max(0, atoi(e) - 1);
             h->pool = new CopyPool(helpers);
         }

@@ -348,19 +348,31 @@ k_build_index(int* __restrict__ hit, int* __restrict__ total, int* __restrict__ 
                 }
             }
         }
+        // compact ids: one atomic per warp and item; all of them are issued before the first result is consumed
+        // (an atomic round trip to L2 is as long as the loads above)
+        unsigned mm[U][VEC];
+        int base_u[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long long q = q0 + u * nthreads;
-            if (q >= NQp) break;                        // warp-uniform: NQp and q0 are multiples of 32 apart
-            unsigned m[VEC];
             int nocc = 0;
+            base_u[u] = 0;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) { m[j] = __ballot_sync(FULL, h[u][j] > 0); nocc += __popc(m[j]); }
-            int base = 0;
-            if (nocc) {
-                if (lane == 0) base = atomicAdd(counter, nocc);
-                base = __shfl_sync(FULL, base, 0);
+            for (int j = 0; j < VEC; ++j) { mm[u][j] = 0; }
+            if (q < NQp) {                              // warp-uniform: NQp and q0 are multiples of 32 apart
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) { mm[u][j] = __ballot_sync(FULL, h[u][j] > 0); nocc += __popc(mm[u][j]); }
+                if (nocc && lane == 0) base_u[u] = atomicAdd(counter, nocc);
             }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long q = q0 + u * nthreads;
+            if (q >= NQp) break;                        // warp-uniform
+            unsigned m[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) m[j] = mm[u][j];
+            int base = __shfl_sync(FULL, base_u[u], 0);
             bool known_any = false;
             if (q < NQ) {
                 int code[VEC];
@@ -471,8 +483,9 @@ k_moments(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevP
     const unsigned heads = __ballot_sync(FULL, head);
     const unsigned after = heads & ~((2u << lane) - 1u);  // heads strictly above my lane
     const int run_end = after ? (__ffs(after) - 2) : 31;  // last lane of my run
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
+    // (runs are short: the scan stops at the longest run of this warp instead of always taking five steps)
+    const int max_d = __reduce_max_sync(FULL, run_end - lane);
+    for (int off = 1; off <= max_d; off <<= 1) {
         const bool take = (lane + off) <= run_end;
 #pragma unroll
         for (int k = 0; k < 10; ++k) q[k] = seg_add(q[k], off, take);
@@ -597,8 +610,8 @@ k_gather_metrics(const int* __restrict__ index_map, const int* __restrict__ cell
 // ---------------------------------------------------------------------------
 constexpr int LPC2 = 8;
 
-template <int RX, int RZ>      // compile-time neighbourhood radius (RX < 0: runtime P.rx / P.rz)
-__global__ void __launch_bounds__(256, 3)
+template <int RX, int RZ, int MINB>      // compile-time neighbourhood radius (RX < 0: runtime P.rx / P.rz); blocks per SM
+__global__ void __launch_bounds__(256, MINB)
 k_gather_metrics2(const int* __restrict__ index_map, const int* __restrict__ cell_voxel,
                   const int* __restrict__ counter, const double* __restrict__ acc,
                   double* __restrict__ metrics, DevParams P, int cap, int* __restrict__ scratch_count) {
@@ -617,11 +630,13 @@ k_gather_metrics2(const int* __restrict__ index_map, const int* __restrict__ cel
         double r[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) r[k] = 0.0;
+        double apron_n = 0.0;                               // fetched early: decides whether the apron block is read at all
         if (id < count) {
+            if (sub == 0) apron_n = acc[(long long)id * ACC + 19];
             const int v = cell_voxel[id];
             const int x = v % P.S, y = (v / P.S) % P.S, z = v / (P.S * P.S);
             for (int j0 = sub; j0 < nn; j0 += LPC2 * CH) {
-                int nid[CH], dxs[CH], dys[CH], dzs[CH];
+                int nid[CH];
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
                     const int j = j0 + u * LPC2;
@@ -629,15 +644,28 @@ k_gather_metrics2(const int* __restrict__ index_map, const int* __restrict__ cel
                     const int xx = x + dx, yy = y + dy, zz = z + dz;
                     const bool in = j < nn && (unsigned)xx < (unsigned)P.S && (unsigned)yy < (unsigned)P.S && (unsigned)zz < (unsigned)P.Z;
                     nid[u] = in ? __ldg(index_map + (xx + (yy + zz * P.S) * P.S)) : -1;
-                    dxs[u] = dx; dys[u] = dy; dzs[u] = dz;
+                }
+                // two-deep pipeline over the occupied neighbours: record u+1 is in flight while record u is folded in
+                double2 rb[2][5];
+#pragma unroll
+                for (int g = 0; g < 5; ++g) { rb[0][g] = make_double2(0.0, 0.0); rb[1][g] = make_double2(0.0, 0.0); }
+                if (nid[0] >= 0) {
+                    const double2* a2 = reinterpret_cast<const double2*>(acc + (long long)nid[0] * ACC);
+#pragma unroll
+                    for (int g = 0; g < 5; ++g) rb[0][g] = a2[g];
                 }
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
+                    if (u + 1 < CH && nid[u + 1 < CH ? u + 1 : u] >= 0) {
+                        const double2* a2 = reinterpret_cast<const double2*>(acc + (long long)nid[u + 1 < CH ? u + 1 : u] * ACC);
+#pragma unroll
+                        for (int g = 0; g < 5; ++g) rb[(u + 1) & 1][g] = a2[g];
+                    }
                     if (nid[u] < 0) continue;
-                    const double2* a2 = reinterpret_cast<const double2*>(acc + (long long)nid[u] * ACC);
-                    const double2 a01 = a2[0], a23 = a2[1], a45 = a2[2], a67 = a2[3], a89 = a2[4];
+                    const double2 a01 = rb[u & 1][0], a23 = rb[u & 1][1], a45 = rb[u & 1][2], a67 = rb[u & 1][3], a89 = rb[u & 1][4];
                     const double a0 = a01.x, a1 = a01.y, a2v = a23.x, an = a89.y;
-                    const double ddx = (double)dxs[u], ddy = (double)dys[u], ddz = (double)dzs[u];
+                    const int j = j0 + u * LPC2;                     // offset of this neighbour (recomputed: cheaper than keeping it)
+                    const double ddx = (double)(j % wx - rx), ddy = (double)((j / wx) % wx - rx), ddz = (double)(j / (wx * wx) - rz);
                     r[0] += a0 + an * ddx; r[1] += a1 + an * ddy; r[2] += a2v + an * ddz;
                     r[3] += a23.y + 2.0 * ddx * a0 + an * ddx * ddx;
                     r[4] += a45.x + ddx * a1 + ddy * a0 + an * ddx * ddy;
@@ -654,9 +682,12 @@ k_gather_metrics2(const int* __restrict__ index_map, const int* __restrict__ cel
 #pragma unroll
             for (int k = 0; k < 10; ++k) r[k] += __shfl_xor_sync(FULL, r[k], off);
         if (sub == 0 && id < count) {
-            const double* e = acc + (long long)id * ACC + 10;
+            if (apron_n != 0.0) {                           // out-of-grid points that reached this cell (rare)
+                const double* e = acc + (long long)id * ACC + 10;
 #pragma unroll
-            for (int k = 0; k < 10; ++k) r[k] += e[k];
+                for (int k = 0; k < 9; ++k) r[k] += e[k];
+                r[9] += apron_n;
+            }
             const double n = r[9];
             double* mo = metrics + (long long)id * 10;
             const double m0 = r[0] / n, m1 = r[1] / n, m2 = r[2] / n;
@@ -978,6 +1009,40 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
     }
 }
 
+// eight x-consecutive codes of a source row starting at xs (any alignment, may leave the row: -1 there), S % 4 == 0.
+// The misalignment xs & 3 only depends on the source's x shift, so it is warp-uniform: three aligned 128-bit
+// loads and a uniform switch instead of eight predicated scalar loads.
+__device__ __forceinline__ void load_codes8_any(const int* __restrict__ row, int xs, int S, int (&o)[8]) {
+    const int a = xs & 3;
+    const int xa = xs - a;
+    int t[12];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        const int x = xa + 4 * g;
+        int4 q = make_int4(-1, -1, -1, -1);
+        if ((g < 2 || a != 0) && (unsigned)x < (unsigned)S) q = __ldg(reinterpret_cast<const int4*>(row + x));
+        t[4 * g] = q.x; t[4 * g + 1] = q.y; t[4 * g + 2] = q.z; t[4 * g + 3] = q.w;
+    }
+    switch (a) {
+    case 0:
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = t[j];
+        break;
+    case 1:
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = t[j + 1];
+        break;
+    case 2:
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = t[j + 2];
+        break;
+    default:
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = t[j + 3];
+        break;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // C1 (second build, single-GPU combine, xy_size % 256 == 0)  same results as k_merge_codes<8, MERGE_FULL>,
 // organised by ROW SEGMENTS instead of independent 8-voxel items: a warp owns 256 x-consecutive voxels of one
@@ -1003,27 +1068,40 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
     const int nseg = (int)(P.V >> 8);
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int has_prev = (A.n > 0 && A.s[A.n - 1].is_prev) ? 1 : 0;
-    for (int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += warps) {
+    // group-mask words of sources kb..kb+15 for segment sg: lanes 0-15 word 0, lanes 16-31 word 1
+    auto mask_words = [&](int sg, int kb) -> unsigned {
+        const int row = sg / spr;
+        const int x0s = (sg - row * spr) << 8;
+        const int z = row / S, y = row - z * S;
+        const int k = kb + (lane & 15), which = lane >> 4;
+        unsigned word = 0;
+        if (k < A.n) {
+            const SlotRef& s = A.s[k];
+            const int ys = y + s.dy, zs = z + s.dz;
+            const int wi = ((x0s + s.dx) >> 8) + which;                  // floor: source word of the segment start, +1
+            if ((unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z && wi >= 0 && wi < spr)
+                word = __ldg(s.gmask + (zs * S + ys) * spr + wi);
+        }
+        return word;
+    };
+    int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // software pipeline: the mask words (and the destination's own word) of the NEXT segment are fetched while this
+    // one is merged, so the mask round trip is off the critical path
+    unsigned word_next = 0, old_next = 0;
+    if (seg < nseg) { word_next = mask_words(seg, 0); old_next = O.gmask[seg]; }
+    for (; seg < nseg; seg += warps) {
         const int row = seg / spr;                        // y + z*S
         const int x0s = (seg - row * spr) << 8;
         const int z = row / S, y = row - z * S;
-        const unsigned old_word = O.gmask[seg];           // what the destination buffer holds here now
+        const unsigned word_first = word_next;
+        const unsigned old_word = old_next;               // what the destination buffer holds here now
+        if (seg + warps < nseg) { word_next = mask_words(seg + warps, 0); old_next = O.gmask[seg + warps]; }
         int acc_and[8], sum[8], op[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc_and[j] = -1; sum[j] = 0; op[j] = -1; }
         unsigned seen = 0;                                // any source knows anything in this segment (uniform)
         for (int kb = 0; kb < A.n; kb += 16) {
-            unsigned word = 0;
-            {
-                const int k = kb + (lane & 15), which = lane >> 4;
-                if (k < A.n) {
-                    const SlotRef& s = A.s[k];
-                    const int ys = y + s.dy, zs = z + s.dz;
-                    const int wi = ((x0s + s.dx) >> 8) + which;          // floor: source word of the segment start, +1
-                    if ((unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z && wi >= 0 && wi < spr)
-                        word = __ldg(s.gmask + (zs * S + ys) * spr + wi);
-                }
-            }
+            const unsigned word = kb == 0 ? word_first : mask_words(seg, kb);
             seen |= __ballot_sync(FULL, word != 0);
             const int kend = min(kb + 16, A.n);
             for (int k0 = kb; k0 < kend; k0 += NB) {
@@ -1053,7 +1131,7 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
                 for (int u = 0; u < NB; ++u) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[u][j] = -1;
-                    if (need & (1u << u)) load_codes<8>(rowp[u], xs[u], S, o[u]);
+                    if (need & (1u << u)) load_codes8_any(rowp[u], xs[u], S, o[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < NB; ++u) {
@@ -1265,8 +1343,8 @@ k_merge_cells(MergeArgs A, const int* __restrict__ counter, const int* __restric
 
 // ---------------------------------------------------------------------------
 // C2 (second build)  same results and the same fold order as k_merge_cells; the look-ups of ALL sources of a
-// cell are issued together (up to 8 per round), and the record of the next present source is fetched while the
-// current one is merged (the Chan merge is a long float64 dependency chain).
+// cell are issued together (up to 8 per round) instead of in batches of SLOT_BATCH.  (A build that also fetched the
+// next record while merging the current one needed 96 registers and lost more to occupancy than it gained.)
 // ---------------------------------------------------------------------------
 struct CellRec { double o[10]; int hit, tot; float mh; };
 
@@ -1283,7 +1361,7 @@ __device__ __forceinline__ void load_cell_rec(const SlotRef& s, int io, CellRec&
     r.hit = s.hit[io]; r.tot = s.total[io]; r.mh = s.minh[io];
 }
 
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, 8)
 k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
                int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
                float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap) {
@@ -1311,16 +1389,13 @@ k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restri
                         io[u] = __ldg(s.map + (xs + (ys + zs * S) * S));
                 }
             }
-            // software pipeline over the present sources: buffer (u & 1) holds source u's record
-            CellRec rb[2];
-            if (io[0] >= 0) load_cell_rec(A.s[k0], io[0], rb[0]);
 #pragma unroll
             for (int u = 0; u < RB; ++u) {
-                if (u + 1 < RB && io[u + 1 < RB ? u + 1 : u] >= 0) load_cell_rec(A.s[k0 + u + 1], io[u + 1 < RB ? u + 1 : u], rb[(u + 1) & 1]);
-                if (io[u] >= 0) {
-                    merge_step(c, rb[u & 1].o);
-                    hit += rb[u & 1].hit; tot += rb[u & 1].tot; mh = fminf(mh, rb[u & 1].mh);
-                }
+                if (io[u] < 0) continue;
+                CellRec rc;
+                load_cell_rec(A.s[k0 + u], io[u], rc);
+                merge_step(c, rc.o);
+                hit += rc.hit; tot += rc.tot; mh = fminf(mh, rc.mh);
             }
         }
         float* mo = cmet + (long long)id * 10;
