@@ -99,7 +99,7 @@ enum { EV_START = 0, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER, EV_CST
 
 // GVOM_VARIANT bits (environment, read at create): earlier builds of kernels kept selectable so that one GPU
 // run can time both and the parity tests can be run on either
-enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_CELLS2 = 8, VAR_MERGE_NB6 = 16, VAR_GATHER_LB2 = 32 };
+enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_OLD_CELLS = 8, VAR_MERGE_NB6 = 16, VAR_GATHER_LB2 = 32 };
 
 }  // namespace
 
@@ -351,7 +351,7 @@ void launch_gather(GvomHandle* h, Slot& s, cudaStream_t st) {
 
 // C2: per-cell record merge + eigenvalues
 void launch_cells(GvomHandle* h, const MergeArgs& A, Combined& c, cudaStream_t st) {
-    if (!(h->variant & VAR_CELLS2))
+    if (h->variant & VAR_OLD_CELLS)
         launch(k_merge_cells, dim3(h->grid_cells), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
                                                       h->dp, (int)h->ccap);
     else

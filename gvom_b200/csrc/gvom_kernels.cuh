@@ -1009,40 +1009,6 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
     }
 }
 
-// eight x-consecutive codes of a source row starting at xs (any alignment, may leave the row: -1 there), S % 4 == 0.
-// The misalignment xs & 3 only depends on the source's x shift, so it is warp-uniform: three aligned 128-bit
-// loads and a uniform switch instead of eight predicated scalar loads.
-__device__ __forceinline__ void load_codes8_any(const int* __restrict__ row, int xs, int S, int (&o)[8]) {
-    const int a = xs & 3;
-    const int xa = xs - a;
-    int t[12];
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-        const int x = xa + 4 * g;
-        int4 q = make_int4(-1, -1, -1, -1);
-        if ((g < 2 || a != 0) && (unsigned)x < (unsigned)S) q = __ldg(reinterpret_cast<const int4*>(row + x));
-        t[4 * g] = q.x; t[4 * g + 1] = q.y; t[4 * g + 2] = q.z; t[4 * g + 3] = q.w;
-    }
-    switch (a) {
-    case 0:
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = t[j];
-        break;
-    case 1:
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = t[j + 1];
-        break;
-    case 2:
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = t[j + 2];
-        break;
-    default:
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = t[j + 3];
-        break;
-    }
-}
-
 // ---------------------------------------------------------------------------
 // C1 (second build, single-GPU combine, xy_size % 256 == 0)  same results as k_merge_codes<8, MERGE_FULL>,
 // organised by ROW SEGMENTS instead of independent 8-voxel items: a warp owns 256 x-consecutive voxels of one
@@ -1052,7 +1018,9 @@ __device__ __forceinline__ void load_codes8_any(const int* __restrict__ row, int
 //     of sources 0-15 with ONE load instruction and the warp shares them by shuffle, so the mask phase costs one
 //     memory round trip per segment instead of one per source batch, and sources that hold nothing in the segment
 //     are skipped by a uniform branch
-//   * NB sources' code loads are in flight before the fold
+//   * NB sources' code loads are in flight before the fold.  (Measured and dropped: three aligned 128-bit loads +
+//     a uniform register shift for x-shifted sources -- 36 us against 32 us with per-element loads, the 32-byte lane
+//     stride wastes half of every 128-bit request; prefetching the next segment's mask words -- no change.)
 //   * segments in which no source knows anything (most of the grid) are not even written when the destination
 //     buffer's own group mask says it already holds "unknown" there (both combined-map buffers start as all
 //     unknown with an empty mask, and every writer keeps map and mask consistent).
@@ -1084,24 +1052,17 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
         }
         return word;
     };
-    int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    // software pipeline: the mask words (and the destination's own word) of the NEXT segment are fetched while this
-    // one is merged, so the mask round trip is off the critical path
-    unsigned word_next = 0, old_next = 0;
-    if (seg < nseg) { word_next = mask_words(seg, 0); old_next = O.gmask[seg]; }
-    for (; seg < nseg; seg += warps) {
+    for (int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += warps) {
         const int row = seg / spr;                        // y + z*S
         const int x0s = (seg - row * spr) << 8;
         const int z = row / S, y = row - z * S;
-        const unsigned word_first = word_next;
-        const unsigned old_word = old_next;               // what the destination buffer holds here now
-        if (seg + warps < nseg) { word_next = mask_words(seg + warps, 0); old_next = O.gmask[seg + warps]; }
+        const unsigned old_word = O.gmask[seg];           // what the destination buffer holds here now
         int acc_and[8], sum[8], op[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc_and[j] = -1; sum[j] = 0; op[j] = -1; }
         unsigned seen = 0;                                // any source knows anything in this segment (uniform)
         for (int kb = 0; kb < A.n; kb += 16) {
-            const unsigned word = kb == 0 ? word_first : mask_words(seg, kb);
+            const unsigned word = mask_words(seg, kb);
             seen |= __ballot_sync(FULL, word != 0);
             const int kend = min(kb + 16, A.n);
             for (int k0 = kb; k0 < kend; k0 += NB) {
@@ -1131,7 +1092,7 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
                 for (int u = 0; u < NB; ++u) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[u][j] = -1;
-                    if (need & (1u << u)) load_codes8_any(rowp[u], xs[u], S, o[u]);
+                    if (need & (1u << u)) load_codes<8>(rowp[u], xs[u], S, o[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < NB; ++u) {
