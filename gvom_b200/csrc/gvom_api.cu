@@ -99,7 +99,7 @@ enum { EV_START = 0, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER, EV_CST
 
 // GVOM_VARIANT bits (environment, read at create): earlier builds of kernels kept selectable so that one GPU
 // run can time both and the parity tests can be run on either
-enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_OLD_CELLS = 8, VAR_MERGE_NB6 = 16, VAR_GATHER_LB2 = 32 };
+enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_OLD_CELLS = 8, VAR_MERGE_NB6 = 16, VAR_GATHER_LB2 = 32, VAR_DMA_OUT = 64 };
 
 }  // namespace
 
@@ -392,13 +392,36 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
     double* xs = h->maps + 3 * (size_t)S2; double* ys = h->maps + 4 * (size_t)S2; double* guessed = h->maps + 5 * (size_t)S2;
     int* pos = h->imaps; int* neg = h->imaps + S2; int* vis = h->imaps + 2 * (size_t)S2;
     // device-resident outputs: the surface kernel writes them itself, next to the library's own result block
-    // (which the debug exports and the OccupancyGrid post-processing read)
-    const bool direct_dev = out_mem == GVOM_DEVICE && positive && negative && roughness && visibility;
+    // (which the debug exports and the OccupancyGrid post-processing read).  Pinned host outputs are written the
+    // same way through their device mapping (posted PCIe writes, coalesced): no DMA operation on the critical path.
+    bool direct_dev = out_mem == GVOM_DEVICE && positive && negative && roughness && visibility;
+    int32_t *kpos = positive, *kneg = negative, *kvis = visibility;
+    double* krough = roughness;
+    if (!direct_dev && out_mem == GVOM_HOST && positive && negative && roughness && visibility && h->zero_copy &&
+        !(h->variant & (VAR_OLD_SURFACE | VAR_DMA_OUT))) {
+        void* m[4] = {nullptr, nullptr, nullptr, nullptr};
+        void* hp[4] = {positive, negative, visibility, roughness};
+        bool ok = true, dev = false;
+        for (int k = 0; k < 4 && ok; ++k) {
+            ok = is_pinned_or_device(hp[k], &dev) && !dev && cudaHostGetDevicePointer(&m[k], hp[k], 0) == cudaSuccess && m[k];
+            if (!ok) cudaGetLastError();
+        }
+        if (ok) {
+            direct_dev = true;
+            kpos = (int32_t*)m[0]; kneg = (int32_t*)m[1]; kvis = (int32_t*)m[2]; krough = (double*)m[3];
+        }
+    }
+    // combined cell count: C3 stores it into a mapped pinned word (else a 4-byte DMA after the kernels)
+    int* host_count = nullptr;
+    if (h->zero_copy && !(h->variant & VAR_DMA_OUT)) {
+        void* m = nullptr;
+        if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) host_count = (int*)m; else cudaGetLastError();
+    }
     const int W = (h->p.xy_size + 31) / 32;
     unsigned* known = h->known; unsigned* knownT = h->known + (size_t)h->p.xy_size * W;
     launch(k_column_maps, dim3(W, W), dim3(1024), 0, st, c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
                                                c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, height, inferred, known, knownT,
-                                               h->flags + 1, c.counter);
+                                               h->flags + 1, c.counter, host_count);
     const size_t mask_bytes = 2 * (size_t)h->p.xy_size * W * sizeof(unsigned);
     const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
     if (h->variant & VAR_OLD_SURFACE) {
@@ -416,13 +439,13 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
         launch(k_surface_maps2, dim3(blocks_for(S2, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit, c.total, height, inferred, known, knownT,
                                                                                  c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
                                                                                  in_smem, h->col_minz, h->flags + 1,
-                                                                                 direct_dev ? positive : nullptr, direct_dev ? negative : nullptr,
-                                                                                 direct_dev ? visibility : nullptr, direct_dev ? roughness : nullptr);
+                                                                                 direct_dev ? kpos : nullptr, direct_dev ? kneg : nullptr,
+                                                                                 direct_dev ? kvis : nullptr, direct_dev ? krough : nullptr);
     }
     h->stats.kernel_launches += 2;
     rec(h, EV_MAPS, st);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(h->counters_host, c.counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!host_count) CUDA_TRY(cudaMemcpyAsync(h->counters_host, c.counter, sizeof(int), cudaMemcpyDeviceToHost, st));
     const size_t bi = (size_t)S2 * sizeof(int), bd = (size_t)S2 * sizeof(double);
     GvomHandle::Pending& pd = h->pend;
     pd = GvomHandle::Pending{};
@@ -889,11 +912,20 @@ static int grids_locked(GvomHandle* h, double thr, double minr, double maxr, int
     const size_t S2 = (size_t)h->S2, bytes = GVOM_GRID_COUNT * S2;
     const int* pos = h->imaps;
     signed char* dst = (out_mem == GVOM_DEVICE) ? reinterpret_cast<signed char*>(out) : h->grids_dev;
+    bool mapped_out = false;
+    if (out_mem == GVOM_HOST && h->zero_copy && !(h->variant & VAR_DMA_OUT)) {   // pinned: the kernel writes through the mapping
+        bool dev = false;
+        void* m = nullptr;
+        if (is_pinned_or_device(out, &dev) && !dev && cudaHostGetDevicePointer(&m, out, 0) == cudaSuccess && m) {
+            dst = static_cast<signed char*>(m);
+            mapped_out = true;
+        } else cudaGetLastError();
+    }
     const int T = (S + 31) / 32;
     launch(k_occupancy_grids, dim3(T, T), dim3(256), 0, st, pos, pos + S2, pos + 2 * S2, (const double*)h->rough_out, S, thr, minr, maxr, dst);
     h->stats.kernel_launches++;
     CUDA_TRY(cudaGetLastError());
-    if (out_mem == GVOM_DEVICE) {
+    if (out_mem == GVOM_DEVICE || mapped_out) {
         CUDA_TRY(cudaStreamSynchronize(st));
         return GVOM_OK;
     }

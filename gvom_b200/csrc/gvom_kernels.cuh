@@ -1378,14 +1378,15 @@ k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restri
 // builds two bit maps of "height known" cells for the ring search of C4:
 //   known [x][y/32] (bits over y) and knownT[y][x/32] (bits over x).
 // Block = 32x32 cell tile, 1024 threads (x fastest), one column per thread.
-// Also publishes the combined cell count (thread 0): C1's running counter -> the map's counter.
+// Also publishes the combined cell count (thread 0): C1's running counter -> the map's counter and, through a
+// mapped pinned word, the host.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 k_column_maps(const int* __restrict__ cmap, const float* __restrict__ cminh, const int* __restrict__ col_occ,
               const int* __restrict__ col_free, double o0, double o1, double o2, double e0, double e1, double e2,
               DevParams P, double* __restrict__ height, double* __restrict__ inferred,
               unsigned* __restrict__ known, unsigned* __restrict__ knownT,
-              const int* __restrict__ scratch_count, int* __restrict__ map_count) {
+              const int* __restrict__ scratch_count, int* __restrict__ map_count, int* __restrict__ host_count) {
     pdl_wait();
     __shared__ unsigned char flag[32][33];
     const int S = P.S;
@@ -1393,7 +1394,11 @@ k_column_maps(const int* __restrict__ cmap, const float* __restrict__ cminh, con
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 32 + ty;
     const long long zs = (long long)S * S;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *map_count = *scratch_count;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        const int n = *scratch_count;
+        *map_count = n;
+        if (host_count) *host_count = n;                   // mapped pinned word: the host reads the count without a DMA op
+    }
     bool kn = false;
     if (x < S && y < S) {
         double h = -1000.0, inf = -1000.0;

@@ -18,7 +18,7 @@ from gvom_b200 import Gvom, synth  # noqa: E402
 from gvom_b200.node import PointCloud2Payload  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 60
-NAMES = {0: "current", 1: "old surface", 2: "old merge", 4: "old gather", 8: "old cells", 16: "rows NB6", 32: "gather2 2 blocks/SM", 15: "all old"}
+NAMES = {0: "current", 1: "old surface", 2: "old merge", 4: "old gather", 8: "old cells", 16: "rows NB6", 32: "gather2 2 blocks/SM", 64: "DMA outputs", 15: "all old"}
 stream = torch.cuda.Stream()
 g = Gvom(*synth.params_tuple(), stream=stream.cuda_stream)
 fr = [synth.frame(i, 128, 2048) for i in range(8)]
@@ -49,7 +49,7 @@ def run(n, profile=False):
 
 
 res = {}
-for mask in (0, 1, 2, 4, 8, 16, 32, 15, 0):
+for mask in (0, 64, 0):
     g.set_variant(mask)
     run(12)
     ev, _ = run(steps)
@@ -104,6 +104,10 @@ def pipelined(n):
     return 1e3 * (time.perf_counter() - t0) / n
 
 
+g.set_variant(64)
+host["pinned_f64_in__maps_out__DMA_outputs"] = wall(lambda k: (g.Process_pointcloud(pin[k], fr[k][1], fr[k][2]), g.combine_maps()), steps)
+host["pinned_f64_in__grids_out__DMA_outputs"] = wall(lambda k: (g.Process_pointcloud(pin[k], fr[k][1], fr[k][2]), g.combine_maps_grids()), steps)
+g.set_variant(0)
 pipelined(10)
 host["pinned_f64_in__maps_out__async_pipelined_ms_per_tick"] = pipelined(steps)
 print(json.dumps({"host_tick_p50_ms": host}), flush=True)
