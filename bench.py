@@ -319,6 +319,9 @@ def main():
     except Exception:
         pass
     abytes = {"raycast": 24 * N, "index": 12 * V, "merge_codes": 4 * V * sources + 4 * V, "maps": 4 * V + 20 * P[2] * P[2]}
+    # (SURVEY.md 8d per-stage figures: ray-cast = the cloud as stored (float64 x 3); index = read hit + pass grids, write
+    #  the index map; merge = read B slot maps + the previous map, write the combined map; maps = one pass over the
+    #  combined map + the five 2-D outputs)
     rooflines = {}
     for k, bts in abytes.items():
         if stage_ms.get(k, 0) > 0:
@@ -335,7 +338,7 @@ def main():
                                         "note": "increments delivered (warp-aggregated) vs RED.ADD.U32 issue rate to "
                                                 "random words of a 16 MiB table measured by gvom_bench_atomics"}
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")        # refreshed with every committed ncu capture
     if os.path.exists(tp):                        # DRAM bytes per launch from the committed ncu --set full capture
         for k, v in json.load(open(tp)).items():
             if isinstance(v, dict) and v.get("dram_read") is not None and v.get("dram_write") is not None:
@@ -368,6 +371,31 @@ def main():
         "l2_atomic_peak_gops": atom,
         "work_per_scan": work,
     }
+    if world == 1:
+        # the callers either side of the path, same workload, wall clock per tick (p50 of 60):
+        # what the reference node hands over (pageable float64 array) and the PointCloud2 payload it received
+        # (48-byte records), maps or the node's int8 OccupancyGrid payloads out
+        try:
+            from gvom_b200.node import PointCloud2Payload
+            msgs = [PointCloud2Payload.from_xyz(f[0], 48) for f in fr]
+            raw = [m.data.tobytes() for m in msgs]
+
+            def wall(fn, n=60):
+                ts = []
+                for i in range(n + 8):
+                    t0 = time.perf_counter()
+                    fn(i % NFRAMES)
+                    ts.append(1e3 * (time.perf_counter() - t0))
+                return statistics.median(ts[8:])
+            line["e2e_variants_p50_ms"] = {
+                "pageable_numpy_f64_in__maps_out": wall(lambda k: (g.Process_pointcloud(fr[k][0], fr[k][1], fr[k][2]), g.combine_maps())),
+                "pinned_f64_in__int8_grids_out": wall(lambda k: (g.Process_pointcloud(pinned[k], fr[k][1], fr[k][2]), g.combine_maps_grids())),
+                "pointcloud2_bytes48_in__maps_out": wall(lambda k: (g.Process_pointcloud2(raw[k], msgs[k].n_points, 48, fr[k][1], fr[k][2]), g.combine_maps())),
+                "pointcloud2_bytes48_in__int8_grids_out": wall(lambda k: (g.Process_pointcloud2(raw[k], msgs[k].n_points, 48, fr[k][1], fr[k][2]), g.combine_maps_grids())),
+                "host_float64_conversion_the_node_does_first": wall(lambda k: msgs[k].to_xyz_array(), 6),
+            }
+        except Exception as ex:
+            line["e2e_variants_p50_ms"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline()

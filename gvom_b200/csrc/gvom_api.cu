@@ -146,10 +146,13 @@ struct GvomHandle {
     bool prof_process = false, prof_combine = false, prof_x = false;
     int sm_count = 148;
     int grid_index = 0, grid_codes = 0, grid_cells = 0, grid_gather = 0;   // resident grids (set at create)
-    int grid_cells2 = 0, grid_gather2 = 0, grid_gather2b = 0, grid_rows3 = 0, grid_rows6 = 0;
+    int grid_cells2 = 0, grid_gather2 = 0, grid_gather2b = 0, grid_rows3 = 0, grid_rows6 = 0, grid_rows3d = 0;
     GvomStats stats{};
     float last_stage_copy_ms = 0.f;       // host time of the last pageable->pinned staging copy
     CopyPool* pool = nullptr;             // staging threads for pageable input (created on first use)
+    char* dev_base = nullptr;             // device workspace base (direct multi-GPU exchange: peers' slots = peer base + same offsets)
+    const int* done_flags = nullptr;      // direct exchange: peers' "finished reading my slots" flags, checked by the next scan's K2
+    int done_n = 0, done_epoch = 0;
     signed char* grids_dev = nullptr;     // [GVOM_GRID_COUNT][S*S] int8 OccupancyGrid payloads
     signed char* grids_host = nullptr;    // pinned mirror
     unsigned variant = 0;                 // GVOM_VARIANT bit mask: kernel builds kept for A/B measurements (see create)
@@ -291,12 +294,14 @@ void rec(GvomHandle* h, int e, cudaStream_t st) {
 void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs* A) {
     A->n = 0;
     A->use_masks = 1;
+    A->meta = nullptr; A->cox = A->coy = A->coz = 0;
     for (auto& s : h->slots) {
         if (!s.valid) continue;
         SlotRef& r = A->s[A->n++];
         r.map = s.index_map; r.metrics = s.metrics; r.hit = s.hit; r.total = s.total; r.minh = s.minh;
         r.dx = (int)(org[0] - s.origin[0]); r.dy = (int)(org[1] - s.origin[1]); r.dz = (int)(org[2] - s.origin[2]);
         r.is_prev = 0;
+        r.meta = -1;
         r.gmask = s.has_gmask ? s.gmask : nullptr;
         if (!r.gmask) A->use_masks = 0;
     }
@@ -306,6 +311,7 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
         r.map = pc.index_map; r.metrics = pc.metrics; r.hit = pc.hit; r.total = pc.total; r.minh = pc.minh;
         r.dx = (int)(org[0] - pc.origin[0]); r.dy = (int)(org[1] - pc.origin[1]); r.dz = (int)(org[2] - pc.origin[2]);
         r.is_prev = 1;
+        r.meta = -1;
         r.gmask = pc.has_gmask ? pc.gmask : nullptr;
         if (!r.gmask) A->use_masks = 0;
     }
@@ -315,9 +321,9 @@ template <int MODE>
 void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStream_t st) {
     if (MODE == MERGE_FULL && h->p.xy_size % 256 == 0 && A.use_masks && O.gmask && !(h->variant & VAR_OLD_MERGE)) {
         if (h->variant & VAR_MERGE_NB6)
-            launch(k_merge_rows<6>, dim3(h->grid_rows6), dim3(256), 0, st, A, O, h->dp);
+            launch(k_merge_rows<6, false>, dim3(h->grid_rows6), dim3(256), 0, st, A, O, h->dp);
         else
-            launch(k_merge_rows<3>, dim3(h->grid_rows3), dim3(256), 0, st, A, O, h->dp);
+            launch(k_merge_rows<3, false>, dim3(h->grid_rows3), dim3(256), 0, st, A, O, h->dp);
         h->stats.kernel_launches++;
         return;
     }
@@ -355,7 +361,7 @@ void launch_cells(GvomHandle* h, const MergeArgs& A, Combined& c, cudaStream_t s
         launch(k_merge_cells, dim3(h->grid_cells), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
                                                       h->dp, (int)h->ccap);
     else
-        launch(k_merge_cells2, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
+        launch(k_merge_cells2<false>, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
                                                        h->dp, (int)h->ccap);
 }
 
@@ -519,6 +525,7 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
     CUDA_TRY(cudaSetDevice(device));
     GvomHandle* h = new GvomHandle();
     h->device = device;
+    h->dev_base = static_cast<char*>(device_ws);
     fill_sizes(h, p, max_points, max_combined_cells);
     size_t hb = 0;
     const size_t db = carve(h, device_ws, host_ws, &hb);
@@ -543,13 +550,14 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
                            : s4 ? resident_grid(k_merge_codes<4, MERGE_FINISH>, 256, h->sm_count)
                                 : resident_grid(k_merge_codes<1, MERGE_FINISH>, 256, h->sm_count);
         h->grid_cells = resident_grid(k_merge_cells, 128, h->sm_count);
-        h->grid_cells2 = resident_grid(k_merge_cells2, 128, h->sm_count);
+        h->grid_cells2 = resident_grid(k_merge_cells2<false>, 128, h->sm_count);
         h->grid_gather2 = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics2<1, 1, 3>, 256, h->sm_count)
                                                                           : resident_grid(k_gather_metrics2<-1, -1, 3>, 256, h->sm_count);
         h->grid_gather2b = resident_grid(k_gather_metrics2<1, 1, 2>, 256, h->sm_count);
         if (const char* m = getenv("GVOM_VARIANT")) h->variant = (unsigned)strtoul(m, nullptr, 0);
-        h->grid_rows3 = resident_grid(k_merge_rows<3>, 256, h->sm_count);
-        h->grid_rows6 = resident_grid(k_merge_rows<6>, 256, h->sm_count);
+        h->grid_rows3 = resident_grid(k_merge_rows<3, false>, 256, h->sm_count);
+        h->grid_rows6 = resident_grid(k_merge_rows<6, false>, 256, h->sm_count);
+        h->grid_rows3d = resident_grid(k_merge_rows<3, true>, 256, h->sm_count);
         h->grid_gather = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics<1, 1>, 256, h->sm_count)
                                                                          : resident_grid(k_gather_metrics<-1, -1>, 256, h->sm_count);
     }
@@ -770,15 +778,15 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
     rec(h, EV_RAYCAST, st);
     if (h->p.xy_size % 8 == 0) {
         launch(k_build_index<8>, dim3(h->grid_index), dim3(256), 0, st, h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
-                                                         s.cell_voxel, h->acc, s.minh, h->V, cap, s.gmask);
+                                                         s.cell_voxel, h->acc, s.minh, h->V, cap, s.gmask, h->done_flags, h->done_n, h->done_epoch);
         s.has_gmask = true;
     } else {
         if (h->V % 4 == 0)
             launch(k_build_index<4>, dim3(h->grid_index), dim3(256), 0, st, h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
-                                                             s.cell_voxel, h->acc, s.minh, h->V, cap, nullptr);
+                                                             s.cell_voxel, h->acc, s.minh, h->V, cap, (unsigned*)nullptr, h->done_flags, h->done_n, h->done_epoch);
         else
             launch(k_build_index<1>, dim3(h->grid_index), dim3(256), 0, st, h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
-                                                             s.cell_voxel, h->acc, s.minh, h->V, cap, nullptr);
+                                                             s.cell_voxel, h->acc, s.minh, h->V, cap, (unsigned*)nullptr, h->done_flags, h->done_n, h->done_epoch);
         s.has_gmask = false;
     }
     h->stats.kernel_launches++;
@@ -1328,6 +1336,136 @@ int gvom_bench_atomics(int device, void* table_dev, int64_t table_words, int32_t
     cudaEventDestroy(b);
     *best_ms = best;
     if (atomics_per_launch) *atomics_per_launch = (int64_t)blocks * 256 * per_thread;
+    return GVOM_OK;
+}
+
+// ------------------------------------------------------------- multi-GPU, direct exchange
+// Every rank's device workspace is mapped into every other rank (torch symmetric memory) and carved identically,
+// so a peer's ring slot is `peer base + the offset of my own slot`.  combine_maps then is the single-GPU combine
+// over ALL ranks' slots, read in place over NVLink by the same two kernels (row merge, cell merge): one pass
+// instead of partial + exchange + finish, results identical to one Gvom holding every rank's slots in rank order.
+// Protocol per combine `epoch` (no host synchronisation, no collective launch):
+//   publish : k_publish_slots writes this rank's slot table (valid, origin) into every rank's copy, then its
+//             "ready" flag = epoch                                   (after this rank's scan kernels, stream order)
+//   merge   : the row-merge kernel waits for all ready flags, then reads every slot in place
+//   done    : after the cell merge (the last reader of peer memory) k_signal writes the "done" flag = epoch into
+//             every rank; a rank's next scan waits for all done flags inside K2 before it overwrites a slot
+static int publish_slots_locked(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, cudaStream_t st) {
+    const int B = h->p.buffer_size, R = pl->nranks;
+    PublishArgs P{};
+    P.n = B; P.nranks = R;
+    for (int i = 0; i < B; ++i) {
+        const Slot& s = h->slots[i];
+        P.m[i].valid = s.valid ? 1 : 0;
+        P.m[i].ox = (int)s.origin[0]; P.m[i].oy = (int)s.origin[1]; P.m[i].oz = (int)s.origin[2];
+        P.m[i].newest = (s.valid && i == h->last_buffer_index) ? 1 : 0;
+    }
+    for (int r = 0; r < R; ++r) {
+        if (!pl->meta_rows[r] || !pl->ready_slots[r] || !pl->done_slots[r] || !pl->peer_ws[r]) return fail(GVOM_EINVAL, "NULL peer pointer");
+        P.row[r] = reinterpret_cast<SlotMeta*>(pl->meta_rows[r]);
+        P.flag[r] = pl->ready_slots[r];
+    }
+    launch(k_publish_slots, dim3(1), dim3(64), 0, st, P, (int)epoch);
+    h->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GVOM_OK;
+}
+
+static int check_links(GvomHandle* h, const GvomPeerLinks* pl) {
+    if (!h || !pl) return fail(GVOM_EINVAL, "NULL argument");
+    if (pl->nranks < 1 || pl->nranks > MAX_RANKS || pl->rank < 0 || pl->rank >= pl->nranks) return fail(GVOM_EINVAL, "bad rank / nranks");
+    if ((int64_t)pl->nranks * h->p.buffer_size > MAX_SLOTS) return fail(GVOM_EINVAL, "nranks * buffer_size must be <= 64");
+    if (h->p.xy_size % 256 != 0) return fail(GVOM_EINVAL, "direct exchange needs xy_size % 256 == 0");
+    if (!pl->meta_table || !pl->ready_flags || !pl->done_flags) return fail(GVOM_EINVAL, "NULL table / flags");
+    return GVOM_OK;
+}
+
+int gvom_publish_slots(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, void* stream) {
+    if (int e = check_links(h, pl)) return e;
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->active = st;
+    return publish_slots_locked(h, pl, epoch, st);
+}
+
+int gvom_combine_maps_direct(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, double origin[3], int32_t* positive,
+                             int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
+    if (int e = check_links(h, pl)) return e;
+    if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE && out_mem != GVOM_NONE) return fail(GVOM_EINVAL, "bad out_mem");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (int e = finish_outputs(h)) return e;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->active = st;
+    const int B = h->p.buffer_size, R = pl->nranks;
+    Slot& newest = h->slots[h->last_buffer_index];
+    // the combined origin: this rank's newest scan, or (a rank that has no scan yet) the origin the caller passes in
+    double org[3];
+    if (newest.valid) { for (int k = 0; k < 3; ++k) org[k] = newest.origin[k]; }
+    else if (origin && origin[0] == origin[0]) { for (int k = 0; k < 3; ++k) org[k] = origin[k]; }
+    else return GVOM_NO_DATA;
+    rec(h, EV_CSTART, st);
+    if (int e = publish_slots_locked(h, pl, epoch, st)) return e;
+    // sources: every rank's slots in rank order (own slots through own pointers), then my previous combined map
+    MergeArgs A;
+    A.n = 0; A.use_masks = 1;
+    A.meta = reinterpret_cast<const SlotMeta*>(pl->meta_table);
+    A.cox = (int)org[0]; A.coy = (int)org[1]; A.coz = (int)org[2];
+    for (int r = 0; r < R; ++r) {
+        const char* base = static_cast<const char*>(pl->peer_ws[r]);
+        auto at = [&](const void* mine) { return base + (static_cast<const char*>(mine) - h->dev_base); };
+        for (int i = 0; i < B; ++i) {
+            const Slot& s = h->slots[i];
+            SlotRef& q = A.s[A.n++];
+            q = SlotRef{};
+            q.map = reinterpret_cast<const int*>(at(s.index_map));
+            q.metrics = at(s.metrics);
+            q.hit = reinterpret_cast<const int*>(at(s.hit));
+            q.total = reinterpret_cast<const int*>(at(s.total));
+            q.minh = reinterpret_cast<const float*>(at(s.minh));
+            q.gmask = reinterpret_cast<const unsigned*>(at(s.gmask));
+            q.is_prev = 0;
+            q.meta = r * MAX_SLOTS + i;
+        }
+    }
+    Combined& pc = h->comb[h->cur];
+    if (pc.valid) {
+        SlotRef& q = A.s[A.n++];
+        q = SlotRef{};
+        q.map = pc.index_map; q.metrics = pc.metrics; q.hit = pc.hit; q.total = pc.total; q.minh = pc.minh;
+        q.dx = (int)(org[0] - pc.origin[0]); q.dy = (int)(org[1] - pc.origin[1]); q.dz = (int)(org[2] - pc.origin[2]);
+        q.is_prev = 1; q.meta = -1;
+        q.gmask = pc.gmask;
+    }
+    Combined& c = h->comb[1 - h->cur];
+    for (int k = 0; k < 3; ++k) c.origin[k] = org[k];
+    {
+        MergeOut O{};
+        O.cmap = c.index_map; O.counter = h->flags + 1; O.cell_voxel = c.cell_voxel;
+        O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
+        O.gmask = c.gmask; O.cap = (int)h->ccap;
+        O.wait_flags = pl->ready_flags; O.wait_n = R; O.wait_epoch = epoch;
+        launch(k_merge_rows<3, true>, dim3(h->grid_rows3d), dim3(256), 0, st, A, O, h->dp);
+    }
+    rec(h, EV_CODES, st);
+    launch(k_merge_cells2<true>, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics,
+                                                          c.eig, h->dp, (int)h->ccap);
+    {   // last reader of peer memory is done: tell every rank
+        SignalSet S; S.n = R;
+        for (int r = 0; r < R; ++r) S.slot[r] = pl->done_slots[r];
+        launch(k_signal, dim3(1), dim3(32), 0, st, S, (int)epoch);
+    }
+    rec(h, EV_CELLS, st);
+    h->stats.kernel_launches += 3;
+    h->prof_combine = h->profiling;
+    c.has_gmask = true;
+    h->done_flags = pl->done_flags; h->done_n = R; h->done_epoch = epoch;   // checked by the next scan's K2
+    if (int e = enqueue_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st)) return e;
+    if (int e = finish_outputs(h)) return e;
+    c.valid = true;
+    h->cur = 1 - h->cur;
+    h->stats.combine_calls++;
     return GVOM_OK;
 }
 

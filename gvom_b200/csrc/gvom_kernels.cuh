@@ -29,6 +29,21 @@ __device__ __forceinline__ void pdl_wait() {
     cudaGridDependencySynchronize();
 #endif
 }
+// device-side barrier of the peer-to-peer exchanges, folded into the consumer kernel: every block waits until all
+// ranks' flag slots (written by their signal kernels after a system-scope fence) have reached `epoch`
+__device__ __forceinline__ void wait_flags_block(const int* flags, int n, int epoch) {
+    if (flags) {
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < n; ++k) {
+                const volatile int* f = flags + k;
+                while (*f < epoch) __nanosleep(100);
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+}
+
 constexpr int MAX_SLOTS = 64;   // ring-buffer slots a single merge pass can take
 constexpr int ACC = 20;         // per-cell accumulators: [0..9] own voxel, [10..19] apron
 
@@ -319,8 +334,12 @@ __global__ void __launch_bounds__(256)
 k_build_index(int* __restrict__ hit, int* __restrict__ total, int* __restrict__ index_map,
               int* __restrict__ counter, int* __restrict__ hit_c, int* __restrict__ total_c,
               int* __restrict__ cell_voxel, double* __restrict__ acc, float* __restrict__ minh,
-              long long V, int cap, unsigned* __restrict__ gmask) {
+              long long V, int cap, unsigned* __restrict__ gmask,
+              const int* __restrict__ wait_flags, int wait_n, int wait_epoch) {
     pdl_wait();
+    // direct multi-GPU exchange: peers read this rank's slots in place; do not overwrite one before every rank has
+    // finished the combine that read it
+    wait_flags_block(wait_flags, wait_n, wait_epoch);
     constexpr int U = 2;                                // items in flight per thread
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -711,12 +730,28 @@ struct SlotRef {
     int dx, dy, dz;          // combined_origin - source_origin, voxels
     int is_prev;             // 1: previous combined map (float32 metrics, [-11,-1] rule)
     const unsigned* gmask;   // one bit per 8-voxel group: something known in the group (NULL: no mask)
+    int meta;                // >= 0: validity and origin come from MergeArgs.meta[meta] (a peer rank's slot), dx/dy/dz unused
 };
+// What a rank publishes about one of its ring slots for the direct multi-GPU exchange (written into every
+// rank's table before the rank's "ready" flag; origins are integral voxel units, |origin| < 1e9).
+struct SlotMeta { int valid, ox, oy, oz, newest, pad0, pad1, pad2; };
 struct MergeArgs {
     SlotRef s[MAX_SLOTS + 1];
     int n;
     int use_masks;           // every source carries a group mask
+    const SlotMeta* meta;    // direct exchange: table of all ranks' slots (local copy), else NULL
+    int cox, coy, coz;       // direct exchange: combined origin (the shifts are formed on the device)
 };
+
+// shift of source k into the combined frame; false = the source holds nothing (direct exchange: slot not valid)
+template <bool DIRECT>
+__device__ __forceinline__ bool src_shift(const MergeArgs& A, int k, int& dx, int& dy, int& dz) {
+    const SlotRef& s = A.s[k];
+    if (!DIRECT || s.meta < 0) { dx = s.dx; dy = s.dy; dz = s.dz; return true; }
+    const int4 m = __ldcg(reinterpret_cast<const int4*>(A.meta + s.meta));     // {valid, ox, oy, oz}
+    dx = A.cox - m.y; dy = A.coy - m.z; dz = A.coz - m.w;
+    return m.x != 0;
+}
 
 // ---------------------------------------------------------------------------
 // C1  merged code per voxel.  Result of __combine_indices run once per slot in
@@ -1025,10 +1060,11 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
 //     buffer's own group mask says it already holds "unknown" there (both combined-map buffers start as all
 //     unknown with an empty mask, and every writer keeps map and mask consistent).
 // ---------------------------------------------------------------------------
-template <int NB>
+template <int NB, bool DIRECT>
 __global__ void __launch_bounds__(256, (NB > 3) ? 2 : 3)
 k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
     pdl_wait();
+    if (DIRECT) wait_flags_block(O.wait_flags, O.wait_n, O.wait_epoch);   // peers' slots are read in place
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int S = P.S, Z = P.Z;
@@ -1045,9 +1081,11 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
         unsigned word = 0;
         if (k < A.n) {
             const SlotRef& s = A.s[k];
-            const int ys = y + s.dy, zs = z + s.dz;
-            const int wi = ((x0s + s.dx) >> 8) + which;                  // floor: source word of the segment start, +1
-            if ((unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z && wi >= 0 && wi < spr)
+            int dx, dy, dz;
+            const bool valid = src_shift<DIRECT>(A, k, dx, dy, dz);
+            const int ys = y + dy, zs = z + dz;
+            const int wi = ((x0s + dx) >> 8) + which;                    // floor: source word of the segment start, +1
+            if (valid && (unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z && wi >= 0 && wi < spr)
                 word = __ldg(s.gmask + (zs * S + ys) * spr + wi);
         }
         return word;
@@ -1077,13 +1115,15 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
                         const unsigned w0 = __shfl_sync(FULL, word, k - kb), w1 = __shfl_sync(FULL, word, 16 + k - kb);
                         if ((w0 | w1) != 0) {                             // uniform: the source holds something in this segment
                             const SlotRef& s = A.s[k];
-                            const int sx0 = x0s + s.dx;
+                            int dx, dy, dz;
+                            src_shift<DIRECT>(A, k, dx, dy, dz);          // (valid: its mask words are non-zero)
+                            const int sx0 = x0s + dx;
                             const unsigned long long Wd = ((unsigned long long)w1 << 32) | w0;
                             const int b = ((sx0 >> 3) & 31) + lane;       // my first voxel's group, relative to word 0
                             const unsigned m = (sx0 & 7) ? 3u : 1u;       // an unaligned shift straddles two groups
                             if ((unsigned)(Wd >> b) & m) need |= 1u << u;
                             xs[u] = sx0 + 8 * lane;
-                            rowp[u] = s.map + ((z + s.dz) * S + (y + s.dy)) * S;
+                            rowp[u] = s.map + ((z + dz) * S + (y + dy)) * S;
                         }
                     }
                 }
@@ -1322,6 +1362,7 @@ __device__ __forceinline__ void load_cell_rec(const SlotRef& s, int io, CellRec&
     r.hit = s.hit[io]; r.tot = s.total[io]; r.mh = s.minh[io];
 }
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(128, 8)
 k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
                int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
@@ -1345,8 +1386,10 @@ k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restri
                 io[u] = -1;
                 if (k0 + u < A.n) {
                     const SlotRef& s = A.s[k0 + u];
-                    const int xs = x + s.dx, ys = y + s.dy, zs = z + s.dz;
-                    if ((unsigned)xs < (unsigned)S && (unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z)
+                    int dx, dy, dz;
+                    const bool valid = src_shift<DIRECT>(A, k0 + u, dx, dy, dz);
+                    const int xs = x + dx, ys = y + dy, zs = z + dz;
+                    if (valid && (unsigned)xs < (unsigned)S && (unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z)
                         io[u] = __ldg(s.map + (xs + (ys + zs * S) * S));
                 }
             }
@@ -1979,6 +2022,27 @@ __global__ void k_signal(SignalSet S, int epoch) {
     __threadfence_system();
     if (threadIdx.x < S.n) {
         volatile int* f = S.slot[threadIdx.x];
+        *f = epoch;
+    }
+    __threadfence_system();
+}
+
+// direct exchange: write this rank's slot descriptions into row `rank` of every rank's table, then the ready flag
+struct PublishArgs { SlotMeta m[MAX_SLOTS]; int n; SlotMeta* row[MAX_RANKS]; int* flag[MAX_RANKS]; int nranks; };
+__global__ void k_publish_slots(PublishArgs A, int epoch) {
+    pdl_wait();                                   // after this rank's scan kernels
+    __threadfence_system();
+    for (int r = 0; r < A.nranks; ++r)
+        for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
+            int4* d = reinterpret_cast<int4*>(A.row[r] + i);
+            const SlotMeta& m = A.m[i];
+            d[0] = make_int4(m.valid, m.ox, m.oy, m.oz);
+            d[1] = make_int4(m.newest, 0, 0, 0);
+        }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < A.nranks) {
+        volatile int* f = A.flag[threadIdx.x];
         *f = epoch;
     }
     __threadfence_system();

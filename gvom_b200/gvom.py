@@ -77,7 +77,7 @@ class Gvom:
         check(self._L.gvom_workspace_size(C.byref(self._P), self.max_points, int(max_combined_cells),
                                           C.byref(db), C.byref(hb)), "gvom_workspace_size")
         # torch owns the memory; raw pointers cross the ABI
-        self._dev_ws = torch.empty(db.value, dtype=torch.uint8, device=f"cuda:{self.device}")
+        self._dev_ws = self._alloc_device_ws(db.value)
         self._host_ws = torch.empty(hb.value, dtype=torch.uint8, pin_memory=True)
         h = C.c_void_p()
         check(self._L.gvom_create(C.byref(self._P), self.max_points, int(max_combined_cells), self.device,
@@ -86,6 +86,10 @@ class Gvom:
         self._h = h
         self._ego_c = (C.c_double * 3)()
         self._org_c = (C.c_double * 3)()
+
+    def _alloc_device_ws(self, nbytes):
+        """Device workspace (torch owns it).  MultiGpuGvom overrides this to place it in symmetric memory."""
+        return self._torch.empty(nbytes, dtype=self._torch.uint8, device=f"cuda:{self.device}")
 
     def __del__(self):
         try:

@@ -21,6 +21,13 @@ B200, and the exchange happens only at combine time:
      cheaper than broadcasting the result and keeps the "previous combined map"
      state replicated, so any rank can serve the maps.
 
+  "direct" exchange (xy_size % 256 == 0, world * buffer_size <= 64): steps 1-3 collapse into ONE
+  merge.  Every rank's whole device workspace lives in symmetric memory, all handles are carved
+  identically, so a peer's ring slot is `peer base + my slot's offset`; combine_maps is then the
+  single-GPU combine over ALL ranks' slots, read in place over NVLink by the same two kernels
+  (gvom_combine_maps_direct).  Ready / done flags written by tiny kernels into every rank's
+  memory order the accesses; there is no collective call and no host synchronisation.
+
 The result equals a single Gvom holding all ranks' slots: occupancy (OR), pass
 sums, hit/total sums and min heights are order independent in the reference's
 merge rules; moments agree to float32 rounding (tests/test_multi_gpu.py).
@@ -32,7 +39,7 @@ import time
 
 import numpy as np
 
-from ._lib import GVOM_DEVICE, GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, check
+from ._lib import (GVOM_DEVICE, GVOM_HOST, GVOM_NO_DATA, META_ROW_INTS, RECORD_FLOATS, GvomPeerLinks, check)
 from .gvom import Gvom
 
 HEADER_DOUBLES = 8          # [valid, count, ox, oy, oz, pad...]
@@ -62,9 +69,17 @@ class MultiGpuGvom(Gvom):
     (every rank must call it) and returns the same maps on every rank."""
 
     def __init__(self, *args, group=None, torch_stream=None, exchange="auto", sharded="auto", **kw):
+        import os
         import torch
         import torch.distributed as dist
         self._dist, self._group = dist, group
+        exchange = os.environ.get("GVOM_MULTI", exchange)
+        # direct exchange: the device workspace itself must be symmetric memory (see _alloc_device_ws)
+        xy, bs = int(args[2]), int(args[4])
+        self._ws_handle = None
+        self._want_direct = exchange in ("auto", "direct") and xy % 256 == 0 and dist.get_world_size(group) * bs <= 64
+        if exchange == "direct" and not self._want_direct:
+            raise ValueError("exchange='direct' needs xy_size % 256 == 0 and world * buffer_size <= 64")
         if torch_stream is None:
             dev = kw.get("device")
             torch_stream = torch.cuda.Stream(device=torch.cuda.current_device() if dev is None else dev)
@@ -87,7 +102,17 @@ class MultiGpuGvom(Gvom):
         self._sharded = bool(sharded) and self.xy_size % 16 == 0
         ccap = min(self.voxel_count, 4 * self.max_points * (self.buffer_size + 1))
         self._res_cap = int(min(self.voxel_count, max(1 << 18, 4 * ccap // self.world)))
-        if exchange in ("auto", "p2p"):
+        if self._want_direct:
+            # all ranks must have got their workspace from symmetric memory
+            ok = torch.tensor([1 if self._ws_handle is not None else 0], device=self._dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                self._init_direct()
+                self.exchange = "direct"
+                return
+            if exchange == "direct":
+                raise RuntimeError("direct exchange: symmetric memory unavailable: " + getattr(self, "_p2p_error", "?"))
+        if exchange in ("auto", "p2p", "direct"):
             try:
                 self._init_p2p()
                 self.exchange = "p2p"
@@ -101,6 +126,80 @@ class MultiGpuGvom(Gvom):
         if int(ok.item()) == 0:
             self.exchange = "nccl"
             self._init_nccl()
+
+    # ------------------------------------------------------------------ direct exchange
+    def _alloc_device_ws(self, nbytes):
+        if self._want_direct:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                group = self._group if self._group is not None else self._dist.group.WORLD
+                t = symm_mem.empty(nbytes, dtype=self._torch.uint8, device=self._torch.device(f"cuda:{self.device}"))
+                self._ws_handle = symm_mem.rendezvous(t, group)
+                return t
+            except Exception as ex:
+                self._p2p_error = repr(ex)
+                self._ws_handle = None
+        return super()._alloc_device_ws(nbytes)
+
+    def _init_direct(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        torch, dist = self._torch, self._dist
+        group = self._group if self._group is not None else dist.group.WORLD
+        R, me = self.world, self.rank
+        o_ready, o_done = 4 * R * META_ROW_INTS, 4 * R * META_ROW_INTS + 256
+        t = symm_mem.empty(o_done + 256, dtype=torch.uint8, device=self._dev)
+        hdl = symm_mem.rendezvous(t, group)
+        t.zero_()
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        ws = [int(p) for p in self._ws_handle.buffer_ptrs]
+        L = GvomPeerLinks()
+        L.rank, L.nranks = me, R
+        for r in range(R):
+            L.peer_ws[r] = ws[r]
+            L.meta_rows[r] = ptrs[r] + 4 * me * META_ROW_INTS
+            L.ready_slots[r] = ptrs[r] + o_ready + 4 * me
+            L.done_slots[r] = ptrs[r] + o_done + 4 * me
+        L.meta_table, L.ready_flags, L.done_flags = ptrs[me], ptrs[me] + o_ready, ptrs[me] + o_done
+        self._links, self._links_t, self._links_hdl = L, t, hdl
+        self._ready_view = t[o_ready:o_ready + 4 * R].view(torch.int32)
+        self._table_view = t[:o_ready].view(torch.int32).view(R, 64, 8)
+        torch.cuda.synchronize(self._dev)
+        dist.barrier(group=self._group)
+
+    def _combine_direct(self, device_outputs):
+        torch, L = self._torch, self._L
+        epoch = self._calls
+        have = L.gvom_newest_origin(self._h, self._org_in) != GVOM_NO_DATA
+        with torch.cuda.stream(self._tstream):
+            org = self._org_c
+            if have:
+                org[0] = org[1] = org[2] = float("nan")          # "use my newest scan's origin"
+            else:
+                # start-up only: publish my (empty) slot table, wait on the host for the peers' tables and adopt
+                # the origin of the first rank that has data
+                check(L.gvom_publish_slots(self._h, C.byref(self._links), epoch, self._stream), "gvom_publish_slots")
+                self._tstream.synchronize()
+                while int(self._ready_view.min().item()) < epoch:
+                    time.sleep(1e-4)
+                tab = self._table_view.cpu().numpy()
+                origin = None
+                for r in range(self.world):
+                    for i in range(self.buffer_size):
+                        if origin is None and tab[r, i, 0] and tab[r, i, 4]:
+                            origin = tab[r, i, 1:4]
+                if origin is None:
+                    print("ERROR: No data in buffer")
+                    return None
+                for k in range(3):
+                    org[k] = float(origin[k])
+            outs, optr, mem = self._outputs(device_outputs)
+            rc = check(L.gvom_combine_maps_direct(self._h, C.byref(self._links), epoch, org, optr[0], optr[1], optr[2],
+                                                  optr[3], mem, self._stream), "gvom_combine_maps_direct")
+            if rc == GVOM_NO_DATA:
+                print("ERROR: No data in buffer")
+                return None
+        pos, neg, rough, vis = outs
+        return (np.array([org[0], org[1], org[2]]), pos, neg, rough, vis)
 
     # ------------------------------------------------------------------ buffers
     def _layout(self):
@@ -173,6 +272,8 @@ class MultiGpuGvom(Gvom):
 
     def combine_maps(self, device_outputs=False):
         self._calls += 1
+        if self.exchange == "direct":
+            return self._combine_direct(device_outputs)
         if self.exchange == "p2p":
             return self._combine_p2p(device_outputs)
         return self._combine_nccl(device_outputs)

@@ -220,6 +220,33 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
                                 int32_t phases, double origin_out[3], int32_t* positive, int32_t* negative,
                                 double* roughness, int32_t* visibility, int32_t out_mem, void* stream);
 
+/* Direct exchange (peer-to-peer, xy_size % 256 == 0, nranks * buffer_size <= 64): every rank's DEVICE WORKSPACE is
+ * mapped into every other rank (the caller allocates it from symmetric memory and created all handles with the
+ * same parameters and capacities, so they are carved identically) and combine_maps is the single-GPU combine over
+ * ALL ranks' ring slots, read in place over NVLink -- one merge pass instead of partial + exchange + finish, and
+ * the result is that of one Gvom holding every rank's slots in rank order.  All pointers are device pointers as
+ * seen from this rank.  Collective: every rank calls it with the same `epoch` (1, 2, ...). */
+#define GVOM_MAX_RANKS 16
+#define GVOM_META_ROW_INTS (64 * 8)      /* one rank's row of the slot table: 64 slots x 8 int32 */
+typedef struct GvomPeerLinks {
+    int32_t rank, nranks;
+    const void* peer_ws[GVOM_MAX_RANKS];         /* device workspace base of every rank (own included) */
+    int32_t* meta_rows[GVOM_MAX_RANKS];          /* row `rank` of the slot table in every rank's memory (written here) */
+    const int32_t* meta_table;                   /* local slot table: nranks rows of GVOM_META_ROW_INTS int32 */
+    int32_t* ready_slots[GVOM_MAX_RANKS];        /* this rank's "slots published" flag in every rank's memory */
+    const int32_t* ready_flags;                  /* local: nranks flags */
+    int32_t* done_slots[GVOM_MAX_RANKS];         /* this rank's "finished reading" flag in every rank's memory */
+    const int32_t* done_flags;                   /* local: nranks flags */
+} GvomPeerLinks;
+/* origin: out (world origin of the combined map); in for a rank that has no scan yet: the combined origin in voxel
+ * units adopted from a peer (NaN = none -> GVOM_NO_DATA). */
+/* Only the first step of gvom_combine_maps_direct (write this rank's slot table + ready flag = epoch); used by a rank
+ * that has no scan yet and must learn the combined origin from its peers before it can merge.  Idempotent. */
+int gvom_publish_slots(GvomHandle* h, const GvomPeerLinks* links, int32_t epoch, void* stream);
+int gvom_combine_maps_direct(GvomHandle* h, const GvomPeerLinks* links, int32_t epoch, double origin[3],
+                             int32_t* positive, int32_t* negative, double* roughness, int32_t* visibility,
+                             int32_t out_mem, void* stream);
+
 /* ---- test / tooling hooks (canonical parity dumps; not on the hot path) ---- */
 int gvom_slot_info(GvomHandle* h, int32_t slot, int32_t* valid, int64_t* cells, double origin[3]);
 int gvom_last_slot(GvomHandle* h, int32_t* slot);
