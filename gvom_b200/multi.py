@@ -77,7 +77,11 @@ class MultiGpuGvom(Gvom):
         # direct exchange: the device workspace itself must be symmetric memory (see _alloc_device_ws)
         xy, bs = int(args[2]), int(args[4])
         self._ws_handle = None
-        self._want_direct = exchange in ("auto", "direct") and xy % 256 == 0 and dist.get_world_size(group) * bs <= 64
+        # measured on 2x B200 (profiles/bench_r01_n2_direct_vs_p2p.json): reading the peers' slots in place makes every
+        # dependent access of the merge an NVLink round trip (row merge 91 us, cell merge 97 us against 31 / 20 us
+        # locally), slower than exchanging pre-merged grids + compact records (276 vs 310 us per step) -- so "auto"
+        # keeps the p2p exchange and the direct one is opt-in
+        self._want_direct = exchange == "direct" and xy % 256 == 0 and dist.get_world_size(group) * bs <= 64
         if exchange == "direct" and not self._want_direct:
             raise ValueError("exchange='direct' needs xy_size % 256 == 0 and world * buffer_size <= 64")
         if torch_stream is None:
