@@ -57,6 +57,7 @@ struct Slot {
     bool has_gmask = false;
     double origin[3] = {0, 0, 0};
     bool valid = false;
+    int64_t seq = 0;              // scan counter when the slot was written (pull exchange: is a mirror current?)
 };
 
 struct Combined {
@@ -813,6 +814,7 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
     // gvom.py:198-216
     for (int k = 0; k < 3; ++k) s.origin[k] = fr.origin[k];
     s.valid = true;
+    s.seq = h->stats.process_calls + 1;
     h->last_buffer_index = h->buffer_index;
     h->buffer_index = (h->buffer_index + 1) % p.buffer_size;
     h->stats.process_calls++;
@@ -1276,6 +1278,7 @@ int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes) {
         Slot& s = h->slots[i];
         s.valid = H.slot_valid[i] != 0;
         s.has_gmask = s.valid && (h->p.xy_size % 8 == 0);
+        s.seq = s.valid ? h->stats.process_calls + 1000 + i : 0;   // a fresh scan counter: mirrors of the old content are stale
         for (int k = 0; k < 3; ++k) s.origin[k] = H.slot_origin[i][k];
     }
     h->cur = 0;
@@ -1359,6 +1362,7 @@ static int publish_slots_locked(GvomHandle* h, const GvomPeerLinks* pl, int32_t 
         P.m[i].valid = s.valid ? 1 : 0;
         P.m[i].ox = (int)s.origin[0]; P.m[i].oy = (int)s.origin[1]; P.m[i].oz = (int)s.origin[2];
         P.m[i].newest = (s.valid && i == h->last_buffer_index) ? 1 : 0;
+        P.m[i].seq = (int)s.seq;
     }
     for (int r = 0; r < R; ++r) {
         if (!pl->meta_rows[r] || !pl->ready_slots[r] || !pl->done_slots[r] || !pl->peer_ws[r]) return fail(GVOM_EINVAL, "NULL peer pointer");
@@ -1389,16 +1393,33 @@ int gvom_publish_slots(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, vo
     return publish_slots_locked(h, pl, epoch, st);
 }
 
-int gvom_combine_maps_direct(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, double origin[3], int32_t* positive,
-                             int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
+static int64_t slot_stride_bytes(GvomHandle* h) {
+    if (h->p.buffer_size >= 2) return (const char*)h->slots[1].index_map - (const char*)h->slots[0].index_map;
+    const Slot& s = h->slots[0];
+    const int64_t end = ((const char*)s.gmask - (const char*)s.index_map) + (int64_t)sizeof(unsigned) * (h->V / 256 + 2);
+    return (end + 255) & ~int64_t(255);
+}
+
+int gvom_mirror_size(GvomHandle* h, int32_t nranks, uint64_t* bytes) {
+    if (!h || !bytes || nranks < 1 || nranks > MAX_RANKS) return fail(GVOM_EINVAL, "bad argument");
+    *bytes = (uint64_t)slot_stride_bytes(h) * (uint64_t)h->p.buffer_size * (uint64_t)nranks + 256;
+    return GVOM_OK;
+}
+
+// direct (pull = false) and pull exchange share everything but where the peers' slots are read from
+static int combine_peers(GvomHandle* h, const GvomPeerLinks* pl, bool pull, int32_t epoch, double origin[3], int32_t* positive,
+                         int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
     if (int e = check_links(h, pl)) return e;
     if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE && out_mem != GVOM_NONE) return fail(GVOM_EINVAL, "bad out_mem");
+    const int B = h->p.buffer_size, R = pl->nranks;
+    const int64_t stride = slot_stride_bytes(h);
+    if (pull && (!pl->mirror || !pl->mirror_seq || !pl->meta_snapshot || pl->mirror_bytes < (uint64_t)stride * B * R))
+        return fail(GVOM_EINVAL, "pull exchange: mirror buffers missing or too small (gvom_mirror_size)");
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
     if (int e = finish_outputs(h)) return e;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->active = st;
-    const int B = h->p.buffer_size, R = pl->nranks;
     Slot& newest = h->slots[h->last_buffer_index];
     // the combined origin: this rank's newest scan, or (a rank that has no scan yet) the origin the caller passes in
     double org[3];
@@ -1407,16 +1428,40 @@ int gvom_combine_maps_direct(GvomHandle* h, const GvomPeerLinks* pl, int32_t epo
     else return GVOM_NO_DATA;
     rec(h, EV_CSTART, st);
     if (int e = publish_slots_locked(h, pl, epoch, st)) return e;
+    SignalSet done; done.n = R;
+    for (int r = 0; r < R; ++r) done.slot[r] = pl->done_slots[r];
+    if (pull) {
+        PullArgs PA{};
+        for (int r = 0; r < R; ++r) PA.peer_ws[r] = static_cast<const char*>(pl->peer_ws[r]);
+        PA.mirror = static_cast<char*>(pl->mirror);
+        const Slot& s0 = h->slots[0];
+        auto off = [&](const void* p) { return (long long)((const char*)p - (const char*)s0.index_map); };
+        PA.slot0 = (const char*)s0.index_map - h->dev_base; PA.slot_stride = stride;
+        PA.off_hit = off(s0.hit); PA.off_total = off(s0.total); PA.off_metrics = off(s0.metrics); PA.off_minh = off(s0.minh);
+        PA.off_counter = off(s0.counter); PA.off_gmask = off(s0.gmask);
+        PA.table = reinterpret_cast<const SlotMeta*>(pl->meta_table);
+        PA.snapshot = reinterpret_cast<SlotMeta*>(pl->meta_snapshot);
+        PA.mirror_seq = pl->mirror_seq; PA.ready_flags = pl->ready_flags;
+        PA.rank = pl->rank; PA.nranks = R; PA.B = B; PA.epoch = epoch;
+        PA.nseg = (int)(h->V >> 8); PA.cap = h->cap;
+        launch(k_pull_slots, dim3(h->sm_count * 8), dim3(256), 0, st, PA);
+        launch(k_pull_finish, dim3(1), dim3(256), 0, st, PA, done);
+        h->stats.kernel_launches += 2;
+    }
     // sources: every rank's slots in rank order (own slots through own pointers), then my previous combined map
     MergeArgs A;
     A.n = 0; A.use_masks = 1;
-    A.meta = reinterpret_cast<const SlotMeta*>(pl->meta_table);
+    A.meta = reinterpret_cast<const SlotMeta*>(pull ? pl->meta_snapshot : pl->meta_table);
     A.cox = (int)org[0]; A.coy = (int)org[1]; A.coz = (int)org[2];
     for (int r = 0; r < R; ++r) {
-        const char* base = static_cast<const char*>(pl->peer_ws[r]);
-        auto at = [&](const void* mine) { return base + (static_cast<const char*>(mine) - h->dev_base); };
         for (int i = 0; i < B; ++i) {
             const Slot& s = h->slots[i];
+            // a peer's slot i: same offsets inside the peer's workspace (direct) or inside my mirror block (pull)
+            const char* mine = (const char*)s.index_map;
+            const char* base = r == pl->rank ? mine
+                             : pull ? static_cast<const char*>(pl->mirror) + ((int64_t)r * B + i) * stride
+                                    : static_cast<const char*>(pl->peer_ws[r]) + (mine - h->dev_base);
+            auto at = [&](const void* p) { return base + ((const char*)p - mine); };
             SlotRef& q = A.s[A.n++];
             q = SlotRef{};
             q.map = reinterpret_cast<const int*>(at(s.index_map));
@@ -1445,19 +1490,18 @@ int gvom_combine_maps_direct(GvomHandle* h, const GvomPeerLinks* pl, int32_t epo
         O.cmap = c.index_map; O.counter = h->flags + 1; O.cell_voxel = c.cell_voxel;
         O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
         O.gmask = c.gmask; O.cap = (int)h->ccap;
-        O.wait_flags = pl->ready_flags; O.wait_n = R; O.wait_epoch = epoch;
+        if (!pull) { O.wait_flags = pl->ready_flags; O.wait_n = R; O.wait_epoch = epoch; }   // (the pull kernel has waited)
         launch(k_merge_rows<3, true>, dim3(h->grid_rows3d), dim3(256), 0, st, A, O, h->dp);
     }
     rec(h, EV_CODES, st);
     launch(k_merge_cells2<true>, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics,
                                                           c.eig, h->dp, (int)h->ccap);
-    {   // last reader of peer memory is done: tell every rank
-        SignalSet S; S.n = R;
-        for (int r = 0; r < R; ++r) S.slot[r] = pl->done_slots[r];
-        launch(k_signal, dim3(1), dim3(32), 0, st, S, (int)epoch);
+    h->stats.kernel_launches += 2;
+    if (!pull) {   // last reader of peer memory is done: tell every rank
+        launch(k_signal, dim3(1), dim3(32), 0, st, done, (int)epoch);
+        h->stats.kernel_launches++;
     }
     rec(h, EV_CELLS, st);
-    h->stats.kernel_launches += 3;
     h->prof_combine = h->profiling;
     c.has_gmask = true;
     h->done_flags = pl->done_flags; h->done_n = R; h->done_epoch = epoch;   // checked by the next scan's K2
@@ -1467,6 +1511,16 @@ int gvom_combine_maps_direct(GvomHandle* h, const GvomPeerLinks* pl, int32_t epo
     h->cur = 1 - h->cur;
     h->stats.combine_calls++;
     return GVOM_OK;
+}
+
+int gvom_combine_maps_direct(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, double origin[3], int32_t* positive,
+                             int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
+    return combine_peers(h, pl, false, epoch, origin, positive, negative, roughness, visibility, out_mem, stream);
+}
+
+int gvom_combine_maps_pull(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, double origin[3], int32_t* positive,
+                           int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
+    return combine_peers(h, pl, true, epoch, origin, positive, negative, roughness, visibility, out_mem, stream);
 }
 
 // ------------------------------------------------------------- multi-GPU

@@ -734,7 +734,7 @@ struct SlotRef {
 };
 // What a rank publishes about one of its ring slots for the direct multi-GPU exchange (written into every
 // rank's table before the rank's "ready" flag; origins are integral voxel units, |origin| < 1e9).
-struct SlotMeta { int valid, ox, oy, oz, newest, pad0, pad1, pad2; };
+struct SlotMeta { int valid, ox, oy, oz, newest, seq, pad1, pad2; };   // seq: scan counter of the rank when the slot was written
 struct MergeArgs {
     SlotRef s[MAX_SLOTS + 1];
     int n;
@@ -2037,13 +2037,101 @@ __global__ void k_publish_slots(PublishArgs A, int epoch) {
             int4* d = reinterpret_cast<int4*>(A.row[r] + i);
             const SlotMeta& m = A.m[i];
             d[0] = make_int4(m.valid, m.ox, m.oy, m.oz);
-            d[1] = make_int4(m.newest, 0, 0, 0);
+            d[1] = make_int4(m.newest, m.seq, 0, 0);
         }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < A.nranks) {
         volatile int* f = A.flag[threadIdx.x];
         *f = epoch;
+    }
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------
+// "pull" exchange: instead of reading the peers' slots in place (every dependent access an NVLink round trip), each
+// rank keeps a MIRROR of every peer's ring slots in its own HBM and refreshes, once per combine, only the slots
+// whose scan counter changed -- one bulk, coalesced, mask-aware copy over NVLink (a 256-voxel segment is fetched
+// only if the peer's group mask says it holds anything; it is cleared only if the mirror held something) -- and then
+// runs the ordinary single-GPU combine over own slots + mirrors.
+// ---------------------------------------------------------------------------
+struct PullArgs {
+    const char* peer_ws[MAX_RANKS];   // device workspace base of every rank
+    char* mirror;                     // [nranks][B] slot blocks (same internal layout as a slot in the workspace)
+    long long slot0, slot_stride;     // offset of slot 0 in a workspace, distance between slots
+    long long off_hit, off_total, off_metrics, off_minh, off_counter, off_gmask;   // inside a slot block (index map at 0)
+    const SlotMeta* table;            // local table all ranks publish into
+    SlotMeta* snapshot;               // private copy the merge kernels read (peers may republish while they run)
+    int* mirror_seq;                  // [nranks*MAX_SLOTS] scan counter of the mirrored copy (0: nothing mirrored)
+    const int* ready_flags;
+    int rank, nranks, B, epoch;
+    int nseg;                         // V / 256
+    long long cap;                    // cells a slot can hold
+};
+
+__global__ void __launch_bounds__(256)
+k_pull_slots(PullArgs A) {
+    pdl_wait();
+    wait_flags_block(A.ready_flags, A.nranks, A.epoch);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+    if (blockIdx.x == 0)                                  // snapshot of the whole table (own row included)
+        for (int i = threadIdx.x; i < A.nranks * MAX_SLOTS * 2; i += blockDim.x)
+            reinterpret_cast<int4*>(A.snapshot)[i] = __ldcg(reinterpret_cast<const int4*>(A.table) + i);
+    for (int r = 0; r < A.nranks; ++r) {
+        if (r == A.rank) continue;
+        for (int i = 0; i < A.B; ++i) {
+            const int4 m0 = __ldcg(reinterpret_cast<const int4*>(A.table + r * MAX_SLOTS + i));
+            const int4 m1 = __ldcg(reinterpret_cast<const int4*>(A.table + r * MAX_SLOTS + i) + 1);
+            const int seq = m1.y;
+            if (!m0.x || seq == A.mirror_seq[r * MAX_SLOTS + i]) continue;      // invalid or already mirrored (uniform)
+            const char* src = A.peer_ws[r] + A.slot0 + (long long)i * A.slot_stride;
+            char* dst = A.mirror + ((long long)r * A.B + i) * A.slot_stride;
+            // index map + group mask, one warp per 256-voxel segment
+            const unsigned* sg = reinterpret_cast<const unsigned*>(src + A.off_gmask);
+            unsigned* dg = reinterpret_cast<unsigned*>(dst + A.off_gmask);
+            const bool had = A.mirror_seq[r * MAX_SLOTS + i] != 0;
+            for (int seg = warp; seg < A.nseg; seg += warps) {
+                const unsigned w = __ldg(sg + seg);
+                const unsigned old = had ? dg[seg] : 0xffffffffu;                // first fill: the mirror holds garbage
+                int4* d = reinterpret_cast<int4*>(dst) + (long long)seg * 64 + lane * 2;
+                if (w) {
+                    const int4* q = reinterpret_cast<const int4*>(src) + (long long)seg * 64 + lane * 2;
+                    const int4 a = __ldg(q), b = __ldg(q + 1);
+                    d[0] = a; d[1] = b;
+                } else if (old) {
+                    d[0] = make_int4(-1, -1, -1, -1); d[1] = make_int4(-1, -1, -1, -1);
+                }
+                if (lane == 0 && (w | old)) dg[seg] = w;
+            }
+            // compact arrays, truncated to the slot's cell count
+            const long long n = min((long long)__ldg(reinterpret_cast<const int*>(src + A.off_counter)), A.cap);
+            const long long offs[4] = {A.off_hit, A.off_total, A.off_minh, A.off_metrics};
+            const long long bytes[4] = {4 * n, 4 * n, 4 * n, 80 * n};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const long long units = (bytes[a] + 15) >> 4;                   // arrays are 256-byte aligned: whole 16-byte units
+                const int4* q = reinterpret_cast<const int4*>(src + offs[a]);
+                int4* d = reinterpret_cast<int4*>(dst + offs[a]);
+                for (long long u = tid; u < units; u += nthreads) d[u] = __ldg(q + u);
+            }
+        }
+    }
+}
+
+// after the pull: remember what is mirrored, then tell every rank this one no longer needs their slots
+__global__ void k_pull_finish(PullArgs A, SignalSet done) {
+    pdl_wait();
+    for (int k = threadIdx.x; k < A.nranks * MAX_SLOTS; k += blockDim.x) {
+        const int r = k / MAX_SLOTS, i = k % MAX_SLOTS;
+        if (r != A.rank && i < A.B && A.snapshot[k].valid) A.mirror_seq[k] = A.snapshot[k].seq;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < done.n) {
+        volatile int* f = done.slot[threadIdx.x];
+        *f = A.epoch;
     }
     __threadfence_system();
 }

@@ -81,9 +81,12 @@ class MultiGpuGvom(Gvom):
         # dependent access of the merge an NVLink round trip (row merge 91 us, cell merge 97 us against 31 / 20 us
         # locally), slower than exchanging pre-merged grids + compact records (276 vs 310 us per step) -- so "auto"
         # keeps the p2p exchange and the direct one is opt-in
-        self._want_direct = exchange == "direct" and xy % 256 == 0 and dist.get_world_size(group) * bs <= 64
-        if exchange == "direct" and not self._want_direct:
-            raise ValueError("exchange='direct' needs xy_size % 256 == 0 and world * buffer_size <= 64")
+        # The "pull" exchange keeps the direct protocol but mirrors the peers' changed slots with one bulk copy per
+        # combine and merges from local memory.
+        self._want_direct = exchange in ("direct", "pull") and xy % 256 == 0 and dist.get_world_size(group) * bs <= 64
+        self._pull = exchange == "pull"
+        if exchange in ("direct", "pull") and not self._want_direct:
+            raise ValueError("exchange='direct' / 'pull' needs xy_size % 256 == 0 and world * buffer_size <= 64")
         if torch_stream is None:
             dev = kw.get("device")
             torch_stream = torch.cuda.Stream(device=torch.cuda.current_device() if dev is None else dev)
@@ -112,11 +115,11 @@ class MultiGpuGvom(Gvom):
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
             if int(ok.item()) == 1:
                 self._init_direct()
-                self.exchange = "direct"
+                self.exchange = "pull" if self._pull else "direct"
                 return
-            if exchange == "direct":
+            if exchange in ("direct", "pull"):
                 raise RuntimeError("direct exchange: symmetric memory unavailable: " + getattr(self, "_p2p_error", "?"))
-        if exchange in ("auto", "p2p", "direct"):
+        if exchange in ("auto", "p2p", "direct", "pull"):
             try:
                 self._init_p2p()
                 self.exchange = "p2p"
@@ -164,6 +167,14 @@ class MultiGpuGvom(Gvom):
             L.ready_slots[r] = ptrs[r] + o_ready + 4 * me
             L.done_slots[r] = ptrs[r] + o_done + 4 * me
         L.meta_table, L.ready_flags, L.done_flags = ptrs[me], ptrs[me] + o_ready, ptrs[me] + o_done
+        if self._pull:      # local mirror of every peer's ring slots (+ what it holds, + a private copy of the slot table)
+            nb = C.c_uint64(0)
+            check(self._L.gvom_mirror_size(self._h, R, C.byref(nb)), "gvom_mirror_size")
+            self._mirror = torch.empty(nb.value, dtype=torch.uint8, device=self._dev)
+            self._mirror_seq = torch.zeros(R * 64, dtype=torch.int32, device=self._dev)
+            self._meta_snap = torch.zeros(R * META_ROW_INTS, dtype=torch.int32, device=self._dev)
+            L.mirror, L.mirror_bytes = self._mirror.data_ptr(), nb.value
+            L.mirror_seq, L.meta_snapshot = self._mirror_seq.data_ptr(), self._meta_snap.data_ptr()
         self._links, self._links_t, self._links_hdl = L, t, hdl
         self._ready_view = t[o_ready:o_ready + 4 * R].view(torch.int32)
         self._table_view = t[:o_ready].view(torch.int32).view(R, 64, 8)
@@ -197,8 +208,9 @@ class MultiGpuGvom(Gvom):
                 for k in range(3):
                     org[k] = float(origin[k])
             outs, optr, mem = self._outputs(device_outputs)
-            rc = check(L.gvom_combine_maps_direct(self._h, C.byref(self._links), epoch, org, optr[0], optr[1], optr[2],
-                                                  optr[3], mem, self._stream), "gvom_combine_maps_direct")
+            fn = L.gvom_combine_maps_pull if self._pull else L.gvom_combine_maps_direct
+            rc = check(fn(self._h, C.byref(self._links), epoch, org, optr[0], optr[1], optr[2], optr[3], mem, self._stream),
+                       "gvom_combine_maps_pull" if self._pull else "gvom_combine_maps_direct")
             if rc == GVOM_NO_DATA:
                 print("ERROR: No data in buffer")
                 return None
@@ -276,7 +288,7 @@ class MultiGpuGvom(Gvom):
 
     def combine_maps(self, device_outputs=False):
         self._calls += 1
-        if self.exchange == "direct":
+        if self.exchange in ("direct", "pull"):
             return self._combine_direct(device_outputs)
         if self.exchange == "p2p":
             return self._combine_p2p(device_outputs)

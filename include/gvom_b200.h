@@ -237,7 +237,20 @@ typedef struct GvomPeerLinks {
     const int32_t* ready_flags;                  /* local: nranks flags */
     int32_t* done_slots[GVOM_MAX_RANKS];         /* this rank's "finished reading" flag in every rank's memory */
     const int32_t* done_flags;                   /* local: nranks flags */
+    /* pull exchange only (else NULL / 0): local, zero-initialised device memory */
+    void* mirror;                                /* gvom_mirror_size() bytes: copies of the peers' ring slots */
+    uint64_t mirror_bytes;
+    int32_t* mirror_seq;                         /* nranks * 64 int32 */
+    int32_t* meta_snapshot;                      /* nranks * GVOM_META_ROW_INTS int32 */
 } GvomPeerLinks;
+/* Pull exchange: same protocol and results as the direct exchange, but every rank first refreshes a local MIRROR of
+ * the peers' ring slots -- only the slots whose scan counter changed, with one bulk, coalesced, mask-aware copy over
+ * NVLink -- and then merges from local memory.  (Dependent accesses over NVLink made the in-place merge slower than
+ * exchanging pre-merged grids; bulk transfers do not have that problem.) */
+int gvom_mirror_size(GvomHandle* h, int32_t nranks, uint64_t* bytes);
+int gvom_combine_maps_pull(GvomHandle* h, const GvomPeerLinks* links, int32_t epoch, double origin[3],
+                           int32_t* positive, int32_t* negative, double* roughness, int32_t* visibility,
+                           int32_t out_mem, void* stream);
 /* origin: out (world origin of the combined map); in for a rank that has no scan yet: the combined origin in voxel
  * units adopted from a peer (NaN = none -> GVOM_NO_DATA). */
 /* Only the first step of gvom_combine_maps_direct (write this rank's slot table + ready flag = epoch); used by a rank
