@@ -88,6 +88,21 @@ def test_pointcloud2_full_scan_chunked_and_without_transform():
         assert da[k] == db[k], k
 
 
+def test_pointcloud2_without_mapped_host_access(monkeypatch):
+    """GVOM_H2D=dma: no zero-copy kernel reads; the PointCloud2 payload is widened to float64 x 3 by the staging
+    threads and takes the chunked-DMA array path.  Same results."""
+    monkeypatch.setenv("GVOM_H2D", "dma")
+    P = synth.params_tuple(**SMALLP)
+    a, b = make(P), make(P)
+    for pc, ego, T in small_frames(3):
+        msg = PointCloud2Payload.from_xyz(pc, 24, (0, 8, 16))
+        a.Process_pointcloud(msg.to_xyz_array(), ego, T)
+        b.Process_pointcloud2(msg.data.tobytes(), msg.n_points, 24, ego, T, (0, 8, 16))
+        same_state(a, b)
+        for x, y in zip(a.combine_maps(), b.combine_maps()):
+            assert np.array_equal(x, y)
+
+
 def test_pointcloud2_message_object_and_errors():
     class F:
         def __init__(self, name, offset, datatype=7):
@@ -272,3 +287,44 @@ def test_earlier_kernel_builds_still_match_the_reference(mask, monkeypatch):
     for name in ("small_moving", "os1_64"):
         bad, _ = replay.replay(make, name, replay.golden(name), view=lambda g: g.refview(), what=f"variant {mask}")
         assert not bad, "\n".join(bad[:20])
+
+
+def test_concurrent_callers_on_the_new_entry_points():
+    """ROS use (README.md:49): a subscriber thread feeds PointCloud2 payloads while a timer thread takes grids,
+    asynchronous maps and a state snapshot.  No errors, every result well formed."""
+    import threading
+    P = synth.params_tuple(**SMALLP)
+    g = make(P)
+    fr = [synth.frame(i, 16, 256, wall_radius=9.0, ego0=(10.0, 5.0, 1.0), dego=(0.3, 0.2, 0.05)) for i in range(30)]
+    msgs = [PointCloud2Payload.from_xyz(f[0], 32) for f in fr]
+    errors, grids, maps = [], [], []
+
+    def feeder():
+        try:
+            for m, (_, ego, T) in zip(msgs, fr):
+                g.Process_pointcloud2(m.data, m.n_points, 32, ego, T)
+        except Exception as ex:                      # pragma: no cover
+            errors.append(ex)
+
+    def timer():
+        try:
+            for k in range(40):
+                r = g.combine_maps_grids(40, -8, 1)
+                if r is not None:
+                    grids.append(r[1])
+                p = g.combine_maps_async()
+                if k % 7 == 0:
+                    g.save_state()
+                o = p.result()
+                if o is not None:
+                    maps.append(o)
+        except Exception as ex:                      # pragma: no cover
+            errors.append(ex)
+
+    th = [threading.Thread(target=feeder), threading.Thread(target=timer)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    assert grids and maps
+    assert all(set(np.unique(x["hard"])) <= {0, 100} and x["roughness"].dtype == np.int8 for x in grids)
+    assert all(o[1].shape == (64, 64) and np.isfinite(o[3]).all() for o in maps)
