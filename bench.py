@@ -5,9 +5,10 @@
   python bench.py --impl reference ...                           (reference arm)
 
 One step = one synthetic OS1-128 scan (262,144 points) processed into
-a 256x256x64 grid (buffer 4) followed by one combine_maps() -- BASELINE.json
-configs[1]; at N>1 every rank owns one sensor stream (configs[2]) and the combine
-is reduced across ranks.  Prints ONE JSON line (rank 0).
+a 256x256x64 grid followed by one combine_maps() -- BASELINE.json configs[1] with 4
+ring slots; at N>1 every rank owns one sensor stream with 2 ring slots (configs[2],
+SURVEY 8d: 2 slots per sensor) and the combine is exchanged across ranks.  Prints ONE
+JSON line (rank 0).
 
   value  : scans/s with the cloud already in HBM and the maps left in HBM
            (CUDA events around every step on the launching stream; L2 flushed
@@ -44,7 +45,7 @@ sys.path.insert(0, ROOT)
 
 from gvom_b200 import synth  # noqa: E402
 
-METRIC = "scans/sec (Process_pointcloud+combine_maps, OS1-128 262,144 pts, 256x256x64 grid, buffer 4)"
+METRIC = "scans/sec (Process_pointcloud+combine_maps, OS1-128 262,144 pts, 256x256x64 grid)"
 BEAMS, COLS = 128, 2048
 NFRAMES = 8
 
@@ -132,9 +133,15 @@ def run_reference(args):
     base = {"impl": "reference", "metric": METRIC, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic OS1-128 scan (128x2048=262,144 pts), 256x256x64 grid "
-                                   "@0.4/0.2 m, buffer 4, one sensor", "frames": NFRAMES}}
-    fr = frames()
+            "config": {}}
+    # the same workload as our arm: N sensors feed ONE reference Gvom (README.md:49) with `slots` ring slots per
+    # sensor; a step is one scan of every sensor + one combine_maps
+    nsens = max(1, args.gpus)
+    slots = args.slots_per_sensor or (2 if nsens > 1 else 4)
+    base["config"] = {"workload": f"configs[{1 if nsens == 1 else 2}]: synthetic OS1-128 scans (128x2048=262,144 pts), 256x256x64 grid "
+                                  f"@0.4/0.2 m, {nsens} sensor(s) into one reference Gvom on one GPU, {slots} ring slots per sensor",
+                      "frames": NFRAMES, "slots_per_sensor": slots}
+    fr = [frames(r) for r in range(nsens)]
     try:
         sys.path.insert(0, os.path.join(ROOT, "baseline"))
         for cand in ("/root/reference/scripts", os.path.join(ROOT, "baseline", "_ref")):
@@ -150,17 +157,18 @@ def run_reference(args):
         import gvom as refgvom
         if refgvom.__file__.startswith(os.path.join(ROOT, "gvom_b200")):
             raise RuntimeError("import gvom resolved to the B200 shim, not the reference")
-        g = refgvom.Gvom(*synth.params_tuple())
+        g = refgvom.Gvom(*synth.params_tuple(buffer_size=slots * nsens))
         ts = []
         for i in range(args.warmup + args.steps):
-            pc, ego, T = fr[i % NFRAMES]
             t0 = time.perf_counter()
-            g.Process_pointcloud(pc, ego, T)
+            for r in range(nsens):
+                pc, ego, T = fr[r][i % NFRAMES]
+                g.Process_pointcloud(pc, ego, T)
             g.combine_maps()
             numba.cuda.synchronize()
             ts.append(time.perf_counter() - t0)
         ts = ts[args.warmup:]
-        v = len(ts) / sum(ts)
+        v = nsens * len(ts) / sum(ts)
         base.update({"value": v, "ms_per_step": 1e3 * sum(ts) / len(ts), "p50_latency_ms": 1e3 * statistics.median(ts),
                      "cpu_baseline": {"value": v, "unit": "scans/s", "cores": 1, "kind": "reference",
                                       "sample": f"{len(ts)} steps; unmodified reference class through Numba-CUDA "
@@ -199,7 +207,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-mode", default="numba", choices=["numba", "oracle"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU combine exchange")
+    ap.add_argument("--slots-per-sensor", type=int, default=0, help="ring slots per sensor / rank (default: 4 at N=1, 2 at N>1)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl", "direct", "pull"], help="multi-GPU combine exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -222,7 +231,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
 
     stream = torch.cuda.Stream(device=dev)
-    P = synth.params_tuple()
+    # ring slots per sensor: 4 for the single-sensor configuration (BASELINE configs[1]); 2 per sensor for the
+    # multi-sensor one (configs[2], SURVEY 8d "config 3": B = 16 slots for 8 sensors, the reference README's rule)
+    slots = args.slots_per_sensor or (2 if multi else 4)
+    P = synth.params_tuple(buffer_size=slots)
     if multi:
         from gvom_b200.multi import MultiGpuGvom
         g = MultiGpuGvom(*P, device=dev, stream=stream.cuda_stream, torch_stream=stream, exchange=args.exchange)
@@ -353,7 +365,9 @@ def main():
         "warmup": args.warmup, "ms_per_step": tot_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": ("configs[1]: synthetic OS1-128 scan (128x2048=262,144 pts), 256x256x64 grid @0.4/0.2 m, "
-                                "buffer 4, one sensor per GPU" + ("; configs[2]: per-GPU streams, NCCL-reduced combine" if multi else "")),
+                                f"{slots} ring slots per sensor, one sensor per GPU" +
+                                (f"; configs[2]: per-GPU streams, {slots * world} slots in total (SURVEY 8d: 2 per sensor), combine exchanged over NVLink" if multi else "")),
+                   "slots_per_sensor": slots,
                    "exchange": (getattr(g, "exchange", None) or "") + (" sharded-finish" if getattr(g, "_sharded", False) and getattr(g, "exchange", "") == "p2p" else ""),
                    "frames": NFRAMES, "l2": "flushed between steps (256 MiB memset, outside the timed region)",
                    "value_io": "cloud resident in HBM (float64 Nx3), maps left in HBM",

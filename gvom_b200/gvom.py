@@ -294,11 +294,14 @@ class Gvom:
     def save_state(self, path=None):
         """Extension: ring slots + last combined map + ego as one opaque uint8 array
         (written to `path` with numpy.save if given)."""
-        n = C.c_size_t(0)
-        check(self._L.gvom_state_size(self._h, C.byref(n)), "gvom_state_size")
-        blob = np.empty(n.value, np.uint8)
-        w = C.c_size_t(0)
-        check(self._L.gvom_save_state(self._h, blob.ctypes.data, blob.size, C.byref(w)), "gvom_save_state")
+        n, w = C.c_size_t(0), C.c_size_t(0)
+        for _ in range(8):
+            check(self._L.gvom_state_size(self._h, C.byref(n)), "gvom_state_size")
+            blob = np.empty(n.value, np.uint8)
+            rc = self._L.gvom_save_state(self._h, blob.ctypes.data, blob.size, C.byref(w))
+            if rc != 3:                  # GVOM_ECAPACITY: another thread processed a scan between the two calls
+                break
+        check(rc, "gvom_save_state")
         blob = blob[:w.value]
         if path is not None:
             np.save(path, blob, allow_pickle=False)

@@ -163,6 +163,8 @@ int gvom_combine_maps_grids(GvomHandle* h, double origin[3], double density_thre
 /* State save / restore (deterministic replay, regression corpora): ring slots, the last combined map
  * (gvom.py:302-308 `last_combined_*`), ego position and ring position, as one opaque host blob that can
  * be loaded into any handle created with the same parameters and capacities. */
+/* (The size changes with every processed scan: a caller that shares the handle with a scan thread retries
+ * gvom_state_size + gvom_save_state when the latter answers GVOM_ECAPACITY.) */
 int gvom_state_size(GvomHandle* h, size_t* bytes);
 int gvom_save_state(GvomHandle* h, void* blob, size_t capacity, size_t* written);
 int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes);
