@@ -156,6 +156,7 @@ struct GvomHandle {
     int done_n = 0, done_epoch = 0;
     signed char* grids_dev = nullptr;     // [GVOM_GRID_COUNT][S*S] int8 OccupancyGrid payloads
     signed char* grids_host = nullptr;    // pinned mirror
+    int gather_blocks = 8;                // blocks per SM of the sharded finish's assembly kernels (GVOM_GATHER_BLOCKS; was 4 / 2)
     unsigned variant = 0;                 // GVOM_VARIANT bit mask: kernel builds kept for A/B measurements (see create)
     // outputs of the last combine that still have to be completed on the host (gvom_combine_maps_async)
     struct Pending {
@@ -556,6 +557,7 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
                                                                           : resident_grid(k_gather_metrics2<-1, -1, 3>, 256, h->sm_count);
         h->grid_gather2b = resident_grid(k_gather_metrics2<1, 1, 2>, 256, h->sm_count);
         if (const char* m = getenv("GVOM_VARIANT")) h->variant = (unsigned)strtoul(m, nullptr, 0);
+        if (const char* m = getenv("GVOM_GATHER_BLOCKS")) h->gather_blocks = std::max(1, std::min(8, atoi(m)));
         h->grid_rows3 = resident_grid(k_merge_rows<3, false>, 256, h->sm_count);
         h->grid_rows6 = resident_grid(k_merge_rows<6, false>, 256, h->sm_count);
         h->grid_rows3d = resident_grid(k_merge_rows<3, true>, 256, h->sm_count);
@@ -1717,10 +1719,10 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     }
     if (!(phases & 2)) { CUDA_TRY(cudaGetLastError()); return GVOM_OK; }
     // 3. everybody's planes and cells
-    launch(k_gather_maps, dim3(h->sm_count * 4), dim3(256), 0, st, R, wait_slab, (int)epoch, c.index_map, c.gmask, h->col_minz,
+    launch(k_gather_maps, dim3(h->sm_count * h->gather_blocks), dim3(256), 0, st, R, wait_slab, (int)epoch, c.index_map, c.gmask, h->col_minz,
            h->col_minz + h->S2, h->flags + 1, h->dp);
     rec(h, EV_X1, st);
-    launch(k_gather_cells, dim3(h->sm_count * 2), dim3(256), 0, st, R, (long long)res_capacity, c.hit, c.total, c.minh, c.metrics,
+    launch(k_gather_cells, dim3(h->sm_count * h->gather_blocks), dim3(256), 0, st, R, (long long)res_capacity, c.hit, c.total, c.minh, c.metrics,
            c.eig, c.cell_voxel, (int)h->ccap);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 2;
