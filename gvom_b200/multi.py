@@ -60,6 +60,18 @@ def merge_headers(headers):
     return org.copy(), counts
 
 
+def adopt_origin(table, world, slots):
+    """Direct / pull exchange, start-up only: a rank that has no scan yet takes the combined origin from the published
+    slot table (int32 [world, 64, 8] rows of {valid, ox, oy, oz, newest, seq, ..}): the newest slot of the first rank
+    that has data, like merge_headers does for the p2p exchange.  Pure host logic (tests/test_multi_cpu.py)."""
+    table = np.asarray(table).reshape(world, 64, 8)
+    for r in range(world):
+        for i in range(slots):
+            if table[r, i, 0] and table[r, i, 4]:
+                return table[r, i, 1:4].astype(np.float64)
+    return None
+
+
 def _ptr_array(ptrs):
     return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
 
@@ -198,12 +210,7 @@ class MultiGpuGvom(Gvom):
                 self._tstream.synchronize()
                 while int(self._ready_view.min().item()) < epoch:
                     time.sleep(1e-4)
-                tab = self._table_view.cpu().numpy()
-                origin = None
-                for r in range(self.world):
-                    for i in range(self.buffer_size):
-                        if origin is None and tab[r, i, 0] and tab[r, i, 4]:
-                            origin = tab[r, i, 1:4]
+                origin = adopt_origin(self._table_view.cpu().numpy(), self.world, self.buffer_size)
                 if origin is None:
                     print("ERROR: No data in buffer")
                     return None
