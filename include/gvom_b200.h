@@ -227,7 +227,9 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
  * same parameters and capacities, so they are carved identically) and combine_maps is the single-GPU combine over
  * ALL ranks' ring slots, read in place over NVLink -- one merge pass instead of partial + exchange + finish, and
  * the result is that of one Gvom holding every rank's slots in rank order.  All pointers are device pointers as
- * seen from this rank.  Collective: every rank calls it with the same `epoch` (1, 2, ...). */
+ * seen from this rank.  Collective: every rank calls it with the same `epoch` (1, 2, ...).  The handle remembers
+ * `done_flags` (the next scan waits on them before it overwrites a ring slot), so the flag block must stay
+ * allocated for as long as the handle is used. */
 #define GVOM_MAX_RANKS 16
 #define GVOM_META_ROW_INTS (64 * 8)      /* one rank's row of the slot table: 64 slots x 8 int32 */
 typedef struct GvomPeerLinks {
