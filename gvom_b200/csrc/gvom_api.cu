@@ -100,7 +100,7 @@ enum { EV_START = 0, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER, EV_CST
 
 // GVOM_VARIANT bits (environment, read at create): earlier builds of kernels kept selectable so that one GPU
 // run can time both and the parity tests can be run on either
-enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_OLD_CELLS = 8, VAR_MERGE_NB6 = 16, VAR_GATHER_LB2 = 32, VAR_DMA_OUT = 64, VAR_KEEP_C3 = 128 };
+enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_OLD_CELLS = 8, VAR_MERGE_NB6 = 16, VAR_GATHER_LB2 = 32, VAR_DMA_OUT = 64 };
 
 }  // namespace
 
@@ -122,8 +122,6 @@ struct GvomHandle {
     double* rough_out = nullptr;          // = (double*)(imaps + 3*S*S)
     int* col_minz = nullptr;              // [2][S*S] lowest occupied / lowest free z per column (C1 -> C3)
     unsigned* known = nullptr;            // [2][S*ceil(S/32)] "height known" bit maps (rows over y, rows over x)
-    unsigned* known_pp[2] = {nullptr, nullptr};   // fused height stage: ping-pong pair (this combine's / cleared for the next)
-    int known_cur = 0;
     float* debug_dev = nullptr;           // [max(ccap*8, S*S*10)]
     int* flags = nullptr;                 // [0] running cell counter of K2, [1] of C1 (reset by their consumers)
     // multi-GPU scratch
@@ -210,7 +208,6 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
     h->rough_out = reinterpret_cast<double*>(h->imaps ? h->imaps + ((3 * S2 + 1) & ~size_t(1)) : nullptr);
     h->col_minz = d.take<int>(2 * S2);
     h->known = d.take<unsigned>(2 * (size_t)p.xy_size * ((p.xy_size + 31) / 32));
-    for (int q = 0; q < 2; ++q) h->known_pp[q] = d.take<unsigned>(2 * (size_t)p.xy_size * ((p.xy_size + 31) / 32));
     h->debug_dev = d.take<float>(std::max(ccap * 8, S2 * 10));
     h->flags = d.take<int>(8);
     h->cacc = d.take<double>(ccap * 10);
@@ -360,27 +357,14 @@ void launch_gather(GvomHandle* h, Slot& s, cudaStream_t st) {
     }
 }
 
-// device pointer of the pinned word the kernels store the combined cell count into (NULL: use a 4-byte DMA)
-int* mapped_count_ptr(GvomHandle* h) {
-    if (!h->zero_copy || (h->variant & VAR_DMA_OUT)) return nullptr;
-    void* m = nullptr;
-    if (cudaHostGetDevicePointer(&m, h->counters_host, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return static_cast<int*>(m);
-}
-
-// single-GPU combine: can the height stage be fused into C1 / C2 / C4 (no k_column_maps launch)?
-bool can_fuse_heights(GvomHandle* h, const MergeArgs& A) {
-    return h->p.xy_size % 256 == 0 && A.use_masks && !(h->variant & (VAR_KEEP_C3 | VAR_OLD_MERGE | VAR_OLD_CELLS | VAR_OLD_SURFACE | VAR_MERGE_NB6));
-}
-
 // C2: per-cell record merge + eigenvalues
-void launch_cells(GvomHandle* h, const MergeArgs& A, Combined& c, cudaStream_t st, const HeightOut& H) {
+void launch_cells(GvomHandle* h, const MergeArgs& A, Combined& c, cudaStream_t st) {
     if (h->variant & VAR_OLD_CELLS)
         launch(k_merge_cells, dim3(h->grid_cells), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
                                                       h->dp, (int)h->ccap);
     else
         launch(k_merge_cells2<false>, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
-                                                       h->dp, (int)h->ccap, H);
+                                                       h->dp, (int)h->ccap);
 }
 
 // Completes the outputs of the last combine on the host: waits for the stream, copies pageable outputs out of
@@ -410,7 +394,7 @@ int finish_outputs(GvomHandle* h) {
 // 2-D stage + outputs, shared by the single- and multi-GPU combine.  Everything is enqueued on `st`;
 // finish_outputs() completes it (the synchronous entry points call it right away).
 int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* positive, int32_t* negative,
-                            double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st, bool fused = false) {
+                            double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st) {
     const int S2 = h->S2;
     double* height = h->maps; double* inferred = h->maps + S2; double* rough = h->rough_out;
     double* xs = h->maps + 3 * (size_t)S2; double* ys = h->maps + 4 * (size_t)S2; double* guessed = h->maps + 5 * (size_t)S2;
@@ -435,22 +419,17 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
             kpos = (int32_t*)m[0]; kneg = (int32_t*)m[1]; kvis = (int32_t*)m[2]; krough = (double*)m[3];
         }
     }
-    // combined cell count: C3 (or, fused, C2) stores it into a mapped pinned word (else a 4-byte DMA after the kernels)
-    int* host_count = mapped_count_ptr(h);
-    const int W = (h->p.xy_size + 31) / 32;
-    // fused height stage: C1 and C2 have already written the height map and this combine's bit maps (known_pp[cur]);
-    // C4 forms the inferred height itself and clears the other bit-map pair for the next combine
-    unsigned* known = fused ? h->known_pp[h->known_cur] : h->known;
-    unsigned* knownT = known + (size_t)h->p.xy_size * W;
-    unsigned* next_known = fused ? h->known_pp[1 - h->known_cur] : nullptr;
-    if (!fused) {
-        launch(k_column_maps, dim3(W, W), dim3(1024), 0, st, c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
-                                                   c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, height, inferred, known, knownT,
-                                                   h->flags + 1, c.counter, host_count);
-        h->stats.kernel_launches++;
-    } else {
-        h->known_cur = 1 - h->known_cur;
+    // combined cell count: C3 stores it into a mapped pinned word (else a 4-byte DMA after the kernels)
+    int* host_count = nullptr;
+    if (h->zero_copy && !(h->variant & VAR_DMA_OUT)) {
+        void* m = nullptr;
+        if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) host_count = (int*)m; else cudaGetLastError();
     }
+    const int W = (h->p.xy_size + 31) / 32;
+    unsigned* known = h->known; unsigned* knownT = h->known + (size_t)h->p.xy_size * W;
+    launch(k_column_maps, dim3(W, W), dim3(1024), 0, st, c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
+                                               c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, height, inferred, known, knownT,
+                                               h->flags + 1, c.counter, host_count);
     const size_t mask_bytes = 2 * (size_t)h->p.xy_size * W * sizeof(unsigned);
     const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
     if (h->variant & VAR_OLD_SURFACE) {
@@ -469,10 +448,9 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
                                                                                  c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
                                                                                  in_smem, h->col_minz, h->flags + 1,
                                                                                  direct_dev ? kpos : nullptr, direct_dev ? kneg : nullptr,
-                                                                                 direct_dev ? kvis : nullptr, direct_dev ? krough : nullptr,
-                                                                                 fused ? 1 : 0, next_known, inferred);
+                                                                                 direct_dev ? kvis : nullptr, direct_dev ? krough : nullptr);
     }
-    h->stats.kernel_launches += 1;
+    h->stats.kernel_launches += 2;
     rec(h, EV_MAPS, st);
     CUDA_TRY(cudaGetLastError());
     if (!host_count) CUDA_TRY(cudaMemcpyAsync(h->counters_host, c.counter, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -591,8 +569,6 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
     if (e == cudaSuccess) e = cudaMemsetAsync(h->total_grid, 0, sizeof(int) * (size_t)h->V, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->flags, 0, sizeof(int) * 8, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->col_minz, 0x7f, sizeof(int) * 2 * (size_t)h->S2, h->stream);
-    for (int q = 0; q < 2; ++q)
-        if (e == cudaSuccess) e = cudaMemsetAsync(h->known_pp[q], 0, sizeof(unsigned) * 2 * (size_t)p->xy_size * ((p->xy_size + 31) / 32), h->stream);
     // both combined-map buffers start as "all unknown" with an empty group mask (k_merge_rows relies on map and
     // mask of its destination being consistent)
     for (auto& c : h->comb) {
@@ -892,34 +868,20 @@ static int combine_locked(GvomHandle* h, double origin[3], int32_t* positive, in
     Combined& c = h->comb[1 - h->cur];
     for (int k = 0; k < 3; ++k) c.origin[k] = newest.origin[k];   // gvom.py:229
     // flags[1] (running cell counter) and the column minima are left clean by the previous combine's C4
-    // fused height stage: C1 writes the height defaults + ego-disc bits, C2 the column heights, C4 the inferred heights
-    const bool fused = can_fuse_heights(h, A);
-    const int W = (h->p.xy_size + 31) / 32;
-    unsigned* kb = h->known_pp[h->known_cur];
     {
         MergeOut O{};
         O.cmap = c.index_map; O.counter = h->flags + 1; O.cell_voxel = c.cell_voxel;
         O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
         O.gmask = (h->p.xy_size % 8 == 0) ? c.gmask : nullptr; O.cap = (int)h->ccap;
-        if (fused) {
-            O.height = h->maps; O.known = kb; O.knownT = kb + (size_t)h->p.xy_size * W;
-            O.o0 = c.origin[0]; O.o1 = c.origin[1]; O.e0 = h->ego[0]; O.e1 = h->ego[1]; O.e2 = h->ego[2];
-        }
         launch_merge<MERGE_FULL>(h, A, O, st);
     }
     rec(h, EV_CODES, st);
-    HeightOut H{};
-    if (fused) {
-        H.height = h->maps; H.known = kb; H.knownT = kb + (size_t)h->p.xy_size * W;
-        H.col_occ = h->col_minz; H.o2 = c.origin[2];
-        H.map_count = c.counter; H.host_count = mapped_count_ptr(h);
-    }
-    launch_cells(h, A, c, st, H);
+    launch_cells(h, A, c, st);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 1;
     h->prof_combine = h->profiling;
     c.has_gmask = h->p.xy_size % 8 == 0;
-    if (int e = enqueue_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st, fused)) return e;
+    if (int e = enqueue_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st)) return e;
     if (!async)
         if (int e = finish_outputs(h)) return e;
     c.valid = true;                                          // gvom.py:302-308
@@ -1347,8 +1309,6 @@ int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes) {
     if (err == cudaSuccess) err = cudaMemset(h->total_grid, 0, sizeof(int) * (size_t)h->V);
     if (err == cudaSuccess) err = cudaMemset(h->flags, 0, sizeof(int) * 8);
     if (err == cudaSuccess) err = cudaMemset(h->col_minz, 0x7f, sizeof(int) * 2 * (size_t)h->S2);
-    for (int q = 0; q < 2 && err == cudaSuccess; ++q)
-        err = cudaMemset(h->known_pp[q], 0, sizeof(unsigned) * 2 * (size_t)h->p.xy_size * ((h->p.xy_size + 31) / 32));
     if (err != cudaSuccess) return fail(GVOM_ECUDA, std::string("gvom_load_state: ") + cudaGetErrorString(err));
     h->stage_busy = false;
     return GVOM_OK;
@@ -1537,7 +1497,7 @@ static int combine_peers(GvomHandle* h, const GvomPeerLinks* pl, bool pull, int3
     }
     rec(h, EV_CODES, st);
     launch(k_merge_cells2<true>, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics,
-                                                          c.eig, h->dp, (int)h->ccap, HeightOut{});
+                                                          c.eig, h->dp, (int)h->ccap);
     h->stats.kernel_launches += 2;
     if (!pull) {   // last reader of peer memory is done: tell every rank
         launch(k_signal, dim3(1), dim3(32), 0, st, done, (int)epoch);

@@ -790,11 +790,6 @@ struct MergeOut {
     const int* wait_flags;   // FINISH, peer-to-peer: flags[k] >= wait_epoch once rank k's partial results are visible
     int wait_n, wait_epoch;
     int slab_r, slab_n;      // FINISH, sharded: this rank finishes the z-planes with z % slab_n == slab_r (slab_n <= 1: all)
-    // k_merge_rows, fused height stage (no separate column-map kernel): the z == 0 segments also write the height
-    // map's defaults (-1000, or the ego disc's ground height) and the disc's "height known" bits
-    double* height;          // NULL: not fused
-    unsigned* known; unsigned* knownT;
-    double o0, o1, e0, e1, e2;
 };
 
 __device__ __forceinline__ void column_min(int* __restrict__ col, int z) {
@@ -1152,26 +1147,6 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
                 }
             }
         }
-        if (O.height && z == 0) {
-            // height-map defaults of this row's 256 columns (gvom.py:327-331, 566-570): -1000, or inside the robot-radius
-            // disc around the ego the assumed ground height.  xp = (o+x)*res - ego with product and difference fused (the
-            // reference's SASS), then fma(xp,xp, yp*yp) <= r*r.  The disc also counts as "height known".
-            const int W = (S + 31) >> 5;
-            const double yp = __fma_rn(__dadd_rn(O.o1, (double)y), P.xy_res, -O.e1);
-            const double yy = __dmul_rn(yp, yp);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int xx = x0s + 8 * lane + j;
-                const double xp = __fma_rn(__dadd_rn(O.o0, (double)xx), P.xy_res, -O.e0);
-                const bool disc = __fma_rn(xp, xp, yy) <= P.r2;
-                const double hd = disc ? __dsub_rn(O.e2, P.ground_to_lidar) : -1000.0;
-                O.height[(long long)xx * S + y] = hd;
-                if (hd > -1000.0) {
-                    atomicOr(O.known + (long long)xx * W + (y >> 5), 1u << (y & 31));
-                    atomicOr(O.knownT + (long long)y * W + (xx >> 5), 1u << (xx & 31));
-                }
-            }
-        }
         if (seen == 0) {                                  // uniform: nothing known anywhere in the segment
             if (old_word != 0) {
                 int4* dst = reinterpret_cast<int4*>(O.cmap) + (long long)seg * 64 + lane * 2;
@@ -1372,14 +1347,6 @@ k_merge_cells(MergeArgs A, const int* __restrict__ counter, const int* __restric
 // cell are issued together (up to 8 per round) instead of in batches of SLOT_BATCH.  (A build that also fetched the
 // next record while merging the current one needed 96 registers and lost more to occupancy than it gained.)
 // ---------------------------------------------------------------------------
-// fused height stage (single-GPU combine): what the cell merge needs to write a column's height
-struct HeightOut {
-    double* height;          // NULL: not fused (k_column_maps runs)
-    unsigned* known; unsigned* knownT;
-    const int* col_occ;
-    double o2;
-    int* map_count; int* host_count;
-};
 struct CellRec { double o[10]; int hit, tot; float mh; };
 
 __device__ __forceinline__ void load_cell_rec(const SlotRef& s, int io, CellRec& r) {
@@ -1399,15 +1366,10 @@ template <bool DIRECT>
 __global__ void __launch_bounds__(128, 8)
 k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
                int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
-               float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap, HeightOut H) {
+               float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap) {
     pdl_wait();
-    const int count_raw = *counter;
-    const int count = min(count_raw, cap);
+    const int count = min(*counter, cap);
     const int S = P.S, Z = P.Z;
-    if (H.height && blockIdx.x == 0 && threadIdx.x == 0) {   // fused height stage: this kernel publishes the cell count
-        *H.map_count = count_raw;
-        if (H.host_count) *H.host_count = count_raw;
-    }
     constexpr int RB = 8;                                   // sources looked up per round
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
         const int v = cell_voxel[id];
@@ -1444,16 +1406,6 @@ k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restri
 #pragma unroll
         for (int k = 0; k < 10; ++k) mo[k] = c[k];
         chit[id] = hit; ctot[id] = tot; cminh[id] = mh;
-        if (H.height && z == H.col_occ[y * S + x]) {
-            // lowest occupied voxel of its column: the column's height (gvom.py:573-575) and its "known" bits
-            const int W = (S + 31) >> 5;
-            const double hh = __dmul_rn(__dadd_rn(__dadd_rn((double)z, (double)mh), H.o2), P.z_res);
-            H.height[(long long)x * S + y] = hh;
-            if (hh > -1000.0) {
-                atomicOr(H.known + (long long)x * W + (y >> 5), 1u << (y & 31));
-                atomicOr(H.knownT + (long long)y * W + (x >> 5), 1u << (x & 31));
-            }
-        }
         float e[3];
         eigen3(c, e);
         ceig[id * 3 + 0] = e[0]; ceig[id * 3 + 1] = e[1]; ceig[id * 3 + 2] = e[2];
@@ -1753,8 +1705,7 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
                 DevParams P, double* __restrict__ rough, double* __restrict__ xs, double* __restrict__ ys,
                 double* __restrict__ guessed, int* __restrict__ pos, int* __restrict__ neg, int* __restrict__ vis,
                 int masks_in_smem, int* __restrict__ col_minz, int* __restrict__ scratch_count,
-                int* __restrict__ pos2, int* __restrict__ neg2, int* __restrict__ vis2, double* __restrict__ rough2,
-                int fused, unsigned* __restrict__ next_known, double* __restrict__ inferred_out) {
+                int* __restrict__ pos2, int* __restrict__ neg2, int* __restrict__ vis2, double* __restrict__ rough2) {
     pdl_wait();
     extern __shared__ unsigned smask[];
     const int S = P.S, Z = P.Z;
@@ -1776,26 +1727,12 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
         }
         if (t >= S * S) return;
         const int y0 = t % S, x0 = t / S;
-        const double h0 = GVOM_HM(height, x0, y0);
-        double inf0;
-        if (fused) {
-            // fused height stage: the inferred height comes straight from C1's column minimum (gvom.py:579-590), and the
-            // thread clears exactly the scratch entries it has read; the "height known" bit maps of the NEXT combine
-            // (ping-pong) are cleared here too
-            const int col = y0 * S + x0;
-            const int zf = col_minz[S * S + col];
-            inf0 = zf < Z ? __dmul_rn(__dadd_rn(o2, (double)zf), P.z_res) : -1000.0;
-            GVOM_HM(inferred_out, x0, y0) = inf0;
-            col_minz[col] = 0x7f7f7f7f;
-            col_minz[S * S + col] = 0x7f7f7f7f;
-            if (t < 2 * S * W) next_known[t] = 0u;
-        } else {
-            // housekeeping for the next combine: C1's column minima and running counter start clean
-            col_minz[t] = 0x7f7f7f7f;
-            col_minz[S * S + t] = 0x7f7f7f7f;
-            inf0 = GVOM_HM(inferred, x0, y0);
-        }
+        // housekeeping for the next combine: C1's column minima and running counter start clean
+        col_minz[t] = 0x7f7f7f7f;
+        col_minz[S * S + t] = 0x7f7f7f7f;
         if (t == 0) *scratch_count = 0;
+        const double h0 = GVOM_HM(height, x0, y0);
+        const double inf0 = GVOM_HM(inferred, x0, y0);
         double dh_out = 0.0;
         if (!(h0 > -1000.0) && inf0 != -1000.0) {
             // ---- guessed height delta (gvom.py:592-713), quirks kept (see oracle/gvom_oracle.c)

@@ -18,7 +18,7 @@ from gvom_b200 import Gvom, synth  # noqa: E402
 from gvom_b200.node import PointCloud2Payload  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 60
-NAMES = {0: "current", 1: "old surface", 2: "old merge", 4: "old gather", 8: "old cells", 16: "rows NB6", 32: "gather2 2 blocks/SM", 64: "DMA outputs", 128: "separate column-map kernel (C3)", 15: "all old"}
+NAMES = {0: "current", 1: "old surface", 2: "old merge", 4: "old gather", 8: "old cells", 16: "rows NB6", 32: "gather2 2 blocks/SM", 64: "DMA outputs", 15: "all old"}
 stream = torch.cuda.Stream()
 g = Gvom(*synth.params_tuple(), stream=stream.cuda_stream)
 fr = [synth.frame(i, 128, 2048) for i in range(8)]
@@ -49,7 +49,7 @@ def run(n, profile=False):
 
 
 res = {}
-for mask in (0, 128, 0, 128):
+for mask in (0, 64, 0):
     g.set_variant(mask)
     run(12)
     ev, _ = run(steps)
