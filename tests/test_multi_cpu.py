@@ -245,3 +245,79 @@ def test_adopt_origin():
     t[1, 0] = [1, 4, -6, 7, 0, 8, 0, 0]
     t[2, 0] = [1, 50, 60, 70, 1, 3, 0, 0]
     assert list(adopt_origin(t, 3, 2)) == [5.0, -6.0, 7.0]
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_plane_sharded_column_exchange_model(nranks):
+    """Executable model of the NEXT multi-GPU design: the combined state stays sharded
+    by WORLD plane, owner(z) = (z + origin_z) mod N, and the 2-D stage gets the three per-column facts that span
+    planes through two small reductions:
+      (a) lowest occupied voxel + its min height:  MIN over ranks of the 64-bit key  z << 32 | float32 bits of min_h
+      (b) lowest free voxel:                       MIN over ranks of z
+      (c) positive-obstacle window sums:           SUM over ranks of (sum hit, sum total) of the cells with hit > 10
+    Every rank only looks at its own planes; the reduced facts must reproduce the oracle's height map, inferred
+    height map and positive-obstacle map (gvom.py:515-590)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gvom_b200 import synth
+    from oracle.gvom_oracle import OracleGvom
+    from test_multi_gpu import sensor_frames
+    S, Z = 32, 16
+    P = synth.params_tuple(xy_size=S, z_size=Z, buffer_size=4, robot_radius=2.0)
+    o = OracleGvom(*P)
+    fr = sensor_frames(2, 3, beams=32, cols=512, wall=5.5)
+    for step in range(3):
+        for r in range(2):
+            o.Process_pointcloud(*fr[step][r])
+        _, pos_ref, _, _, _ = o.combine_maps()           # two ego steps: the origin (and with it plane ownership) moves
+    pos_ref = pos_ref.T                                   # oracle maps are [x, y]; everything below is [y, x]
+    z_res, pos_thr, robot_h, slope_thr = P[1], P[6], P[9], P[8]
+    oz = int(o.combined_origin[2])
+    cmap = o.combined_index_map.reshape(Z, S, S)          # [z, y, x]
+    hit, tot, minh = o.combined_hit_count, o.combined_total_count, o.combined_min_height
+    INF = np.uint64(0xFFFFFFFFFFFFFFFF)
+    key_occ = np.full((nranks, S, S), INF, np.uint64)     # [rank, y, x]
+    z_free = np.full((nranks, S, S), 1 << 30, np.int64)
+    owner = (np.arange(Z) + oz) % nranks
+    for r in range(nranks):
+        for z in np.flatnonzero(owner == r):
+            plane = cmap[z]
+            occ = plane >= 0
+            bits = np.zeros((S, S), np.uint64)
+            bits[occ] = minh[plane[occ]].view(np.uint32).astype(np.uint64)
+            key = (np.uint64(z) << np.uint64(32)) | bits
+            key_occ[r] = np.where(occ, np.minimum(key_occ[r], key), key_occ[r])
+            z_free[r] = np.where(plane < -1, np.minimum(z_free[r], z), z_free[r])
+    k = key_occ.min(axis=0)                               # reduction (a)
+    zf = z_free.min(axis=0)                               # reduction (b)
+    has = k != INF
+    zo = (k >> np.uint64(32)).astype(np.int64)
+    mh = (k & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32).astype(np.float64)
+    h_model = np.where(has, (zo + mh + oz) * z_res, -1000.0)           # [y, x]
+    h_ref = o.height_map.T                                # oracle maps are [x, y]
+    outside_disc = ~((h_ref > -1000.0) & ~has)            # the ego disc's assumed ground is not a column fact
+    assert np.array_equal(h_model[has], h_ref[has])
+    assert (h_ref[outside_disc & ~has] == -1000.0).all()
+    inf_model = np.where(zf < (1 << 30), (oz + zf) * z_res, -1000.0)
+    assert np.array_equal(inf_model, o.inferred_height_map.T)
+    # (c): the window depends on the (now global) height; each rank sums inside it over ITS planes only
+    h_all = h_ref                                         # incl. the disc default, as the 2-D stage sees it
+    lo = np.floor((h_all + pos_thr) / z_res - oz).astype(np.int64) + 1
+    hi = np.floor((h_all + robot_h) / z_res - oz).astype(np.int64)
+    ok = (lo >= 0) & (lo < Z) & (hi >= 0) & (hi < Z)
+    sums = np.zeros((nranks, 2, S, S), np.int64)
+    for r in range(nranks):
+        for z in np.flatnonzero(owner == r):
+            plane = cmap[z]
+            inwin = ok & (lo <= z) & (z <= hi) & (plane >= 0)
+            big = np.zeros((S, S), bool)
+            big[inwin] = hit[plane[inwin]] > 10
+            sums[r, 0][big] += hit[plane[big]]
+            sums[r, 1][big] += tot[plane[big]]
+    sh, st = sums[:, 0].sum(axis=0).astype(np.float64), sums[:, 1].sum(axis=0).astype(np.float64)     # reduction (c)
+    dens = np.where(st > 0, sh / np.where(st > 0, st, 1.0), sh)
+    pos_model = np.where(ok, (dens * 100.0).astype(np.int32), 0)
+    steep = ~(np.sqrt(o.x_slope_map ** 2 + o.y_slope_map ** 2) < slope_thr).T
+    pos_model = np.where(steep, 100, pos_model)
+    assert np.array_equal(pos_model, pos_ref)
+    # the scenario exercises both paths: steep cells (100) and density values from the window sums
+    assert has.sum() > 20 and (pos_ref == 100).sum() > 0 and ((pos_ref > 0) & ~steep).sum() > 0
