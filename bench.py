@@ -49,6 +49,35 @@ METRIC = "scans/sec (Process_pointcloud+combine_maps, OS1-128 262,144 pts, 256x2
 BEAMS, COLS = 128, 2048
 NFRAMES = 8
 
+# --config: BASELINE.json configs[1] is the headline (default); configs[3] / configs[4] are the stress regimes
+# (ray-cast / atomic bound, and DDA-length + buffer-merge bound).  The stress lines are extra evidence committed under
+# profiles/, not the driver's line.
+CONFIGS = {
+    "os1_128": dict(workload="configs[1]: synthetic OS1-128 scan (128x2048=262,144 pts), 256x256x64 grid @0.4/0.2 m",
+                    params={}, points=BEAMS * COLS, frames=NFRAMES, max_points=None),
+    "dense": dict(workload="configs[3]: dense stress, 2,097,152-point aggregated cloud (16 x 128x1024 scans) into a 1024x1024x128 grid @0.1 m",
+                  params=dict(xy_resolution=0.1, z_resolution=0.1, xy_size=1024, z_size=128, buffer_size=4),
+                  points=16 * 128 * 1024, frames=3, max_points=16 * 128 * 1024),
+    "long_range": dict(workload="configs[4]: long-range stress, OS1-128 scan with a 200 m wall, 256x256x64 grid @0.4/0.2 m, 16 ring slots",
+                       params=dict(buffer_size=16), points=BEAMS * COLS, frames=NFRAMES, max_points=None),
+}
+CONFIG = "os1_128"
+
+
+def config_frames(name, rank=0):
+    """Frames of a stress configuration (same generators as the parity scenarios of gvom_b200/synth.py)."""
+    out = []
+    if name == "dense":
+        for i in range(CONFIGS[name]["frames"]):
+            ego = (100.0 + 0.4 * i, 50.0 + 0.1 * i, 1.0)
+            T = synth.pose_matrix(ego, 0.01 * i)
+            pc = np.concatenate([synth.synthetic_scan(128, 1024, seed=5000 + 16 * i + k, ego=ego) for k in range(16)], axis=0)
+            out.append((np.ascontiguousarray(pc), ego, T))
+    elif name == "long_range":
+        for i in range(CONFIGS[name]["frames"]):
+            out.append(synth.frame(i, BEAMS, COLS, wall_radius=200.0, seed_base=1000 * rank))
+    return out
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -93,6 +122,8 @@ class ClockSampler:
 
 def frames(rank=0):
     """NFRAMES consecutive frames of the SURVEY 8(d) stream (sensor `rank` on a 2 m ring)."""
+    if CONFIG != "os1_128":
+        return config_frames(CONFIG, rank)
     out = []
     for i in range(NFRAMES):
         pc, ego, T = synth.frame(i, BEAMS, COLS, seed_base=1000 * rank)
@@ -208,9 +239,13 @@ def main():
     ap.add_argument("--ref-mode", default="numba", choices=["numba", "oracle"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots-per-sensor", type=int, default=0, help="ring slots per sensor / rank (default: 4 at N=1, 2 at N>1)")
+    ap.add_argument("--config", default="os1_128", choices=list(CONFIGS), help="workload: BASELINE.json configs[1] (default), [3] dense, [4] long_range")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl", "direct", "pull"], help="multi-GPU combine exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global CONFIG, NFRAMES
+    CONFIG = args.config
+    NFRAMES = CONFIGS[CONFIG]["frames"]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -234,12 +269,15 @@ def main():
     # ring slots per sensor: 4 for the single-sensor configuration (BASELINE configs[1]); 2 per sensor for the
     # multi-sensor one (configs[2], SURVEY 8d "config 3": B = 16 slots for 8 sensors, the reference README's rule)
     slots = args.slots_per_sensor or (2 if multi else 4)
-    P = synth.params_tuple(buffer_size=slots)
+    cfg = CONFIGS[CONFIG]
+    P = synth.params_tuple(**dict(dict(buffer_size=slots), **cfg["params"]))
+    slots = P[4]
+    extra = {"max_points": cfg["max_points"]} if cfg["max_points"] else {}
     if multi:
         from gvom_b200.multi import MultiGpuGvom
         g = MultiGpuGvom(*P, device=dev, stream=stream.cuda_stream, torch_stream=stream, exchange=args.exchange)
     else:
-        g = Gvom(*P, device=dev, stream=stream.cuda_stream)
+        g = Gvom(*P, device=dev, stream=stream.cuda_stream, **extra)
     fr = frames(rank)
     pinned = [torch.from_numpy(f[0]).pin_memory() for f in fr]
     on_dev = [p.cuda(dev) for p in pinned]
@@ -317,7 +355,7 @@ def main():
     hbm, hbm_src = peaks()
     V = P[2] * P[2] * P[3]
     B = P[4]
-    N = BEAMS * COLS
+    N = cfg["points"]
     sources = min(B, args.warmup + args.steps) + 1
     stage_ms = {k: v / psteps for k, v in stages.items()}
     # algorithmic bytes per launch (DESIGN.md "kernels")
@@ -325,9 +363,10 @@ def main():
     atom = atomic_peak(_lib.lib(), torch, dev)
     try:
         from oracle.gvom_oracle import OracleGvom
-        o = OracleGvom(*P)
-        o.Process_pointcloud(*fr[0])
-        work = o.work
+        if CONFIG == "os1_128":                 # (the stress grids take the CPU oracle minutes: work counts only here)
+            o = OracleGvom(*P)
+            o.Process_pointcloud(*fr[0])
+            work = o.work
     except Exception:
         pass
     abytes = {"raycast": 24 * N, "index": 12 * V, "merge_codes": 4 * V * sources + 4 * V, "maps": 4 * V + 20 * P[2] * P[2]}
@@ -364,8 +403,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": ("configs[1]: synthetic OS1-128 scan (128x2048=262,144 pts), 256x256x64 grid @0.4/0.2 m, "
-                                f"{slots} ring slots per sensor, one sensor per GPU" +
+        "config": {"workload": (cfg["workload"] + f", {slots} ring slots per sensor, one sensor per GPU" +
                                 (f"; configs[2]: per-GPU streams, {slots * world} slots in total (SURVEY 8d: 2 per sensor), combine exchanged over NVLink" if multi else "")),
                    "slots_per_sensor": slots,
                    "exchange": (getattr(g, "exchange", None) or "") + (" sharded-finish" if getattr(g, "_sharded", False) and getattr(g, "exchange", "") == "p2p" else ""),
@@ -385,7 +423,7 @@ def main():
         "l2_atomic_peak_gops": atom,
         "work_per_scan": work,
     }
-    if world == 1:
+    if world == 1 and CONFIG == "os1_128":
         # the callers either side of the path, same workload, wall clock per tick (p50 of 60):
         # what the reference node hands over (pageable float64 array) and the PointCloud2 payload it received
         # (48-byte records), maps or the node's int8 OccupancyGrid payloads out
@@ -410,7 +448,7 @@ def main():
             }
         except Exception as ex:
             line["e2e_variants_p50_ms"] = {"error": repr(ex)}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and CONFIG == "os1_128":
         try:
             line["cpu_baseline"] = cpu_baseline()
         except Exception as ex:

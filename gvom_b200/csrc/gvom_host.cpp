@@ -77,12 +77,12 @@ struct CopyPool::Impl {
     void slice(int i, int parts) {
         if (i >= parts) return;
         if (mode == 1) {
-            const int64_t per = ((n / parts) + 255) & ~int64_t(255);
+            const int64_t per = (((n + parts - 1) / parts) + 255) & ~int64_t(255);   // ceil: per * parts >= n
             const int64_t a = std::min<int64_t>(n, per * i), b = std::min<int64_t>(n, per * (i + 1));
             if (b > a) extract_range(dst, src, a, b, step, ox, oy, oz, as_double);
             return;
         }
-        const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);
+        const size_t per = (((bytes + parts - 1) / parts) + 4095) & ~size_t(4095);
         const size_t a = std::min(bytes, per * i), b = std::min(bytes, per * (i + 1));
         if (b > a) stream_copy(dst + a, src + a, b - a);
     }

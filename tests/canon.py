@@ -122,14 +122,8 @@ class Golden:
                 v64, g64 = v.astype(np.float64), gv.astype(np.float64)
                 ok = np.isclose(v64, g64, rtol=rtol, atol=atol, equal_nan=True)
                 if k in ("eig", "voxel") and v64.ndim == 2:
-                    # Eigenvalues come from the closed-form trig solve on FLOAT32 covariances
-                    # (gvom.py:1437-1487).  Near a repeated eigenvalue acos() turns a 1-ulp
-                    # float32 difference of the input (which the reference's own float-atomic
-                    # order already produces run to run) into ~sqrt(ulp) of phi, i.e. up to
-                    # ~5e-4 of the largest eigenvalue.  Tolerance: 1e-3 of the row's scale.
                     cols = slice(0, 3) if k == "eig" else slice(5, 8)
-                    scale = np.abs(g64[:, cols]).sum(axis=1, keepdims=True)
-                    ok[:, cols] |= np.abs(v64[:, cols] - g64[:, cols]) <= 1e-3 * scale + 1e-6
+                    ok[:, cols] |= eig_ok(v64, g64, k)
                 if not ok.all():
                     j = np.argmax(np.abs(v64 - g64) * ~ok)
                     bad.append(f"{what} step {step} ({kind}): {k} {int((~ok).sum())}/{gv.size} outside "
@@ -140,3 +134,36 @@ class Golden:
                 if got[k[len(pre):]] != want:
                     bad.append(f"{what} step {step} ({kind}): sha256 of {k[len(pre):-4]} differs")
         return bad
+
+
+def eig_degenerate_gap():
+    """Rows whose smaller eigenvalue gap is at most this fraction of the spread (l0 - l2) count as
+    near-degenerate: only those may use the wide eigenvalue band (see eig_ok)."""
+    return EIG_GAP_GATE
+
+
+EIG_GAP_GATE = 0.05
+
+
+def eig_ok(v64, g64, kind="eig"):
+    """Eigenvalue tolerance: |error| <= 1e-4 * lambda_max of the row.  The eigenvalues come from the
+    closed-form trig solve on FLOAT32 covariances (gvom.py:1437-1487); near a repeated eigenvalue acos() turns a
+    1-ulp float32 difference of the input (which the reference's own float-atomic order produces run to run)
+    into ~sqrt(ulp) of the angle, so rows that an explicit gap test flags as near-degenerate
+    (min(l0-l1, l1-l2) <= EIG_GAP_GATE * (l0-l2) on the golden values) may use 1e-3 * lambda_max.
+    Measured (scripts/eigen_error_hist.py, profiles/eigen_hist_*.json): non-degenerate rows stay below 1e-6,
+    all rows below 1e-4 on every golden scenario.  kind "voxel": debug rows hold (l0-l1, l1-l2, l2) in columns 5..7.
+    Returns a boolean [rows, 3] array."""
+    if kind == "eig":
+        w, v = g64[:, 0:3], v64[:, 0:3]
+        l0, l1, l2 = w[:, 0], w[:, 1], w[:, 2]
+    else:
+        w, v = g64[:, 5:8], v64[:, 5:8]
+        l2 = w[:, 2]; l1 = l2 + w[:, 1]; l0 = l1 + w[:, 0]
+    lmax = np.maximum(np.abs(l0), np.abs(l2))
+    spread = np.maximum(l0 - l2, 1e-300)
+    degenerate = np.minimum(l0 - l1, l1 - l2) <= EIG_GAP_GATE * spread
+    err = np.abs(v - w)
+    tight = err <= 1e-4 * lmax[:, None] + 1e-7
+    wide = degenerate[:, None] & (err <= 1e-3 * lmax[:, None] + 1e-7)
+    return tight | wide

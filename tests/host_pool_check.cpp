@@ -29,5 +29,29 @@ int main() {
         if (memcmp(c.data() + ((64 - ((uintptr_t)c.data() & 63)) & 63), in.data(), in.size()) != 0) ++bad;
         free(out); free(out2);
     }
+
+    // slicing regression: n / parts already a multiple of 256 with a remainder -- the last n % parts
+    // records used to be skipped (n = 16387, 4 slices covered 16384); same for byte copies with 3 slices
+    for (int helpers = 2; helpers <= 7; ++helpers) {
+        const int64_t ns[4] = {16387, 16384 * 5 + 3, 65536 + 7, 262144 + 5};
+        for (int t = 0; t < 4; ++t) {
+            const int64_t n = ns[t]; const int step = 48;
+            std::vector<char> in((size_t)n * step);
+            for (size_t i = 0; i < in.size(); ++i) in[i] = (char)(i * 13 + 1);
+            char* out = (char*)aligned_alloc(256, (size_t)n * 16 + 256);
+            memset(out, 0x5a, (size_t)n * 16 + 256);
+            CopyPool pool(helpers);
+            pool.extract_xyz(out, in.data(), n, step, 0, 4, 8, false);
+            for (int64_t i = 0; i < n; ++i)
+                if (memcmp(out + i * 16, in.data() + i * step, 12) != 0) ++bad;
+            free(out);
+            const size_t bytes = (size_t)4096 * 3 * 40 + 4096 * 2 + 17;       // floor(bytes / 3) a multiple of 4096, remainder != 0
+            std::vector<char> src(bytes), dst(bytes + 64, (char)0x5a);
+            for (size_t i = 0; i < bytes; ++i) src[i] = (char)(i * 31 + 7);
+            char* d = dst.data() + ((64 - ((uintptr_t)dst.data() & 63)) & 63);
+            pool.copy(d, src.data(), bytes);
+            if (memcmp(d, src.data(), bytes) != 0) ++bad;
+        }
+    }
     printf("bad=%d\n", bad); return bad != 0;
 }
