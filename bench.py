@@ -369,7 +369,7 @@ def main():
             work = o.work
     except Exception:
         pass
-    abytes = {"raycast": 24 * N, "index": 12 * V, "merge_codes": 4 * V * sources + 4 * V, "maps": 4 * V + 20 * P[2] * P[2]}
+    abytes = {"scan_points": 24 * N, "scan_cells": 4 * V, "merge_codes": 4 * V * sources + 4 * V, "maps": 4 * V + 20 * P[2] * P[2]}
     # (SURVEY.md 8d per-stage figures: ray-cast = the cloud as stored (float64 x 3); index = read hit + pass grids, write
     #  the index map; merge = read B slot maps + the previous map, write the combined map; maps = one pass over the
     #  combined map + the five 2-D outputs)
@@ -379,12 +379,12 @@ def main():
             ach = bts / (stage_ms[k] * 1e-3) / 1e9
             rooflines[k] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                             "ms": stage_ms[k], "algorithmic_bytes": bts}
-    if work and stage_ms.get("raycast", 0) > 0 and atom.get("spread"):
+    if work and stage_ms.get("scan_points", 0) > 0 and atom.get("spread"):
         n_at = 2 * work["n_in"] + work["dda_steps"]
-        ach = n_at / (stage_ms["raycast"] * 1e-3) / 1e9
+        ach = n_at / (stage_ms["scan_points"] * 1e-3) / 1e9
         rooflines["raycast_atomics"] = {"bound": "l2_atomic", "achieved": ach, "peak": atom["spread"],
                                         "unit": "G atomic increments/s", "frac": ach / atom["spread"],
-                                        "ms": stage_ms["raycast"], "algorithmic_atomics": n_at,
+                                        "ms": stage_ms["scan_points"], "algorithmic_atomics": n_at,
                                         "peak_same_address": atom.get("same_address"),
                                         "note": "increments delivered (warp-aggregated) vs RED.ADD.U32 issue rate to "
                                                 "random words of a 16 MiB table measured by gvom_bench_atomics"}
@@ -394,7 +394,7 @@ def main():
         for k, v in json.load(open(tp)).items():
             if isinstance(v, dict) and v.get("dram_read") is not None and v.get("dram_write") is not None:
                 traffic[k] = v["dram_read"] + v["dram_write"]
-    kernels = {k: v for k, v in stage_ms.items() if k in ("raycast", "index", "moments", "gather", "merge_codes", "merge_cells", "maps")}
+    kernels = {k: v for k, v in stage_ms.items() if k in ("scan_points", "scan_cells", "merge_codes", "merge_cells", "maps")}
     dom = max((k for k in kernels if k in rooflines), key=lambda k: kernels[k], default=None)
     roof = dict(rooflines[dom], kernel=dom, traffic=traffic.get(dom), peak_source=hbm_src,
                 traffic_source="profiles/traffic_r01.json (ncu --set full, bytes per launch)") if dom else None

@@ -35,17 +35,6 @@ class GvomStats(C.Structure):
 
 
 MAX_RANKS = 16
-META_ROW_INTS = 64 * 8
-
-
-class GvomPeerLinks(C.Structure):
-    """include/gvom_b200.h: GvomPeerLinks (direct multi-GPU exchange)."""
-    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32),
-                ("peer_ws", C.c_void_p * MAX_RANKS), ("meta_rows", C.c_void_p * MAX_RANKS), ("meta_table", C.c_void_p),
-                ("ready_slots", C.c_void_p * MAX_RANKS), ("ready_flags", C.c_void_p),
-                ("done_slots", C.c_void_p * MAX_RANKS), ("done_flags", C.c_void_p),
-                ("mirror", C.c_void_p), ("mirror_bytes", C.c_uint64), ("mirror_seq", C.c_void_p),
-                ("meta_snapshot", C.c_void_p)]
 
 
 # every symbol include/gvom_b200.h declares: name -> (restype, argtypes)
@@ -57,6 +46,8 @@ SYMBOLS = {
     "gvom_create": (C.c_int, [C.POINTER(GvomParams), _i64, _i64, C.c_int, _vp, _sz, _vp, _sz, C.POINTER(_vp)]),
     "gvom_destroy": (C.c_int, [_vp]),
     "gvom_process_pointcloud": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _pd, _vp, _vp]),
+    "gvom_get_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "gvom_wait_input": (C.c_int, [_vp]),
     "gvom_combine_maps": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gvom_process_pointcloud2": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _pd, _vp, _vp]),
     "gvom_combine_maps_async": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
@@ -78,10 +69,6 @@ SYMBOLS = {
     "gvom_combine_finish_sharded": (C.c_int, [_vp, _pd, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i64, _vp,
                                               C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, C.POINTER(_vp), _vp, _i32, _i32,
                                               _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "gvom_publish_slots": (C.c_int, [_vp, C.POINTER(GvomPeerLinks), _i32, _vp]),
-    "gvom_combine_maps_direct": (C.c_int, [_vp, C.POINTER(GvomPeerLinks), _i32, _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "gvom_mirror_size": (C.c_int, [_vp, _i32, C.POINTER(C.c_uint64)]),
-    "gvom_combine_maps_pull": (C.c_int, [_vp, C.POINTER(GvomPeerLinks), _i32, _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gvom_slot_info": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i64), _pd]),
     "gvom_last_slot": (C.c_int, [_vp, C.POINTER(_i32)]),
     "gvom_export_slot": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),

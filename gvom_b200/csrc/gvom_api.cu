@@ -26,6 +26,7 @@
 
 #include "../../include/gvom_b200.h"
 #include "gvom_kernels.cuh"
+#include "gvom_scan.cuh"
 
 using namespace gvom;
 
@@ -55,9 +56,9 @@ struct Slot {
     int* counter = nullptr;       // device cell count
     unsigned* gmask = nullptr;    // [V/256] one bit per 8-voxel group: something known (valid when has_gmask)
     bool has_gmask = false;
+    bool dirty = false;           // the map holds something else than "all unknown" (a physical slot is wiped before reuse)
     double origin[3] = {0, 0, 0};
     bool valid = false;
-    int64_t seq = 0;              // scan counter when the slot was written (pull exchange: is a mirror current?)
 };
 
 struct Combined {
@@ -95,12 +96,11 @@ struct Carver {                    // sub-allocates a workspace block, 256-byte 
     }
 };
 
-enum { EV_START = 0, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER, EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS, EV_D2H,
+enum { EV_START = 0, EV_H2D, EV_POINTS, EV_SCELLS, EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS, EV_D2H,
        EV_X0, EV_X1, EV_X2, EV_COUNT };   // EV_X*: extra marks inside the multi-GPU combine
 
-// GVOM_VARIANT bits (environment, read at create): earlier builds of kernels kept selectable so that one GPU
-// run can time both and the parity tests can be run on either
-enum { VAR_OLD_SURFACE = 1, VAR_OLD_MERGE = 2, VAR_OLD_GATHER = 4, VAR_OLD_CELLS = 8, VAR_MERGE_NB6 = 16, VAR_GATHER_LB2 = 32, VAR_DMA_OUT = 64 };
+// GVOM_VARIANT bits (environment / gvom_set_variant): A/B switches for measurements; every setting gives the same results
+enum { VAR_GENERIC_MERGE = 2, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128 };
 
 }  // namespace
 
@@ -108,13 +108,16 @@ struct GvomHandle {
     GvomParams p;
     DevParams dp;
     int device = 0;
-    int64_t max_points = 0, cap = 0, ccap = 0, V = 0;
-    int S2 = 0;
+    int64_t max_points = 0, cap = 0, gcap = 0, ccap = 0, V = 0, EV = 0;
+    int S2 = 0, ES = 0, EZ = 0;
     // device
-    int *hit_grid = nullptr, *total_grid = nullptr;
-    double* acc = nullptr;
-    char* stage_dev = nullptr;           // input cloud staging [max_points * 32 B]
-    std::vector<Slot> slots;
+    unsigned* cellid = nullptr;           // [EV] extended, epoch-tagged voxel -> cell grid of the scan kernels
+    unsigned scan_tag = 0;                // tag of the last scan (1..255; wraps through a clear of cellid)
+    double* acc = nullptr;                // [cap + gcap][MOM] raw moments of the scan in flight
+    char* stage_dev = nullptr;            // input cloud staging [max_points * 32 B]
+    std::vector<Slot> slots;              // B + 1 PHYSICAL slots: B ring entries + one spare that is kept wiped
+    std::vector<int> phys;                // ring index (the reference's buffer index) -> physical slot
+    int spare = 0;                        // physical slot the next scan is written to
     Combined comb[2];
     int cur = 0;                          // comb[cur] = last combined map (if valid)
     double* maps = nullptr;               // height, inferred, rough_work, xs, ys, guessed  [6][S*S]
@@ -123,7 +126,7 @@ struct GvomHandle {
     int* col_minz = nullptr;              // [2][S*S] lowest occupied / lowest free z per column (C1 -> C3)
     unsigned* known = nullptr;            // [2][S*ceil(S/32)] "height known" bit maps (rows over y, rows over x)
     float* debug_dev = nullptr;           // [max(ccap*8, S*S*10)]
-    int* flags = nullptr;                 // [0] running cell counter of K2, [1] of C1 (reset by their consumers)
+    int* flags = nullptr;                 // [0,1] / [2,3] cell + ghost counters of even / odd scans, [4] C1's running cell counter
     // multi-GPU scratch
     double* cacc = nullptr;               // [ccap,10] raw-moment scratch of the multi-GPU combine
     // pinned host
@@ -140,24 +143,21 @@ struct GvomHandle {
     bool stage_busy = false;
     cudaStream_t copy_stream = nullptr;   // H2D of the cloud, chunked so that ray casting overlaps the transfer
     cudaEvent_t ev_chunk[8];              // chunk c has landed in stage_dev
-    cudaEvent_t ev_proc_done = nullptr;   // last reader of stage_dev (K3 of the previous scan) is done
+    cudaEvent_t ev_proc_done = nullptr;   // last reader of stage_dev (the previous scan) is done
+    cudaEvent_t ev_input = nullptr;       // the scan kernels have consumed the caller's device cloud
     cudaEvent_t ev[EV_COUNT];
     bool profiling = false;
-    bool zero_copy = true;                // host clouds: K1 reads pinned memory directly (else chunked DMA)
+    bool zero_copy = true;                // host clouds: S1 reads pinned memory directly (else chunked DMA)
     bool prof_process = false, prof_combine = false, prof_x = false;
     int sm_count = 148;
-    int grid_index = 0, grid_codes = 0, grid_cells = 0, grid_gather = 0;   // resident grids (set at create)
-    int grid_cells2 = 0, grid_gather2 = 0, grid_gather2b = 0, grid_rows3 = 0, grid_rows6 = 0, grid_rows3d = 0;
+    int grid_codes = 0, grid_cells = 0, grid_cells2 = 0, grid_rows3 = 0, grid_scan_cells = 0;   // resident grids (set at create)
     GvomStats stats{};
     float last_stage_copy_ms = 0.f;       // host time of the last pageable->pinned staging copy
     CopyPool* pool = nullptr;             // staging threads for pageable input (created on first use)
-    char* dev_base = nullptr;             // device workspace base (direct multi-GPU exchange: peers' slots = peer base + same offsets)
-    const int* done_flags = nullptr;      // direct exchange: peers' "finished reading my slots" flags, checked by the next scan's K2
-    int done_n = 0, done_epoch = 0;
     signed char* grids_dev = nullptr;     // [GVOM_GRID_COUNT][S*S] int8 OccupancyGrid payloads
     signed char* grids_host = nullptr;    // pinned mirror
-    int gather_blocks = 8;                // blocks per SM of the sharded finish's assembly kernels (GVOM_GATHER_BLOCKS; was 4 / 2)
-    unsigned variant = 0;                 // GVOM_VARIANT bit mask: kernel builds kept for A/B measurements (see create)
+    int gather_blocks = 8;                // blocks per SM of the sharded finish's assembly kernels (GVOM_GATHER_BLOCKS)
+    unsigned variant = 0;                 // GVOM_VARIANT bit mask (A/B switches, see VAR_*)
     // outputs of the last combine that still have to be completed on the host (gvom_combine_maps_async)
     struct Pending {
         bool active = false;
@@ -168,6 +168,7 @@ struct GvomHandle {
         double* roughness = nullptr;
     } pend;
     std::mutex mu;
+    Slot& ring(int i) { return slots[phys[i]]; }
 };
 
 namespace {
@@ -176,11 +177,13 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
     const GvomParams& p = h->p;
     const size_t V = (size_t)h->V, cap = (size_t)h->cap, ccap = (size_t)h->ccap, S2 = (size_t)h->S2;
     Carver d(dev);
-    h->hit_grid = d.take<int>(V);
-    h->total_grid = d.take<int>(V);
-    h->acc = d.take<double>(cap * ACC);
+    h->cellid = d.take<unsigned>((size_t)h->EV);
+    h->acc = d.take<double>((cap + (size_t)h->gcap) * MOM);
     h->stage_dev = d.take<char>((size_t)h->max_points * 32);
-    h->slots.resize(p.buffer_size);
+    h->slots.resize(p.buffer_size + 1);
+    h->phys.resize(p.buffer_size);
+    for (int i = 0; i < p.buffer_size; ++i) h->phys[i] = i;
+    h->spare = p.buffer_size;
     for (auto& s : h->slots) {
         s.index_map = d.take<int>(V);
         s.hit = d.take<int>(cap);
@@ -228,8 +231,10 @@ int check_params(const GvomParams* p, int64_t max_points) {
     if (p->buffer_size < 1 || p->buffer_size > MAX_SLOTS) return fail(GVOM_EINVAL, "buffer_size must be in [1,64]");
     if (p->xy_eigen_dist < 0 || p->z_eigen_dist < 0) return fail(GVOM_EINVAL, "eigen distances must be >= 0");
     const double V = (double)p->xy_size * p->xy_size * p->z_size;
-    if (V >= 2147483647.0) return fail(GVOM_EINVAL, "grid has >= 2^31 voxels");
-    if (max_points < 1 || max_points > (1 << 30)) return fail(GVOM_EINVAL, "max_points out of range");
+    const double EVd = ((double)p->xy_size + 2.0 * p->xy_eigen_dist) * ((double)p->xy_size + 2.0 * p->xy_eigen_dist) *
+                       ((double)p->z_size + 2.0 * p->z_eigen_dist);
+    if (V >= 2147483647.0 || EVd >= 2147483647.0) return fail(GVOM_EINVAL, "grid (with its eigen-distance margin) has >= 2^31 voxels");
+    if (max_points < 1 || max_points > (int64_t)CELL_OVERFLOW - 1) return fail(GVOM_EINVAL, "max_points out of range (1 .. 2^23 - 3)");
     return GVOM_OK;
 }
 
@@ -239,6 +244,10 @@ void fill_sizes(GvomHandle* h, const GvomParams* p, int64_t max_points, int64_t 
     h->S2 = p->xy_size * p->xy_size;
     h->max_points = max_points;
     h->cap = std::min<int64_t>(max_points, h->V);
+    h->ES = p->xy_size + 2 * p->xy_eigen_dist;
+    h->EZ = p->z_size + 2 * p->z_eigen_dist;
+    h->EV = (int64_t)h->ES * h->ES * h->EZ;
+    h->gcap = std::min<int64_t>(max_points, h->EV - h->V);      // margin ("ghost") cells
     int64_t dflt = std::min<int64_t>(h->V, 4 * max_points * ((int64_t)p->buffer_size + 1));
     h->ccap = max_cells > 0 ? std::min<int64_t>(max_cells, h->V) : dflt;
     DevParams& d = h->dp;
@@ -296,14 +305,13 @@ void rec(GvomHandle* h, int e, cudaStream_t st) {
 void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs* A) {
     A->n = 0;
     A->use_masks = 1;
-    A->meta = nullptr; A->cox = A->coy = A->coz = 0;
-    for (auto& s : h->slots) {
+    for (int i = 0; i < h->p.buffer_size; ++i) {         // ring order = the reference's slot order
+        Slot& s = h->ring(i);
         if (!s.valid) continue;
         SlotRef& r = A->s[A->n++];
         r.map = s.index_map; r.metrics = s.metrics; r.hit = s.hit; r.total = s.total; r.minh = s.minh;
         r.dx = (int)(org[0] - s.origin[0]); r.dy = (int)(org[1] - s.origin[1]); r.dz = (int)(org[2] - s.origin[2]);
         r.is_prev = 0;
-        r.meta = -1;
         r.gmask = s.has_gmask ? s.gmask : nullptr;
         if (!r.gmask) A->use_masks = 0;
     }
@@ -313,7 +321,6 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
         r.map = pc.index_map; r.metrics = pc.metrics; r.hit = pc.hit; r.total = pc.total; r.minh = pc.minh;
         r.dx = (int)(org[0] - pc.origin[0]); r.dy = (int)(org[1] - pc.origin[1]); r.dz = (int)(org[2] - pc.origin[2]);
         r.is_prev = 1;
-        r.meta = -1;
         r.gmask = pc.has_gmask ? pc.gmask : nullptr;
         if (!r.gmask) A->use_masks = 0;
     }
@@ -321,11 +328,8 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
 
 template <int MODE>
 void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStream_t st) {
-    if (MODE == MERGE_FULL && h->p.xy_size % 256 == 0 && A.use_masks && O.gmask && !(h->variant & VAR_OLD_MERGE)) {
-        if (h->variant & VAR_MERGE_NB6)
-            launch(k_merge_rows<6, false>, dim3(h->grid_rows6), dim3(256), 0, st, A, O, h->dp);
-        else
-            launch(k_merge_rows<3, false>, dim3(h->grid_rows3), dim3(256), 0, st, A, O, h->dp);
+    if (MODE == MERGE_FULL && h->p.xy_size % 256 == 0 && A.use_masks && O.gmask && !(h->variant & VAR_GENERIC_MERGE)) {
+        launch(k_merge_rows<3>, dim3(h->grid_rows3), dim3(256), 0, st, A, O, h->dp);
         h->stats.kernel_launches++;
         return;
     }
@@ -338,33 +342,10 @@ void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStre
     h->stats.kernel_launches++;
 }
 
-// K4: neighbourhood gather of the per-cell moments
-void launch_gather(GvomHandle* h, Slot& s, cudaStream_t st) {
-    const int cap = (int)h->cap;
-    const bool r11 = h->p.xy_eigen_dist == 1 && h->p.z_eigen_dist == 1;
-    if (h->variant & VAR_OLD_GATHER) {
-        if (r11)
-            launch(k_gather_metrics<1, 1>, dim3(h->grid_gather), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
-        else
-            launch(k_gather_metrics<-1, -1>, dim3(h->grid_gather), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
-    } else {
-        if (r11 && (h->variant & VAR_GATHER_LB2))
-            launch(k_gather_metrics2<1, 1, 2>, dim3(h->grid_gather2b), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
-        else if (r11)
-            launch(k_gather_metrics2<1, 1, 3>, dim3(h->grid_gather2), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
-        else
-            launch(k_gather_metrics2<-1, -1, 3>, dim3(h->grid_gather2), dim3(256), 0, st, s.index_map, s.cell_voxel, s.counter, h->acc, s.metrics, h->dp, cap, h->flags);
-    }
-}
-
 // C2: per-cell record merge + eigenvalues
 void launch_cells(GvomHandle* h, const MergeArgs& A, Combined& c, cudaStream_t st) {
-    if (h->variant & VAR_OLD_CELLS)
-        launch(k_merge_cells, dim3(h->grid_cells), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
-                                                      h->dp, (int)h->ccap);
-    else
-        launch(k_merge_cells2<false>, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
-                                                       h->dp, (int)h->ccap);
+    launch(k_merge_cells2, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 4, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
+                                                h->dp, (int)h->ccap);
 }
 
 // Completes the outputs of the last combine on the host: waits for the stream, copies pageable outputs out of
@@ -406,7 +387,7 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
     int32_t *kpos = positive, *kneg = negative, *kvis = visibility;
     double* krough = roughness;
     if (!direct_dev && out_mem == GVOM_HOST && positive && negative && roughness && visibility && h->zero_copy &&
-        !(h->variant & (VAR_OLD_SURFACE | VAR_DMA_OUT))) {
+        !(h->variant & VAR_DMA_OUT)) {
         void* m[4] = {nullptr, nullptr, nullptr, nullptr};
         void* hp[4] = {positive, negative, visibility, roughness};
         bool ok = true, dev = false;
@@ -429,24 +410,13 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
     unsigned* known = h->known; unsigned* knownT = h->known + (size_t)h->p.xy_size * W;
     launch(k_column_maps, dim3(W, W), dim3(1024), 0, st, c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
                                                c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, height, inferred, known, knownT,
-                                               h->flags + 1, c.counter, host_count);
+                                               h->flags + 4, c.counter, host_count);
     const size_t mask_bytes = 2 * (size_t)h->p.xy_size * W * sizeof(unsigned);
     const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
-    if (h->variant & VAR_OLD_SURFACE) {
-        launch(k_surface_maps, dim3(blocks_for(S2, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit, c.total, height, inferred, known, knownT,
-                                                                                c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
-                                                                                in_smem, h->col_minz, h->flags + 1);
-        if (direct_dev) {
-            const size_t bi = (size_t)S2 * sizeof(int);
-            CUDA_TRY(cudaMemcpyAsync(positive, pos, bi, cudaMemcpyDeviceToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(negative, neg, bi, cudaMemcpyDeviceToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(visibility, vis, bi, cudaMemcpyDeviceToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(roughness, rough, (size_t)S2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        }
-    } else {
+    {
         launch(k_surface_maps2, dim3(blocks_for(S2, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit, c.total, height, inferred, known, knownT,
                                                                                  c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
-                                                                                 in_smem, h->col_minz, h->flags + 1,
+                                                                                 in_smem, h->col_minz, h->flags + 4,
                                                                                  direct_dev ? kpos : nullptr, direct_dev ? kneg : nullptr,
                                                                                  direct_dev ? kvis : nullptr, direct_dev ? krough : nullptr);
     }
@@ -527,7 +497,6 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
     CUDA_TRY(cudaSetDevice(device));
     GvomHandle* h = new GvomHandle();
     h->device = device;
-    h->dev_base = static_cast<char*>(device_ws);
     fill_sizes(h, p, max_points, max_combined_cells);
     size_t hb = 0;
     const size_t db = carve(h, device_ws, host_ws, &hb);
@@ -539,38 +508,35 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_proc_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_input, cudaEventDisableTiming);
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming);
     for (int i = 0; i < EV_COUNT && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
     int sms = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (sms > 0) h->sm_count = sms;
     {
-        const bool v8 = p->xy_size % 8 == 0, v4 = h->V % 4 == 0, s4 = p->xy_size % 4 == 0;
-        h->grid_index = v8 ? resident_grid(k_build_index<8>, 256, h->sm_count)
-                           : v4 ? resident_grid(k_build_index<4>, 256, h->sm_count) : resident_grid(k_build_index<1>, 256, h->sm_count);
+        const bool v8 = p->xy_size % 8 == 0, s4 = p->xy_size % 4 == 0;
         h->grid_codes = v8 ? resident_grid(k_merge_codes<8, MERGE_FINISH>, 256, h->sm_count)
                            : s4 ? resident_grid(k_merge_codes<4, MERGE_FINISH>, 256, h->sm_count)
                                 : resident_grid(k_merge_codes<1, MERGE_FINISH>, 256, h->sm_count);
-        h->grid_cells = resident_grid(k_merge_cells, 128, h->sm_count);
-        h->grid_cells2 = resident_grid(k_merge_cells2<false>, 128, h->sm_count);
-        h->grid_gather2 = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics2<1, 1, 3>, 256, h->sm_count)
-                                                                          : resident_grid(k_gather_metrics2<-1, -1, 3>, 256, h->sm_count);
-        h->grid_gather2b = resident_grid(k_gather_metrics2<1, 1, 2>, 256, h->sm_count);
+        h->grid_cells = resident_grid(k_slab_cells, 128, h->sm_count);
+        h->grid_cells2 = resident_grid(k_merge_cells2, 128, h->sm_count);
+        h->grid_scan_cells = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_scan_cells<1, 1>, 256, h->sm_count)
+                                                                             : resident_grid(k_scan_cells<-1, -1>, 256, h->sm_count);
         if (const char* m = getenv("GVOM_VARIANT")) h->variant = (unsigned)strtoul(m, nullptr, 0);
         if (const char* m = getenv("GVOM_GATHER_BLOCKS")) h->gather_blocks = std::max(1, std::min(8, atoi(m)));
-        h->grid_rows3 = resident_grid(k_merge_rows<3, false>, 256, h->sm_count);
-        h->grid_rows6 = resident_grid(k_merge_rows<6, false>, 256, h->sm_count);
-        h->grid_rows3d = resident_grid(k_merge_rows<3, true>, 256, h->sm_count);
-        h->grid_gather = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_gather_metrics<1, 1>, 256, h->sm_count)
-                                                                         : resident_grid(k_gather_metrics<-1, -1>, 256, h->sm_count);
+        h->grid_rows3 = resident_grid(k_merge_rows<3>, 256, h->sm_count);
     }
-    // dense grids are kept zero between scans (k_build_index re-zeroes what it reads)
-    if (e == cudaSuccess) e = cudaMemsetAsync(h->hit_grid, 0, sizeof(int) * (size_t)h->V, h->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(h->total_grid, 0, sizeof(int) * (size_t)h->V, h->stream);
+    // the cell grid of the scan kernels starts with tag 0 ("never used") everywhere; every slot map starts as "all
+    // unknown" with an empty group mask (S1 ray-casts into a wiped map; the row merge relies on map and mask of its
+    // destination being consistent)
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->cellid, 0, sizeof(unsigned) * (size_t)h->EV, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->flags, 0, sizeof(int) * 8, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->col_minz, 0x7f, sizeof(int) * 2 * (size_t)h->S2, h->stream);
-    // both combined-map buffers start as "all unknown" with an empty group mask (k_merge_rows relies on map and
-    // mask of its destination being consistent)
+    for (auto& sl : h->slots) {
+        if (e == cudaSuccess) e = cudaMemsetAsync(sl.index_map, 0xff, sizeof(int) * (size_t)h->V, h->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(sl.gmask, 0, sizeof(unsigned) * ((size_t)h->V / 256 + 2), h->stream);
+    }
     for (auto& c : h->comb) {
         if (e == cudaSuccess) e = cudaMemsetAsync(c.index_map, 0xff, sizeof(int) * (size_t)h->V, h->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c.gmask, 0, sizeof(unsigned) * ((size_t)h->V / 256 + 2), h->stream);
@@ -593,6 +559,7 @@ int gvom_destroy(GvomHandle* h) {
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(h->ev[i]);
     cudaEventDestroy(h->ev_stage);
     cudaEventDestroy(h->ev_proc_done);
+    cudaEventDestroy(h->ev_input);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]);
     cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
@@ -629,35 +596,47 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
     Xform tf;
     tf.enabled = T ? 1 : 0;
     for (int k = 0; k < 12; ++k) tf.m[k] = T ? T[k] : 0.0;
+    // the DDA's floor() shortcut holds while every coordinate the ray can take stays below 2^22 in magnitude
+    bool fast = !(h->variant & VAR_NO_FASTFLOOR);
+    for (int k = 0; k < 3; ++k)
+        if (!(std::fabs((double)fr.start[k]) + std::max(p.xy_size, p.z_size) + 8.0 < 4194304.0)) fast = false;
+
+    // ---- the scan is written into the (wiped) spare slot; the slot it replaces in the ring becomes the new spare
+    const int target = h->spare;
+    Slot& s = h->slots[target];
+    if (++h->scan_tag > 255u) {                          // tags wrapped: forget every entry of the cell grid
+        CUDA_TRY(cudaMemsetAsync(h->cellid, 0, sizeof(unsigned) * (size_t)h->EV, st));
+        h->scan_tag = 1u;
+    }
+    const int par = (int)(h->stats.process_calls & 1);
+    ScanOut O{};
+    O.map = s.index_map; O.cellid = h->cellid; O.tag = h->scan_tag; O.counters = h->flags + 2 * par;
+    O.acc = h->acc; O.minh = s.minh; O.cell_voxel = s.cell_voxel; O.cap = (int)h->cap; O.gcap = (int)h->gcap; O.ES = h->ES;
 
     rec(h, EV_START, st);
-    // ---- input staging + K1.  Host clouds are moved in chunks on a copy stream and every chunk
-    // is ray-cast as soon as it has landed, so K1 hides behind the PCIe transfer.
+    // ---- input staging + S1.  Host clouds: zero-copy (the kernel streams pinned memory over PCIe while it ray-casts),
+    // pageable ones through the pinned staging block chunk by chunk; or chunked DMA on a copy stream (GVOM_H2D=dma).
     const size_t esz = dtype == GVOM_F32 ? 4 : 8;
     const size_t row = (size_t)stride * esz;
-    const void* src = points;
-    const int nb = blocks_for(n, 256);
-    Xform tf_moments = tf;                               // transform K3 applies (none after a zero-copy K1)
-    auto launch_k1 = [&](const void* base, int64_t first, int64_t count, void* world_out) {
+    auto launch_s1 = [&](const void* base, int64_t first, int64_t count, int from_host) {
         if (count <= 0) return;
         const char* p0 = static_cast<const char*>(base) + (size_t)first * row;
-        if (world_out) world_out = static_cast<char*>(world_out) + (size_t)first * row;
-        const int blocks = blocks_for(count, 256);
-        if (dtype == GVOM_F32)
-            launch(k_voxelize_raycast<float>, dim3(blocks), dim3(256), 0, st, (const float*)p0, stride, (int)count, tf, fr, h->dp, h->hit_grid,
-                                                              h->total_grid, (float*)world_out);
-        else
-            launch(k_voxelize_raycast<double>, dim3(blocks), dim3(256), 0, st, (const double*)p0, stride, (int)count, tf, fr, h->dp, h->hit_grid,
-                                                               h->total_grid, (double*)world_out);
+        const dim3 g(blocks_for(count, 256)), b(256);
+        if (dtype == GVOM_F32) {
+            if (fast) launch(k_scan_points<float, true>, g, b, 0, st, (const float*)p0, stride, (int)count, from_host, tf, fr, h->dp, O);
+            else launch(k_scan_points<float, false>, g, b, 0, st, (const float*)p0, stride, (int)count, from_host, tf, fr, h->dp, O);
+        } else {
+            if (fast) launch(k_scan_points<double, true>, g, b, 0, st, (const double*)p0, stride, (int)count, from_host, tf, fr, h->dp, O);
+            else launch(k_scan_points<double, false>, g, b, 0, st, (const double*)p0, stride, (int)count, from_host, tf, fr, h->dp, O);
+        }
         h->stats.kernel_launches++;
     };
-    // PointCloud2 records: the kernel widens the float32 fields and keeps the world points (float64 x 3) in stage_dev
-    auto launch_k1_pc2 = [&](const void* base, int step, int ox, int oy, int oz, int64_t first, int64_t count) {
+    auto launch_s1_pc2 = [&](const void* base, int step, int ox, int oy, int oz, int64_t first, int64_t count) {
         if (count <= 0) return;
         const char* p0 = static_cast<const char*>(base) + (size_t)first * step;
-        double* wo = reinterpret_cast<double*>(h->stage_dev) + (size_t)first * 3;
-        launch(k_voxelize_raycast_pc2, dim3(blocks_for(count, 256)), dim3(256), 0, st, p0, step, ox, oy, oz, (int)count, tf, fr, h->dp,
-                                                               h->hit_grid, h->total_grid, wo);
+        const dim3 g(blocks_for(count, 256)), b(256);
+        if (fast) launch(k_scan_points_pc2<true>, g, b, 0, st, p0, step, ox, oy, oz, (int)count, tf, fr, h->dp, O);
+        else launch(k_scan_points_pc2<false>, g, b, 0, st, p0, step, ox, oy, oz, (int)count, tf, fr, h->dp, O);
         h->stats.kernel_launches++;
     };
     auto ensure_pool = [&]() {
@@ -672,7 +651,7 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
     if (cd.pc2 && n > 0) {
         if (mem == GVOM_DEVICE) {
             rec(h, EV_H2D, st);
-            launch_k1_pc2(points, cd.point_step, cd.ox, cd.oy, cd.oz, 0, n);
+            launch_s1_pc2(points, cd.point_step, cd.ox, cd.oy, cd.oz, 0, n);
             pc2_done = true;
         } else {
             if (h->stage_busy) CUDA_TRY(cudaEventSynchronize(h->ev_stage));   // stage_host still being read
@@ -683,7 +662,7 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
             const auto t0 = std::chrono::steady_clock::now();
             if (mapped) {
                 // field extraction (threaded, non-temporal) into packed 16-byte records, pipelined chunk by chunk
-                // with the zero-copy ray-cast that streams them over PCIe
+                // with the zero-copy kernel that streams them over PCIe
                 rec(h, EV_H2D, st);
                 const int nchunks = n >= 131072 ? 4 : 1;
                 const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~int64_t(255);
@@ -692,7 +671,7 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
                     if (count <= 0) break;
                     h->pool->extract_xyz(h->stage_host + (size_t)first * 16, static_cast<const char*>(points) + (size_t)first * cd.point_step,
                                          count, cd.point_step, cd.ox, cd.oy, cd.oz, false);
-                    launch_k1_pc2(mapped, 16, 0, 4, 8, first, count);
+                    launch_s1_pc2(mapped, 16, 0, 4, 8, first, count);
                 }
                 CUDA_TRY(cudaEventRecord(h->ev_stage, st));
                 h->stage_busy = true;
@@ -701,21 +680,21 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
                 // no mapped access: widen to float64 x 3 in the staging block and take the array path below
                 h->pool->extract_xyz(h->stage_host, static_cast<const char*>(points), n, cd.point_step, cd.ox, cd.oy, cd.oz, true);
                 points = h->stage_host;
-                src = points;
             }
             h->last_stage_copy_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         }
-        if (pc2_done) { tf_moments.enabled = 0; src = h->stage_dev; }
     }
     if (pc2_done) {
-        // K1 launched above
+        // S1 launched above
     } else if (n > 0 && mem == GVOM_DEVICE) {
+        const void* src = points;
         if (stride == 4 && ((uintptr_t)points & 15)) {   // vector loads need 16-byte alignment
             CUDA_TRY(cudaMemcpyAsync(h->stage_dev, points, (size_t)n * row, cudaMemcpyDeviceToDevice, st));
             src = h->stage_dev;
         }
         rec(h, EV_H2D, st);
-        launch_k1(src, 0, n, nullptr);
+        launch_s1(src, 0, n, 0);
+        CUDA_TRY(cudaEventRecord(h->ev_input, st));      // gvom_wait_input(): the caller's buffer has been consumed
     } else if (n > 0) {
         bool dev = false;
         const bool staged = points == h->stage_host;     // PointCloud2 fallback: already in the pinned staging block
@@ -728,10 +707,9 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
             if (mapped && ((uintptr_t)mapped & 15)) mapped = nullptr;   // the staged loads are 128-bit
         }
         if (mapped) {
-            // zero-copy: K1 streams the cloud over PCIe while it ray-casts; no DMA op, no staging pass on the GPU
             rec(h, EV_H2D, st);
             if (pinned) {
-                launch_k1(mapped, 0, n, h->stage_dev);
+                launch_s1(mapped, 0, n, 1);
             } else {
                 // pageable: the staging copy (threaded, non-temporal) is pipelined with the kernel chunk by chunk
                 ensure_pool();
@@ -743,14 +721,13 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
                     if (count <= 0) break;
                     h->pool->copy(h->stage_host + (size_t)first * row, static_cast<const char*>(points) + (size_t)first * row,
                                   (size_t)count * row);
-                    launch_k1(mapped, first, count, h->stage_dev);
+                    launch_s1(mapped, first, count, 1);
                 }
                 h->last_stage_copy_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
             }
             CUDA_TRY(cudaEventRecord(h->ev_stage, st));
-            tf_moments.enabled = 0;
         } else {
-            // chunked DMA on a copy stream; every chunk is ray-cast as soon as it has landed
+            // chunked DMA on a copy stream; every chunk is processed as soon as it has landed
             const int nchunks = n >= 65536 ? 4 : 1;
             const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~int64_t(255);
             CUDA_TRY(cudaEventRecord(h->ev_proc_done, st));   // stage_dev: previous scan's readers first
@@ -764,59 +741,53 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
                 CUDA_TRY(cudaMemcpyAsync(h->stage_dev + off, from, bytes, cudaMemcpyHostToDevice, h->copy_stream));
                 CUDA_TRY(cudaEventRecord(h->ev_chunk[c], h->copy_stream));
                 CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
-                launch_k1(h->stage_dev, first, count, nullptr);
+                launch_s1(h->stage_dev, first, count, 0);
             }
             CUDA_TRY(cudaEventRecord(h->ev_stage, h->copy_stream));
             rec(h, EV_H2D, st);
         }
         h->stage_busy = !pinned || staged;
         wait_for_input = pinned && !staged;              // the caller may reuse its buffer when we return
-        src = h->stage_dev;
     } else {
         rec(h, EV_H2D, st);
     }
+    rec(h, EV_POINTS, st);
 
-    Slot& s = h->slots[h->buffer_index];
-    const int cap = (int)h->cap;
-    rec(h, EV_RAYCAST, st);
-    if (h->p.xy_size % 8 == 0) {
-        launch(k_build_index<8>, dim3(h->grid_index), dim3(256), 0, st, h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
-                                                         s.cell_voxel, h->acc, s.minh, h->V, cap, s.gmask, h->done_flags, h->done_n, h->done_epoch);
-        s.has_gmask = true;
-    } else {
-        if (h->V % 4 == 0)
-            launch(k_build_index<4>, dim3(h->grid_index), dim3(256), 0, st, h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
-                                                             s.cell_voxel, h->acc, s.minh, h->V, cap, (unsigned*)nullptr, h->done_flags, h->done_n, h->done_epoch);
+    // ---- S2: cells of this scan; group mask of its slot; wipe of the slot that leaves the ring
+    const int ring_i = h->buffer_index;
+    const int leaving = h->phys[ring_i];
+    Slot& old = h->slots[leaving];
+    {
+        CellArgs A{};
+        A.map = s.index_map;
+        A.gmask = (p.xy_size % 8 == 0) ? s.gmask : nullptr;
+        A.cellid = h->cellid; A.tag = h->scan_tag;
+        A.counters = h->flags + 2 * par; A.counters_next = h->flags + 2 * (1 - par);
+        A.acc = h->acc; A.cell_voxel = s.cell_voxel;
+        A.hit = s.hit; A.total = s.total; A.metrics = s.metrics; A.slot_count = s.counter;
+        A.old_map = old.dirty ? old.index_map : nullptr;
+        A.old_gmask = (old.dirty && old.has_gmask) ? old.gmask : nullptr;
+        A.cap = (int)h->cap; A.ES = h->ES;
+        if (p.xy_eigen_dist == 1 && p.z_eigen_dist == 1)
+            launch(k_scan_cells<1, 1>, dim3(h->grid_scan_cells), dim3(256), 0, st, A, h->dp);
         else
-            launch(k_build_index<1>, dim3(h->grid_index), dim3(256), 0, st, h->hit_grid, h->total_grid, s.index_map, h->flags, s.hit, s.total,
-                                                             s.cell_voxel, h->acc, s.minh, h->V, cap, (unsigned*)nullptr, h->done_flags, h->done_n, h->done_epoch);
-        s.has_gmask = false;
-    }
-    h->stats.kernel_launches++;
-    rec(h, EV_INDEX, st);
-    {   // always launched (>= 1 block): thread 0 also publishes the slot's cell count
-        const int mb = nb > 0 ? nb : 1;
-        if (dtype == GVOM_F32)
-            launch(k_moments<float>, dim3(mb), dim3(256), 0, st, (const float*)src, stride, (int)n, tf_moments, fr, h->dp, s.index_map, h->acc, s.minh,
-                                                 h->flags, s.counter);
-        else
-            launch(k_moments<double>, dim3(mb), dim3(256), 0, st, (const double*)src, stride, (int)n, tf_moments, fr, h->dp, s.index_map, h->acc, s.minh,
-                                                  h->flags, s.counter);
+            launch(k_scan_cells<-1, -1>, dim3(h->grid_scan_cells), dim3(256), 0, st, A, h->dp);
         h->stats.kernel_launches++;
     }
-    rec(h, EV_MOMENTS, st);
-    launch_gather(h, s, st);
-    h->stats.kernel_launches++;
-    rec(h, EV_GATHER, st);
+    rec(h, EV_SCELLS, st);
     CUDA_TRY(cudaGetLastError());
     h->prof_process = h->profiling;
     // a caller-owned host buffer may be reused as soon as we return: wait for the transfer (not the kernels)
     if (wait_for_input) CUDA_TRY(cudaEventSynchronize(h->ev_stage));
 
     // gvom.py:198-216
+    s.has_gmask = p.xy_size % 8 == 0;
+    s.dirty = true;
     for (int k = 0; k < 3; ++k) s.origin[k] = fr.origin[k];
     s.valid = true;
-    s.seq = h->stats.process_calls + 1;
+    old.valid = false; old.dirty = false; old.has_gmask = false;      // wiped by S2 above (stream order)
+    h->phys[ring_i] = target;
+    h->spare = leaving;
     h->last_buffer_index = h->buffer_index;
     h->buffer_index = (h->buffer_index + 1) % p.buffer_size;
     h->stats.process_calls++;
@@ -835,6 +806,19 @@ int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_
     CUDA_TRY(cudaSetDevice(h->device));
     const CloudDesc cd{points, n, stride, dtype, mem, false, 0, 0, 0, 0};
     return process_locked(h, cd, ego, T, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int gvom_get_stream(GvomHandle* h, void** stream) {
+    if (!h || !stream) return fail(GVOM_EINVAL, "NULL argument");
+    *stream = (void*)h->stream;
+    return GVOM_OK;
+}
+
+int gvom_wait_input(GvomHandle* h) {
+    if (!h) return fail(GVOM_EINVAL, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->ev_input));
+    return GVOM_OK;
 }
 
 int gvom_process_pointcloud2(GvomHandle* h, const void* data, int64_t n, int32_t point_step, int32_t off_x,
@@ -859,7 +843,7 @@ int gvom_process_pointcloud2(GvomHandle* h, const void* data, int64_t n, int32_t
 static int combine_locked(GvomHandle* h, double origin[3], int32_t* positive, int32_t* negative, double* roughness,
                           int32_t* visibility, int32_t out_mem, cudaStream_t st, bool async) {
     if (int e = finish_outputs(h)) return e;                // a pending asynchronous combine owns the pinned mirrors
-    Slot& newest = h->slots[h->last_buffer_index];
+    Slot& newest = h->ring(h->last_buffer_index);
     if (!newest.valid) return GVOM_NO_DATA;                 // gvom.py:225-227
     h->active = st;
     rec(h, EV_CSTART, st);
@@ -870,7 +854,7 @@ static int combine_locked(GvomHandle* h, double origin[3], int32_t* positive, in
     // flags[1] (running cell counter) and the column minima are left clean by the previous combine's C4
     {
         MergeOut O{};
-        O.cmap = c.index_map; O.counter = h->flags + 1; O.cell_voxel = c.cell_voxel;
+        O.cmap = c.index_map; O.counter = h->flags + 4; O.cell_voxel = c.cell_voxel;
         O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
         O.gmask = (h->p.xy_size % 8 == 0) ? c.gmask : nullptr; O.cap = (int)h->ccap;
         launch_merge<MERGE_FULL>(h, A, O, st);
@@ -1046,7 +1030,7 @@ int gvom_slot_info(GvomHandle* h, int32_t slot, int32_t* valid, int64_t* cells, 
     if (!h || slot < 0 || slot >= h->p.buffer_size) return fail(GVOM_EINVAL, "bad slot");
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
-    Slot& s = h->slots[slot];
+    Slot& s = h->ring(slot);
     if (valid) *valid = s.valid ? 1 : 0;
     if (s.valid) {
         int cnt = 0;
@@ -1067,7 +1051,7 @@ int gvom_export_slot(GvomHandle* h, int32_t slot, int32_t* index_map, int32_t* h
     if (int e = gvom_slot_info(h, slot, &valid, &cells, nullptr)) return e;
     if (!valid) return GVOM_NO_DATA;
     std::lock_guard<std::mutex> lock(h->mu);
-    Slot& s = h->slots[slot];
+    Slot& s = h->ring(slot);
     if (index_map) CUDA_TRY(cudaMemcpy(index_map, s.index_map, sizeof(int) * (size_t)h->V, cudaMemcpyDeviceToHost));
     if (hit) CUDA_TRY(cudaMemcpy(hit, s.hit, sizeof(int) * (size_t)cells, cudaMemcpyDeviceToHost));
     if (total) CUDA_TRY(cudaMemcpy(total, s.total, sizeof(int) * (size_t)cells, cudaMemcpyDeviceToHost));
@@ -1121,10 +1105,10 @@ int gvom_stage_times(GvomHandle* h, float ms[16]) {
     CUDA_TRY(cudaSetDevice(h->device));
     for (int i = 0; i < 16; ++i) ms[i] = 0.f;
     CUDA_TRY(cudaStreamSynchronize(h->active));
-    if (h->prof_process) {
-        const int a[5] = {EV_START, EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS};
-        const int b[5] = {EV_H2D, EV_RAYCAST, EV_INDEX, EV_MOMENTS, EV_GATHER};
-        for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], h->ev[a[i]], h->ev[b[i]]));
+    if (h->prof_process) {          // [0] input staging, [1] S1 points (voxelise + claim + moments + ray-cast), [2] S2 cells
+        CUDA_TRY(cudaEventElapsedTime(&ms[0], h->ev[EV_START], h->ev[EV_H2D]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[1], h->ev[EV_H2D], h->ev[EV_POINTS]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[2], h->ev[EV_POINTS], h->ev[EV_SCELLS]));
     }
     ms[9] = h->last_stage_copy_ms;
     if (h->prof_x) {   // sharded multi-GPU combine: [10] slab cells, [11] signal + wait + gather maps, [12] gather cells
@@ -1170,7 +1154,7 @@ void state_sections(GvomHandle* h, const StateHeader& H, F&& visit) {
     const size_t V = (size_t)h->V, S2 = (size_t)h->S2, gm = V / 256 + 2;
     for (int i = 0; i < h->p.buffer_size; ++i) {
         if (!H.slot_valid[i]) continue;
-        Slot& s = h->slots[i];
+        Slot& s = h->ring(i);
         const size_t n = (size_t)H.slot_cells[i];
         visit(s.index_map, V * sizeof(int)); visit(s.gmask, gm * sizeof(unsigned));
         visit(s.hit, n * sizeof(int)); visit(s.total, n * sizeof(int)); visit(s.metrics, n * 10 * sizeof(double));
@@ -1201,7 +1185,7 @@ int fill_state_header(GvomHandle* h, StateHeader* H) {
     H->have_maps = h->have_maps ? 1 : 0;
     for (int k = 0; k < 3; ++k) H->ego[k] = h->ego[k];
     for (int i = 0; i < h->p.buffer_size; ++i) {
-        Slot& s = h->slots[i];
+        Slot& s = h->ring(i);
         H->slot_valid[i] = s.valid ? 1 : 0;
         if (!s.valid) continue;
         int cnt = 0;
@@ -1262,36 +1246,58 @@ int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes) {
     CUDA_TRY(cudaSetDevice(h->device));
     StateHeader H;
     memcpy(&H, blob, sizeof(H));
+    // ---- validate everything before the handle is touched (a rejected blob leaves it as it was)
     if (memcmp(H.magic, "GVOMST01", 8) != 0) return fail(GVOM_EINVAL, "not a gvom_b200 state blob");
-    if (memcmp(&H.p, &h->p, sizeof(GvomParams)) != 0 || H.max_points != h->max_points || H.ccap != h->ccap || H.V != h->V)
-        return fail(GVOM_EINVAL, "state blob was saved with different parameters / capacities");
+    if (memcmp(&H.p, &h->p, sizeof(GvomParams)) != 0 || H.V != h->V)
+        return fail(GVOM_EINVAL, "state blob was saved with different parameters");
+    // capacities may have GROWN since the blob was saved (the Python side re-creates the handle with a larger
+    // max_points when a bigger cloud arrives and carries the state over); shrinking is refused
+    if (H.max_points > h->max_points || H.cap > h->cap || H.ccap > h->ccap)
+        return fail(GVOM_EINVAL, "state blob was saved with larger capacities than this handle has");
+    for (int i = 0; i < h->p.buffer_size; ++i)
+        if (H.slot_valid[i] && (H.slot_cells[i] < 0 || H.slot_cells[i] > H.cap)) return fail(GVOM_EINVAL, "corrupt state blob (slot cells)");
+    if (H.comb_valid && (H.comb_cells < 0 || H.comb_cells > H.ccap)) return fail(GVOM_EINVAL, "corrupt state blob (combined cells)");
+    if (H.buffer_index < 0 || H.buffer_index >= h->p.buffer_size || H.last_buffer_index < 0 || H.last_buffer_index >= h->p.buffer_size)
+        return fail(GVOM_EINVAL, "corrupt state blob (ring position)");
+    {
+        const size_t V = (size_t)h->V, S2 = (size_t)h->S2, gm = V / 256 + 2;
+        auto pad = [](size_t b) { return (b + 15) & ~size_t(15); };
+        size_t total = sizeof(StateHeader);
+        for (int i = 0; i < h->p.buffer_size; ++i) {
+            if (!H.slot_valid[i]) continue;
+            const size_t n = (size_t)H.slot_cells[i];
+            total += pad(V * 4) + pad(gm * 4) + 2 * pad(n * 4) + pad(n * 80) + 2 * pad(n * 4) + pad(4);
+        }
+        if (H.comb_valid) {
+            const size_t n = (size_t)H.comb_cells;
+            total += pad(V * 4) + pad(gm * 4) + 3 * pad(n * 4) + pad(n * 40) + pad(n * 12) + pad(n * 4) + pad(4);
+        }
+        if (H.have_maps) total += pad(6 * S2 * 8) + pad((3 * S2 + 2 * S2 + 2) * 4);
+        if (total > bytes) return fail(GVOM_EINVAL, "state blob truncated");
+    }
     if (int e = finish_outputs(h)) return e;
     CUDA_TRY(cudaStreamSynchronize(h->active));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < h->p.buffer_size; ++i) {
-        if (H.slot_valid[i] && (H.slot_cells[i] < 0 || H.slot_cells[i] > h->cap)) return fail(GVOM_EINVAL, "corrupt state blob (slot cells)");
-    }
-    if (H.comb_valid && (H.comb_cells < 0 || H.comb_cells > h->ccap)) return fail(GVOM_EINVAL, "corrupt state blob (combined cells)");
-    // host state first: state_sections() walks the buffers the header describes
+    // ---- host state: ring entry i lives in physical slot i again, the extra slot is the (wiped) spare
     h->buffer_index = H.buffer_index; h->last_buffer_index = H.last_buffer_index;
     h->have_maps = H.have_maps != 0;
     for (int k = 0; k < 3; ++k) h->ego[k] = H.ego[k];
     for (int i = 0; i < h->p.buffer_size; ++i) {
+        h->phys[i] = i;
         Slot& s = h->slots[i];
         s.valid = H.slot_valid[i] != 0;
+        s.dirty = s.valid;
         s.has_gmask = s.valid && (h->p.xy_size % 8 == 0);
-        s.seq = s.valid ? h->stats.process_calls + 1000 + i : 0;   // a fresh scan counter: mirrors of the old content are stale
         for (int k = 0; k < 3; ++k) s.origin[k] = H.slot_origin[i][k];
     }
+    h->spare = h->p.buffer_size;
+    { Slot& sp = h->slots[h->spare]; sp.valid = false; sp.dirty = false; sp.has_gmask = false; }
     h->cur = 0;
     Combined& c = h->comb[0];
     c.valid = H.comb_valid != 0; c.cells = H.comb_cells; c.has_gmask = c.valid && (h->p.xy_size % 8 == 0);
     for (int k = 0; k < 3; ++k) c.origin[k] = H.comb_origin[k];
     h->comb[1].valid = false; h->comb[1].cells = 0;
     h->stats.combined_cells = c.cells;
-    size_t total = sizeof(StateHeader);
-    state_sections(h, H, [&](void*, size_t b) { total += (b + 15) & ~size_t(15); });
-    if (total > bytes) return fail(GVOM_EINVAL, "state blob truncated");
     const char* in = static_cast<const char*>(blob);
     size_t off = sizeof(StateHeader);
     cudaError_t err = cudaSuccess;
@@ -1300,16 +1306,22 @@ int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes) {
         off += (b + 15) & ~size_t(15);
     });
     // buffers the blob does not describe go back to their start-up state
+    const size_t gmb = sizeof(unsigned) * ((size_t)h->V / 256 + 2);
+    for (auto& sl : h->slots) {
+        if (sl.valid || err != cudaSuccess) continue;
+        err = cudaMemset(sl.index_map, 0xff, sizeof(int) * (size_t)h->V);
+        if (err == cudaSuccess) err = cudaMemset(sl.gmask, 0, gmb);
+    }
     for (int q = 0; q < 2 && err == cudaSuccess; ++q) {
         if (q == 0 && c.valid) continue;
         err = cudaMemset(h->comb[q].index_map, 0xff, sizeof(int) * (size_t)h->V);
-        if (err == cudaSuccess) err = cudaMemset(h->comb[q].gmask, 0, sizeof(unsigned) * ((size_t)h->V / 256 + 2));
+        if (err == cudaSuccess) err = cudaMemset(h->comb[q].gmask, 0, gmb);
     }
-    if (err == cudaSuccess) err = cudaMemset(h->hit_grid, 0, sizeof(int) * (size_t)h->V);
-    if (err == cudaSuccess) err = cudaMemset(h->total_grid, 0, sizeof(int) * (size_t)h->V);
+    if (err == cudaSuccess) err = cudaMemset(h->cellid, 0, sizeof(unsigned) * (size_t)h->EV);
     if (err == cudaSuccess) err = cudaMemset(h->flags, 0, sizeof(int) * 8);
     if (err == cudaSuccess) err = cudaMemset(h->col_minz, 0x7f, sizeof(int) * 2 * (size_t)h->S2);
     if (err != cudaSuccess) return fail(GVOM_ECUDA, std::string("gvom_load_state: ") + cudaGetErrorString(err));
+    h->scan_tag = 0;
     h->stage_busy = false;
     return GVOM_OK;
 }
@@ -1344,192 +1356,11 @@ int gvom_bench_atomics(int device, void* table_dev, int64_t table_words, int32_t
     return GVOM_OK;
 }
 
-// ------------------------------------------------------------- multi-GPU, direct exchange
-// Every rank's device workspace is mapped into every other rank (torch symmetric memory) and carved identically,
-// so a peer's ring slot is `peer base + the offset of my own slot`.  combine_maps then is the single-GPU combine
-// over ALL ranks' slots, read in place over NVLink by the same two kernels (row merge, cell merge): one pass
-// instead of partial + exchange + finish, results identical to one Gvom holding every rank's slots in rank order.
-// Protocol per combine `epoch` (no host synchronisation, no collective launch):
-//   publish : k_publish_slots writes this rank's slot table (valid, origin) into every rank's copy, then its
-//             "ready" flag = epoch                                   (after this rank's scan kernels, stream order)
-//   merge   : the row-merge kernel waits for all ready flags, then reads every slot in place
-//   done    : after the cell merge (the last reader of peer memory) k_signal writes the "done" flag = epoch into
-//             every rank; a rank's next scan waits for all done flags inside K2 before it overwrites a slot
-static int publish_slots_locked(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, cudaStream_t st) {
-    const int B = h->p.buffer_size, R = pl->nranks;
-    PublishArgs P{};
-    P.n = B; P.nranks = R;
-    for (int i = 0; i < B; ++i) {
-        const Slot& s = h->slots[i];
-        P.m[i].valid = s.valid ? 1 : 0;
-        P.m[i].ox = (int)s.origin[0]; P.m[i].oy = (int)s.origin[1]; P.m[i].oz = (int)s.origin[2];
-        P.m[i].newest = (s.valid && i == h->last_buffer_index) ? 1 : 0;
-        P.m[i].seq = (int)s.seq;
-    }
-    for (int r = 0; r < R; ++r) {
-        if (!pl->meta_rows[r] || !pl->ready_slots[r] || !pl->done_slots[r] || !pl->peer_ws[r]) return fail(GVOM_EINVAL, "NULL peer pointer");
-        P.row[r] = reinterpret_cast<SlotMeta*>(pl->meta_rows[r]);
-        P.flag[r] = pl->ready_slots[r];
-    }
-    launch(k_publish_slots, dim3(1), dim3(64), 0, st, P, (int)epoch);
-    h->stats.kernel_launches++;
-    CUDA_TRY(cudaGetLastError());
-    return GVOM_OK;
-}
-
-static int check_links(GvomHandle* h, const GvomPeerLinks* pl) {
-    if (!h || !pl) return fail(GVOM_EINVAL, "NULL argument");
-    if (pl->nranks < 1 || pl->nranks > MAX_RANKS || pl->rank < 0 || pl->rank >= pl->nranks) return fail(GVOM_EINVAL, "bad rank / nranks");
-    if ((int64_t)pl->nranks * h->p.buffer_size > MAX_SLOTS) return fail(GVOM_EINVAL, "nranks * buffer_size must be <= 64");
-    if (h->p.xy_size % 256 != 0) return fail(GVOM_EINVAL, "direct exchange needs xy_size % 256 == 0");
-    if (!pl->meta_table || !pl->ready_flags || !pl->done_flags) return fail(GVOM_EINVAL, "NULL table / flags");
-    return GVOM_OK;
-}
-
-int gvom_publish_slots(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, void* stream) {
-    if (int e = check_links(h, pl)) return e;
-    std::lock_guard<std::mutex> lock(h->mu);
-    CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    h->active = st;
-    return publish_slots_locked(h, pl, epoch, st);
-}
-
-static int64_t slot_stride_bytes(GvomHandle* h) {
-    if (h->p.buffer_size >= 2) return (const char*)h->slots[1].index_map - (const char*)h->slots[0].index_map;
-    const Slot& s = h->slots[0];
-    const int64_t end = ((const char*)s.gmask - (const char*)s.index_map) + (int64_t)sizeof(unsigned) * (h->V / 256 + 2);
-    return (end + 255) & ~int64_t(255);
-}
-
-int gvom_mirror_size(GvomHandle* h, int32_t nranks, uint64_t* bytes) {
-    if (!h || !bytes || nranks < 1 || nranks > MAX_RANKS) return fail(GVOM_EINVAL, "bad argument");
-    *bytes = (uint64_t)slot_stride_bytes(h) * (uint64_t)h->p.buffer_size * (uint64_t)nranks + 256;
-    return GVOM_OK;
-}
-
-// direct (pull = false) and pull exchange share everything but where the peers' slots are read from
-static int combine_peers(GvomHandle* h, const GvomPeerLinks* pl, bool pull, int32_t epoch, double origin[3], int32_t* positive,
-                         int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
-    if (int e = check_links(h, pl)) return e;
-    if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE && out_mem != GVOM_NONE) return fail(GVOM_EINVAL, "bad out_mem");
-    const int B = h->p.buffer_size, R = pl->nranks;
-    const int64_t stride = slot_stride_bytes(h);
-    if (pull && (!pl->mirror || !pl->mirror_seq || !pl->meta_snapshot || pl->mirror_bytes < (uint64_t)stride * B * R))
-        return fail(GVOM_EINVAL, "pull exchange: mirror buffers missing or too small (gvom_mirror_size)");
-    std::lock_guard<std::mutex> lock(h->mu);
-    CUDA_TRY(cudaSetDevice(h->device));
-    if (int e = finish_outputs(h)) return e;
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    h->active = st;
-    Slot& newest = h->slots[h->last_buffer_index];
-    // the combined origin: this rank's newest scan, or (a rank that has no scan yet) the origin the caller passes in
-    double org[3];
-    if (newest.valid) { for (int k = 0; k < 3; ++k) org[k] = newest.origin[k]; }
-    else if (origin && origin[0] == origin[0]) { for (int k = 0; k < 3; ++k) org[k] = origin[k]; }
-    else return GVOM_NO_DATA;
-    rec(h, EV_CSTART, st);
-    if (int e = publish_slots_locked(h, pl, epoch, st)) return e;
-    SignalSet done; done.n = R;
-    for (int r = 0; r < R; ++r) done.slot[r] = pl->done_slots[r];
-    if (pull) {
-        PullArgs PA{};
-        for (int r = 0; r < R; ++r) PA.peer_ws[r] = static_cast<const char*>(pl->peer_ws[r]);
-        PA.mirror = static_cast<char*>(pl->mirror);
-        const Slot& s0 = h->slots[0];
-        auto off = [&](const void* p) { return (long long)((const char*)p - (const char*)s0.index_map); };
-        PA.slot0 = (const char*)s0.index_map - h->dev_base; PA.slot_stride = stride;
-        PA.off_hit = off(s0.hit); PA.off_total = off(s0.total); PA.off_metrics = off(s0.metrics); PA.off_minh = off(s0.minh);
-        PA.off_counter = off(s0.counter); PA.off_gmask = off(s0.gmask);
-        PA.table = reinterpret_cast<const SlotMeta*>(pl->meta_table);
-        PA.snapshot = reinterpret_cast<SlotMeta*>(pl->meta_snapshot);
-        PA.mirror_seq = pl->mirror_seq; PA.ready_flags = pl->ready_flags;
-        PA.rank = pl->rank; PA.nranks = R; PA.B = B; PA.epoch = epoch;
-        PA.nseg = (int)(h->V >> 8); PA.cap = h->cap;
-        launch(k_pull_slots, dim3(h->sm_count * 8), dim3(256), 0, st, PA);
-        launch(k_pull_finish, dim3(1), dim3(256), 0, st, PA, done);
-        h->stats.kernel_launches += 2;
-    }
-    // sources: every rank's slots in rank order (own slots through own pointers), then my previous combined map
-    MergeArgs A;
-    A.n = 0; A.use_masks = 1;
-    A.meta = reinterpret_cast<const SlotMeta*>(pull ? pl->meta_snapshot : pl->meta_table);
-    A.cox = (int)org[0]; A.coy = (int)org[1]; A.coz = (int)org[2];
-    for (int r = 0; r < R; ++r) {
-        for (int i = 0; i < B; ++i) {
-            const Slot& s = h->slots[i];
-            // a peer's slot i: same offsets inside the peer's workspace (direct) or inside my mirror block (pull)
-            const char* mine = (const char*)s.index_map;
-            const char* base = r == pl->rank ? mine
-                             : pull ? static_cast<const char*>(pl->mirror) + ((int64_t)r * B + i) * stride
-                                    : static_cast<const char*>(pl->peer_ws[r]) + (mine - h->dev_base);
-            auto at = [&](const void* p) { return base + ((const char*)p - mine); };
-            SlotRef& q = A.s[A.n++];
-            q = SlotRef{};
-            q.map = reinterpret_cast<const int*>(at(s.index_map));
-            q.metrics = at(s.metrics);
-            q.hit = reinterpret_cast<const int*>(at(s.hit));
-            q.total = reinterpret_cast<const int*>(at(s.total));
-            q.minh = reinterpret_cast<const float*>(at(s.minh));
-            q.gmask = reinterpret_cast<const unsigned*>(at(s.gmask));
-            q.is_prev = 0;
-            q.meta = r * MAX_SLOTS + i;
-        }
-    }
-    Combined& pc = h->comb[h->cur];
-    if (pc.valid) {
-        SlotRef& q = A.s[A.n++];
-        q = SlotRef{};
-        q.map = pc.index_map; q.metrics = pc.metrics; q.hit = pc.hit; q.total = pc.total; q.minh = pc.minh;
-        q.dx = (int)(org[0] - pc.origin[0]); q.dy = (int)(org[1] - pc.origin[1]); q.dz = (int)(org[2] - pc.origin[2]);
-        q.is_prev = 1; q.meta = -1;
-        q.gmask = pc.gmask;
-    }
-    Combined& c = h->comb[1 - h->cur];
-    for (int k = 0; k < 3; ++k) c.origin[k] = org[k];
-    {
-        MergeOut O{};
-        O.cmap = c.index_map; O.counter = h->flags + 1; O.cell_voxel = c.cell_voxel;
-        O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
-        O.gmask = c.gmask; O.cap = (int)h->ccap;
-        if (!pull) { O.wait_flags = pl->ready_flags; O.wait_n = R; O.wait_epoch = epoch; }   // (the pull kernel has waited)
-        launch(k_merge_rows<3, true>, dim3(h->grid_rows3d), dim3(256), 0, st, A, O, h->dp);
-    }
-    rec(h, EV_CODES, st);
-    launch(k_merge_cells2<true>, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 1, c.cell_voxel, c.hit, c.total, c.minh, c.metrics,
-                                                          c.eig, h->dp, (int)h->ccap);
-    h->stats.kernel_launches += 2;
-    if (!pull) {   // last reader of peer memory is done: tell every rank
-        launch(k_signal, dim3(1), dim3(32), 0, st, done, (int)epoch);
-        h->stats.kernel_launches++;
-    }
-    rec(h, EV_CELLS, st);
-    h->prof_combine = h->profiling;
-    c.has_gmask = true;
-    h->done_flags = pl->done_flags; h->done_n = R; h->done_epoch = epoch;   // checked by the next scan's K2
-    if (int e = enqueue_maps_and_output(h, c, origin, positive, negative, roughness, visibility, out_mem, st)) return e;
-    if (int e = finish_outputs(h)) return e;
-    c.valid = true;
-    h->cur = 1 - h->cur;
-    h->stats.combine_calls++;
-    return GVOM_OK;
-}
-
-int gvom_combine_maps_direct(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, double origin[3], int32_t* positive,
-                             int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
-    return combine_peers(h, pl, false, epoch, origin, positive, negative, roughness, visibility, out_mem, stream);
-}
-
-int gvom_combine_maps_pull(GvomHandle* h, const GvomPeerLinks* pl, int32_t epoch, double origin[3], int32_t* positive,
-                           int32_t* negative, double* roughness, int32_t* visibility, int32_t out_mem, void* stream) {
-    return combine_peers(h, pl, true, epoch, origin, positive, negative, roughness, visibility, out_mem, stream);
-}
-
 // ------------------------------------------------------------- multi-GPU
 int gvom_newest_origin(GvomHandle* h, double origin[3]) {
     if (!h || !origin) return fail(GVOM_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lock(h->mu);
-    Slot& newest = h->slots[h->last_buffer_index];
+    Slot& newest = h->ring(h->last_buffer_index);
     if (!newest.valid) return GVOM_NO_DATA;
     for (int k = 0; k < 3; ++k) origin[k] = newest.origin[k];
     return GVOM_OK;
@@ -1614,7 +1445,7 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     double* cacc = h->cacc;
     {
         MergeOut O{};
-        O.cmap = c.index_map; O.counter = h->flags + 1; O.cell_voxel = c.cell_voxel;
+        O.cmap = c.index_map; O.counter = h->flags + 4; O.cell_voxel = c.cell_voxel;
         O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
         O.gmask = (h->p.xy_size % 8 == 0) ? c.gmask : nullptr; O.cap = (int)h->ccap;
         O.cacc = cacc; O.chit = c.hit; O.ctot = c.total; O.cminh = c.minh;
@@ -1624,7 +1455,7 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     rec(h, EV_CODES, st);
     launch(k_scatter_records, dim3(h->sm_count * 8), dim3(256), 0, st, R, record_capacity, c.index_map,
                                                       cacc, c.hit, c.total, c.minh);
-    launch(k_finish_cells, dim3(h->grid_cells), dim3(128), 0, st, prev, has_prev, h->flags + 1, c.cell_voxel, cacc, c.hit, c.total, c.minh,
+    launch(k_finish_cells, dim3(h->grid_cells), dim3(128), 0, st, prev, has_prev, h->flags + 4, c.cell_voxel, cacc, c.hit, c.total, c.minh,
                                                    c.metrics, c.eig, h->dp, (int)h->ccap);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 2;
@@ -1696,7 +1527,7 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     const SlabCells mine = slab_cells_at(res_cells[rank], res_capacity);
     if (phases & 1) {   // 1. my planes
         MergeOut O{};
-        O.cmap = res_maps[rank]; O.counter = h->flags + 1; O.cell_voxel = mine.voxel;
+        O.cmap = res_maps[rank]; O.counter = h->flags + 4; O.cell_voxel = mine.voxel;
         O.cap = (int)res_capacity;
         O.wait_flags = wait_partial; O.wait_n = nranks; O.wait_epoch = epoch;
         O.slab_r = rank; O.slab_n = nranks;
@@ -1706,7 +1537,7 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     {
         SignalSet CS; CS.n = nranks;
         for (int k = 0; k < nranks; ++k) CS.slot[k] = count_slots[k];
-        launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 1, mine, CS, h->dp,
+        launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 4, mine, CS, h->dp,
                (int)res_capacity, (int)record_capacity);
     }
     rec(h, EV_X0, st);
@@ -1720,7 +1551,7 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     if (!(phases & 2)) { CUDA_TRY(cudaGetLastError()); return GVOM_OK; }
     // 3. everybody's planes and cells
     launch(k_gather_maps, dim3(h->sm_count * h->gather_blocks), dim3(256), 0, st, R, wait_slab, (int)epoch, c.index_map, c.gmask, h->col_minz,
-           h->col_minz + h->S2, h->flags + 1, h->dp);
+           h->col_minz + h->S2, h->flags + 4, h->dp);
     rec(h, EV_X1, st);
     launch(k_gather_cells, dim3(h->sm_count * h->gather_blocks), dim3(256), 0, st, R, (long long)res_capacity, c.hit, c.total, c.minh, c.metrics,
            c.eig, c.cell_voxel, (int)h->ccap);

@@ -145,579 +145,6 @@ __device__ __forceinline__ bool world_from_raw(T p0, T p1, T p2, const Xform& tf
     return (d2 >= min_d2) && (d2 < CUDART_INF);
 }
 
-// ---------------------------------------------------------------------------
-// K1  voxelise + ray-cast.  Result of __point_2_map (gvom.py:1140-1231) on dense
-// hit / pass grids that are zero on entry.
-//   * one thread per point; the whole warp walks its 32 rays in lock step
-//   * every increment is warp-aggregated: runs of consecutive lanes that land in the
-//     same voxel are found with one shuffle + one vote and the run's first lane issues
-//     a single RED of the run length.  Azimuth-adjacent rays of a spinning lidar share
-//     most voxels, so this removes the bulk of the same-address traffic at the L2
-//     atomic units.
-//   * aggregation changes who issues the atomic, never the per-ray arithmetic.
-// ---------------------------------------------------------------------------
-// per-point part of K1 shared by every input layout: hit + DDA of one world-frame point per lane
-__device__ __forceinline__ void raycast_point(bool ok, double wx, double wy, double wz, const Frame& fr,
-                                              const DevParams& P, int* __restrict__ hit, int* __restrict__ total) {
-    const int lane = threadIdx.x & 31;
-    const double ox = fr.origin[0], oy = fr.origin[1], oz = fr.origin[2];
-    const double dS = (double)P.S, dZ = (double)P.Z;
-    // ---- hit (gvom.py:1153-1171)
-    double ex = 0, ey = 0, ez = 0;
-    bool inb = false;
-    int v = 0;
-    if (ok) {
-        ex = __ddiv_rn(wx, P.xy_res); ey = __ddiv_rn(wy, P.xy_res); ez = __ddiv_rn(wz, P.z_res);
-        const double xi = floor(__dsub_rn(ex, ox)), yi = floor(__dsub_rn(ey, oy)), zi = floor(__dsub_rn(ez, oz));
-        inb = (xi >= 0.0) && (xi < dS) && (yi >= 0.0) && (yi < dS) && (zi >= 0.0) && (zi < dZ);
-        if (inb) v = (int)xi + ((int)yi + (int)zi * P.S) * P.S;
-    }
-    {
-        const int key = inb ? v : ~lane;
-        const int prev_key = __shfl_up_sync(FULL, key, 1);
-        const bool head = (lane == 0) || (prev_key != key);
-        const unsigned heads = __ballot_sync(FULL, head);
-        if (inb && head) {
-            const unsigned above = heads & ~((2u << lane) - 1u);
-            const unsigned next = above & (0u - above);
-            const int c = __popc((next - 1u) & (0xffffffffu << lane));
-            atomicAdd(hit + v, c);
-            atomicAdd(total + v, c);
-        }
-    }
-
-    // ---- ray set-up (gvom.py:1174-1207): float32 state, float64 length
-    float px = fr.start[0], py = fr.start[1], pz = fr.start[2];
-    float ix = 0.f, iy = 0.f, iz = 0.f;
-    double dlen = 0.0, lim = 0.0, length = 0.0;
-    bool active = false;
-    if (ok) {
-        float sx = __fsub_rn((float)ex, px), sy = __fsub_rn((float)ey, py), sz = __fsub_rn((float)ez, pz);
-        float l2 = __fmul_rn(sx, sx);
-        l2 = __fmaf_rn(sy, sy, l2);
-        l2 = __fmaf_rn(sz, sz, l2);
-        const float L = __fsqrt_rn(l2);
-        sx = __fdiv_rn(sx, L); sy = __fdiv_rn(sy, L); sz = __fdiv_rn(sz, L);
-        const float a0 = fabsf(sx), a1 = fabsf(sy), a2 = fabsf(sz);
-        const float m = fmaxf(a0, fmaxf(a1, a2));
-        float sk = sx;                                   // dominant axis; later axis wins ties
-        if (m == a1) sk = sy;
-        if (m == a2) sk = sz;
-        lim = __dadd_rn((double)L, -1.0);
-        if (lim > 0.0) {
-            active = true;
-            const float ak = fabsf(sk);
-            ix = __fdiv_rn(sx, ak); iy = __fdiv_rn(sy, ak); iz = __fdiv_rn(sz, ak);
-            dlen = fabs(__drcp_rn((double)sk));
-        }
-    }
-
-    // ---- DDA (gvom.py:1208-1231), warp-synchronous and branch-free.
-    // The reference evaluates floor(float64(pt) - origin) per axis.  origin is integral and
-    // float64(pt) - origin is exact (24-bit pt, |origin| < 2^31), so floor(pt - origin) ==
-    // floorf(pt) - origin exactly: the loop runs on float32/int32 only, plus the float64
-    // length accumulation whose sequential rounding decides the trip count.  The ego voxel is
-    // the grid centre and a ray ends as soon as it leaves the grid, so pt stays within one
-    // voxel of the grid and the float->int conversions cannot overflow.
-    // Finished lanes keep stepping with zero increments and take a unique negative key in the
-    // match, so the only branch in the loop is the loop itself.
-    const int iox = (int)ox, ioy = (int)oy, ioz = (int)oz;
-    if (!active) { ix = 0.f; iy = 0.f; iz = 0.f; dlen = 0.0; }
-    unsigned any = __ballot_sync(FULL, active);
-    while (any) {
-        px = __fadd_rn(px, ix); py = __fadd_rn(py, iy); pz = __fadd_rn(pz, iz);
-        const int x = __float2int_rd(px) - iox, y = __float2int_rd(py) - ioy, z = __float2int_rd(pz) - ioz;
-        const bool inside = active && ((unsigned)x < (unsigned)P.S) && ((unsigned)y < (unsigned)P.S) &&
-                            ((unsigned)z < (unsigned)P.Z);
-        const int vv = x + (y + z * P.S) * P.S;
-        // warp aggregation by RUNS: consecutive lanes (neighbouring azimuths) in the same voxel form a run and
-        // its first lane adds the run length.  One shuffle + one vote instead of MATCH.ANY, whose latency was
-        // 36 % of this kernel's stall samples; equal voxels in non-adjacent lanes just cost one more RED.
-        const int key = inside ? vv : ~lane;                      // finished lanes: unique negative keys
-        const int prev_key = __shfl_up_sync(FULL, key, 1);
-        const bool head = (lane == 0) || (prev_key != key);
-        const unsigned heads = __ballot_sync(FULL, head);
-        if (inside && head) {
-            const unsigned above = heads & ~((2u << lane) - 1u);  // heads after my lane
-            const unsigned next = above & (0u - above);           // lowest of them (0: my run ends the warp)
-            atomicAdd(total + vv, __popc((next - 1u) & (0xffffffffu << lane)));
-        }
-        length = __dadd_rn(length, dlen);
-        active = inside && (length < lim);
-        any = __ballot_sync(FULL, active);
-    }
-}
-
-
-template <typename T>
-__global__ void __launch_bounds__(256, 8)
-k_voxelize_raycast(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevParams P,
-                   int* __restrict__ hit, int* __restrict__ total, T* __restrict__ world_out) {
-    pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-
-    double wx = 0, wy = 0, wz = 0;
-    bool ok = false;
-    if (world_out) {
-        // zero-copy mode: pts is pinned HOST memory, read over PCIe exactly once.  The block's
-        // contiguous chunk (256 points) is fetched with 128-bit coalesced loads into shared memory
-        // (every byte requested once, full-width PCIe reads), then each thread picks its point.
-        // The transformed point (in the cloud's dtype, as the reference stores it back,
-        // gvom.py:1136-1138) is kept in HBM for the moment pass.
-        __shared__ uint4 chunk[256 * 4 * sizeof(double) / 16];
-        const long long first = (long long)blockIdx.x * blockDim.x;
-        const int cnt = (int)min((long long)blockDim.x, (long long)n - first);
-        const size_t bytes = (size_t)cnt * stride * sizeof(T);
-        const char* g = reinterpret_cast<const char*>(pts + first * stride);
-        const int n16 = (int)(bytes >> 4);
-        for (int k = threadIdx.x; k < n16; k += blockDim.x)
-            chunk[k] = __ldg(reinterpret_cast<const uint4*>(g) + k);
-        if (threadIdx.x < (int)(bytes & 15))                  // tail bytes (none when the chunk is full)
-            reinterpret_cast<char*>(chunk)[(n16 << 4) + threadIdx.x] = g[(n16 << 4) + threadIdx.x];
-        __syncthreads();
-        if (i < n) {
-            const T* q = reinterpret_cast<const T*>(chunk) + (long long)threadIdx.x * stride;
-            ok = world_from_raw<T>(q[0], q[1], q[2], tf, P.min_d2, wx, wy, wz);
-            T* w = world_out + (long long)i * stride;
-            w[0] = (T)wx; w[1] = (T)wy; w[2] = (T)wz;
-        }
-    } else if (i < n) {
-        ok = load_world<T>(pts, stride, i, tf, P.min_d2, wx, wy, wz);
-    }
-
-    raycast_point(ok, wx, wy, wz, fr, P, hit, total);
-}
-
-// K1 for PointCloud2 wire records (sensor_msgs/PointCloud2: n records of point_step bytes, float32 x / y / z
-// at byte offsets ox / oy / oz).  Replaces ros_numpy.point_cloud2.pointcloud2_to_xyz_array + Process_pointcloud
-// (gvom_ros.py:108-109): the float32 fields are widened to float64 (what ros_numpy hands the reference), NaN / Inf
-// points are dropped (ros_numpy's remove_nans), and everything downstream is the float64 path.  The transformed
-// points are kept in HBM (float64 x 3) for the moment pass.  Packed 16-byte records (x, y, z, pad) -- the layout
-// the host-side field extraction produces -- are read with one 128-bit load per point.
-__global__ void __launch_bounds__(256, 8)
-k_voxelize_raycast_pc2(const char* __restrict__ data, int point_step, int offx, int offy, int offz, int n, Xform tf,
-                       Frame fr, DevParams P, int* __restrict__ hit, int* __restrict__ total,
-                       double* __restrict__ world_out) {
-    pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double wx = 0, wy = 0, wz = 0;
-    bool ok = false;
-    if (i < n) {
-        const char* q = data + (size_t)i * point_step;
-        float x, y, z;
-        if (point_step == 16 && offx == 0 && offy == 4 && offz == 8) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(q));
-            x = v.x; y = v.y; z = v.z;
-        } else {
-            x = __ldg(reinterpret_cast<const float*>(q + offx));
-            y = __ldg(reinterpret_cast<const float*>(q + offy));
-            z = __ldg(reinterpret_cast<const float*>(q + offz));
-        }
-        ok = world_from_raw<double>((double)x, (double)y, (double)z, tf, P.min_d2, wx, wy, wz);
-        double* w = world_out + (long long)i * 3;
-        w[0] = wx; w[1] = wy; w[2] = wz;
-    }
-    raycast_point(ok, wx, wy, wz, fr, P, hit, total);
-}
-
-// ---------------------------------------------------------------------------
-// K2  index map + compaction.  Result of __assign_indices + __move_data x2
-// (gvom.py:1233-1247) without the host round trip of gvom.py:172: the cell count
-// stays on the device and compact arrays are sized for the worst case.  Also
-// re-zeroes the dense grids for the next scan (replaces the three fill launches
-// of gvom.py:125-131) and initialises the per-cell accumulators
-// (gvom.py:1079-1085).  Compact ids are allotted per warp (ballots + one atomic).
-// VEC = 4: 128-bit loads/stores, four voxels per thread (needs V % 4 == 0).
-// ---------------------------------------------------------------------------
-template <int VEC>
-__global__ void __launch_bounds__(256)
-k_build_index(int* __restrict__ hit, int* __restrict__ total, int* __restrict__ index_map,
-              int* __restrict__ counter, int* __restrict__ hit_c, int* __restrict__ total_c,
-              int* __restrict__ cell_voxel, double* __restrict__ acc, float* __restrict__ minh,
-              long long V, int cap, unsigned* __restrict__ gmask,
-              const int* __restrict__ wait_flags, int wait_n, int wait_epoch) {
-    pdl_wait();
-    // direct multi-GPU exchange: peers read this rank's slots in place; do not overwrite one before every rank has
-    // finished the combine that read it
-    wait_flags_block(wait_flags, wait_n, wait_epoch);
-    constexpr int U = 2;                                // items in flight per thread
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    const long long NQ = V / VEC;                       // items of VEC voxels
-    const long long NQp = (NQ + 31) & ~31LL;
-    for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < NQp; q0 += nthreads * U) {
-        int h[U][VEC], t[U][VEC];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long q = q0 + u * nthreads;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) { h[u][j] = 0; t[u][j] = 0; }
-            if (q < NQ) {
-                if (VEC >= 4) {
-#pragma unroll
-                    for (int g = 0; g < VEC / 4; ++g) {
-                        const int4 hv = reinterpret_cast<const int4*>(hit)[q * (VEC / 4) + g];
-                        const int4 tv = reinterpret_cast<const int4*>(total)[q * (VEC / 4) + g];
-                        h[u][4 * g] = hv.x; h[u][4 * g + (VEC > 1 ? 1 : 0)] = hv.y; h[u][4 * g + (VEC > 2 ? 2 : 0)] = hv.z; h[u][4 * g + (VEC > 3 ? 3 : 0)] = hv.w;
-                        t[u][4 * g] = tv.x; t[u][4 * g + (VEC > 1 ? 1 : 0)] = tv.y; t[u][4 * g + (VEC > 2 ? 2 : 0)] = tv.z; t[u][4 * g + (VEC > 3 ? 3 : 0)] = tv.w;
-                    }
-                } else {
-                    h[u][0] = hit[q]; t[u][0] = total[q];
-                }
-            }
-        }
-        // compact ids: one atomic per warp and item; all of them are issued before the first result is consumed
-        // (an atomic round trip to L2 is as long as the loads above)
-        unsigned mm[U][VEC];
-        int base_u[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long q = q0 + u * nthreads;
-            int nocc = 0;
-            base_u[u] = 0;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) { mm[u][j] = 0; }
-            if (q < NQp) {                              // warp-uniform: NQp and q0 are multiples of 32 apart
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) { mm[u][j] = __ballot_sync(FULL, h[u][j] > 0); nocc += __popc(mm[u][j]); }
-                if (nocc && lane == 0) base_u[u] = atomicAdd(counter, nocc);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long q = q0 + u * nthreads;
-            if (q >= NQp) break;                        // warp-uniform
-            unsigned m[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) m[j] = mm[u][j];
-            int base = __shfl_sync(FULL, base_u[u], 0);
-            bool known_any = false;
-            if (q < NQ) {
-                int code[VEC];
-                bool anyh = false, anyt = false;
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    code[j] = -t[u][j] - 1;
-                    if (h[u][j] > 0) {
-                        const int id = base + __popc(m[j] & lt);
-                        if (id < cap) {
-                            code[j] = id;
-                            hit_c[id] = h[u][j]; total_c[id] = t[u][j]; cell_voxel[id] = (int)(q * VEC + j); minh[id] = 1.0f;
-                            double2* a = reinterpret_cast<double2*>(acc + (long long)id * ACC);
-#pragma unroll
-                            for (int k = 0; k < ACC / 2; ++k) a[k] = make_double2(0.0, 0.0);
-                        }
-                    }
-                    base += __popc(m[j]);
-                    anyh |= h[u][j] != 0; anyt |= t[u][j] != 0;
-                }
-                if (VEC >= 4) {
-#pragma unroll
-                    for (int g = 0; g < VEC / 4; ++g) {
-                        reinterpret_cast<int4*>(index_map)[q * (VEC / 4) + g] =
-                            make_int4(code[4 * g], code[4 * g + (VEC > 1 ? 1 : 0)], code[4 * g + (VEC > 2 ? 2 : 0)], code[4 * g + (VEC > 3 ? 3 : 0)]);
-                        if (anyt) reinterpret_cast<int4*>(total)[q * (VEC / 4) + g] = make_int4(0, 0, 0, 0);
-                        if (anyh) reinterpret_cast<int4*>(hit)[q * (VEC / 4) + g] = make_int4(0, 0, 0, 0);
-                    }
-                } else {
-                    index_map[q] = code[0];
-                    if (anyt) total[q] = 0;
-                    if (anyh) hit[q] = 0;
-                }
-                known_any = anyt;                       // a voxel is known iff a ray touched it (total > 0)
-            }
-            if (VEC == 8) {                             // one bit per 8-voxel group: "anything known in here"
-                const unsigned w = __ballot_sync(FULL, known_any);
-                if (lane == 0 && q < NQ) gmask[q >> 5] = w;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// K3  per-point moment accumulation.  Together with K4 it produces the result of
-// __calculate_mean/__normalize_mean/__calculate_covariance/__normalize_covariance
-// and __calculate_min_height (gvom.py:1249-1421).
-// The reference scatters every point into every occupied voxel of its
-// (2rx+1)^2(2rz+1) neighbourhood, twice (16.6 M float64 atomics per OS1-128 scan).
-// Here a point only adds its raw first/second moments (about its own voxel's
-// centre) to its OWN cell, and K4 gathers the neighbourhood.  Consecutive points
-// of a spinning lidar mostly fall into the same voxel, so each warp first reduces
-// runs of equal voxel id with a segmented shuffle scan and only the head lane of a
-// run issues the 10 float64 REDs (+1 min): ~5x fewer atomics again.
-// Points whose own voxel lies outside the grid still reach in-grid neighbours in
-// the reference (gvom.py:1262-1279); they are rare and are scattered directly into
-// the neighbour's "apron" accumulators.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double seg_add(double v, int offset, bool take) {
-    const double t = __shfl_down_sync(FULL, v, offset);
-    return take ? v + t : v;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_moments(const T* __restrict__ pts, int stride, int n, Xform tf, Frame fr, DevParams P,
-          const int* __restrict__ index_map, double* __restrict__ acc, float* __restrict__ minh,
-          const int* __restrict__ scratch_count, int* __restrict__ slot_count) {
-    pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    if (i == 0) *slot_count = *scratch_count;             // K2's running counter -> the slot's cell count
-    double wx = 0, wy = 0, wz = 0;
-    bool ok = false;
-    if (i < n) ok = load_world<T>(pts, stride, i, tf, P.min_d2, wx, wy, wz);
-    double fx = 0, fy = 0, fz = 0, bx = 0, by = 0, bz = 0;
-    bool inb = false;
-    if (ok) {
-        fx = __dsub_rn(__ddiv_rn(wx, P.xy_res), fr.origin[0]);
-        fy = __dsub_rn(__ddiv_rn(wy, P.xy_res), fr.origin[1]);
-        fz = __dsub_rn(__ddiv_rn(wz, P.z_res), fr.origin[2]);
-        bx = floor(fx); by = floor(fy); bz = floor(fz);
-        const double dS = (double)P.S, dZ = (double)P.Z;
-        inb = (bx >= 0.0) && (bx < dS) && (by >= 0.0) && (by < dS) && (bz >= 0.0) && (bz < dZ);
-    }
-    // ---- own-voxel accumulation, run-reduced within the warp
-    int id = -1 - lane;                                   // distinct negative keys: never equal to a neighbour
-    double q[10];
-    float lzf = 1.0f;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) q[k] = 0.0;
-    if (inb) {
-        const int v = (int)bx + ((int)by + (int)bz * P.S) * P.S;
-        const int c = index_map[v];
-        if (c >= 0) {                                     // < 0 only on compact-capacity overflow
-            id = c;
-            const double lz = __dsub_rn(fz, bz);
-            const double qx = (fx - bx) - 0.5, qy = (fy - by) - 0.5, qz = lz - 0.5;
-            q[0] = qx; q[1] = qy; q[2] = qz;
-            q[3] = qx * qx; q[4] = qx * qy; q[5] = qx * qz; q[6] = qy * qy; q[7] = qy * qz; q[8] = qz * qz;
-            q[9] = 1.0;
-            lzf = (float)lz;                              // min height: float32 of the in-voxel z fraction
-        }
-    }
-    const int id_up = __shfl_up_sync(FULL, id, 1);
-    const bool head = (lane == 0) || (id_up != id);
-    // distance (in lanes) to the end of my run = number of following lanes with the same id
-    const unsigned heads = __ballot_sync(FULL, head);
-    const unsigned after = heads & ~((2u << lane) - 1u);  // heads strictly above my lane
-    const int run_end = after ? (__ffs(after) - 2) : 31;  // last lane of my run
-    // (runs are short: the scan stops at the longest run of this warp instead of always taking five steps)
-    const int max_d = __reduce_max_sync(FULL, run_end - lane);
-    for (int off = 1; off <= max_d; off <<= 1) {
-        const bool take = (lane + off) <= run_end;
-#pragma unroll
-        for (int k = 0; k < 10; ++k) q[k] = seg_add(q[k], off, take);
-        const float t = __shfl_down_sync(FULL, lzf, off);
-        if (take) lzf = fminf(lzf, t);
-    }
-    if (head && id >= 0) {
-        double* a = acc + (long long)id * ACC;
-#pragma unroll
-        for (int k = 0; k < 10; ++k) atomicAdd(a + k, q[k]);
-        atomicMin(reinterpret_cast<int*>(minh) + id, __float_as_int(lzf));   // values in [0,1]: ordered as int bits
-    }
-    // ---- apron: own voxel outside the grid; walk the neighbourhood like the reference does
-    if (ok && !inb) {
-        const double dS = (double)P.S, dZ = (double)P.Z;
-        const double rx = (double)P.rx, rz = (double)P.rz;
-        if (bx < -rx - 1.0 || bx > dS + rx || by < -rx - 1.0 || by > dS + rx || bz < -rz - 1.0 || bz > dZ + rz) return;
-        const int x0 = (int)bx - P.rx, y0 = (int)by - P.rx, z0 = (int)bz - P.rz;
-        for (int z = z0; z <= z0 + 2 * P.rz; ++z) {
-            if (z < 0 || z >= P.Z) continue;
-            for (int y = y0; y <= y0 + 2 * P.rx; ++y) {
-                if (y < 0 || y >= P.S) continue;
-                for (int x = x0; x <= x0 + 2 * P.rx; ++x) {
-                    if (x < 0 || x >= P.S) continue;
-                    const int nid = index_map[x + (y + z * P.S) * P.S];
-                    if (nid < 0) continue;
-                    const double qx = (fx - (double)x) - 0.5, qy = (fy - (double)y) - 0.5, qz = (fz - (double)z) - 0.5;
-                    double* a = acc + (long long)nid * ACC + 10;
-                    atomicAdd(a + 0, qx); atomicAdd(a + 1, qy); atomicAdd(a + 2, qz);
-                    atomicAdd(a + 3, qx * qx); atomicAdd(a + 4, qx * qy); atomicAdd(a + 5, qx * qz);
-                    atomicAdd(a + 6, qy * qy); atomicAdd(a + 7, qy * qz); atomicAdd(a + 8, qz * qz);
-                    atomicAdd(a + 9, 1.0);
-                }
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// K4  neighbourhood gather: metrics[id] = {mean xyz, cov xx xy xz yy yz zz, n}
-// of all points within (rx, rx, rz) voxels, in coordinates relative to the cell's
-// own voxel corner (the reference's local_point, gvom.py:1283-1285).
-// A neighbour's raw moments are about ITS centre; shifting by the integer voxel
-// offset d gives moments about this cell's centre:
-//   S' = S + n d,  Q'_ab = Q_ab + d_a S_b + S_a d_b + n d_a d_b.
-// LPC (4) lanes per cell: each lane takes every 4th neighbour (independent loads in
-// flight), two shuffle steps reduce the group; 30 k cells x 4 lanes fill the GPU, which
-// one thread per cell would not, and a whole warp per cell spends its time in shuffles.
-// ---------------------------------------------------------------------------
-constexpr int LPC = 4;
-
-template <int RX, int RZ>      // compile-time neighbourhood radius (RX < 0: runtime P.rx / P.rz)
-__global__ void __launch_bounds__(256)
-k_gather_metrics(const int* __restrict__ index_map, const int* __restrict__ cell_voxel,
-                 const int* __restrict__ counter, const double* __restrict__ acc,
-                 double* __restrict__ metrics, DevParams P, int cap, int* __restrict__ scratch_count) {
-    pdl_wait();
-    const int count = min(*counter, cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *scratch_count = 0;   // ready for the next scan's K2
-    const int sub = threadIdx.x & (LPC - 1);
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / LPC;
-    const int ngroups = (gridDim.x * blockDim.x) / LPC;
-    const int rx = RX >= 0 ? RX : P.rx, rz = RX >= 0 ? RZ : P.rz;
-    const int wx = 2 * rx + 1, wz = 2 * rz + 1;
-    const int nn = wx * wx * wz;
-    const int per_lane = (nn + LPC - 1) / LPC;
-    const int count_pad = (count + (32 / LPC) - 1) / (32 / LPC) * (32 / LPC);   // whole warps iterate together
-    for (int id = gid; id < count_pad; id += ngroups) {
-        double r[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) r[k] = 0.0;
-        if (id < count) {
-            const int v = cell_voxel[id];
-            const int x = v % P.S, y = (v / P.S) % P.S, z = v / (P.S * P.S);
-#pragma unroll 7
-            for (int u = 0; u < per_lane; ++u) {
-                const int j = sub + u * LPC;
-                if (j >= nn) continue;
-                const int dx = j % wx - rx, dy = (j / wx) % wx - rx, dz = j / (wx * wx) - rz;
-                const int xx = x + dx, yy = y + dy, zz = z + dz;
-                if (xx < 0 || xx >= P.S || yy < 0 || yy >= P.S || zz < 0 || zz >= P.Z) continue;
-                const int nid = __ldg(index_map + (xx + (yy + zz * P.S) * P.S));
-                if (nid < 0) continue;
-                const double2* a2 = reinterpret_cast<const double2*>(acc + (long long)nid * ACC);
-                const double2 a01 = a2[0], a23 = a2[1], a45 = a2[2], a67 = a2[3], a89 = a2[4];
-                const double a0 = a01.x, a1 = a01.y, a2v = a23.x, an = a89.y;
-                const double ddx = (double)dx, ddy = (double)dy, ddz = (double)dz;
-                r[0] += a0 + an * ddx; r[1] += a1 + an * ddy; r[2] += a2v + an * ddz;
-                r[3] += a23.y + 2.0 * ddx * a0 + an * ddx * ddx;
-                r[4] += a45.x + ddx * a1 + ddy * a0 + an * ddx * ddy;
-                r[5] += a45.y + ddx * a2v + ddz * a0 + an * ddx * ddz;
-                r[6] += a67.x + 2.0 * ddy * a1 + an * ddy * ddy;
-                r[7] += a67.y + ddy * a2v + ddz * a1 + an * ddy * ddz;
-                r[8] += a89.x + 2.0 * ddz * a2v + an * ddz * ddz;
-                r[9] += an;
-            }
-        }
-#pragma unroll
-        for (int off = LPC / 2; off > 0; off >>= 1)
-#pragma unroll
-            for (int k = 0; k < 10; ++k) r[k] += __shfl_xor_sync(FULL, r[k], off);
-        if (sub == 0 && id < count) {
-            const double* e = acc + (long long)id * ACC + 10;
-#pragma unroll
-            for (int k = 0; k < 10; ++k) r[k] += e[k];
-            const double n = r[9];
-            double* mo = metrics + (long long)id * 10;
-            const double m0 = r[0] / n, m1 = r[1] / n, m2 = r[2] / n;
-            mo[0] = m0 + 0.5; mo[1] = m1 + 0.5; mo[2] = m2 + 0.5;
-            mo[3] = r[3] / n - m0 * m0; mo[4] = r[4] / n - m0 * m1; mo[5] = r[5] / n - m0 * m2;
-            mo[6] = r[6] / n - m1 * m1; mo[7] = r[7] / n - m1 * m2; mo[8] = r[8] / n - m2 * m2;
-            mo[9] = n;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// K4 (second build)  same results as k_gather_metrics, restructured for memory-level parallelism: 8 lanes per
-// cell, each lane first issues ALL its neighbour look-ups (independent loads, no branches between them) and only
-// then fetches the moments of the occupied ones, so a cell costs ~3 dependent memory round trips instead of up
-// to 2 x 7.  Three shuffle steps reduce the group.
-// ---------------------------------------------------------------------------
-constexpr int LPC2 = 8;
-
-template <int RX, int RZ, int MINB>      // compile-time neighbourhood radius (RX < 0: runtime P.rx / P.rz); blocks per SM
-__global__ void __launch_bounds__(256, MINB)
-k_gather_metrics2(const int* __restrict__ index_map, const int* __restrict__ cell_voxel,
-                  const int* __restrict__ counter, const double* __restrict__ acc,
-                  double* __restrict__ metrics, DevParams P, int cap, int* __restrict__ scratch_count) {
-    pdl_wait();
-    const int count = min(*counter, cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *scratch_count = 0;   // ready for the next scan's K2
-    const int sub = threadIdx.x & (LPC2 - 1);
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / LPC2;
-    const int ngroups = (gridDim.x * blockDim.x) / LPC2;
-    const int rx = RX >= 0 ? RX : P.rx, rz = RX >= 0 ? RZ : P.rz;
-    const int wx = 2 * rx + 1, wz = 2 * rz + 1;
-    const int nn = wx * wx * wz;
-    constexpr int CH = 4;                                  // look-ups in flight per lane
-    const int count_pad = (count + (32 / LPC2) - 1) / (32 / LPC2) * (32 / LPC2);   // whole warps iterate together
-    for (int id = gid; id < count_pad; id += ngroups) {
-        double r[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) r[k] = 0.0;
-        double apron_n = 0.0;                               // fetched early: decides whether the apron block is read at all
-        if (id < count) {
-            if (sub == 0) apron_n = acc[(long long)id * ACC + 19];
-            const int v = cell_voxel[id];
-            const int x = v % P.S, y = (v / P.S) % P.S, z = v / (P.S * P.S);
-            for (int j0 = sub; j0 < nn; j0 += LPC2 * CH) {
-                int nid[CH];
-#pragma unroll
-                for (int u = 0; u < CH; ++u) {
-                    const int j = j0 + u * LPC2;
-                    const int dx = j % wx - rx, dy = (j / wx) % wx - rx, dz = j / (wx * wx) - rz;
-                    const int xx = x + dx, yy = y + dy, zz = z + dz;
-                    const bool in = j < nn && (unsigned)xx < (unsigned)P.S && (unsigned)yy < (unsigned)P.S && (unsigned)zz < (unsigned)P.Z;
-                    nid[u] = in ? __ldg(index_map + (xx + (yy + zz * P.S) * P.S)) : -1;
-                }
-                // two-deep pipeline over the occupied neighbours: record u+1 is in flight while record u is folded in
-                double2 rb[2][5];
-#pragma unroll
-                for (int g = 0; g < 5; ++g) { rb[0][g] = make_double2(0.0, 0.0); rb[1][g] = make_double2(0.0, 0.0); }
-                if (nid[0] >= 0) {
-                    const double2* a2 = reinterpret_cast<const double2*>(acc + (long long)nid[0] * ACC);
-#pragma unroll
-                    for (int g = 0; g < 5; ++g) rb[0][g] = a2[g];
-                }
-#pragma unroll
-                for (int u = 0; u < CH; ++u) {
-                    if (u + 1 < CH && nid[u + 1 < CH ? u + 1 : u] >= 0) {
-                        const double2* a2 = reinterpret_cast<const double2*>(acc + (long long)nid[u + 1 < CH ? u + 1 : u] * ACC);
-#pragma unroll
-                        for (int g = 0; g < 5; ++g) rb[(u + 1) & 1][g] = a2[g];
-                    }
-                    if (nid[u] < 0) continue;
-                    const double2 a01 = rb[u & 1][0], a23 = rb[u & 1][1], a45 = rb[u & 1][2], a67 = rb[u & 1][3], a89 = rb[u & 1][4];
-                    const double a0 = a01.x, a1 = a01.y, a2v = a23.x, an = a89.y;
-                    const int j = j0 + u * LPC2;                     // offset of this neighbour (recomputed: cheaper than keeping it)
-                    const double ddx = (double)(j % wx - rx), ddy = (double)((j / wx) % wx - rx), ddz = (double)(j / (wx * wx) - rz);
-                    r[0] += a0 + an * ddx; r[1] += a1 + an * ddy; r[2] += a2v + an * ddz;
-                    r[3] += a23.y + 2.0 * ddx * a0 + an * ddx * ddx;
-                    r[4] += a45.x + ddx * a1 + ddy * a0 + an * ddx * ddy;
-                    r[5] += a45.y + ddx * a2v + ddz * a0 + an * ddx * ddz;
-                    r[6] += a67.x + 2.0 * ddy * a1 + an * ddy * ddy;
-                    r[7] += a67.y + ddy * a2v + ddz * a1 + an * ddy * ddz;
-                    r[8] += a89.x + 2.0 * ddz * a2v + an * ddz * ddz;
-                    r[9] += an;
-                }
-            }
-        }
-#pragma unroll
-        for (int off = LPC2 / 2; off > 0; off >>= 1)
-#pragma unroll
-            for (int k = 0; k < 10; ++k) r[k] += __shfl_xor_sync(FULL, r[k], off);
-        if (sub == 0 && id < count) {
-            if (apron_n != 0.0) {                           // out-of-grid points that reached this cell (rare)
-                const double* e = acc + (long long)id * ACC + 10;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) r[k] += e[k];
-                r[9] += apron_n;
-            }
-            const double n = r[9];
-            double* mo = metrics + (long long)id * 10;
-            const double m0 = r[0] / n, m1 = r[1] / n, m2 = r[2] / n;
-            mo[0] = m0 + 0.5; mo[1] = m1 + 0.5; mo[2] = m2 + 0.5;
-            mo[3] = r[3] / n - m0 * m0; mo[4] = r[4] / n - m0 * m1; mo[5] = r[5] / n - m0 * m2;
-            mo[6] = r[6] / n - m1 * m1; mo[7] = r[7] / n - m1 * m2; mo[8] = r[8] / n - m2 * m2;
-            mo[9] = n;
-        }
-    }
-}
-
 // ===========================================================================
 // combine_maps
 // ===========================================================================
@@ -730,28 +157,12 @@ struct SlotRef {
     int dx, dy, dz;          // combined_origin - source_origin, voxels
     int is_prev;             // 1: previous combined map (float32 metrics, [-11,-1] rule)
     const unsigned* gmask;   // one bit per 8-voxel group: something known in the group (NULL: no mask)
-    int meta;                // >= 0: validity and origin come from MergeArgs.meta[meta] (a peer rank's slot), dx/dy/dz unused
 };
-// What a rank publishes about one of its ring slots for the direct multi-GPU exchange (written into every
-// rank's table before the rank's "ready" flag; origins are integral voxel units, |origin| < 1e9).
-struct SlotMeta { int valid, ox, oy, oz, newest, seq, pad1, pad2; };   // seq: scan counter of the rank when the slot was written
 struct MergeArgs {
     SlotRef s[MAX_SLOTS + 1];
     int n;
     int use_masks;           // every source carries a group mask
-    const SlotMeta* meta;    // direct exchange: table of all ranks' slots (local copy), else NULL
-    int cox, coy, coz;       // direct exchange: combined origin (the shifts are formed on the device)
 };
-
-// shift of source k into the combined frame; false = the source holds nothing (direct exchange: slot not valid)
-template <bool DIRECT>
-__device__ __forceinline__ bool src_shift(const MergeArgs& A, int k, int& dx, int& dy, int& dz) {
-    const SlotRef& s = A.s[k];
-    if (!DIRECT || s.meta < 0) { dx = s.dx; dy = s.dy; dz = s.dz; return true; }
-    const int4 m = __ldcg(reinterpret_cast<const int4*>(A.meta + s.meta));     // {valid, ox, oy, oz}
-    dx = A.cox - m.y; dy = A.coy - m.z; dz = A.coz - m.w;
-    return m.x != 0;
-}
 
 // ---------------------------------------------------------------------------
 // C1  merged code per voxel.  Result of __combine_indices run once per slot in
@@ -1060,11 +471,10 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
 //     buffer's own group mask says it already holds "unknown" there (both combined-map buffers start as all
 //     unknown with an empty mask, and every writer keeps map and mask consistent).
 // ---------------------------------------------------------------------------
-template <int NB, bool DIRECT>
+template <int NB>
 __global__ void __launch_bounds__(256, (NB > 3) ? 2 : 3)
 k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
     pdl_wait();
-    if (DIRECT) wait_flags_block(O.wait_flags, O.wait_n, O.wait_epoch);   // peers' slots are read in place
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int S = P.S, Z = P.Z;
@@ -1081,11 +491,10 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
         unsigned word = 0;
         if (k < A.n) {
             const SlotRef& s = A.s[k];
-            int dx, dy, dz;
-            const bool valid = src_shift<DIRECT>(A, k, dx, dy, dz);
+            const int dx = s.dx, dy = s.dy, dz = s.dz;
             const int ys = y + dy, zs = z + dz;
             const int wi = ((x0s + dx) >> 8) + which;                    // floor: source word of the segment start, +1
-            if (valid && (unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z && wi >= 0 && wi < spr)
+            if ((unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z && wi >= 0 && wi < spr)
                 word = __ldg(s.gmask + (zs * S + ys) * spr + wi);
         }
         return word;
@@ -1115,8 +524,7 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
                         const unsigned w0 = __shfl_sync(FULL, word, k - kb), w1 = __shfl_sync(FULL, word, 16 + k - kb);
                         if ((w0 | w1) != 0) {                             // uniform: the source holds something in this segment
                             const SlotRef& s = A.s[k];
-                            int dx, dy, dz;
-                            src_shift<DIRECT>(A, k, dx, dy, dz);          // (valid: its mask words are non-zero)
+                            const int dx = s.dx, dy = s.dy, dz = s.dz;
                             const int sx0 = x0s + dx;
                             const unsigned long long Wd = ((unsigned long long)w1 << 32) | w0;
                             const int b = ((sx0 >> 3) & 31) + lane;       // my first voxel's group, relative to word 0
@@ -1280,69 +688,6 @@ __device__ __forceinline__ void merge_step(float* c, const double* o) {
 }
 
 // ---------------------------------------------------------------------------
-// C2  per-cell record merge + eigenvalues.  Result of __combine_metrics run per
-// slot and for the previous map (gvom.py:280-298, 888-980) and of
-// __calculate_eigenvalues (gvom.py:318), one thread per combined cell, sources
-// folded in the reference's order so the float32 rounding sequence is the same.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_merge_cells(MergeArgs A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
-              int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
-              float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap) {
-    pdl_wait();
-    const int count = min(*counter, cap);
-    const int S = P.S, Z = P.Z;
-    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
-        const int v = cell_voxel[id];
-        const int x = v % S, y = (v / S) % S, z = v / (S * S);
-        float c[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) c[k] = 0.f;
-        int hit = 0, tot = 0;
-        float mh = 1.0f;
-        for (int k0 = 0; k0 < A.n; k0 += SLOT_BATCH) {
-            int io[SLOT_BATCH];
-#pragma unroll
-            for (int u = 0; u < SLOT_BATCH; ++u) {                  // independent index loads first
-                io[u] = -1;
-                if (k0 + u < A.n) {
-                    const SlotRef& s = A.s[k0 + u];
-                    const int xs = x + s.dx, ys = y + s.dy, zs = z + s.dz;
-                    if (!(xs < 0 || xs >= S || ys < 0 || ys >= S || zs < 0 || zs >= Z))
-                        io[u] = __ldg(s.map + (xs + (ys + (long long)zs * S) * S));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < SLOT_BATCH; ++u) {
-                if (io[u] < 0) continue;
-                const SlotRef& s = A.s[k0 + u];
-                double o[10];
-                if (s.is_prev) {
-                    const float2* om = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(s.metrics) + (long long)io[u] * 10);
-#pragma unroll
-                    for (int a = 0; a < 5; ++a) { const float2 t = om[a]; o[2 * a] = (double)t.x; o[2 * a + 1] = (double)t.y; }
-                } else {
-                    const double2* om = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(s.metrics) + (long long)io[u] * 10);
-#pragma unroll
-                    for (int a = 0; a < 5; ++a) { const double2 t = om[a]; o[2 * a] = t.x; o[2 * a + 1] = t.y; }
-                }
-                merge_step(c, o);
-                hit += s.hit[io[u]];
-                tot += s.total[io[u]];
-                mh = fminf(mh, s.minh[io[u]]);
-            }
-        }
-        float* mo = cmet + (long long)id * 10;
-#pragma unroll
-        for (int k = 0; k < 10; ++k) mo[k] = c[k];
-        chit[id] = hit; ctot[id] = tot; cminh[id] = mh;
-        float e[3];
-        eigen3(c, e);
-        ceig[id * 3 + 0] = e[0]; ceig[id * 3 + 1] = e[1]; ceig[id * 3 + 2] = e[2];
-    }
-}
-
-// ---------------------------------------------------------------------------
 // C2 (second build)  same results and the same fold order as k_merge_cells; the look-ups of ALL sources of a
 // cell are issued together (up to 8 per round) instead of in batches of SLOT_BATCH.  (A build that also fetched the
 // next record while merging the current one needed 96 registers and lost more to occupancy than it gained.)
@@ -1362,7 +707,6 @@ __device__ __forceinline__ void load_cell_rec(const SlotRef& s, int io, CellRec&
     r.hit = s.hit[io]; r.tot = s.total[io]; r.mh = s.minh[io];
 }
 
-template <bool DIRECT>
 __global__ void __launch_bounds__(128, 8)
 k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
                int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
@@ -1386,10 +730,8 @@ k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restri
                 io[u] = -1;
                 if (k0 + u < A.n) {
                     const SlotRef& s = A.s[k0 + u];
-                    int dx, dy, dz;
-                    const bool valid = src_shift<DIRECT>(A, k0 + u, dx, dy, dz);
-                    const int xs = x + dx, ys = y + dy, zs = z + dz;
-                    if (valid && (unsigned)xs < (unsigned)S && (unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z)
+                    const int xs = x + s.dx, ys = y + s.dy, zs = z + s.dz;
+                    if ((unsigned)xs < (unsigned)S && (unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z)
                         io[u] = __ldg(s.map + (xs + (ys + zs * S) * S));
                 }
             }
@@ -1471,212 +813,6 @@ k_column_maps(const int* __restrict__ cmap, const float* __restrict__ cminh, con
         const int xx = blockIdx.x * 32 + threadIdx.x;
         if (xx < S) known[(long long)xx * W + blockIdx.y] = w;
     }
-}
-
-// first set bit with index in [lo, hi] of a bit row, or -1
-__device__ __forceinline__ int first_known(const unsigned* row, int lo, int hi) {
-    for (int w = lo >> 5; w <= (hi >> 5); ++w) {
-        unsigned m = row[w];
-        if (w == (lo >> 5)) m &= 0xffffffffu << (lo & 31);
-        if (w == (hi >> 5)) m &= 0xffffffffu >> (31 - (hi & 31));
-        if (m) return (w << 5) + __ffs(m) - 1;
-    }
-    return -1;
-}
-
-// ---------------------------------------------------------------------------
-// C4  surface maps.  Result of __calculate_slope, __guess_height,
-// __make_positive_obstacle_map, __make_negative_obstacle_map and
-// __make_visability_map (gvom.py:444-452, 505-555, 592-805) and their fills, one
-// thread per map cell (the slope of the own cell is all the positive-obstacle test
-// needs).  Thread <-> y fastest: height-map reads of a warp are contiguous.
-// The ring search of __guess_height walks up to 4x15 row/column segments per cell;
-// here each segment is one or two words of the "height known" bit maps and a
-// find-first-set, and only the found cell's height is loaded.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_surface_maps(const int* __restrict__ cmap, const int* __restrict__ chit, const int* __restrict__ ctot,
-               const double* __restrict__ height, const double* __restrict__ inferred,
-               const unsigned* __restrict__ known_g, const unsigned* __restrict__ knownT_g, double o2,
-               DevParams P, double* __restrict__ rough, double* __restrict__ xs, double* __restrict__ ys,
-               double* __restrict__ guessed, int* __restrict__ pos, int* __restrict__ neg, int* __restrict__ vis,
-               int masks_in_smem, int* __restrict__ col_minz, int* __restrict__ scratch_count) {
-    pdl_wait();
-    extern __shared__ unsigned smask[];
-    const int S = P.S, Z = P.Z;
-    const int W = (S + 31) >> 5;
-    // 128 cells per block, two warp-groups: warps 0-3 fit the plane (slope, roughness, positive
-    // obstacles), warps 4-7 run the ring search (guessed height, negative obstacles, visibility).  The
-    // two chains are independent and both latency bound, so running them side by side doubles the
-    // warps an SM can switch between.
-    const int role = threadIdx.x >> 7;
-    const int t = blockIdx.x * 128 + (threadIdx.x & 127);
-    // both bit maps (2*S*W words, 16 KB at S = 256) go to shared memory when they fit: the ring
-    // search then never waits on L2
-    const unsigned* known = known_g;
-    const unsigned* knownT = knownT_g;
-    if (masks_in_smem) {
-        const int nw4 = (2 * S * W) >> 2;                  // known and knownT are contiguous; S*W % 2 == 0 here
-        const uint4* g4 = reinterpret_cast<const uint4*>(known_g);
-        uint4* s4 = reinterpret_cast<uint4*>(smask);
-#pragma unroll 4
-        for (int k = threadIdx.x; k < nw4; k += blockDim.x) s4[k] = __ldg(g4 + k);
-        __syncthreads();
-        known = smask;
-        knownT = smask + S * W;
-    }
-    if (t >= S * S) return;
-    const int y0 = t % S, x0 = t / S;
-    if (role == 1) {
-    // housekeeping for the next combine: C1's column minima and running counter start clean
-    col_minz[t] = 0x7f7f7f7f;
-    col_minz[S * S + t] = 0x7f7f7f7f;
-    if (t == 0) *scratch_count = 0;
-    const double h0 = GVOM_HM(height, x0, y0);
-
-    // ---- guessed height delta (gvom.py:592-713), quirks kept (see oracle/gvom_oracle.c)
-    double dh_out = 0.0;
-    const double inf0 = GVOM_HM(inferred, x0, y0);
-    if (!(h0 > -1000.0) && inf0 != -1000.0) {
-        bool xpd = false, xnd = false, ypd = false, ynd = false;
-        double x_ph = -1000.0, x_nh = -1000.0, y_ph = -1000.0, y_nh = -1000.0;
-        int i = 0;
-        while (i < 15 && !(xnd && ypd && ynd)) {          // x_p_done is NOT part of the condition (gvom.py:619)
-            i += 1;
-            const int x_p = x0 + i, x_n = x0 - i, y_p = y0 + i, y_n = y0 - i;
-            if (!xpd) {
-                if (x_p < S) {                            // y in [y0-i, y0+i-1], ascending
-                    const int f = first_known(known + (long long)x_p * W, max(0, y0 - i), min(S - 1, y0 + i - 1));
-                    if (f >= 0) { x_ph = GVOM_HM(height, x_p, f); xpd = true; }
-                } else xpd = true;
-            }
-            if (!xnd) {
-                if (x_n >= 0) {                           // y in [y0-i+1, y0+i]
-                    const int f = first_known(known + (long long)x_n * W, max(0, y0 - i + 1), min(S - 1, y0 + i));
-                    if (f >= 0) { x_nh = GVOM_HM(height, x_n, f); xnd = true; }
-                } else xnd = true;
-            }
-            if (!ypd) {
-                if (y_p < S) {                            // x in [x0-i+1, x0+i]
-                    const int f = first_known(knownT + (long long)y_p * W, max(0, x0 - i + 1), min(S - 1, x0 + i));
-                    if (f >= 0) { y_ph = GVOM_HM(height, f, y_p); ypd = true; }
-                } else ypd = true;
-            }
-            if (!ynd) {
-                if (y_n >= 0) {                           // x in [x0-i, x0+i-1]
-                    const int f = first_known(knownT + (long long)y_n * W, max(0, x0 - i), min(S - 1, x0 + i - 1));
-                    if (f >= 0) { y_nh = GVOM_HM(height, f, y_n); ynd = true; }
-                } else ynd = true;
-            }
-        }
-        double mn = 1000.0, mx = inf0;
-        if (x_ph > -1000.0) { mn = fmin(x_ph, mn); mx = fmax(x_ph, mx); }
-        if (x_nh > -1000.0) { mn = fmin(x_nh, mn); mx = fmax(x_nh, mx); }
-        if (y_ph > -1000.0) { mn = fmin(y_ph, mn); mx = fmax(y_ph, mx); }
-        if (x_nh > -1000.0) { mn = fmin(y_nh, mn); mx = fmax(y_nh, mx); }   // sic (gvom.py:704-706)
-        const double dh = __dsub_rn(mx, mn);
-        if (dh > 0.0) dh_out = dh;
-    }
-    GVOM_HM(guessed, x0, y0) = dh_out;
-    GVOM_HM(neg, x0, y0) = dh_out > P.neg_thr ? 100 : 0;
-    GVOM_HM(vis, x0, y0) = h0 > -1000.0 ? 1 : 0;
-    return;
-    }
-
-    // ---- slope + roughness (gvom.py:717-805); contraction pattern = SASS of the reference.
-    // 3x3 neighbourhood in registers, visited in the reference's order (x outer, y inner).
-    double hz[9];
-    unsigned okm = 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            const int x = x0 - 1 + a, y = y0 - 1 + b;
-            double h = -1000.0;
-            if (x >= 0 && x < S && y >= 0 && y < S) h = GVOM_HM(height, x, y);
-            hz[a * 3 + b] = h;
-            if (h > -1000.0) okm |= 1u << (a * 3 + b);
-        }
-    const double h0 = hz[4];
-    double sxv = 0.0, syv = 0.0, rg = -1.0;
-    const int n = __popc(okm);
-    if (n >= 3) {
-        double sx = 0, sy = 0, sz = 0;
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-            if (okm & (1u << j)) {
-                sx = __dadd_rn(sx, __dmul_rn((double)(x0 - 1 + j / 3), P.xy_res));
-                sy = __dadd_rn(sy, __dmul_rn((double)(y0 - 1 + j % 3), P.xy_res));
-                sz = __dadd_rn(sz, hz[j]);
-            }
-        const double dn = (double)n;
-        const double mx = __ddiv_rn(sx, dn), my = __ddiv_rn(sy, dn), mz = __ddiv_rn(sz, dn);
-        double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0;
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-            if (okm & (1u << j)) {
-                const double dx = __dsub_rn(__dmul_rn((double)(x0 - 1 + j / 3), P.xy_res), mx);
-                const double dy = __dsub_rn(__dmul_rn((double)(y0 - 1 + j % 3), P.xy_res), my);
-                const double dz = __dsub_rn(hz[j], mz);
-                xx = __fma_rn(dx, dx, xx); xy = __fma_rn(dx, dy, xy); xz = __fma_rn(dx, dz, xz);
-                yy = __fma_rn(dy, dy, yy); yz = __fma_rn(dy, dz, yz);
-            }
-        const double det = __fma_rn(xx, yy, -__dmul_rn(xy, xy));
-        if (det != 0.0) {
-            double a0 = __ddiv_rn(__fma_rn(xz, yy, -__dmul_rn(xy, yz)), det);
-            double a1 = __ddiv_rn(__fma_rn(xx, yz, -__dmul_rn(xy, xz)), det);
-            const double m = __dsqrt_rn(__dadd_rn(__fma_rn(a0, a0, __dmul_rn(a1, a1)), 1.0));
-            a0 = __ddiv_rn(a0, m); a1 = __ddiv_rn(a1, m);
-            double err = 0.0;
-#pragma unroll
-            for (int j = 0; j < 9; ++j)
-                if (okm & (1u << j)) {
-                    const double dx = __dsub_rn(__dmul_rn((double)(x0 - 1 + j / 3), P.xy_res), mx);
-                    const double dy = __dsub_rn(__dmul_rn((double)(y0 - 1 + j % 3), P.xy_res), my);
-                    const double e = __dsub_rn(__dsub_rn(hz[j], mz), __fma_rn(a0, dx, __dmul_rn(a1, dy)));
-                    err = __fma_rn(e, e, err);
-                }
-            err = __ddiv_rn(err, dn);
-            if (err > 0.0) err = log(err);
-            rg = err;
-            const double im = __drcp_rn(m);
-            sxv = atan2(a0, im);
-            syv = atan2(a1, im);
-        }
-    }
-    GVOM_HM(rough, x0, y0) = rg;
-    GVOM_HM(xs, x0, y0) = sxv;
-    GVOM_HM(ys, x0, y0) = syv;
-
-    // ---- positive obstacles (gvom.py:515-555)
-    int pv = 0;
-    const double sl = __dsqrt_rn(__fma_rn(sxv, sxv, __dmul_rn(syv, syv)));
-    if (!(sl < P.slope_thr)) {
-        pv = 100;
-    } else {
-        const double lo = floor(__dsub_rn(__ddiv_rn(__dadd_rn(h0, P.pos_thr), P.z_res), o2));
-        const double hi = floor(__dsub_rn(__ddiv_rn(__dadd_rn(h0, P.robot_height), P.z_res), o2));
-        if (lo > -2.0e9 && lo < 2.0e9 && hi > -2.0e9 && hi < 2.0e9) {
-            const long long zlo = (long long)lo + 1, zhi = (long long)hi;
-            if (zlo >= 0 && zlo < Z && zhi >= 0 && zhi < Z) {
-                double density = 0.0, nn = 0.0;
-                for (long long zb = zlo; zb <= zhi; zb += 8) {        // 8 levels per batch: loads first
-                    int idx[8], hc[8], tc[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        idx[u] = (zb + u <= zhi) ? __ldg(cmap + (x0 + (y0 + (zb + u) * S) * S)) : -1;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) { hc[u] = idx[u] >= 0 ? __ldg(chit + idx[u]) : 0; tc[u] = idx[u] >= 0 ? __ldg(ctot + idx[u]) : 0; }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (hc[u] > 10) { nn = __dadd_rn(nn, (double)tc[u]); density = __dadd_rn(density, (double)hc[u]); }
-                }
-                if (nn > 0.0) density = __ddiv_rn(density, nn);
-                pv = (int)__dmul_rn(density, 100.0);
-            }
-        }
-    }
-    GVOM_HM(pos, x0, y0) = pv;
 }
 
 // 32 bits of a bit row starting at bit position `pos` (may be negative / run past the row: those bits read 0)
@@ -2023,115 +1159,6 @@ __global__ void k_signal(SignalSet S, int epoch) {
     if (threadIdx.x < S.n) {
         volatile int* f = S.slot[threadIdx.x];
         *f = epoch;
-    }
-    __threadfence_system();
-}
-
-// direct exchange: write this rank's slot descriptions into row `rank` of every rank's table, then the ready flag
-struct PublishArgs { SlotMeta m[MAX_SLOTS]; int n; SlotMeta* row[MAX_RANKS]; int* flag[MAX_RANKS]; int nranks; };
-__global__ void k_publish_slots(PublishArgs A, int epoch) {
-    pdl_wait();                                   // after this rank's scan kernels
-    __threadfence_system();
-    for (int r = 0; r < A.nranks; ++r)
-        for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
-            int4* d = reinterpret_cast<int4*>(A.row[r] + i);
-            const SlotMeta& m = A.m[i];
-            d[0] = make_int4(m.valid, m.ox, m.oy, m.oz);
-            d[1] = make_int4(m.newest, m.seq, 0, 0);
-        }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < A.nranks) {
-        volatile int* f = A.flag[threadIdx.x];
-        *f = epoch;
-    }
-    __threadfence_system();
-}
-
-// ---------------------------------------------------------------------------
-// "pull" exchange: instead of reading the peers' slots in place (every dependent access an NVLink round trip), each
-// rank keeps a MIRROR of every peer's ring slots in its own HBM and refreshes, once per combine, only the slots
-// whose scan counter changed -- one bulk, coalesced, mask-aware copy over NVLink (a 256-voxel segment is fetched
-// only if the peer's group mask says it holds anything; it is cleared only if the mirror held something) -- and then
-// runs the ordinary single-GPU combine over own slots + mirrors.
-// ---------------------------------------------------------------------------
-struct PullArgs {
-    const char* peer_ws[MAX_RANKS];   // device workspace base of every rank
-    char* mirror;                     // [nranks][B] slot blocks (same internal layout as a slot in the workspace)
-    long long slot0, slot_stride;     // offset of slot 0 in a workspace, distance between slots
-    long long off_hit, off_total, off_metrics, off_minh, off_counter, off_gmask;   // inside a slot block (index map at 0)
-    const SlotMeta* table;            // local table all ranks publish into
-    SlotMeta* snapshot;               // private copy the merge kernels read (peers may republish while they run)
-    int* mirror_seq;                  // [nranks*MAX_SLOTS] scan counter of the mirrored copy (0: nothing mirrored)
-    const int* ready_flags;
-    int rank, nranks, B, epoch;
-    int nseg;                         // V / 256
-    long long cap;                    // cells a slot can hold
-};
-
-__global__ void __launch_bounds__(256)
-k_pull_slots(PullArgs A) {
-    pdl_wait();
-    wait_flags_block(A.ready_flags, A.nranks, A.epoch);
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
-    if (blockIdx.x == 0)                                  // snapshot of the whole table (own row included)
-        for (int i = threadIdx.x; i < A.nranks * MAX_SLOTS * 2; i += blockDim.x)
-            reinterpret_cast<int4*>(A.snapshot)[i] = __ldcg(reinterpret_cast<const int4*>(A.table) + i);
-    for (int r = 0; r < A.nranks; ++r) {
-        if (r == A.rank) continue;
-        for (int i = 0; i < A.B; ++i) {
-            const int4 m0 = __ldcg(reinterpret_cast<const int4*>(A.table + r * MAX_SLOTS + i));
-            const int4 m1 = __ldcg(reinterpret_cast<const int4*>(A.table + r * MAX_SLOTS + i) + 1);
-            const int seq = m1.y;
-            if (!m0.x || seq == A.mirror_seq[r * MAX_SLOTS + i]) continue;      // invalid or already mirrored (uniform)
-            const char* src = A.peer_ws[r] + A.slot0 + (long long)i * A.slot_stride;
-            char* dst = A.mirror + ((long long)r * A.B + i) * A.slot_stride;
-            // index map + group mask, one warp per 256-voxel segment
-            const unsigned* sg = reinterpret_cast<const unsigned*>(src + A.off_gmask);
-            unsigned* dg = reinterpret_cast<unsigned*>(dst + A.off_gmask);
-            const bool had = A.mirror_seq[r * MAX_SLOTS + i] != 0;
-            for (int seg = warp; seg < A.nseg; seg += warps) {
-                const unsigned w = __ldg(sg + seg);
-                const unsigned old = had ? dg[seg] : 0xffffffffu;                // first fill: the mirror holds garbage
-                int4* d = reinterpret_cast<int4*>(dst) + (long long)seg * 64 + lane * 2;
-                if (w) {
-                    const int4* q = reinterpret_cast<const int4*>(src) + (long long)seg * 64 + lane * 2;
-                    const int4 a = __ldg(q), b = __ldg(q + 1);
-                    d[0] = a; d[1] = b;
-                } else if (old) {
-                    d[0] = make_int4(-1, -1, -1, -1); d[1] = make_int4(-1, -1, -1, -1);
-                }
-                if (lane == 0 && (w | old)) dg[seg] = w;
-            }
-            // compact arrays, truncated to the slot's cell count
-            const long long n = min((long long)__ldg(reinterpret_cast<const int*>(src + A.off_counter)), A.cap);
-            const long long offs[4] = {A.off_hit, A.off_total, A.off_minh, A.off_metrics};
-            const long long bytes[4] = {4 * n, 4 * n, 4 * n, 80 * n};
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const long long units = (bytes[a] + 15) >> 4;                   // arrays are 256-byte aligned: whole 16-byte units
-                const int4* q = reinterpret_cast<const int4*>(src + offs[a]);
-                int4* d = reinterpret_cast<int4*>(dst + offs[a]);
-                for (long long u = tid; u < units; u += nthreads) d[u] = __ldg(q + u);
-            }
-        }
-    }
-}
-
-// after the pull: remember what is mirrored, then tell every rank this one no longer needs their slots
-__global__ void k_pull_finish(PullArgs A, SignalSet done) {
-    pdl_wait();
-    for (int k = threadIdx.x; k < A.nranks * MAX_SLOTS; k += blockDim.x) {
-        const int r = k / MAX_SLOTS, i = k % MAX_SLOTS;
-        if (r != A.rank && i < A.B && A.snapshot[k].valid) A.mirror_seq[k] = A.snapshot[k].seq;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < done.n) {
-        volatile int* f = done.slot[threadIdx.x];
-        *f = A.epoch;
     }
     __threadfence_system();
 }

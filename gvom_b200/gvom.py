@@ -11,7 +11,9 @@ tensors own the device and pinned workspaces) and one ctypes call per method.
 All computation is in hand-written sm_100a CUDA behind the C-ABI; there is no
 Numba, Triton or CPU fallback.
 """
+import collections
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -30,16 +32,14 @@ def _torch():
 
 
 class Gvom:
-    """
-    A class to take lidar scans and create a costmap (B200-native build)\n
-    xy_resolution:  x,y resolution in metres of each voxel\n
-    z_resolution:   z resolution in metres of each voxel\n
-    xy_size:        Number of voxels in x,y\n
-    z_size:         Number of voxels in z\n
-    buffer_size:    Number of lidar scans to keep in memory\n
-    min_distance:   Minimum point distance, any points closer than this will be discarded\n
-    Keyword-only extras (not in the reference): max_points (capacity of one scan),
-    device (CUDA ordinal), max_combined_cells, pinned_outputs.
+    """Lidar scans in, 2-D cost maps out (B200-native build of the reference class `Gvom`).
+
+    The 14 positional arguments are the reference's (gvom.py:21-22), same order and meaning: voxel
+    resolutions [m] and grid sizes [voxels] in xy and z, number of scans kept in the ring buffer, minimum point
+    range, the obstacle / slope thresholds, robot height and radius, lidar height above ground, and the
+    neighbourhood radii (voxels) of the per-voxel covariance.
+    Keyword-only extras (not in the reference): max_points (initial capacity of one scan; grows on demand),
+    device (CUDA ordinal), max_combined_cells, pinned_outputs, stream.
     """
 
     def __init__(self, xy_resolution, z_resolution, xy_size, z_size, buffer_size, min_distance,
@@ -73,19 +73,41 @@ class Gvom:
                              float(negative_obstacle_threshold), float(slope_obsacle_threshold),
                              float(robot_height), float(robot_radius), float(ground_to_lidar_height),
                              self.xy_eigen_dist, self.z_eigen_dist)
+        self._max_combined_cells = int(max_combined_cells)
+        self._inflight = collections.deque()     # (event, CUDA input tensor) of scans whose kernels may still be running
+        self._lock = threading.Lock()            # callback threads (README.md:49: several sensors) share one handle
+        self._create()
+        self._org_c = (C.c_double * 3)()
+
+    def _create(self):
+        """Allocate the workspaces (torch owns the memory; raw pointers cross the ABI) and create the handle."""
+        torch = self._torch
         db, hb = C.c_size_t(0), C.c_size_t(0)
-        check(self._L.gvom_workspace_size(C.byref(self._P), self.max_points, int(max_combined_cells),
+        check(self._L.gvom_workspace_size(C.byref(self._P), self.max_points, self._max_combined_cells,
                                           C.byref(db), C.byref(hb)), "gvom_workspace_size")
-        # torch owns the memory; raw pointers cross the ABI
         self._dev_ws = self._alloc_device_ws(db.value)
         self._host_ws = torch.empty(hb.value, dtype=torch.uint8, pin_memory=True)
         h = C.c_void_p()
-        check(self._L.gvom_create(C.byref(self._P), self.max_points, int(max_combined_cells), self.device,
+        check(self._L.gvom_create(C.byref(self._P), self.max_points, self._max_combined_cells, self.device,
                                   self._dev_ws.data_ptr(), db.value, self._host_ws.data_ptr(), hb.value,
                                   C.byref(h)), "gvom_create")
         self._h = h
-        self._ego_c = (C.c_double * 3)()
-        self._org_c = (C.c_double * 3)()
+        # torch view of the stream the library works on (ordering / lifetime of CUDA-tensor inputs)
+        sp = C.c_void_p()
+        check(self._L.gvom_get_stream(self._h, C.byref(sp)), "gvom_get_stream")
+        raw = self._stream.value if self._stream is not None else sp.value
+        self._work_stream = torch.cuda.ExternalStream(raw, device=torch.device(f"cuda:{self.device}"))
+
+    def _grow(self, n_points):
+        """A cloud larger than the current capacity arrived (the reference has no limit: it allocates per scan,
+        gvom.py:115-131): re-create the handle with twice the room and carry the ring buffer over."""
+        blob = self.save_state()
+        old_h, old_ws = self._h, (self._dev_ws, self._host_ws)
+        self.max_points = max(2 * self.max_points, 1 << (int(n_points) - 1).bit_length())
+        self._create()
+        self.load_state(blob)
+        self._L.gvom_destroy(old_h)
+        del old_ws
 
     def _alloc_device_ws(self, nbytes):
         """Device workspace (torch owns it).  MultiGpuGvom overrides this to place it in symmetric memory."""
@@ -99,8 +121,9 @@ class Gvom:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.gvom_destroy(self._h)
+            self._L.gvom_destroy(self._h)           # synchronises the handle's stream
             self._h = None
+            self._inflight.clear()
 
     # ------------------------------------------------------------------ scans
     def _describe(self, pointcloud):
@@ -130,29 +153,49 @@ class Gvom:
             a = np.ascontiguousarray(a)
         return a, a.ctypes.data, a.shape[0], a.shape[1], GVOM_F32 if a.dtype == np.float32 else GVOM_F64, GVOM_HOST
 
+    def _order_device_input(self, keep):
+        """A CUDA tensor is read in place, asynchronously, on the library's stream: order the tensor's producer
+        (torch's current stream) before it and keep the memory from being reused until the kernels are done."""
+        torch = self._torch
+        cur = torch.cuda.current_stream(keep.device)
+        if cur.cuda_stream != self._work_stream.cuda_stream:
+            self._work_stream.wait_stream(cur)
+
+    def _hold_until_consumed(self, keep):
+        """Keep a reference to a CUDA input tensor (or the temporary made from it) until the kernels that read it
+        are done: otherwise torch's caching allocator could hand the memory to another stream's op while the scan
+        kernels are still reading it.  (Not tensor.record_stream(): the allocator would later record an event on
+        the library's stream, which may no longer exist.)"""
+        ev = self._torch.cuda.Event()
+        ev.record(self._work_stream)
+        q = self._inflight
+        q.append((ev, keep))
+        while q and q[0][0].query():
+            q.popleft()
+
     def Process_pointcloud(self, pointcloud, ego_position, transform=None):
         """ Imports a pointcloud and processes it into a voxel map then adds the map to the buffer"""
         keep, ptr, n, stride, dt, mem = self._describe(pointcloud)
-        self.ego_position = ego_position
-        e = self._ego_c
-        e[0], e[1], e[2] = float(ego_position[0]), float(ego_position[1]), float(ego_position[2])
-        if transform is None:
-            tp = None
-        else:
-            T = np.ascontiguousarray(transform, dtype=np.float64)
-            if T.shape != (4, 4):
-                raise ValueError("transform must be 4x4")
-            tp = T.ctypes.data
+        e, T, tp = self._ego_and_transform(ego_position, transform)
+        if n > self.max_points:
+            with self._lock:
+                if n > self.max_points:
+                    self._grow(n)
+        if mem == GVOM_DEVICE:
+            self._order_device_input(keep)
         check(self._L.gvom_process_pointcloud(self._h, ptr, n, stride, dt, mem, e, tp, self._stream),
               "gvom_process_pointcloud")
-        del keep
+        if mem == GVOM_DEVICE:
+            self._hold_until_consumed(keep)
+        del keep, T
 
     process_pointcloud = Process_pointcloud      # spelling used by BASELINE.json
 
     def _ego_and_transform(self, ego_position, transform):
         self.ego_position = ego_position
-        e = self._ego_c
-        e[0], e[1], e[2] = float(ego_position[0]), float(ego_position[1]), float(ego_position[2])
+        # a fresh buffer per call: concurrent callback threads must not see each other's ego (the C side copies it
+        # under the handle's mutex)
+        e = (C.c_double * 3)(float(ego_position[0]), float(ego_position[1]), float(ego_position[2]))
         if transform is None:
             return e, None, None
         T = np.ascontiguousarray(transform, dtype=np.float64)
@@ -179,8 +222,16 @@ class Gvom:
         if nbytes < n_points * point_step:
             raise ValueError("PointCloud2 payload shorter than n_points * point_step")
         e, T, tp = self._ego_and_transform(ego_position, transform)
+        if n_points > self.max_points:
+            with self._lock:
+                if n_points > self.max_points:
+                    self._grow(n_points)
+        if mem == GVOM_DEVICE:
+            self._order_device_input(keep)
         check(self._L.gvom_process_pointcloud2(self._h, ptr, n_points, point_step, int(offsets[0]), int(offsets[1]),
                                                int(offsets[2]), mem, e, tp, self._stream), "gvom_process_pointcloud2")
+        if mem == GVOM_DEVICE:
+            self._hold_until_consumed(keep)
         del keep, T
 
     def process_pointcloud2_msg(self, msg, ego_position, transform=None):
@@ -356,7 +407,7 @@ class Gvom:
     def stage_times(self):
         ms = (C.c_float * 16)()
         check(self._L.gvom_stage_times(self._h, ms), "gvom_stage_times")
-        names = ("h2d", "raycast", "index", "moments", "gather", "merge_codes", "merge_cells", "maps", "d2h", "stage_copy_host", "slab_cells", "slab_gather_maps", "slab_gather_cells")
+        names = ("h2d", "scan_points", "scan_cells", "_3", "_4", "merge_codes", "merge_cells", "maps", "d2h", "stage_copy_host", "slab_cells", "slab_gather_maps", "slab_gather_cells")
         return {k: float(ms[i]) for i, k in enumerate(names)}
 
     def refview(self):

@@ -21,12 +21,9 @@ B200, and the exchange happens only at combine time:
      cheaper than broadcasting the result and keeps the "previous combined map"
      state replicated, so any rank can serve the maps.
 
-  "direct" exchange (xy_size % 256 == 0, world * buffer_size <= 64): steps 1-3 collapse into ONE
-  merge.  Every rank's whole device workspace lives in symmetric memory, all handles are carved
-  identically, so a peer's ring slot is `peer base + my slot's offset`; combine_maps is then the
-  single-GPU combine over ALL ranks' slots, read in place over NVLink by the same two kernels
-  (gvom_combine_maps_direct).  Ready / done flags written by tiny kernels into every rank's
-  memory order the accesses; there is no collective call and no host synchronisation.
+(Two replicated alternatives were built and measured in round 1 -- every rank merging every rank's slots read in
+place over NVLink ("direct"), or from bulk-copied mirrors ("pull") -- lost to partial + finish already at N = 2
+ and were removed.)
 
 The result equals a single Gvom holding all ranks' slots: occupancy (OR), pass
 sums, hit/total sums and min heights are order independent in the reference's
@@ -39,7 +36,7 @@ import time
 
 import numpy as np
 
-from ._lib import (GVOM_DEVICE, GVOM_HOST, GVOM_NO_DATA, META_ROW_INTS, RECORD_FLOATS, GvomPeerLinks, check)
+from ._lib import GVOM_DEVICE, GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, check
 from .gvom import Gvom
 
 HEADER_DOUBLES = 8          # [valid, count, ox, oy, oz, pad...]
@@ -60,18 +57,6 @@ def merge_headers(headers):
     return org.copy(), counts
 
 
-def adopt_origin(table, world, slots):
-    """Direct / pull exchange, start-up only: a rank that has no scan yet takes the combined origin from the published
-    slot table (int32 [world, 64, 8] rows of {valid, ox, oy, oz, newest, seq, ..}): the newest slot of the first rank
-    that has data, like merge_headers does for the p2p exchange.  Pure host logic (tests/test_multi_cpu.py)."""
-    table = np.asarray(table).reshape(world, 64, 8)
-    for r in range(world):
-        for i in range(slots):
-            if table[r, i, 0] and table[r, i, 4]:
-                return table[r, i, 1:4].astype(np.float64)
-    return None
-
-
 def _ptr_array(ptrs):
     return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
 
@@ -86,25 +71,13 @@ class MultiGpuGvom(Gvom):
         import torch.distributed as dist
         self._dist, self._group = dist, group
         exchange = os.environ.get("GVOM_MULTI", exchange)
-        # direct exchange: the device workspace itself must be symmetric memory (see _alloc_device_ws)
-        xy, bs = int(args[2]), int(args[4])
-        self._ws_handle = None
-        # measured on 2x B200 (profiles/bench_r01_n2_direct_vs_p2p.json): reading the peers' slots in place makes every
-        # dependent access of the merge an NVLink round trip (row merge 91 us, cell merge 97 us against 31 / 20 us
-        # locally), slower than exchanging pre-merged grids + compact records (276 vs 310 us per step) -- so "auto"
-        # keeps the p2p exchange and the direct one is opt-in
-        # The "pull" exchange keeps the direct protocol but mirrors the peers' changed slots with one bulk copy per
-        # combine and merges from local memory: no dependent remote accesses any more, but every rank now merges ALL
-        # ranks' slots (9 sources at N = 2, B = 4) where the p2p exchange merges its own slots once and then only N
-        # pre-merged grids -- measured 327 us per step against 269 us (same file).  Opt-in as well.
-        self._want_direct = exchange in ("direct", "pull") and xy % 256 == 0 and dist.get_world_size(group) * bs <= 64
-        self._pull = exchange == "pull"
-        if exchange in ("direct", "pull") and not self._want_direct:
-            raise ValueError("exchange='direct' / 'pull' needs xy_size % 256 == 0 and world * buffer_size <= 64")
         if torch_stream is None:
             dev = kw.get("device")
             torch_stream = torch.cuda.Stream(device=torch.cuda.current_device() if dev is None else dev)
-            kw["stream"] = torch_stream.cuda_stream
+        # the library kernels and the torch ops of the exchange (copies, fills, NCCL) must share ONE stream
+        if kw.get("stream") is not None and int(kw["stream"]) != int(torch_stream.cuda_stream):
+            raise ValueError("MultiGpuGvom: `stream` and `torch_stream` name different CUDA streams")
+        kw["stream"] = torch_stream.cuda_stream
         self._tstream = torch_stream
         super().__init__(*args, **kw)
         self.world = dist.get_world_size(group)
@@ -123,17 +96,7 @@ class MultiGpuGvom(Gvom):
         self._sharded = bool(sharded) and self.xy_size % 16 == 0
         ccap = min(self.voxel_count, 4 * self.max_points * (self.buffer_size + 1))
         self._res_cap = int(min(self.voxel_count, max(1 << 18, 4 * ccap // self.world)))
-        if self._want_direct:
-            # all ranks must have got their workspace from symmetric memory
-            ok = torch.tensor([1 if self._ws_handle is not None else 0], device=self._dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if int(ok.item()) == 1:
-                self._init_direct()
-                self.exchange = "pull" if self._pull else "direct"
-                return
-            if exchange in ("direct", "pull"):
-                raise RuntimeError("direct exchange: symmetric memory unavailable: " + getattr(self, "_p2p_error", "?"))
-        if exchange in ("auto", "p2p", "direct", "pull"):
+        if exchange in ("auto", "p2p"):
             try:
                 self._init_p2p()
                 self.exchange = "p2p"
@@ -148,83 +111,9 @@ class MultiGpuGvom(Gvom):
             self.exchange = "nccl"
             self._init_nccl()
 
-    # ------------------------------------------------------------------ direct exchange
-    def _alloc_device_ws(self, nbytes):
-        if self._want_direct:
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-                group = self._group if self._group is not None else self._dist.group.WORLD
-                t = symm_mem.empty(nbytes, dtype=self._torch.uint8, device=self._torch.device(f"cuda:{self.device}"))
-                self._ws_handle = symm_mem.rendezvous(t, group)
-                return t
-            except Exception as ex:
-                self._p2p_error = repr(ex)
-                self._ws_handle = None
-        return super()._alloc_device_ws(nbytes)
-
-    def _init_direct(self):
-        import torch.distributed._symmetric_memory as symm_mem
-        torch, dist = self._torch, self._dist
-        group = self._group if self._group is not None else dist.group.WORLD
-        R, me = self.world, self.rank
-        o_ready, o_done = 4 * R * META_ROW_INTS, 4 * R * META_ROW_INTS + 256
-        t = symm_mem.empty(o_done + 256, dtype=torch.uint8, device=self._dev)
-        hdl = symm_mem.rendezvous(t, group)
-        t.zero_()
-        ptrs = [int(p) for p in hdl.buffer_ptrs]
-        ws = [int(p) for p in self._ws_handle.buffer_ptrs]
-        L = GvomPeerLinks()
-        L.rank, L.nranks = me, R
-        for r in range(R):
-            L.peer_ws[r] = ws[r]
-            L.meta_rows[r] = ptrs[r] + 4 * me * META_ROW_INTS
-            L.ready_slots[r] = ptrs[r] + o_ready + 4 * me
-            L.done_slots[r] = ptrs[r] + o_done + 4 * me
-        L.meta_table, L.ready_flags, L.done_flags = ptrs[me], ptrs[me] + o_ready, ptrs[me] + o_done
-        if self._pull:      # local mirror of every peer's ring slots (+ what it holds, + a private copy of the slot table)
-            nb = C.c_uint64(0)
-            check(self._L.gvom_mirror_size(self._h, R, C.byref(nb)), "gvom_mirror_size")
-            self._mirror = torch.empty(nb.value, dtype=torch.uint8, device=self._dev)
-            self._mirror_seq = torch.zeros(R * 64, dtype=torch.int32, device=self._dev)
-            self._meta_snap = torch.zeros(R * META_ROW_INTS, dtype=torch.int32, device=self._dev)
-            L.mirror, L.mirror_bytes = self._mirror.data_ptr(), nb.value
-            L.mirror_seq, L.meta_snapshot = self._mirror_seq.data_ptr(), self._meta_snap.data_ptr()
-        self._links, self._links_t, self._links_hdl = L, t, hdl
-        self._ready_view = t[o_ready:o_ready + 4 * R].view(torch.int32)
-        self._table_view = t[:o_ready].view(torch.int32).view(R, 64, 8)
-        torch.cuda.synchronize(self._dev)
-        dist.barrier(group=self._group)
-
-    def _combine_direct(self, device_outputs):
-        torch, L = self._torch, self._L
-        epoch = self._calls
-        have = L.gvom_newest_origin(self._h, self._org_in) != GVOM_NO_DATA
-        with torch.cuda.stream(self._tstream):
-            org = self._org_c
-            if have:
-                org[0] = org[1] = org[2] = float("nan")          # "use my newest scan's origin"
-            else:
-                # start-up only: publish my (empty) slot table, wait on the host for the peers' tables and adopt
-                # the origin of the first rank that has data
-                check(L.gvom_publish_slots(self._h, C.byref(self._links), epoch, self._stream), "gvom_publish_slots")
-                self._tstream.synchronize()
-                while int(self._ready_view.min().item()) < epoch:
-                    time.sleep(1e-4)
-                origin = adopt_origin(self._table_view.cpu().numpy(), self.world, self.buffer_size)
-                if origin is None:
-                    print("ERROR: No data in buffer")
-                    return None
-                for k in range(3):
-                    org[k] = float(origin[k])
-            outs, optr, mem = self._outputs(device_outputs)
-            fn = L.gvom_combine_maps_pull if self._pull else L.gvom_combine_maps_direct
-            rc = check(fn(self._h, C.byref(self._links), epoch, org, optr[0], optr[1], optr[2], optr[3], mem, self._stream),
-                       "gvom_combine_maps_pull" if self._pull else "gvom_combine_maps_direct")
-            if rc == GVOM_NO_DATA:
-                print("ERROR: No data in buffer")
-                return None
-        pos, neg, rough, vis = outs
-        return (np.array([org[0], org[1], org[2]]), pos, neg, rough, vis)
+    def _grow(self, n_points):
+        raise RuntimeError(f"MultiGpuGvom: a scan of {n_points} points exceeds max_points={self.max_points}; the exchange "
+                           "buffers are sized at construction (pass max_points=...)")
 
     # ------------------------------------------------------------------ buffers
     def _layout(self):
@@ -297,8 +186,6 @@ class MultiGpuGvom(Gvom):
 
     def combine_maps(self, device_outputs=False):
         self._calls += 1
-        if self.exchange in ("direct", "pull"):
-            return self._combine_direct(device_outputs)
         if self.exchange == "p2p":
             return self._combine_p2p(device_outputs)
         return self._combine_nccl(device_outputs)

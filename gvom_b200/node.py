@@ -58,19 +58,6 @@ def from_translation_rotation(translation, rotation):
     return m
 
 
-def host_grids(obs_map, neg_map, rough_map, cert_map, density_threshold, min_roughness, max_roughness):
-    """The node's host-side post-processing (gvom_ros.py:142-164), verbatim in behaviour: dict of int8 payloads."""
-    out = {}
-    out["hard"] = np.reshape(np.maximum(100 * (obs_map > density_threshold), neg_map), -1, order="F").astype(np.int8)
-    out["soft"] = np.reshape(100 * (obs_map <= density_threshold) * (obs_map > 0), -1, order="F").astype(np.int8)
-    out["certainty"] = np.reshape(cert_map * 100, -1, order="F").astype(np.int8)
-    out["negative"] = np.reshape(neg_map, -1, order="F").astype(np.int8)
-    r = ((np.maximum(np.minimum(rough_map, max_roughness), min_roughness) + min_roughness)
-         / (max_roughness - min_roughness)) * 100
-    out["roughness"] = np.reshape(r, -1, order="F").astype(np.int8)
-    return out
-
-
 class PointCloud2Payload:
     """The part of a sensor_msgs/PointCloud2 the path needs: byte payload + layout of the x, y, z fields."""
 
@@ -105,13 +92,14 @@ class VoxelMapperReplay:
     PointCloud2 ingestion and OccupancyGrid post-processing of the B200 class.  debug: also produce the
     three debug exports in cb_timer, as the node does."""
 
-    def __init__(self, gvom_class=None, fused=False, debug=True, **params):
+    def __init__(self, gvom_class=None, fused=False, debug=True, host_postprocess=None, **params):
         unknown = set(params) - set(DEFAULTS)
         if unknown:
             raise TypeError(f"unknown node parameter(s): {sorted(unknown)}")
         p = dict(DEFAULTS, **params)
         self.__dict__.update(p)
         self.fused, self.debug = bool(fused), bool(debug)
+        self.host_postprocess = host_postprocess      # fused=False: the node's numpy OccupancyGrid post-processing
         self.odom_data = None
         if gvom_class is None:
             from .gvom import Gvom as gvom_class
@@ -158,8 +146,11 @@ class VoxelMapperReplay:
             if map_data is None:
                 return None
             map_origin, obs_map, neg_map, rough_map, cert_map = map_data
-            grids = host_grids(obs_map, neg_map, rough_map, cert_map, self.density_threshold, self.min_roughness,
-                               self.max_roughness)
+            if self.host_postprocess is None:
+                raise RuntimeError("VoxelMapperReplay(fused=False) needs host_postprocess= (the node's numpy "
+                                   "post-processing lives with the tests: tests/host_grids.py)")
+            grids = self.host_postprocess(obs_map, neg_map, rough_map, cert_map, self.density_threshold,
+                                          self.min_roughness, self.max_roughness)
         out = {"origin": (float(map_origin[0]), float(map_origin[1])), "resolution": self.xy_resolution,
                "width": self.width, "frame_id": self.odom_frame}
         for topic, key in GRID_TOPICS.items():

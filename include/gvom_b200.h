@@ -91,10 +91,19 @@ int gvom_destroy(GvomHandle* h);
  * store the per-scan map in the next ring-buffer slot.
  * points: n rows of `stride` elements (>= 3; x,y,z first) of `dtype`, in host
  * (pageable or pinned) or device memory.  Asynchronous on `stream` except for
- * the staging copy of pageable host input. */
+ * the staging copy of pageable host input.
+ * Buffer contract: a HOST buffer may be reused as soon as the call returns.  A DEVICE buffer is read in place,
+ * asynchronously, on `stream` (or the handle's own stream, gvom_get_stream()): the caller orders the producer of
+ * the buffer before this call on that stream and keeps the buffer alive and unmodified until gvom_wait_input()
+ * returns (or the stream has been synchronised). */
 int gvom_process_pointcloud(GvomHandle* h, const void* points, int64_t n, int32_t stride,
                             int32_t dtype, int32_t mem, const double ego[3],
                             const double* transform16, void* stream);
+/* The handle's own stream (cudaStream_t as void*), the one used when `stream` arguments are NULL; lets a caller
+ * order its own work against the library's (cudaStreamWaitEvent). */
+int gvom_get_stream(GvomHandle* h, void** stream);
+/* Blocks until the device cloud of the last gvom_process_pointcloud* call has been consumed by the kernels. */
+int gvom_wait_input(GvomHandle* h);
 
 /* Replaces Gvom.combine_maps (gvom.py:222-393).  Outputs are [x,y]-indexed
  * (row-major, x major) xy_size*xy_size arrays: positive / negative obstacle and
@@ -162,7 +171,8 @@ int gvom_combine_maps_grids(GvomHandle* h, double origin[3], double density_thre
 
 /* State save / restore (deterministic replay, regression corpora): ring slots, the last combined map
  * (gvom.py:302-308 `last_combined_*`), ego position and ring position, as one opaque host blob that can
- * be loaded into any handle created with the same parameters and capacities. */
+ * be loaded into any handle created with the same parameters and the same or LARGER capacities (that is how the
+ * Python host side grows max_points on demand). */
 /* (The size changes with every processed scan: a caller that shares the handle with a scan thread retries
  * gvom_state_size + gvom_save_state when the latter answers GVOM_ECAPACITY.) */
 int gvom_state_size(GvomHandle* h, size_t* bytes);
@@ -222,48 +232,6 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
                                 int32_t phases, double origin_out[3], int32_t* positive, int32_t* negative,
                                 double* roughness, int32_t* visibility, int32_t out_mem, void* stream);
 
-/* Direct exchange (peer-to-peer, xy_size % 256 == 0, nranks * buffer_size <= 64): every rank's DEVICE WORKSPACE is
- * mapped into every other rank (the caller allocates it from symmetric memory and created all handles with the
- * same parameters and capacities, so they are carved identically) and combine_maps is the single-GPU combine over
- * ALL ranks' ring slots, read in place over NVLink -- one merge pass instead of partial + exchange + finish, and
- * the result is that of one Gvom holding every rank's slots in rank order.  All pointers are device pointers as
- * seen from this rank.  Collective: every rank calls it with the same `epoch` (1, 2, ...).  The handle remembers
- * `done_flags` (the next scan waits on them before it overwrites a ring slot), so the flag block must stay
- * allocated for as long as the handle is used. */
-#define GVOM_MAX_RANKS 16
-#define GVOM_META_ROW_INTS (64 * 8)      /* one rank's row of the slot table: 64 slots x 8 int32 */
-typedef struct GvomPeerLinks {
-    int32_t rank, nranks;
-    const void* peer_ws[GVOM_MAX_RANKS];         /* device workspace base of every rank (own included) */
-    int32_t* meta_rows[GVOM_MAX_RANKS];          /* row `rank` of the slot table in every rank's memory (written here) */
-    const int32_t* meta_table;                   /* local slot table: nranks rows of GVOM_META_ROW_INTS int32 */
-    int32_t* ready_slots[GVOM_MAX_RANKS];        /* this rank's "slots published" flag in every rank's memory */
-    const int32_t* ready_flags;                  /* local: nranks flags */
-    int32_t* done_slots[GVOM_MAX_RANKS];         /* this rank's "finished reading" flag in every rank's memory */
-    const int32_t* done_flags;                   /* local: nranks flags */
-    /* pull exchange only (else NULL / 0): local, zero-initialised device memory */
-    void* mirror;                                /* gvom_mirror_size() bytes: copies of the peers' ring slots */
-    uint64_t mirror_bytes;
-    int32_t* mirror_seq;                         /* nranks * 64 int32 */
-    int32_t* meta_snapshot;                      /* nranks * GVOM_META_ROW_INTS int32 */
-} GvomPeerLinks;
-/* Pull exchange: same protocol and results as the direct exchange, but every rank first refreshes a local MIRROR of
- * the peers' ring slots -- only the slots whose scan counter changed, with one bulk, coalesced, mask-aware copy over
- * NVLink -- and then merges from local memory.  (Dependent accesses over NVLink made the in-place merge slower than
- * exchanging pre-merged grids; bulk transfers do not have that problem.) */
-int gvom_mirror_size(GvomHandle* h, int32_t nranks, uint64_t* bytes);
-int gvom_combine_maps_pull(GvomHandle* h, const GvomPeerLinks* links, int32_t epoch, double origin[3],
-                           int32_t* positive, int32_t* negative, double* roughness, int32_t* visibility,
-                           int32_t out_mem, void* stream);
-/* origin: out (world origin of the combined map); in for a rank that has no scan yet: the combined origin in voxel
- * units adopted from a peer (NaN = none -> GVOM_NO_DATA). */
-/* Only the first step of gvom_combine_maps_direct (write this rank's slot table + ready flag = epoch); used by a rank
- * that has no scan yet and must learn the combined origin from its peers before it can merge.  Idempotent. */
-int gvom_publish_slots(GvomHandle* h, const GvomPeerLinks* links, int32_t epoch, void* stream);
-int gvom_combine_maps_direct(GvomHandle* h, const GvomPeerLinks* links, int32_t epoch, double origin[3],
-                             int32_t* positive, int32_t* negative, double* roughness, int32_t* visibility,
-                             int32_t out_mem, void* stream);
-
 /* ---- test / tooling hooks (canonical parity dumps; not on the hot path) ---- */
 int gvom_slot_info(GvomHandle* h, int32_t slot, int32_t* valid, int64_t* cells, double origin[3]);
 int gvom_last_slot(GvomHandle* h, int32_t* slot);
@@ -278,16 +246,16 @@ int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_
                          float* min_height, float* metrics, float* eig, double* maps6);
 int gvom_get_stats(GvomHandle* h, GvomStats* out);
 /* CUDA-event time (ms) of the stages of the last process / combine call:
- * [0] H2D+staging, [1] voxelise+ray-cast, [2] index build, [3] moments, [4] gather,
+ * [0] H2D+staging, [1] scan points (voxelise, claim, moments, ray-cast), [2] scan cells (gather, group mask,
+ * spare-slot wipe), [3], [4] unused,
  * [5] merge codes, [6] merge cells, [7] 2-D maps, [8] D2H, [9] host time of the last
  * pageable->pinned staging copy.  [0..8] are only recorded when
  * gvom_set_profiling(h, 1) is on (adds event records to the stream). */
 int gvom_set_profiling(GvomHandle* h, int32_t on);
 int gvom_stage_times(GvomHandle* h, float ms[16]);
 
-/* Tooling: select earlier builds of individual kernels (bit mask, see gvom_api.cu VAR_*; 0 = current builds)
- * so that one process can time both and the parity tests can exercise either.  Also read from the
- * environment variable GVOM_VARIANT at gvom_create(). */
+/* Tooling: A/B switches for measurements (bit mask, see gvom_api.cu VAR_*; 0 = defaults); every setting gives the
+ * same results.  Also read from the environment variable GVOM_VARIANT at gvom_create(). */
 int gvom_set_variant(GvomHandle* h, uint32_t mask);
 
 /* Tooling: L2 atomic-throughput microbenchmark (denominator of the ray-cast roofline).

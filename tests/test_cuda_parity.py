@@ -96,13 +96,35 @@ def test_error_conventions(capsys):
     assert g.make_debug_voxel_map() is None and g.make_debug_height_map() is None
     assert g.make_debug_inferred_height_map() is None
     assert "No data" in capsys.readouterr().out
-    with pytest.raises(RuntimeError):
-        g.Process_pointcloud(np.zeros((2000, 3)), (0.0, 0.0, 0.0))   # over max_points
+    with pytest.raises(ValueError):
+        g.Process_pointcloud(np.zeros((10, 2)), (0.0, 0.0, 0.0))     # not (N, >=3)
     g.Process_pointcloud(np.zeros((0, 3)), (0.0, 0.0, 1.0))          # empty scan is legal
     out = g.combine_maps()
     assert out is not None and out[1].dtype == np.int32 and out[3].dtype == np.float64
     assert out[1].shape == (32, 32)
     assert 0 < out[4].sum() < 32 * 32        # only the robot-radius disc is "seen" (gvom.py:566-570)
+
+
+def test_capacity_grows_on_demand():
+    """The reference has no per-scan point limit (it allocates per scan, gvom.py:115-131) and the unchanged node
+    cannot pass max_points: a cloud larger than the current capacity re-creates the workspace and carries the ring
+    buffer over.  Same results as a handle that was big enough from the start."""
+    P = synth.params_tuple(xy_size=64, z_size=16, buffer_size=3, robot_radius=2.0)
+    small, big = make(P, max_points=1024), make(P, max_points=1 << 16)
+    outs = []
+    for i in range(4):
+        beams = 4 if i < 2 else 16                      # 1024 points, then 4096: the third scan forces the growth
+        pc, ego, T = synth.frame(i, beams, 256, wall_radius=9.0, ego0=(10.0, 5.0, 1.0), dego=(0.9, 0.5, 0.25))
+        for g in (small, big):
+            g.Process_pointcloud(pc, ego, T)
+        outs.append((small.combine_maps(), big.combine_maps()))
+    assert small.max_points >= 4096
+    for a, b in outs:
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y) if x.dtype.kind != "f" else np.allclose(x, y, rtol=1e-6, atol=1e-9, equal_nan=True)
+    ca, cb = canon.canon_combine(small.refview(), outs[-1][0]), canon.canon_combine(big.refview(), outs[-1][1])
+    for k in ("n_occ", "codes_sha", "ids_sha", "hit_sha", "total_sha", "minh_sha"):
+        assert ca[k] == cb[k], k
 
 
 def test_full_size_invariants():

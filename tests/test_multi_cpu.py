@@ -144,109 +144,6 @@ def fold_slots(slots, origin, S, Z):
     return occ, passes
 
 
-def worker_direct(rank, world, port, result):
-    """Direct / pull exchange protocol on CPU: every rank publishes its slot table {valid, origin, newest, seq}
-    (all_gather = the table every rank holds), keeps a MIRROR of the peers' slots that it refreshes only where the
-    published scan counter differs from the mirrored one (the pull rule; the transfer itself is modelled by an
-    all_gather of the slot index maps), merges all slots + its previous map, and must end up with the codes of ONE
-    oracle Gvom holding every rank's scans -- including a rank that joins one combine late and adopts the origin."""
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    from gvom_b200 import synth
-    from gvom_b200.multi import adopt_origin
-    from oracle.gvom_oracle import OracleGvom
-    from test_multi_gpu import sensor_frames
-    S, Z, B = 32, 8, 2
-    V = S * S * Z
-    P1 = synth.params_tuple(xy_size=S, z_size=Z, buffer_size=B, robot_radius=2.0)
-    PN = synth.params_tuple(xy_size=S, z_size=Z, buffer_size=B * world, robot_radius=2.0)
-    fr = sensor_frames(world, 5, beams=8, cols=64, wall=5.0)
-    mine = OracleGvom(*P1)
-    ref = OracleGvom(*PN) if rank == 0 else None
-    seq = [0] * B                                             # scan counter per own slot
-    scans = 0
-    mirror = {}                                               # (rank, slot) -> (seq, index map copy)
-    refreshed = 0
-    prev_codes, prev_origin = None, None
-    ok = True
-    for step in range(5):
-        if not (rank == 1 and step == 0):
-            slot = mine.buffer_index
-            mine.Process_pointcloud(*fr[step][rank])
-            scans += 1
-            seq[slot] = scans
-        # publish: my row of the table
-        row = np.zeros((64, 8), np.int32)
-        for i in range(B):
-            if mine.origin_buffer[i] is not None:
-                row[i, 0] = 1
-                row[i, 1:4] = mine.origin_buffer[i]
-                row[i, 4] = 1 if i == mine.last_buffer_index else 0
-                row[i, 5] = seq[i]
-        rows = [torch.zeros(64 * 8, dtype=torch.int32) for _ in range(world)]
-        dist.all_gather(rows, torch.from_numpy(row.reshape(-1).copy()))
-        table = torch.stack(rows).numpy().reshape(world, 64, 8)
-        have = mine.origin_buffer[mine.last_buffer_index] is not None
-        origin = np.asarray(mine.origin_buffer[mine.last_buffer_index], np.float64) if have else adopt_origin(table, world, B)
-        assert origin is not None
-        # "transfer": every rank's slot index maps (what NVLink would move); the pull rule decides what is taken
-        maps = np.full((B, V), -1, np.int32)
-        for i in range(B):
-            if mine.origin_buffer[i] is not None:
-                maps[i] = mine.index_buffer[i]
-        allmaps = [torch.zeros(B * V, dtype=torch.int32) for _ in range(world)]
-        dist.all_gather(allmaps, torch.from_numpy(maps.reshape(-1).copy()))
-        for r in range(world):
-            if r == rank:
-                continue
-            for i in range(B):
-                if table[r, i, 0] and mirror.get((r, i), (0, None))[0] != table[r, i, 5]:
-                    mirror[(r, i)] = (int(table[r, i, 5]), allmaps[r].numpy().reshape(B, V)[i].copy())
-                    refreshed += 1
-        slots = [(mine.index_buffer[i], np.asarray(mine.origin_buffer[i], np.float64)) for i in range(B) if mine.origin_buffer[i] is not None]
-        slots += [(m, table[r, i, 1:4].astype(np.float64)) for (r, i), (_, m) in mirror.items()]
-        occ, passes = fold_slots(slots, origin, S, Z)
-        total = np.where(occ, OCC, np.minimum(passes, OCC - 1)).astype(np.int32)
-        codes = finish_codes(total, prev_codes, prev_origin, origin, S, Z)
-        both = [torch.zeros(V, dtype=torch.int32) for _ in range(world)]
-        dist.all_gather(both, torch.from_numpy(codes.reshape(-1).copy()))
-        ok &= bool(torch.equal(both[0], both[1]))
-        prev_codes, prev_origin = codes, origin
-        if rank == 0:
-            for r in range(world):
-                if not (r == 1 and step == 0):
-                    ref.Process_pointcloud(*fr[step][r])
-            ref.combine_maps()
-            want = np.where(ref.combined_index_map >= 0, 0, ref.combined_index_map).reshape(Z, S, S)
-            ok &= bool(np.array_equal(codes, want))
-    # only changed slots were transferred: one per peer scan, never the whole ring again
-    expected = 5 if rank == 1 else 4
-    ok &= refreshed == expected
-    result[rank] = ok
-    dist.barrier()
-    dist.destroy_process_group()
-
-
-def test_direct_pull_protocol_gloo():
-    world = 2
-    with mp.Manager() as m:
-        result = m.dict()
-        mp.spawn(worker_direct, args=(world, 29641, result), nprocs=world, join=True)
-        assert dict(result) == {0: True, 1: True}
-
-
-def test_adopt_origin():
-    from gvom_b200.multi import adopt_origin
-    t = np.zeros((3, 64, 8), np.int32)
-    assert adopt_origin(t, 3, 2) is None
-    t[1, 1] = [1, 5, -6, 7, 1, 9, 0, 0]
-    t[1, 0] = [1, 4, -6, 7, 0, 8, 0, 0]
-    t[2, 0] = [1, 50, 60, 70, 1, 3, 0, 0]
-    assert list(adopt_origin(t, 3, 2)) == [5.0, -6.0, 7.0]
-
-
 @pytest.mark.parametrize("nranks", [2, 3, 8])
 def test_plane_sharded_column_exchange_model(nranks):
     """Executable model of the NEXT multi-GPU design: the combined state stays sharded

@@ -167,126 +167,13 @@ def test_partial_finish_equals_single(nranks, reduced):
             compare_state(got, want, f"step {step} rank {r}")
 
 
-def make_direct_links(ranks):
-    """Link tables for the DIRECT exchange with all "ranks" living in one process / on one device: every rank gets
-    its own (table | ready flags | done flags) block, and the peers' device workspaces are the other handles'."""
-    import torch
-    from gvom_b200._lib import META_ROW_INTS, GvomPeerLinks
-    R = len(ranks)
-    dev = f"cuda:{ranks[0].device}"
-    blocks = [torch.zeros(R * META_ROW_INTS + 128, dtype=torch.int32, device=dev) for _ in ranks]
-    o_ready, o_done = 4 * R * META_ROW_INTS, 4 * (R * META_ROW_INTS + 64)
-    links = []
-    for me in range(R):
-        L = GvomPeerLinks()
-        L.rank, L.nranks = me, R
-        for r in range(R):
-            L.peer_ws[r] = ranks[r]._dev_ws.data_ptr()
-            L.meta_rows[r] = blocks[r].data_ptr() + 4 * me * META_ROW_INTS
-            L.ready_slots[r] = blocks[r].data_ptr() + o_ready + 4 * me
-            L.done_slots[r] = blocks[r].data_ptr() + o_done + 4 * me
-        L.meta_table, L.ready_flags, L.done_flags = blocks[me].data_ptr(), blocks[me].data_ptr() + o_ready, blocks[me].data_ptr() + o_done
-        links.append(L)
-    return links, blocks
-
-
-def add_mirrors(ranks, links):
-    """pull exchange: give every "rank" its mirror block, mirror scan counters and table snapshot."""
-    import torch
-    from gvom_b200._lib import META_ROW_INTS, check
-    keep = []
-    R = len(ranks)
-    for g, lk in zip(ranks, links):
-        nb = C.c_uint64(0)
-        check(g._L.gvom_mirror_size(g._h, R, C.byref(nb)), "mirror_size")
-        dev = f"cuda:{g.device}"
-        mir = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-        seq = torch.zeros(R * 64, dtype=torch.int32, device=dev)
-        snap = torch.zeros(R * META_ROW_INTS, dtype=torch.int32, device=dev)
-        lk.mirror, lk.mirror_bytes, lk.mirror_seq, lk.meta_snapshot = mir.data_ptr(), nb.value, seq.data_ptr(), snap.data_ptr()
-        keep.append((mir, seq, snap))
-    return keep
-
-
-def local_exchange_direct(ranks, links, epoch, pull=False):
-    """All ranks publish, then every rank merges all ranks' slots in place (sequentially: the in-kernel waits are
-    already satisfied).  A rank without a scan adopts the origin of the first rank that has one."""
-    import torch
-    from gvom_b200._lib import GVOM_HOST, GVOM_NO_DATA, check
-    L = ranks[0]._L
-    org = (C.c_double * 3)()
-    adopted = None
-    for g, lk in zip(ranks, links):
-        check(L.gvom_publish_slots(g._h, C.byref(lk), epoch, None), "publish")
-        if adopted is None and L.gvom_newest_origin(g._h, org) != GVOM_NO_DATA:
-            adopted = [org[0], org[1], org[2]]
-    torch.cuda.synchronize()
-    outs = []
-    for g, lk in zip(ranks, links):
-        pos, neg, rough, vis = g._out_arrays()
-        have = L.gvom_newest_origin(g._h, org) != GVOM_NO_DATA
-        oo = (C.c_double * 3)(*([float("nan")] * 3 if have else adopted))
-        fn = L.gvom_combine_maps_pull if pull else L.gvom_combine_maps_direct
-        rc = check(fn(g._h, C.byref(lk), epoch, oo, pos.ctypes.data, neg.ctypes.data, rough.ctypes.data,
-                      vis.ctypes.data, GVOM_HOST, None), "direct")
-        assert rc == 0
-        outs.append((np.array(list(oo)), pos, neg, rough, vis))
-    return outs
-
-
-@pytest.mark.parametrize("nranks,late,pull", [(1, False, False), (2, False, False), (3, False, False), (2, True, False),
-                                              (1, False, True), (2, False, True), (3, False, True), (2, True, True)])
-def test_direct_exchange_equals_single(nranks, late, pull):
-    """gvom_combine_maps_direct / _pull: one merge over every rank's ring slots (read in place / mirrored by a bulk
-    copy of the changed slots) == one Gvom holding them all."""
-    from gvom_b200 import Gvom
-    B = 2
-    P1 = synth.params_tuple(xy_size=256, z_size=16, buffer_size=B, robot_radius=2.0)
-    PN = synth.params_tuple(xy_size=256, z_size=16, buffer_size=B * nranks, robot_radius=2.0)
-    fr = sensor_frames(nranks, 5, beams=16, cols=512, wall=30.0)
-    ranks = [Gvom(*P1, max_points=1 << 14) for _ in range(nranks)]
-    links, _blocks = make_direct_links(ranks)
-    _mirrors = add_mirrors(ranks, links) if pull else None
-    feeds = lambda step, r: not (late and r == 1 and step == 0)       # late: rank 1 has no scan at the first combine
-    for step in range(5):
-        for r in range(nranks):
-            if feeds(step, r):
-                ranks[r].Process_pointcloud(*fr[step][r])
-        outs = local_exchange_direct(ranks, links, step + 1, pull)
-        if late:
-            # (the single-Gvom replay below cannot express a ring with an empty slot in the middle: compare the ranks
-            #  with each other instead -- the protocol must give every rank the same combined map)
-            want = canon.canon_combine(ranks[0].refview(), outs[0])
-            got = canon.canon_combine(ranks[1].refview(), outs[1])
-            if step == 0:
-                # a rank that has never seen a scan has no ego position (gvom.py:110-112), so its 2-D maps differ
-                # inside the robot-radius disc; the voxel state it carries forward must still be the common one
-                for k in ("out_origin", "codes", "ids", "hit", "total", "minh"):
-                    assert np.array_equal(got[k], want[k]), f"step {step} late rank: {k}"
-                assert want["n_occ"] > 0
-            else:
-                compare_state(got, want, f"step {step} late rank vs rank 0")
-            continue
-        ref = Gvom(*PN, max_points=1 << 14)
-        for s2 in range(step + 1):
-            for q in range(max(0, s2 - B + 1), s2 + 1):
-                for r in range(nranks):
-                    ref.Process_pointcloud(*fr[q][r])
-            last = ref.combine_maps()
-        want = canon.canon_combine(ref.refview(), last)
-        for r in range(nranks):
-            got = canon.canon_combine(ranks[r].refview(), outs[r])
-            compare_state(got, want, f"step {step} rank {r}")
-
-
 def test_nccl_two_ranks(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     script = os.path.join(ROOT, "tests", "multi_rank_check.py")
     for port, exchange, extra in ((29533, "nccl", []), (29534, "p2p", []), (29535, "p2p", ["late"]),
-                                  (29536, "p2p", ["sharded"]), (29537, "direct", ["grid256"]), (29538, "direct", ["late", "grid256"]),
-                                  (29539, "pull", ["grid256"]), (29540, "pull", ["late", "grid256"])):
+                                  (29536, "p2p", ["sharded"]), (29537, "p2p", ["grid256"])):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                             "--master-addr", "127.0.0.1", "--master-port", str(port), script, exchange] + extra,
                            capture_output=True, text=True, timeout=600)

@@ -12,7 +12,8 @@ import pytest
 
 import canon
 from gvom_b200 import synth
-from gvom_b200.node import PointCloud2Payload, VoxelMapperReplay, host_grids
+from gvom_b200.node import PointCloud2Payload, VoxelMapperReplay
+from host_grids import host_grids
 
 pytestmark = pytest.mark.gpu
 
@@ -241,7 +242,7 @@ def test_state_save_restore(tmp_path):
 
 def test_replay_driver_fused_matches_host_post_processing():
     params = dict(width=64, height=16, robot_radius=2.0, buffer_size=3, density_threshold=40)
-    host = VoxelMapperReplay(fused=False, **params)
+    host = VoxelMapperReplay(fused=False, host_postprocess=host_grids, **params)
     dev = VoxelMapperReplay(fused=True, **params)
     assert host.cb_lidar(np.zeros((4, 3)), (0, 0, 0), (0, 0, 0, 1)) is False        # "no odom"
     assert dev.cb_timer() is None
@@ -279,9 +280,10 @@ def test_replay_driver_matches_the_unmodified_node():
             assert np.array_equal(out[topic], want[topic][i]), (i, topic)
 
 
-@pytest.mark.parametrize("mask", [1, 2, 4, 8, 16, 32, 64, 15])
-def test_earlier_kernel_builds_still_match_the_reference(mask, monkeypatch):
-    """The kernel builds kept for A/B timing (GVOM_VARIANT bits) stay parity-green."""
+@pytest.mark.parametrize("mask", [2, 64, 128, 194])
+def test_ab_switches_do_not_change_results(mask, monkeypatch):
+    """The A/B switches kept for measurements (GVOM_VARIANT bits: generic merge kernel, DMA outputs, F2I floor in the
+    DDA) stay parity-green."""
     import replay
     monkeypatch.setenv("GVOM_VARIANT", str(mask))
     for name in ("small_moving", "os1_64"):

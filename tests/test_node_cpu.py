@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from gvom_b200 import synth
-from gvom_b200.node import GRID_TOPICS, PointCloud2Payload, VoxelMapperReplay, from_translation_rotation, host_grids
+from gvom_b200.node import GRID_TOPICS, PointCloud2Payload, VoxelMapperReplay, from_translation_rotation
+from host_grids import host_grids
 
 
 def frames(n):
@@ -57,7 +58,7 @@ def test_replay_driver_matches_unmodified_node_on_the_oracle():
     from oracle.gvom_oracle import OracleGvom
     fr = frames(3)
     want = run_node(OracleGvom, fr, {"~width": 32, "~height": 16, "~robot_radius": 2.0, "~buffer_size": 2})
-    node = VoxelMapperReplay(OracleGvom, fused=False, width=32, height=16, robot_radius=2.0, buffer_size=2)
+    node = VoxelMapperReplay(OracleGvom, fused=False, host_postprocess=host_grids, width=32, height=16, robot_radius=2.0, buffer_size=2)
     assert node.cb_timer() is None
     for i, (pc, ego, yaw) in enumerate(fr):
         node.cb_odom(ego)
