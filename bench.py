@@ -79,6 +79,15 @@ def config_frames(name, rank=0):
     return out
 
 
+def config_dict(nsens, slots):
+    """`config` of the JSON line -- the SAME dict in both arms (the driver compares them)."""
+    w = CONFIGS[CONFIG]["workload"] + f", {slots} ring slots per sensor, {nsens} sensor stream(s)"
+    if nsens > 1:
+        w += f" (configs[2]: {slots * nsens} slots in total, SURVEY 8d: 2 per sensor; one combine_maps over all of them per step)"
+    return {"workload": w, "sensors": nsens, "slots_per_sensor": slots, "frames": NFRAMES,
+            "l2": "flushed between steps (256 MiB memset, outside the timed region)"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -156,6 +165,27 @@ def cpu_baseline(sample_steps=4, threads=None):
             "ms_per_step": 1e3 * dt / sample_steps, "work": g.work}
 
 
+def cudasim_baseline(timeout_s=150):
+    """The north_star's second reported baseline: the UNMODIFIED reference under NUMBA_ENABLE_CUDASIM on this box's
+    host cores.  The simulator runs every CUDA thread as a Python thread (about a day per OS1-128 scan),
+    so the sample is a reduced configuration: 4 x 24 points into a 16 x 16 x 8 grid, one timed scan + combine."""
+    out = os.path.join(ROOT, "gpurun_out", "ref_probe_cudasim_bench.json")
+    try:
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        env = dict(os.environ, NUMBA_ENABLE_CUDASIM="1")
+        t0 = time.perf_counter()
+        subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_probe.py"), "--xy", "16", "--z", "8", "--beams", "4",
+                        "--cols", "24", "--iters", "1", "--out", out], env=env, check=True, timeout=timeout_s,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        d = json.load(open(out))
+        return {"kind": "cudasim-reduced", "value": d["scans_per_sec"], "unit": "scans/s", "cores": os.cpu_count(),
+                "ms_per_step": d["end_to_end_ms_p50"], "wall_s": time.perf_counter() - t0,
+                "sample": "unmodified reference, NUMBA_ENABLE_CUDASIM=1, 96 points into 16x16x8 (the full workload is "
+                          "262,144 points into 256x256x64: ~2700x the points, 2048x the voxels), 1 timed scan + combine"}
+    except Exception as ex:
+        return {"kind": "cudasim-reduced", "error": repr(ex)}
+
+
 def run_reference(args):
     """Reference arm: unmodified reference Gvom via Numba-CUDA on this GPU."""
     rank = int(os.environ.get("RANK", "0"))
@@ -169,9 +199,9 @@ def run_reference(args):
     # sensor; a step is one scan of every sensor + one combine_maps
     nsens = max(1, args.gpus)
     slots = args.slots_per_sensor or (2 if nsens > 1 else 4)
-    base["config"] = {"workload": f"configs[{1 if nsens == 1 else 2}]: synthetic OS1-128 scans (128x2048=262,144 pts), 256x256x64 grid "
-                                  f"@0.4/0.2 m, {nsens} sensor(s) into one reference Gvom on one GPU, {slots} ring slots per sensor",
-                      "frames": NFRAMES, "slots_per_sensor": slots}
+    slots = CONFIGS[CONFIG]["params"].get("buffer_size", slots)
+    base["config"] = config_dict(nsens, slots)
+    base["arm"] = f"{nsens} sensor stream(s) into ONE unmodified reference Gvom ({slots * nsens} ring slots) on one GPU"
     fr = [frames(r) for r in range(nsens)]
     try:
         sys.path.insert(0, os.path.join(ROOT, "baseline"))
@@ -188,9 +218,12 @@ def run_reference(args):
         import gvom as refgvom
         if refgvom.__file__.startswith(os.path.join(ROOT, "gvom_b200")):
             raise RuntimeError("import gvom resolved to the B200 shim, not the reference")
-        g = refgvom.Gvom(*synth.params_tuple(buffer_size=slots * nsens))
+        g = refgvom.Gvom(*synth.params_tuple(**dict(CONFIGS[CONFIG]["params"], buffer_size=slots * nsens)))
+        flush = numba.cuda.device_array(256 << 20, dtype=np.uint8)
         ts = []
         for i in range(args.warmup + args.steps):
+            numba.cuda.cudadrv.driver.device_memset(flush, 0, 256 << 20)       # L2 flush, outside the timed region
+            numba.cuda.synchronize()
             t0 = time.perf_counter()
             for r in range(nsens):
                 pc, ego, T = fr[r][i % NFRAMES]
@@ -201,11 +234,13 @@ def run_reference(args):
         ts = ts[args.warmup:]
         v = nsens * len(ts) / sum(ts)
         base.update({"value": v, "ms_per_step": 1e3 * sum(ts) / len(ts), "p50_latency_ms": 1e3 * statistics.median(ts),
+                     "value_p50": nsens / statistics.median(ts),
                      "cpu_baseline": {"value": v, "unit": "scans/s", "cores": 1, "kind": "reference",
                                       "sample": f"{len(ts)} steps; unmodified reference class through Numba-CUDA "
                                                 "(PTX JIT compute_90->sm_100) on the same B200, 1 host thread; "
                                                 "shims: baseline/ref_shims.py"},
-                     "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                             "value_p50": nsens / statistics.median(ts)},
                      "gpu_launches": None})
     except Exception as ex:  # Numba cannot drive this GPU: CPU oracle port on all host threads
         steps = max(1, min(args.steps, 6))
@@ -289,6 +324,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # device-resident outputs are left in HBM in stream order (no host wait inside the timed region); the multi-GPU
+    # class completes every combine on the host (its exchange needs the epoch bookkeeping)
+    dev_kw = {} if multi else {"wait": False}
+
     def timed(device_io, steps, warmup, profile=False):
         """-> (per-step ms list [device events], per-step wall ms, stage-time sums)"""
         ev, wall, stages = [], [], {}
@@ -304,7 +343,7 @@ def main():
             a.record(stream)
             if device_io:
                 g.Process_pointcloud(on_dev[k], fr[k][1], fr[k][2])
-                out = g.combine_maps(device_outputs=True)
+                out = g.combine_maps(device_outputs=True, **dev_kw)
             else:
                 g.Process_pointcloud(pinned[k], fr[k][1], fr[k][2])
                 out = g.combine_maps()
@@ -403,16 +442,15 @@ def main():
         "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (cfg["workload"] + f", {slots} ring slots per sensor, one sensor per GPU" +
-                                (f"; configs[2]: per-GPU streams, {slots * world} slots in total (SURVEY 8d: 2 per sensor), combine exchanged over NVLink" if multi else "")),
-                   "slots_per_sensor": slots,
-                   "exchange": (getattr(g, "exchange", None) or "") + (" sharded-finish" if getattr(g, "_sharded", False) and getattr(g, "exchange", "") == "p2p" else ""),
-                   "frames": NFRAMES, "l2": "flushed between steps (256 MiB memset, outside the timed region)",
-                   "value_io": "cloud resident in HBM (float64 Nx3), maps left in HBM",
-                   "e2e_io": "pinned host float64 Nx3 cloud in, numpy maps out (pinned), per-step wall clock around both calls"},
+        "config": config_dict(world, slots),
+        "io": {"exchange": (getattr(g, "exchange", None) or "") + (" sharded-finish" if getattr(g, "_sharded", False) and getattr(g, "exchange", "") == "p2p" else ""),
+               "value": "cloud resident in HBM (float64 Nx3), maps left in HBM in stream order; CUDA events around both calls on the launching stream",
+               "e2e": "pinned host float64 Nx3 cloud in, numpy maps out (pinned), per-step wall clock around both calls"},
+        "value_p50": world / (statistics.median(ev_dev) * 1e-3),
         "p50_latency_ms": statistics.median(ev_dev),
         "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": int(fr[0][0].nbytes),
                 "d2h_bytes_per_step": 20 * P[2] * P[2], "p50_latency_ms": statistics.median(wall_e2e),
+                "value_p50": world / (statistics.median(wall_e2e) * 1e-3),
                 "p50_device_ms": statistics.median(ev_e2e)},
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "gpu_launches_per_step": launches_per_step,
@@ -453,6 +491,8 @@ def main():
             line["cpu_baseline"] = cpu_baseline()
         except Exception as ex:
             line["cpu_baseline"] = {"error": repr(ex)}
+    if world == 1 and not args.no_cpu_baseline and CONFIG == "os1_128":
+        line["cpu_baseline_cudasim"] = cudasim_baseline()
     print(json.dumps(line), flush=True)
     if multi:
         dist.destroy_process_group()

@@ -27,6 +27,7 @@
 #include "../../include/gvom_b200.h"
 #include "gvom_kernels.cuh"
 #include "gvom_scan.cuh"
+#include "gvom_merge.cuh"
 
 using namespace gvom;
 
@@ -100,7 +101,7 @@ enum { EV_START = 0, EV_H2D, EV_POINTS, EV_SCELLS, EV_CSTART, EV_CODES, EV_CELLS
        EV_X0, EV_X1, EV_X2, EV_COUNT };   // EV_X*: extra marks inside the multi-GPU combine
 
 // GVOM_VARIANT bits (environment / gvom_set_variant): A/B switches for measurements; every setting gives the same results
-enum { VAR_GENERIC_MERGE = 2, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128 };
+enum { VAR_GENERIC_MERGE = 2, VAR_ASYNC_ROWS = 4, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128 };
 
 }  // namespace
 
@@ -150,7 +151,7 @@ struct GvomHandle {
     bool zero_copy = true;                // host clouds: S1 reads pinned memory directly (else chunked DMA)
     bool prof_process = false, prof_combine = false, prof_x = false;
     int sm_count = 148;
-    int grid_codes = 0, grid_cells = 0, grid_cells2 = 0, grid_rows3 = 0, grid_scan_cells = 0;   // resident grids (set at create)
+    int grid_codes = 0, grid_cells = 0, grid_cells2 = 0, grid_rows3 = 0, grid_scan_cells = 0, grid_rows_async[2] = {0, 0};   // resident grids (set at create)
     GvomStats stats{};
     float last_stage_copy_ms = 0.f;       // host time of the last pageable->pinned staging copy
     CopyPool* pool = nullptr;             // staging threads for pageable input (created on first use)
@@ -329,7 +330,13 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
 template <int MODE>
 void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStream_t st) {
     if (MODE == MERGE_FULL && h->p.xy_size % 256 == 0 && A.use_masks && O.gmask && !(h->variant & VAR_GENERIC_MERGE)) {
-        launch(k_merge_rows<3>, dim3(h->grid_rows3), dim3(256), 0, st, A, O, h->dp);
+        // the bulk-copy pipeline build of the row merge is opt-in: parity green, but measured slower (gvom_merge.cuh)
+        if (A.n <= 16 && h->grid_rows_async[0] > 0 && (h->variant & VAR_ASYNC_ROWS))
+            launch(k_merge_rows_async<1>, dim3(h->grid_rows_async[0]), dim3(32), sizeof(MrWarp<1>), st, A, O, h->dp);
+        else if (A.n <= MR_MAX_SRC && h->grid_rows_async[1] > 0 && (h->variant & VAR_ASYNC_ROWS))
+            launch(k_merge_rows_async<2>, dim3(h->grid_rows_async[1]), dim3(32), sizeof(MrWarp<2>), st, A, O, h->dp);
+        else
+            launch(k_merge_rows<3>, dim3(h->grid_rows3), dim3(256), 0, st, A, O, h->dp);
         h->stats.kernel_launches++;
         return;
     }
@@ -526,6 +533,8 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
         if (const char* m = getenv("GVOM_VARIANT")) h->variant = (unsigned)strtoul(m, nullptr, 0);
         if (const char* m = getenv("GVOM_GATHER_BLOCKS")) h->gather_blocks = std::max(1, std::min(8, atoi(m)));
         h->grid_rows3 = resident_grid(k_merge_rows<3>, 256, h->sm_count);
+        h->grid_rows_async[0] = resident_grid(k_merge_rows_async<1>, 32, h->sm_count, sizeof(MrWarp<1>));
+        h->grid_rows_async[1] = resident_grid(k_merge_rows_async<2>, 32, h->sm_count, sizeof(MrWarp<2>));
     }
     // the cell grid of the scan kernels starts with tag 0 ("never used") everywhere; every slot map starts as "all
     // unknown" with an empty group mask (S1 ray-casts into a wiped map; the row merge relies on map and mask of its

@@ -74,6 +74,7 @@ class Gvom:
                              float(robot_height), float(robot_radius), float(ground_to_lidar_height),
                              self.xy_eigen_dist, self.z_eigen_dist)
         self._max_combined_cells = int(max_combined_cells)
+        self._devstr = f"cuda:{self.device}"
         self._inflight = collections.deque()     # (event, CUDA input tensor) of scans whose kernels may still be running
         self._lock = threading.Lock()            # callback threads (README.md:49: several sensors) share one handle
         self._create()
@@ -268,17 +269,23 @@ class Gvom:
         return (np.empty((S, S), np.int32), np.empty((S, S), np.int32), np.empty((S, S), np.float64),
                 np.empty((S, S), np.int32))
 
-    def combine_maps(self, device_outputs=False):
+    def combine_maps(self, device_outputs=False, wait=True):
         """ Combines all maps in the buffer and processes into 2D maps.
-        device_outputs=True (extension) returns torch CUDA tensors instead of numpy arrays."""
+        device_outputs=True (extension) returns torch CUDA tensors instead of numpy arrays; with wait=False the call
+        returns as soon as the kernels are enqueued and the tensors are valid in STREAM ORDER on the Gvom's stream
+        (like the result of any asynchronous torch op; `synchronize()` or a stream wait before reading them elsewhere)."""
         if device_outputs:
             torch, S = self._torch, self.xy_size
-            dev = f"cuda:{self.device}"
-            ti = torch.empty((3, S, S), dtype=torch.int32, device=dev)
-            rough = torch.empty((S, S), dtype=torch.float64, device=dev)
-            rc = check(self._L.gvom_combine_maps(self._h, self._org_c, ti[0].data_ptr(), ti[1].data_ptr(),
-                                                 rough.data_ptr(), ti[2].data_ptr(), GVOM_DEVICE, self._stream),
+            ro = (12 * S * S + 7) & ~7               # roughness starts 8-byte aligned (odd xy_size)
+            blk = torch.empty(ro + 8 * S * S, dtype=torch.uint8, device=self._devstr)   # one allocation, laid out like the result block
+            ti = blk[:12 * S * S].view(torch.int32).view(3, S, S)
+            rough = blk[ro:].view(torch.float64).view(S, S)
+            p0 = blk.data_ptr()
+            fn = self._L.gvom_combine_maps if wait else self._L.gvom_combine_maps_async
+            rc = check(fn(self._h, self._org_c, p0, p0 + 4 * S * S, p0 + ro, p0 + 8 * S * S, GVOM_DEVICE, self._stream),
                        "gvom_combine_maps")
+            if not wait:
+                self._hold_until_consumed(blk)       # (the stream may still be writing it when the caller drops it)
             pos, neg, vis = ti[0], ti[1], ti[2]
         else:
             pos, neg, rough, vis = self._out_arrays()
@@ -390,6 +397,10 @@ class Gvom:
             print("No data")
             return None
         return out
+
+    def synchronize(self):
+        """Wait until everything enqueued on the Gvom's stream (scans, asynchronous combines) has finished."""
+        self._work_stream.synchronize()
 
     # ---------------------------------------------------------------- tooling
     def stats(self):
