@@ -37,6 +37,16 @@ class GvomStats(C.Structure):
 MAX_RANKS = 16
 
 
+class GvomRowsLinks(C.Structure):
+    """include/gvom_b200.h: GvomRowsLinks (row-sharded multi-GPU finish)."""
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32),
+                ("code_grids", C.c_void_p * MAX_RANKS), ("group_masks", C.c_void_p * MAX_RANKS),
+                ("records", C.c_void_p * MAX_RANKS), ("record_capacity", C.c_int64),
+                ("partial_headers", C.c_void_p), ("blocks2d", C.c_void_p * MAX_RANKS),
+                ("heights_slots", C.c_void_p * MAX_RANKS), ("heights_flags", C.c_void_p),
+                ("results_slots", C.c_void_p * MAX_RANKS), ("results_flags", C.c_void_p)]
+
+
 # every symbol include/gvom_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 _pd = C.POINTER(C.c_double)
@@ -69,6 +79,9 @@ SYMBOLS = {
     "gvom_combine_finish_sharded": (C.c_int, [_vp, _pd, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i64, _vp,
                                               C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, C.POINTER(_vp), _vp, _i32, _i32,
                                               _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "gvom_rows_block_size": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "gvom_combine_partial_header": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _i64, _vp, C.POINTER(_vp), _i32, _i32, _vp]),
+    "gvom_combine_finish_rows": (C.c_int, [_vp, _pd, C.POINTER(GvomRowsLinks), _i32, _i32, _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gvom_slot_info": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i64), _pd]),
     "gvom_last_slot": (C.c_int, [_vp, C.POINTER(_i32)]),
     "gvom_export_slot": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -425,7 +425,8 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
                                                                                  c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
                                                                                  in_smem, h->col_minz, h->flags + 4,
                                                                                  direct_dev ? kpos : nullptr, direct_dev ? kneg : nullptr,
-                                                                                 direct_dev ? kvis : nullptr, direct_dev ? krough : nullptr);
+                                                                                 direct_dev ? kvis : nullptr, direct_dev ? krough : nullptr,
+                                                                                 RowShard{0, 1, h->p.xy_size}, PushSet{});
     }
     h->stats.kernel_launches += 2;
     rec(h, EV_MAPS, st);
@@ -1375,9 +1376,9 @@ int gvom_newest_origin(GvomHandle* h, double origin[3]) {
     return GVOM_OK;
 }
 
-int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, uint32_t* group_mask_dev,
-                         float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
-                         int32_t* const* signal_slots, int32_t n_signal, int32_t epoch, void* stream) {
+static int combine_partial_impl(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, uint32_t* group_mask_dev,
+                                float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
+                                int32_t* const* signal_slots, int32_t n_signal, int32_t epoch, bool header, void* stream) {
     if (!h || !origin || !code_grid_dev || !records_dev || !record_count_dev) return fail(GVOM_EINVAL, "NULL argument");
     if (record_capacity < 1 || record_capacity > 2147483647LL) return fail(GVOM_EINVAL, "bad record capacity");
     std::lock_guard<std::mutex> lock(h->mu);
@@ -1399,12 +1400,29 @@ int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_gr
         if (n_signal > MAX_RANKS) return fail(GVOM_EINVAL, "too many ranks");
         SignalSet S; S.n = n_signal;
         for (int k = 0; k < n_signal; ++k) S.slot[k] = signal_slots[k];
-        launch(k_signal, dim3(1), dim3(32), 0, st, S, (int)epoch);
+        if (header)      // {epoch, origin}: the finishing ranks verify that everybody merged in the same frame
+            launch(k_signal_header, dim3(1), dim3(32), 0, st, S, (int)epoch, (int)origin[0], (int)origin[1], (int)origin[2]);
+        else
+            launch(k_signal, dim3(1), dim3(32), 0, st, S, (int)epoch);
         h->stats.kernel_launches += 1;
     }
     rec(h, EV_CODES, st);
     CUDA_TRY(cudaGetLastError());
     return GVOM_OK;
+}
+
+int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, uint32_t* group_mask_dev,
+                         float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
+                         int32_t* const* signal_slots, int32_t n_signal, int32_t epoch, void* stream) {
+    return combine_partial_impl(h, origin, code_grid_dev, group_mask_dev, records_dev, record_capacity, record_count_dev,
+                                signal_slots, n_signal, epoch, false, stream);
+}
+
+int gvom_combine_partial_header(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, uint32_t* group_mask_dev,
+                                float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
+                                int32_t* const* header_slots, int32_t n_signal, int32_t epoch, void* stream) {
+    return combine_partial_impl(h, origin, code_grid_dev, group_mask_dev, records_dev, record_capacity, record_count_dev,
+                                header_slots, n_signal, epoch, true, stream);
 }
 
 int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* const* code_grids,
@@ -1475,6 +1493,195 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     c.valid = true;
     h->cur = 1 - h->cur;
     h->stats.combine_calls++;
+    return GVOM_OK;
+}
+
+
+// ------------------------------------------------------------- multi-GPU, row-sharded finish
+// Rank r owns the grid rows y with (y + origin_y) mod nranks == r -- WORLD rows, so an origin shift never moves a row
+// (and with it the previous combined map of that row) to another rank.  Owning whole columns makes everything below
+// the exchange local: the merge of the rank's rows from all ranks' encoded grids + its own previous rows, the cells on
+// them, the column reductions and the 2-D stage of its columns.  Only 2-D data is replicated, by pushing (posted remote
+// stores into every rank's 2-D block): heights after the column stage, the finished maps after the surface stage.
+//   phase 1: [wait: partial results]  merge own rows -> cells -> heights of own columns pushed -> signal "heights"
+//   phase 2: [wait: heights]          "height known" bit maps (whole map) -> surface stage of own rows pushed -> signal "results"
+//   phase 4: [wait: results]          deliver the maps to the caller, refresh the library's own 2-D block
+// (separate phases let one process play several ranks in the tests).
+static size_t rows_block_bytes(const GvomHandle* h) {
+    const size_t S2 = (size_t)h->S2;
+    return 6 * S2 * sizeof(double) + (3 * S2 + 2 * S2 + 2) * sizeof(int) + 256;
+}
+
+int gvom_rows_block_size(GvomHandle* h, uint64_t* bytes) {
+    if (!h || !bytes) return fail(GVOM_EINVAL, "NULL argument");
+    *bytes = rows_block_bytes(h);
+    return GVOM_OK;
+}
+
+int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRowsLinks* K, int32_t epoch, int32_t phases,
+                             double origin_out[3], int32_t* positive, int32_t* negative, double* roughness,
+                             int32_t* visibility, int32_t out_mem, void* stream) {
+    if (!h || !origin || !K) return fail(GVOM_EINVAL, "NULL argument");
+    const int N = K->nranks, me = K->rank;
+    if (N < 1 || N > MAX_RANKS || me < 0 || me >= N) return fail(GVOM_EINVAL, "bad rank / nranks");
+    if (h->p.xy_size % 256 != 0) return fail(GVOM_EINVAL, "row-sharded finish needs xy_size % 256 == 0");
+    if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE && out_mem != GVOM_NONE) return fail(GVOM_EINVAL, "bad out_mem");
+    for (int k = 0; k < N; ++k)
+        if (!K->code_grids[k] || !K->group_masks[k] || !K->records[k] || !K->blocks2d[k] || !K->heights_slots[k] || !K->results_slots[k])
+            return fail(GVOM_EINVAL, "NULL rank buffer");
+    if (!K->partial_headers || !K->heights_flags || !K->results_flags) return fail(GVOM_EINVAL, "NULL flag table");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->active = st;
+    const int S = h->p.xy_size;
+    const size_t S2 = (size_t)h->S2;
+    Combined& pc = h->comb[h->cur];
+    Combined& c = h->comb[1 - h->cur];
+    // the rows this rank owns in the frame of this combine
+    const long long oy = (long long)origin[1];
+    RowShard R;
+    R.n = N;
+    R.y0 = (int)((((long long)me - oy) % N + N) % N);
+    R.nrows = R.y0 < S ? (S - R.y0 + N - 1) / N : 0;
+    PushSet D{};
+    D.n = N; D.self = me;
+    for (int k = 0; k < N; ++k) D.base[k] = static_cast<char*>(K->blocks2d[k]);
+    D.off_maps = 0;
+    D.off_pos = (long long)(6 * S2 * sizeof(double));
+    D.off_neg = D.off_pos + (long long)(S2 * sizeof(int));
+    D.off_vis = D.off_neg + (long long)(S2 * sizeof(int));
+    D.off_rough = D.off_pos + (long long)(((3 * S2 + 1) & ~size_t(1)) * sizeof(int));
+    char* mine = D.base[me];
+    double* maps = reinterpret_cast<double*>(mine);
+    int* imaps = reinterpret_cast<int*>(mine + D.off_pos);
+    double* rough = reinterpret_cast<double*>(mine + D.off_rough);
+    const int W = (S + 31) / 32;
+    unsigned* known = h->known; unsigned* knownT = h->known + (size_t)S * W;
+
+    if (phases & 1) {
+        if (int e = finish_outputs(h)) return e;
+        for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];
+        MergeArgs A;
+        A.n = 0; A.use_masks = 1;
+        RankBufs B; B.n = N;
+        for (int k = 0; k < N; ++k) {
+            SlotRef& r = A.s[A.n++];
+            r = SlotRef{};
+            r.map = K->code_grids[k]; r.gmask = K->group_masks[k];
+            B.grid[k] = K->code_grids[k]; B.rec[k] = K->records[k];
+        }
+        SlotRef prev{};
+        const int has_prev = pc.valid ? 1 : 0;
+        if (has_prev) {
+            prev.map = pc.index_map; prev.metrics = pc.metrics; prev.hit = pc.hit; prev.total = pc.total; prev.minh = pc.minh;
+            prev.dx = (int)(origin[0] - pc.origin[0]); prev.dy = (int)(origin[1] - pc.origin[1]); prev.dz = (int)(origin[2] - pc.origin[2]);
+            prev.is_prev = 1;
+            prev.gmask = pc.has_gmask ? pc.gmask : nullptr;
+            if (!prev.gmask) A.use_masks = 0;
+            A.s[A.n++] = prev;
+        }
+        rec(h, EV_CSTART, st);
+        {
+            MergeOut O{};
+            O.cmap = c.index_map; O.counter = h->flags + 4; O.cell_voxel = c.cell_voxel;
+            O.col_occ = h->col_minz; O.col_free = h->col_minz + S2;
+            O.gmask = c.gmask; O.cap = (int)h->ccap;
+            O.wait_flags = K->partial_headers; O.wait_n = N; O.wait_epoch = epoch; O.wait_stride = 4;
+            O.org[0] = (int)origin[0]; O.org[1] = (int)origin[1]; O.org[2] = (int)origin[2];
+            void* m = nullptr;
+            if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) O.err_flag = (int*)m + 1; else cudaGetLastError();
+            h->counters_host[1] = 0;
+            O.row_y0 = R.y0; O.row_n = N;
+            launch(k_merge_codes<8, MERGE_FINISH>, dim3(std::max(1, h->grid_codes / std::max(1, N / 2))), dim3(256), 0, st, A, O, h->dp);
+        }
+        rec(h, EV_CODES, st);
+        {
+            SlabCells out{c.hit, c.total, c.minh, c.cell_voxel, c.metrics, c.eig};
+            SignalSet none{};
+            launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 4, out, none, h->dp,
+                   (int)h->ccap, (int)K->record_capacity);
+        }
+        rec(h, EV_CELLS, st);
+        {
+            int* host_count = nullptr;
+            void* m = nullptr;
+            if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) host_count = (int*)m; else cudaGetLastError();
+            launch(k_rows_columns, dim3(blocks_for((int64_t)S * R.nrows + 1, 256)), dim3(256), 0, st, c.index_map, c.minh, h->col_minz,
+                   h->col_minz + S2, c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, R, D,
+                   h->flags + 4, c.counter, host_count);
+            SignalSet Sg; Sg.n = N;
+            for (int k = 0; k < N; ++k) Sg.slot[k] = K->heights_slots[k];
+            launch(k_signal, dim3(1), dim3(32), 0, st, Sg, (int)epoch);
+        }
+        h->stats.kernel_launches += 4;
+        h->prof_combine = false;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (phases & 2) {
+        launch(k_rows_known, dim3(W, W), dim3(1024), 0, st, (const double*)maps, h->dp, known, knownT, K->heights_flags, N, (int)epoch);
+        const size_t mask_bytes = 2 * (size_t)S * W * sizeof(unsigned);
+        const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
+        launch(k_surface_maps2, dim3(blocks_for((int64_t)S * R.nrows, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit,
+               c.total, (const double*)maps, (const double*)(maps + S2), known, knownT, c.origin[2], h->dp, rough, maps + 3 * S2,
+               maps + 4 * S2, maps + 5 * S2, imaps, imaps + S2, imaps + 2 * S2, in_smem, h->col_minz, h->flags + 4,
+               (int*)nullptr, (int*)nullptr, (int*)nullptr, (double*)nullptr, R, D);
+        SignalSet Sg; Sg.n = N;
+        for (int k = 0; k < N; ++k) Sg.slot[k] = K->results_slots[k];
+        launch(k_signal, dim3(1), dim3(32), 0, st, Sg, (int)epoch);
+        h->stats.kernel_launches += 3;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (phases & 4) {
+        launch(k_wait_flags, dim3(1), dim3(32), 0, st, K->results_flags, N, (int)epoch);
+        h->stats.kernel_launches += 1;
+        rec(h, EV_MAPS, st);
+        const size_t bi = S2 * sizeof(int), bd = S2 * sizeof(double);
+        const size_t rough_off = ((3 * S2 + 1) & ~size_t(1)) * sizeof(int);
+        GvomHandle::Pending& pd = h->pend;
+        pd = GvomHandle::Pending{};
+        pd.active = true; pd.c = &c; pd.st = st;
+        if (out_mem == GVOM_DEVICE) {
+            if (positive) CUDA_TRY(cudaMemcpyAsync(positive, imaps, bi, cudaMemcpyDeviceToDevice, st));
+            if (negative) CUDA_TRY(cudaMemcpyAsync(negative, imaps + S2, bi, cudaMemcpyDeviceToDevice, st));
+            if (visibility) CUDA_TRY(cudaMemcpyAsync(visibility, imaps + 2 * S2, bi, cudaMemcpyDeviceToDevice, st));
+            if (roughness) CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToDevice, st));
+        } else if (out_mem == GVOM_HOST) {
+            bool dev = false;
+            const bool pinned = positive && negative && visibility && roughness && is_pinned_or_device(positive, &dev) &&
+                                is_pinned_or_device(negative, &dev) && is_pinned_or_device(visibility, &dev) &&
+                                is_pinned_or_device(roughness, &dev);
+            if (pinned && negative == positive + S2 && visibility == negative + S2 &&
+                reinterpret_cast<char*>(roughness) == reinterpret_cast<char*>(positive) + rough_off) {
+                CUDA_TRY(cudaMemcpyAsync(positive, imaps, rough_off + bd, cudaMemcpyDeviceToHost, st));
+            } else if (pinned) {
+                CUDA_TRY(cudaMemcpyAsync(positive, imaps, bi, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(negative, imaps + S2, bi, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(visibility, imaps + 2 * S2, bi, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToHost, st));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(h->out_i_host, imaps, rough_off + bd, cudaMemcpyDeviceToHost, st));
+                pd.from_mirror = true;
+                pd.positive = positive; pd.negative = negative; pd.visibility = visibility; pd.roughness = roughness;
+            }
+        }
+        // the library's own 2-D block (debug exports, OccupancyGrid post-processing, state save) follows
+        CUDA_TRY(cudaMemcpyAsync(h->maps, maps, 6 * bd, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(h->imaps, imaps, rough_off + bd, cudaMemcpyDeviceToDevice, st));
+        rec(h, EV_D2H, st);
+        h->have_maps = true;
+        if (origin_out) {
+            origin_out[0] = c.origin[0] * h->p.xy_resolution;
+            origin_out[1] = c.origin[1] * h->p.xy_resolution;
+            origin_out[2] = c.origin[2] * h->p.z_resolution;
+        }
+        if (int e = finish_outputs(h)) return e;
+        if (h->counters_host[1]) return fail(GVOM_EINVAL, "multi-GPU combine: ranks disagree on the map origin (sensors must share the ego position)");
+        c.has_gmask = true;
+        c.valid = true;
+        h->cur = 1 - h->cur;
+        h->stats.combine_calls++;
+    }
     return GVOM_OK;
 }
 

@@ -201,6 +201,11 @@ struct MergeOut {
     const int* wait_flags;   // FINISH, peer-to-peer: flags[k] >= wait_epoch once rank k's partial results are visible
     int wait_n, wait_epoch;
     int slab_r, slab_n;      // FINISH, sharded: this rank finishes the z-planes with z % slab_n == slab_r (slab_n <= 1: all)
+    int row_y0, row_n;       // FINISH, row-sharded: this rank finishes the rows y = row_y0, row_y0 + row_n, ... of every plane
+                             // (row_n <= 1: all); needs S % (32 VEC) == 0 so that a warp never straddles two rows
+    int wait_stride;         // ints between two ranks' flags (1: plain flags, 4: {epoch, ox, oy, oz} headers)
+    int org[3];              // wait_stride == 4: the origin this rank merges in; a peer header that disagrees raises *err_flag
+    int* err_flag;
 };
 
 __device__ __forceinline__ void column_min(int* __restrict__ col, int z) {
@@ -247,9 +252,13 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
         // until all ranks have published this combine's partial results (their signal kernel wrote the epoch
         // into OUR flag slots after a system-scope fence), then reads the peers' grids over NVLink.
         if (threadIdx.x == 0) {
+            const int stride = O.wait_stride > 0 ? O.wait_stride : 1;
             for (int k = 0; k < O.wait_n; ++k) {
-                const volatile int* f = O.wait_flags + k;
+                const volatile int* f = O.wait_flags + k * stride;
                 while (*f < O.wait_epoch) __nanosleep(100);
+                // headers carry the origin their rank merged in: all ranks must have used the same frame
+                if (stride == 4 && blockIdx.x == 0 && O.err_flag && f[1] != 0x7fffffff &&
+                    (f[1] != O.org[0] || f[2] != O.org[1] || f[3] != O.org[2])) *O.err_flag = 1;
             }
             __threadfence_system();
         }
@@ -262,14 +271,22 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
     // sharded finish: only the z-planes this rank owns (interleaved: z % slab_n == slab_r, so the few ground
     // planes that hold most cells spread over all ranks); QP = items per plane
     const bool slab = MODE == MERGE_FINISH && O.slab_n > 1;
+    const bool rslab = MODE == MERGE_FINISH && O.row_n > 1;
     const long long QP = ((long long)S * S) / VEC;
+    const int RQ = S / VEC;                                   // items per row
+    const int my_rows = (rslab && O.row_y0 < S) ? (S - O.row_y0 + O.row_n - 1) / O.row_n : 0;
     const int my_planes = slab ? (Z - O.slab_r + O.slab_n - 1) / O.slab_n : Z;
-    const long long NQ = slab ? my_planes * QP : P.V / VEC;
+    const long long NQ = rslab ? (long long)Z * my_rows * RQ : slab ? my_planes * QP : P.V / VEC;
     const long long NQp = (NQ + 31) & ~31LL;
     const int has_prev = (A.n > 0 && A.s[A.n - 1].is_prev) ? 1 : 0;
     for (long long ql = (long long)blockIdx.x * blockDim.x + threadIdx.x; ql < NQp; ql += step) {
         // local item -> global item (warp-uniform plane: QP is a multiple of 32 in slab mode)
-        const long long q = slab ? ((long long)O.slab_r + (long long)O.slab_n * (ql / QP)) * QP + ql % QP : ql;
+        long long q = slab ? ((long long)O.slab_r + (long long)O.slab_n * (ql / QP)) * QP + ql % QP : ql;
+        if (rslab) {                                          // local row counter -> (z, own row) -> global item
+            const int jr = (int)(ql / RQ), xi = (int)(ql - (long long)jr * RQ);
+            const int zz = jr / max(my_rows, 1), yi = jr - zz * my_rows;
+            q = ((long long)zz * S + (O.row_y0 + O.row_n * yi)) * RQ + xi;
+        }
         const bool live = ql < NQ;
         int acc_and[VEC], sum[VEC], enc_or[VEC];
 #pragma unroll
@@ -815,6 +832,23 @@ k_column_maps(const int* __restrict__ cmap, const float* __restrict__ cminh, con
     }
 }
 
+// Row-sharded multi-GPU combine: rank r owns the grid rows y with (y + origin_y) mod n == r -- whole columns, so the
+// column reductions and the 2-D stage of its rows are local -- i.e. the rows y0, y0 + n, ... (nrows of them).
+struct RowShard { int y0, n, nrows; };
+// The 2-D maps of a row-sharded combine are replicated by PUSHING: the owner of a row stores its values into every
+// rank's 2-D block (symmetric memory, same layout everywhere; remote stores are posted).  n == 0: single GPU.
+struct PushSet {
+    char* base[16];          // every rank's 2-D block as mapped here
+    int n, self;
+    long long off_maps;      // six float64 maps [height, inferred, -, x slope, y slope, guessed]
+    long long off_pos, off_neg, off_vis, off_rough;
+};
+template <typename T>
+__device__ __forceinline__ void push_value(const PushSet& D, long long off, long long idx, T v) {
+    for (int d = 0; d < D.n; ++d)
+        if (d != D.self) reinterpret_cast<T*>(D.base[d] + off)[idx] = v;
+}
+
 // 32 bits of a bit row starting at bit position `pos` (may be negative / run past the row: those bits read 0)
 __device__ __forceinline__ unsigned row_window(const unsigned* __restrict__ row, int W, int pos) {
     const int wi = pos >> 5;                                  // floor
@@ -841,13 +875,16 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
                 DevParams P, double* __restrict__ rough, double* __restrict__ xs, double* __restrict__ ys,
                 double* __restrict__ guessed, int* __restrict__ pos, int* __restrict__ neg, int* __restrict__ vis,
                 int masks_in_smem, int* __restrict__ col_minz, int* __restrict__ scratch_count,
-                int* __restrict__ pos2, int* __restrict__ neg2, int* __restrict__ vis2, double* __restrict__ rough2) {
+                int* __restrict__ pos2, int* __restrict__ neg2, int* __restrict__ vis2, double* __restrict__ rough2,
+                RowShard R, PushSet D) {
     pdl_wait();
     extern __shared__ unsigned smask[];
     const int S = P.S, Z = P.Z;
     const int W = (S + 31) >> 5;
     const int role = threadIdx.x >> 7;
     const int t = blockIdx.x * 128 + (threadIdx.x & 127);
+    const int ncell = S * R.nrows;                        // cells this launch owns (all of them on a single GPU)
+    const long long S2 = (long long)S * S;
     if (role == 1) {
         const unsigned* known = known_g;
         const unsigned* knownT = knownT_g;
@@ -861,11 +898,11 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
             known = smask;
             knownT = smask + S * W;
         }
-        if (t >= S * S) return;
-        const int y0 = t % S, x0 = t / S;
+        if (t >= ncell) return;
+        const int y0 = R.y0 + R.n * (t % R.nrows), x0 = t / R.nrows;
         // housekeeping for the next combine: C1's column minima and running counter start clean
-        col_minz[t] = 0x7f7f7f7f;
-        col_minz[S * S + t] = 0x7f7f7f7f;
+        col_minz[y0 * S + x0] = 0x7f7f7f7f;
+        col_minz[S2 + y0 * S + x0] = 0x7f7f7f7f;
         if (t == 0) *scratch_count = 0;
         const double h0 = GVOM_HM(height, x0, y0);
         const double inf0 = GVOM_HM(inferred, x0, y0);
@@ -926,10 +963,16 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
         GVOM_HM(neg, x0, y0) = nv;
         GVOM_HM(vis, x0, y0) = vv;
         if (neg2) { GVOM_HM(neg2, x0, y0) = nv; GVOM_HM(vis2, x0, y0) = vv; }
+        if (D.n) {
+            const long long ci = (long long)x0 * S + y0;
+            push_value<double>(D, D.off_maps + 5 * S2 * 8, ci, dh_out);
+            push_value<int>(D, D.off_neg, ci, nv);
+            push_value<int>(D, D.off_vis, ci, vv);
+        }
         return;
     }
-    if (t >= S * S) return;
-    const int y0 = t % S, x0 = t / S;
+    if (t >= ncell) return;
+    const int y0 = R.y0 + R.n * (t % R.nrows), x0 = t / R.nrows;
 
     // ---- slope + roughness (gvom.py:717-805); contraction pattern = SASS of the reference.
     double hz[9];
@@ -1026,6 +1069,83 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
     }
     GVOM_HM(pos, x0, y0) = pv;
     if (pos2) GVOM_HM(pos2, x0, y0) = pv;
+    if (D.n) {
+        const long long ci = (long long)x0 * S + y0;
+        push_value<double>(D, D.off_rough, ci, rg);
+        push_value<double>(D, D.off_maps + 3 * S2 * 8, ci, sxv);
+        push_value<double>(D, D.off_maps + 4 * S2 * 8, ci, syv);
+        push_value<int>(D, D.off_pos, ci, pv);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Row-sharded multi-GPU combine, 2-D stage helpers.
+//   k_rows_columns   C3 for the rows this rank owns: heights from its (complete) column minima, pushed into every
+//                    rank's 2-D block; publishes the rank's cell count
+//   k_rows_known     after the height barrier: the "height known" bit maps of the WHOLE map (every rank builds its own)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rows_columns(const int* __restrict__ cmap, const float* __restrict__ cminh, const int* __restrict__ col_occ,
+               const int* __restrict__ col_free, double o0, double o1, double o2, double e0, double e1, double e2,
+               DevParams P, RowShard R, PushSet D, const int* __restrict__ scratch_count, int* __restrict__ map_count,
+               int* __restrict__ host_count) {
+    pdl_wait();
+    const int S = P.S;
+    const long long S2 = (long long)S * S;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        const int n = *scratch_count;
+        *map_count = n;
+        if (host_count) *host_count = n;
+    }
+    if (t >= S * R.nrows) return;
+    const int x = t % S, y = R.y0 + R.n * (t / S);        // x fastest: the column minima are [y][x]
+    double h = -1000.0, inf = -1000.0;
+    const double xp = __fma_rn(__dadd_rn(o0, (double)x), P.xy_res, -e0);
+    const double yp = __fma_rn(__dadd_rn(o1, (double)y), P.xy_res, -e1);
+    if (__fma_rn(xp, xp, __dmul_rn(yp, yp)) <= P.r2) h = __dsub_rn(e2, P.ground_to_lidar);
+    const int zo = col_occ[(long long)y * S + x], zf = col_free[(long long)y * S + x];
+    if (zo < P.Z) {
+        const int idx = cmap[x + (long long)y * S + zo * S2];
+        h = __dmul_rn(__dadd_rn(__dadd_rn((double)zo, (double)cminh[idx]), o2), P.z_res);
+    }
+    if (zf < P.Z) inf = __dmul_rn(__dadd_rn(o2, (double)zf), P.z_res);
+    const long long ci = (long long)x * S + y;
+    for (int d = 0; d < D.n; ++d) {                        // own copy included
+        double* m = reinterpret_cast<double*>(D.base[d] + D.off_maps);
+        m[ci] = h; m[S2 + ci] = inf;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_rows_known(const double* __restrict__ height, DevParams P, unsigned* __restrict__ known, unsigned* __restrict__ knownT,
+             const int* __restrict__ wait_flags, int wait_n, int wait_epoch) {
+    pdl_wait();
+    wait_flags_block(wait_flags, wait_n, wait_epoch);      // every rank has pushed the heights of its rows
+    __shared__ unsigned char flag[32][33];
+    const int S = P.S;
+    const int W = (S + 31) >> 5;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 32 + ty;
+    bool kn = false;
+    if (x < S && y < S) kn = __ldcg(height + (long long)x * S + y) > -1000.0;
+    flag[ty][tx] = kn ? 1 : 0;
+    const unsigned wT = __ballot_sync(FULL, kn);          // bits over x for row y
+    if (tx == 0 && y < S) knownT[(long long)y * W + blockIdx.x] = wT;
+    __syncthreads();
+    if (threadIdx.x < 32) {                               // bits over y for column x = tile x0 + threadIdx.x
+        unsigned w = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) w |= (unsigned)flag[b][threadIdx.x] << b;
+        const int xx = blockIdx.x * 32 + threadIdx.x;
+        if (xx < S) known[(long long)xx * W + blockIdx.y] = w;
+    }
+}
+
+// waits (device side) until all ranks' flags have reached the epoch; ordered before the copies that follow it
+__global__ void k_wait_flags(const int* __restrict__ flags, int n, int epoch) {
+    pdl_wait();
+    wait_flags_block(flags, n, epoch);
 }
 
 // ---------------------------------------------------------------------------
@@ -1151,6 +1271,19 @@ constexpr int MAX_RANKS = 16;
 // the OTHER GPUs' buffers mapped over NVLink, read directly by the kernels below.
 struct RecordSet { const float* r[MAX_RANKS]; const int* count[MAX_RANKS]; int n; };
 struct SignalSet { int* slot[MAX_RANKS]; int n; };
+
+// header variant: {epoch, ox, oy, oz} -- the origin first, then (after a fence) the epoch the waiters poll
+__global__ void k_signal_header(SignalSet S, int epoch, int ox, int oy, int oz) {
+    pdl_wait();
+    __threadfence_system();
+    if (threadIdx.x < S.n) {
+        volatile int* f = S.slot[threadIdx.x];
+        f[1] = ox; f[2] = oy; f[3] = oz;
+        __threadfence_system();
+        f[0] = epoch;
+    }
+    __threadfence_system();
+}
 
 // publish "my partial results of combine `epoch` are complete" into every rank's flag slot for this rank
 __global__ void k_signal(SignalSet S, int epoch) {

@@ -36,7 +36,7 @@ import time
 
 import numpy as np
 
-from ._lib import GVOM_DEVICE, GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, check
+from ._lib import GVOM_DEVICE, GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, GvomRowsLinks, check
 from .gvom import Gvom
 
 HEADER_DOUBLES = 8          # [valid, count, ox, oy, oz, pad...]
@@ -65,7 +65,7 @@ class MultiGpuGvom(Gvom):
     """One rank of a multi-GPU Gvom.  Same API as Gvom; combine_maps() is collective
     (every rank must call it) and returns the same maps on every rank."""
 
-    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", sharded="auto", **kw):
+    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", sharded="auto", rows="auto", **kw):
         import os
         import torch
         import torch.distributed as dist
@@ -94,6 +94,17 @@ class MultiGpuGvom(Gvom):
         if sharded == "auto":
             sharded = self.world >= 6
         self._sharded = bool(sharded) and self.xy_size % 16 == 0
+        # row-sharded finish (default where it applies: xy_size % 256 == 0): every rank merges only the world rows it owns
+        # and keeps the 3-D state of those rows; only 2-D maps are replicated.  GVOM_MULTI_ROWS=0 selects the older
+        # finishes (replicated / plane-sharded with full assembly) for A/B runs.
+        if rows == "auto":
+            rows = os.environ.get("GVOM_MULTI_ROWS", "1") != "0"
+        self._rows = bool(rows) and self.xy_size % 256 == 0
+        if self._rows:
+            self._sharded = False
+        nb = C.c_uint64(0)
+        check(self._L.gvom_rows_block_size(self._h, C.byref(nb)), "gvom_rows_block_size")
+        self._b2d_bytes = int(nb.value)
         ccap = min(self.voxel_count, 4 * self.max_points * (self.buffer_size + 1))
         self._res_cap = int(min(self.voxel_count, max(1 << 18, 4 * ccap // self.world)))
         if exchange in ("auto", "p2p"):
@@ -133,6 +144,13 @@ class MultiGpuGvom(Gvom):
         self._o_rcel = (self._o_rmap + 4 * V + 255) & ~255
         if self._sharded:
             total = self._o_rcel + 68 * self._res_cap + 256
+        if self._rows:
+            # row-sharded finish: {epoch, origin} headers of the partial results, "heights" / "results" flags, the 2-D block
+            self._o_hdr4 = (total + 255) & ~255
+            self._o_fh = self._o_hdr4 + 16 * 64 + 256
+            self._o_fr = self._o_fh + 4 * 64 + 256
+            self._o_b2d = (self._o_fr + 4 * 64 + 255 + 256) & ~255
+            total = self._o_b2d + self._b2d_bytes + 256
         return o_grid, o_msk, o_rec, o_cnt, o_hdr, total, o_flg
 
     def _init_p2p(self):
@@ -161,6 +179,18 @@ class MultiGpuGvom(Gvom):
                 # count table (64 ints) in every rank's block: entry r is pushed by rank r
                 "cslots": _ptr_array([p + self._o_rcnt + 4 * self.rank for p in ptrs]), "ctable": ptrs[self.rank] + self._o_rcnt,
             })
+            if self._rows:
+                K = GvomRowsLinks()
+                K.rank, K.nranks, K.record_capacity = self.rank, self.world, self._rec_cap
+                for r, p in enumerate(ptrs):
+                    K.code_grids[r], K.group_masks[r], K.records[r] = p + o_grid, p + o_msk, p + o_rec
+                    K.blocks2d[r] = p + self._o_b2d
+                    K.heights_slots[r] = p + self._o_fh + 4 * self.rank
+                    K.results_slots[r] = p + self._o_fr + 4 * self.rank
+                me_p = ptrs[self.rank]
+                K.partial_headers, K.heights_flags, K.results_flags = me_p + self._o_hdr4, me_p + self._o_fh, me_p + self._o_fr
+                self._sets[-1]["links"] = K
+                self._sets[-1]["hdr4"] = _ptr_array([p + self._o_hdr4 + 16 * self.rank for p in ptrs])
         torch.cuda.synchronize(self._dev)
         dist.barrier(group=self._group)
         self._hdr_host = torch.zeros(HEADER_DOUBLES, dtype=torch.float64).pin_memory()
@@ -203,7 +233,12 @@ class MultiGpuGvom(Gvom):
             hh[0] = 1.0 if have else 0.0
             hh[2], hh[3], hh[4] = (self._org_in[0], self._org_in[1], self._org_in[2]) if have else (0.0, 0.0, 0.0)
             X["hdr_view"].copy_(hh, non_blocking=True)
-            if have:
+            if have and self._rows:
+                # partial kernels, then the header kernel: {epoch, origin} into every rank's block
+                check(L.gvom_combine_partial_header(self._h, self._org_in, me + o_grid, me + o_msk, me + o_rec, self._rec_cap,
+                                                    me + o_cnt, X["hdr4"], self.world, epoch, self._stream),
+                      "gvom_combine_partial_header")
+            elif have:
                 # partial kernels, then the signal kernel: "rank `me`, combine `epoch`: done" into every rank's block
                 check(L.gvom_combine_partial(self._h, self._org_in, me + o_grid, me + o_msk, me + o_rec, self._rec_cap,
                                              me + o_cnt, X["signal"], self.world, epoch, self._stream), "gvom_combine_partial")
@@ -212,10 +247,16 @@ class MultiGpuGvom(Gvom):
                 # for the others and adopt the origin of a rank that has data.
                 t[o_grid:o_rec].zero_()              # empty grid, empty group mask
                 t[o_cnt:o_cnt + 4].zero_()
-                for r in range(self.world):
-                    hdl.get_buffer(r, (64,), torch.int32, o_flg // 4)[self.rank:self.rank + 1].fill_(epoch)
+                if self._rows:       # header {epoch, no origin}
+                    mine = torch.tensor([epoch, 0x7fffffff, 0, 0], dtype=torch.int32, device=self._dev)
+                    for r in range(self.world):
+                        hdl.get_buffer(r, (64 * 4,), torch.int32, self._o_hdr4 // 4)[4 * self.rank:4 * self.rank + 4].copy_(mine)
+                    flags = t[self._o_hdr4:self._o_hdr4 + 16 * 64].view(torch.int32)[:4 * self.world:4]
+                else:
+                    for r in range(self.world):
+                        hdl.get_buffer(r, (64,), torch.int32, o_flg // 4)[self.rank:self.rank + 1].fill_(epoch)
+                    flags = t[o_flg:o_flg + 4 * 64].view(torch.int32)[:self.world]
                 self._tstream.synchronize()
-                flags = t[o_flg:o_flg + 4 * 64].view(torch.int32)[:self.world]
                 while int(flags.min().item()) < epoch:
                     time.sleep(1e-4)
                 heads = np.stack([hdl.get_buffer(r, (HEADER_DOUBLES,), torch.float64, o_hdr // 8).cpu().numpy()
@@ -227,6 +268,13 @@ class MultiGpuGvom(Gvom):
                 for k in range(3):
                     self._org_in[k] = float(origin[k])
             outs, optr, mem = self._outputs(device_outputs)
+            if self._rows:
+                # own world rows: merge + cells + columns; heights and finished maps are pushed to every rank
+                check(L.gvom_combine_finish_rows(self._h, self._org_in, C.byref(X["links"]), epoch, 7, self._org_c,
+                                                 optr[0], optr[1], optr[2], optr[3], mem, self._stream),
+                      "gvom_combine_finish_rows")
+                pos, neg, rough, vis = outs
+                return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
             if self._sharded:
                 # every rank finishes 1/world of the planes, publishes them, and assembles the full map from all ranks
                 check(L.gvom_combine_finish_sharded(self._h, self._org_in, self.rank, self.world, X["grids"], X["masks"],

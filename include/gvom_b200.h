@@ -232,6 +232,39 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
                                 int32_t phases, double origin_out[3], int32_t* positive, int32_t* negative,
                                 double* roughness, int32_t* visibility, int32_t out_mem, void* stream);
 
+/* Row-sharded finish (peer-to-peer exchange, xy_size % 256 == 0) -- the default multi-GPU combine.  Rank r owns
+ * the WORLD rows y with (y + origin_y) mod nranks == r (whole columns): it merges only those rows from every rank's
+ * encoded grid and keeps the previous combined map and the cells of those rows, so the 3-D state is SHARDED; the
+ * column reductions and the 2-D stage of its columns are local.  Only 2-D maps are replicated, by pushing into every
+ * rank's 2-D block (symmetric memory, gvom_rows_block_size() bytes): heights after the column stage, the finished maps
+ * after the surface stage.  gvom_combine_partial_header() is gvom_combine_partial() whose signal carries the origin
+ * ({epoch, ox, oy, oz} int32 headers): the finishing ranks verify that everybody merged in the same frame
+ * (GVOM_EINVAL otherwise).  phases: 1 = own rows + cells + heights, 2 = surface stage, 4 = deliver; 7 = all
+ * (separate phases let one process play several ranks in the tests).  Every flag / header table has one entry per rank,
+ * written by that rank with the combine's epoch (1, 2, ...). */
+#define GVOM_MAX_RANKS 16
+typedef struct GvomRowsLinks {
+    int32_t rank, nranks;
+    const int32_t* code_grids[GVOM_MAX_RANKS];     /* every rank's encoded grid / group mask / records as mapped here */
+    const uint32_t* group_masks[GVOM_MAX_RANKS];
+    const float* records[GVOM_MAX_RANKS];
+    int64_t record_capacity;
+    const int32_t* partial_headers;                /* local: nranks x {epoch, ox, oy, oz} */
+    void* blocks2d[GVOM_MAX_RANKS];                /* every rank's 2-D block */
+    int32_t* heights_slots[GVOM_MAX_RANKS];        /* this rank's "heights pushed" flag in every rank's memory */
+    const int32_t* heights_flags;                  /* local: nranks flags */
+    int32_t* results_slots[GVOM_MAX_RANKS];        /* this rank's "maps pushed" flag in every rank's memory */
+    const int32_t* results_flags;                  /* local: nranks flags */
+} GvomRowsLinks;
+int gvom_rows_block_size(GvomHandle* h, uint64_t* bytes);
+int gvom_combine_partial_header(GvomHandle* h, const double origin[3], int32_t* code_grid_dev,
+                                uint32_t* group_mask_dev, float* records_dev, int64_t record_capacity,
+                                int32_t* record_count_dev, int32_t* const* header_slots, int32_t n_signal,
+                                int32_t epoch, void* stream);
+int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRowsLinks* links, int32_t epoch,
+                             int32_t phases, double origin_out[3], int32_t* positive, int32_t* negative,
+                             double* roughness, int32_t* visibility, int32_t out_mem, void* stream);
+
 /* ---- test / tooling hooks (canonical parity dumps; not on the hot path) ---- */
 int gvom_slot_info(GvomHandle* h, int32_t slot, int32_t* valid, int64_t* cells, double origin[3]);
 int gvom_last_slot(GvomHandle* h, int32_t* slot);

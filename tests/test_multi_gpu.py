@@ -130,6 +130,119 @@ def local_exchange_sharded(ranks, epoch):
     return outs
 
 
+def local_exchange_rows(ranks, epoch):
+    """In-process emulation of the ROW-SHARDED finish: every "rank" merges the world rows it owns + their cells and
+    pushes the heights of its columns (phase 1, all ranks), runs the surface stage of its rows and pushes the maps
+    (phase 2), then delivers (phase 4)."""
+    import torch
+    from gvom_b200._lib import GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, GvomRowsLinks, check
+    g0 = ranks[0]
+    L, V = g0._L, g0.voxel_count
+    dev = f"cuda:{g0.device}"
+    n = len(ranks)
+    org = (C.c_double * 3)()
+    origin = None
+    for g in ranks:
+        if L.gvom_newest_origin(g._h, org) != GVOM_NO_DATA and origin is None:
+            origin = [org[0], org[1], org[2]]
+    o = (C.c_double * 3)(*origin)
+    cap = int(min(V, g0.buffer_size * g0.max_points))
+    nb = C.c_uint64(0)
+    check(L.gvom_rows_block_size(g0._h, C.byref(nb)), "block size")
+    parr = lambda ps: (C.c_void_p * len(ps))(*[C.c_void_p(int(p)) for p in ps])
+    B = [dict(grid=torch.empty(V, dtype=torch.int32, device=dev), msk=torch.empty(V // 256 + 2, dtype=torch.int32, device=dev),
+              rec=torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev), cnt=torch.zeros(1, dtype=torch.int32, device=dev),
+              hdr=torch.zeros(64 * 4, dtype=torch.int32, device=dev), fh=torch.zeros(64, dtype=torch.int32, device=dev),
+              fr=torch.zeros(64, dtype=torch.int32, device=dev), b2d=torch.zeros(nb.value, dtype=torch.uint8, device=dev)) for _ in ranks]
+    for r, g in enumerate(ranks):
+        hs = parr([b["hdr"].data_ptr() + 16 * r for b in B])
+        check(L.gvom_combine_partial_header(g._h, o, B[r]["grid"].data_ptr(), B[r]["msk"].data_ptr(), B[r]["rec"].data_ptr(), cap,
+                                            B[r]["cnt"].data_ptr(), hs, n, epoch, None), "partial")
+    torch.cuda.synchronize()
+    links = []
+    for r in range(n):
+        K = GvomRowsLinks()
+        K.rank, K.nranks, K.record_capacity = r, n, cap
+        for k, b in enumerate(B):
+            K.code_grids[k], K.group_masks[k], K.records[k] = b["grid"].data_ptr(), b["msk"].data_ptr(), b["rec"].data_ptr()
+            K.blocks2d[k] = b["b2d"].data_ptr()
+            K.heights_slots[k] = b["fh"].data_ptr() + 4 * r
+            K.results_slots[k] = b["fr"].data_ptr() + 4 * r
+        K.partial_headers, K.heights_flags, K.results_flags = B[r]["hdr"].data_ptr(), B[r]["fh"].data_ptr(), B[r]["fr"].data_ptr()
+        links.append(K)
+    outs = []
+    for phase in (1, 2, 4):
+        for r, g in enumerate(ranks):
+            pos, neg, rough, vis = g._out_arrays()
+            oo = (C.c_double * 3)()
+            check(L.gvom_combine_finish_rows(g._h, o, C.byref(links[r]), epoch, phase, oo, pos.ctypes.data, neg.ctypes.data,
+                                             rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None), "rows")
+            torch.cuda.synchronize()
+            if phase == 4:
+                outs.append((np.array(list(oo)), pos, neg, rough, vis))
+    return outs, B
+
+
+def assemble_rows_state(ranks, outs, xy_res):
+    """Row-sharded state -> one canonical dump: rank r contributes the world rows (y + origin_y) % n == r."""
+    n = len(ranks)
+    S, Z = ranks[0].xy_size, ranks[0].z_size
+    oy = int(round(outs[0][0][1] / xy_res))
+    idx_all = np.full((Z, S, S), -1, np.int32)
+    vals = {}
+    for r, g in enumerate(ranks):
+        v = g.refview()
+        y0 = (r - oy) % n
+        idx = v.combined_index_map.reshape(Z, S, S)
+        own = np.zeros((Z, S, S), bool)
+        own[:, y0::n, :] = True
+        idx_all[own] = idx[own]
+        occ = np.flatnonzero((idx >= 0) & own)
+        ids = idx.reshape(-1)[occ]
+        for vox, i in zip(occ.tolist(), ids.tolist()):
+            vals[vox] = (v.combined_hit_count[i], v.combined_total_count[i], v.combined_min_height[i], v.combined_metrics[i],
+                         v.voxels_eigenvalues[i])
+    flat = idx_all.reshape(-1)
+    ids = np.flatnonzero(flat >= 0).astype(np.int32)
+    codes = np.where(flat >= 0, 0, flat).astype(np.int32)
+    hit = np.array([vals[i][0] for i in ids.tolist()], np.int32)
+    tot = np.array([vals[i][1] for i in ids.tolist()], np.int32)
+    mnh = np.array([vals[i][2] for i in ids.tolist()], np.float32)
+    met = np.array([vals[i][3] for i in ids.tolist()], np.float32).reshape(-1, 10)
+    return {"codes": codes, "ids": ids, "hit": hit, "total": tot, "minh": mnh, "metrics": met}
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+def test_row_sharded_finish_equals_single(nranks):
+    """gvom_combine_partial_header + gvom_combine_finish_rows (the default multi-GPU combine): the maps every rank
+    delivers and the 3-D state assembled from the ranks' row shards equal one Gvom holding every rank's ring slots."""
+    from gvom_b200 import Gvom
+    Bs = 2
+    kw = dict(xy_size=256, z_size=16, robot_radius=2.0)
+    P1, PN = synth.params_tuple(buffer_size=Bs, **kw), synth.params_tuple(buffer_size=Bs * nranks, **kw)
+    fr = sensor_frames(nranks, 4, wall=30.0)
+    ranks = [Gvom(*P1) for _ in range(nranks)]
+    for step in range(4):
+        for r in range(nranks):
+            ranks[r].Process_pointcloud(*fr[step][r])
+        outs, _keep = local_exchange_rows(ranks, step + 1)
+        ref = Gvom(*PN)
+        for s2 in range(step + 1):
+            for q in range(max(0, s2 - Bs + 1), s2 + 1):
+                for r in range(nranks):
+                    ref.Process_pointcloud(*fr[q][r])
+            last = ref.combine_maps()
+        want = canon.canon_combine(ref.refview(), last)
+        for r in range(nranks):
+            for a, b, name in zip(outs[r], last, ("origin", "pos", "neg", "rough", "vis")):
+                ok = np.allclose(a, b, rtol=1e-4, atol=1e-9, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b)
+                assert ok, f"step {step} rank {r}: {name}"
+        got = assemble_rows_state(ranks, outs, P1[0])
+        for k in ("codes", "ids", "hit", "total", "minh"):
+            assert np.array_equal(got[k], want[k]), f"step {step}: {k}"
+        assert np.allclose(got["metrics"], want["metrics"], rtol=1e-4, atol=2e-6), f"step {step}: metrics"
+
+
 def compare_state(a, b, what):
     """a, b: canon_combine dumps. ints exact, floats to tolerance."""
     for k in ("out_origin", "out_pos", "out_neg", "out_vis", "codes", "ids", "hit", "total", "minh"):
