@@ -251,6 +251,62 @@ def run_reference(args):
     print(json.dumps(base), flush=True)
 
 
+def multi_parity_check(g_class, P_rank, slots, world, rank, dev, exchange, steps=3):
+    """N > 1: a fresh multi-GPU Gvom replays `steps` frames per sensor; every rank also feeds ALL sensors' frames
+    through one single-GPU Gvom with world * slots ring slots on its own GPU and compares: the delivered maps
+    (ints exact, roughness 1e-4) and the 3-D state of the rows it owns (codes, hit / pass counts, min heights
+    exact; moments 1e-4).  -> dict for the JSON line; "ok" is the AND over all ranks."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from gvom_b200.gvom import Gvom
+    st = torch.cuda.Stream(device=dev)
+    g = g_class(*P_rank, device=dev, stream=st.cuda_stream, torch_stream=st, exchange=exchange)
+    PN = list(P_rank); PN[4] = slots * world
+    ref = Gvom(*PN, device=dev)
+    allfr = [frames(r)[:steps] for r in range(world)]
+    res = {"maps_equal": True, "codes_equal": True, "counts_equal": True, "moments_close": True}
+    sha = hashlib.sha256()
+    for s in range(steps):
+        g.Process_pointcloud(*allfr[rank][s])
+        out = g.combine_maps()
+        for r in range(world):
+            ref.Process_pointcloud(*allfr[r][s])
+        want = ref.combine_maps()
+        for a, b in zip(out, want):
+            same = np.allclose(a, b, rtol=1e-4, atol=1e-9, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b)
+            res["maps_equal"] &= bool(same)
+        S, Z = g.xy_size, g.z_size
+        v, w = g.refview(), ref.refview()
+        rows = slice(None)
+        if getattr(g, "_rows", False) and g.exchange == "p2p":      # sharded state: the world rows this rank owns
+            oy = int(round(out[0][1] / g.xy_resolution))
+            rows = slice((rank - oy) % world, None, world)
+        a = v.combined_index_map.reshape(Z, S, S)[:, rows, :]
+        b = w.combined_index_map.reshape(Z, S, S)[:, rows, :]
+        ca, cb = np.where(a >= 0, 0, a), np.where(b >= 0, 0, b)
+        res["codes_equal"] &= bool(np.array_equal(ca, cb))
+        ia, ib = a[a >= 0], b[b >= 0]
+        if ia.size == ib.size:
+            res["counts_equal"] &= bool(np.array_equal(v.combined_hit_count[ia], w.combined_hit_count[ib]) and
+                                        np.array_equal(v.combined_total_count[ia], w.combined_total_count[ib]) and
+                                        np.array_equal(v.combined_min_height[ia], w.combined_min_height[ib]))
+            res["moments_close"] &= bool(np.allclose(v.combined_metrics[ia], w.combined_metrics[ib], rtol=1e-4, atol=2e-6))
+        else:
+            res["counts_equal"] = res["moments_close"] = False
+        sha.update(np.ascontiguousarray(cb).tobytes())
+        for m in want[1:]:
+            sha.update(np.ascontiguousarray(m if m.dtype.kind != "f" else np.round(m, 6)).tobytes())
+    ok = all(res.values())
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{dev}")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    res.update({"ok": bool(int(t.item())), "steps": steps, "ranks": world, "rank0_reference_sha": sha.hexdigest()[:16],
+                "against": f"one single-GPU Gvom with {slots * world} ring slots fed with all {world} sensors' frames, on every rank",
+                "state": "row shards (world rows (y + origin_y) mod ranks)" if rows != slice(None) else "replicated"})
+    g.close(); ref.close()
+    return res
+
+
 def atomic_peak(L, torch, dev):
     """L2 atomic throughput (G atomics/s): random words of a 16 MiB table, and one word."""
     import ctypes as C
@@ -275,7 +331,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots-per-sensor", type=int, default=0, help="ring slots per sensor / rank (default: 4 at N=1, 2 at N>1)")
     ap.add_argument("--config", default="os1_128", choices=list(CONFIGS), help="workload: BASELINE.json configs[1] (default), [3] dense, [4] long_range")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl", "direct", "pull"], help="multi-GPU combine exchange")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU combine exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global CONFIG, NFRAMES
@@ -384,6 +440,10 @@ def main():
         return float(t.item())
 
     tot_dev, tot_e2e = agg(ev_dev), agg(wall_e2e)
+    parity = None
+    if multi:
+        from gvom_b200.multi import MultiGpuGvom
+        parity = multi_parity_check(MultiGpuGvom, P, slots, world, rank, dev, args.exchange)
     if rank != 0:
         if multi:
             dist.destroy_process_group()
@@ -443,7 +503,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": tot_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(world, slots),
-        "io": {"exchange": (getattr(g, "exchange", None) or "") + (" sharded-finish" if getattr(g, "_sharded", False) and getattr(g, "exchange", "") == "p2p" else ""),
+        "io": {"exchange": (getattr(g, "exchange", None) or "") + (" row-sharded finish" if getattr(g, "_rows", False) and getattr(g, "exchange", "") == "p2p" else "") + (" plane-sharded finish" if getattr(g, "_sharded", False) and getattr(g, "exchange", "") == "p2p" else ""),
                "value": "cloud resident in HBM (float64 Nx3), maps left in HBM in stream order; CUDA events around both calls on the launching stream",
                "e2e": "pinned host float64 Nx3 cloud in, numpy maps out (pinned), per-step wall clock around both calls"},
         "value_p50": world / (statistics.median(ev_dev) * 1e-3),
@@ -493,9 +553,13 @@ def main():
             line["cpu_baseline"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline and CONFIG == "os1_128":
         line["cpu_baseline_cudasim"] = cudasim_baseline()
+    if parity is not None:
+        line["parity_check"] = parity
     print(json.dumps(line), flush=True)
     if multi:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("multi-GPU parity check failed: " + json.dumps(parity))
 
 
 if __name__ == "__main__":
