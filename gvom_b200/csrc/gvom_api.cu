@@ -98,7 +98,7 @@ struct Carver {                    // sub-allocates a workspace block, 256-byte 
 };
 
 enum { EV_START = 0, EV_H2D, EV_POINTS, EV_SCELLS, EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS, EV_D2H,
-       EV_X0, EV_X1, EV_X2, EV_COUNT };   // EV_X*: extra marks inside the multi-GPU combine
+       EV_X0, EV_X1, EV_X2, EV_P0, EV_P1, EV_COUNT };   // EV_X*: extra marks inside the multi-GPU combine
 
 // GVOM_VARIANT bits (environment / gvom_set_variant): A/B switches for measurements; every setting gives the same results
 enum { VAR_GENERIC_MERGE = 2, VAR_ASYNC_ROWS = 4, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128 };
@@ -124,6 +124,9 @@ struct GvomHandle {
     double* maps = nullptr;               // height, inferred, rough_work, xs, ys, guessed  [6][S*S]
     int* imaps = nullptr;                 // result block: pos, neg, vis int32 [3][S*S] then roughness f64 [S*S]
     double* rough_out = nullptr;          // = (double*)(imaps + 3*S*S)
+    // where the 2-D maps of the last combine live: the library's own block above, or (row-sharded multi-GPU combine) the
+    // exchange block the ranks pushed into -- debug exports, OccupancyGrid post-processing and state save read these
+    double* v_maps = nullptr; int* v_imaps = nullptr; double* v_rough = nullptr;
     int* col_minz = nullptr;              // [2][S*S] lowest occupied / lowest free z per column (C1 -> C3)
     unsigned* known = nullptr;            // [2][S*ceil(S/32)] "height known" bit maps (rows over y, rows over x)
     float* debug_dev = nullptr;           // [max(ccap*8, S*S*10)]
@@ -149,7 +152,7 @@ struct GvomHandle {
     cudaEvent_t ev[EV_COUNT];
     bool profiling = false;
     bool zero_copy = true;                // host clouds: S1 reads pinned memory directly (else chunked DMA)
-    bool prof_process = false, prof_combine = false, prof_x = false;
+    bool prof_process = false, prof_combine = false, prof_x = false, prof_partial = false, prof_rows = false;
     int sm_count = 148;
     int grid_codes = 0, grid_cells = 0, grid_cells2 = 0, grid_rows3 = 0, grid_scan_cells = 0, grid_rows_async[2] = {0, 0};   // resident grids (set at create)
     GvomStats stats{};
@@ -210,6 +213,7 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
     // result block: three int32 maps, padding to 8 bytes (odd xy_size), then the float64 roughness map
     h->imaps = d.take<int>(3 * S2 + 2 * S2 + 2);
     h->rough_out = reinterpret_cast<double*>(h->imaps ? h->imaps + ((3 * S2 + 1) & ~size_t(1)) : nullptr);
+    h->v_maps = h->maps; h->v_imaps = h->imaps; h->v_rough = h->rough_out;
     h->col_minz = d.take<int>(2 * S2);
     h->known = d.take<unsigned>(2 * (size_t)p.xy_size * ((p.xy_size + 31) / 32));
     h->debug_dev = d.take<float>(std::max(ccap * 8, S2 * 10));
@@ -328,24 +332,27 @@ void build_sources(GvomHandle* h, const double org[3], bool with_prev, MergeArgs
 }
 
 template <int MODE>
-void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStream_t st) {
-    if (MODE == MERGE_FULL && h->p.xy_size % 256 == 0 && A.use_masks && O.gmask && !(h->variant & VAR_GENERIC_MERGE)) {
+void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStream_t st, int grid_div = 1) {
+    // row-segment kernels: xy_size % 256 == 0, every source carries a group mask, the destination has one
+    if (h->p.xy_size % 256 == 0 && A.use_masks && O.gmask && !(h->variant & VAR_GENERIC_MERGE) &&
+        (MODE != MERGE_FINISH || O.cacc == nullptr)) {
         // the bulk-copy pipeline build of the row merge is opt-in: parity green, but measured slower (gvom_merge.cuh)
-        if (A.n <= 16 && h->grid_rows_async[0] > 0 && (h->variant & VAR_ASYNC_ROWS))
+        if (MODE == MERGE_FULL && A.n <= 16 && h->grid_rows_async[0] > 0 && (h->variant & VAR_ASYNC_ROWS))
             launch(k_merge_rows_async<1>, dim3(h->grid_rows_async[0]), dim3(32), sizeof(MrWarp<1>), st, A, O, h->dp);
-        else if (A.n <= MR_MAX_SRC && h->grid_rows_async[1] > 0 && (h->variant & VAR_ASYNC_ROWS))
+        else if (MODE == MERGE_FULL && A.n <= MR_MAX_SRC && h->grid_rows_async[1] > 0 && (h->variant & VAR_ASYNC_ROWS))
             launch(k_merge_rows_async<2>, dim3(h->grid_rows_async[1]), dim3(32), sizeof(MrWarp<2>), st, A, O, h->dp);
         else
-            launch(k_merge_rows<3>, dim3(h->grid_rows3), dim3(256), 0, st, A, O, h->dp);
+            launch(k_merge_rows<3, MODE>, dim3(std::max(1, h->grid_rows3 / grid_div)), dim3(256), 0, st, A, O, h->dp);
         h->stats.kernel_launches++;
         return;
     }
+    const dim3 g(std::max(1, h->grid_codes / grid_div));
     if (h->p.xy_size % 8 == 0)
-        launch(k_merge_codes<8, MODE>, dim3(h->grid_codes), dim3(256), 0, st, A, O, h->dp);
+        launch(k_merge_codes<8, MODE>, g, dim3(256), 0, st, A, O, h->dp);
     else if (h->p.xy_size % 4 == 0)
-        launch(k_merge_codes<4, MODE>, dim3(h->grid_codes), dim3(256), 0, st, A, O, h->dp);
+        launch(k_merge_codes<4, MODE>, g, dim3(256), 0, st, A, O, h->dp);
     else
-        launch(k_merge_codes<1, MODE>, dim3(h->grid_codes), dim3(256), 0, st, A, O, h->dp);
+        launch(k_merge_codes<1, MODE>, g, dim3(256), 0, st, A, O, h->dp);
     h->stats.kernel_launches++;
 }
 
@@ -384,6 +391,7 @@ int finish_outputs(GvomHandle* h) {
 int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_t* positive, int32_t* negative,
                             double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st) {
     const int S2 = h->S2;
+    h->v_maps = h->maps; h->v_imaps = h->imaps; h->v_rough = h->rough_out;
     double* height = h->maps; double* inferred = h->maps + S2; double* rough = h->rough_out;
     double* xs = h->maps + 3 * (size_t)S2; double* ys = h->maps + 4 * (size_t)S2; double* guessed = h->maps + 5 * (size_t)S2;
     int* pos = h->imaps; int* neg = h->imaps + S2; int* vis = h->imaps + 2 * (size_t)S2;
@@ -426,7 +434,7 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
                                                                                  in_smem, h->col_minz, h->flags + 4,
                                                                                  direct_dev ? kpos : nullptr, direct_dev ? kneg : nullptr,
                                                                                  direct_dev ? kvis : nullptr, direct_dev ? krough : nullptr,
-                                                                                 RowShard{0, 1, h->p.xy_size}, PushSet{});
+                                                                                 RowShard{0, 1, h->p.xy_size}, PushSet{}, GridSignal{});
     }
     h->stats.kernel_launches += 2;
     rec(h, EV_MAPS, st);
@@ -533,7 +541,9 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
                                                                              : resident_grid(k_scan_cells<-1, -1>, 256, h->sm_count);
         if (const char* m = getenv("GVOM_VARIANT")) h->variant = (unsigned)strtoul(m, nullptr, 0);
         if (const char* m = getenv("GVOM_GATHER_BLOCKS")) h->gather_blocks = std::max(1, std::min(8, atoi(m)));
-        h->grid_rows3 = resident_grid(k_merge_rows<3>, 256, h->sm_count);
+        h->grid_rows3 = std::min(resident_grid(k_merge_rows<3, MERGE_FULL>, 256, h->sm_count),
+                                 std::min(resident_grid(k_merge_rows<3, MERGE_PARTIAL>, 256, h->sm_count),
+                                          resident_grid(k_merge_rows<3, MERGE_FINISH>, 256, h->sm_count)));
         h->grid_rows_async[0] = resident_grid(k_merge_rows_async<1>, 32, h->sm_count, sizeof(MrWarp<1>));
         h->grid_rows_async[1] = resident_grid(k_merge_rows_async<2>, 32, h->sm_count, sizeof(MrWarp<2>));
     }
@@ -916,7 +926,7 @@ static int grids_locked(GvomHandle* h, double thr, double minr, double maxr, int
     if (!h->have_maps || !h->comb[h->cur].valid) return GVOM_NO_DATA;
     const int S = h->p.xy_size;
     const size_t S2 = (size_t)h->S2, bytes = GVOM_GRID_COUNT * S2;
-    const int* pos = h->imaps;
+    const int* pos = h->v_imaps;
     signed char* dst = (out_mem == GVOM_DEVICE) ? reinterpret_cast<signed char*>(out) : h->grids_dev;
     bool mapped_out = false;
     if (out_mem == GVOM_HOST && h->zero_copy && !(h->variant & VAR_DMA_OUT)) {   // pinned: the kernel writes through the mapping
@@ -928,7 +938,7 @@ static int grids_locked(GvomHandle* h, double thr, double minr, double maxr, int
         } else cudaGetLastError();
     }
     const int T = (S + 31) / 32;
-    launch(k_occupancy_grids, dim3(T, T), dim3(256), 0, st, pos, pos + S2, pos + 2 * S2, (const double*)h->rough_out, S, thr, minr, maxr, dst);
+    launch(k_occupancy_grids, dim3(T, T), dim3(256), 0, st, pos, pos + S2, pos + 2 * S2, (const double*)h->v_rough, S, thr, minr, maxr, dst);
     h->stats.kernel_launches++;
     CUDA_TRY(cudaGetLastError());
     if (out_mem == GVOM_DEVICE || mapped_out) {
@@ -1010,8 +1020,8 @@ static int debug_height_common(GvomHandle* h, float* out7, float* out3) {
     if (!c.valid || !h->have_maps) return GVOM_NO_DATA;
     const size_t S2 = (size_t)h->S2;
     float* d7 = h->debug_dev; float* d3 = h->debug_dev + 7 * S2;
-    k_debug_height<<<blocks_for(h->S2, 256), 256, 0, h->active>>>(h->maps, h->rough_out, h->maps + 3 * S2, h->maps + 4 * S2,
-                                                                h->maps + 5 * S2, c.origin[0], c.origin[1], h->dp,
+    k_debug_height<<<blocks_for(h->S2, 256), 256, 0, h->active>>>(h->v_maps, h->v_rough, h->v_maps + 3 * S2, h->v_maps + 4 * S2,
+                                                                h->v_maps + 5 * S2, c.origin[0], c.origin[1], h->dp,
                                                                 out7 ? d7 : nullptr, out3 ? d3 : nullptr);
     h->stats.kernel_launches++;
     if (out7) CUDA_TRY(cudaMemcpyAsync(out7, d7, sizeof(float) * 7 * S2, cudaMemcpyDeviceToHost, h->active));
@@ -1088,8 +1098,8 @@ int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_
     if (eig) CUDA_TRY(cudaMemcpy(eig, c.eig, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
     if (maps6) {
         const size_t mb = sizeof(double) * (size_t)h->S2;
-        CUDA_TRY(cudaMemcpy(maps6, h->maps, 6 * mb, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(maps6 + 2 * (size_t)h->S2, h->rough_out, mb, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(maps6, h->v_maps, 6 * mb, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(maps6 + 2 * (size_t)h->S2, h->v_rough, mb, cudaMemcpyDeviceToHost));
     }
     return GVOM_OK;
 }
@@ -1105,7 +1115,7 @@ int gvom_set_profiling(GvomHandle* h, int32_t on) {
     if (!h) return fail(GVOM_EINVAL, "NULL handle");
     std::lock_guard<std::mutex> lock(h->mu);
     h->profiling = on != 0;
-    if (!on) h->prof_process = h->prof_combine = false;
+    if (!on) h->prof_process = h->prof_combine = h->prof_partial = h->prof_rows = false;
     return GVOM_OK;
 }
 
@@ -1125,6 +1135,15 @@ int gvom_stage_times(GvomHandle* h, float ms[16]) {
         CUDA_TRY(cudaEventElapsedTime(&ms[10], h->ev[EV_CODES], h->ev[EV_X0]));
         CUDA_TRY(cudaEventElapsedTime(&ms[11], h->ev[EV_X0], h->ev[EV_X1]));
         CUDA_TRY(cudaEventElapsedTime(&ms[12], h->ev[EV_X1], h->ev[EV_CELLS]));
+    }
+    if (h->prof_partial) CUDA_TRY(cudaEventElapsedTime(&ms[13], h->ev[EV_P0], h->ev[EV_P1]));   // multi-GPU: partial merge + cells
+    if (h->prof_rows) {    // row-sharded finish: [5] wait + own rows, [6] own cells, [7] = [14] columns + [15] wait + surface, [8] wait + deliver
+        CUDA_TRY(cudaEventElapsedTime(&ms[5], h->ev[EV_CSTART], h->ev[EV_CODES]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[6], h->ev[EV_CODES], h->ev[EV_CELLS]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[14], h->ev[EV_CELLS], h->ev[EV_X0]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[15], h->ev[EV_X0], h->ev[EV_X1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[8], h->ev[EV_X1], h->ev[EV_D2H]));
+        ms[7] = ms[14] + ms[15];
     }
     if (h->prof_combine) {
         const int a[4] = {EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS};
@@ -1179,8 +1198,8 @@ void state_sections(GvomHandle* h, const StateHeader& H, F&& visit) {
         visit(c.counter, sizeof(int));
     }
     if (H.have_maps) {
-        visit(h->maps, 6 * S2 * sizeof(double));
-        visit(h->imaps, (3 * S2 + 2 * S2 + 2) * sizeof(int));
+        visit(h->v_maps, 6 * S2 * sizeof(double));
+        visit(h->v_imaps, (3 * S2 + 2 * S2 + 2) * sizeof(int));
     }
 }
 
@@ -1333,6 +1352,7 @@ int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes) {
     if (err != cudaSuccess) return fail(GVOM_ECUDA, std::string("gvom_load_state: ") + cudaGetErrorString(err));
     h->scan_tag = 0;
     h->stage_busy = false;
+    h->v_maps = h->maps; h->v_imaps = h->imaps; h->v_rough = h->rough_out;
     return GVOM_OK;
 }
 
@@ -1386,7 +1406,7 @@ static int combine_partial_impl(GvomHandle* h, const double origin[3], int32_t* 
     if (int e = finish_outputs(h)) return e;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->active = st;
-    rec(h, EV_CSTART, st);
+    rec(h, EV_P0, st);
     MergeArgs A;
     build_sources(h, origin, false, &A);       // a rank without data contributes an empty grid
     CUDA_TRY(cudaMemsetAsync(record_count_dev, 0, sizeof(int), st));
@@ -1394,19 +1414,19 @@ static int combine_partial_impl(GvomHandle* h, const double origin[3], int32_t* 
     O.cmap = code_grid_dev; O.counter = record_count_dev; O.records = records_dev;
     O.gmask = (h->p.xy_size % 8 == 0) ? group_mask_dev : nullptr; O.cap = (int)record_capacity;
     launch_merge<MERGE_PARTIAL>(h, A, O, st);
-    launch(k_partial_cells, dim3(h->grid_cells), dim3(128), 0, st, A, record_count_dev, records_dev, h->dp, (int)record_capacity);
-    h->stats.kernel_launches += 1;
-    if (signal_slots && n_signal > 0) {            // peer-to-peer exchange: tell every rank this one is done
+    GridSignal G{};
+    if (signal_slots && n_signal > 0) {            // peer-to-peer exchange: the last block of the cell kernel tells every rank
         if (n_signal > MAX_RANKS) return fail(GVOM_EINVAL, "too many ranks");
-        SignalSet S; S.n = n_signal;
-        for (int k = 0; k < n_signal; ++k) S.slot[k] = signal_slots[k];
-        if (header)      // {epoch, origin}: the finishing ranks verify that everybody merged in the same frame
-            launch(k_signal_header, dim3(1), dim3(32), 0, st, S, (int)epoch, (int)origin[0], (int)origin[1], (int)origin[2]);
-        else
-            launch(k_signal, dim3(1), dim3(32), 0, st, S, (int)epoch);
-        h->stats.kernel_launches += 1;
+        G.S.n = n_signal;
+        for (int k = 0; k < n_signal; ++k) G.S.slot[k] = signal_slots[k];
+        G.counter = h->flags + 5; G.epoch = epoch;
+        G.header = header ? 1 : 0;                 // {epoch, origin}: the finishing ranks verify that everybody merged in the same frame
+        G.ox = (int)origin[0]; G.oy = (int)origin[1]; G.oz = (int)origin[2];
     }
-    rec(h, EV_CODES, st);
+    launch(k_partial_cells, dim3(h->grid_cells), dim3(128), 0, st, A, record_count_dev, records_dev, h->dp, (int)record_capacity, G);
+    h->stats.kernel_launches += 1;
+    rec(h, EV_P1, st);
+    h->prof_partial = h->profiling;
     CUDA_TRY(cudaGetLastError());
     return GVOM_OK;
 }
@@ -1445,6 +1465,7 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     if (int e = finish_outputs(h)) return e;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->active = st;
+    rec(h, EV_CSTART, st);
     Combined& pc = h->comb[h->cur];
     Combined& c = h->comb[1 - h->cur];
     for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];
@@ -1593,7 +1614,7 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
             if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) O.err_flag = (int*)m + 1; else cudaGetLastError();
             h->counters_host[1] = 0;
             O.row_y0 = R.y0; O.row_n = N;
-            launch(k_merge_codes<8, MERGE_FINISH>, dim3(std::max(1, h->grid_codes / std::max(1, N / 2))), dim3(256), 0, st, A, O, h->dp);
+            launch_merge<MERGE_FINISH>(h, A, O, st, std::max(1, N / 2));
         }
         rec(h, EV_CODES, st);
         {
@@ -1607,14 +1628,16 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
             int* host_count = nullptr;
             void* m = nullptr;
             if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) host_count = (int*)m; else cudaGetLastError();
+            GridSignal G{};
+            G.S.n = N;
+            for (int k = 0; k < N; ++k) G.S.slot[k] = K->heights_slots[k];
+            G.counter = h->flags + 6; G.epoch = epoch;
             launch(k_rows_columns, dim3(blocks_for((int64_t)S * R.nrows + 1, 256)), dim3(256), 0, st, c.index_map, c.minh, h->col_minz,
                    h->col_minz + S2, c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, R, D,
-                   h->flags + 4, c.counter, host_count);
-            SignalSet Sg; Sg.n = N;
-            for (int k = 0; k < N; ++k) Sg.slot[k] = K->heights_slots[k];
-            launch(k_signal, dim3(1), dim3(32), 0, st, Sg, (int)epoch);
+                   h->flags + 4, c.counter, host_count, G);
         }
-        h->stats.kernel_launches += 4;
+        rec(h, EV_X0, st);
+        h->stats.kernel_launches += 3;
         h->prof_combine = false;
         CUDA_TRY(cudaGetLastError());
     }
@@ -1622,53 +1645,59 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
         launch(k_rows_known, dim3(W, W), dim3(1024), 0, st, (const double*)maps, h->dp, known, knownT, K->heights_flags, N, (int)epoch);
         const size_t mask_bytes = 2 * (size_t)S * W * sizeof(unsigned);
         const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
-        launch(k_surface_maps2, dim3(blocks_for((int64_t)S * R.nrows, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit,
+        GridSignal G{};
+        G.S.n = N;
+        for (int k = 0; k < N; ++k) G.S.slot[k] = K->results_slots[k];
+        G.counter = h->flags + 7; G.epoch = epoch;
+        launch(k_surface_maps2, dim3(std::max(1, blocks_for((int64_t)S * R.nrows, 128))), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit,
                c.total, (const double*)maps, (const double*)(maps + S2), known, knownT, c.origin[2], h->dp, rough, maps + 3 * S2,
                maps + 4 * S2, maps + 5 * S2, imaps, imaps + S2, imaps + 2 * S2, in_smem, h->col_minz, h->flags + 4,
-               (int*)nullptr, (int*)nullptr, (int*)nullptr, (double*)nullptr, R, D);
-        SignalSet Sg; Sg.n = N;
-        for (int k = 0; k < N; ++k) Sg.slot[k] = K->results_slots[k];
-        launch(k_signal, dim3(1), dim3(32), 0, st, Sg, (int)epoch);
-        h->stats.kernel_launches += 3;
+               (int*)nullptr, (int*)nullptr, (int*)nullptr, (double*)nullptr, R, D, G);
+        h->stats.kernel_launches += 2;
+        rec(h, EV_X1, st);
         CUDA_TRY(cudaGetLastError());
     }
     if (phases & 4) {
-        launch(k_wait_flags, dim3(1), dim3(32), 0, st, K->results_flags, N, (int)epoch);
+        // wait for every rank's pushes, then transpose the exchange block ([y][x]) into the library's own 2-D block and the
+        // caller's buffers ([x][y]); device and pinned host buffers are written by the kernel itself
+        MapSet own{h->maps, h->imaps, h->imaps + S2, h->imaps + 2 * S2, h->rough_out};
+        MapSet user{nullptr, nullptr, nullptr, nullptr, nullptr};
+        bool direct = false;
+        if (out_mem == GVOM_DEVICE && positive && negative && roughness && visibility) {
+            user = MapSet{nullptr, positive, negative, visibility, roughness};
+            direct = true;
+        } else if (out_mem == GVOM_HOST && positive && negative && roughness && visibility && h->zero_copy) {
+            void* mp[4] = {nullptr, nullptr, nullptr, nullptr};
+            void* hp[4] = {positive, negative, visibility, roughness};
+            bool ok = true, dev = false;
+            for (int k = 0; k < 4 && ok; ++k) {
+                ok = is_pinned_or_device(hp[k], &dev) && !dev && cudaHostGetDevicePointer(&mp[k], hp[k], 0) == cudaSuccess && mp[k];
+                if (!ok) cudaGetLastError();
+            }
+            if (ok) { user = MapSet{nullptr, (int*)mp[0], (int*)mp[1], (int*)mp[2], (double*)mp[3]}; direct = true; }
+        }
+        launch(k_rows_deliver, dim3(W, W, 10), dim3(256), 0, st, (const char*)mine, D, S, own, user, K->results_flags, N, (int)epoch);
         h->stats.kernel_launches += 1;
         rec(h, EV_MAPS, st);
+        CUDA_TRY(cudaGetLastError());
         const size_t bi = S2 * sizeof(int), bd = S2 * sizeof(double);
         const size_t rough_off = ((3 * S2 + 1) & ~size_t(1)) * sizeof(int);
         GvomHandle::Pending& pd = h->pend;
         pd = GvomHandle::Pending{};
         pd.active = true; pd.c = &c; pd.st = st;
-        if (out_mem == GVOM_DEVICE) {
-            if (positive) CUDA_TRY(cudaMemcpyAsync(positive, imaps, bi, cudaMemcpyDeviceToDevice, st));
-            if (negative) CUDA_TRY(cudaMemcpyAsync(negative, imaps + S2, bi, cudaMemcpyDeviceToDevice, st));
-            if (visibility) CUDA_TRY(cudaMemcpyAsync(visibility, imaps + 2 * S2, bi, cudaMemcpyDeviceToDevice, st));
-            if (roughness) CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToDevice, st));
-        } else if (out_mem == GVOM_HOST) {
-            bool dev = false;
-            const bool pinned = positive && negative && visibility && roughness && is_pinned_or_device(positive, &dev) &&
-                                is_pinned_or_device(negative, &dev) && is_pinned_or_device(visibility, &dev) &&
-                                is_pinned_or_device(roughness, &dev);
-            if (pinned && negative == positive + S2 && visibility == negative + S2 &&
-                reinterpret_cast<char*>(roughness) == reinterpret_cast<char*>(positive) + rough_off) {
-                CUDA_TRY(cudaMemcpyAsync(positive, imaps, rough_off + bd, cudaMemcpyDeviceToHost, st));
-            } else if (pinned) {
-                CUDA_TRY(cudaMemcpyAsync(positive, imaps, bi, cudaMemcpyDeviceToHost, st));
-                CUDA_TRY(cudaMemcpyAsync(negative, imaps + S2, bi, cudaMemcpyDeviceToHost, st));
-                CUDA_TRY(cudaMemcpyAsync(visibility, imaps + 2 * S2, bi, cudaMemcpyDeviceToHost, st));
-                CUDA_TRY(cudaMemcpyAsync(roughness, rough, bd, cudaMemcpyDeviceToHost, st));
-            } else {
-                CUDA_TRY(cudaMemcpyAsync(h->out_i_host, imaps, rough_off + bd, cudaMemcpyDeviceToHost, st));
-                pd.from_mirror = true;
-                pd.positive = positive; pd.negative = negative; pd.visibility = visibility; pd.roughness = roughness;
-            }
+        if (!direct && out_mem == GVOM_DEVICE) {
+            if (positive) CUDA_TRY(cudaMemcpyAsync(positive, h->imaps, bi, cudaMemcpyDeviceToDevice, st));
+            if (negative) CUDA_TRY(cudaMemcpyAsync(negative, h->imaps + S2, bi, cudaMemcpyDeviceToDevice, st));
+            if (visibility) CUDA_TRY(cudaMemcpyAsync(visibility, h->imaps + 2 * S2, bi, cudaMemcpyDeviceToDevice, st));
+            if (roughness) CUDA_TRY(cudaMemcpyAsync(roughness, h->rough_out, bd, cudaMemcpyDeviceToDevice, st));
+        } else if (!direct && out_mem == GVOM_HOST) {       // pageable: one DMA into the pinned mirror, memcpy when it has landed
+            CUDA_TRY(cudaMemcpyAsync(h->out_i_host, h->imaps, rough_off + bd, cudaMemcpyDeviceToHost, st));
+            pd.from_mirror = true;
+            pd.positive = positive; pd.negative = negative; pd.visibility = visibility; pd.roughness = roughness;
         }
-        // the library's own 2-D block (debug exports, OccupancyGrid post-processing, state save) follows
-        CUDA_TRY(cudaMemcpyAsync(h->maps, maps, 6 * bd, cudaMemcpyDeviceToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(h->imaps, imaps, rough_off + bd, cudaMemcpyDeviceToDevice, st));
+        h->v_maps = h->maps; h->v_imaps = h->imaps; h->v_rough = h->rough_out;
         rec(h, EV_D2H, st);
+        h->prof_rows = h->profiling && phases == 7;
         h->have_maps = true;
         if (origin_out) {
             origin_out[0] = c.origin[0] * h->p.xy_resolution;
@@ -1712,6 +1741,7 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     if (int e = finish_outputs(h)) return e;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->active = st;
+    rec(h, EV_CSTART, st);
     Combined& pc = h->comb[h->cur];
     Combined& c = h->comb[1 - h->cur];
     for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];

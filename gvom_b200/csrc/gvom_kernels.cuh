@@ -44,6 +44,34 @@ __device__ __forceinline__ void wait_flags_block(const int* flags, int n, int ep
     }
 }
 
+
+constexpr int MAX_RANKS = 16;
+struct SignalSet { int* slot[MAX_RANKS]; int n; };   // one flag slot per rank (this rank's slot in every rank's memory)
+
+// "The whole grid is done" signal folded into the producing kernel (saves a launch per barrier): every block makes its
+// writes visible system-wide and counts itself in; the last one publishes the epoch into every rank's slot (header
+// slots: the origin first) and resets the counter for the next launch.  Every thread of the block must call it.
+struct GridSignal { SignalSet S; int* counter; int epoch; int header; int ox, oy, oz; };
+__device__ __forceinline__ void signal_when_grid_done(const GridSignal& G) {
+    if (G.S.n == 0) return;
+    __syncthreads();                                      // the block's writes happen before thread 0's fence (cumulativity)
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(G.counter, 1) == nblocks - 1) {
+            *G.counter = 0;
+            __threadfence();
+            for (int k = 0; k < G.S.n; ++k) {
+                volatile int* f = G.S.slot[k];
+                if (G.header) { f[1] = G.ox; f[2] = G.oy; f[3] = G.oz; }
+            }
+            __threadfence_system();
+            for (int k = 0; k < G.S.n; ++k) { volatile int* f = G.S.slot[k]; f[0] = G.epoch; }
+            __threadfence_system();
+        }
+    }
+}
+
 constexpr int MAX_SLOTS = 64;   // ring-buffer slots a single merge pass can take
 constexpr int ACC = 20;         // per-cell accumulators: [0..9] own voxel, [10..19] apron
 
@@ -488,17 +516,36 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
 //     buffer's own group mask says it already holds "unknown" there (both combined-map buffers start as all
 //     unknown with an empty mask, and every writer keeps map and mask consistent).
 // ---------------------------------------------------------------------------
-template <int NB>
+// MODE as in k_merge_codes: MERGE_FULL (single-GPU combine), MERGE_PARTIAL (a rank's own slots -> encoded grid + record
+// ids; "unknown" is 0 there) and MERGE_FINISH (every rank's encoded grid + previous map -> combined map; optionally only
+// the rows this rank owns, O.row_n > 1; waits for the peers' partial results itself).
+template <int NB, int MODE>
 __global__ void __launch_bounds__(256, (NB > 3) ? 2 : 3)
 k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
     pdl_wait();
+    if (MODE == MERGE_FINISH && O.wait_flags) {           // device-side barrier of the peer-to-peer exchange (see k_merge_codes)
+        if (threadIdx.x == 0) {
+            const int stride = O.wait_stride > 0 ? O.wait_stride : 1;
+            for (int k = 0; k < O.wait_n; ++k) {
+                const volatile int* f = O.wait_flags + k * stride;
+                while (*f < O.wait_epoch) __nanosleep(100);
+                if (stride == 4 && blockIdx.x == 0 && O.err_flag && f[1] != 0x7fffffff &&
+                    (f[1] != O.org[0] || f[2] != O.org[1] || f[3] != O.org[2])) *O.err_flag = 1;
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int S = P.S, Z = P.Z;
     const int spr = S >> 8;                               // segments per row
-    const int nseg = (int)(P.V >> 8);
+    const bool rslab = MODE == MERGE_FINISH && O.row_n > 1;
+    const int my_rows = rslab ? (O.row_y0 < S ? (S - O.row_y0 + O.row_n - 1) / O.row_n : 0) : S;
+    const int nseg = rslab ? Z * my_rows * spr : (int)(P.V >> 8);
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    const int has_prev = (A.n > 0 && A.s[A.n - 1].is_prev) ? 1 : 0;
+    const int has_prev = (MODE != MERGE_PARTIAL && A.n > 0 && A.s[A.n - 1].is_prev) ? 1 : 0;
+    constexpr int UNK = MODE == MERGE_PARTIAL ? 0 : -1;   // what "unknown" looks like in the destination
     // group-mask words of sources kb..kb+15 for segment sg: lanes 0-15 word 0, lanes 16-31 word 1
     auto mask_words = [&](int sg, int kb) -> unsigned {
         const int row = sg / spr;
@@ -516,14 +563,20 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
         }
         return word;
     };
-    for (int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += warps) {
+    for (int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sl < nseg; sl += warps) {
+        int seg = sl;
+        if (rslab) {                                      // local segment counter -> (z, own row, x segment)
+            const int jr = sl / spr, xsg = sl - jr * spr;
+            const int zz = jr / my_rows, yi = jr - zz * my_rows;
+            seg = (zz * S + (O.row_y0 + O.row_n * yi)) * spr + xsg;
+        }
         const int row = seg / spr;                        // y + z*S
         const int x0s = (seg - row * spr) << 8;
         const int z = row / S, y = row - z * S;
         const unsigned old_word = O.gmask[seg];           // what the destination buffer holds here now
-        int acc_and[8], sum[8], op[8];
+        int acc_and[8], sum[8], op[8], enc_or[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc_and[j] = -1; sum[j] = 0; op[j] = -1; }
+        for (int j = 0; j < 8; ++j) { acc_and[j] = -1; sum[j] = 0; op[j] = -1; enc_or[j] = 0; }
         unsigned seen = 0;                                // any source knows anything in this segment (uniform)
         for (int kb = 0; kb < A.n; kb += 16) {
             const unsigned word = mask_words(seg, kb);
@@ -555,9 +608,10 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
                 int o[NB][8];
 #pragma unroll
                 for (int u = 0; u < NB; ++u) {
+                    const bool enc = MODE == MERGE_FINISH && !(has_prev && k0 + u == A.n - 1);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[u][j] = -1;
-                    if (need & (1u << u)) load_codes<8>(rowp[u], xs[u], S, o[u]);
+                    for (int j = 0; j < 8; ++j) o[u][j] = enc ? 0 : -1;   // "unknown": folds to nothing
+                    if (need & (1u << u)) load_codes<8>(rowp[u], xs[u], S, o[u]);   // (encoded grids are unshifted: never out of range)
                 }
 #pragma unroll
                 for (int u = 0; u < NB; ++u) {
@@ -565,6 +619,9 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
                     if (has_prev && k0 + u == A.n - 1) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) op[j] = o[u][j];
+                    } else if (MODE == MERGE_FINISH) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { enc_or[j] |= o[u][j]; sum[j] += o[u][j] < OCC_FLAG ? o[u][j] : 0; }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { acc_and[j] &= o[u][j]; sum[j] += max(~o[u][j], 0); }
@@ -575,7 +632,7 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
         if (seen == 0) {                                  // uniform: nothing known anywhere in the segment
             if (old_word != 0) {
                 int4* dst = reinterpret_cast<int4*>(O.cmap) + (long long)seg * 64 + lane * 2;
-                dst[0] = make_int4(-1, -1, -1, -1); dst[1] = make_int4(-1, -1, -1, -1);
+                dst[0] = make_int4(UNK, UNK, UNK, UNK); dst[1] = make_int4(UNK, UNK, UNK, UNK);
                 if (lane == 0) O.gmask[seg] = 0u;
             }
             continue;
@@ -584,7 +641,7 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
         int c[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            occ[j] = acc_and[j] >= 0;
+            occ[j] = (acc_and[j] >= 0) || (enc_or[j] >= OCC_FLAG);
             c[j] = -1 - sum[j];
             if (!occ[j]) {                                // previous combined map (gvom.py:1058-1063)
                 if (op[j] >= 0) { if (c[j] >= -11) occ[j] = true; }
@@ -606,24 +663,40 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
         }
         bool known_any = false;
         const int x = x0s + 8 * lane;
-        if (!my_occ && !any_free) {
+        if (MODE == MERGE_PARTIAL) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int rid = OCC_FLAG - 1;                    // "occupied, record dropped" (capacity overflow)
+                if (occ[j]) {
+                    const int id = base + __popc(m[j] & lt);
+                    if (id < O.cap) { O.records[(long long)id * REC] = __int_as_float(seg * 256 + lane * 8 + j); rid = id; }
+                }
+                base += __popc(m[j]);
+                // occupied: flag | record id (lets a finishing rank fetch the record without a search)
+                c[j] = occ[j] ? (OCC_FLAG | rid) : min(sum[j], OCC_FLAG - 1);
+                known_any |= c[j] != 0;
+            }
+        } else if (!my_occ && !any_free) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) c[j] = -1;
         } else {
+            const bool cols = O.col_occ != nullptr;
             int* colo = O.col_occ + y * S + x;
             int* colf = O.col_free + y * S + x;
             int cur_occ[8], cur_free[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { cur_occ[j] = 0x7fffffff; cur_free[j] = 0x7fffffff; }
+            for (int j = 0; j < 8; ++j) { cur_occ[j] = cols ? 0x7fffffff : -1; cur_free[j] = cols ? 0x7fffffff : -1; }
+            if (cols) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                if (my_occ) {
-                    const int4 a = *(reinterpret_cast<const int4*>(colo) + g);
-                    cur_occ[4 * g] = a.x; cur_occ[4 * g + 1] = a.y; cur_occ[4 * g + 2] = a.z; cur_occ[4 * g + 3] = a.w;
-                }
-                if (any_free) {
-                    const int4 b = *(reinterpret_cast<const int4*>(colf) + g);
-                    cur_free[4 * g] = b.x; cur_free[4 * g + 1] = b.y; cur_free[4 * g + 2] = b.z; cur_free[4 * g + 3] = b.w;
+                for (int g = 0; g < 2; ++g) {
+                    if (my_occ) {
+                        const int4 a = *(reinterpret_cast<const int4*>(colo) + g);
+                        cur_occ[4 * g] = a.x; cur_occ[4 * g + 1] = a.y; cur_occ[4 * g + 2] = a.z; cur_occ[4 * g + 3] = a.w;
+                    }
+                    if (any_free) {
+                        const int4 b = *(reinterpret_cast<const int4*>(colf) + g);
+                        cur_free[4 * g] = b.x; cur_free[4 * g + 1] = b.y; cur_free[4 * g + 2] = b.z; cur_free[4 * g + 3] = b.w;
+                    }
                 }
             }
 #pragma unroll
@@ -868,8 +941,8 @@ __device__ __forceinline__ unsigned row_window(const unsigned* __restrict__ row,
 //     start on their height loads at once.
 //   * optional second output set (pos2 ...): device-resident caller buffers are written by the kernel itself.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4)
-k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, const int* __restrict__ ctot,
+__device__ __forceinline__ void
+surface_maps_body(const int* __restrict__ cmap, const int* __restrict__ chit, const int* __restrict__ ctot,
                 const double* __restrict__ height, const double* __restrict__ inferred,
                 const unsigned* __restrict__ known_g, const unsigned* __restrict__ knownT_g, double o2,
                 DevParams P, double* __restrict__ rough, double* __restrict__ xs, double* __restrict__ ys,
@@ -877,7 +950,6 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
                 int masks_in_smem, int* __restrict__ col_minz, int* __restrict__ scratch_count,
                 int* __restrict__ pos2, int* __restrict__ neg2, int* __restrict__ vis2, double* __restrict__ rough2,
                 RowShard R, PushSet D) {
-    pdl_wait();
     extern __shared__ unsigned smask[];
     const int S = P.S, Z = P.Z;
     const int W = (S + 31) >> 5;
@@ -885,6 +957,10 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
     const int t = blockIdx.x * 128 + (threadIdx.x & 127);
     const int ncell = S * R.nrows;                        // cells this launch owns (all of them on a single GPU)
     const long long S2 = (long long)S * S;
+    // 2-D maps are [x][y] like the reference's outputs; in the row-sharded multi-GPU combine (D.n > 0) the exchange block
+    // is [y][x] and threads run along x, so that the rows a rank owns are contiguous and the pushes coalesce
+    const bool TR = D.n > 0;
+#define HMX(a, x, y) (a)[TR ? (long long)(y) * S + (x) : (long long)(x) * S + (y)]
     if (role == 1) {
         const unsigned* known = known_g;
         const unsigned* knownT = knownT_g;
@@ -899,13 +975,13 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
             knownT = smask + S * W;
         }
         if (t >= ncell) return;
-        const int y0 = R.y0 + R.n * (t % R.nrows), x0 = t / R.nrows;
+        const int y0 = TR ? R.y0 + R.n * (t / S) : t % S, x0 = TR ? t % S : t / S;
         // housekeeping for the next combine: C1's column minima and running counter start clean
         col_minz[y0 * S + x0] = 0x7f7f7f7f;
         col_minz[S2 + y0 * S + x0] = 0x7f7f7f7f;
         if (t == 0) *scratch_count = 0;
-        const double h0 = GVOM_HM(height, x0, y0);
-        const double inf0 = GVOM_HM(inferred, x0, y0);
+        const double h0 = HMX(height, x0, y0);
+        const double inf0 = HMX(inferred, x0, y0);
         double dh_out = 0.0;
         if (!(h0 > -1000.0) && inf0 != -1000.0) {
             // ---- guessed height delta (gvom.py:592-713), quirks kept (see oracle/gvom_oracle.c)
@@ -946,10 +1022,10 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
                 }
             }
             double x_ph = -1000.0, x_nh = -1000.0, y_ph = -1000.0, y_nh = -1000.0;
-            if (fxp >= 0) x_ph = GVOM_HM(height, x0 + ixp, fxp);
-            if (fxn >= 0) x_nh = GVOM_HM(height, x0 - ixn, fxn);
-            if (fyp >= 0) y_ph = GVOM_HM(height, fyp, y0 + iyp);
-            if (fyn >= 0) y_nh = GVOM_HM(height, fyn, y0 - iyn);
+            if (fxp >= 0) x_ph = HMX(height, x0 + ixp, fxp);
+            if (fxn >= 0) x_nh = HMX(height, x0 - ixn, fxn);
+            if (fyp >= 0) y_ph = HMX(height, fyp, y0 + iyp);
+            if (fyn >= 0) y_nh = HMX(height, fyn, y0 - iyn);
             double mn = 1000.0, mx = inf0;
             if (x_ph > -1000.0) { mn = fmin(x_ph, mn); mx = fmax(x_ph, mx); }
             if (x_nh > -1000.0) { mn = fmin(x_nh, mn); mx = fmax(x_nh, mx); }
@@ -959,12 +1035,12 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
             if (dh > 0.0) dh_out = dh;
         }
         const int nv = dh_out > P.neg_thr ? 100 : 0, vv = h0 > -1000.0 ? 1 : 0;
-        GVOM_HM(guessed, x0, y0) = dh_out;
-        GVOM_HM(neg, x0, y0) = nv;
-        GVOM_HM(vis, x0, y0) = vv;
-        if (neg2) { GVOM_HM(neg2, x0, y0) = nv; GVOM_HM(vis2, x0, y0) = vv; }
+        HMX(guessed, x0, y0) = dh_out;
+        HMX(neg, x0, y0) = nv;
+        HMX(vis, x0, y0) = vv;
+        if (neg2) { HMX(neg2, x0, y0) = nv; HMX(vis2, x0, y0) = vv; }
         if (D.n) {
-            const long long ci = (long long)x0 * S + y0;
+            const long long ci = (long long)y0 * S + x0;
             push_value<double>(D, D.off_maps + 5 * S2 * 8, ci, dh_out);
             push_value<int>(D, D.off_neg, ci, nv);
             push_value<int>(D, D.off_vis, ci, vv);
@@ -972,7 +1048,7 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
         return;
     }
     if (t >= ncell) return;
-    const int y0 = R.y0 + R.n * (t % R.nrows), x0 = t / R.nrows;
+    const int y0 = TR ? R.y0 + R.n * (t / S) : t % S, x0 = TR ? t % S : t / S;
 
     // ---- slope + roughness (gvom.py:717-805); contraction pattern = SASS of the reference.
     double hz[9];
@@ -983,7 +1059,7 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
         for (int b = 0; b < 3; ++b) {
             const int x = x0 - 1 + a, y = y0 - 1 + b;
             double h = -1000.0;
-            if (x >= 0 && x < S && y >= 0 && y < S) h = GVOM_HM(height, x, y);
+            if (x >= 0 && x < S && y >= 0 && y < S) h = HMX(height, x, y);
             hz[a * 3 + b] = h;
             if (h > -1000.0) okm |= 1u << (a * 3 + b);
         }
@@ -1034,10 +1110,10 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
             syv = atan2(a1, im);
         }
     }
-    GVOM_HM(rough, x0, y0) = rg;
-    if (rough2) GVOM_HM(rough2, x0, y0) = rg;
-    GVOM_HM(xs, x0, y0) = sxv;
-    GVOM_HM(ys, x0, y0) = syv;
+    HMX(rough, x0, y0) = rg;
+    if (rough2) HMX(rough2, x0, y0) = rg;
+    HMX(xs, x0, y0) = sxv;
+    HMX(ys, x0, y0) = syv;
 
     // ---- positive obstacles (gvom.py:515-555)
     int pv = 0;
@@ -1067,15 +1143,31 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
             }
         }
     }
-    GVOM_HM(pos, x0, y0) = pv;
-    if (pos2) GVOM_HM(pos2, x0, y0) = pv;
+    HMX(pos, x0, y0) = pv;
+    if (pos2) HMX(pos2, x0, y0) = pv;
     if (D.n) {
-        const long long ci = (long long)x0 * S + y0;
+        const long long ci = (long long)y0 * S + x0;
         push_value<double>(D, D.off_rough, ci, rg);
         push_value<double>(D, D.off_maps + 3 * S2 * 8, ci, sxv);
         push_value<double>(D, D.off_maps + 4 * S2 * 8, ci, syv);
         push_value<int>(D, D.off_pos, ci, pv);
     }
+}
+#undef HMX
+
+__global__ void __launch_bounds__(256, 4)
+k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, const int* __restrict__ ctot,
+                const double* __restrict__ height, const double* __restrict__ inferred,
+                const unsigned* __restrict__ known_g, const unsigned* __restrict__ knownT_g, double o2,
+                DevParams P, double* __restrict__ rough, double* __restrict__ xs, double* __restrict__ ys,
+                double* __restrict__ guessed, int* __restrict__ pos, int* __restrict__ neg, int* __restrict__ vis,
+                int masks_in_smem, int* __restrict__ col_minz, int* __restrict__ scratch_count,
+                int* __restrict__ pos2, int* __restrict__ neg2, int* __restrict__ vis2, double* __restrict__ rough2,
+                RowShard R, PushSet D, GridSignal G) {
+    pdl_wait();
+    surface_maps_body(cmap, chit, ctot, height, inferred, known_g, knownT_g, o2, P, rough, xs, ys, guessed, pos, neg, vis,
+                      masks_in_smem, col_minz, scratch_count, pos2, neg2, vis2, rough2, R, D);
+    signal_when_grid_done(G);                             // row-sharded combine: this rank's maps are in every rank's block
 }
 
 // ---------------------------------------------------------------------------
@@ -1088,7 +1180,7 @@ __global__ void __launch_bounds__(256)
 k_rows_columns(const int* __restrict__ cmap, const float* __restrict__ cminh, const int* __restrict__ col_occ,
                const int* __restrict__ col_free, double o0, double o1, double o2, double e0, double e1, double e2,
                DevParams P, RowShard R, PushSet D, const int* __restrict__ scratch_count, int* __restrict__ map_count,
-               int* __restrict__ host_count) {
+               int* __restrict__ host_count, GridSignal G) {
     pdl_wait();
     const int S = P.S;
     const long long S2 = (long long)S * S;
@@ -1098,7 +1190,7 @@ k_rows_columns(const int* __restrict__ cmap, const float* __restrict__ cminh, co
         *map_count = n;
         if (host_count) *host_count = n;
     }
-    if (t >= S * R.nrows) return;
+    if (t < S * R.nrows) {
     const int x = t % S, y = R.y0 + R.n * (t / S);        // x fastest: the column minima are [y][x]
     double h = -1000.0, inf = -1000.0;
     const double xp = __fma_rn(__dadd_rn(o0, (double)x), P.xy_res, -e0);
@@ -1110,11 +1202,13 @@ k_rows_columns(const int* __restrict__ cmap, const float* __restrict__ cminh, co
         h = __dmul_rn(__dadd_rn(__dadd_rn((double)zo, (double)cminh[idx]), o2), P.z_res);
     }
     if (zf < P.Z) inf = __dmul_rn(__dadd_rn(o2, (double)zf), P.z_res);
-    const long long ci = (long long)x * S + y;
+    const long long ci = (long long)y * S + x;             // the exchange block is [y][x]: a rank's rows are contiguous
     for (int d = 0; d < D.n; ++d) {                        // own copy included
         double* m = reinterpret_cast<double*>(D.base[d] + D.off_maps);
         m[ci] = h; m[S2 + ci] = inf;
     }
+    }
+    signal_when_grid_done(G);                             // heights of this rank's columns are in every rank's block
 }
 
 __global__ void __launch_bounds__(1024)
@@ -1128,7 +1222,7 @@ k_rows_known(const double* __restrict__ height, DevParams P, unsigned* __restric
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 32 + ty;
     bool kn = false;
-    if (x < S && y < S) kn = __ldcg(height + (long long)x * S + y) > -1000.0;
+    if (x < S && y < S) kn = __ldcg(height + (long long)y * S + x) > -1000.0;      // exchange block: [y][x]
     flag[ty][tx] = kn ? 1 : 0;
     const unsigned wT = __ballot_sync(FULL, kn);          // bits over x for row y
     if (tx == 0 && y < S) knownT[(long long)y * W + blockIdx.x] = wT;
@@ -1142,10 +1236,50 @@ k_rows_known(const double* __restrict__ height, DevParams P, unsigned* __restric
     }
 }
 
-// waits (device side) until all ranks' flags have reached the epoch; ordered before the copies that follow it
-__global__ void k_wait_flags(const int* __restrict__ flags, int n, int epoch) {
+// Delivery of a row-sharded combine: waits (device side) until every rank has pushed the maps of its rows, then
+// transposes the exchange block ([y][x]) into the library's own 2-D block and, if given, the caller's buffers
+// (device memory or mapped pinned host memory), which are [x][y] like the reference's outputs.
+struct MapSet { double* maps6; int* pos; int* neg; int* vis; double* rough; };
+__global__ void __launch_bounds__(256)
+k_rows_deliver(const char* __restrict__ blk, PushSet D, int S, MapSet own, MapSet user,
+               const int* __restrict__ wait_flags, int wait_n, int wait_epoch) {
     pdl_wait();
-    wait_flags_block(flags, n, epoch);
+    wait_flags_block(wait_flags, wait_n, wait_epoch);
+    __shared__ double td[32][33];
+    __shared__ int ti[32][33];
+    const long long S2 = (long long)S * S;
+    const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int m = blockIdx.z;                              // 0..5: float64 maps of maps6, 6: roughness, 7..9: pos / neg / vis
+    const bool is_d = m < 7;
+    const double* sd = m < 6 ? reinterpret_cast<const double*>(blk + D.off_maps) + m * S2 : reinterpret_cast<const double*>(blk + D.off_rough);
+    const int* si = reinterpret_cast<const int*>(blk + (m == 7 ? D.off_pos : m == 8 ? D.off_neg : D.off_vis));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                          // read along x (the block's fast axis)
+        const int yl = ty0 + 8 * r, y = by + yl, x = bx + tx;
+        if (x < S && y < S) {
+            if (is_d) td[yl][tx] = __ldcg(sd + (long long)y * S + x); else ti[yl][tx] = __ldcg(si + (long long)y * S + x);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                          // write along y (the outputs' fast axis)
+        const int xl = ty0 + 8 * r, x = bx + xl, y = by + tx;
+        if (x < S && y < S) {
+            const long long o = (long long)x * S + y;
+            if (is_d) {
+                const double v = td[tx][xl];
+                if (m < 6) own.maps6[m * S2 + o] = v;
+                else { own.rough[o] = v; if (user.rough) user.rough[o] = v; }
+            } else {
+                const int v = ti[tx][xl];
+                int* a = m == 7 ? own.pos : m == 8 ? own.neg : own.vis;
+                int* u = m == 7 ? user.pos : m == 8 ? user.neg : user.vis;
+                a[o] = v;
+                if (u) u[o] = v;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1264,13 +1398,11 @@ __global__ void k_debug_height(const double* __restrict__ height, const double* 
 // single Gvom holding all ranks' slots; moments are reduced commutatively (raw
 // sums in float64 atomics) and agree to float32 rounding.
 // ===========================================================================
-constexpr int MAX_RANKS = 16;
 
 // Per-rank exchange buffers as the finishing rank sees them.  With the NCCL exchange these
 // point into local (all-reduced / all-gathered) memory; with the peer-to-peer exchange they are
 // the OTHER GPUs' buffers mapped over NVLink, read directly by the kernels below.
 struct RecordSet { const float* r[MAX_RANKS]; const int* count[MAX_RANKS]; int n; };
-struct SignalSet { int* slot[MAX_RANKS]; int n; };
 
 // header variant: {epoch, ox, oy, oz} -- the origin first, then (after a fence) the epoch the waiters poll
 __global__ void k_signal_header(SignalSet S, int epoch, int ox, int oy, int oz) {
@@ -1298,7 +1430,7 @@ __global__ void k_signal(SignalSet S, int epoch) {
 
 // per record: fold this rank's slots (reference order, float32 rounding as in C2)
 __global__ void __launch_bounds__(128)
-k_partial_cells(MergeArgs A, const int* __restrict__ counter, float* __restrict__ records, DevParams P, int cap) {
+k_partial_cells(MergeArgs A, const int* __restrict__ counter, float* __restrict__ records, DevParams P, int cap, GridSignal G) {
     pdl_wait();
     const int count = min(*counter, cap);
     const int S = P.S, Z = P.Z;
@@ -1329,6 +1461,7 @@ k_partial_cells(MergeArgs A, const int* __restrict__ counter, float* __restrict_
         for (int k = 0; k < 10; ++k) r[4 + k] = c[k];
         r[14] = 0.f; r[15] = 0.f;
     }
+    signal_when_grid_done(G);                             // partial results complete: tell every rank
 }
 
 // scatter every rank's records into the cells: raw moments n, n*mu, n*(C + mu mu^T) in float64

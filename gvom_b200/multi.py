@@ -36,7 +36,7 @@ import time
 
 import numpy as np
 
-from ._lib import GVOM_DEVICE, GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, GvomRowsLinks, check
+from ._lib import GVOM_DEVICE, GVOM_HOST, GVOM_NO_DATA, GVOM_NONE, RECORD_FLOATS, GvomRowsLinks, check
 from .gvom import Gvom
 
 HEADER_DOUBLES = 8          # [valid, count, ox, oy, oz, pad...]
@@ -267,14 +267,15 @@ class MultiGpuGvom(Gvom):
                     return None
                 for k in range(3):
                     self._org_in[k] = float(origin[k])
-            outs, optr, mem = self._outputs(device_outputs)
             if self._rows:
                 # own world rows: merge + cells + columns; heights and finished maps are pushed to every rank
+                outs, optr, mem = self._outputs(device_outputs)
                 check(L.gvom_combine_finish_rows(self._h, self._org_in, C.byref(X["links"]), epoch, 7, self._org_c,
                                                  optr[0], optr[1], optr[2], optr[3], mem, self._stream),
                       "gvom_combine_finish_rows")
                 pos, neg, rough, vis = outs
                 return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
+            outs, optr, mem = self._outputs(device_outputs)
             if self._sharded:
                 # every rank finishes 1/world of the planes, publishes them, and assembles the full map from all ranks
                 check(L.gvom_combine_finish_sharded(self._h, self._org_in, self.rank, self.world, X["grids"], X["masks"],

@@ -57,8 +57,8 @@ def local_exchange(ranks, reduced=False):
     o = (C.c_double * 3)(*origin)
     cap = int(min(V, g0.buffer_size * g0.max_points))
     for g in ranks:
-        grid = torch.empty(V, dtype=torch.int32, device=dev)
-        msk = torch.empty(V // 256 + 2, dtype=torch.int32, device=dev)
+        grid = torch.zeros(V, dtype=torch.int32, device=dev)
+        msk = torch.zeros(V // 256 + 2, dtype=torch.int32, device=dev)
         rec = torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
         check(L.gvom_combine_partial(g._h, o, grid.data_ptr(), msk.data_ptr(), rec.data_ptr(), cap, cnt.data_ptr(), None, 0, 0, None),
@@ -101,7 +101,7 @@ def local_exchange_sharded(ranks, epoch):
     cap = int(min(V, g0.buffer_size * g0.max_points))
     rcap = V
     parr = lambda ps: (C.c_void_p * len(ps))(*[C.c_void_p(int(p)) for p in ps])
-    B = [dict(grid=torch.empty(V, dtype=torch.int32, device=dev), msk=torch.empty(V // 256 + 2, dtype=torch.int32, device=dev),
+    B = [dict(grid=torch.zeros(V, dtype=torch.int32, device=dev), msk=torch.zeros(V // 256 + 2, dtype=torch.int32, device=dev),
               rec=torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev), cnt=torch.zeros(1, dtype=torch.int32, device=dev),
               f1=torch.zeros(64, dtype=torch.int32, device=dev), f2=torch.zeros(64, dtype=torch.int32, device=dev),
               rcnt=torch.zeros(64, dtype=torch.int32, device=dev), rmap=torch.full((V,), -7, dtype=torch.int32, device=dev),
@@ -150,7 +150,7 @@ def local_exchange_rows(ranks, epoch):
     nb = C.c_uint64(0)
     check(L.gvom_rows_block_size(g0._h, C.byref(nb)), "block size")
     parr = lambda ps: (C.c_void_p * len(ps))(*[C.c_void_p(int(p)) for p in ps])
-    B = [dict(grid=torch.empty(V, dtype=torch.int32, device=dev), msk=torch.empty(V // 256 + 2, dtype=torch.int32, device=dev),
+    B = [dict(grid=torch.zeros(V, dtype=torch.int32, device=dev), msk=torch.zeros(V // 256 + 2, dtype=torch.int32, device=dev),
               rec=torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev), cnt=torch.zeros(1, dtype=torch.int32, device=dev),
               hdr=torch.zeros(64 * 4, dtype=torch.int32, device=dev), fh=torch.zeros(64, dtype=torch.int32, device=dev),
               fr=torch.zeros(64, dtype=torch.int32, device=dev), b2d=torch.zeros(nb.value, dtype=torch.uint8, device=dev)) for _ in ranks]
