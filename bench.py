@@ -380,9 +380,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # device-resident outputs are left in HBM in stream order (no host wait inside the timed region); the multi-GPU
-    # class completes every combine on the host (its exchange needs the epoch bookkeeping)
-    dev_kw = {} if multi else {"wait": False}
+    # device-resident outputs are left in HBM in stream order (no host wait inside the timed region)
+    dev_kw = {"wait": False}
 
     def timed(device_io, steps, warmup, profile=False):
         """-> (per-step ms list [device events], per-step wall ms, stage-time sums)"""
@@ -398,8 +397,9 @@ def main():
             t0 = time.perf_counter()
             a.record(stream)
             if device_io:
-                g.Process_pointcloud(on_dev[k], fr[k][1], fr[k][2])
-                out = g.combine_maps(device_outputs=True, **dev_kw)
+                with torch.cuda.stream(stream):                 # the Gvom's stream is the caller's current stream
+                    g.Process_pointcloud(on_dev[k], fr[k][1], fr[k][2])
+                    out = g.combine_maps(device_outputs=True, **dev_kw)
             else:
                 g.Process_pointcloud(pinned[k], fr[k][1], fr[k][2])
                 out = g.combine_maps()
@@ -468,35 +468,76 @@ def main():
             work = o.work
     except Exception:
         pass
-    abytes = {"scan_points": 24 * N, "scan_cells": 4 * V, "merge_codes": 4 * V * sources + 4 * V, "maps": 4 * V + 20 * P[2] * P[2]}
-    # (SURVEY.md 8d per-stage figures: ray-cast = the cloud as stored (float64 x 3); index = read hit + pass grids, write
-    #  the index map; merge = read B slot maps + the previous map, write the combined map; maps = one pass over the
-    #  combined map + the five 2-D outputs)
+    # ---- rooflines.  Every stage gets a bound it cannot beat, so frac <= 1:
+    #   hbm    algorithmic bytes (SURVEY.md 8d figures where the survey gives one, else the bytes the stage's own data
+    #          structures force it to move) / measured copy bandwidth
+    #   issue  warp instructions the kernel executed (committed ncu counter capture of this build) / peak issue rate
+    #   l2_atomic  atomic sectors the kernel sent to L2 after warp aggregation (same capture) / the atomic issue rate
+    #          measured live by gvom_bench_atomics
+    # the bound of a stage is the LARGEST of the times these give; frac = that time / the measured stage time.
+    S2c = P[2] * P[2]
+    counters = {}
+    cp_path = os.path.join(ROOT, "profiles", "kernel_counters_r02.json")
+    if os.path.exists(cp_path):
+        counters = json.load(open(cp_path)).get(CONFIG, {})
+    sm_clock_hz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_clock_hz * 1e6            # warp instructions / s (4 schedulers per SM, 1 per clock)
+    cells_scan = (work or {}).get("n_occ") or (work or {}).get("cells") or 30000
+    st_now = g.stats()
+    cells_comb = max(1, int(st_now.get("combined_cells", 0))) if not multi else None
+    abytes = {
+        "scan_points": 24 * N,                                            # the cloud as stored (float64 x 3), read once
+        "scan_cells": 4 * V + cells_scan * (27 * 4 + 80 + 8),             # the slot map once (group mask) + per cell: look-ups, metrics, counts
+        "merge_codes": 4 * V * sources + 4 * V,                           # B slot maps + previous map read, combined map written
+        "merge_cells": (cells_comb or 100000) * (4 * sources + 92 + 68),  # per combined cell: look-ups, >= one source record, the merged record
+        "maps": 4 * V + 20 * S2c,                                         # one pass over the combined map + the 2-D outputs
+    }
+    stage_kernels = {"scan_points": ["k_scan_points"], "scan_cells": ["k_scan_cells"], "merge_codes": ["k_merge_rows", "k_merge_codes"],
+                     "merge_cells": ["k_merge_cells2"], "maps": ["k_column_maps", "k_surface_maps2"]}
     rooflines = {}
     for k, bts in abytes.items():
-        if stage_ms.get(k, 0) > 0:
-            ach = bts / (stage_ms[k] * 1e-3) / 1e9
-            rooflines[k] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                            "ms": stage_ms[k], "algorithmic_bytes": bts}
-    if work and stage_ms.get("scan_points", 0) > 0 and atom.get("spread"):
-        n_at = 2 * work["n_in"] + work["dda_steps"]
-        ach = n_at / (stage_ms["scan_points"] * 1e-3) / 1e9
-        rooflines["raycast_atomics"] = {"bound": "l2_atomic", "achieved": ach, "peak": atom["spread"],
-                                        "unit": "G atomic increments/s", "frac": ach / atom["spread"],
-                                        "ms": stage_ms["scan_points"], "algorithmic_atomics": n_at,
-                                        "peak_same_address": atom.get("same_address"),
-                                        "note": "increments delivered (warp-aggregated) vs RED.ADD.U32 issue rate to "
-                                                "random words of a 16 MiB table measured by gvom_bench_atomics"}
+        t = stage_ms.get(k, 0) * 1e-3
+        if t <= 0 or multi:
+            continue
+        bounds = {"hbm": bts / (hbm * 1e9)}
+        inst = sum(v.get("inst_executed", 0) for kn, v in counters.items() if any(kn.startswith(p) for p in stage_kernels[k]))
+        atoms = sum(v.get("atom_sectors", 0) + v.get("red_sectors", 0) for kn, v in counters.items() if any(kn.startswith(p) for p in stage_kernels[k]))
+        if inst:
+            bounds["issue"] = inst / issue_peak
+        if atoms and atom.get("spread"):
+            bounds["l2_atomic"] = atoms / (atom["spread"] * 1e9)
+        which = max(bounds, key=bounds.get)
+        r = {"bound": which, "frac": bounds[which] / t, "ms": stage_ms[k], "bound_ms": {b: 1e3 * v for b, v in bounds.items()},
+             "algorithmic_bytes": bts}
+        if which == "hbm":
+            r.update({"achieved": bts / t / 1e9, "peak": hbm, "unit": "GB/s"})
+        elif which == "issue":
+            r.update({"achieved": inst / t / 1e9, "peak": issue_peak / 1e9, "unit": "G warp instructions/s", "instructions": inst})
+        else:
+            r.update({"achieved": atoms / t / 1e9, "peak": atom["spread"], "unit": "G atomic sectors/s", "atomic_sectors": atoms})
+        rooflines[k] = r
+    if work and stage_ms.get("scan_points", 0) > 0:
+        rooflines.setdefault("scan_points", {})["increments_delivered_per_s_G"] = (2 * work["n_in"] + work["dda_steps"]) / (stage_ms["scan_points"] * 1e-3) / 1e9
+    # the whole step against the HBM roofline of the path (206.8 MB per scan + combine at configs[1])
+    step_bytes = 24 * N + 12 * V + 4 * V * sources + 4 * V + 4 * V + 20 * S2c
+    step_roof = {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (tot_dev / args.steps * 1e-3) / 1e9,
+                 "peak": hbm, "unit": "GB/s", "frac": step_bytes / (tot_dev / args.steps * 1e-3) / 1e9 / hbm,
+                 "note": "SURVEY 8d per-stage bytes summed (cloud, index build, merge, column pass, outputs) / ms_per_step"}
+    if multi:
+        # N > 1: the per-rank step is scan + partial merge of the rank's own slots + the row-sharded finish; the
+        # dominant transfers are the rank's own slot maps (partial), 1/N of every rank's encoded grid + previous rows
+        # (finish) and the 2-D pushes -- reported as stage times, the single-GPU kernel rooflines do not apply
+        step_roof["note"] += "; per rank (weak scaling: the same bytes on every GPU, exchange traffic not counted)"
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")        # refreshed with every committed ncu capture
-    if os.path.exists(tp):                        # DRAM bytes per launch from the committed ncu --set full capture
-        for k, v in json.load(open(tp)).items():
-            if isinstance(v, dict) and v.get("dram_read") is not None and v.get("dram_write") is not None:
-                traffic[k] = v["dram_read"] + v["dram_write"]
-    kernels = {k: v for k, v in stage_ms.items() if k in ("scan_points", "scan_cells", "merge_codes", "merge_cells", "maps")}
-    dom = max((k for k in kernels if k in rooflines), key=lambda k: kernels[k], default=None)
+    for k, pref in stage_kernels.items():
+        vals = [v["dram_read"] + v["dram_write"] for kn, v in counters.items() if any(kn.startswith(p) for p in pref) and "dram_read" in v]
+        if vals:
+            traffic[k] = sum(vals)
+    kernels = {k: v for k, v in stage_ms.items() if k in rooflines}
+    dom = max(kernels, key=lambda k: kernels[k], default=None)
     roof = dict(rooflines[dom], kernel=dom, traffic=traffic.get(dom), peak_source=hbm_src,
-                traffic_source="profiles/traffic_r01.json (ncu --set full, bytes per launch)") if dom else None
+                traffic_source="profiles/kernel_counters_r02.json (ncu single-pass counters of this build, per launch)") if dom else \
+        dict(step_roof, kernel="whole step", traffic=None, peak_source=hbm_src)
 
     line = {
         "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
@@ -517,6 +558,7 @@ def main():
         "clocks": clocks,
         "roofline": roof,
         "rooflines": rooflines,
+        "step_roofline": step_roof,
         "stage_ms": stage_ms,
         "l2_atomic_peak_gops": atom,
         "work_per_scan": work,

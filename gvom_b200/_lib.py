@@ -89,6 +89,7 @@ SYMBOLS = {
     "gvom_get_stats": (C.c_int, [_vp, C.POINTER(GvomStats)]),
     "gvom_set_profiling": (C.c_int, [_vp, _i32]),
     "gvom_stage_times": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "gvom_graph_probe": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _pd, _vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_i32)]),
     "gvom_bench_atomics": (C.c_int, [C.c_int, _vp, _i64, _i32, _i32, _i32, C.POINTER(C.c_float), C.POINTER(_i64)]),
 }
 

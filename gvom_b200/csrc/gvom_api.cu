@@ -114,7 +114,7 @@ struct GvomHandle {
     // device
     unsigned* cellid = nullptr;           // [EV] extended, epoch-tagged voxel -> cell grid of the scan kernels
     unsigned scan_tag = 0;                // tag of the last scan (1..255; wraps through a clear of cellid)
-    double* acc = nullptr;                // [cap + gcap][MOM] raw moments of the scan in flight
+    double* acc[2] = {nullptr, nullptr};  // [cap + gcap][MOM] raw moments of the scan in flight, double-buffered: S2 clears behind S1
     char* stage_dev = nullptr;            // input cloud staging [max_points * 32 B]
     std::vector<Slot> slots;              // B + 1 PHYSICAL slots: B ring entries + one spare that is kept wiped
     std::vector<int> phys;                // ring index (the reference's buffer index) -> physical slot
@@ -130,7 +130,7 @@ struct GvomHandle {
     int* col_minz = nullptr;              // [2][S*S] lowest occupied / lowest free z per column (C1 -> C3)
     unsigned* known = nullptr;            // [2][S*ceil(S/32)] "height known" bit maps (rows over y, rows over x)
     float* debug_dev = nullptr;           // [max(ccap*8, S*S*10)]
-    int* flags = nullptr;                 // [0,1] / [2,3] cell + ghost counters of even / odd scans, [4] C1's running cell counter
+    int* flags = nullptr;                 // [0..5] cell + ghost counters of scans k % 3, [8] C1's running cell counter, [9..11] grid-done counters
     // multi-GPU scratch
     double* cacc = nullptr;               // [ccap,10] raw-moment scratch of the multi-GPU combine
     // pinned host
@@ -161,6 +161,7 @@ struct GvomHandle {
     signed char* grids_dev = nullptr;     // [GVOM_GRID_COUNT][S*S] int8 OccupancyGrid payloads
     signed char* grids_host = nullptr;    // pinned mirror
     int gather_blocks = 8;                // blocks per SM of the sharded finish's assembly kernels (GVOM_GATHER_BLOCKS)
+    int host_chunks = 4;                  // pieces a large pageable / PointCloud2 host cloud is staged in (GVOM_CHUNKS), pipelined with S1
     unsigned variant = 0;                 // GVOM_VARIANT bit mask (A/B switches, see VAR_*)
     // outputs of the last combine that still have to be completed on the host (gvom_combine_maps_async)
     struct Pending {
@@ -182,7 +183,7 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
     const size_t V = (size_t)h->V, cap = (size_t)h->cap, ccap = (size_t)h->ccap, S2 = (size_t)h->S2;
     Carver d(dev);
     h->cellid = d.take<unsigned>((size_t)h->EV);
-    h->acc = d.take<double>((cap + (size_t)h->gcap) * MOM);
+    for (int q = 0; q < 2; ++q) h->acc[q] = d.take<double>((cap + (size_t)h->gcap) * MOM);
     h->stage_dev = d.take<char>((size_t)h->max_points * 32);
     h->slots.resize(p.buffer_size + 1);
     h->phys.resize(p.buffer_size);
@@ -217,7 +218,7 @@ size_t carve(GvomHandle* h, void* dev, void* host, size_t* host_bytes) {
     h->col_minz = d.take<int>(2 * S2);
     h->known = d.take<unsigned>(2 * (size_t)p.xy_size * ((p.xy_size + 31) / 32));
     h->debug_dev = d.take<float>(std::max(ccap * 8, S2 * 10));
-    h->flags = d.take<int>(8);
+    h->flags = d.take<int>(16);
     h->cacc = d.take<double>(ccap * 10);
     h->grids_dev = d.take<signed char>(GVOM_GRID_COUNT * S2);
     Carver c(host);
@@ -358,7 +359,7 @@ void launch_merge(GvomHandle* h, const MergeArgs& A, const MergeOut& O, cudaStre
 
 // C2: per-cell record merge + eigenvalues
 void launch_cells(GvomHandle* h, const MergeArgs& A, Combined& c, cudaStream_t st) {
-    launch(k_merge_cells2, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 4, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
+    launch(k_merge_cells2, dim3(h->grid_cells2), dim3(128), 0, st, A, h->flags + 8, c.cell_voxel, c.hit, c.total, c.minh, c.metrics, c.eig,
                                                 h->dp, (int)h->ccap);
 }
 
@@ -377,6 +378,10 @@ int finish_outputs(GvomHandle* h) {
         if (pd.negative) memcpy(pd.negative, h->out_i_host + S2, bi);
         if (pd.visibility) memcpy(pd.visibility, h->out_i_host + 2 * S2, bi);
         if (pd.roughness) memcpy(pd.roughness, reinterpret_cast<char*>(h->out_i_host) + rough_off, bd);
+    }
+    if (h->counters_host[1]) {
+        h->counters_host[1] = 0;
+        return fail(GVOM_EINVAL, "multi-GPU combine: ranks disagree on the map origin (sensors must share the ego position)");
     }
     Combined& c = *pd.c;
     c.cells = std::min<int64_t>(h->counters_host[0], h->ccap);
@@ -425,13 +430,13 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
     unsigned* known = h->known; unsigned* knownT = h->known + (size_t)h->p.xy_size * W;
     launch(k_column_maps, dim3(W, W), dim3(1024), 0, st, c.index_map, c.minh, h->col_minz, h->col_minz + S2, c.origin[0], c.origin[1],
                                                c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, height, inferred, known, knownT,
-                                               h->flags + 4, c.counter, host_count);
+                                               h->flags + 8, c.counter, host_count);
     const size_t mask_bytes = 2 * (size_t)h->p.xy_size * W * sizeof(unsigned);
     const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
     {
         launch(k_surface_maps2, dim3(blocks_for(S2, 128)), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit, c.total, height, inferred, known, knownT,
                                                                                  c.origin[2], h->dp, rough, xs, ys, guessed, pos, neg, vis,
-                                                                                 in_smem, h->col_minz, h->flags + 4,
+                                                                                 in_smem, h->col_minz, h->flags + 8,
                                                                                  direct_dev ? kpos : nullptr, direct_dev ? kneg : nullptr,
                                                                                  direct_dev ? kvis : nullptr, direct_dev ? krough : nullptr,
                                                                                  RowShard{0, 1, h->p.xy_size}, PushSet{}, GridSignal{});
@@ -541,6 +546,7 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
                                                                              : resident_grid(k_scan_cells<-1, -1>, 256, h->sm_count);
         if (const char* m = getenv("GVOM_VARIANT")) h->variant = (unsigned)strtoul(m, nullptr, 0);
         if (const char* m = getenv("GVOM_GATHER_BLOCKS")) h->gather_blocks = std::max(1, std::min(8, atoi(m)));
+        if (const char* m = getenv("GVOM_CHUNKS")) h->host_chunks = std::max(1, std::min(16, atoi(m)));
         h->grid_rows3 = std::min(resident_grid(k_merge_rows<3, MERGE_FULL>, 256, h->sm_count),
                                  std::min(resident_grid(k_merge_rows<3, MERGE_PARTIAL>, 256, h->sm_count),
                                           resident_grid(k_merge_rows<3, MERGE_FINISH>, 256, h->sm_count)));
@@ -551,12 +557,16 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
     // unknown" with an empty group mask (S1 ray-casts into a wiped map; the row merge relies on map and mask of its
     // destination being consistent)
     if (e == cudaSuccess) e = cudaMemsetAsync(h->cellid, 0, sizeof(unsigned) * (size_t)h->EV, h->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(h->flags, 0, sizeof(int) * 8, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->flags, 0, sizeof(int) * 16, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->col_minz, 0x7f, sizeof(int) * 2 * (size_t)h->S2, h->stream);
     for (auto& sl : h->slots) {
         if (e == cudaSuccess) e = cudaMemsetAsync(sl.index_map, 0xff, sizeof(int) * (size_t)h->V, h->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(sl.gmask, 0, sizeof(unsigned) * ((size_t)h->V / 256 + 2), h->stream);
+        if (e == cudaSuccess) k_fill_f32<<<h->sm_count * 4, 256, 0, h->stream>>>(sl.minh, (long long)h->cap, 1.0f);
     }
+    // the scan kernels find their accumulator rows and min heights already clear (S2 resets behind S1)
+    for (int q = 0; q < 2; ++q)
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->acc[q], 0, sizeof(double) * MOM * (size_t)(h->cap + h->gcap), h->stream);
     for (auto& c : h->comb) {
         if (e == cudaSuccess) e = cudaMemsetAsync(c.index_map, 0xff, sizeof(int) * (size_t)h->V, h->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c.gmask, 0, sizeof(unsigned) * ((size_t)h->V / 256 + 2), h->stream);
@@ -566,6 +576,7 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
         delete h;
         return fail(GVOM_ECUDA, std::string("gvom_create: ") + cudaGetErrorString(e));
     }
+    memset(h->counters_host, 0, sizeof(int) * 8);            // (the caller's pinned block is not zeroed)
     if (const char* m = getenv("GVOM_H2D")) h->zero_copy = std::string(m) != "dma";
     h->active = h->stream;
     *out = h;
@@ -613,6 +624,12 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
     fr.start[0] = (float)(ego[0] / p.xy_resolution);
     fr.start[1] = (float)(ego[1] / p.xy_resolution);
     fr.start[2] = (float)(ego[2] / p.z_resolution);
+    for (int k = 0; k < 3; ++k) fr.io[k] = (int)fr.origin[k];
+    {
+        const uint32_t M = 0x4B400000u, S = (uint32_t)p.xy_size;
+        fr.S2 = p.xy_size * p.xy_size;
+        fr.cc = (int)((M + (uint32_t)fr.io[0]) + (M + (uint32_t)fr.io[1]) * S + (M + (uint32_t)fr.io[2]) * S * S);
+    }
     Xform tf;
     tf.enabled = T ? 1 : 0;
     for (int k = 0; k < 12; ++k) tf.m[k] = T ? T[k] : 0.0;
@@ -628,10 +645,10 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
         CUDA_TRY(cudaMemsetAsync(h->cellid, 0, sizeof(unsigned) * (size_t)h->EV, st));
         h->scan_tag = 1u;
     }
-    const int par = (int)(h->stats.process_calls & 1);
+    const int par = (int)(h->stats.process_calls % 3), buf = (int)(h->stats.process_calls & 1);
     ScanOut O{};
     O.map = s.index_map; O.cellid = h->cellid; O.tag = h->scan_tag; O.counters = h->flags + 2 * par;
-    O.acc = h->acc; O.minh = s.minh; O.cell_voxel = s.cell_voxel; O.cap = (int)h->cap; O.gcap = (int)h->gcap; O.ES = h->ES;
+    O.acc = h->acc[buf]; O.minh = s.minh; O.cell_voxel = s.cell_voxel; O.cap = (int)h->cap; O.gcap = (int)h->gcap; O.ES = h->ES;
 
     rec(h, EV_START, st);
     // ---- input staging + S1.  Host clouds: zero-copy (the kernel streams pinned memory over PCIe while it ray-casts),
@@ -684,7 +701,7 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
                 // field extraction (threaded, non-temporal) into packed 16-byte records, pipelined chunk by chunk
                 // with the zero-copy kernel that streams them over PCIe
                 rec(h, EV_H2D, st);
-                const int nchunks = n >= 131072 ? 4 : 1;
+                const int nchunks = n >= 131072 ? h->host_chunks : 1;
                 const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~int64_t(255);
                 for (int c = 0; c < nchunks; ++c) {
                     const int64_t first = c * per, count = std::min<int64_t>(per, n - first);
@@ -734,7 +751,7 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
                 // pageable: the staging copy (threaded, non-temporal) is pipelined with the kernel chunk by chunk
                 ensure_pool();
                 const auto t0 = std::chrono::steady_clock::now();
-                const int nchunks = n >= 131072 ? 4 : 1;
+                const int nchunks = n >= 131072 ? h->host_chunks : 1;
                 const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~int64_t(255);
                 for (int c = 0; c < nchunks; ++c) {
                     const int64_t first = c * per, count = std::min<int64_t>(per, n - first);
@@ -782,8 +799,9 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
         A.map = s.index_map;
         A.gmask = (p.xy_size % 8 == 0) ? s.gmask : nullptr;
         A.cellid = h->cellid; A.tag = h->scan_tag;
-        A.counters = h->flags + 2 * par; A.counters_next = h->flags + 2 * (1 - par);
-        A.acc = h->acc; A.cell_voxel = s.cell_voxel;
+        A.counters = h->flags + 2 * par; A.counters_prev = h->flags + 2 * ((par + 2) % 3); A.counters_next = h->flags + 2 * ((par + 1) % 3);
+        A.acc = h->acc[buf]; A.acc_other = h->acc[1 - buf]; A.cell_voxel = s.cell_voxel;
+        A.spare_minh = old.dirty ? old.minh : nullptr; A.spare_count = old.counter; A.gcap = (int)h->gcap;
         A.hit = s.hit; A.total = s.total; A.metrics = s.metrics; A.slot_count = s.counter;
         A.old_map = old.dirty ? old.index_map : nullptr;
         A.old_gmask = (old.dirty && old.has_gmask) ? old.gmask : nullptr;
@@ -874,7 +892,7 @@ static int combine_locked(GvomHandle* h, double origin[3], int32_t* positive, in
     // flags[1] (running cell counter) and the column minima are left clean by the previous combine's C4
     {
         MergeOut O{};
-        O.cmap = c.index_map; O.counter = h->flags + 4; O.cell_voxel = c.cell_voxel;
+        O.cmap = c.index_map; O.counter = h->flags + 8; O.cell_voxel = c.cell_voxel;
         O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
         O.gmask = (h->p.xy_size % 8 == 0) ? c.gmask : nullptr; O.cap = (int)h->ccap;
         launch_merge<MERGE_FULL>(h, A, O, st);
@@ -1330,6 +1348,9 @@ int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes) {
     const char* in = static_cast<const char*>(blob);
     size_t off = sizeof(StateHeader);
     cudaError_t err = cudaSuccess;
+    for (auto& sl : h->slots) k_fill_f32<<<h->sm_count * 4, 256>>>(sl.minh, (long long)h->cap, 1.0f);
+    for (int q = 0; q < 2 && err == cudaSuccess; ++q) err = cudaMemset(h->acc[q], 0, sizeof(double) * MOM * (size_t)(h->cap + h->gcap));
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
     state_sections(h, H, [&](void* d, size_t b) {
         if (b && err == cudaSuccess) err = cudaMemcpy(d, in + off, b, cudaMemcpyHostToDevice);
         off += (b + 15) & ~size_t(15);
@@ -1347,12 +1368,85 @@ int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes) {
         if (err == cudaSuccess) err = cudaMemset(h->comb[q].gmask, 0, gmb);
     }
     if (err == cudaSuccess) err = cudaMemset(h->cellid, 0, sizeof(unsigned) * (size_t)h->EV);
-    if (err == cudaSuccess) err = cudaMemset(h->flags, 0, sizeof(int) * 8);
+    if (err == cudaSuccess) err = cudaMemset(h->flags, 0, sizeof(int) * 16);
     if (err == cudaSuccess) err = cudaMemset(h->col_minz, 0x7f, sizeof(int) * 2 * (size_t)h->S2);
     if (err != cudaSuccess) return fail(GVOM_ECUDA, std::string("gvom_load_state: ") + cudaGetErrorString(err));
     h->scan_tag = 0;
     h->stage_busy = false;
     h->v_maps = h->maps; h->v_imaps = h->imaps; h->v_rough = h->rough_out;
+    return GVOM_OK;
+}
+
+// ------------------------------------------------------------- tooling: CUDA-graph replay of a tick
+// Measures what capturing the tick in a CUDA graph would buy: the launches of ONE
+// Process_pointcloud (device cloud) + combine_maps (outputs left in the library's block) are captured -- PDL edges
+// included -- instantiated, and replayed `iters` times; then the same tick is issued `iters` times as plain
+// PDL-chained launches from this thread.  Both are timed with CUDA events around the whole batch, so host launch
+// cost shows up only where the GPU starves.  The replay re-runs the same kernels on the same buffers (the maps it
+// produces are not meaningful) and the handle must not be used for mapping afterwards.
+int gvom_graph_probe(GvomHandle* h, const void* points_dev, int64_t n, int32_t stride, int32_t dtype, const double ego[3],
+                     const double* T, int32_t iters, float* graph_ms_per_tick, float* launch_ms_per_tick, int32_t* graph_nodes) {
+    if (!h || !points_dev || !ego || !graph_ms_per_tick || !launch_ms_per_tick || iters < 1) return fail(GVOM_EINVAL, "bad argument");
+    if (n < 1 || n > h->max_points) return fail(GVOM_ECAPACITY, "point count exceeds max_points");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (int e = finish_outputs(h)) return e;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const bool prof = h->profiling;
+    h->profiling = false;
+    const CloudDesc cd{points_dev, n, stride, dtype, GVOM_DEVICE, false, 0, 0, 0, 0};
+    double org[3];
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = process_locked(h, cd, ego, T, st);
+    if (rc == GVOM_OK) rc = combine_locked(h, org, nullptr, nullptr, nullptr, nullptr, GVOM_NONE, st, true);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    h->pend.active = false;                                  // (nothing was executed: no outputs to complete)
+    if (rc != GVOM_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->profiling = prof;
+        return rc != GVOM_OK ? rc : fail(GVOM_ECUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+    }
+    size_t nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &nodes);
+    if (graph_nodes) *graph_nodes = (int32_t)nodes;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        h->profiling = prof;
+        return fail(GVOM_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+    }
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int w = 0; w < 3; ++w) cudaGraphLaunch(exec, st);
+    cudaStreamSynchronize(st);
+    cudaEventRecord(a, st);
+    for (int i = 0; i < iters; ++i) cudaGraphLaunch(exec, st);
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    *graph_ms_per_tick = ms / iters;
+    for (int w = 0; w < 3; ++w) { process_locked(h, cd, ego, T, st); combine_locked(h, org, nullptr, nullptr, nullptr, nullptr, GVOM_NONE, st, true); h->pend.active = false; }
+    cudaStreamSynchronize(st);
+    cudaEventRecord(a, st);
+    for (int i = 0; i < iters; ++i) {
+        process_locked(h, cd, ego, T, st);
+        combine_locked(h, org, nullptr, nullptr, nullptr, nullptr, GVOM_NONE, st, true);
+        h->pend.active = false;
+    }
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    cudaEventElapsedTime(&ms, a, b);
+    *launch_ms_per_tick = ms / iters;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    h->profiling = prof;
+    CUDA_TRY(cudaGetLastError());
     return GVOM_OK;
 }
 
@@ -1419,7 +1513,7 @@ static int combine_partial_impl(GvomHandle* h, const double origin[3], int32_t* 
         if (n_signal > MAX_RANKS) return fail(GVOM_EINVAL, "too many ranks");
         G.S.n = n_signal;
         for (int k = 0; k < n_signal; ++k) G.S.slot[k] = signal_slots[k];
-        G.counter = h->flags + 5; G.epoch = epoch;
+        G.counter = h->flags + 9; G.epoch = epoch;
         G.header = header ? 1 : 0;                 // {epoch, origin}: the finishing ranks verify that everybody merged in the same frame
         G.ox = (int)origin[0]; G.oy = (int)origin[1]; G.oz = (int)origin[2];
     }
@@ -1493,7 +1587,7 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     double* cacc = h->cacc;
     {
         MergeOut O{};
-        O.cmap = c.index_map; O.counter = h->flags + 4; O.cell_voxel = c.cell_voxel;
+        O.cmap = c.index_map; O.counter = h->flags + 8; O.cell_voxel = c.cell_voxel;
         O.col_occ = h->col_minz; O.col_free = h->col_minz + h->S2;
         O.gmask = (h->p.xy_size % 8 == 0) ? c.gmask : nullptr; O.cap = (int)h->ccap;
         O.cacc = cacc; O.chit = c.hit; O.ctot = c.total; O.cminh = c.minh;
@@ -1503,7 +1597,7 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
     rec(h, EV_CODES, st);
     launch(k_scatter_records, dim3(h->sm_count * 8), dim3(256), 0, st, R, record_capacity, c.index_map,
                                                       cacc, c.hit, c.total, c.minh);
-    launch(k_finish_cells, dim3(h->grid_cells), dim3(128), 0, st, prev, has_prev, h->flags + 4, c.cell_voxel, cacc, c.hit, c.total, c.minh,
+    launch(k_finish_cells, dim3(h->grid_cells), dim3(128), 0, st, prev, has_prev, h->flags + 8, c.cell_voxel, cacc, c.hit, c.total, c.minh,
                                                    c.metrics, c.eig, h->dp, (int)h->ccap);
     rec(h, EV_CELLS, st);
     h->stats.kernel_launches += 2;
@@ -1605,7 +1699,7 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
         rec(h, EV_CSTART, st);
         {
             MergeOut O{};
-            O.cmap = c.index_map; O.counter = h->flags + 4; O.cell_voxel = c.cell_voxel;
+            O.cmap = c.index_map; O.counter = h->flags + 8; O.cell_voxel = c.cell_voxel;
             O.col_occ = h->col_minz; O.col_free = h->col_minz + S2;
             O.gmask = c.gmask; O.cap = (int)h->ccap;
             O.wait_flags = K->partial_headers; O.wait_n = N; O.wait_epoch = epoch; O.wait_stride = 4;
@@ -1620,7 +1714,7 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
         {
             SlabCells out{c.hit, c.total, c.minh, c.cell_voxel, c.metrics, c.eig};
             SignalSet none{};
-            launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 4, out, none, h->dp,
+            launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 8, out, none, h->dp,
                    (int)h->ccap, (int)K->record_capacity);
         }
         rec(h, EV_CELLS, st);
@@ -1631,10 +1725,10 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
             GridSignal G{};
             G.S.n = N;
             for (int k = 0; k < N; ++k) G.S.slot[k] = K->heights_slots[k];
-            G.counter = h->flags + 6; G.epoch = epoch;
+            G.counter = h->flags + 10; G.epoch = epoch;
             launch(k_rows_columns, dim3(blocks_for((int64_t)S * R.nrows + 1, 256)), dim3(256), 0, st, c.index_map, c.minh, h->col_minz,
                    h->col_minz + S2, c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, R, D,
-                   h->flags + 4, c.counter, host_count, G);
+                   h->flags + 8, c.counter, host_count, G);
         }
         rec(h, EV_X0, st);
         h->stats.kernel_launches += 3;
@@ -1648,10 +1742,10 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
         GridSignal G{};
         G.S.n = N;
         for (int k = 0; k < N; ++k) G.S.slot[k] = K->results_slots[k];
-        G.counter = h->flags + 7; G.epoch = epoch;
+        G.counter = h->flags + 11; G.epoch = epoch;
         launch(k_surface_maps2, dim3(std::max(1, blocks_for((int64_t)S * R.nrows, 128))), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit,
                c.total, (const double*)maps, (const double*)(maps + S2), known, knownT, c.origin[2], h->dp, rough, maps + 3 * S2,
-               maps + 4 * S2, maps + 5 * S2, imaps, imaps + S2, imaps + 2 * S2, in_smem, h->col_minz, h->flags + 4,
+               maps + 4 * S2, maps + 5 * S2, imaps, imaps + S2, imaps + 2 * S2, in_smem, h->col_minz, h->flags + 8,
                (int*)nullptr, (int*)nullptr, (int*)nullptr, (double*)nullptr, R, D, G);
         h->stats.kernel_launches += 2;
         rec(h, EV_X1, st);
@@ -1704,8 +1798,8 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
             origin_out[1] = c.origin[1] * h->p.xy_resolution;
             origin_out[2] = c.origin[2] * h->p.z_resolution;
         }
-        if (int e = finish_outputs(h)) return e;
-        if (h->counters_host[1]) return fail(GVOM_EINVAL, "multi-GPU combine: ranks disagree on the map origin (sensors must share the ego position)");
+        if (!(phases & 8))                                  // phases & 8: asynchronous, completed by the next call on the handle
+            if (int e = finish_outputs(h)) return e;
         c.has_gmask = true;
         c.valid = true;
         h->cur = 1 - h->cur;
@@ -1773,7 +1867,7 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     const SlabCells mine = slab_cells_at(res_cells[rank], res_capacity);
     if (phases & 1) {   // 1. my planes
         MergeOut O{};
-        O.cmap = res_maps[rank]; O.counter = h->flags + 4; O.cell_voxel = mine.voxel;
+        O.cmap = res_maps[rank]; O.counter = h->flags + 8; O.cell_voxel = mine.voxel;
         O.cap = (int)res_capacity;
         O.wait_flags = wait_partial; O.wait_n = nranks; O.wait_epoch = epoch;
         O.slab_r = rank; O.slab_n = nranks;
@@ -1783,7 +1877,7 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     {
         SignalSet CS; CS.n = nranks;
         for (int k = 0; k < nranks; ++k) CS.slot[k] = count_slots[k];
-        launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 4, mine, CS, h->dp,
+        launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 8, mine, CS, h->dp,
                (int)res_capacity, (int)record_capacity);
     }
     rec(h, EV_X0, st);
@@ -1797,7 +1891,7 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
     if (!(phases & 2)) { CUDA_TRY(cudaGetLastError()); return GVOM_OK; }
     // 3. everybody's planes and cells
     launch(k_gather_maps, dim3(h->sm_count * h->gather_blocks), dim3(256), 0, st, R, wait_slab, (int)epoch, c.index_map, c.gmask, h->col_minz,
-           h->col_minz + h->S2, h->flags + 4, h->dp);
+           h->col_minz + h->S2, h->flags + 8, h->dp);
     rec(h, EV_X1, st);
     launch(k_gather_cells, dim3(h->sm_count * h->gather_blocks), dim3(256), 0, st, R, (long long)res_capacity, c.hit, c.total, c.minh, c.metrics,
            c.eig, c.cell_voxel, (int)h->ccap);

@@ -94,6 +94,9 @@ struct Frame {
     double ego[3];            // world position of the sensor (float64, as passed)
     double origin[3];         // grid origin in voxel units, integral (gvom.py:138-141)
     float start[3];           // f32(ego / res): DDA start point (gvom.py:1178-1180)
+    int io[3];                // origin as int32
+    int cc;                   // (M + io[0]) + (M + io[1]) S + (M + io[2]) S^2 mod 2^32, M = bits of 12582912.0f (bulk DDA phase)
+    int S2;                   // S * S
 };
 
 // ---------------------------------------------------------------------------

@@ -47,6 +47,17 @@ struct ScanOut {
 };
 
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+// Fire-and-forget reductions (RED): nvcc emitted the returning form (ATOMG ..., RZ) for every atomic of this kernel;
+// the explicit PTX keeps the return path out of the atomic-bound regime (dense stress configuration).
+__device__ __forceinline__ void red_add(int* p, int v) {
+    asm volatile("red.global.add.s32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_min(int* p, int v) {
+    asm volatile("red.global.min.s32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+}
 
 // One world-frame point per lane: hit, cell claim, own-voxel moments, ray (gvom.py:1140-1231, 1249-1421).
 template <bool FASTFLOOR>
@@ -82,12 +93,12 @@ __device__ __forceinline__ void scan_point(bool ok, double wx, double wy, double
     const unsigned above = heads & ~((2u << lane) - 1u);                  // heads after my lane
     const int run_end = above ? (__ffs(above) - 2) : 31;                  // last lane of my run
     const bool act = head && cls != 0;
-    if (head && cls == 1) atomicAdd(O.map + v, -(run_end - lane + 1));    // the hit counts as a pass too (gvom.py:1169)
+    if (head && cls == 1) red_add(O.map + v, -(run_end - lane + 1));    // the hit counts as a pass too (gvom.py:1169)
 
     // ---- claim the voxel's cell (first hit of this scan) or find the id somebody else claimed.
     // Phase A: compare-and-swap the grid entry to "pending".  Phase B: the block's winners take their ids from ONE
     // atomic per block and counter (30 k same-address atomics would serialise for ~20 us at the L2 atomic unit:
-    // measured 1.5 G/s), clear their accumulator rows and publish the ids.  Nobody waits on another thread before
+    // measured 1.5 G/s) and publish them.  Nobody waits on another thread before
     // its own ids are published, so the waits of phase C cannot form a cycle.
     unsigned cur = 0;
     unsigned* e = O.cellid + vext;
@@ -120,13 +131,12 @@ __device__ __forceinline__ void scan_point(bool ok, double wx, double wy, double
             for (int w = 0; w < warp; ++w) id += s_cnt[w][t];
             unsigned pay = CELL_OVERFLOW;
             if (id < (t ? O.gcap : O.cap)) {
-                double2* a = reinterpret_cast<double2*>(O.acc + (long long)(t ? O.cap + id : id) * MOM);
-#pragma unroll
-                for (int k = 0; k < MOM / 2; ++k) a[k] = make_double2(0.0, 0.0);
-                if (!t) { O.minh[id] = 1.0f; O.cell_voxel[id] = v; }
+                // the accumulator row and the min-height entry are already clear: S2 of the previous scan reset what
+                // the scan before used (double-buffered), so publishing needs no memory fence -- a fence anywhere in
+                // this kernel makes ptxas emit every later atomic in its returning form (ATOMG) instead of RED
+                if (!t) O.cell_voxel[id] = v;
                 pay = (unsigned)id;
             }
-            __threadfence();                                              // the cleared row is visible before the id is
             cur = (O.tag << CELL_TAG_SHIFT) | (t ? CELL_GHOST : 0u) | pay;
             *reinterpret_cast<volatile unsigned*>(e) = cur;
         }
@@ -157,14 +167,14 @@ __device__ __forceinline__ void scan_point(bool ok, double wx, double wy, double
             const double t = __shfl_down_sync(FULL, val, off);
             if (lane + off <= run_end) val += t;
         }
-        if (row) atomicAdd(row + k, val);
+        if (row) red_add(row + k, val);
     }
     {
         for (int off = 1; off <= max_d; off <<= 1) {
             const float t = __shfl_down_sync(FULL, lzf, off);
             if (lane + off <= run_end) lzf = fminf(lzf, t);
         }
-        if (row && real) atomicMin(reinterpret_cast<int*>(O.minh) + id, __float_as_int(lzf));   // values in [0,1]: ordered as int bits
+        if (row && real) red_min(reinterpret_cast<int*>(O.minh) + id, __float_as_int(lzf));   // values in [0,1]: ordered as int bits
     }
 
     // ---- ray set-up (gvom.py:1174-1207): float32 state, float64 length
@@ -195,10 +205,41 @@ __device__ __forceinline__ void scan_point(bool ok, double wx, double wy, double
     // ---- DDA (gvom.py:1208-1231), warp-synchronous and branch-free; exactness argument in gvom_kernels.cuh
     // (raycast_point).  FASTFLOOR: floorf(p) for |p| < 2^22 is the low mantissa of p + 1.5 * 2^23 rounded DOWN
     // (one FADD.RM on the FP32 pipe instead of a quarter-rate F2I.FLOOR), the host checks the range.
-    const int iox = (int)ox, ioy = (int)oy, ioz = (int)oz;
+    const int iox = fr.io[0], ioy = fr.io[1], ioz = fr.io[2];
     constexpr int MAGIC_BITS = 0x4B400000;               // bit pattern of 12582912.0f
     const int cx = FASTFLOOR ? MAGIC_BITS + iox : iox, cy = FASTFLOOR ? MAGIC_BITS + ioy : ioy, cz = FASTFLOOR ? MAGIC_BITS + ioz : ioz;
     if (!active) { ix = 0.f; iy = 0.f; iz = 0.f; dlen = 0.0; }
+    if (FASTFLOOR && __all_sync(FULL, active)) {
+        // Bulk phase: the first n_safe steps of EVERY ray of the warp stay strictly inside the grid and below the
+        // length limit, so they need no bounds / length checks and no per-lane activity handling.  n_safe is a
+        // conservative closed-form bound (positions accumulate < 0.02 voxel of float32 rounding over 1000 steps; the
+        // bound keeps a 2-step margin); the arithmetic per step is unchanged, and the checked loop below finishes every
+        // ray exactly as before.
+        float kmin = 1.0e6f;
+        if (ix > 0.f) kmin = fminf(kmin, ((float)(iox + P.S - 1) - px) / ix); else if (ix < 0.f) kmin = fminf(kmin, (px - (float)(iox + 1)) / -ix);
+        if (iy > 0.f) kmin = fminf(kmin, ((float)(ioy + P.S - 1) - py) / iy); else if (iy < 0.f) kmin = fminf(kmin, (py - (float)(ioy + 1)) / -iy);
+        if (iz > 0.f) kmin = fminf(kmin, ((float)(ioz + P.Z - 1) - pz) / iz); else if (iz < 0.f) kmin = fminf(kmin, (pz - (float)(ioz + 1)) / -iz);
+        kmin = fminf(kmin, (float)(lim / dlen));
+        int it = __reduce_min_sync(FULL, (int)fmaxf(kmin - 2.0f, 0.f));
+        const unsigned above_me = ~((2u << lane) - 1u), from_me = 0xffffffffu << lane;
+        const int l0 = lane == 0 ? (int)0x80000000 : 0;       // lane 0 always starts a run
+#pragma unroll 1
+        for (; it > 0; --it) {
+            px = __fadd_rn(px, ix); py = __fadd_rn(py, iy); pz = __fadd_rn(pz, iz);
+            const int bx = __float_as_int(__fadd_rd(px, 12582912.0f)), by = __float_as_int(__fadd_rd(py, 12582912.0f)),
+                      bz = __float_as_int(__fadd_rd(pz, 12582912.0f));
+            const int vv = (bx - fr.cc) + by * P.S + bz * fr.S2;
+            const int p2 = __shfl_up_sync(FULL, vv, 1);
+            const bool h2 = p2 != (vv ^ l0);
+            const unsigned hs = __ballot_sync(FULL, h2);
+            if (h2) {
+                const unsigned ab = hs & above_me;
+                const unsigned nx = ab & (0u - ab);
+                red_add(O.map + vv, -__popc((nx - 1u) & from_me));
+            }
+            length = __dadd_rn(length, dlen);
+        }
+    }
     unsigned any = __ballot_sync(FULL, active);
     while (any) {
         px = __fadd_rn(px, ix); py = __fadd_rn(py, iy); pz = __fadd_rn(pz, iz);
@@ -220,7 +261,7 @@ __device__ __forceinline__ void scan_point(bool ok, double wx, double wy, double
         if (inside && h2) {
             const unsigned ab = hs & ~((2u << lane) - 1u);        // heads after my lane
             const unsigned nx = ab & (0u - ab);                   // lowest of them (0: my run ends the warp)
-            atomicAdd(O.map + vv, -__popc((nx - 1u) & (0xffffffffu << lane)));
+            red_add(O.map + vv, -__popc((nx - 1u) & (0xffffffffu << lane)));
         }
         length = __dadd_rn(length, dlen);
         active = inside && (length < lim);
@@ -304,7 +345,12 @@ struct CellArgs {
     const unsigned* cellid;
     unsigned tag;
     const int* counters;         // [0] cells, [1] ghosts of this scan
+    const int* counters_prev;    // the previous scan's pair: the rows of acc_other it used are cleared here
     int* counters_next;          // the next scan's pair, zeroed here
+    double* acc_other;           // the accumulator buffer the NEXT scan will use (this scan's is `acc`)
+    float* spare_minh;           // min heights of the spare slot (next scan's target), reset to 1.0 here
+    const int* spare_count;      // its cell count
+    int gcap;
     const double* acc;
     const int* cell_voxel;
     int* hit; int* total; double* metrics; int* slot_count;
@@ -331,6 +377,19 @@ k_scan_cells(CellArgs A, DevParams P) {
         const int sw = blockIdx.x * (8 - S2_GATHER_WARPS) + (warp - S2_GATHER_WARPS);
         const int nsw = gridDim.x * (8 - S2_GATHER_WARPS);
         const long long V = P.V;
+        {   // housekeeping for the next scan: clear the accumulator rows the previous scan used in the other buffer
+            // (cells and margin cells) and the min heights of the spare slot, so that S1 can publish cell ids unfenced
+            const long long nc = min(A.counters_prev[0], A.cap), ng = min(A.counters_prev[1], A.gcap);
+            double2* a0 = reinterpret_cast<double2*>(A.acc_other);
+            double2* a1 = reinterpret_cast<double2*>(A.acc_other + (long long)A.cap * MOM);
+            const double2 z2 = make_double2(0.0, 0.0);
+            for (long long i = (long long)sw * 32 + lane; i < nc * (MOM / 2); i += (long long)nsw * 32) a0[i] = z2;
+            for (long long i = (long long)sw * 32 + lane; i < ng * (MOM / 2); i += (long long)nsw * 32) a1[i] = z2;
+            if (A.spare_minh) {
+                const int ns = min(*A.spare_count, A.cap);
+                for (int i = sw * 32 + lane; i < ns; i += nsw * 32) A.spare_minh[i] = 1.0f;
+            }
+        }
         if (A.gmask) {
             const int nseg = (int)((V + 255) >> 8);
             constexpr int U = 4;                                   // segments in flight per warp
@@ -459,6 +518,11 @@ k_scan_cells(CellArgs A, DevParams P) {
             A.map[v] = id;
         }
     }
+}
+
+// start-up / restore: every slot's min heights read 1.0 (S2 keeps the spare slot's that way afterwards)
+__global__ void k_fill_f32(float* __restrict__ p, long long n, float v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
 }  // namespace gvom

@@ -214,14 +214,16 @@ class MultiGpuGvom(Gvom):
         pos, neg, rough, vis = self._out_arrays()
         return (pos, neg, rough, vis), (pos.ctypes.data, neg.ctypes.data, rough.ctypes.data, vis.ctypes.data), GVOM_HOST
 
-    def combine_maps(self, device_outputs=False):
+    def combine_maps(self, device_outputs=False, wait=True):
+        """Collective.  wait=False (device outputs, row-sharded exchange only): return once everything is enqueued; the
+        tensors are valid in stream order on the Gvom's stream."""
         self._calls += 1
         if self.exchange == "p2p":
-            return self._combine_p2p(device_outputs)
+            return self._combine_p2p(device_outputs, wait)
         return self._combine_nccl(device_outputs)
 
     # ------------------------------------------------------------------ peer-to-peer exchange
-    def _combine_p2p(self, device_outputs):
+    def _combine_p2p(self, device_outputs, wait=True):
         torch, L = self._torch, self._L
         X = self._sets[self._calls & 1]
         t, hdl, me = X["t"], X["hdl"], X["me"]
@@ -270,9 +272,12 @@ class MultiGpuGvom(Gvom):
             if self._rows:
                 # own world rows: merge + cells + columns; heights and finished maps are pushed to every rank
                 outs, optr, mem = self._outputs(device_outputs)
-                check(L.gvom_combine_finish_rows(self._h, self._org_in, C.byref(X["links"]), epoch, 7, self._org_c,
+                phases = 7 if (wait or not device_outputs) else 15
+                check(L.gvom_combine_finish_rows(self._h, self._org_in, C.byref(X["links"]), epoch, phases, self._org_c,
                                                  optr[0], optr[1], optr[2], optr[3], mem, self._stream),
                       "gvom_combine_finish_rows")
+                if phases == 15:
+                    self._hold_until_consumed(outs)      # the stream may still be writing them when the caller drops them
                 pos, neg, rough, vis = outs
                 return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
             outs, optr, mem = self._outputs(device_outputs)

@@ -239,7 +239,9 @@ int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t r
  * rank's 2-D block (symmetric memory, gvom_rows_block_size() bytes): heights after the column stage, the finished maps
  * after the surface stage.  gvom_combine_partial_header() is gvom_combine_partial() whose signal carries the origin
  * ({epoch, ox, oy, oz} int32 headers): the finishing ranks verify that everybody merged in the same frame
- * (GVOM_EINVAL otherwise).  phases: 1 = own rows + cells + heights, 2 = surface stage, 4 = deliver; 7 = all
+ * (GVOM_EINVAL otherwise).  phases: 1 = own rows + cells + heights, 2 = surface stage, 4 = deliver; 7 = all; + 8 =
+ * return without waiting for the stream (outputs in device memory are valid in stream order; completed, and errors
+ * reported, by the next call on the handle)
  * (separate phases let one process play several ranks in the tests).  Every flag / header table has one entry per rank,
  * written by that rank with the combine's epoch (1, 2, ...). */
 #define GVOM_MAX_RANKS 16
@@ -290,6 +292,15 @@ int gvom_stage_times(GvomHandle* h, float ms[16]);
 /* Tooling: A/B switches for measurements (bit mask, see gvom_api.cu VAR_*; 0 = defaults); every setting gives the
  * same results.  Also read from the environment variable GVOM_VARIANT at gvom_create(). */
 int gvom_set_variant(GvomHandle* h, uint32_t mask);
+
+/* Tooling: what would capturing the tick in a CUDA graph buy?  Captures the launches of one Process_pointcloud
+ * (device cloud) + combine_maps (outputs left in the library's block) including their programmatic-dependent-launch
+ * edges, replays the graph `iters` times and then issues the same tick `iters` times as plain launches; CUDA-event
+ * time per tick of both.  The handle must not be used for mapping afterwards (the replay re-runs the same kernels on
+ * the same buffers). */
+int gvom_graph_probe(GvomHandle* h, const void* points_dev, int64_t n, int32_t stride, int32_t dtype,
+                     const double ego[3], const double* transform16, int32_t iters, float* graph_ms_per_tick,
+                     float* launch_ms_per_tick, int32_t* graph_nodes);
 
 /* Tooling: L2 atomic-throughput microbenchmark (denominator of the ray-cast roofline).
  * Launches sm_count*8 blocks of 256 threads, each thread issuing per_thread
