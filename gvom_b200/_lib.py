@@ -82,6 +82,9 @@ SYMBOLS = {
     "gvom_rows_block_size": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "gvom_combine_partial_header": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _i64, _vp, C.POINTER(_vp), _i32, _i32, _vp]),
     "gvom_combine_finish_rows": (C.c_int, [_vp, _pd, C.POINTER(GvomRowsLinks), _i32, _i32, _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "gvom_mirror_block_size": (C.c_int, [_vp, _i32, C.POINTER(C.c_uint64)]),
+    "gvom_mirror_attach": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
+    "gvom_adopt_ego": (C.c_int, [_vp, _pd]),
     "gvom_slot_info": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i64), _pd]),
     "gvom_last_slot": (C.c_int, [_vp, C.POINTER(_i32)]),
     "gvom_export_slot": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),

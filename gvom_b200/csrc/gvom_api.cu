@@ -28,6 +28,7 @@
 #include "gvom_kernels.cuh"
 #include "gvom_scan.cuh"
 #include "gvom_merge.cuh"
+#include "gvom_mirror.cuh"
 
 using namespace gvom;
 
@@ -127,6 +128,9 @@ struct GvomHandle {
     // where the 2-D maps of the last combine live: the library's own block above, or (row-sharded multi-GPU combine) the
     // exchange block the ranks pushed into -- debug exports, OccupancyGrid post-processing and state save read these
     double* v_maps = nullptr; int* v_imaps = nullptr; double* v_rough = nullptr;
+    // row-sharded combine: the six float64 work maps (heights, slopes, guessed heights) stay in the exchange block
+    // ([y][x]) and are only transposed into `maps` when a debug export / state save asks for them
+    struct Maps6Pending { bool active = false; const char* blk = nullptr; PushSet D{}; } maps6;
     int* col_minz = nullptr;              // [2][S*S] lowest occupied / lowest free z per column (C1 -> C3)
     unsigned* known = nullptr;            // [2][S*ceil(S/32)] "height known" bit maps (rows over y, rows over x)
     float* debug_dev = nullptr;           // [max(ccap*8, S*S*10)]
@@ -154,7 +158,7 @@ struct GvomHandle {
     bool zero_copy = true;                // host clouds: S1 reads pinned memory directly (else chunked DMA)
     bool prof_process = false, prof_combine = false, prof_x = false, prof_partial = false, prof_rows = false;
     int sm_count = 148;
-    int grid_codes = 0, grid_cells = 0, grid_cells2 = 0, grid_rows3 = 0, grid_scan_cells = 0, grid_rows_async[2] = {0, 0};   // resident grids (set at create)
+    int grid_codes = 0, grid_cells = 0, grid_cells2 = 0, grid_rows3 = 0, grid_scan_cells = 0, grid_rows_mirror = 0, grid_rows_async[2] = {0, 0};   // resident grids (set at create)
     GvomStats stats{};
     float last_stage_copy_ms = 0.f;       // host time of the last pageable->pinned staging copy
     CopyPool* pool = nullptr;             // staging threads for pageable input (created on first use)
@@ -172,6 +176,13 @@ struct GvomHandle {
         int32_t *positive = nullptr, *negative = nullptr, *visibility = nullptr;
         double* roughness = nullptr;
     } pend;
+    // mirrored multi-GPU combine (gvom_mirror_attach): every scan is pushed to the owners of its rows
+    struct Mirror {
+        int n = 0, self = 0;
+        char* base[MAX_RANKS] = {};
+        size_t o_flags = 0, o_table = 0, o_args = 0, o_held = 0, o_mirrors = 0, mirror_bytes = 0;
+        size_t f_gmask = 0, f_hit = 0, f_tot = 0, f_minh = 0, f_met = 0, nsegp = 0, total = 0;
+    } mir;
     std::mutex mu;
     Slot& ring(int i) { return slots[phys[i]]; }
 };
@@ -363,6 +374,18 @@ void launch_cells(GvomHandle* h, const MergeArgs& A, Combined& c, cudaStream_t s
                                                 h->dp, (int)h->ccap);
 }
 
+// Row-sharded combine: bring the six work maps of the last combine from the exchange block into the library's own
+// [x][y] block (debug exports, state save).  No-op otherwise.
+void ensure_maps6(GvomHandle* h) {
+    if (!h->maps6.active) return;
+    h->maps6.active = false;
+    const int S = h->p.xy_size, W = (S + 31) / 32;
+    const size_t S2 = (size_t)h->S2;
+    MapSet own{h->maps, h->imaps, h->imaps + S2, h->imaps + 2 * S2, h->rough_out};
+    MapSet user{nullptr, nullptr, nullptr, nullptr, nullptr};
+    k_rows_deliver<<<dim3(W, W, 6), dim3(256), 0, h->active>>>(h->maps6.blk, h->maps6.D, S, own, user, (const int*)nullptr, 0, 0, 0);
+}
+
 // Completes the outputs of the last combine on the host: waits for the stream, copies pageable outputs out of
 // the pinned mirror, publishes the cell count.  No-op when nothing is pending.
 int finish_outputs(GvomHandle* h) {
@@ -397,6 +420,7 @@ int enqueue_maps_and_output(GvomHandle* h, Combined& c, double origin[3], int32_
                             double* roughness, int32_t* visibility, int32_t out_mem, cudaStream_t st) {
     const int S2 = h->S2;
     h->v_maps = h->maps; h->v_imaps = h->imaps; h->v_rough = h->rough_out;
+    h->maps6.active = false;
     double* height = h->maps; double* inferred = h->maps + S2; double* rough = h->rough_out;
     double* xs = h->maps + 3 * (size_t)S2; double* ys = h->maps + 4 * (size_t)S2; double* guessed = h->maps + 5 * (size_t)S2;
     int* pos = h->imaps; int* neg = h->imaps + S2; int* vis = h->imaps + 2 * (size_t)S2;
@@ -550,6 +574,7 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
         h->grid_rows3 = std::min(resident_grid(k_merge_rows<3, MERGE_FULL>, 256, h->sm_count),
                                  std::min(resident_grid(k_merge_rows<3, MERGE_PARTIAL>, 256, h->sm_count),
                                           resident_grid(k_merge_rows<3, MERGE_FINISH>, 256, h->sm_count)));
+        h->grid_rows_mirror = resident_grid(k_merge_rows_ind<3>, 256, h->sm_count);
         h->grid_rows_async[0] = resident_grid(k_merge_rows_async<1>, 32, h->sm_count, sizeof(MrWarp<1>));
         h->grid_rows_async[1] = resident_grid(k_merge_rows_async<2>, 32, h->sm_count, sizeof(MrWarp<2>));
     }
@@ -813,6 +838,29 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
         h->stats.kernel_launches++;
     }
     rec(h, EV_SCELLS, st);
+    if (h->mir.n > 0) {
+        // mirrored multi-GPU combine: deliver the scan to the owners of its rows (posted NVLink stores)
+        const GvomHandle::Mirror& m = h->mir;
+        MirrorPush M{};
+        M.n = m.n; M.self = m.self;
+        for (int k = 0; k < m.n; ++k) M.base[k] = m.base[k];
+        const size_t mo = m.o_mirrors + ((size_t)m.self * p.buffer_size + ring_i) * m.mirror_bytes;
+        M.o_map = (long long)mo; M.o_gmask = (long long)(mo + m.f_gmask); M.o_hit = (long long)(mo + m.f_hit);
+        M.o_tot = (long long)(mo + m.f_tot); M.o_minh = (long long)(mo + m.f_minh); M.o_met = (long long)(mo + m.f_met);
+        M.o_entry = (long long)(m.o_table + ((size_t)m.self * p.buffer_size + ring_i) * MIRROR_ENTRY * sizeof(int));
+        M.held = reinterpret_cast<unsigned*>(m.base[m.self] + m.o_held) + (size_t)ring_i * m.n * m.nsegp;
+        M.nsegp = (int)m.nsegp;
+        M.oy = fr.io[1];
+        M.entry[0] = (int)((h->stats.process_calls + 1) & 0x7fffffff);
+        M.entry[1] = fr.io[0]; M.entry[2] = fr.io[1]; M.entry[3] = fr.io[2];
+        memcpy(&M.entry[8], ego, 3 * sizeof(double));       // a rank that has not scanned yet adopts origin and ego from here
+        rec(h, EV_P0, st);
+        launch(k_push_scan, dim3(h->sm_count * 4), dim3(256), 0, st, (const int*)s.index_map, (const unsigned*)s.gmask, (const int*)s.counter,
+               (const int*)s.cell_voxel, (const int*)s.hit, (const int*)s.total, (const float*)s.minh, (const double*)s.metrics, M, h->dp, (int)h->cap);
+        h->stats.kernel_launches++;
+        rec(h, EV_P1, st);
+        h->prof_partial = h->profiling;
+    }
     CUDA_TRY(cudaGetLastError());
     h->prof_process = h->profiling;
     // a caller-owned host buffer may be reused as soon as we return: wait for the transfer (not the kernels)
@@ -1036,6 +1084,7 @@ static int debug_height_common(GvomHandle* h, float* out7, float* out3) {
     if (int e = finish_outputs(h)) return e;
     Combined& c = h->comb[h->cur];
     if (!c.valid || !h->have_maps) return GVOM_NO_DATA;
+    ensure_maps6(h);
     const size_t S2 = (size_t)h->S2;
     float* d7 = h->debug_dev; float* d3 = h->debug_dev + 7 * S2;
     k_debug_height<<<blocks_for(h->S2, 256), 256, 0, h->active>>>(h->v_maps, h->v_rough, h->v_maps + 3 * S2, h->v_maps + 4 * S2,
@@ -1106,6 +1155,7 @@ int gvom_export_combined(GvomHandle* h, int32_t* index_map, int32_t* hit, int32_
     if (int e = finish_outputs(h)) return e;
     Combined& c = h->comb[h->cur];
     if (!c.valid) return GVOM_NO_DATA;
+    if (maps6) ensure_maps6(h);
     CUDA_TRY(cudaStreamSynchronize(h->active));
     const size_t n = (size_t)c.cells;
     if (index_map) CUDA_TRY(cudaMemcpy(index_map, c.index_map, sizeof(int) * (size_t)h->V, cudaMemcpyDeviceToHost));
@@ -1223,6 +1273,7 @@ void state_sections(GvomHandle* h, const StateHeader& H, F&& visit) {
 
 int fill_state_header(GvomHandle* h, StateHeader* H) {
     if (int e = finish_outputs(h)) return e;
+    ensure_maps6(h);
     CUDA_TRY(cudaStreamSynchronize(h->active));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     memset(H, 0, sizeof(*H));
@@ -1374,6 +1425,7 @@ int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes) {
     h->scan_tag = 0;
     h->stage_busy = false;
     h->v_maps = h->maps; h->v_imaps = h->imaps; h->v_rough = h->rough_out;
+    h->maps6.active = false;
     return GVOM_OK;
 }
 
@@ -1633,6 +1685,71 @@ int gvom_rows_block_size(GvomHandle* h, uint64_t* bytes) {
     return GVOM_OK;
 }
 
+// ---- mirrored ring slots (gvom_mirror.cuh).  One block per rank, same layout everywhere:
+//   flags[64] | slot table [n][B][8] | source list (MergeArgs, local use) | held masks [B][n][nsegp] (local use) |
+//   mirrors [n][B] x {index map [V] | group mask [nsegp] | hit [cap] | total [cap] | min height [cap] | metrics [cap][10] f64}
+static void mirror_layout(const GvomHandle* h, int n, GvomHandle::Mirror* m) {
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t V = (size_t)h->V, cap = (size_t)h->cap, B = (size_t)h->p.buffer_size;
+    m->nsegp = (V / 256 + 2 + 63) & ~size_t(63);
+    m->o_flags = 0;
+    m->o_table = 256;
+    m->o_args = up(m->o_table + (size_t)n * B * MIRROR_ENTRY * sizeof(int));
+    m->o_held = up(m->o_args + sizeof(MergeArgs));
+    m->o_mirrors = up(m->o_held + B * (size_t)n * m->nsegp * sizeof(unsigned));
+    m->f_gmask = up(V * sizeof(int));
+    m->f_hit = up(m->f_gmask + m->nsegp * sizeof(unsigned));
+    m->f_tot = up(m->f_hit + cap * sizeof(int));
+    m->f_minh = up(m->f_tot + cap * sizeof(int));
+    m->f_met = up(m->f_minh + cap * sizeof(float));
+    m->mirror_bytes = up(m->f_met + cap * 10 * sizeof(double));
+    m->total = m->o_mirrors + (size_t)n * B * m->mirror_bytes + 256;
+}
+
+int gvom_mirror_block_size(GvomHandle* h, int32_t nranks, uint64_t* bytes) {
+    if (!h || !bytes) return fail(GVOM_EINVAL, "NULL argument");
+    if (nranks < 1 || nranks > MAX_RANKS) return fail(GVOM_EINVAL, "1..16 ranks");
+    if ((int64_t)nranks * h->p.buffer_size > MAX_SLOTS) return fail(GVOM_EINVAL, "more than 64 ring slots over all ranks");
+    if (h->p.xy_size % 256 != 0) return fail(GVOM_EINVAL, "mirrored ring slots need xy_size % 256 == 0");
+    GvomHandle::Mirror m;
+    mirror_layout(h, nranks, &m);
+    *bytes = m.total;
+    return GVOM_OK;
+}
+
+int gvom_mirror_attach(GvomHandle* h, int32_t rank, int32_t nranks, void* const* blocks) {
+    if (!h || !blocks) return fail(GVOM_EINVAL, "NULL argument");
+    uint64_t need = 0;
+    if (int e = gvom_mirror_block_size(h, nranks, &need)) return e;
+    if (rank < 0 || rank >= nranks) return fail(GVOM_EINVAL, "bad rank");
+    for (int k = 0; k < nranks; ++k) if (!blocks[k]) return fail(GVOM_EINVAL, "NULL mirror block");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->stats.process_calls != 0) return fail(GVOM_EINVAL, "gvom_mirror_attach: the handle already holds scans");
+    GvomHandle::Mirror m;
+    mirror_layout(h, nranks, &m);
+    m.n = nranks; m.self = rank;
+    for (int k = 0; k < nranks; ++k) m.base[k] = static_cast<char*>(blocks[k]);
+    // own block: flags, table, held masks and group masks clear; every mirror map "all unknown"
+    char* me = m.base[rank];
+    CUDA_TRY(cudaMemsetAsync(me, 0, m.o_mirrors, h->stream));
+    for (size_t q = 0; q < (size_t)nranks * h->p.buffer_size; ++q) {
+        char* mq = me + m.o_mirrors + q * m.mirror_bytes;
+        CUDA_TRY(cudaMemsetAsync(mq, 0xff, (size_t)h->V * sizeof(int), h->stream));
+        CUDA_TRY(cudaMemsetAsync(mq + m.f_gmask, 0, m.nsegp * sizeof(unsigned), h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->mir = m;
+    return GVOM_OK;
+}
+
+int gvom_adopt_ego(GvomHandle* h, const double ego[3]) {
+    if (!h || !ego) return fail(GVOM_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    for (int k = 0; k < 3; ++k) h->ego[k] = ego[k];
+    return GVOM_OK;
+}
+
 int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRowsLinks* K, int32_t epoch, int32_t phases,
                              double origin_out[3], int32_t* positive, int32_t* negative, double* roughness,
                              int32_t* visibility, int32_t out_mem, void* stream) {
@@ -1641,10 +1758,12 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
     if (N < 1 || N > MAX_RANKS || me < 0 || me >= N) return fail(GVOM_EINVAL, "bad rank / nranks");
     if (h->p.xy_size % 256 != 0) return fail(GVOM_EINVAL, "row-sharded finish needs xy_size % 256 == 0");
     if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE && out_mem != GVOM_NONE) return fail(GVOM_EINVAL, "bad out_mem");
+    const bool mirrored = h->mir.n > 0;
+    if (mirrored && (h->mir.n != N || h->mir.self != me)) return fail(GVOM_EINVAL, "links disagree with gvom_mirror_attach");
     for (int k = 0; k < N; ++k)
-        if (!K->code_grids[k] || !K->group_masks[k] || !K->records[k] || !K->blocks2d[k] || !K->heights_slots[k] || !K->results_slots[k])
+        if ((!mirrored && (!K->code_grids[k] || !K->group_masks[k] || !K->records[k])) || !K->blocks2d[k] || !K->heights_slots[k] || !K->results_slots[k])
             return fail(GVOM_EINVAL, "NULL rank buffer");
-    if (!K->partial_headers || !K->heights_flags || !K->results_flags) return fail(GVOM_EINVAL, "NULL flag table");
+    if ((!mirrored && !K->partial_headers) || !K->heights_flags || !K->results_flags) return fail(GVOM_EINVAL, "NULL flag table");
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
@@ -1674,7 +1793,74 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
     const int W = (S + 31) / 32;
     unsigned* known = h->known; unsigned* knownT = h->known + (size_t)S * W;
 
-    if (phases & 1) {
+    auto mirror_sync = [&](int mode, const SlotRef& prev, int has_prev) -> MirrorSync {
+        const GvomHandle::Mirror& m = h->mir;
+        MirrorSync Y{};
+        char* mine_m = m.base[me];
+        for (int k = 0; k < N; ++k) Y.flag_slot[k] = reinterpret_cast<int*>(m.base[k] + m.o_flags) + me;
+        Y.flags = reinterpret_cast<const int*>(mine_m + m.o_flags);
+        Y.table = reinterpret_cast<const int*>(mine_m + m.o_table);
+        Y.mirrors = mine_m + m.o_mirrors;
+        Y.mirror_bytes = (long long)m.mirror_bytes; Y.f_gmask = (long long)m.f_gmask; Y.f_hit = (long long)m.f_hit;
+        Y.f_tot = (long long)m.f_tot; Y.f_minh = (long long)m.f_minh; Y.f_met = (long long)m.f_met;
+        Y.n = N; Y.B = h->p.buffer_size; Y.epoch = epoch; Y.mode = mode;
+        Y.org[0] = (int)origin[0]; Y.org[1] = (int)origin[1]; Y.org[2] = (int)origin[2];
+        Y.prev = prev; Y.has_prev = has_prev;
+        Y.out = reinterpret_cast<MergeArgs*>(mine_m + m.o_args);
+        void* mp = nullptr;
+        if (cudaHostGetDevicePointer(&mp, h->counters_host, 0) == cudaSuccess) Y.err_flag = (int*)mp + 1; else cudaGetLastError();
+        return Y;
+    };
+    if (mirrored && (phases & 16) && !(phases & 1)) {       // publish "my scans are pushed" only (tests: one process plays all ranks)
+        launch(k_mirror_args, dim3(1), dim3(32), 0, st, mirror_sync(1, SlotRef{}, 0));
+        h->stats.kernel_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if ((phases & 1) && mirrored) {
+        // own world rows from the local mirrors of every rank's ring slots + own previous rows: the single-GPU kernels
+        if (int e = finish_outputs(h)) return e;
+        for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];
+        SlotRef prev{};
+        const int has_prev = pc.valid ? 1 : 0;
+        if (has_prev) {
+            prev.map = pc.index_map; prev.metrics = pc.metrics; prev.hit = pc.hit; prev.total = pc.total; prev.minh = pc.minh;
+            prev.dx = (int)(origin[0] - pc.origin[0]); prev.dy = (int)(origin[1] - pc.origin[1]); prev.dz = (int)(origin[2] - pc.origin[2]);
+            prev.is_prev = 1;
+            prev.gmask = pc.gmask;
+        }
+        rec(h, EV_CSTART, st);
+        h->counters_host[1] = 0;
+        const MergeArgs* Ad = reinterpret_cast<const MergeArgs*>(h->mir.base[me] + h->mir.o_args);
+        {
+            // flag exchange + source list (from the slot table the pushes carried), then the row merge of the own rows
+            MergeOut O{};
+            O.cmap = c.index_map; O.counter = h->flags + 8; O.cell_voxel = c.cell_voxel;
+            O.col_occ = h->col_minz; O.col_free = h->col_minz + S2;
+            O.gmask = c.gmask; O.cap = (int)h->ccap;
+            O.row_y0 = R.y0; O.row_n = N;
+            launch(k_mirror_args, dim3(1), dim3(32), 0, st, mirror_sync((phases & 32) ? 2 : 3, prev, has_prev));
+            launch(k_merge_rows_ind<3>, dim3(std::max(1, h->grid_rows_mirror)), dim3(256), 0, st, Ad, O, h->dp);
+        }
+        rec(h, EV_CODES, st);
+        {
+            // cells of the own rows + heights of the own columns (pushed to every rank) + "heights" signal: one launch
+            int* host_count = nullptr;
+            void* m = nullptr;
+            if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) host_count = (int*)m; else cudaGetLastError();
+            GridSignal G{};
+            G.S.n = N;
+            for (int k = 0; k < N; ++k) G.S.slot[k] = K->heights_slots[k];
+            G.counter = h->flags + 10; G.epoch = epoch;
+            launch(k_merge_cells2_rows, dim3(h->grid_cells2), dim3(128), 0, st, Ad, (const int*)(h->flags + 8), (const int*)c.cell_voxel, c.hit,
+                   c.total, c.minh, c.metrics, c.eig, h->dp, (int)h->ccap, (const int*)h->col_minz, (const int*)(h->col_minz + S2),
+                   c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1], h->ego[2], R, D, c.counter, host_count, G);
+        }
+        rec(h, EV_CELLS, st);
+        rec(h, EV_X0, st);
+        h->stats.kernel_launches += 3;
+        h->prof_combine = false;
+        CUDA_TRY(cudaGetLastError());
+    } else if (phases & 1) {
         if (int e = finish_outputs(h)) return e;
         for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];
         MergeArgs A;
@@ -1770,7 +1956,9 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
             }
             if (ok) { user = MapSet{nullptr, (int*)mp[0], (int*)mp[1], (int*)mp[2], (double*)mp[3]}; direct = true; }
         }
-        launch(k_rows_deliver, dim3(W, W, 10), dim3(256), 0, st, (const char*)mine, D, S, own, user, K->results_flags, N, (int)epoch);
+        // the four output maps now; the six work maps on demand (ensure_maps6)
+        launch(k_rows_deliver, dim3(W, W, 4), dim3(256), 0, st, (const char*)mine, D, S, own, user, K->results_flags, N, (int)epoch, 6);
+        h->maps6.active = true; h->maps6.blk = mine; h->maps6.D = D;
         h->stats.kernel_launches += 1;
         rec(h, EV_MAPS, st);
         CUDA_TRY(cudaGetLastError());
@@ -1791,7 +1979,7 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
         }
         h->v_maps = h->maps; h->v_imaps = h->imaps; h->v_rough = h->rough_out;
         rec(h, EV_D2H, st);
-        h->prof_rows = h->profiling && phases == 7;
+        h->prof_rows = h->profiling;
         h->have_maps = true;
         if (origin_out) {
             origin_out[0] = c.origin[0] * h->p.xy_resolution;

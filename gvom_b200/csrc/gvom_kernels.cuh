@@ -216,7 +216,9 @@ constexpr int REC = 16;               // floats per multi-GPU cell record
 //   MERGE_PARTIAL multi-GPU, step 1: this rank's ring slots -> encoded grid (OCC_FLAG | passes) + record ids
 //   MERGE_FINISH  multi-GPU, step 2: every rank's encoded grid (own HBM or a peer's over NVLink, or one
 //                 all-reduced grid) + previous map -> combined index map, cell accumulators cleared
-enum { MERGE_FULL = 0, MERGE_PARTIAL = 1, MERGE_FINISH = 2 };
+//   MERGE_ROWS    multi-GPU, mirrored ring slots: like MERGE_FULL, restricted to the world rows this rank owns
+//                 (O.row_y0 / O.row_n); the sources are local mirrors of every rank's ring slots + the previous map
+enum { MERGE_FULL = 0, MERGE_PARTIAL = 1, MERGE_FINISH = 2, MERGE_ROWS = 3 };
 
 struct MergeOut {
     int* cmap;               // combined index map (FULL / FINISH) or encoded grid (PARTIAL)
@@ -523,9 +525,7 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
 // ids; "unknown" is 0 there) and MERGE_FINISH (every rank's encoded grid + previous map -> combined map; optionally only
 // the rows this rank owns, O.row_n > 1; waits for the peers' partial results itself).
 template <int NB, int MODE>
-__global__ void __launch_bounds__(256, (NB > 3) ? 2 : 3)
-k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
-    pdl_wait();
+__device__ __forceinline__ void merge_rows_body(const MergeArgs& A, const MergeOut& O, const DevParams& P) {
     if (MODE == MERGE_FINISH && O.wait_flags) {           // device-side barrier of the peer-to-peer exchange (see k_merge_codes)
         if (threadIdx.x == 0) {
             const int stride = O.wait_stride > 0 ? O.wait_stride : 1;
@@ -543,7 +543,7 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
     const unsigned lt = (1u << lane) - 1u;
     const int S = P.S, Z = P.Z;
     const int spr = S >> 8;                               // segments per row
-    const bool rslab = MODE == MERGE_FINISH && O.row_n > 1;
+    const bool rslab = (MODE == MERGE_FINISH || MODE == MERGE_ROWS) && O.row_n > 1;
     const int my_rows = rslab ? (O.row_y0 < S ? (S - O.row_y0 + O.row_n - 1) / O.row_n : 0) : S;
     const int nseg = rslab ? Z * my_rows * spr : (int)(P.V >> 8);
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -726,6 +726,12 @@ k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
     }
 }
 
+template <int NB, int MODE>
+__global__ void __launch_bounds__(256, (NB > 3) ? 2 : 3)
+k_merge_rows(MergeArgs A, MergeOut O, DevParams P) {
+    pdl_wait();
+    merge_rows_body<NB, MODE>(A, O, P);
+}
 // closed-form eigenvalues of the float32 covariance (gvom.py:1423-1487)
 __device__ __forceinline__ void eigen3(const float* m, float* e) {
     const float xx = m[3], xy = m[4], xz = m[5], yy = m[6], yz = m[7], zz = m[8];
@@ -800,11 +806,12 @@ __device__ __forceinline__ void load_cell_rec(const SlotRef& s, int io, CellRec&
     r.hit = s.hit[io]; r.tot = s.total[io]; r.mh = s.minh[io];
 }
 
-__global__ void __launch_bounds__(128, 8)
-k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
+struct NoCellHook { __device__ __forceinline__ void operator()(int, int, int, float) const {} };
+// hook(x, y, z, min height) runs for every finished cell (the mirrored multi-GPU combine derives the column heights there)
+template <typename Hook>
+__device__ __forceinline__ void merge_cells2_body(const MergeArgs& A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
                int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
-               float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap) {
-    pdl_wait();
+               float* __restrict__ cmet, float* __restrict__ ceig, const DevParams& P, int cap, const Hook& hook) {
     const int count = min(*counter, cap);
     const int S = P.S, Z = P.Z;
     constexpr int RB = 8;                                   // sources looked up per round
@@ -841,10 +848,19 @@ k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restri
 #pragma unroll
         for (int k = 0; k < 10; ++k) mo[k] = c[k];
         chit[id] = hit; ctot[id] = tot; cminh[id] = mh;
+        hook(x, y, z, mh);
         float e[3];
         eigen3(c, e);
         ceig[id * 3 + 0] = e[0]; ceig[id * 3 + 1] = e[1]; ceig[id * 3 + 2] = e[2];
     }
+}
+
+__global__ void __launch_bounds__(128, 8)
+k_merge_cells2(MergeArgs A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
+               int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
+               float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap) {
+    pdl_wait();
+    merge_cells2_body(A, counter, cell_voxel, chit, ctot, cminh, cmet, ceig, P, cap, NoCellHook{});
 }
 
 // 2-D maps are indexed [x,y] row-major like the reference's numpy outputs
@@ -1245,7 +1261,7 @@ k_rows_known(const double* __restrict__ height, DevParams P, unsigned* __restric
 struct MapSet { double* maps6; int* pos; int* neg; int* vis; double* rough; };
 __global__ void __launch_bounds__(256)
 k_rows_deliver(const char* __restrict__ blk, PushSet D, int S, MapSet own, MapSet user,
-               const int* __restrict__ wait_flags, int wait_n, int wait_epoch) {
+               const int* __restrict__ wait_flags, int wait_n, int wait_epoch, int m0) {
     pdl_wait();
     wait_flags_block(wait_flags, wait_n, wait_epoch);
     __shared__ double td[32][33];
@@ -1253,7 +1269,7 @@ k_rows_deliver(const char* __restrict__ blk, PushSet D, int S, MapSet own, MapSe
     const long long S2 = (long long)S * S;
     const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
-    const int m = blockIdx.z;                              // 0..5: float64 maps of maps6, 6: roughness, 7..9: pos / neg / vis
+    const int m = blockIdx.z + m0;                         // 0..5: float64 maps of maps6, 6: roughness, 7..9: pos / neg / vis
     const bool is_d = m < 7;
     const double* sd = m < 6 ? reinterpret_cast<const double*>(blk + D.off_maps) + m * S2 : reinterpret_cast<const double*>(blk + D.off_rough);
     const int* si = reinterpret_cast<const int*>(blk + (m == 7 ? D.off_pos : m == 8 ? D.off_neg : D.off_vis));

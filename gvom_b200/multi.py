@@ -57,6 +57,22 @@ def merge_headers(headers):
     return org.copy(), counts
 
 
+MIRROR_ENTRY_INTS = 16      # include/gvom_b200.h: slot-table entry of the mirrored exchange
+
+
+def newest_origin(table):
+    """table: (ranks, slots, 16) int32 slot-table entries {seq (0: empty), ox, oy, oz, cells, ..., ego xyz float64 at
+    ints 8..13} of the mirrored exchange -> (origin, ego) of the newest scan of the first rank that holds one, or
+    (None, None).  Pure host logic (start-up path only)."""
+    table = np.ascontiguousarray(table, dtype=np.int32)
+    for g in range(table.shape[0]):
+        seq = table[g, :, 0]
+        if (seq > 0).any():
+            e = table[g, int(np.argmax(seq))]
+            return e[1:4].astype(np.float64), e[8:14].copy().view(np.float64).copy()
+    return None, None
+
+
 def _ptr_array(ptrs):
     return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
 
@@ -65,7 +81,7 @@ class MultiGpuGvom(Gvom):
     """One rank of a multi-GPU Gvom.  Same API as Gvom; combine_maps() is collective
     (every rank must call it) and returns the same maps on every rank."""
 
-    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", sharded="auto", rows="auto", **kw):
+    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", sharded="auto", rows="auto", mirror="auto", **kw):
         import os
         import torch
         import torch.distributed as dist
@@ -102,6 +118,12 @@ class MultiGpuGvom(Gvom):
         self._rows = bool(rows) and self.xy_size % 256 == 0
         if self._rows:
             self._sharded = False
+        # mirrored ring slots (default with the row-sharded finish): every scan is pushed to the owners of its rows at
+        # Process_pointcloud time, the combine merges from local mirrors -- no partial merge, no encoded grids.
+        # GVOM_MULTI_MIRROR=0 selects the partial-merge exchange for A/B runs.
+        if mirror == "auto":
+            mirror = os.environ.get("GVOM_MULTI_MIRROR", "1") != "0"
+        self._mirror = bool(mirror) and self._rows and self.world * self.buffer_size <= 64
         nb = C.c_uint64(0)
         check(self._L.gvom_rows_block_size(self._h, C.byref(nb)), "gvom_rows_block_size")
         self._b2d_bytes = int(nb.value)
@@ -191,8 +213,15 @@ class MultiGpuGvom(Gvom):
                 K.partial_headers, K.heights_flags, K.results_flags = me_p + self._o_hdr4, me_p + self._o_fh, me_p + self._o_fr
                 self._sets[-1]["links"] = K
                 self._sets[-1]["hdr4"] = _ptr_array([p + self._o_hdr4 + 16 * self.rank for p in ptrs])
+        if self._mirror:
+            nb = C.c_uint64(0)
+            check(self._L.gvom_mirror_block_size(self._h, self.world, C.byref(nb)), "gvom_mirror_block_size")
+            self._mir_t = symm_mem.empty(int(nb.value), dtype=torch.uint8, device=self._dev)
+            self._mir_hdl = symm_mem.rendezvous(self._mir_t, group)
+            check(self._L.gvom_mirror_attach(self._h, self.rank, self.world, _ptr_array([int(p) for p in self._mir_hdl.buffer_ptrs])),
+                  "gvom_mirror_attach")
         torch.cuda.synchronize(self._dev)
-        dist.barrier(group=self._group)
+        dist.barrier(group=self._group)          # nobody scans (pushes) before every rank's mirrors are initialised
         self._hdr_host = torch.zeros(HEADER_DOUBLES, dtype=torch.float64).pin_memory()
 
     def _init_nccl(self):
@@ -230,6 +259,8 @@ class MultiGpuGvom(Gvom):
         o_grid, o_msk, o_rec, o_cnt, o_hdr, _, o_flg = self._off
         epoch = self._calls
         have = L.gvom_newest_origin(self._h, self._org_in) != GVOM_NO_DATA
+        if self._mirror:
+            return self._combine_mirror(device_outputs, wait, X, epoch, have)
         with torch.cuda.stream(self._tstream):
             hh = self._hdr_host                      # header: only read by ranks that have no scan yet (start-up)
             hh[0] = 1.0 if have else 0.0
@@ -294,6 +325,42 @@ class MultiGpuGvom(Gvom):
             check(L.gvom_combine_finish(self._h, self._org_in, X["grids"], X["masks"], self.world, X["recs"], X["cnts"],
                                         self.world, self._rec_cap, X["wait"], epoch, self._org_c, optr[0], optr[1],
                                         optr[2], optr[3], mem, self._stream), "gvom_combine_finish")
+        pos, neg, rough, vis = outs
+        return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
+
+    # ------------------------------------------------------------------ mirrored ring slots
+    def _combine_mirror(self, device_outputs, wait, X, epoch, have):
+        """Row-sharded combine over the local mirrors of every rank's ring slots (gvom_mirror_attach): the scans were
+        pushed when they were made; here one warp publishes / awaits the epoch flags and builds the source list."""
+        torch, L = self._torch, self._L
+        extra = 0
+        with torch.cuda.stream(self._tstream):
+            if not have:
+                # start-up only: this rank has no scan yet.  Publish the flag, wait (on the host) for the others and
+                # adopt the origin of a rank that has data (the slot table the pushes carried).
+                check(L.gvom_combine_finish_rows(self._h, self._org_in, C.byref(X["links"]), epoch, 16, self._org_c,
+                                                 None, None, None, None, GVOM_NONE, self._stream), "gvom_combine_finish_rows")
+                self._tstream.synchronize()
+                flags = self._mir_t[:4 * self.world].view(torch.int32)
+                while int(flags.min().item()) < epoch:
+                    time.sleep(1e-4)
+                nt = self.world * self.buffer_size * MIRROR_ENTRY_INTS
+                table = self._mir_t[256:256 + 4 * nt].view(torch.int32).cpu().numpy().reshape(self.world, self.buffer_size, MIRROR_ENTRY_INTS)
+                origin, ego = newest_origin(table)
+                if origin is None:
+                    print("ERROR: No data in buffer")
+                    return None
+                for k in range(3):
+                    self._org_in[k] = float(origin[k])
+                check(L.gvom_adopt_ego(self._h, (C.c_double * 3)(*[float(v) for v in ego])), "gvom_adopt_ego")
+                extra = 32
+            outs, optr, mem = self._outputs(device_outputs)
+            phases = (7 if (wait or not device_outputs) else 15) | extra
+            check(L.gvom_combine_finish_rows(self._h, self._org_in, C.byref(X["links"]), epoch, phases, self._org_c,
+                                             optr[0], optr[1], optr[2], optr[3], mem, self._stream),
+                  "gvom_combine_finish_rows")
+            if phases & 8:
+                self._hold_until_consumed(outs)
         pos, neg, rough, vis = outs
         return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
 

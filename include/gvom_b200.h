@@ -267,6 +267,25 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
                              int32_t phases, double origin_out[3], int32_t* positive, int32_t* negative,
                              double* roughness, int32_t* visibility, int32_t out_mem, void* stream);
 
+/* Mirrored ring slots -- the exchange of the row-sharded combine without a partial merge.  Every rank owns a block of
+ * gvom_mirror_block_size() bytes that all ranks can write (symmetric memory).  After gvom_mirror_attach() every
+ * Process_pointcloud ends with one push kernel that stores the new slot's index-map rows, group-mask words and cell
+ * records into the memory of the rank that owns the row (world rows, as above) -- posted NVLink stores -- together
+ * with a slot-table entry {sequence, origin, cells}; every rank thus holds exact local copies of all ranks' ring slots
+ * for the rows it owns.  gvom_combine_finish_rows() on an attached handle then needs no encoded grids, records or
+ * partial headers (those link fields may be NULL): one warp publishes this rank's epoch flag, waits for the others' and
+ * builds the source list on the device from the slot table; the single-GPU merge kernels run over the own rows from
+ * local memory.  Replaces the roles of gvom.py:242-257 (merge over the whole ring) across GPUs.  blocks[k] = rank k's
+ * block as mapped into this process; attach before the first scan and synchronise all ranks (barrier) before any of
+ * them scans.  Extra phase bits of gvom_combine_finish_rows() for attached handles: 16 = publish the epoch flag only;
+ * 32 (with 1) = do not publish it again (16 for all ranks first, then 1 | 32: one process plays several ranks). */
+int gvom_mirror_block_size(GvomHandle* h, int32_t nranks, uint64_t* bytes);
+int gvom_mirror_attach(GvomHandle* h, int32_t rank, int32_t nranks, void* const* blocks);
+/* A rank that has not scanned yet takes part in a combine with the origin AND the vehicle position of a rank that has
+ * (slot-table entry: 16 int32 {sequence (0: empty), ox, oy, oz, cells, -, -, -, ego xyz as 3 float64, -, -} at byte 256 +
+ * 64 * (rank * buffer_size + slot) of the block): the ego disc of the height map (gvom.py:560-571) needs it. */
+int gvom_adopt_ego(GvomHandle* h, const double ego[3]);
+
 /* ---- test / tooling hooks (canonical parity dumps; not on the hot path) ---- */
 int gvom_slot_info(GvomHandle* h, int32_t slot, int32_t* valid, int64_t* cells, double origin[3]);
 int gvom_last_slot(GvomHandle* h, int32_t* slot);

@@ -1,0 +1,30 @@
+#!/bin/bash
+# mirrored ring slots on real peers: in-process parity, torchrun parity (incl. a late rank), bench A/B against the partial-merge exchange
+N=${1:-2}
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_multi_gpu.py -x -q -k "mirrored" 2>&1 | tail -5
+port=29700
+LOG=gpurun_out/multi_rank_check_r02_mirror_n$N.log
+: > $LOG
+for spec in "p2p grid256" "p2p grid256 late"; do
+  port=$((port+1))
+  echo "=== torchrun x$N tests/multi_rank_check.py $spec" >> $LOG
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port tests/multi_rank_check.py $spec 2>&1 | grep -E "MULTI_RANK_OK|Error|error|assert|Traceback" | head -8 >> $LOG
+done
+cat $LOG
+for tag in mirror rows; do
+  [ $tag = rows ] && export GVOM_MULTI_MIRROR=0
+  port=$((port+1))
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --steps 100 --warmup 20 > gpurun_out/bench_r02_c9_n${N}_$tag.json 2> gpurun_out/bench_r02_c9_n${N}_$tag.err
+  tail -3 gpurun_out/bench_r02_c9_n${N}_$tag.err
+done
+python - <<PY
+import json
+for tag in ("mirror","rows"):
+    try:
+        d=json.loads(open("gpurun_out/bench_r02_c9_n${N}_%s.json" % tag).read().strip().splitlines()[-1])
+        print(tag, {k:d[k] for k in ("value","ms_per_step","p50_latency_ms","gpu_launches_per_step")}, d["io"]["exchange"], d.get("parity_check",{}).get("ok"), d["e2e"]["value"])
+        print({k:round(1e3*v,1) for k,v in d["stage_ms"].items() if v})
+    except Exception as e: print(tag, "ERR", e)
+PY

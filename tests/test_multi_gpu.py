@@ -183,6 +183,73 @@ def local_exchange_rows(ranks, epoch):
     return outs, B
 
 
+def attach_mirrors(ranks):
+    """Mirrored ring slots for handles living in one process: one block per "rank" in plain device memory."""
+    import torch
+    from gvom_b200._lib import check
+    L, n = ranks[0]._L, len(ranks)
+    nb = C.c_uint64(0)
+    check(L.gvom_mirror_block_size(ranks[0]._h, n, C.byref(nb)), "mirror block size")
+    blocks = [torch.zeros(nb.value, dtype=torch.uint8, device=f"cuda:{ranks[0].device}") for _ in ranks]
+    ptrs = (C.c_void_p * n)(*[C.c_void_p(b.data_ptr()) for b in blocks])
+    for r, g in enumerate(ranks):
+        check(L.gvom_mirror_attach(g._h, r, n, ptrs), "mirror attach")
+    return blocks
+
+
+def local_exchange_mirror(ranks, epoch, blocks=None):
+    """In-process emulation of the MIRRORED row-sharded combine: the scans were pushed by Process_pointcloud; every
+    "rank" publishes its epoch flag (phase 16, all ranks), merges its rows from the local mirrors (phase 1 | 32), then
+    the 2-D phases as in local_exchange_rows."""
+    import torch
+    from gvom_b200._lib import GVOM_HOST, GVOM_NO_DATA, GvomRowsLinks, check
+    g0 = ranks[0]
+    L = g0._L
+    dev = f"cuda:{g0.device}"
+    n = len(ranks)
+    org = (C.c_double * 3)()
+    origin = None
+    for g in ranks:
+        if L.gvom_newest_origin(g._h, org) != GVOM_NO_DATA and origin is None:
+            origin = [org[0], org[1], org[2]]
+    o = (C.c_double * 3)(*origin)
+    nb = C.c_uint64(0)
+    check(L.gvom_rows_block_size(g0._h, C.byref(nb)), "block size")
+    B = [dict(fh=torch.zeros(64, dtype=torch.int32, device=dev), fr=torch.zeros(64, dtype=torch.int32, device=dev),
+              b2d=torch.zeros(nb.value, dtype=torch.uint8, device=dev)) for _ in ranks]
+    links = []
+    for r in range(n):
+        K = GvomRowsLinks()
+        K.rank, K.nranks, K.record_capacity = r, n, 0
+        for k, b in enumerate(B):
+            K.blocks2d[k] = b["b2d"].data_ptr()
+            K.heights_slots[k] = b["fh"].data_ptr() + 4 * r
+            K.results_slots[k] = b["fr"].data_ptr() + 4 * r
+        K.heights_flags, K.results_flags = B[r]["fh"].data_ptr(), B[r]["fr"].data_ptr()
+        links.append(K)
+    if blocks is not None:                                  # ranks that have not scanned yet adopt the vehicle position
+        from gvom_b200.multi import MIRROR_ENTRY_INTS, newest_origin
+        torch.cuda.synchronize()
+        nt = n * g0.buffer_size * MIRROR_ENTRY_INTS
+        for r, g in enumerate(ranks):
+            if L.gvom_newest_origin(g._h, org) == GVOM_NO_DATA:
+                table = blocks[r][256:256 + 4 * nt].view(torch.int32).cpu().numpy().reshape(n, g0.buffer_size, MIRROR_ENTRY_INTS)
+                o2, ego = newest_origin(table)
+                assert o2 is not None and list(o2) == origin
+                check(L.gvom_adopt_ego(g._h, (C.c_double * 3)(*[float(v) for v in ego])), "adopt ego")
+    outs = []
+    for phase in (16, 1 | 32, 2, 4):
+        for r, g in enumerate(ranks):
+            pos, neg, rough, vis = g._out_arrays()
+            oo = (C.c_double * 3)()
+            check(L.gvom_combine_finish_rows(g._h, o, C.byref(links[r]), epoch, phase, oo, pos.ctypes.data, neg.ctypes.data,
+                                             rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None), "rows (mirrored)")
+            torch.cuda.synchronize()
+            if phase == 4:
+                outs.append((np.array(list(oo)), pos, neg, rough, vis))
+    return outs, B
+
+
 def assemble_rows_state(ranks, outs, xy_res):
     """Row-sharded state -> one canonical dump: rank r contributes the world rows (y + origin_y) % n == r."""
     n = len(ranks)
@@ -231,6 +298,43 @@ def test_row_sharded_finish_equals_single(nranks):
             for q in range(max(0, s2 - Bs + 1), s2 + 1):
                 for r in range(nranks):
                     ref.Process_pointcloud(*fr[q][r])
+            last = ref.combine_maps()
+        want = canon.canon_combine(ref.refview(), last)
+        for r in range(nranks):
+            for a, b, name in zip(outs[r], last, ("origin", "pos", "neg", "rough", "vis")):
+                ok = np.allclose(a, b, rtol=1e-4, atol=1e-9, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b)
+                assert ok, f"step {step} rank {r}: {name}"
+        got = assemble_rows_state(ranks, outs, P1[0])
+        for k in ("codes", "ids", "hit", "total", "minh"):
+            assert np.array_equal(got[k], want[k]), f"step {step}: {k}"
+        assert np.allclose(got["metrics"], want["metrics"], rtol=1e-4, atol=2e-6), f"step {step}: metrics"
+
+
+@pytest.mark.parametrize("nranks,late", [(1, 0), (2, 0), (3, 0), (3, 2)])
+def test_mirrored_rows_equals_single(nranks, late):
+    """gvom_mirror_attach + gvom_combine_finish_rows (the default multi-GPU combine): every scan is pushed to the owners
+    of its rows by Process_pointcloud; the maps every rank delivers and the 3-D state assembled from the ranks' row
+    shards equal one Gvom holding every rank's ring slots.  The ego moves 1.25 rows per step, so rows change owner
+    between scans (wipes at the old owner).  late: the last rank only starts scanning at that step."""
+    from gvom_b200 import Gvom
+    Bs = 2
+    kw = dict(xy_size=256, z_size=16, robot_radius=2.0)
+    P1, PN = synth.params_tuple(buffer_size=Bs, **kw), synth.params_tuple(buffer_size=Bs * nranks, **kw)
+    fr = sensor_frames(nranks, 5, wall=30.0)
+    ranks = [Gvom(*P1) for _ in range(nranks)]
+    blocks = attach_mirrors(ranks)
+    active = lambda step, r: not (late and r == nranks - 1 and step < late)
+    for step in range(5):
+        for r in range(nranks):
+            if active(step, r):
+                ranks[r].Process_pointcloud(*fr[step][r])
+        outs, _keep = local_exchange_mirror(ranks, step + 1, blocks)
+        ref = Gvom(*PN)
+        for s2 in range(step + 1):
+            for q in range(max(0, s2 - Bs + 1), s2 + 1):
+                for r in range(nranks):          # a rank that has not started yet: an empty scan (knows nothing) keeps the ring aligned
+                    pc, ego, T = fr[q][r]
+                    ref.Process_pointcloud(pc if active(q, r) else np.zeros((0, 3)), ego, T)
             last = ref.combine_maps()
         want = canon.canon_combine(ref.refview(), last)
         for r in range(nranks):
