@@ -102,7 +102,7 @@ enum { EV_START = 0, EV_H2D, EV_POINTS, EV_SCELLS, EV_CSTART, EV_CODES, EV_CELLS
        EV_X0, EV_X1, EV_X2, EV_P0, EV_P1, EV_COUNT };   // EV_X*: extra marks inside the multi-GPU combine
 
 // GVOM_VARIANT bits (environment / gvom_set_variant): A/B switches for measurements; every setting gives the same results
-enum { VAR_GENERIC_MERGE = 2, VAR_ASYNC_ROWS = 4, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128 };
+enum { VAR_GENERIC_MERGE = 2, VAR_ASYNC_ROWS = 4, VAR_NO_SRCMASK = 16, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128 };
 
 }  // namespace
 
@@ -383,7 +383,7 @@ void ensure_maps6(GvomHandle* h) {
     const size_t S2 = (size_t)h->S2;
     MapSet own{h->maps, h->imaps, h->imaps + S2, h->imaps + 2 * S2, h->rough_out};
     MapSet user{nullptr, nullptr, nullptr, nullptr, nullptr};
-    k_rows_deliver<<<dim3(W, W, 6), dim3(256), 0, h->active>>>(h->maps6.blk, h->maps6.D, S, own, user, (const int*)nullptr, 0, 0, 0);
+    k_rows_deliver<<<dim3(W, W, 6), dim3(256), 0, h->active>>>(h->maps6.blk, h->maps6.D, S, own, user, (const int*)nullptr, 0, 0, 0, SignalSet{});
 }
 
 // Completes the outputs of the last combine on the host: waits for the stream, copies pageable outputs out of
@@ -403,7 +403,9 @@ int finish_outputs(GvomHandle* h) {
         if (pd.roughness) memcpy(pd.roughness, reinterpret_cast<char*>(h->out_i_host) + rough_off, bd);
     }
     if (h->counters_host[1]) {
+        const int why = h->counters_host[1];
         h->counters_host[1] = 0;
+        if (why == 2) return fail(GVOM_ECUDA, "multi-GPU combine: timed out waiting for a rank (every rank must call combine_maps)");
         return fail(GVOM_EINVAL, "multi-GPU combine: ranks disagree on the map origin (sensors must share the ego position)");
     }
     Combined& c = *pd.c;
@@ -574,7 +576,7 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
         h->grid_rows3 = std::min(resident_grid(k_merge_rows<3, MERGE_FULL>, 256, h->sm_count),
                                  std::min(resident_grid(k_merge_rows<3, MERGE_PARTIAL>, 256, h->sm_count),
                                           resident_grid(k_merge_rows<3, MERGE_FINISH>, 256, h->sm_count)));
-        h->grid_rows_mirror = resident_grid(k_merge_rows_ind<3>, 256, h->sm_count);
+        h->grid_rows_mirror = std::min(resident_grid(k_merge_rows_ind<3, false>, 256, h->sm_count), resident_grid(k_merge_rows_ind<3, true>, 256, h->sm_count));
         h->grid_rows_async[0] = resident_grid(k_merge_rows_async<1>, 32, h->sm_count, sizeof(MrWarp<1>));
         h->grid_rows_async[1] = resident_grid(k_merge_rows_async<2>, 32, h->sm_count, sizeof(MrWarp<2>));
     }
@@ -1831,6 +1833,7 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
         rec(h, EV_CSTART, st);
         h->counters_host[1] = 0;
         const MergeArgs* Ad = reinterpret_cast<const MergeArgs*>(h->mir.base[me] + h->mir.o_args);
+        const unsigned* srcmask = nullptr;
         {
             // flag exchange + source list (from the slot table the pushes carried), then the row merge of the own rows
             MergeOut O{};
@@ -1838,8 +1841,15 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
             O.col_occ = h->col_minz; O.col_free = h->col_minz + S2;
             O.gmask = c.gmask; O.cap = (int)h->ccap;
             O.row_y0 = R.y0; O.row_n = N;
+            // which sources are occupied at each combined cell (<= 32 sources): saves the cell kernel 2N - 2 look-ups per cell
+            // (from 9 sources up: below that the extra registers cost the row merge more than the cell kernel saves;
+            // GVOM_VARIANT bit 16 switches it off for A/B runs)
+            const int nsrc = N * h->p.buffer_size;
+            if (nsrc >= 8 && nsrc <= 31 && !(h->variant & VAR_NO_SRCMASK)) O.srcmask = reinterpret_cast<unsigned*>(h->cacc);
+            srcmask = O.srcmask;
             launch(k_mirror_args, dim3(1), dim3(32), 0, st, mirror_sync((phases & 32) ? 2 : 3, prev, has_prev));
-            launch(k_merge_rows_ind<3>, dim3(std::max(1, h->grid_rows_mirror)), dim3(256), 0, st, Ad, O, h->dp);
+            if (O.srcmask) launch(k_merge_rows_ind<3, true>, dim3(std::max(1, h->grid_rows_mirror)), dim3(256), 0, st, Ad, O, h->dp);
+            else launch(k_merge_rows_ind<3, false>, dim3(std::max(1, h->grid_rows_mirror)), dim3(256), 0, st, Ad, O, h->dp);
         }
         rec(h, EV_CODES, st);
         {
@@ -1847,13 +1857,10 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
             int* host_count = nullptr;
             void* m = nullptr;
             if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) host_count = (int*)m; else cudaGetLastError();
-            GridSignal G{};
-            G.S.n = N;
-            for (int k = 0; k < N; ++k) G.S.slot[k] = K->heights_slots[k];
-            G.counter = h->flags + 10; G.epoch = epoch;
+            GridSignal G{};                                // (the "heights" flag is published by the next kernel, k_rows_known)
             launch(k_merge_cells2_rows, dim3(h->grid_cells2), dim3(128), 0, st, Ad, (const int*)(h->flags + 8), (const int*)c.cell_voxel, c.hit,
                    c.total, c.minh, c.metrics, c.eig, h->dp, (int)h->ccap, (const int*)h->col_minz, (const int*)(h->col_minz + S2),
-                   c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1], h->ego[2], R, D, c.counter, host_count, G);
+                   c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1], h->ego[2], R, D, c.counter, host_count, G, srcmask);
         }
         rec(h, EV_CELLS, st);
         rec(h, EV_X0, st);
@@ -1921,14 +1928,22 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
         h->prof_combine = false;
         CUDA_TRY(cudaGetLastError());
     }
+    auto flag_set = [&](int32_t* const* slots) { SignalSet P{}; P.n = N; for (int k = 0; k < N; ++k) P.slot[k] = slots[k]; return P; };
+    // mirrored combine: the "heights" / "results" flags are published by the first block of the kernel that then waits for
+    // everybody's (phases & 256: they do not publish; 64 / 128: publish only -- one process playing several ranks)
+    if (mirrored && (phases & 64)) { launch(k_signal, dim3(1), dim3(32), 0, st, flag_set(K->heights_slots), (int)epoch); h->stats.kernel_launches++; }
+    if (mirrored && (phases & 128)) { launch(k_signal, dim3(1), dim3(32), 0, st, flag_set(K->results_slots), (int)epoch); h->stats.kernel_launches++; }
+    const bool publish = mirrored && !(phases & 256);
     if (phases & 2) {
-        launch(k_rows_known, dim3(W, W), dim3(1024), 0, st, (const double*)maps, h->dp, known, knownT, K->heights_flags, N, (int)epoch);
+        launch(k_rows_known, dim3(W, W), dim3(1024), 0, st, (const double*)maps, h->dp, known, knownT, K->heights_flags, N, (int)epoch,
+               publish ? flag_set(K->heights_slots) : SignalSet{});
         const size_t mask_bytes = 2 * (size_t)S * W * sizeof(unsigned);
         const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
         GridSignal G{};
         G.S.n = N;
         for (int k = 0; k < N; ++k) G.S.slot[k] = K->results_slots[k];
         G.counter = h->flags + 11; G.epoch = epoch;
+        if (mirrored) G = GridSignal{};                     // published by k_rows_deliver instead
         launch(k_surface_maps2, dim3(std::max(1, blocks_for((int64_t)S * R.nrows, 128))), dim3(256), in_smem ? mask_bytes : 0, st, c.index_map, c.hit,
                c.total, (const double*)maps, (const double*)(maps + S2), known, knownT, c.origin[2], h->dp, rough, maps + 3 * S2,
                maps + 4 * S2, maps + 5 * S2, imaps, imaps + S2, imaps + 2 * S2, in_smem, h->col_minz, h->flags + 8,
@@ -1957,7 +1972,8 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
             if (ok) { user = MapSet{nullptr, (int*)mp[0], (int*)mp[1], (int*)mp[2], (double*)mp[3]}; direct = true; }
         }
         // the four output maps now; the six work maps on demand (ensure_maps6)
-        launch(k_rows_deliver, dim3(W, W, 4), dim3(256), 0, st, (const char*)mine, D, S, own, user, K->results_flags, N, (int)epoch, 6);
+        launch(k_rows_deliver, dim3(W, W, 4), dim3(256), 0, st, (const char*)mine, D, S, own, user, K->results_flags, N, (int)epoch, 6,
+               publish ? flag_set(K->results_slots) : SignalSet{});
         h->maps6.active = true; h->maps6.blk = mine; h->maps6.D = D;
         h->stats.kernel_launches += 1;
         rec(h, EV_MAPS, st);

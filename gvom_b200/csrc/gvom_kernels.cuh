@@ -31,12 +31,29 @@ __device__ __forceinline__ void pdl_wait() {
 }
 // device-side barrier of the peer-to-peer exchanges, folded into the consumer kernel: every block waits until all
 // ranks' flag slots (written by their signal kernels after a system-scope fence) have reached `epoch`
+// A rank that died or never calls the collective must not hang the others' GPUs: every spin gives up after ~10 s
+// (the combine then produces garbage, which the callers' error paths / parity checks report -- but the kernel ends).
+constexpr unsigned long long SPIN_LIMIT_NS = 10000000000ULL;
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool spin_until(const volatile int* f, int epoch) {
+    if (*f >= epoch) return true;
+    const unsigned long long t0 = now_ns();
+    while (*f < epoch) {
+        __nanosleep(100);
+        if (now_ns() - t0 > SPIN_LIMIT_NS) return false;
+    }
+    return true;
+}
 __device__ __forceinline__ void wait_flags_block(const int* flags, int n, int epoch) {
     if (flags) {
         if (threadIdx.x == 0) {
             for (int k = 0; k < n; ++k) {
                 const volatile int* f = flags + k;
-                while (*f < epoch) __nanosleep(100);
+                if (!spin_until(f, epoch)) break;
             }
             __threadfence_system();
         }
@@ -69,6 +86,18 @@ __device__ __forceinline__ void signal_when_grid_done(const GridSignal& G) {
             for (int k = 0; k < G.S.n; ++k) { volatile int* f = G.S.slot[k]; f[0] = G.epoch; }
             __threadfence_system();
         }
+    }
+}
+
+// The cheaper form of the same signal, used where the NEXT kernel of the stream starts with a wait anyway: that kernel's
+// first block publishes the flag before it waits.  Everything the previous kernels of the stream wrote -- remote stores
+// included -- is complete and visible when a kernel passes pdl_wait(), so no per-block system fence (ERRBAR: 21 % of the
+// stall samples of the cell kernel at 8 ranks) and no counter are needed in the producer.  Call before the wait.
+__device__ __forceinline__ void publish_flag_first_block(const SignalSet& S, int epoch) {
+    if (S.n == 0 || blockIdx.x != 0 || blockIdx.y != 0 || blockIdx.z != 0) return;
+    if (threadIdx.x < S.n) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(S.slot[threadIdx.x]) = epoch;
     }
 }
 
@@ -239,6 +268,7 @@ struct MergeOut {
     int wait_stride;         // ints between two ranks' flags (1: plain flags, 4: {epoch, ox, oy, oz} headers)
     int org[3];              // wait_stride == 4: the origin this rank merges in; a peer header that disagrees raises *err_flag
     int* err_flag;
+    unsigned* srcmask;       // ROWS: per combined cell, bit k set <=> source k is occupied there (NULL / more than 32 sources: off)
 };
 
 __device__ __forceinline__ void column_min(int* __restrict__ col, int z) {
@@ -288,7 +318,7 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
             const int stride = O.wait_stride > 0 ? O.wait_stride : 1;
             for (int k = 0; k < O.wait_n; ++k) {
                 const volatile int* f = O.wait_flags + k * stride;
-                while (*f < O.wait_epoch) __nanosleep(100);
+                if (!spin_until(f, O.wait_epoch)) break;
                 // headers carry the origin their rank merged in: all ranks must have used the same frame
                 if (stride == 4 && blockIdx.x == 0 && O.err_flag && f[1] != 0x7fffffff &&
                     (f[1] != O.org[0] || f[2] != O.org[1] || f[3] != O.org[2])) *O.err_flag = 1;
@@ -524,14 +554,14 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
 // MODE as in k_merge_codes: MERGE_FULL (single-GPU combine), MERGE_PARTIAL (a rank's own slots -> encoded grid + record
 // ids; "unknown" is 0 there) and MERGE_FINISH (every rank's encoded grid + previous map -> combined map; optionally only
 // the rows this rank owns, O.row_n > 1; waits for the peers' partial results itself).
-template <int NB, int MODE>
+template <int NB, int MODE, bool MASKS = false>      // MASKS (ROWS only): also record which sources are occupied at every combined cell
 __device__ __forceinline__ void merge_rows_body(const MergeArgs& A, const MergeOut& O, const DevParams& P) {
     if (MODE == MERGE_FINISH && O.wait_flags) {           // device-side barrier of the peer-to-peer exchange (see k_merge_codes)
         if (threadIdx.x == 0) {
             const int stride = O.wait_stride > 0 ? O.wait_stride : 1;
             for (int k = 0; k < O.wait_n; ++k) {
                 const volatile int* f = O.wait_flags + k * stride;
-                while (*f < O.wait_epoch) __nanosleep(100);
+                if (!spin_until(f, O.wait_epoch)) break;
                 if (stride == 4 && blockIdx.x == 0 && O.err_flag && f[1] != 0x7fffffff &&
                     (f[1] != O.org[0] || f[2] != O.org[1] || f[3] != O.org[2])) *O.err_flag = 1;
             }
@@ -578,8 +608,9 @@ __device__ __forceinline__ void merge_rows_body(const MergeArgs& A, const MergeO
         const int z = row / S, y = row - z * S;
         const unsigned old_word = O.gmask[seg];           // what the destination buffer holds here now
         int acc_and[8], sum[8], op[8], enc_or[8];
+        unsigned srcm[8];                                 // ROWS: which sources are occupied at my voxels (for the cell kernel)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc_and[j] = -1; sum[j] = 0; op[j] = -1; enc_or[j] = 0; }
+        for (int j = 0; j < 8; ++j) { acc_and[j] = -1; sum[j] = 0; op[j] = -1; enc_or[j] = 0; srcm[j] = 0u; }
         unsigned seen = 0;                                // any source knows anything in this segment (uniform)
         for (int kb = 0; kb < A.n; kb += 16) {
             const unsigned word = mask_words(seg, kb);
@@ -628,6 +659,10 @@ __device__ __forceinline__ void merge_rows_body(const MergeArgs& A, const MergeO
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { acc_and[j] &= o[u][j]; sum[j] += max(~o[u][j], 0); }
+                        if (MASKS) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) srcm[j] |= (o[u][j] >= 0 ? 1u : 0u) << ((k0 + u) & 31);
+                        }
                     }
                 }
             }
@@ -708,6 +743,7 @@ __device__ __forceinline__ void merge_rows_body(const MergeArgs& A, const MergeO
                     const int id = base + __popc(m[j] & lt);
                     if (id < O.cap) {
                         c[j] = id; O.cell_voxel[id] = seg * 256 + lane * 8 + j;
+                        if (MASKS) O.srcmask[id] = srcm[j];
                         if (z < cur_occ[j]) atomicMin(colo + j, z);
                     } else c[j] = -1;
                 } else if (c[j] < -1) {
@@ -811,7 +847,8 @@ struct NoCellHook { __device__ __forceinline__ void operator()(int, int, int, fl
 template <typename Hook>
 __device__ __forceinline__ void merge_cells2_body(const MergeArgs& A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
                int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
-               float* __restrict__ cmet, float* __restrict__ ceig, const DevParams& P, int cap, const Hook& hook) {
+               float* __restrict__ cmet, float* __restrict__ ceig, const DevParams& P, int cap, const Hook& hook,
+               const unsigned* __restrict__ srcmask = nullptr) {
     const int count = min(*counter, cap);
     const int S = P.S, Z = P.Z;
     constexpr int RB = 8;                                   // sources looked up per round
@@ -823,12 +860,15 @@ __device__ __forceinline__ void merge_cells2_body(const MergeArgs& A, const int*
         for (int k = 0; k < 10; ++k) c[k] = 0.f;
         int hit = 0, tot = 0;
         float mh = 1.0f;
+        // (mirrored multi-GPU combine: the row merge left a mask of the sources that are occupied here -- with 2N + 1
+        // sources most look-ups would find nothing)
+        const unsigned want = srcmask ? srcmask[id] : 0xffffffffu;
         for (int k0 = 0; k0 < A.n; k0 += RB) {
             int io[RB];
 #pragma unroll
             for (int u = 0; u < RB; ++u) {                  // independent index loads first
                 io[u] = -1;
-                if (k0 + u < A.n) {
+                if (k0 + u < A.n && (!srcmask || A.s[k0 + u].is_prev || ((want >> ((k0 + u) & 31)) & 1u))) {
                     const SlotRef& s = A.s[k0 + u];
                     const int xs = x + s.dx, ys = y + s.dy, zs = z + s.dz;
                     if ((unsigned)xs < (unsigned)S && (unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z)
@@ -1232,8 +1272,9 @@ k_rows_columns(const int* __restrict__ cmap, const float* __restrict__ cminh, co
 
 __global__ void __launch_bounds__(1024)
 k_rows_known(const double* __restrict__ height, DevParams P, unsigned* __restrict__ known, unsigned* __restrict__ knownT,
-             const int* __restrict__ wait_flags, int wait_n, int wait_epoch) {
+             const int* __restrict__ wait_flags, int wait_n, int wait_epoch, SignalSet pub) {
     pdl_wait();
+    publish_flag_first_block(pub, wait_epoch);             // (mirrored combine) this rank's heights are pushed: tell every rank
     wait_flags_block(wait_flags, wait_n, wait_epoch);      // every rank has pushed the heights of its rows
     __shared__ unsigned char flag[32][33];
     const int S = P.S;
@@ -1261,8 +1302,9 @@ k_rows_known(const double* __restrict__ height, DevParams P, unsigned* __restric
 struct MapSet { double* maps6; int* pos; int* neg; int* vis; double* rough; };
 __global__ void __launch_bounds__(256)
 k_rows_deliver(const char* __restrict__ blk, PushSet D, int S, MapSet own, MapSet user,
-               const int* __restrict__ wait_flags, int wait_n, int wait_epoch, int m0) {
+               const int* __restrict__ wait_flags, int wait_n, int wait_epoch, int m0, SignalSet pub) {
     pdl_wait();
+    publish_flag_first_block(pub, wait_epoch);             // (mirrored combine) this rank's maps are pushed: tell every rank
     wait_flags_block(wait_flags, wait_n, wait_epoch);
     __shared__ double td[32][33];
     __shared__ int ti[32][33];
@@ -1655,7 +1697,7 @@ __device__ __forceinline__ void slab_wait_and_offsets(const SlabSet& R, const in
         if (wait_flags)
             for (int k = 0; k < R.n; ++k) {
                 const volatile int* f = wait_flags + k;
-                while (*f < epoch) __nanosleep(100);
+                if (!spin_until(f, epoch)) break;
             }
         __threadfence_system();
         int acc = 0;

@@ -140,7 +140,7 @@ __device__ __forceinline__ void mirror_signal(const MirrorSync& Y, int lane) {
 __device__ __forceinline__ void mirror_wait_build(const MirrorSync& Y, MergeArgs& A, int lane) {
     if (lane < Y.n) {
         const volatile int* f = Y.flags + lane;
-        while (*f < Y.epoch) __nanosleep(100);
+        if (!spin_until(f, Y.epoch) && Y.err_flag) *Y.err_flag = 2;     // a rank never arrived: reported by the host
         __threadfence_system();                            // (only the polling lanes: a system-scope fence is not cheap)
     }
     __syncwarp();
@@ -195,11 +195,11 @@ k_mirror_args(const __grid_constant__ MirrorSync Y) {
 // C1 of the mirrored combine: the row merge of the own rows with its source list in device memory (built by
 // k_mirror_args just before).  (Measured and dropped: the flag wait + list build folded into this kernel, every block
 // building the list in shared memory -- one launch less, but 183 us against 177 us per step at 2 ranks.)
-template <int NB>
+template <int NB, bool MASKS>
 __global__ void __launch_bounds__(256, (NB > 3) ? 2 : 3)
 k_merge_rows_ind(const MergeArgs* __restrict__ A, MergeOut O, DevParams P) {
     pdl_wait();
-    merge_rows_body<NB, MERGE_ROWS>(*A, O, P);
+    merge_rows_body<NB, MERGE_ROWS, MASKS>(*A, O, P);
 }
 
 // ---------------------------------------------------------------------------
@@ -232,7 +232,7 @@ k_merge_cells2_rows(const MergeArgs* __restrict__ A, const int* __restrict__ cou
                     float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap,
                     const int* __restrict__ col_occ, const int* __restrict__ col_free, double o0, double o1, double o2,
                     double e0, double e1, double e2, RowShard R, const __grid_constant__ PushSet D, int* __restrict__ map_count,
-                    int* __restrict__ host_count, GridSignal G) {
+                    int* __restrict__ host_count, GridSignal G, const unsigned* __restrict__ srcmask) {
     pdl_wait();
     const int S = P.S;
     const long long S2 = (long long)S * S;
@@ -259,7 +259,7 @@ k_merge_cells2_rows(const MergeArgs* __restrict__ A, const int* __restrict__ cou
         }
     }
     HeightPush hook{col_occ, col_free, D, S2, S, P.Z, o2, P.z_res};
-    merge_cells2_body(*A, counter, cell_voxel, chit, ctot, cminh, cmet, ceig, P, cap, hook);
+    merge_cells2_body(*A, counter, cell_voxel, chit, ctot, cminh, cmet, ceig, P, cap, hook, srcmask);
     signal_when_grid_done(G);                             // heights of this rank's columns are in every rank's block
 }
 

@@ -277,8 +277,12 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
  * builds the source list on the device from the slot table; the single-GPU merge kernels run over the own rows from
  * local memory.  Replaces the roles of gvom.py:242-257 (merge over the whole ring) across GPUs.  blocks[k] = rank k's
  * block as mapped into this process; attach before the first scan and synchronise all ranks (barrier) before any of
- * them scans.  Extra phase bits of gvom_combine_finish_rows() for attached handles: 16 = publish the epoch flag only;
- * 32 (with 1) = do not publish it again (16 for all ranks first, then 1 | 32: one process plays several ranks). */
+ * them scans.  On attached handles the three flags of a combine (epoch / heights / results) are published by the first
+ * block of the kernel that then waits for everybody's, so the producing kernels need no per-block system fence.  Extra
+ * phase bits of gvom_combine_finish_rows() for attached handles: 16 / 64 / 128 = publish the epoch / heights / results
+ * flag only; 32 (with 1) = the epoch flag is already out (also the start-up path of a rank without scans); 256 (with
+ * 2, 4) = the waiting kernels do not publish the heights / results flags (one process playing several ranks calls
+ * 16, 1 | 32, 64, 2 | 256, 128, 4 | 256, each for all ranks in turn). */
 int gvom_mirror_block_size(GvomHandle* h, int32_t nranks, uint64_t* bytes);
 int gvom_mirror_attach(GvomHandle* h, int32_t rank, int32_t nranks, void* const* blocks);
 /* A rank that has not scanned yet takes part in a combine with the origin AND the vehicle position of a rank that has

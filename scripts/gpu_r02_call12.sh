@@ -10,12 +10,12 @@ LOG=gpurun_out/multi_rank_check_r02_mirror_n$N.log
 for spec in "p2p grid256" "p2p grid256 late"; do
   port=$((port+1))
   echo "=== torchrun x$N tests/multi_rank_check.py $spec" >> $LOG
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port tests/multi_rank_check.py $spec 2>&1 | grep -E "MULTI_RANK_OK|Error|error|assert|Traceback" | head -8 >> $LOG
+  timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port tests/multi_rank_check.py $spec 2>&1 | grep -E "MULTI_RANK_OK|Error|error|assert|Traceback" | head -8 >> $LOG
 done
 cat $LOG
 for tag in mirror; do
   port=$((port+1))
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --steps 100 --warmup 20 > gpurun_out/bench_r02_c12_n${N}_$tag.json 2> gpurun_out/bench_r02_c12_n${N}_$tag.err
+  timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --steps 100 --warmup 20 > gpurun_out/bench_r02_c12_n${N}_$tag.json 2> gpurun_out/bench_r02_c12_n${N}_$tag.err
   tail -3 gpurun_out/bench_r02_c12_n${N}_$tag.err
 done
 python - <<PY

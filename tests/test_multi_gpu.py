@@ -238,14 +238,16 @@ def local_exchange_mirror(ranks, epoch, blocks=None):
                 assert o2 is not None and list(o2) == origin
                 check(L.gvom_adopt_ego(g._h, (C.c_double * 3)(*[float(v) for v in ego])), "adopt ego")
     outs = []
-    for phase in (16, 1 | 32, 2, 4):
+    # (every flag is published for all ranks before any rank waits for it: 16 epoch, 64 heights, 128 results; + 32 / 256 = the
+    # waiting kernels do not publish again)
+    for phase in (16, 1 | 32, 64, 2 | 256, 128, 4 | 256):
         for r, g in enumerate(ranks):
             pos, neg, rough, vis = g._out_arrays()
             oo = (C.c_double * 3)()
             check(L.gvom_combine_finish_rows(g._h, o, C.byref(links[r]), epoch, phase, oo, pos.ctypes.data, neg.ctypes.data,
                                              rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None), "rows (mirrored)")
             torch.cuda.synchronize()
-            if phase == 4:
+            if phase & 4:
                 outs.append((np.array(list(oo)), pos, neg, rough, vis))
     return outs, B
 
