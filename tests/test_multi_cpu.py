@@ -218,3 +218,62 @@ def test_plane_sharded_column_exchange_model(nranks):
     assert np.array_equal(pos_model, pos_ref)
     # the scenario exercises both paths: steep cells (100) and density values from the window sums
     assert has.sum() > 20 and (pos_ref == 100).sum() > 0 and ((pos_ref > 0) & ~steep).sum() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Mirrored ring slots (gvom_mirror.cuh): executable model of the push protocol of k_push_scan and of what a rank may
+# read.  numpy only; the CUDA kernels are checked against a single-GPU Gvom in tests/test_multi_gpu.py.
+# ---------------------------------------------------------------------------------------------------------------
+def test_newest_origin_host_logic():
+    from gvom_b200.multi import MIRROR_ENTRY_INTS, newest_origin
+    t = np.zeros((3, 2, MIRROR_ENTRY_INTS), np.int32)
+    assert newest_origin(t) == (None, None)
+    ego = np.array([12.5, -3.25, 1.0])
+    t[1, 0, :5] = [4, 10, 20, -3, 77]
+    t[1, 1, :5] = [5, 11, 21, -3, 80]                       # the newer scan of rank 1
+    t[1, 1, 8:14] = ego.view(np.int32)
+    t[2, 0, :5] = [9, 99, 99, 99, 1]                        # a later rank is not consulted once one is found
+    org, e = newest_origin(t)
+    assert list(org) == [11, 21, -3] and np.array_equal(e, ego)
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_mirror_push_protocol_model(nranks):
+    """One ring slot of one rank, overwritten by a sequence of scans whose origin moves (rows change owner): after
+    every push, every rank's mirror must equal the scan on the rows that rank owns under the scan's origin --
+    the only rows a combine reads -- although nothing is ever cleaned up at ranks that lost a row."""
+    rng = np.random.default_rng(7)
+    S, Z, spr = 256, 4, 1
+    nseg = S * Z * spr
+    mirrors = [np.full((nseg, 256), -1, np.int32) for _ in range(nranks)]       # per rank: map segments of the mirror
+    masks = [np.zeros(nseg, np.uint32) for _ in range(nranks)]
+    held = np.zeros((nranks, nseg), np.uint32)                                  # pusher's memory of what each rank holds
+    seg_row = (np.arange(nseg) // spr) % S
+    oy = 0
+    for step in range(12):
+        oy += int(rng.integers(-2, 3))                                          # the ego moves: ownership shifts
+        scan = np.full((nseg, 256), -1, np.int32)
+        known = rng.random(nseg) < 0.4
+        for s in np.flatnonzero(known):
+            g = rng.integers(0, 32, 3)                                          # a few known 8-voxel groups
+            for gi in g:
+                scan[s, 8 * gi:8 * gi + 8] = rng.integers(-50, 40, 8)
+        word = np.zeros(nseg, np.uint32)
+        for gi in range(32):
+            word |= ((scan[:, 8 * gi:8 * gi + 8] != -1).any(axis=1).astype(np.uint32) << np.uint32(gi))
+        own = (seg_row + oy) % nranks
+        # ---- k_push_scan: only the owner of a row is written; wipe where it holds older codes and the scan knows nothing
+        for s in range(nseg):
+            r = own[s]
+            if word[s] == 0 and held[r, s] == 0:
+                continue
+            mirrors[r][s] = scan[s]
+            masks[r][s] = word[s]
+            held[r, s] = word[s]
+        # ---- what a combine reads: the rows each rank owns under THIS origin
+        for r in range(nranks):
+            mine = own == r
+            assert np.array_equal(mirrors[r][mine], scan[mine]), f"step {step} rank {r}: codes"
+            assert np.array_equal(masks[r][mine], word[mine]), f"step {step} rank {r}: masks"
+        # every segment is owned by exactly one rank
+        assert np.array_equal(np.bincount(own, minlength=nranks).sum(), nseg)
