@@ -102,7 +102,7 @@ enum { EV_START = 0, EV_H2D, EV_POINTS, EV_SCELLS, EV_CSTART, EV_CODES, EV_CELLS
        EV_X0, EV_X1, EV_X2, EV_P0, EV_P1, EV_COUNT };   // EV_X*: extra marks inside the multi-GPU combine
 
 // GVOM_VARIANT bits (environment / gvom_set_variant): A/B switches for measurements; every setting gives the same results
-enum { VAR_GENERIC_MERGE = 2, VAR_ASYNC_ROWS = 4, VAR_NO_SRCMASK = 16, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128 };
+enum { VAR_GENERIC_MERGE = 2, VAR_ASYNC_ROWS = 4, VAR_NO_SRCMASK = 16, VAR_BULK_PUSH = 32, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128 };
 
 }  // namespace
 
@@ -857,6 +857,10 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
         M.entry[1] = fr.io[0]; M.entry[2] = fr.io[1]; M.entry[3] = fr.io[2];
         memcpy(&M.entry[8], ego, 3 * sizeof(double));       // a rank that has not scanned yet adopts origin and ego from here
         rec(h, EV_P0, st);
+        if (h->variant & VAR_BULK_PUSH)
+            launch(k_push_scan_bulk, dim3(h->sm_count * 4), dim3(256), 0, st, (const int*)s.index_map, (const unsigned*)s.gmask, (const int*)s.counter,
+                   (const int*)s.cell_voxel, (const int*)s.hit, (const int*)s.total, (const float*)s.minh, (const double*)s.metrics, M, h->dp, (int)h->cap);
+        else
         launch(k_push_scan, dim3(h->sm_count * 4), dim3(256), 0, st, (const int*)s.index_map, (const unsigned*)s.gmask, (const int*)s.counter,
                (const int*)s.cell_voxel, (const int*)s.hit, (const int*)s.total, (const float*)s.minh, (const double*)s.metrics, M, h->dp, (int)h->cap);
         h->stats.kernel_launches++;

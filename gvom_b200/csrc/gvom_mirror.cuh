@@ -22,6 +22,7 @@
 // the slot's current origin may hold leftovers (the ego moved and the row changed owner); nobody reads them.
 #pragma once
 #include "gvom_kernels.cuh"
+#include "gvom_merge.cuh"      // mbarrier / bulk-copy helpers
 
 namespace gvom {
 
@@ -98,6 +99,109 @@ k_push_scan(const int* __restrict__ map, const unsigned* __restrict__ gmask, con
         }
     }
     // ---- cell records: to the owner of the cell's row, at the cell's own id (the codes in the map rows refer to it)
+    const int count = min(*count_ptr, cap);
+    const int sub = lane & 7;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngroups = (gridDim.x * blockDim.x) >> 3;
+    for (int id = gid; id < count; id += ngroups) {
+        const int v = cell_voxel[id];
+        const int y = P.lgS >= 0 ? (v >> P.lgS) & (S - 1) : (v / S) % S;
+        char* base = M.base[owner_of_row(y, M.oy, M.n)];
+        if (sub < 5) reinterpret_cast<double2*>(base + M.o_met)[(long long)id * 5 + sub] = __ldcg(reinterpret_cast<const double2*>(metrics) + (long long)id * 5 + sub);
+        else if (sub == 5) reinterpret_cast<int*>(base + M.o_hit)[id] = __ldcg(hit + id);
+        else if (sub == 6) reinterpret_cast<int*>(base + M.o_tot)[id] = __ldcg(total + id);
+        else reinterpret_cast<float*>(base + M.o_minh)[id] = __ldcg(minh + id);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_push_scan with the index-map rows moved by the bulk-copy (TMA) engine: a warp's lane 0 asks for the 1 KB segments
+// to be copied HBM -> shared memory (`cp.async.bulk.shared.global`, completion counted in bytes on an mbarrier) and,
+// as each lands, from shared memory straight into the owner's mirror (`cp.async.bulk.global.shared::cta` to the peer
+// address: 1 KB per request on the NVLink side instead of 64 sixteen-byte lane stores).  The (rare) wipes and the
+// cell records use plain stores as in k_push_scan.  Same results; selected by GVOM_VARIANT bit 32.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_push_scan_bulk(const int* __restrict__ map, const unsigned* __restrict__ gmask, const int* __restrict__ count_ptr,
+                 const int* __restrict__ cell_voxel, const int* __restrict__ hit, const int* __restrict__ total,
+                 const float* __restrict__ minh, const double* __restrict__ metrics, const __grid_constant__ MirrorPush M,
+                 DevParams P, int cap) {
+    constexpr int U = 4;
+    __shared__ __align__(128) int buf[8][U][256];           // 4 KB per warp
+    __shared__ unsigned long long bars[8][U];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int S = P.S;
+    const int spr = S >> 8;
+    const int nseg = (int)(P.V >> 8);
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) mbar_init(smem_u32(&bars[wib][u]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x < M.n) {           // slot table: {seq, origin, cells, ego} of this slot, to every rank
+        volatile int* e = reinterpret_cast<volatile int*>(M.base[threadIdx.x] + M.o_entry);
+#pragma unroll
+        for (int k = 1; k < MIRROR_ENTRY; ++k) e[k] = k == 4 ? min(*count_ptr, cap) : M.entry[k];
+        e[0] = M.entry[0];
+    }
+    unsigned parity = 0;
+    for (int s0 = warp * U; s0 < nseg; s0 += nwarps * U) {
+        unsigned nw[U], hw[U];
+        int own[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int seg = s0 + u;
+            nw[u] = 0; hw[u] = 0; own[u] = 0;
+            if (seg < nseg) {
+                own[u] = owner_of_row((seg / spr) % S, M.oy, M.n);
+                nw[u] = __ldcg(gmask + seg);
+                if (nw[u]) {
+                    if (lane == 0) {
+                        const unsigned bar = smem_u32(&bars[wib][u]);
+                        mbar_expect_tx(bar, 1024u);
+                        bulk_g2s(smem_u32(&buf[wib][u][0]), map + (long long)seg * 256, 1024u, bar);
+                    }
+                } else {
+                    hw[u] = M.held[(long long)own[u] * M.nsegp + seg];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int seg = s0 + u;
+            if (seg >= nseg) break;
+            if (nw[u] == 0u && hw[u] == 0u) continue;      // uniform
+            const int r = own[u];
+            if (nw[u]) {
+                if (lane == 0) {
+                    mbar_wait(smem_u32(&bars[wib][u]), parity);
+                    bulk_s2g(M.base[r] + M.o_map + (long long)seg * 1024, smem_u32(&buf[wib][u][0]), 1024u);
+                }
+            } else {                                       // the owner still holds codes of an earlier scan: "unknown" over them
+                int4* dst = reinterpret_cast<int4*>(M.base[r] + M.o_map) + (long long)seg * 64 + lane;
+                const int4 unk = make_int4(-1, -1, -1, -1);
+                dst[0] = unk; dst[32] = unk;
+            }
+            if (lane == 0) {
+                reinterpret_cast<unsigned*>(M.base[r] + M.o_gmask)[seg] = nw[u];
+                M.held[(long long)r * M.nsegp + seg] = nw[u];
+            }
+        }
+        if (lane == 0) {                                   // the staging buffers are reused by the next pass
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
+        parity ^= 1u;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // ---- cell records: to the owner of the cell's row, at the cell's own id
     const int count = min(*count_ptr, cap);
     const int sub = lane & 7;
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngroups = (gridDim.x * blockDim.x) >> 3;
