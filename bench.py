@@ -539,9 +539,8 @@ def main():
                  "peak": hbm, "unit": "GB/s", "frac": step_bytes / (tot_dev / args.steps * 1e-3) / 1e9 / hbm,
                  "note": "SURVEY 8d per-stage bytes summed (cloud, index build, merge, column pass, outputs) / ms_per_step"}
     if multi:
-        # N > 1: the per-rank step is scan + partial merge of the rank's own slots + the row-sharded finish; the
-        # dominant transfers are the rank's own slot maps (partial), 1/N of every rank's encoded grid + previous rows
-        # (finish) and the 2-D pushes -- reported as stage times, the single-GPU kernel rooflines do not apply
+        # N > 1: the per-rank step is scan + push of the scan to the row owners + the combine of the own rows from local
+        # mirrors + the 2-D pushes -- reported as stage times, the single-GPU kernel rooflines do not apply
         step_roof["note"] += "; per rank (weak scaling: the same bytes on every GPU, exchange traffic not counted)"
     traffic = {}
     for k, pref in stage_kernels.items():
@@ -559,7 +558,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": tot_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(world, slots),
-        "io": {"exchange": (getattr(g, "exchange", None) or "") + (" row-sharded finish" if getattr(g, "_rows", False) and getattr(g, "exchange", "") == "p2p" else "") + (", ring slots mirrored at scan time" if getattr(g, "_mirror", False) and getattr(g, "exchange", "") == "p2p" else "") + (" plane-sharded finish" if getattr(g, "_sharded", False) and getattr(g, "exchange", "") == "p2p" else ""),
+        "io": {"exchange": (getattr(g, "exchange", None) or "") + (": ring slots mirrored to the row owners at scan time, row-sharded combine" if getattr(g, "_mirror", False) and getattr(g, "exchange", "") == "p2p" else " (partial merge + replicated finish)" if world > 1 else ""),
                "value": "cloud resident in HBM (float64 Nx3), maps left in HBM in stream order; steps enqueued back to back, CUDA events around both calls of every step on the launching stream (L2 flush between the intervals), summed",
                "e2e": "pinned host float64 Nx3 cloud in, numpy maps out (pinned), per-step wall clock around both calls"},
         "value_p50": world / (statistics.median(ev_dev) * 1e-3),

@@ -38,11 +38,9 @@ MAX_RANKS = 16
 
 
 class GvomRowsLinks(C.Structure):
-    """include/gvom_b200.h: GvomRowsLinks (row-sharded multi-GPU finish)."""
+    """include/gvom_b200.h: GvomRowsLinks (2-D exchange of the mirrored, row-sharded multi-GPU combine)."""
     _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32),
-                ("code_grids", C.c_void_p * MAX_RANKS), ("group_masks", C.c_void_p * MAX_RANKS),
-                ("records", C.c_void_p * MAX_RANKS), ("record_capacity", C.c_int64),
-                ("partial_headers", C.c_void_p), ("blocks2d", C.c_void_p * MAX_RANKS),
+                ("blocks2d", C.c_void_p * MAX_RANKS),
                 ("heights_slots", C.c_void_p * MAX_RANKS), ("heights_flags", C.c_void_p),
                 ("results_slots", C.c_void_p * MAX_RANKS), ("results_flags", C.c_void_p)]
 
@@ -76,11 +74,7 @@ SYMBOLS = {
     "gvom_combine_partial": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _i64, _vp, C.POINTER(_vp), _i32, _i32, _vp]),
     "gvom_combine_finish": (C.c_int, [_vp, _pd, C.POINTER(_vp), C.POINTER(_vp), _i32, C.POINTER(_vp), C.POINTER(_vp), _i32, _i64, _vp, _i32, _pd,
                                       _vp, _vp, _vp, _vp, _i32, _vp]),
-    "gvom_combine_finish_sharded": (C.c_int, [_vp, _pd, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i64, _vp,
-                                              C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, C.POINTER(_vp), _vp, _i32, _i32,
-                                              _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gvom_rows_block_size": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
-    "gvom_combine_partial_header": (C.c_int, [_vp, _pd, _vp, _vp, _vp, _i64, _vp, C.POINTER(_vp), _i32, _i32, _vp]),
     "gvom_combine_finish_rows": (C.c_int, [_vp, _pd, C.POINTER(GvomRowsLinks), _i32, _i32, _pd, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gvom_mirror_block_size": (C.c_int, [_vp, _i32, C.POINTER(C.c_uint64)]),
     "gvom_mirror_attach": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),

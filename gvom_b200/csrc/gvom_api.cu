@@ -156,7 +156,7 @@ struct GvomHandle {
     cudaEvent_t ev[EV_COUNT];
     bool profiling = false;
     bool zero_copy = true;                // host clouds: S1 reads pinned memory directly (else chunked DMA)
-    bool prof_process = false, prof_combine = false, prof_x = false, prof_partial = false, prof_rows = false;
+    bool prof_process = false, prof_combine = false, prof_partial = false, prof_rows = false;
     int sm_count = 148;
     int grid_codes = 0, grid_cells = 0, grid_cells2 = 0, grid_rows3 = 0, grid_scan_cells = 0, grid_rows_mirror = 0, grid_rows_async[2] = {0, 0};   // resident grids (set at create)
     GvomStats stats{};
@@ -164,7 +164,6 @@ struct GvomHandle {
     CopyPool* pool = nullptr;             // staging threads for pageable input (created on first use)
     signed char* grids_dev = nullptr;     // [GVOM_GRID_COUNT][S*S] int8 OccupancyGrid payloads
     signed char* grids_host = nullptr;    // pinned mirror
-    int gather_blocks = 8;                // blocks per SM of the sharded finish's assembly kernels (GVOM_GATHER_BLOCKS)
     int host_chunks = 4;                  // pieces a large pageable / PointCloud2 host cloud is staged in (GVOM_CHUNKS), pipelined with S1
     unsigned variant = 0;                 // GVOM_VARIANT bit mask (A/B switches, see VAR_*)
     // outputs of the last combine that still have to be completed on the host (gvom_combine_maps_async)
@@ -566,12 +565,11 @@ int gvom_create(const GvomParams* p, int64_t max_points, int64_t max_combined_ce
         h->grid_codes = v8 ? resident_grid(k_merge_codes<8, MERGE_FINISH>, 256, h->sm_count)
                            : s4 ? resident_grid(k_merge_codes<4, MERGE_FINISH>, 256, h->sm_count)
                                 : resident_grid(k_merge_codes<1, MERGE_FINISH>, 256, h->sm_count);
-        h->grid_cells = resident_grid(k_slab_cells, 128, h->sm_count);
+        h->grid_cells = resident_grid(k_finish_cells, 128, h->sm_count);
         h->grid_cells2 = resident_grid(k_merge_cells2, 128, h->sm_count);
         h->grid_scan_cells = (p->xy_eigen_dist == 1 && p->z_eigen_dist == 1) ? resident_grid(k_scan_cells<1, 1>, 256, h->sm_count)
                                                                              : resident_grid(k_scan_cells<-1, -1>, 256, h->sm_count);
         if (const char* m = getenv("GVOM_VARIANT")) h->variant = (unsigned)strtoul(m, nullptr, 0);
-        if (const char* m = getenv("GVOM_GATHER_BLOCKS")) h->gather_blocks = std::max(1, std::min(8, atoi(m)));
         if (const char* m = getenv("GVOM_CHUNKS")) h->host_chunks = std::max(1, std::min(16, atoi(m)));
         h->grid_rows3 = std::min(resident_grid(k_merge_rows<3, MERGE_FULL>, 256, h->sm_count),
                                  std::min(resident_grid(k_merge_rows<3, MERGE_PARTIAL>, 256, h->sm_count),
@@ -1205,19 +1203,13 @@ int gvom_stage_times(GvomHandle* h, float ms[16]) {
         CUDA_TRY(cudaEventElapsedTime(&ms[2], h->ev[EV_POINTS], h->ev[EV_SCELLS]));
     }
     ms[9] = h->last_stage_copy_ms;
-    if (h->prof_x) {   // sharded multi-GPU combine: [10] slab cells, [11] signal + wait + gather maps, [12] gather cells
-        CUDA_TRY(cudaEventElapsedTime(&ms[10], h->ev[EV_CODES], h->ev[EV_X0]));
-        CUDA_TRY(cudaEventElapsedTime(&ms[11], h->ev[EV_X0], h->ev[EV_X1]));
-        CUDA_TRY(cudaEventElapsedTime(&ms[12], h->ev[EV_X1], h->ev[EV_CELLS]));
-    }
-    if (h->prof_partial) CUDA_TRY(cudaEventElapsedTime(&ms[13], h->ev[EV_P0], h->ev[EV_P1]));   // multi-GPU: partial merge + cells
-    if (h->prof_rows) {    // row-sharded finish: [5] wait + own rows, [6] own cells, [7] = [14] columns + [15] wait + surface, [8] wait + deliver
+    if (h->prof_partial) CUDA_TRY(cudaEventElapsedTime(&ms[13], h->ev[EV_P0], h->ev[EV_P1]));   // multi-GPU: push of the scan (mirrored) or partial merge + cells (generic)
+    if (h->prof_rows) {    // mirrored combine: [5] flag exchange + own rows, [6] own cells + heights, [15] wait + bit maps + surface, [8] wait + deliver
         CUDA_TRY(cudaEventElapsedTime(&ms[5], h->ev[EV_CSTART], h->ev[EV_CODES]));
         CUDA_TRY(cudaEventElapsedTime(&ms[6], h->ev[EV_CODES], h->ev[EV_CELLS]));
-        CUDA_TRY(cudaEventElapsedTime(&ms[14], h->ev[EV_CELLS], h->ev[EV_X0]));
-        CUDA_TRY(cudaEventElapsedTime(&ms[15], h->ev[EV_X0], h->ev[EV_X1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[15], h->ev[EV_CELLS], h->ev[EV_X1]));
         CUDA_TRY(cudaEventElapsedTime(&ms[8], h->ev[EV_X1], h->ev[EV_D2H]));
-        ms[7] = ms[14] + ms[15];
+        ms[7] = ms[15];
     }
     if (h->prof_combine) {
         const int a[4] = {EV_CSTART, EV_CODES, EV_CELLS, EV_MAPS};
@@ -1550,7 +1542,7 @@ int gvom_newest_origin(GvomHandle* h, double origin[3]) {
 
 static int combine_partial_impl(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, uint32_t* group_mask_dev,
                                 float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
-                                int32_t* const* signal_slots, int32_t n_signal, int32_t epoch, bool header, void* stream) {
+                                int32_t* const* signal_slots, int32_t n_signal, int32_t epoch, void* stream) {
     if (!h || !origin || !code_grid_dev || !records_dev || !record_count_dev) return fail(GVOM_EINVAL, "NULL argument");
     if (record_capacity < 1 || record_capacity > 2147483647LL) return fail(GVOM_EINVAL, "bad record capacity");
     std::lock_guard<std::mutex> lock(h->mu);
@@ -1572,8 +1564,6 @@ static int combine_partial_impl(GvomHandle* h, const double origin[3], int32_t* 
         G.S.n = n_signal;
         for (int k = 0; k < n_signal; ++k) G.S.slot[k] = signal_slots[k];
         G.counter = h->flags + 9; G.epoch = epoch;
-        G.header = header ? 1 : 0;                 // {epoch, origin}: the finishing ranks verify that everybody merged in the same frame
-        G.ox = (int)origin[0]; G.oy = (int)origin[1]; G.oz = (int)origin[2];
     }
     launch(k_partial_cells, dim3(h->grid_cells), dim3(128), 0, st, A, record_count_dev, records_dev, h->dp, (int)record_capacity, G);
     h->stats.kernel_launches += 1;
@@ -1587,14 +1577,7 @@ int gvom_combine_partial(GvomHandle* h, const double origin[3], int32_t* code_gr
                          float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
                          int32_t* const* signal_slots, int32_t n_signal, int32_t epoch, void* stream) {
     return combine_partial_impl(h, origin, code_grid_dev, group_mask_dev, records_dev, record_capacity, record_count_dev,
-                                signal_slots, n_signal, epoch, false, stream);
-}
-
-int gvom_combine_partial_header(GvomHandle* h, const double origin[3], int32_t* code_grid_dev, uint32_t* group_mask_dev,
-                                float* records_dev, int64_t record_capacity, int32_t* record_count_dev,
-                                int32_t* const* header_slots, int32_t n_signal, int32_t epoch, void* stream) {
-    return combine_partial_impl(h, origin, code_grid_dev, group_mask_dev, records_dev, record_capacity, record_count_dev,
-                                header_slots, n_signal, epoch, true, stream);
+                                signal_slots, n_signal, epoch, stream);
 }
 
 int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* const* code_grids,
@@ -1765,11 +1748,11 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
     if (h->p.xy_size % 256 != 0) return fail(GVOM_EINVAL, "row-sharded finish needs xy_size % 256 == 0");
     if (out_mem != GVOM_HOST && out_mem != GVOM_DEVICE && out_mem != GVOM_NONE) return fail(GVOM_EINVAL, "bad out_mem");
     const bool mirrored = h->mir.n > 0;
-    if (mirrored && (h->mir.n != N || h->mir.self != me)) return fail(GVOM_EINVAL, "links disagree with gvom_mirror_attach");
+    if (!mirrored) return fail(GVOM_EINVAL, "gvom_combine_finish_rows needs gvom_mirror_attach() first");
+    if (h->mir.n != N || h->mir.self != me) return fail(GVOM_EINVAL, "links disagree with gvom_mirror_attach");
     for (int k = 0; k < N; ++k)
-        if ((!mirrored && (!K->code_grids[k] || !K->group_masks[k] || !K->records[k])) || !K->blocks2d[k] || !K->heights_slots[k] || !K->results_slots[k])
-            return fail(GVOM_EINVAL, "NULL rank buffer");
-    if ((!mirrored && !K->partial_headers) || !K->heights_flags || !K->results_flags) return fail(GVOM_EINVAL, "NULL flag table");
+        if (!K->blocks2d[k] || !K->heights_slots[k] || !K->results_slots[k]) return fail(GVOM_EINVAL, "NULL rank buffer");
+    if (!K->heights_flags || !K->results_flags) return fail(GVOM_EINVAL, "NULL flag table");
     std::lock_guard<std::mutex> lock(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
@@ -1867,67 +1850,6 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
                    c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1], h->ego[2], R, D, c.counter, host_count, G, srcmask);
         }
         rec(h, EV_CELLS, st);
-        rec(h, EV_X0, st);
-        h->stats.kernel_launches += 3;
-        h->prof_combine = false;
-        CUDA_TRY(cudaGetLastError());
-    } else if (phases & 1) {
-        if (int e = finish_outputs(h)) return e;
-        for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];
-        MergeArgs A;
-        A.n = 0; A.use_masks = 1;
-        RankBufs B; B.n = N;
-        for (int k = 0; k < N; ++k) {
-            SlotRef& r = A.s[A.n++];
-            r = SlotRef{};
-            r.map = K->code_grids[k]; r.gmask = K->group_masks[k];
-            B.grid[k] = K->code_grids[k]; B.rec[k] = K->records[k];
-        }
-        SlotRef prev{};
-        const int has_prev = pc.valid ? 1 : 0;
-        if (has_prev) {
-            prev.map = pc.index_map; prev.metrics = pc.metrics; prev.hit = pc.hit; prev.total = pc.total; prev.minh = pc.minh;
-            prev.dx = (int)(origin[0] - pc.origin[0]); prev.dy = (int)(origin[1] - pc.origin[1]); prev.dz = (int)(origin[2] - pc.origin[2]);
-            prev.is_prev = 1;
-            prev.gmask = pc.has_gmask ? pc.gmask : nullptr;
-            if (!prev.gmask) A.use_masks = 0;
-            A.s[A.n++] = prev;
-        }
-        rec(h, EV_CSTART, st);
-        {
-            MergeOut O{};
-            O.cmap = c.index_map; O.counter = h->flags + 8; O.cell_voxel = c.cell_voxel;
-            O.col_occ = h->col_minz; O.col_free = h->col_minz + S2;
-            O.gmask = c.gmask; O.cap = (int)h->ccap;
-            O.wait_flags = K->partial_headers; O.wait_n = N; O.wait_epoch = epoch; O.wait_stride = 4;
-            O.org[0] = (int)origin[0]; O.org[1] = (int)origin[1]; O.org[2] = (int)origin[2];
-            void* m = nullptr;
-            if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) O.err_flag = (int*)m + 1; else cudaGetLastError();
-            h->counters_host[1] = 0;
-            O.row_y0 = R.y0; O.row_n = N;
-            launch_merge<MERGE_FINISH>(h, A, O, st, std::max(1, N / 2));
-        }
-        rec(h, EV_CODES, st);
-        {
-            SlabCells out{c.hit, c.total, c.minh, c.cell_voxel, c.metrics, c.eig};
-            SignalSet none{};
-            launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 8, out, none, h->dp,
-                   (int)h->ccap, (int)K->record_capacity);
-        }
-        rec(h, EV_CELLS, st);
-        {
-            int* host_count = nullptr;
-            void* m = nullptr;
-            if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) host_count = (int*)m; else cudaGetLastError();
-            GridSignal G{};
-            G.S.n = N;
-            for (int k = 0; k < N; ++k) G.S.slot[k] = K->heights_slots[k];
-            G.counter = h->flags + 10; G.epoch = epoch;
-            launch(k_rows_columns, dim3(blocks_for((int64_t)S * R.nrows + 1, 256)), dim3(256), 0, st, c.index_map, c.minh, h->col_minz,
-                   h->col_minz + S2, c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1], h->ego[2], h->dp, R, D,
-                   h->flags + 8, c.counter, host_count, G);
-        }
-        rec(h, EV_X0, st);
         h->stats.kernel_launches += 3;
         h->prof_combine = false;
         CUDA_TRY(cudaGetLastError());
@@ -2016,104 +1938,5 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
     return GVOM_OK;
 }
 
-
-// Sharded finish of the peer-to-peer exchange.  Rank `rank` of `nranks`:
-//   1. merges the z-planes it owns (z % nranks == rank) from every rank's encoded grid + its (replicated) copy of
-//      the previous combined map                        -> res_map (own planes), local cell ids
-//   2. folds the ranks' records of those cells (found through the record ids in the grids) + previous map, eigenvalues
-//                                                       -> res_cells, res_count;  signals "slab done"
-//   3. waits for every rank's slab, assembles the full combined map / cell arrays (ids rebased), column minima, group
-//      mask; then the 2-D stage and the outputs as in the single-GPU combine.
-int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t rank, int32_t nranks,
-                                const int32_t* const* code_grids, const uint32_t* const* group_masks,
-                                const float* const* records, int64_t record_capacity,
-                                const int32_t* wait_partial, int32_t* const* res_maps, void* const* res_cells,
-                                int32_t* const* count_slots, const int32_t* count_table, int64_t res_capacity,
-                                int32_t* const* signal_slab, const int32_t* wait_slab, int32_t epoch, int32_t phases,
-                                double origin_out[3], int32_t* positive, int32_t* negative, double* roughness,
-                                int32_t* visibility, int32_t out_mem, void* stream) {
-    if (!h || !origin || !code_grids || !records || !res_maps || !res_cells || !count_slots || !count_table || !signal_slab)
-        return fail(GVOM_EINVAL, "NULL argument");
-    if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return fail(GVOM_EINVAL, "bad rank / nranks");
-    if (h->p.xy_size % 8 != 0 || (((int64_t)h->p.xy_size * h->p.xy_size / 8) % 32) != 0)
-        return fail(GVOM_EINVAL, "sharded finish needs xy_size % 16 == 0");
-    if (res_capacity < 1 || res_capacity > 2147483647LL) return fail(GVOM_EINVAL, "bad result capacity");
-    std::lock_guard<std::mutex> lock(h->mu);
-    CUDA_TRY(cudaSetDevice(h->device));
-    if (int e = finish_outputs(h)) return e;
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    h->active = st;
-    rec(h, EV_CSTART, st);
-    Combined& pc = h->comb[h->cur];
-    Combined& c = h->comb[1 - h->cur];
-    for (int k = 0; k < 3; ++k) c.origin[k] = origin[k];
-
-    MergeArgs A;
-    A.n = 0; A.use_masks = 1;
-    RankBufs B; B.n = nranks;
-    SlabSet R; R.n = nranks; R.counts = count_table;
-    for (int k = 0; k < nranks; ++k) {
-        if (!code_grids[k] || !records[k] || !res_maps[k] || !res_cells[k] || !count_slots[k]) return fail(GVOM_EINVAL, "NULL rank buffer");
-        SlotRef& r = A.s[A.n++];
-        r = SlotRef{};
-        r.map = code_grids[k];
-        r.gmask = group_masks ? group_masks[k] : nullptr;
-        if (!r.gmask) A.use_masks = 0;
-        B.grid[k] = code_grids[k]; B.rec[k] = records[k];
-        R.map[k] = res_maps[k]; R.cells[k] = res_cells[k];
-    }
-    SlotRef prev{};
-    const int has_prev = pc.valid ? 1 : 0;
-    if (has_prev) {
-        prev.map = pc.index_map; prev.metrics = pc.metrics; prev.hit = pc.hit; prev.total = pc.total; prev.minh = pc.minh;
-        prev.dx = (int)(origin[0] - pc.origin[0]); prev.dy = (int)(origin[1] - pc.origin[1]); prev.dz = (int)(origin[2] - pc.origin[2]);
-        prev.is_prev = 1;
-        prev.gmask = pc.has_gmask ? pc.gmask : nullptr;
-        if (!prev.gmask) A.use_masks = 0;
-        A.s[A.n++] = prev;
-    }
-    const SlabCells mine = slab_cells_at(res_cells[rank], res_capacity);
-    if (phases & 1) {   // 1. my planes
-        MergeOut O{};
-        O.cmap = res_maps[rank]; O.counter = h->flags + 8; O.cell_voxel = mine.voxel;
-        O.cap = (int)res_capacity;
-        O.wait_flags = wait_partial; O.wait_n = nranks; O.wait_epoch = epoch;
-        O.slab_r = rank; O.slab_n = nranks;
-        launch(k_merge_codes<8, MERGE_FINISH>, dim3(std::max(1, h->grid_codes / std::max(1, nranks / 2))), dim3(256), 0, st, A, O, h->dp);
-    rec(h, EV_CODES, st);
-    // 2. my cells
-    {
-        SignalSet CS; CS.n = nranks;
-        for (int k = 0; k < nranks; ++k) CS.slot[k] = count_slots[k];
-        launch(k_slab_cells, dim3(h->grid_cells), dim3(128), 0, st, B, prev, has_prev, h->flags + 8, mine, CS, h->dp,
-               (int)res_capacity, (int)record_capacity);
-    }
-    rec(h, EV_X0, st);
-    {
-        SignalSet S; S.n = nranks;
-        for (int k = 0; k < nranks; ++k) S.slot[k] = signal_slab[k];
-        launch(k_signal, dim3(1), dim3(32), 0, st, S, (int)epoch);
-    }
-    h->stats.kernel_launches += 3;
-    }
-    if (!(phases & 2)) { CUDA_TRY(cudaGetLastError()); return GVOM_OK; }
-    // 3. everybody's planes and cells
-    launch(k_gather_maps, dim3(h->sm_count * h->gather_blocks), dim3(256), 0, st, R, wait_slab, (int)epoch, c.index_map, c.gmask, h->col_minz,
-           h->col_minz + h->S2, h->flags + 8, h->dp);
-    rec(h, EV_X1, st);
-    launch(k_gather_cells, dim3(h->sm_count * h->gather_blocks), dim3(256), 0, st, R, (long long)res_capacity, c.hit, c.total, c.minh, c.metrics,
-           c.eig, c.cell_voxel, (int)h->ccap);
-    rec(h, EV_CELLS, st);
-    h->stats.kernel_launches += 2;
-    h->prof_combine = h->profiling;
-    h->prof_x = h->profiling && (phases == 3);
-    c.has_gmask = true;
-    const int r = run_maps_and_output(h, c, origin_out, positive, negative, roughness, visibility, out_mem, st);
-    if (r != GVOM_OK) return r;
-    c.valid = true;
-    h->cur = 1 - h->cur;
-    h->stats.combine_calls++;
-    return GVOM_OK;
-}
 
 }  // extern "C"

@@ -66,9 +66,9 @@ constexpr int MAX_RANKS = 16;
 struct SignalSet { int* slot[MAX_RANKS]; int n; };   // one flag slot per rank (this rank's slot in every rank's memory)
 
 // "The whole grid is done" signal folded into the producing kernel (saves a launch per barrier): every block makes its
-// writes visible system-wide and counts itself in; the last one publishes the epoch into every rank's slot (header
-// slots: the origin first) and resets the counter for the next launch.  Every thread of the block must call it.
-struct GridSignal { SignalSet S; int* counter; int epoch; int header; int ox, oy, oz; };
+// writes visible system-wide and counts itself in; the last one publishes the epoch into every rank's slot
+// and resets the counter for the next launch.  Every thread of the block must call it.
+struct GridSignal { SignalSet S; int* counter; int epoch; };
 __device__ __forceinline__ void signal_when_grid_done(const GridSignal& G) {
     if (G.S.n == 0) return;
     __syncthreads();                                      // the block's writes happen before thread 0's fence (cumulativity)
@@ -78,11 +78,6 @@ __device__ __forceinline__ void signal_when_grid_done(const GridSignal& G) {
         if (atomicAdd(G.counter, 1) == nblocks - 1) {
             *G.counter = 0;
             __threadfence();
-            for (int k = 0; k < G.S.n; ++k) {
-                volatile int* f = G.S.slot[k];
-                if (G.header) { f[1] = G.ox; f[2] = G.oy; f[3] = G.oz; }
-            }
-            __threadfence_system();
             for (int k = 0; k < G.S.n; ++k) { volatile int* f = G.S.slot[k]; f[0] = G.epoch; }
             __threadfence_system();
         }
@@ -262,12 +257,7 @@ struct MergeOut {
     int cap;
     const int* wait_flags;   // FINISH, peer-to-peer: flags[k] >= wait_epoch once rank k's partial results are visible
     int wait_n, wait_epoch;
-    int slab_r, slab_n;      // FINISH, sharded: this rank finishes the z-planes with z % slab_n == slab_r (slab_n <= 1: all)
-    int row_y0, row_n;       // FINISH, row-sharded: this rank finishes the rows y = row_y0, row_y0 + row_n, ... of every plane
-                             // (row_n <= 1: all); needs S % (32 VEC) == 0 so that a warp never straddles two rows
-    int wait_stride;         // ints between two ranks' flags (1: plain flags, 4: {epoch, ox, oy, oz} headers)
-    int org[3];              // wait_stride == 4: the origin this rank merges in; a peer header that disagrees raises *err_flag
-    int* err_flag;
+    int row_y0, row_n;       // ROWS: this rank merges the rows y = row_y0, row_y0 + row_n, ... of every plane (row_n <= 1: all)
     unsigned* srcmask;       // ROWS: per combined cell, bit k set <=> source k is occupied there (NULL / more than 32 sources: off)
 };
 
@@ -315,14 +305,8 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
         // until all ranks have published this combine's partial results (their signal kernel wrote the epoch
         // into OUR flag slots after a system-scope fence), then reads the peers' grids over NVLink.
         if (threadIdx.x == 0) {
-            const int stride = O.wait_stride > 0 ? O.wait_stride : 1;
-            for (int k = 0; k < O.wait_n; ++k) {
-                const volatile int* f = O.wait_flags + k * stride;
-                if (!spin_until(f, O.wait_epoch)) break;
-                // headers carry the origin their rank merged in: all ranks must have used the same frame
-                if (stride == 4 && blockIdx.x == 0 && O.err_flag && f[1] != 0x7fffffff &&
-                    (f[1] != O.org[0] || f[2] != O.org[1] || f[3] != O.org[2])) *O.err_flag = 1;
-            }
+            for (int k = 0; k < O.wait_n; ++k)
+                if (!spin_until(O.wait_flags + k, O.wait_epoch)) break;
             __threadfence_system();
         }
         __syncthreads();
@@ -331,25 +315,11 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
     const unsigned lt = (1u << lane) - 1u;
     const long long step = (long long)gridDim.x * blockDim.x;
     const int S = P.S, Z = P.Z;
-    // sharded finish: only the z-planes this rank owns (interleaved: z % slab_n == slab_r, so the few ground
-    // planes that hold most cells spread over all ranks); QP = items per plane
-    const bool slab = MODE == MERGE_FINISH && O.slab_n > 1;
-    const bool rslab = MODE == MERGE_FINISH && O.row_n > 1;
-    const long long QP = ((long long)S * S) / VEC;
-    const int RQ = S / VEC;                                   // items per row
-    const int my_rows = (rslab && O.row_y0 < S) ? (S - O.row_y0 + O.row_n - 1) / O.row_n : 0;
-    const int my_planes = slab ? (Z - O.slab_r + O.slab_n - 1) / O.slab_n : Z;
-    const long long NQ = rslab ? (long long)Z * my_rows * RQ : slab ? my_planes * QP : P.V / VEC;
+    const long long NQ = P.V / VEC;
     const long long NQp = (NQ + 31) & ~31LL;
     const int has_prev = (A.n > 0 && A.s[A.n - 1].is_prev) ? 1 : 0;
     for (long long ql = (long long)blockIdx.x * blockDim.x + threadIdx.x; ql < NQp; ql += step) {
-        // local item -> global item (warp-uniform plane: QP is a multiple of 32 in slab mode)
-        long long q = slab ? ((long long)O.slab_r + (long long)O.slab_n * (ql / QP)) * QP + ql % QP : ql;
-        if (rslab) {                                          // local row counter -> (z, own row) -> global item
-            const int jr = (int)(ql / RQ), xi = (int)(ql - (long long)jr * RQ);
-            const int zz = jr / max(my_rows, 1), yi = jr - zz * my_rows;
-            q = ((long long)zz * S + (O.row_y0 + O.row_n * yi)) * RQ + xi;
-        }
+        const long long q = ql;
         const bool live = ql < NQ;
         int acc_and[VEC], sum[VEC], enc_or[VEC];
 #pragma unroll
@@ -552,19 +522,14 @@ k_merge_codes(MergeArgs A, MergeOut O, DevParams P) {
 //     unknown with an empty mask, and every writer keeps map and mask consistent).
 // ---------------------------------------------------------------------------
 // MODE as in k_merge_codes: MERGE_FULL (single-GPU combine), MERGE_PARTIAL (a rank's own slots -> encoded grid + record
-// ids; "unknown" is 0 there) and MERGE_FINISH (every rank's encoded grid + previous map -> combined map; optionally only
-// the rows this rank owns, O.row_n > 1; waits for the peers' partial results itself).
+// ids; "unknown" is 0 there), MERGE_FINISH (every rank's encoded grid + previous map -> combined map; waits for the peers'
+// partial results itself) and MERGE_ROWS (mirrored multi-GPU combine: MERGE_FULL on the rows this rank owns).
 template <int NB, int MODE, bool MASKS = false>      // MASKS (ROWS only): also record which sources are occupied at every combined cell
 __device__ __forceinline__ void merge_rows_body(const MergeArgs& A, const MergeOut& O, const DevParams& P) {
     if (MODE == MERGE_FINISH && O.wait_flags) {           // device-side barrier of the peer-to-peer exchange (see k_merge_codes)
         if (threadIdx.x == 0) {
-            const int stride = O.wait_stride > 0 ? O.wait_stride : 1;
-            for (int k = 0; k < O.wait_n; ++k) {
-                const volatile int* f = O.wait_flags + k * stride;
-                if (!spin_until(f, O.wait_epoch)) break;
-                if (stride == 4 && blockIdx.x == 0 && O.err_flag && f[1] != 0x7fffffff &&
-                    (f[1] != O.org[0] || f[2] != O.org[1] || f[3] != O.org[2])) *O.err_flag = 1;
-            }
+            for (int k = 0; k < O.wait_n; ++k)
+                if (!spin_until(O.wait_flags + k, O.wait_epoch)) break;
             __threadfence_system();
         }
         __syncthreads();
@@ -573,7 +538,7 @@ __device__ __forceinline__ void merge_rows_body(const MergeArgs& A, const MergeO
     const unsigned lt = (1u << lane) - 1u;
     const int S = P.S, Z = P.Z;
     const int spr = S >> 8;                               // segments per row
-    const bool rslab = (MODE == MERGE_FINISH || MODE == MERGE_ROWS) && O.row_n > 1;
+    const bool rslab = MODE == MERGE_ROWS && O.row_n > 1;
     const int my_rows = rslab ? (O.row_y0 < S ? (S - O.row_y0 + O.row_n - 1) / O.row_n : 0) : S;
     const int nseg = rslab ? Z * my_rows * spr : (int)(P.V >> 8);
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -1231,45 +1196,8 @@ k_surface_maps2(const int* __restrict__ cmap, const int* __restrict__ chit, cons
 
 // ---------------------------------------------------------------------------
 // Row-sharded multi-GPU combine, 2-D stage helpers.
-//   k_rows_columns   C3 for the rows this rank owns: heights from its (complete) column minima, pushed into every
-//                    rank's 2-D block; publishes the rank's cell count
 //   k_rows_known     after the height barrier: the "height known" bit maps of the WHOLE map (every rank builds its own)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_rows_columns(const int* __restrict__ cmap, const float* __restrict__ cminh, const int* __restrict__ col_occ,
-               const int* __restrict__ col_free, double o0, double o1, double o2, double e0, double e1, double e2,
-               DevParams P, RowShard R, PushSet D, const int* __restrict__ scratch_count, int* __restrict__ map_count,
-               int* __restrict__ host_count, GridSignal G) {
-    pdl_wait();
-    const int S = P.S;
-    const long long S2 = (long long)S * S;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) {
-        const int n = *scratch_count;
-        *map_count = n;
-        if (host_count) *host_count = n;
-    }
-    if (t < S * R.nrows) {
-    const int x = t % S, y = R.y0 + R.n * (t / S);        // x fastest: the column minima are [y][x]
-    double h = -1000.0, inf = -1000.0;
-    const double xp = __fma_rn(__dadd_rn(o0, (double)x), P.xy_res, -e0);
-    const double yp = __fma_rn(__dadd_rn(o1, (double)y), P.xy_res, -e1);
-    if (__fma_rn(xp, xp, __dmul_rn(yp, yp)) <= P.r2) h = __dsub_rn(e2, P.ground_to_lidar);
-    const int zo = col_occ[(long long)y * S + x], zf = col_free[(long long)y * S + x];
-    if (zo < P.Z) {
-        const int idx = cmap[x + (long long)y * S + zo * S2];
-        h = __dmul_rn(__dadd_rn(__dadd_rn((double)zo, (double)cminh[idx]), o2), P.z_res);
-    }
-    if (zf < P.Z) inf = __dmul_rn(__dadd_rn(o2, (double)zf), P.z_res);
-    const long long ci = (long long)y * S + x;             // the exchange block is [y][x]: a rank's rows are contiguous
-    for (int d = 0; d < D.n; ++d) {                        // own copy included
-        double* m = reinterpret_cast<double*>(D.base[d] + D.off_maps);
-        m[ci] = h; m[S2 + ci] = inf;
-    }
-    }
-    signal_when_grid_done(G);                             // heights of this rank's columns are in every rank's block
-}
-
 __global__ void __launch_bounds__(1024)
 k_rows_known(const double* __restrict__ height, DevParams P, unsigned* __restrict__ known, unsigned* __restrict__ knownT,
              const int* __restrict__ wait_flags, int wait_n, int wait_epoch, SignalSet pub) {
@@ -1466,18 +1394,6 @@ __global__ void k_debug_height(const double* __restrict__ height, const double* 
 struct RecordSet { const float* r[MAX_RANKS]; const int* count[MAX_RANKS]; int n; };
 
 // header variant: {epoch, ox, oy, oz} -- the origin first, then (after a fence) the epoch the waiters poll
-__global__ void k_signal_header(SignalSet S, int epoch, int ox, int oy, int oz) {
-    pdl_wait();
-    __threadfence_system();
-    if (threadIdx.x < S.n) {
-        volatile int* f = S.slot[threadIdx.x];
-        f[1] = ox; f[2] = oy; f[3] = oz;
-        __threadfence_system();
-        f[0] = epoch;
-    }
-    __threadfence_system();
-}
-
 // publish "my partial results of combine `epoch` are complete" into every rank's flag slot for this rank
 __global__ void k_signal(SignalSet S, int epoch) {
     pdl_wait();                                   // after this rank's partial kernels
@@ -1602,181 +1518,6 @@ k_finish_cells(SlotRef prev, int has_prev, const int* __restrict__ counter, cons
     }
 }
 
-
-// ===========================================================================
-// sharded finish (peer-to-peer exchange): rank r finishes only its z-planes, then every rank
-// assembles the full combined map from all ranks' results.  Per-rank finishing work is V/N.
-// ===========================================================================
-struct RankBufs {                 // every rank's partial results as seen from here (own HBM or NVLink-mapped)
-    const int* grid[MAX_RANKS];   // encoded grid: OCC_FLAG | record id, or summed passes
-    const float* rec[MAX_RANKS];  // records [*, REC]
-    int n;
-};
-
-// result of a rank's slab, struct of arrays with `cap` rows, living in symmetric memory
-struct SlabCells {
-    int* hit; int* tot; float* minh; int* voxel; float* met; float* eig;
-};
-__host__ __device__ inline SlabCells slab_cells_at(void* base, long long cap) {
-    SlabCells c;
-    char* b = static_cast<char*>(base);
-    c.hit = reinterpret_cast<int*>(b);
-    c.tot = reinterpret_cast<int*>(b + 4 * cap);
-    c.minh = reinterpret_cast<float*>(b + 8 * cap);
-    c.voxel = reinterpret_cast<int*>(b + 12 * cap);
-    c.met = reinterpret_cast<float*>(b + 16 * cap);
-    c.eig = reinterpret_cast<float*>(b + 56 * cap);
-    return c;
-}
-constexpr int SLAB_CELL_BYTES = 68;
-
-// per cell of this rank's slab: fold every rank's record of that voxel (rank order), then the previous
-// combined map, then the eigenvalues -- the multi-GPU counterpart of C2 without atomics: the record is
-// found through the id stored in the rank's encoded grid.
-__global__ void __launch_bounds__(128)
-k_slab_cells(RankBufs B, SlotRef prev, int has_prev, const int* __restrict__ counter, SlabCells out,
-             SignalSet count_slots, DevParams P, int cap, int rec_cap) {
-    pdl_wait();
-    const int count = min(*counter, cap);
-    // publish my cell count into every rank's count table (remote WRITES are posted; a remote read costs ~2 us)
-    if (blockIdx.x == 0 && threadIdx.x < count_slots.n) *count_slots.slot[threadIdx.x] = count;
-    const int S = P.S, Z = P.Z;
-    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
-        const int v = out.voxel[id];
-        float c[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) c[k] = 0.f;
-        int hit = 0, tot = 0;
-        float mh = 1.0f;
-        int g[MAX_RANKS];
-        for (int k = 0; k < B.n; ++k) g[k] = __ldg(B.grid[k] + v);          // independent (remote) loads first
-        for (int k = 0; k < B.n; ++k) {
-            if (g[k] < OCC_FLAG) continue;
-            const int rid = g[k] & (OCC_FLAG - 1);
-            if (rid >= rec_cap) continue;
-            const float4* r4 = reinterpret_cast<const float4*>(B.rec[k] + (long long)rid * REC);
-            const float4 a = __ldg(r4), b = __ldg(r4 + 1), d = __ldg(r4 + 2), e = __ldg(r4 + 3);
-            const double o[10] = {b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w, e.x, e.y};
-            merge_step(c, o);
-            hit += __float_as_int(a.y); tot += __float_as_int(a.z); mh = fminf(mh, a.w);
-        }
-        if (has_prev) {
-            const int x = v % S, y = (v / S) % S, z = v / (S * S);
-            const int xs = x + prev.dx, ys = y + prev.dy, zs = z + prev.dz;
-            if (!(xs < 0 || xs >= S || ys < 0 || ys >= S || zs < 0 || zs >= Z)) {
-                const int io = __ldg(prev.map + (xs + (ys + (long long)zs * S) * S));
-                if (io >= 0) {
-                    double o[10];
-                    const float* om = reinterpret_cast<const float*>(prev.metrics) + (long long)io * 10;
-#pragma unroll
-                    for (int k = 0; k < 10; ++k) o[k] = (double)om[k];
-                    merge_step(c, o);
-                    hit += prev.hit[io]; tot += prev.total[io]; mh = fminf(mh, prev.minh[io]);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 10; ++k) out.met[(long long)id * 10 + k] = c[k];
-        out.hit[id] = hit; out.tot[id] = tot; out.minh[id] = mh;
-        float e[3];
-        eigen3(c, e);
-        out.eig[id * 3 + 0] = e[0]; out.eig[id * 3 + 1] = e[1]; out.eig[id * 3 + 2] = e[2];
-    }
-}
-
-struct SlabSet {                  // every rank's slab result as seen from here
-    const int* map[MAX_RANKS];    // full-size index map, valid on the rank's own planes, ids local to the rank
-    const int* counts;            // LOCAL table: counts[k] = cells of rank k (pushed by rank k)
-    const void* cells[MAX_RANKS]; // SlabCells base
-    int n;
-};
-
-__device__ __forceinline__ void slab_wait_and_offsets(const SlabSet& R, const int* wait_flags, int epoch, int* off) {
-    // off[k] = first global cell id of rank k, off[n] = total; computed once per block in shared memory
-    if (threadIdx.x == 0) {
-        if (wait_flags)
-            for (int k = 0; k < R.n; ++k) {
-                const volatile int* f = wait_flags + k;
-                if (!spin_until(f, epoch)) break;
-            }
-        __threadfence_system();
-        int acc = 0;
-        for (int k = 0; k < R.n; ++k) { off[k] = acc; acc += *reinterpret_cast<const volatile int*>(R.counts + k); }
-        off[R.n] = acc;
-    }
-    __syncthreads();
-}
-
-// assemble the full combined index map from the ranks' planes (compact ids rebased to the global
-// numbering), with the column minima and the group mask the single-GPU merge would have produced
-__global__ void __launch_bounds__(256)
-k_gather_maps(SlabSet R, const int* __restrict__ wait_flags, int epoch, int* __restrict__ cmap,
-              unsigned* __restrict__ gmask, int* __restrict__ col_occ, int* __restrict__ col_free,
-              int* __restrict__ total_count, DevParams P) {
-    pdl_wait();
-    __shared__ int off[MAX_RANKS + 1];
-    slab_wait_and_offsets(R, wait_flags, epoch, off);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *total_count = off[R.n];
-    const int lane = threadIdx.x & 31;
-    const int S = P.S;
-    const long long QP = ((long long)S * S) / 8;
-    const long long NQ = P.V / 8, NQp = (NQ + 31) & ~31LL;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < NQp; q += (long long)gridDim.x * blockDim.x) {
-        bool known_any = false;
-        if (q < NQ) {
-            const int z = (int)(q / QP);
-            const int k = z % R.n;
-            const int4* src = reinterpret_cast<const int4*>(R.map[k]) + q * 2;
-            int4 a = __ldg(src), b = __ldg(src + 1);
-            int c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            const long long rem = q % QP;
-            const int y = (int)((rem * 8) / S), x = (int)((rem * 8) % S);
-            bool any_occ = false, any_free = false;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (c[j] >= 0) { c[j] += off[k]; any_occ = true; }
-                else if (c[j] < -1) any_free = true;
-                known_any |= c[j] != -1;
-            }
-            if (any_occ || any_free) {
-                int* colo = col_occ + y * S + x;
-                int* colf = col_free + y * S + x;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (c[j] >= 0) { if (z < colo[j]) atomicMin(colo + j, z); }
-                    else if (c[j] < -1) { if (z < colf[j]) atomicMin(colf + j, z); }
-                }
-            }
-            int4* dst = reinterpret_cast<int4*>(cmap) + q * 2;
-            dst[0] = make_int4(c[0], c[1], c[2], c[3]);
-            dst[1] = make_int4(c[4], c[5], c[6], c[7]);
-        }
-        const unsigned w = __ballot_sync(FULL, known_any);
-        if (lane == 0 && q < NQ) gmask[q >> 5] = w;
-    }
-}
-
-// copy every rank's cells into the global compact arrays (global id = rank offset + local id)
-__global__ void __launch_bounds__(256)
-k_gather_cells(SlabSet R, long long res_cap, int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
-               float* __restrict__ cmet, float* __restrict__ ceig, int* __restrict__ cell_voxel, int cap) {
-    pdl_wait();
-    __shared__ int off[MAX_RANKS + 1];
-    slab_wait_and_offsets(R, nullptr, 0, off);           // k_gather_maps (same stream) already waited
-    const int total = min(off[R.n], cap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int k = 0;
-        while (k + 1 < R.n && i >= off[k + 1]) ++k;
-        const int l = i - off[k];
-        const SlabCells s = slab_cells_at(const_cast<void*>(R.cells[k]), res_cap);
-        chit[i] = s.hit[l]; ctot[i] = s.tot[l]; cminh[i] = s.minh[l]; cell_voxel[i] = s.voxel[l];
-        const float2* m2 = reinterpret_cast<const float2*>(s.met + (long long)l * 10);
-        float2* d2 = reinterpret_cast<float2*>(cmet + (long long)i * 10);
-#pragma unroll
-        for (int a = 0; a < 5; ++a) d2[a] = m2[a];
-        ceig[i * 3 + 0] = s.eig[l * 3 + 0]; ceig[i * 3 + 1] = s.eig[l * 3 + 1]; ceig[i * 3 + 2] = s.eig[l * 3 + 2];
-    }
-}
 
 // ---------------------------------------------------------------------------
 // tooling: L2 atomic-throughput microbenchmark (roofline denominator of the

@@ -418,7 +418,7 @@ class Gvom:
     def stage_times(self):
         ms = (C.c_float * 16)()
         check(self._L.gvom_stage_times(self._h, ms), "gvom_stage_times")
-        names = ("h2d", "scan_points", "scan_cells", "_3", "_4", "merge_codes", "merge_cells", "maps", "d2h", "stage_copy_host", "slab_cells", "slab_gather_maps", "slab_gather_cells", "partial", "rows_columns", "rows_surface")
+        names = ("h2d", "scan_points", "scan_cells", "_3", "_4", "merge_codes", "merge_cells", "maps", "d2h", "stage_copy_host", "_10", "_11", "_12", "push_or_partial", "_14", "rows_surface")
         return {k: float(ms[i]) for i, k in enumerate(names)}
 
     def refview(self):

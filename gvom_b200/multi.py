@@ -3,27 +3,26 @@
 README of the reference (README.md:49) allows several sensors to feed one Gvom;
 the per-scan work (Process_pointcloud) of different sensors is independent until
 combine_maps() merges the ring buffer.  That is where the path shards
-(SURVEY.md 8e): rank g owns sensor stream g and its own ring slots on its own
-B200, and the exchange happens only at combine time:
+(SURVEY.md 8e): rank g owns sensor stream g and its own ring slots on its own B200.
 
+Default (xy_size % 256 == 0; gvom_mirror.cuh) -- MIRRORED RING SLOTS, ROW-SHARDED COMBINE:
+  * the combined map is sharded by world rows: rank r owns the rows y with (y + origin_y) % world == r
+  * every Process_pointcloud ends with a push of the new scan to the owners of its rows (posted NVLink stores into
+    torch symmetric memory), so every rank holds local copies of all ranks' ring slots for the rows it owns
+  * combine_maps(): one flag exchange on the device, the single-GPU merge kernels over the own rows from LOCAL memory,
+    then two pushes of 2-D data (heights, finished maps).  No NCCL call, no host synchronisation.
+
+Generic exchange (any grid size; GVOM_MULTI_MIRROR=0) -- PARTIAL MERGE + REPLICATED FINISH:
   1. every rank folds its OWN slots into the common frame (gvom_combine_partial):
      a dense int32 code grid (occupied flag | summed pass count) + compact records
-  2. exchange, one of
-       "p2p"  (default): the grids / records live in torch symmetric memory, i.e.
-              every rank's buffers are mapped into every other rank over NVLink.
-              One device-side barrier, then the finishing kernels read the peers'
-              buffers directly -- compute and "collective" are the same kernels,
-              no NCCL launch, no host synchronisation, no staging copy.
-       "nccl": all-reduce(sum) of the grids + all-gather of records and a header
-              through torch.distributed (the baseline; also the fallback when
-              symmetric memory cannot be set up).
-  3. every rank finishes the combine (gvom_combine_finish) -- redundantly, which is
-     cheaper than broadcasting the result and keeps the "previous combined map"
-     state replicated, so any rank can serve the maps.
+  2. "p2p": the grids / records live in symmetric memory; one device-side barrier, then the finishing kernels read
+     the peers' buffers directly over NVLink.  "nccl": all-reduce(sum) of the grids + all-gather of records and a
+     header through torch.distributed (the fallback when symmetric memory cannot be set up).
+  3. every rank finishes the combine (gvom_combine_finish); the combined state is replicated.
 
-(Two replicated alternatives were built and measured in round 1 -- every rank merging every rank's slots read in
-place over NVLink ("direct"), or from bulk-copied mirrors ("pull") -- lost to partial + finish already at N = 2
- and were removed.)
+(Built, measured and removed over the two rounds: every rank merging every rank's slots read in place over NVLink
+("direct") or from bulk-copied mirrors ("pull"); a plane-sharded finish with full re-assembly; a row-sharded finish
+fed by partial merges.  DESIGN.md section 6 has the numbers.)
 
 The result equals a single Gvom holding all ranks' slots: occupancy (OR), pass
 sums, hit/total sums and min heights are order independent in the reference's
@@ -81,7 +80,7 @@ class MultiGpuGvom(Gvom):
     """One rank of a multi-GPU Gvom.  Same API as Gvom; combine_maps() is collective
     (every rank must call it) and returns the same maps on every rank."""
 
-    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", sharded="auto", rows="auto", mirror="auto", **kw):
+    def __init__(self, *args, group=None, torch_stream=None, exchange="auto", mirror="auto", **kw):
         import os
         import torch
         import torch.distributed as dist
@@ -104,43 +103,31 @@ class MultiGpuGvom(Gvom):
         self._org_in = (C.c_double * 3)()
         self._calls = 0
         self.exchange = None
-        # sharded finish (each rank merges 1/world of the z-planes) needs whole warps per plane
-        # measured on 8x B200 (profiles/): the sharded finish wins from ~6 ranks up; below that the extra assembly
-        # pass costs more than the finishing work it saves, so the replicated finish is used
-        if sharded == "auto":
-            sharded = self.world >= 6
-        self._sharded = bool(sharded) and self.xy_size % 16 == 0
-        # row-sharded finish (default where it applies: xy_size % 256 == 0): every rank merges only the world rows it owns
-        # and keeps the 3-D state of those rows; only 2-D maps are replicated.  GVOM_MULTI_ROWS=0 selects the older
-        # finishes (replicated / plane-sharded with full assembly) for A/B runs.
-        if rows == "auto":
-            rows = os.environ.get("GVOM_MULTI_ROWS", "1") != "0"
-        self._rows = bool(rows) and self.xy_size % 256 == 0
-        if self._rows:
-            self._sharded = False
-        # mirrored ring slots (default with the row-sharded finish): every scan is pushed to the owners of its rows at
-        # Process_pointcloud time, the combine merges from local mirrors -- no partial merge, no encoded grids.
-        # GVOM_MULTI_MIRROR=0 selects the partial-merge exchange for A/B runs.
+        # mirrored ring slots + row-sharded combine (default where it applies: xy_size % 256 == 0, at most 64 ring slots
+        # over all ranks): every scan is pushed to the owners of its world rows at Process_pointcloud time, the combine
+        # merges the own rows from local mirrors; only 2-D maps are replicated.  GVOM_MULTI_MIRROR=0 selects the generic
+        # exchange (partial merge + replicated finish) for A/B runs.
         if mirror == "auto":
             mirror = os.environ.get("GVOM_MULTI_MIRROR", "1") != "0"
-        self._mirror = bool(mirror) and self._rows and self.world * self.buffer_size <= 64
-        nb = C.c_uint64(0)
-        check(self._L.gvom_rows_block_size(self._h, C.byref(nb)), "gvom_rows_block_size")
-        self._b2d_bytes = int(nb.value)
-        ccap = min(self.voxel_count, 4 * self.max_points * (self.buffer_size + 1))
-        self._res_cap = int(min(self.voxel_count, max(1 << 18, 4 * ccap // self.world)))
+        self._mirror = bool(mirror) and self.xy_size % 256 == 0 and self.world * self.buffer_size <= 64
+        self._rows = self._mirror                 # (the 3-D combined state is sharded by world rows)
         if exchange in ("auto", "p2p"):
             try:
                 self._init_p2p()
                 self.exchange = "p2p"
             except Exception as ex:          # symmetric memory unavailable: fall back (all ranks agree below)
                 self._p2p_error = repr(ex)
+                self._mirror = self._rows = False
                 if exchange == "p2p":
                     raise
+        else:
+            self._mirror = self._rows = False
         # every rank must use the same exchange
         ok = torch.tensor([1 if self.exchange == "p2p" else 0], device=self._dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 0:
+            if self._mirror:
+                raise RuntimeError("MultiGpuGvom: symmetric memory came up on some ranks only, after the mirrors were attached")
             self.exchange = "nccl"
             self._init_nccl()
 
@@ -150,7 +137,13 @@ class MultiGpuGvom(Gvom):
 
     # ------------------------------------------------------------------ buffers
     def _layout(self):
-        """byte offsets inside one exchange set: grid | group mask | records | count(+pad) | header"""
+        """byte offsets inside one exchange set.  Generic exchange: grid | group mask | records | count(+pad) | header |
+        flags.  Mirrored combine: "heights" flags | "results" flags | 2-D block."""
+        if self._mirror:
+            nb = C.c_uint64(0)
+            check(self._L.gvom_rows_block_size(self._h, C.byref(nb)), "gvom_rows_block_size")
+            self._o_fh, self._o_fr, self._o_b2d = 0, 512, 1024
+            return 0, 0, 0, 0, 0, self._o_b2d + int(nb.value) + 256, 0
         V, cap = self.voxel_count, self._rec_cap
         o_grid = 0
         o_msk = (o_grid + 4 * V + 255) & ~255
@@ -159,20 +152,6 @@ class MultiGpuGvom(Gvom):
         o_hdr = o_cnt + 256
         o_flg = o_hdr + 8 * HEADER_DOUBLES + 256          # flags[rank] int32: rank's epoch, written by that rank
         total = o_flg + 4 * 64 + 256
-        # sharded finish: slab-done flags, result count, result index map, result cells (68 B per row)
-        self._o_flg2 = total
-        self._o_rcnt = self._o_flg2 + 4 * 64 + 256
-        self._o_rmap = self._o_rcnt + 4 * 64 + 256
-        self._o_rcel = (self._o_rmap + 4 * V + 255) & ~255
-        if self._sharded:
-            total = self._o_rcel + 68 * self._res_cap + 256
-        if self._rows:
-            # row-sharded finish: {epoch, origin} headers of the partial results, "heights" / "results" flags, the 2-D block
-            self._o_hdr4 = (total + 255) & ~255
-            self._o_fh = self._o_hdr4 + 16 * 64 + 256
-            self._o_fr = self._o_fh + 4 * 64 + 256
-            self._o_b2d = (self._o_fr + 4 * 64 + 255 + 256) & ~255
-            total = self._o_b2d + self._b2d_bytes + 256
         return o_grid, o_msk, o_rec, o_cnt, o_hdr, total, o_flg
 
     def _init_p2p(self):
@@ -187,6 +166,16 @@ class MultiGpuGvom(Gvom):
             hdl = symm_mem.rendezvous(t, group)
             t.zero_()
             ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if self._mirror:
+                K = GvomRowsLinks()
+                K.rank, K.nranks = self.rank, self.world
+                for r, p in enumerate(ptrs):
+                    K.blocks2d[r] = p + self._o_b2d
+                    K.heights_slots[r] = p + self._o_fh + 4 * self.rank
+                    K.results_slots[r] = p + self._o_fr + 4 * self.rank
+                K.heights_flags, K.results_flags = ptrs[self.rank] + self._o_fh, ptrs[self.rank] + self._o_fr
+                self._sets.append({"t": t, "hdl": hdl, "me": ptrs[self.rank], "links": K})
+                continue
             o_grid, o_msk, o_rec, o_cnt, o_hdr, _, o_flg = self._off
             self._sets.append({
                 "t": t, "hdl": hdl, "me": ptrs[self.rank],
@@ -196,23 +185,7 @@ class MultiGpuGvom(Gvom):
                 "hdr_view": t[o_hdr:o_hdr + 8 * HEADER_DOUBLES].view(torch.float64),
                 # my flag slot in every rank's block (signal) / all ranks' slots in my block (wait)
                 "signal": _ptr_array([p + o_flg + 4 * self.rank for p in ptrs]), "wait": ptrs[self.rank] + o_flg,
-                "signal2": _ptr_array([p + self._o_flg2 + 4 * self.rank for p in ptrs]), "wait2": ptrs[self.rank] + self._o_flg2,
-                "rmaps": _ptr_array([p + self._o_rmap for p in ptrs]), "rcells": _ptr_array([p + self._o_rcel for p in ptrs]),
-                # count table (64 ints) in every rank's block: entry r is pushed by rank r
-                "cslots": _ptr_array([p + self._o_rcnt + 4 * self.rank for p in ptrs]), "ctable": ptrs[self.rank] + self._o_rcnt,
             })
-            if self._rows:
-                K = GvomRowsLinks()
-                K.rank, K.nranks, K.record_capacity = self.rank, self.world, self._rec_cap
-                for r, p in enumerate(ptrs):
-                    K.code_grids[r], K.group_masks[r], K.records[r] = p + o_grid, p + o_msk, p + o_rec
-                    K.blocks2d[r] = p + self._o_b2d
-                    K.heights_slots[r] = p + self._o_fh + 4 * self.rank
-                    K.results_slots[r] = p + self._o_fr + 4 * self.rank
-                me_p = ptrs[self.rank]
-                K.partial_headers, K.heights_flags, K.results_flags = me_p + self._o_hdr4, me_p + self._o_fh, me_p + self._o_fr
-                self._sets[-1]["links"] = K
-                self._sets[-1]["hdr4"] = _ptr_array([p + self._o_hdr4 + 16 * self.rank for p in ptrs])
         if self._mirror:
             nb = C.c_uint64(0)
             check(self._L.gvom_mirror_block_size(self._h, self.world, C.byref(nb)), "gvom_mirror_block_size")
@@ -255,23 +228,18 @@ class MultiGpuGvom(Gvom):
     def _combine_p2p(self, device_outputs, wait=True):
         torch, L = self._torch, self._L
         X = self._sets[self._calls & 1]
-        t, hdl, me = X["t"], X["hdl"], X["me"]
-        o_grid, o_msk, o_rec, o_cnt, o_hdr, _, o_flg = self._off
         epoch = self._calls
         have = L.gvom_newest_origin(self._h, self._org_in) != GVOM_NO_DATA
         if self._mirror:
             return self._combine_mirror(device_outputs, wait, X, epoch, have)
+        t, hdl, me = X["t"], X["hdl"], X["me"]
+        o_grid, o_msk, o_rec, o_cnt, o_hdr, _, o_flg = self._off
         with torch.cuda.stream(self._tstream):
             hh = self._hdr_host                      # header: only read by ranks that have no scan yet (start-up)
             hh[0] = 1.0 if have else 0.0
             hh[2], hh[3], hh[4] = (self._org_in[0], self._org_in[1], self._org_in[2]) if have else (0.0, 0.0, 0.0)
             X["hdr_view"].copy_(hh, non_blocking=True)
-            if have and self._rows:
-                # partial kernels, then the header kernel: {epoch, origin} into every rank's block
-                check(L.gvom_combine_partial_header(self._h, self._org_in, me + o_grid, me + o_msk, me + o_rec, self._rec_cap,
-                                                    me + o_cnt, X["hdr4"], self.world, epoch, self._stream),
-                      "gvom_combine_partial_header")
-            elif have:
+            if have:
                 # partial kernels, then the signal kernel: "rank `me`, combine `epoch`: done" into every rank's block
                 check(L.gvom_combine_partial(self._h, self._org_in, me + o_grid, me + o_msk, me + o_rec, self._rec_cap,
                                              me + o_cnt, X["signal"], self.world, epoch, self._stream), "gvom_combine_partial")
@@ -280,15 +248,9 @@ class MultiGpuGvom(Gvom):
                 # for the others and adopt the origin of a rank that has data.
                 t[o_grid:o_rec].zero_()              # empty grid, empty group mask
                 t[o_cnt:o_cnt + 4].zero_()
-                if self._rows:       # header {epoch, no origin}
-                    mine = torch.tensor([epoch, 0x7fffffff, 0, 0], dtype=torch.int32, device=self._dev)
-                    for r in range(self.world):
-                        hdl.get_buffer(r, (64 * 4,), torch.int32, self._o_hdr4 // 4)[4 * self.rank:4 * self.rank + 4].copy_(mine)
-                    flags = t[self._o_hdr4:self._o_hdr4 + 16 * 64].view(torch.int32)[:4 * self.world:4]
-                else:
-                    for r in range(self.world):
-                        hdl.get_buffer(r, (64,), torch.int32, o_flg // 4)[self.rank:self.rank + 1].fill_(epoch)
-                    flags = t[o_flg:o_flg + 4 * 64].view(torch.int32)[:self.world]
+                for r in range(self.world):
+                    hdl.get_buffer(r, (64,), torch.int32, o_flg // 4)[self.rank:self.rank + 1].fill_(epoch)
+                flags = t[o_flg:o_flg + 4 * 64].view(torch.int32)[:self.world]
                 self._tstream.synchronize()
                 while int(flags.min().item()) < epoch:
                     time.sleep(1e-4)
@@ -300,27 +262,7 @@ class MultiGpuGvom(Gvom):
                     return None
                 for k in range(3):
                     self._org_in[k] = float(origin[k])
-            if self._rows:
-                # own world rows: merge + cells + columns; heights and finished maps are pushed to every rank
-                outs, optr, mem = self._outputs(device_outputs)
-                phases = 7 if (wait or not device_outputs) else 15
-                check(L.gvom_combine_finish_rows(self._h, self._org_in, C.byref(X["links"]), epoch, phases, self._org_c,
-                                                 optr[0], optr[1], optr[2], optr[3], mem, self._stream),
-                      "gvom_combine_finish_rows")
-                if phases == 15:
-                    self._hold_until_consumed(outs)      # the stream may still be writing them when the caller drops them
-                pos, neg, rough, vis = outs
-                return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
             outs, optr, mem = self._outputs(device_outputs)
-            if self._sharded:
-                # every rank finishes 1/world of the planes, publishes them, and assembles the full map from all ranks
-                check(L.gvom_combine_finish_sharded(self._h, self._org_in, self.rank, self.world, X["grids"], X["masks"],
-                                                    X["recs"], self._rec_cap, X["wait"], X["rmaps"], X["rcells"], X["cslots"],
-                                                    X["ctable"], self._res_cap, X["signal2"], X["wait2"], epoch, 3, self._org_c,
-                                                    optr[0], optr[1], optr[2], optr[3], mem, self._stream),
-                      "gvom_combine_finish_sharded")
-                pos, neg, rough, vis = outs
-                return (np.array([self._org_c[0], self._org_c[1], self._org_c[2]]), pos, neg, rough, vis)
             # the finishing merge kernel waits on the flag slots itself, then reads the peers' buffers over NVLink
             check(L.gvom_combine_finish(self._h, self._org_in, X["grids"], X["masks"], self.world, X["recs"], X["cnts"],
                                         self.world, self._rec_cap, X["wait"], epoch, self._org_c, optr[0], optr[1],

@@ -179,7 +179,7 @@ int gvom_state_size(GvomHandle* h, size_t* bytes);
 int gvom_save_state(GvomHandle* h, void* blob, size_t capacity, size_t* written);
 int gvom_load_state(GvomHandle* h, const void* blob, size_t bytes);
 
-/* ---- multi-GPU: independent sensor streams per GPU, merged at combine time ----
+/* ---- multi-GPU, generic exchange (any grid size; also the NCCL fallback): partial merge + replicated finish ----
  * Each rank pre-merges its own ring buffer into the common frame `origin`
  * (integral voxel units): a dense int32 code grid (V entries: occupied flag
  * 1<<26, else the pass count) and compact cell records (GVOM_RECORD_FLOATS
@@ -213,78 +213,44 @@ int gvom_combine_finish(GvomHandle* h, const double origin[3], const int32_t* co
                         double origin_out[3], int32_t* positive, int32_t* negative, double* roughness,
                         int32_t* visibility, int32_t out_mem, void* stream);
 
-/* Sharded finish (peer-to-peer exchange, xy_size % 16 == 0): rank `rank` merges only the z-planes with
- * z % nranks == rank (from every rank's encoded grid, read over NVLink) and the cells on them, publishes
- * the result (res_maps[rank], res_cells[rank]; arrays of nranks pointers into the ranks' mapped
- * memory; its cell count is pushed into count_slots[k] = entry `rank` of rank k's count_table), then assembles the full combined map from all ranks' planes.  Per-rank
- * finishing work is V / nranks; the combined state stays replicated.  wait_partial / wait_slab:
- * nranks local int32 flag slots (partial results / slab results published, value >= epoch);
- * signal_slab: this rank's slab flag slot in every rank's memory.  res_cells block: 68 bytes per row.
- * phases: 1 = own planes only, 2 = assemble only, 3 = both (1 and 2 separately let one process play
- * several ranks in the tests). */
-int gvom_combine_finish_sharded(GvomHandle* h, const double origin[3], int32_t rank, int32_t nranks,
-                                const int32_t* const* code_grids, const uint32_t* const* group_masks,
-                                const float* const* records, int64_t record_capacity,
-                                const int32_t* wait_partial, int32_t* const* res_maps,
-                                void* const* res_cells, int32_t* const* count_slots,
-                                const int32_t* count_table, int64_t res_capacity,
-                                int32_t* const* signal_slab, const int32_t* wait_slab, int32_t epoch,
-                                int32_t phases, double origin_out[3], int32_t* positive, int32_t* negative,
-                                double* roughness, int32_t* visibility, int32_t out_mem, void* stream);
-
-/* Row-sharded finish (peer-to-peer exchange, xy_size % 256 == 0) -- the default multi-GPU combine.  Rank r owns
- * the WORLD rows y with (y + origin_y) mod nranks == r (whole columns): it merges only those rows from every rank's
- * encoded grid and keeps the previous combined map and the cells of those rows, so the 3-D state is SHARDED; the
- * column reductions and the 2-D stage of its columns are local.  Only 2-D maps are replicated, by pushing into every
- * rank's 2-D block (symmetric memory, gvom_rows_block_size() bytes): heights after the column stage, the finished maps
- * after the surface stage.  gvom_combine_partial_header() is gvom_combine_partial() whose signal carries the origin
- * ({epoch, ox, oy, oz} int32 headers): the finishing ranks verify that everybody merged in the same frame
- * (GVOM_EINVAL otherwise).  phases: 1 = own rows + cells + heights, 2 = surface stage, 4 = deliver; 7 = all; + 8 =
- * return without waiting for the stream (outputs in device memory are valid in stream order; completed, and errors
- * reported, by the next call on the handle)
- * (separate phases let one process play several ranks in the tests).  Every flag / header table has one entry per rank,
- * written by that rank with the combine's epoch (1, 2, ...). */
+/* ---- multi-GPU, default (xy_size % 256 == 0): mirrored ring slots + row-sharded combine (gvom_mirror.cuh) ----
+ * Replaces the roles of gvom.py:242-257 (merge over the whole ring) when the ring is spread over GPUs.  Rank r owns the
+ * WORLD rows y with (y + origin_y) mod nranks == r (whole columns), so an origin shift never moves a row -- and the
+ * previous combined map of that row -- to another rank; the 3-D combined state is SHARDED by rows.
+ *  * Every rank owns a block of gvom_mirror_block_size() bytes that all ranks can write (symmetric memory).  After
+ *    gvom_mirror_attach() every Process_pointcloud ends with one push kernel that stores the new slot's index-map rows,
+ *    group-mask words and cell records into the memory of the rank that owns the row -- posted NVLink stores --
+ *    together with a slot-table entry; every rank thus holds exact local copies of all ranks' ring slots for the rows
+ *    it owns.  blocks[k] = rank k's block as mapped into this process; attach before the first scan and synchronise all
+ *    ranks (barrier) before any of them scans.
+ *  * gvom_combine_finish_rows() (collective; no NCCL call, no host synchronisation): one warp publishes this rank's epoch
+ *    flag, waits for the others' and builds the source list on the device from the slot table; the single-GPU merge
+ *    kernels run over the own rows from local memory; the column heights of the own rows are pushed into every rank's
+ *    2-D block (symmetric memory, gvom_rows_block_size() bytes); after the "heights" flags the surface stage of the own
+ *    rows runs and its maps are pushed; after the "results" flags the four output maps are delivered.  Every flag table
+ *    has one entry per rank, written by that rank with the combine's epoch (1, 2, ...); a rank that never arrives makes
+ *    the others give up after 10 s (GVOM_ECUDA); ranks whose newest scans disagree on the origin: GVOM_EINVAL.
+ *    phases: 1 = own rows + cells + heights, 2 = surface stage, 4 = deliver; 7 = all; + 8 = return without waiting for
+ *    the stream (outputs in device memory are valid in stream order; completed, and errors reported, by the next call
+ *    on the handle).  One process playing several ranks (tests) publishes every flag for all ranks before any rank waits
+ *    for it: 16 / 64 / 128 = publish the epoch / heights / results flag only; 32 (with 1) = the epoch flag is already
+ *    out (also the start-up path of a rank without scans); 256 (with 2, 4) = the waiting kernels do not publish --
+ *    i.e. 16, 1 | 32, 64, 2 | 256, 128, 4 | 256, each for all ranks in turn. */
 #define GVOM_MAX_RANKS 16
 typedef struct GvomRowsLinks {
     int32_t rank, nranks;
-    const int32_t* code_grids[GVOM_MAX_RANKS];     /* every rank's encoded grid / group mask / records as mapped here */
-    const uint32_t* group_masks[GVOM_MAX_RANKS];
-    const float* records[GVOM_MAX_RANKS];
-    int64_t record_capacity;
-    const int32_t* partial_headers;                /* local: nranks x {epoch, ox, oy, oz} */
-    void* blocks2d[GVOM_MAX_RANKS];                /* every rank's 2-D block */
+    void* blocks2d[GVOM_MAX_RANKS];                /* every rank's 2-D block as mapped here */
     int32_t* heights_slots[GVOM_MAX_RANKS];        /* this rank's "heights pushed" flag in every rank's memory */
     const int32_t* heights_flags;                  /* local: nranks flags */
     int32_t* results_slots[GVOM_MAX_RANKS];        /* this rank's "maps pushed" flag in every rank's memory */
     const int32_t* results_flags;                  /* local: nranks flags */
 } GvomRowsLinks;
+int gvom_mirror_block_size(GvomHandle* h, int32_t nranks, uint64_t* bytes);
+int gvom_mirror_attach(GvomHandle* h, int32_t rank, int32_t nranks, void* const* blocks);
 int gvom_rows_block_size(GvomHandle* h, uint64_t* bytes);
-int gvom_combine_partial_header(GvomHandle* h, const double origin[3], int32_t* code_grid_dev,
-                                uint32_t* group_mask_dev, float* records_dev, int64_t record_capacity,
-                                int32_t* record_count_dev, int32_t* const* header_slots, int32_t n_signal,
-                                int32_t epoch, void* stream);
 int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRowsLinks* links, int32_t epoch,
                              int32_t phases, double origin_out[3], int32_t* positive, int32_t* negative,
                              double* roughness, int32_t* visibility, int32_t out_mem, void* stream);
-
-/* Mirrored ring slots -- the exchange of the row-sharded combine without a partial merge.  Every rank owns a block of
- * gvom_mirror_block_size() bytes that all ranks can write (symmetric memory).  After gvom_mirror_attach() every
- * Process_pointcloud ends with one push kernel that stores the new slot's index-map rows, group-mask words and cell
- * records into the memory of the rank that owns the row (world rows, as above) -- posted NVLink stores -- together
- * with a slot-table entry {sequence, origin, cells}; every rank thus holds exact local copies of all ranks' ring slots
- * for the rows it owns.  gvom_combine_finish_rows() on an attached handle then needs no encoded grids, records or
- * partial headers (those link fields may be NULL): one warp publishes this rank's epoch flag, waits for the others' and
- * builds the source list on the device from the slot table; the single-GPU merge kernels run over the own rows from
- * local memory.  Replaces the roles of gvom.py:242-257 (merge over the whole ring) across GPUs.  blocks[k] = rank k's
- * block as mapped into this process; attach before the first scan and synchronise all ranks (barrier) before any of
- * them scans.  On attached handles the three flags of a combine (epoch / heights / results) are published by the first
- * block of the kernel that then waits for everybody's, so the producing kernels need no per-block system fence.  Extra
- * phase bits of gvom_combine_finish_rows() for attached handles: 16 / 64 / 128 = publish the epoch / heights / results
- * flag only; 32 (with 1) = the epoch flag is already out (also the start-up path of a rank without scans); 256 (with
- * 2, 4) = the waiting kernels do not publish the heights / results flags (one process playing several ranks calls
- * 16, 1 | 32, 64, 2 | 256, 128, 4 | 256, each for all ranks in turn). */
-int gvom_mirror_block_size(GvomHandle* h, int32_t nranks, uint64_t* bytes);
-int gvom_mirror_attach(GvomHandle* h, int32_t rank, int32_t nranks, void* const* blocks);
 /* A rank that has not scanned yet takes part in a combine with the origin AND the vehicle position of a rank that has
  * (slot-table entry: 16 int32 {sequence (0: empty), ox, oy, oz, cells, -, -, -, ego xyz as 3 float64, -, -} at byte 256 +
  * 64 * (rank * buffer_size + slot) of the block): the ego disc of the height map (gvom.py:560-571) needs it. */

@@ -37,8 +37,8 @@ for i in range(steps):
     outs, _ = local_exchange_mirror(ranks, i + 1, blocks)
     t_comb = [g.stage_times() for g in ranks]
     if i >= 4:
-        for key in ("scan_points", "scan_cells", "partial"):
+        for key in ("scan_points", "scan_cells", "push_or_partial"):
             acc.setdefault(key, []).append(np.mean([t[key] for t in t_proc]))
-        for key in ("merge_codes", "merge_cells", "rows_columns", "rows_surface", "d2h"):
+        for key in ("merge_codes", "merge_cells", "rows_surface", "d2h"):
             acc.setdefault(key, []).append(np.mean([t[key] for t in t_comb]))
-print(f"ranks {n}:", {k: round(1e3 * float(np.median(v)), 1) for k, v in acc.items()}, "us (partial = push kernel)")
+print(f"ranks {n}:", {k: round(1e3 * float(np.median(v)), 1) for k, v in acc.items()}, "us (push_or_partial = push kernel; merge_codes includes the flag exchange; rows_surface = known + surface; d2h = deliver)")

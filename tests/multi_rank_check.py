@@ -43,12 +43,11 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     B = 2
-    xy = 256 if "grid256" in sys.argv else 64                 # the row-sharded finish needs xy_size % 256 == 0
+    xy = 256 if "grid256" in sys.argv else 64                 # the mirrored, row-sharded combine needs xy_size % 256 == 0
     P1 = synth.params_tuple(xy_size=xy, z_size=16, buffer_size=B, robot_radius=2.0)
     PN = synth.params_tuple(xy_size=xy, z_size=16, buffer_size=B * world, robot_radius=2.0)
     fr = sensor_frames(world, 4, beams=16, cols=512, wall=30.0) if xy == 256 else sensor_frames(world, 4)
-    g = MultiGpuGvom(*P1, device=local, exchange=sys.argv[1] if len(sys.argv) > 1 else "auto",
-                     sharded=True if "sharded" in sys.argv else "auto")
+    g = MultiGpuGvom(*P1, device=local, exchange=sys.argv[1] if len(sys.argv) > 1 else "auto")
     if "late" in sys.argv[2:]:                             # start-up path: rank 1 joins one combine late
         first = MultiGpuGvom(*P1, device=local, exchange=sys.argv[1])
         if rank == 0:
@@ -74,7 +73,7 @@ def main():
     assert sys.argv[1] == "auto" or g.exchange == sys.argv[1], (g.exchange, getattr(g, "_p2p_error", ""))
     dist.barrier()
     if rank == 0:
-        print("MULTI_RANK_OK exchange=" + g.exchange + (" rows" if getattr(g, "_rows", False) and g.exchange == "p2p" else "") + (" sharded" if getattr(g, "_sharded", False) and g.exchange == "p2p" else "") + (" p2p_error=" + getattr(g, "_p2p_error", "") if g.exchange != "p2p" else ""))
+        print("MULTI_RANK_OK exchange=" + g.exchange + (" mirrored rows" if getattr(g, "_rows", False) and g.exchange == "p2p" else "") + (" p2p_error=" + getattr(g, "_p2p_error", "") if g.exchange != "p2p" else ""))
     dist.destroy_process_group()
 
 

@@ -1,12 +1,14 @@
-"""World-size-2 `gloo` test of the multi-GPU combine PROTOCOL on CPU (no CUDA).
+"""World-size-2 `gloo` tests of the multi-GPU combine PROTOCOLS on CPU (no CUDA).
 
-The device kernels cannot run here, so each rank models its partial result with the CPU oracle
-and numpy: ring slots folded into the common frame as an encoded grid (1<<26 = occupied, else
-summed passes), exactly what gvom_combine_partial produces.  The ranks exchange with the same
-collectives the NCCL path uses (all_gather of the header, all_reduce(sum) of the grid), decode
-like gvom_combine_finish does, and rank 0 checks the result against ONE oracle Gvom that holds
-both ranks' scans.  This pins: the encoding, the order independence of the fold, the header
-logic (merge_headers) and the previous-map rule applied after the cross-rank sum."""
+The device kernels cannot run here, so each rank models its part with the CPU oracle and numpy:
+ * test_mirrored_row_sharded_protocol_gloo -- the default combine (mirrored ring slots, state sharded by world rows):
+   which rows of which slot a rank may read, the merge of the own rows + own previous rows while the origin moves, the
+   assembly of the result.
+ * test_two_rank_protocol_gloo -- the generic exchange: ring slots folded into the common frame as an encoded grid
+   (1<<26 = occupied, else summed passes), exactly what gvom_combine_partial produces; the collectives of the NCCL path
+   (all_gather of the header, all_reduce(sum) of the grid); decoding like gvom_combine_finish.
+ * test_mirror_push_protocol_model, test_newest_origin_host_logic, test_merge_headers -- host logic / push bookkeeping.
+Rank 0 checks every result against ONE oracle Gvom that holds both ranks' scans."""
 import os
 import sys
 
@@ -144,80 +146,77 @@ def fold_slots(slots, origin, S, Z):
     return occ, passes
 
 
-@pytest.mark.parametrize("nranks", [2, 3, 8])
-def test_plane_sharded_column_exchange_model(nranks):
-    """Executable model of the NEXT multi-GPU design: the combined state stays sharded
-    by WORLD plane, owner(z) = (z + origin_z) mod N, and the 2-D stage gets the three per-column facts that span
-    planes through two small reductions:
-      (a) lowest occupied voxel + its min height:  MIN over ranks of the 64-bit key  z << 32 | float32 bits of min_h
-      (b) lowest free voxel:                       MIN over ranks of z
-      (c) positive-obstacle window sums:           SUM over ranks of (sum hit, sum total) of the cells with hit > 10
-    Every rank only looks at its own planes; the reduced facts must reproduce the oracle's height map, inferred
-    height map and positive-obstacle map (gvom.py:515-590)."""
+def mirror_worker(rank, world, port, result):
+    """World-size-2 gloo model of the DEFAULT multi-GPU combine (mirrored ring slots, row-sharded state): every rank keeps
+    of every rank's slots only the world rows it owns (the rest is filled with garbage: it must never be read), merges its
+    own rows + its own rows of the previous combined map, and the assembled result must equal one oracle Gvom holding
+    all ranks' scans -- while the ego moves, i.e. the local index of a world row changes from combine to combine."""
+    sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
     from gvom_b200 import synth
     from oracle.gvom_oracle import OracleGvom
     from test_multi_gpu import sensor_frames
-    S, Z = 32, 16
-    P = synth.params_tuple(xy_size=S, z_size=Z, buffer_size=4, robot_radius=2.0)
-    o = OracleGvom(*P)
-    fr = sensor_frames(2, 3, beams=32, cols=512, wall=5.5)
-    for step in range(3):
-        for r in range(2):
-            o.Process_pointcloud(*fr[step][r])
-        _, pos_ref, _, _, _ = o.combine_maps()           # two ego steps: the origin (and with it plane ownership) moves
-    pos_ref = pos_ref.T                                   # oracle maps are [x, y]; everything below is [y, x]
-    z_res, pos_thr, robot_h, slope_thr = P[1], P[6], P[9], P[8]
-    oz = int(o.combined_origin[2])
-    cmap = o.combined_index_map.reshape(Z, S, S)          # [z, y, x]
-    hit, tot, minh = o.combined_hit_count, o.combined_total_count, o.combined_min_height
-    INF = np.uint64(0xFFFFFFFFFFFFFFFF)
-    key_occ = np.full((nranks, S, S), INF, np.uint64)     # [rank, y, x]
-    z_free = np.full((nranks, S, S), 1 << 30, np.int64)
-    owner = (np.arange(Z) + oz) % nranks
-    for r in range(nranks):
-        for z in np.flatnonzero(owner == r):
-            plane = cmap[z]
-            occ = plane >= 0
-            bits = np.zeros((S, S), np.uint64)
-            bits[occ] = minh[plane[occ]].view(np.uint32).astype(np.uint64)
-            key = (np.uint64(z) << np.uint64(32)) | bits
-            key_occ[r] = np.where(occ, np.minimum(key_occ[r], key), key_occ[r])
-            z_free[r] = np.where(plane < -1, np.minimum(z_free[r], z), z_free[r])
-    k = key_occ.min(axis=0)                               # reduction (a)
-    zf = z_free.min(axis=0)                               # reduction (b)
-    has = k != INF
-    zo = (k >> np.uint64(32)).astype(np.int64)
-    mh = (k & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32).astype(np.float64)
-    h_model = np.where(has, (zo + mh + oz) * z_res, -1000.0)           # [y, x]
-    h_ref = o.height_map.T                                # oracle maps are [x, y]
-    outside_disc = ~((h_ref > -1000.0) & ~has)            # the ego disc's assumed ground is not a column fact
-    assert np.array_equal(h_model[has], h_ref[has])
-    assert (h_ref[outside_disc & ~has] == -1000.0).all()
-    inf_model = np.where(zf < (1 << 30), (oz + zf) * z_res, -1000.0)
-    assert np.array_equal(inf_model, o.inferred_height_map.T)
-    # (c): the window depends on the (now global) height; each rank sums inside it over ITS planes only
-    h_all = h_ref                                         # incl. the disc default, as the 2-D stage sees it
-    lo = np.floor((h_all + pos_thr) / z_res - oz).astype(np.int64) + 1
-    hi = np.floor((h_all + robot_h) / z_res - oz).astype(np.int64)
-    ok = (lo >= 0) & (lo < Z) & (hi >= 0) & (hi < Z)
-    sums = np.zeros((nranks, 2, S, S), np.int64)
-    for r in range(nranks):
-        for z in np.flatnonzero(owner == r):
-            plane = cmap[z]
-            inwin = ok & (lo <= z) & (z <= hi) & (plane >= 0)
-            big = np.zeros((S, S), bool)
-            big[inwin] = hit[plane[inwin]] > 10
-            sums[r, 0][big] += hit[plane[big]]
-            sums[r, 1][big] += tot[plane[big]]
-    sh, st = sums[:, 0].sum(axis=0).astype(np.float64), sums[:, 1].sum(axis=0).astype(np.float64)     # reduction (c)
-    dens = np.where(st > 0, sh / np.where(st > 0, st, 1.0), sh)
-    pos_model = np.where(ok, (dens * 100.0).astype(np.int32), 0)
-    steep = ~(np.sqrt(o.x_slope_map ** 2 + o.y_slope_map ** 2) < slope_thr).T
-    pos_model = np.where(steep, 100, pos_model)
-    assert np.array_equal(pos_model, pos_ref)
-    # the scenario exercises both paths: steep cells (100) and density values from the window sums
-    assert has.sum() > 20 and (pos_ref == 100).sum() > 0 and ((pos_ref > 0) & ~steep).sum() > 0
+    S, Z, B = 32, 8, 2
+    P1 = synth.params_tuple(xy_size=S, z_size=Z, buffer_size=B, robot_radius=2.0)
+    PN = synth.params_tuple(xy_size=S, z_size=Z, buffer_size=B * world, robot_radius=2.0)
+    fr = sensor_frames(world, 5, beams=8, cols=64, wall=5.0)
+    mine = OracleGvom(*P1)
+    ref = OracleGvom(*PN) if rank == 0 else None
+    rng = np.random.default_rng(100 + rank)
+    prev_codes, prev_origin = None, None                       # this rank's shard: only its own rows are meaningful
+    ok = True
+    ys = np.arange(S)
+    for step in range(5):
+        mine.Process_pointcloud(*fr[step][rank])
+        origin = np.asarray(mine.origin_buffer[mine.last_buffer_index], np.float64)
+        # "push": every rank's valid slots travel (gloo stands in for the NVLink stores) ...
+        local = [(np.asarray(mine.index_buffer[i]).reshape(Z, S, S).copy(), np.asarray(mine.origin_buffer[i], np.float64))
+                 for i in range(B) if mine.origin_buffer[i] is not None]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        # ... but a rank keeps only the rows it owns under the SLOT's origin; everything else is garbage here
+        mirrors = []
+        for slots in gathered:
+            for idx, org in slots:
+                own = (ys + int(org[1])) % world == rank
+                m = rng.integers(-40, 40, size=idx.shape).astype(idx.dtype)
+                m[:, own, :] = idx[:, own, :]
+                mirrors.append((m.reshape(-1), org))
+        occ, passes = fold_slots(mirrors, origin, S, Z)
+        total = np.where(occ, OCC, np.minimum(passes, OCC - 1)).astype(np.int32)
+        codes = finish_codes(total, prev_codes, prev_origin, origin, S, Z)
+        own_now = (ys + int(origin[1])) % world == rank
+        shard = rng.integers(-40, 40, size=codes.shape).astype(np.int32)     # rows of other ranks: garbage in MY state
+        shard[:, own_now, :] = codes[:, own_now, :]
+        prev_codes, prev_origin = shard, origin
+        # every rank delivers its rows; the assembly is what the 2-D pushes replicate
+        parts = [None] * world
+        dist.all_gather_object(parts, (own_now, shard[:, own_now, :]))
+        full = np.zeros((Z, S, S), np.int32)
+        seen = np.zeros(S, int)
+        for o_rows, data in parts:
+            full[:, o_rows, :] = data
+            seen += o_rows
+        ok &= bool((seen == 1).all())                           # every row has exactly one owner
+        if rank == 0:
+            for r in range(world):
+                ref.Process_pointcloud(*fr[step][r])
+            ref.combine_maps()
+            want = np.where(ref.combined_index_map >= 0, 0, ref.combined_index_map).reshape(Z, S, S)
+            ok &= bool(np.array_equal(full, want))
+    result[rank] = ok
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_mirrored_row_sharded_protocol_gloo():
+    world = 2
+    with mp.Manager() as m:
+        result = m.dict()
+        mp.spawn(mirror_worker, args=(world, 29641, result), nprocs=world, join=True)
+        assert dict(result) == {0: True, 1: True}
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -1,11 +1,11 @@
-"""Multi-GPU combine: per-rank partial merge + exchange + finish must
-equal one Gvom that holds every rank's ring slots.
+"""Multi-GPU combine: every exchange must equal one Gvom that holds every rank's ring slots.
 
- * test_partial_finish_equals_single (1 GPU): two handles on the same device play
-   two ranks; the exchange (sum of code grids, concatenation of records) is done in
-   process, so the kernels of gvom_combine_partial / gvom_combine_finish are
-   covered on the single-GPU box.
- * test_nccl_two_ranks (>= 2 GPUs): the same through MultiGpuGvom over NCCL.
+ * test_mirrored_rows_equals_single (1 GPU): several handles on the same device play the ranks of the default
+   combine -- mirrored ring slots (gvom_mirror_attach: every scan pushed to the owners of its world rows) + row-sharded
+   combine (gvom_combine_finish_rows); all blocks in plain device memory.
+ * test_partial_finish_equals_single (1 GPU): the generic exchange (gvom_combine_partial / gvom_combine_finish), peer
+   buffers read directly or one summed grid + gathered records (what NCCL delivers).
+ * test_nccl_two_ranks (>= 2 GPUs): MultiGpuGvom under torchrun -- NCCL, p2p generic, p2p mirrored, late-joining rank.
 """
 import ctypes as C
 import os
@@ -83,106 +83,6 @@ def local_exchange(ranks, reduced=False):
     return outs
 
 
-def local_exchange_sharded(ranks, epoch):
-    """In-process emulation of the SHARDED peer-to-peer finish: every "rank" merges the z-planes it owns
-    (phase 1, all ranks), then assembles the full map from all ranks' planes (phase 2)."""
-    import torch
-    from gvom_b200._lib import GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, check
-    g0 = ranks[0]
-    L, V = g0._L, g0.voxel_count
-    dev = f"cuda:{g0.device}"
-    n = len(ranks)
-    org = (C.c_double * 3)()
-    origin = None
-    for g in ranks:
-        if L.gvom_newest_origin(g._h, org) != GVOM_NO_DATA and origin is None:
-            origin = [org[0], org[1], org[2]]
-    o = (C.c_double * 3)(*origin)
-    cap = int(min(V, g0.buffer_size * g0.max_points))
-    rcap = V
-    parr = lambda ps: (C.c_void_p * len(ps))(*[C.c_void_p(int(p)) for p in ps])
-    B = [dict(grid=torch.zeros(V, dtype=torch.int32, device=dev), msk=torch.zeros(V // 256 + 2, dtype=torch.int32, device=dev),
-              rec=torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev), cnt=torch.zeros(1, dtype=torch.int32, device=dev),
-              f1=torch.zeros(64, dtype=torch.int32, device=dev), f2=torch.zeros(64, dtype=torch.int32, device=dev),
-              rcnt=torch.zeros(64, dtype=torch.int32, device=dev), rmap=torch.full((V,), -7, dtype=torch.int32, device=dev),
-              rcel=torch.empty(68 * rcap, dtype=torch.uint8, device=dev)) for _ in ranks]
-    for r, g in enumerate(ranks):
-        sig = parr([b["f1"].data_ptr() + 4 * r for b in B])
-        check(L.gvom_combine_partial(g._h, o, B[r]["grid"].data_ptr(), B[r]["msk"].data_ptr(), B[r]["rec"].data_ptr(), cap,
-                                     B[r]["cnt"].data_ptr(), sig, n, epoch, None), "partial")
-    torch.cuda.synchronize()
-    grids, masks = parr([b["grid"].data_ptr() for b in B]), parr([b["msk"].data_ptr() for b in B])
-    recs = parr([b["rec"].data_ptr() for b in B])
-    rmaps, rcels = parr([b["rmap"].data_ptr() for b in B]), parr([b["rcel"].data_ptr() for b in B])
-    outs = []
-    for phase in (1, 2):
-        for r, g in enumerate(ranks):
-            sig2 = parr([b["f2"].data_ptr() + 4 * r for b in B])
-            cslots = parr([b["rcnt"].data_ptr() + 4 * r for b in B])
-            pos, neg, rough, vis = g._out_arrays()
-            oo = (C.c_double * 3)()
-            check(L.gvom_combine_finish_sharded(g._h, o, r, n, grids, masks, recs, cap, B[r]["f1"].data_ptr(), rmaps, rcels, cslots,
-                                                B[r]["rcnt"].data_ptr(), rcap, sig2, B[r]["f2"].data_ptr(), epoch, phase, oo, pos.ctypes.data,
-                                                neg.ctypes.data, rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None), "sharded")
-            torch.cuda.synchronize()
-            if phase == 2:
-                outs.append((np.array(list(oo)), pos, neg, rough, vis))
-    return outs
-
-
-def local_exchange_rows(ranks, epoch):
-    """In-process emulation of the ROW-SHARDED finish: every "rank" merges the world rows it owns + their cells and
-    pushes the heights of its columns (phase 1, all ranks), runs the surface stage of its rows and pushes the maps
-    (phase 2), then delivers (phase 4)."""
-    import torch
-    from gvom_b200._lib import GVOM_HOST, GVOM_NO_DATA, RECORD_FLOATS, GvomRowsLinks, check
-    g0 = ranks[0]
-    L, V = g0._L, g0.voxel_count
-    dev = f"cuda:{g0.device}"
-    n = len(ranks)
-    org = (C.c_double * 3)()
-    origin = None
-    for g in ranks:
-        if L.gvom_newest_origin(g._h, org) != GVOM_NO_DATA and origin is None:
-            origin = [org[0], org[1], org[2]]
-    o = (C.c_double * 3)(*origin)
-    cap = int(min(V, g0.buffer_size * g0.max_points))
-    nb = C.c_uint64(0)
-    check(L.gvom_rows_block_size(g0._h, C.byref(nb)), "block size")
-    parr = lambda ps: (C.c_void_p * len(ps))(*[C.c_void_p(int(p)) for p in ps])
-    B = [dict(grid=torch.zeros(V, dtype=torch.int32, device=dev), msk=torch.zeros(V // 256 + 2, dtype=torch.int32, device=dev),
-              rec=torch.empty((cap, RECORD_FLOATS), dtype=torch.float32, device=dev), cnt=torch.zeros(1, dtype=torch.int32, device=dev),
-              hdr=torch.zeros(64 * 4, dtype=torch.int32, device=dev), fh=torch.zeros(64, dtype=torch.int32, device=dev),
-              fr=torch.zeros(64, dtype=torch.int32, device=dev), b2d=torch.zeros(nb.value, dtype=torch.uint8, device=dev)) for _ in ranks]
-    for r, g in enumerate(ranks):
-        hs = parr([b["hdr"].data_ptr() + 16 * r for b in B])
-        check(L.gvom_combine_partial_header(g._h, o, B[r]["grid"].data_ptr(), B[r]["msk"].data_ptr(), B[r]["rec"].data_ptr(), cap,
-                                            B[r]["cnt"].data_ptr(), hs, n, epoch, None), "partial")
-    torch.cuda.synchronize()
-    links = []
-    for r in range(n):
-        K = GvomRowsLinks()
-        K.rank, K.nranks, K.record_capacity = r, n, cap
-        for k, b in enumerate(B):
-            K.code_grids[k], K.group_masks[k], K.records[k] = b["grid"].data_ptr(), b["msk"].data_ptr(), b["rec"].data_ptr()
-            K.blocks2d[k] = b["b2d"].data_ptr()
-            K.heights_slots[k] = b["fh"].data_ptr() + 4 * r
-            K.results_slots[k] = b["fr"].data_ptr() + 4 * r
-        K.partial_headers, K.heights_flags, K.results_flags = B[r]["hdr"].data_ptr(), B[r]["fh"].data_ptr(), B[r]["fr"].data_ptr()
-        links.append(K)
-    outs = []
-    for phase in (1, 2, 4):
-        for r, g in enumerate(ranks):
-            pos, neg, rough, vis = g._out_arrays()
-            oo = (C.c_double * 3)()
-            check(L.gvom_combine_finish_rows(g._h, o, C.byref(links[r]), epoch, phase, oo, pos.ctypes.data, neg.ctypes.data,
-                                             rough.ctypes.data, vis.ctypes.data, GVOM_HOST, None), "rows")
-            torch.cuda.synchronize()
-            if phase == 4:
-                outs.append((np.array(list(oo)), pos, neg, rough, vis))
-    return outs, B
-
-
 def attach_mirrors(ranks):
     """Mirrored ring slots for handles living in one process: one block per "rank" in plain device memory."""
     import torch
@@ -220,7 +120,7 @@ def local_exchange_mirror(ranks, epoch, blocks=None):
     links = []
     for r in range(n):
         K = GvomRowsLinks()
-        K.rank, K.nranks, K.record_capacity = r, n, 0
+        K.rank, K.nranks = r, n
         for k, b in enumerate(B):
             K.blocks2d[k] = b["b2d"].data_ptr()
             K.heights_slots[k] = b["fh"].data_ptr() + 4 * r
@@ -281,37 +181,6 @@ def assemble_rows_state(ranks, outs, xy_res):
     return {"codes": codes, "ids": ids, "hit": hit, "total": tot, "minh": mnh, "metrics": met}
 
 
-@pytest.mark.parametrize("nranks", [1, 2, 3])
-def test_row_sharded_finish_equals_single(nranks):
-    """gvom_combine_partial_header + gvom_combine_finish_rows (the default multi-GPU combine): the maps every rank
-    delivers and the 3-D state assembled from the ranks' row shards equal one Gvom holding every rank's ring slots."""
-    from gvom_b200 import Gvom
-    Bs = 2
-    kw = dict(xy_size=256, z_size=16, robot_radius=2.0)
-    P1, PN = synth.params_tuple(buffer_size=Bs, **kw), synth.params_tuple(buffer_size=Bs * nranks, **kw)
-    fr = sensor_frames(nranks, 4, wall=30.0)
-    ranks = [Gvom(*P1) for _ in range(nranks)]
-    for step in range(4):
-        for r in range(nranks):
-            ranks[r].Process_pointcloud(*fr[step][r])
-        outs, _keep = local_exchange_rows(ranks, step + 1)
-        ref = Gvom(*PN)
-        for s2 in range(step + 1):
-            for q in range(max(0, s2 - Bs + 1), s2 + 1):
-                for r in range(nranks):
-                    ref.Process_pointcloud(*fr[q][r])
-            last = ref.combine_maps()
-        want = canon.canon_combine(ref.refview(), last)
-        for r in range(nranks):
-            for a, b, name in zip(outs[r], last, ("origin", "pos", "neg", "rough", "vis")):
-                ok = np.allclose(a, b, rtol=1e-4, atol=1e-9, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b)
-                assert ok, f"step {step} rank {r}: {name}"
-        got = assemble_rows_state(ranks, outs, P1[0])
-        for k in ("codes", "ids", "hit", "total", "minh"):
-            assert np.array_equal(got[k], want[k]), f"step {step}: {k}"
-        assert np.allclose(got["metrics"], want["metrics"], rtol=1e-4, atol=2e-6), f"step {step}: metrics"
-
-
 @pytest.mark.parametrize("nranks,late", [(1, 0), (2, 0), (3, 0), (3, 2)])
 def test_mirrored_rows_equals_single(nranks, late):
     """gvom_mirror_attach + gvom_combine_finish_rows (the default multi-GPU combine): every scan is pushed to the owners
@@ -358,8 +227,7 @@ def compare_state(a, b, what):
     assert np.allclose(a["metrics"], b["metrics"], rtol=1e-4, atol=2e-6), f"{what}: metrics"
 
 
-@pytest.mark.parametrize("nranks,reduced", [(1, False), (2, False), (3, False), (2, True), (1, "sharded"), (2, "sharded"),
-                                            (3, "sharded")])
+@pytest.mark.parametrize("nranks,reduced", [(1, False), (2, False), (3, False), (2, True)])
 def test_partial_finish_equals_single(nranks, reduced):
     from gvom_b200 import Gvom
     B = 2
@@ -370,7 +238,7 @@ def test_partial_finish_equals_single(nranks, reduced):
     for step in range(5):
         for r in range(nranks):
             ranks[r].Process_pointcloud(*fr[step][r])
-        outs = local_exchange_sharded(ranks, step + 1) if reduced == "sharded" else local_exchange(ranks, reduced)
+        outs = local_exchange(ranks, reduced)
         # One Gvom with B*nranks slots holding the same scans: replay the whole history from
         # scratch (it needs the same chain of "previous combined map" states), feeding before
         # every combine the scans the rank rings hold at that step, newest step last.
@@ -392,10 +260,10 @@ def test_nccl_two_ranks(tmp_path):
         pytest.skip("needs >= 2 GPUs")
     script = os.path.join(ROOT, "tests", "multi_rank_check.py")
     for port, exchange, extra in ((29533, "nccl", []), (29534, "p2p", []), (29535, "p2p", ["late"]),
-                                  (29536, "p2p", ["sharded"]), (29537, "p2p", ["grid256"])):
+                                  (29536, "p2p", ["grid256"]), (29537, "p2p", ["grid256", "late"])):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                             "--master-addr", "127.0.0.1", "--master-port", str(port), script, exchange] + extra,
-                           capture_output=True, text=True, timeout=600)
+                           capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         assert "MULTI_RANK_OK" in r.stdout, r.stdout[-2000:]
         print(r.stdout[-300:])
