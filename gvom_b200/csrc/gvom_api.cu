@@ -102,7 +102,7 @@ enum { EV_START = 0, EV_H2D, EV_POINTS, EV_SCELLS, EV_CSTART, EV_CODES, EV_CELLS
        EV_X0, EV_X1, EV_X2, EV_P0, EV_P1, EV_COUNT };   // EV_X*: extra marks inside the multi-GPU combine
 
 // GVOM_VARIANT bits (environment / gvom_set_variant): A/B switches for measurements; every setting gives the same results
-enum { VAR_GENERIC_MERGE = 2, VAR_ASYNC_ROWS = 4, VAR_NO_SRCMASK = 16, VAR_BULK_PUSH = 32, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128 };
+enum { VAR_GENERIC_MERGE = 2, VAR_ASYNC_ROWS = 4, VAR_NO_SRCMASK = 16, VAR_BULK_PUSH = 32, VAR_DMA_OUT = 64, VAR_NO_FASTFLOOR = 128, VAR_NO_BULK_H2D = 256 };
 
 }  // namespace
 
@@ -770,8 +770,9 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
         }
         if (mapped) {
             rec(h, EV_H2D, st);
+            const int zc = (h->variant & VAR_NO_BULK_H2D) ? 1 : 2;         // 2: a block's chunk is fetched by the TMA engine
             if (pinned) {
-                launch_s1(mapped, 0, n, 1);
+                launch_s1(mapped, 0, n, zc);
             } else {
                 // pageable: the staging copy (threaded, non-temporal) is pipelined with the kernel chunk by chunk
                 ensure_pool();
@@ -783,7 +784,7 @@ static int process_locked(GvomHandle* h, const CloudDesc& cd, const double ego[3
                     if (count <= 0) break;
                     h->pool->copy(h->stage_host + (size_t)first * row, static_cast<const char*>(points) + (size_t)first * row,
                                   (size_t)count * row);
-                    launch_s1(mapped, first, count, 1);
+                    launch_s1(mapped, first, count, zc);
                 }
                 h->last_stage_copy_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
             }

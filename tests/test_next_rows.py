@@ -280,10 +280,10 @@ def test_replay_driver_matches_the_unmodified_node():
             assert np.array_equal(out[topic], want[topic][i]), (i, topic)
 
 
-@pytest.mark.parametrize("mask", [2, 4, 64, 128, 194])
+@pytest.mark.parametrize("mask", [2, 4, 64, 128, 256, 450])
 def test_ab_switches_do_not_change_results(mask, monkeypatch):
     """The A/B switches kept for measurements (GVOM_VARIANT bits: generic merge kernel, bulk-copy pipeline build of the row
-    merge, DMA outputs, F2I floor in the DDA) stay parity-green."""
+    merge, DMA outputs, F2I floor in the DDA, per-thread loads instead of the bulk copy of host clouds) stay parity-green."""
     import replay
     monkeypatch.setenv("GVOM_VARIANT", str(mask))
     for name in ("small_moving", "os1_64"):
