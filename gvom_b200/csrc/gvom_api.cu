@@ -1720,7 +1720,10 @@ int gvom_mirror_attach(GvomHandle* h, int32_t rank, int32_t nranks, void* const*
     mirror_layout(h, nranks, &m);
     m.n = nranks; m.self = rank;
     for (int k = 0; k < nranks; ++k) m.base[k] = static_cast<char*>(blocks[k]);
-    // own block: flags, table, held masks and group masks clear; every mirror map "all unknown"
+    // own block: flags, table, held masks and group masks clear; every mirror map "all unknown".  The caller may have
+    // just filled the block on another stream (torch.zeros on the default stream does not order against this handle's
+    // non-blocking stream: found by a racecheck run, where the fill landed AFTER the memsets below): wait for the device
+    CUDA_TRY(cudaDeviceSynchronize());
     char* me = m.base[rank];
     CUDA_TRY(cudaMemsetAsync(me, 0, m.o_mirrors, h->stream));
     for (size_t q = 0; q < (size_t)nranks * h->p.buffer_size; ++q) {

@@ -90,7 +90,7 @@ def attach_mirrors(ranks):
     L, n = ranks[0]._L, len(ranks)
     nb = C.c_uint64(0)
     check(L.gvom_mirror_block_size(ranks[0]._h, n, C.byref(nb)), "mirror block size")
-    blocks = [torch.zeros(nb.value, dtype=torch.uint8, device=f"cuda:{ranks[0].device}") for _ in ranks]
+    blocks = [torch.empty(nb.value, dtype=torch.uint8, device=f"cuda:{ranks[0].device}") for _ in ranks]   # (attach initialises them)
     ptrs = (C.c_void_p * n)(*[C.c_void_p(b.data_ptr()) for b in blocks])
     for r, g in enumerate(ranks):
         check(L.gvom_mirror_attach(g._h, r, n, ptrs), "mirror attach")
