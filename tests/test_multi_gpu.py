@@ -181,12 +181,13 @@ def assemble_rows_state(ranks, outs, xy_res):
     return {"codes": codes, "ids": ids, "hit": hit, "total": tot, "minh": mnh, "metrics": met}
 
 
-@pytest.mark.parametrize("nranks,late", [(1, 0), (2, 0), (3, 0), (3, 2)])
+@pytest.mark.parametrize("nranks,late", [(1, 0), (2, 0), (3, 0), (3, 2), (4, 0), (5, 1)])
 def test_mirrored_rows_equals_single(nranks, late):
     """gvom_mirror_attach + gvom_combine_finish_rows (the default multi-GPU combine): every scan is pushed to the owners
     of its rows by Process_pointcloud; the maps every rank delivers and the 3-D state assembled from the ranks' row
     shards equal one Gvom holding every rank's ring slots.  The ego moves 1.25 rows per step, so rows change owner
-    between scans (wipes at the old owner).  late: the last rank only starts scanning at that step."""
+    between scans.  late: the last rank only starts scanning at that step.  From 4 ranks up (>= 8 ring slots) the row
+    merge hands source masks to the cell kernel, which then fetches the records of a cell four at a time."""
     from gvom_b200 import Gvom
     Bs = 2
     kw = dict(xy_size=256, z_size=16, robot_radius=2.0)
