@@ -5,7 +5,7 @@ set -x
 mkdir -p gpurun_out
 for c in os1_128 long_range dense; do
   full=""; [ $c = os1_128 ] && full=full
-  bash scripts/gpu_r02_ncu.sh r02_final_$c $c $full > /dev/null 2>&1
+  bash scripts/gpu_ncu.sh r02_final_$c $c $full > /dev/null 2>&1
   python scripts/ncu_counters.py gpurun_out/traffic_r02_final_$c.csv $c profiles/kernel_counters_r02.json > /dev/null
 done
 cp profiles/kernel_counters_r02.json gpurun_out/kernel_counters_r02.json

@@ -1,9 +1,9 @@
 #!/bin/bash
-# fused cells+heights kernel, 4-map deliver, wider push: parity + bench at N ranks
+# multi-GPU check at N ranks (gpurun --gpus N): in-process parity, torchrun parity incl. a late-joining rank (log kept), bench.py --gpus N
 N=${1:-2}
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_multi_gpu.py -x -q -k "mirrored or row_sharded" 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_multi_gpu.py -x -q -k "mirrored" 2>&1 | tail -3
 port=29740
 LOG=gpurun_out/multi_rank_check_r02_mirror_n$N.log
 : > $LOG

@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu evidence of the current build: launch list, single-pass counters, one --set full capture per kernel
-#   bash scripts/gpu_r02_ncu.sh TAG [config] [full]
+#   bash scripts/gpu_ncu.sh TAG [config] [full]
 set -x
 mkdir -p gpurun_out
 TAG=${1:-r02_a}
