@@ -1844,17 +1844,25 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
         }
         rec(h, EV_CODES, st);
         {
-            // cells of the own rows + heights of the own columns (pushed to every rank) + "heights" signal: one launch
+            // fork: the heights of the own columns (k_rows_heights, then the flag exchange + bit maps of phase 2) run on the
+            // side stream while the cell kernel runs here; joined before the surface stage (or at the end of this phase)
+            CUDA_TRY(cudaEventRecord(h->ev_chunk[0], st));
+            CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[0], 0));
+            launch(k_rows_heights, dim3(blocks_for((int64_t)S * R.nrows + 1, 256)), dim3(256), 0, h->copy_stream, Ad, (const int*)c.index_map,
+                   (const int*)h->col_minz, (const int*)(h->col_minz + S2), c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1],
+                   h->ego[2], h->dp, R, D, srcmask);
             int* host_count = nullptr;
             void* m = nullptr;
             if (cudaHostGetDevicePointer(&m, h->counters_host, 0) == cudaSuccess) host_count = (int*)m; else cudaGetLastError();
-            GridSignal G{};                                // (the "heights" flag is published by the next kernel, k_rows_known)
             launch(k_merge_cells2_rows, dim3(h->grid_cells2), dim3(128), 0, st, Ad, (const int*)(h->flags + 8), (const int*)c.cell_voxel, c.hit,
-                   c.total, c.minh, c.metrics, c.eig, h->dp, (int)h->ccap, (const int*)h->col_minz, (const int*)(h->col_minz + S2),
-                   c.origin[0], c.origin[1], c.origin[2], h->ego[0], h->ego[1], h->ego[2], R, D, c.counter, host_count, G, srcmask);
+                   c.total, c.minh, c.metrics, c.eig, h->dp, (int)h->ccap, c.counter, host_count, srcmask);
+            if (!(phases & 2)) {                           // phases run one by one (tests): join here
+                CUDA_TRY(cudaEventRecord(h->ev_chunk[1], h->copy_stream));
+                CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[1], 0));
+            }
         }
         rec(h, EV_CELLS, st);
-        h->stats.kernel_launches += 3;
+        h->stats.kernel_launches += 4;
         h->prof_combine = false;
         CUDA_TRY(cudaGetLastError());
     }
@@ -1865,8 +1873,15 @@ int gvom_combine_finish_rows(GvomHandle* h, const double origin[3], const GvomRo
     if (mirrored && (phases & 128)) { launch(k_signal, dim3(1), dim3(32), 0, st, flag_set(K->results_slots), (int)epoch); h->stats.kernel_launches++; }
     const bool publish = mirrored && !(phases & 256);
     if (phases & 2) {
-        launch(k_rows_known, dim3(W, W), dim3(1024), 0, st, (const double*)maps, h->dp, known, knownT, K->heights_flags, N, (int)epoch,
+        // (all phases in one call: the bit maps follow the heights on the side stream, beside the cell kernel)
+        const bool beside = mirrored && (phases & 1);
+        cudaStream_t ks = beside ? h->copy_stream : st;
+        launch(k_rows_known, dim3(W, W), dim3(1024), 0, ks, (const double*)maps, h->dp, known, knownT, K->heights_flags, N, (int)epoch,
                publish ? flag_set(K->heights_slots) : SignalSet{});
+        if (beside) {
+            CUDA_TRY(cudaEventRecord(h->ev_chunk[1], h->copy_stream));
+            CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[1], 0));
+        }
         const size_t mask_bytes = 2 * (size_t)S * W * sizeof(unsigned);
         const int in_smem = (mask_bytes <= 40 * 1024 && (mask_bytes % 16) == 0) ? 1 : 0;
         GridSignal G{};

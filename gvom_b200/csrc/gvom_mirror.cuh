@@ -307,64 +307,82 @@ k_merge_rows_ind(const MergeArgs* __restrict__ A, MergeOut O, DevParams P) {
 }
 
 // ---------------------------------------------------------------------------
-// C2 + C3 of the mirrored combine in one launch: the cells of this rank's rows (source list in device memory, see
-// k_merge_rows_ind) and the heights of its columns, pushed into every rank's 2-D block ([y][x]).
-//   * a column with an occupied voxel: height = (z + min height + origin_z) * z_res of its LOWEST occupied cell
-//     (__make_height_map, gvom.py:560-580) -- stored by the thread that has just merged that cell (z == the column
-//     minimum the row merge left), so the column pass needs no look-up of the cell
-//   * every column: inferred height from the lowest free voxel (gvom.py:582-590); columns without an occupied voxel
-//     get the ego-disc height or -1000 -- one thread per column, disjoint from the cell writers
-// then the "heights pushed" signal (last block).  Also publishes the rank's cell count.
+// C2 and C3 of the mirrored combine run SIDE BY SIDE on two streams after the row merge:
+//   k_merge_cells2_rows (main stream)  the cells of this rank's rows (source list in device memory, see k_merge_rows_ind);
+//                                      publishes the rank's cell count
+//   k_rows_heights      (side stream)  the heights of this rank's columns, pushed into every rank's 2-D block ([y][x]),
+//                                      followed on the same stream by k_rows_known (flag exchange + bit maps).
+// The height of a column needs only the MIN HEIGHT of its lowest occupied cell (__make_height_map, gvom.py:560-580):
+// the minimum over the sources that are occupied at that one voxel -- a few look-ups per column instead of waiting for
+// the whole cell merge (20-36 us), so the first 2-D exchange overlaps the cell kernel.  Inferred heights from the lowest
+// free voxel (gvom.py:582-590); columns without an occupied voxel get the ego-disc height or -1000.
 // ---------------------------------------------------------------------------
-struct HeightPush {
-    const int* col_occ; const int* col_free;
-    const PushSet& D;                // the kernel's __grid_constant__ parameter (indexed in the constant bank)
-    long long S2;
-    int S, Z;
-    double o2, z_res;
-    __device__ __forceinline__ void operator()(int x, int y, int z, float mh) const {
-        const long long ci = (long long)y * S + x;
-        if (z != col_occ[ci]) return;
-        const double h = __dmul_rn(__dadd_rn(__dadd_rn((double)z, (double)mh), o2), z_res);
-        for (int d = 0; d < D.n; ++d) reinterpret_cast<double*>(D.base[d] + D.off_maps)[ci] = h;
-    }
-};
-
 __global__ void __launch_bounds__(128, 8)
 k_merge_cells2_rows(const MergeArgs* __restrict__ A, const int* __restrict__ counter, const int* __restrict__ cell_voxel,
                     int* __restrict__ chit, int* __restrict__ ctot, float* __restrict__ cminh,
                     float* __restrict__ cmet, float* __restrict__ ceig, DevParams P, int cap,
-                    const int* __restrict__ col_occ, const int* __restrict__ col_free, double o0, double o1, double o2,
-                    double e0, double e1, double e2, RowShard R, const __grid_constant__ PushSet D, int* __restrict__ map_count,
-                    int* __restrict__ host_count, GridSignal G, const unsigned* __restrict__ srcmask) {
+                    int* __restrict__ map_count, int* __restrict__ host_count, const unsigned* __restrict__ srcmask) {
     pdl_wait();
-    const int S = P.S;
-    const long long S2 = (long long)S * S;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const int n = *counter;
         *map_count = n;
         if (host_count) *host_count = n;
     }
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < S * R.nrows; t += gridDim.x * blockDim.x) {
-        const int x = t % S, y = R.y0 + R.n * (t / S);    // x fastest: the column minima and the exchange block are [y][x]
-        const long long ci = (long long)y * S + x;
-        const int zo = col_occ[ci], zf = col_free[ci];
-        const double inf = zf < P.Z ? __dmul_rn(__dadd_rn(o2, (double)zf), P.z_res) : -1000.0;
-        double h = -1000.0;
-        if (zo >= P.Z) {
-            const double xp = __fma_rn(__dadd_rn(o0, (double)x), P.xy_res, -e0);
-            const double yp = __fma_rn(__dadd_rn(o1, (double)y), P.xy_res, -e1);
-            if (__fma_rn(xp, xp, __dmul_rn(yp, yp)) <= P.r2) h = __dsub_rn(e2, P.ground_to_lidar);
+    merge_cells2_body(*A, counter, cell_voxel, chit, ctot, cminh, cmet, ceig, P, cap, NoCellHook{}, srcmask);
+}
+
+__global__ void __launch_bounds__(256)
+k_rows_heights(const MergeArgs* __restrict__ Ap, const int* __restrict__ cmap, const int* __restrict__ col_occ,
+               const int* __restrict__ col_free, double o0, double o1, double o2, double e0, double e1, double e2,
+               DevParams P, RowShard R, const __grid_constant__ PushSet D, const unsigned* __restrict__ srcmask) {
+    pdl_wait();
+    const MergeArgs& A = *Ap;
+    const int S = P.S, Z = P.Z;
+    const long long S2 = (long long)S * S;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * R.nrows) return;
+    const int x = t % S, y = R.y0 + R.n * (t / S);        // x fastest: the column minima and the exchange block are [y][x]
+    const long long ci = (long long)y * S + x;
+    const int zo = col_occ[ci], zf = col_free[ci];
+    const double inf = zf < Z ? __dmul_rn(__dadd_rn(o2, (double)zf), P.z_res) : -1000.0;
+    double h = -1000.0;
+    if (zo < Z) {
+        // min height of the column's lowest occupied cell: the minimum over the sources occupied at that voxel -- the
+        // same min the cell kernel takes for this cell (order independent, exact)
+        unsigned want = 0xffffffffu;
+        if (srcmask) {
+            const int id = cmap[x + (long long)y * S + zo * S2];
+            want = id >= 0 ? srcmask[id] : 0u;
         }
-        for (int d = 0; d < D.n; ++d) {                    // own copy included
-            double* m = reinterpret_cast<double*>(D.base[d] + D.off_maps);
-            if (zo >= P.Z) m[ci] = h;
-            m[S2 + ci] = inf;
+        float mh = 1.0f;
+        constexpr int RB = 8;
+        for (int k0 = 0; k0 < A.n; k0 += RB) {
+            int io[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                io[u] = -1;
+                if (k0 + u < A.n && (!srcmask || A.s[k0 + u].is_prev || ((want >> ((k0 + u) & 31)) & 1u))) {
+                    const SlotRef& s = A.s[k0 + u];
+                    const int xs = x + s.dx, ys = y + s.dy, zs = zo + s.dz;
+                    if ((unsigned)xs < (unsigned)S && (unsigned)ys < (unsigned)S && (unsigned)zs < (unsigned)Z)
+                        io[u] = __ldg(s.map + (xs + (ys + zs * S) * S));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RB; ++u)
+                if (io[u] >= 0) mh = fminf(mh, A.s[k0 + u].minh[io[u]]);
         }
+        h = __dmul_rn(__dadd_rn(__dadd_rn((double)zo, (double)mh), o2), P.z_res);
+    } else {
+        const double xp = __fma_rn(__dadd_rn(o0, (double)x), P.xy_res, -e0);
+        const double yp = __fma_rn(__dadd_rn(o1, (double)y), P.xy_res, -e1);
+        if (__fma_rn(xp, xp, __dmul_rn(yp, yp)) <= P.r2) h = __dsub_rn(e2, P.ground_to_lidar);
     }
-    HeightPush hook{col_occ, col_free, D, S2, S, P.Z, o2, P.z_res};
-    merge_cells2_body(*A, counter, cell_voxel, chit, ctot, cminh, cmet, ceig, P, cap, hook, srcmask);
-    signal_when_grid_done(G);                             // heights of this rank's columns are in every rank's block
+    for (int d = 0; d < D.n; ++d) {                        // own copy included
+        double* m = reinterpret_cast<double*>(D.base[d] + D.off_maps);
+        m[ci] = h;
+        m[S2 + ci] = inf;
+    }
 }
 
 }  // namespace gvom
