@@ -14,7 +14,9 @@
 //                 slot table the pushes carried (slot origins are only known to the rank that made the scan) --
 //                 no host round trip, no collective.
 //   then the single-GPU merge kernels run over the own rows with the mirrors as sources (k_merge_rows_ind,
-//   k_merge_cells2_ind): local memory only.  Only 2-D maps cross the links afterwards (heights, finished maps).
+//   k_merge_cells2_rows): local memory only.  Beside the cell kernel, on a second stream, k_rows_heights pushes the
+//   heights of the own columns and k_rows_known exchanges the "heights" flags and builds the bit maps; after the join
+//   the surface stage of the own rows pushes the finished maps.  Only 2-D maps cross the links at combine time.
 //
 // The rows a rank owns in a mirror are exact: the pusher remembers per (destination rank, 256-voxel segment) which
 // group-mask word it last delivered ("held"), overwrites whole segments, and wipes a segment at the owner when the
